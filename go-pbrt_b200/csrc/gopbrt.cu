@@ -1,0 +1,710 @@
+// gopbrt.cu — C ABI of libgopbrt_cuda.so (include/gopbrt_cuda.h): scene upload, batched Intersect/IntersectP,
+// and the wavefront render loop.  sm_100a only; there is no CPU fallback — every entry point needs a live B200.
+//
+// build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false -Xcompiler -fPIC,-ffp-contract=off -shared
+#include <atomic>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/gopbrt_cuda.h"
+#include "gp_bvh.h"
+#include "gp_render.cuh"
+
+using namespace gp;
+
+// the ctypes / cgo views of these structs are checked against the same numbers (tests/test_abi.py)
+static_assert(sizeof(gopbrt_transform) == 256 && sizeof(gopbrt_sphere) == 40 && sizeof(gopbrt_disk) == 40, "ABI layout");
+static_assert(sizeof(gopbrt_triangle) == 16 && sizeof(gopbrt_primitive) == 16 && sizeof(gopbrt_material) == 48, "ABI layout");
+static_assert(sizeof(gopbrt_texture) == 136 && sizeof(gopbrt_light) == 64 && sizeof(gopbrt_camera) == 288, "ABI layout");
+static_assert(sizeof(gopbrt_sampler) == 24 && sizeof(gopbrt_integrator) == 32 && sizeof(gopbrt_film) == 56, "ABI layout");
+static_assert(sizeof(gopbrt_render_options) == 16 && sizeof(gopbrt_stats) == 192 && sizeof(gopbrt_scene_desc) == 152, "ABI layout");
+
+struct gopbrt_ctx {
+  int device = 0;
+  int sm_count = 148;
+  cudaStream_t stream = nullptr;
+  std::string last_error;
+  std::atomic<uint64_t> launches{0};
+  std::mutex mu;
+};
+
+#define GP_CUDA(ctx, call)                                                                               \
+  do {                                                                                                   \
+    cudaError_t e__ = (call);                                                                            \
+    if (e__ != cudaSuccess) {                                                                            \
+      (ctx)->last_error = std::string(#call) + ": " + cudaGetErrorString(e__);                           \
+      return GOPBRT_ERR_CUDA;                                                                            \
+    }                                                                                                    \
+  } while (0)
+
+template <class T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  cudaError_t alloc(size_t count) {
+    release();
+    n = count;
+    if (count == 0) return cudaSuccess;
+    return cudaMalloc((void**)&p, count * sizeof(T));
+  }
+  cudaError_t upload(const std::vector<T>& v, cudaStream_t s) {
+    cudaError_t e = alloc(v.size());
+    if (e != cudaSuccess || v.empty()) return e;
+    return cudaMemcpyAsync(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, s);
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+  ~DevBuf() { release(); }
+};
+
+struct Workspace {  // per-scene render workspace, kept between gopbrt_render calls of the same shape
+  long long lanes = 0;
+  size_t bytes_tables = 0, bytes_tilepix = 0;
+  DevBuf<double> f64;     // all double planes
+  DevBuf<int> i32;        // int planes + queues
+  DevBuf<unsigned long long> u64;
+  DevBuf<unsigned char> u8;
+  DevBuf<double> tables, tilepix;
+  DevBuf<int> cnt;
+  DevBuf<RenderCounters> rctr;
+  int* remaining_host = nullptr;  // pinned, device-mapped
+  int* remaining_dev = nullptr;
+  ~Workspace() { if (remaining_host) cudaFreeHost(remaining_host); }
+};
+
+struct gopbrt_scene {
+  gopbrt_ctx* ctx = nullptr;
+  DevScene dev{};
+  DevBuf<gpbvh::Node32> nodes;
+  DevBuf<PrimRec> recs;
+  DevBuf<double> rec_bounds;
+  DevBuf<int4> prims;
+  DevBuf<double> xf;
+  DevBuf<int> xf_flags;
+  DevBuf<SphereDev> spheres;
+  DevBuf<DiskDev> disks;
+  DevBuf<MaterialDev> materials;
+  DevBuf<TextureDev> textures;
+  DevBuf<LightDev> lights;
+  DevBuf<double> light_cdf;
+  DevBuf<TraceCounters> tctr;
+  double world[6] = {0, 0, 0, 0, 0, 0};
+  uint64_t bvh_nodes = 0, bvh_depth = 0;
+  std::atomic<int> cancel{0};
+  Workspace ws;
+  std::mutex mu;
+};
+
+static int grid_for(gopbrt_ctx* ctx, const void* kernel, int block, size_t smem = 0) {
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+  return ctx->sm_count * per_sm;  // persistent grid: a whole number of resident CTAs per SM
+}
+
+extern "C" {
+
+int gopbrt_abi_version(void) { return GOPBRT_ABI_VERSION; }
+
+int gopbrt_init(int device, gopbrt_ctx** out) {
+  if (!out) return GOPBRT_ERR_INVALID;
+  *out = nullptr;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || device < 0 || device >= n) return GOPBRT_ERR_CUDA;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return GOPBRT_ERR_CUDA;
+  if (prop.major != 10) return GOPBRT_ERR_CUDA;  // sm_100a cubin only: no fallback
+  if (cudaSetDevice(device) != cudaSuccess) return GOPBRT_ERR_CUDA;
+  gopbrt_ctx* c = new gopbrt_ctx();
+  c->device = device;
+  c->sm_count = prop.multiProcessorCount;
+  if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return GOPBRT_ERR_CUDA; }
+  *out = c;
+  return GOPBRT_OK;
+}
+
+void gopbrt_shutdown(gopbrt_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+const char* gopbrt_last_error(const gopbrt_ctx* c) { return c ? c->last_error.c_str() : "null ctx"; }
+uint64_t gopbrt_launch_count(const gopbrt_ctx* c) { return c ? c->launches.load() : 0; }
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------ scene build (host)
+static M4 m4_from(const double* a) {
+  M4 m;
+  for (int i = 0; i < 4; i++) for (int j = 0; j < 4; j++) m.m[i][j] = a[i * 4 + j];
+  return m;
+}
+static bool is_translation_only(const double* a) {
+  for (int i = 0; i < 4; i++) for (int j = 0; j < 4; j++) {
+    if (j == 3 && i < 3) continue;
+    if (a[i * 4 + j] != (i == j ? 1.0 : 0.0)) return false;
+  }
+  return true;
+}
+static bool is_identity(const double* a) {
+  for (int i = 0; i < 4; i++) for (int j = 0; j < 4; j++) if (a[i * 4 + j] != (i == j ? 1.0 : 0.0)) return false;
+  return true;
+}
+
+// Bounds3 with the reference's Union/UnionPoint semantics (bounds.go:209-238: Go Min/Max)
+struct HB { double mn[3], mx[3]; bool valid = false; };
+static void hb_union_point(HB& b, V3 p) {
+  double v[3] = {p.x, p.y, p.z};
+  if (!b.valid) { for (int k = 0; k < 3; k++) { b.mn[k] = v[k]; b.mx[k] = v[k]; } b.valid = true; }
+  for (int k = 0; k < 3; k++) { b.mn[k] = go_min(b.mn[k], v[k]); b.mx[k] = go_max(b.mx[k], v[k]); }
+}
+static void hb_union(HB& b, const HB& o) {
+  if (!o.valid) return;
+  if (!b.valid) b = o;
+  for (int k = 0; k < 3; k++) { b.mn[k] = go_min(b.mn[k], o.mn[k]); b.mx[k] = go_max(b.mx[k], o.mx[k]); }
+}
+// Transform.TransformBounds (transform.go:336-345)
+static HB xf_bounds(const M4& m, const HB& b) {
+  HB r;
+  hb_union_point(r, xf_point(m, mk3(b.mn[0], b.mn[1], b.mn[2]), mk3(0, 0, 0), nullptr));
+  for (int i = 1; i < 8; i++) {
+    V3 c = mk3((i & 1) ? b.mx[0] : b.mn[0], (i & 2) ? b.mx[1] : b.mn[1], (i & 4) ? b.mx[2] : b.mn[2]);  // bounds.go:114-120
+    hb_union_point(r, xf_point(m, c, mk3(0, 0, 0), nullptr));
+  }
+  return r;
+}
+
+extern "C" int gopbrt_scene_create(gopbrt_ctx* ctx, const gopbrt_scene_desc* d, gopbrt_scene** out) {
+  if (!ctx || !d || !out) return GOPBRT_ERR_INVALID;
+  *out = nullptr;
+  std::lock_guard<std::mutex> g(ctx->mu);
+  GP_CUDA(ctx, cudaSetDevice(ctx->device));
+  auto bad = [&](const char* msg) { ctx->last_error = msg; return GOPBRT_ERR_INVALID; };
+  if (d->n_primitives < 0 || d->n_primitives > 0x7fffffff) return bad("n_primitives out of range");
+
+  // ---- transforms
+  std::vector<double> xf(32 * (size_t)d->n_transforms);
+  std::vector<int> xf_flags(d->n_transforms, 0);
+  for (int i = 0; i < d->n_transforms; i++) {
+    memcpy(&xf[32 * (size_t)i], d->transforms[i].m, 16 * sizeof(double));
+    memcpy(&xf[32 * (size_t)i + 16], d->transforms[i].minv, 16 * sizeof(double));
+    if (is_translation_only(d->transforms[i].m) && is_translation_only(d->transforms[i].minv)) xf_flags[i] |= XF_TRANSLATION;
+    if (is_identity(d->transforms[i].m)) xf_flags[i] |= XF_IDENTITY;  // Transform.IsIdentity looks at Matrix only (transform.go:167-173)
+  }
+  auto xf_ok = [&](int i) { return i >= 0 && i < d->n_transforms; };
+
+  // ---- shapes (NewSphere sphere.go:19-32, NewDisk disk.go:22-35)
+  std::vector<SphereDev> spheres(d->n_spheres);
+  for (int i = 0; i < d->n_spheres; i++) {
+    const gopbrt_sphere& s = d->spheres[i];
+    if (!xf_ok(s.object_to_world)) return bad("sphere transform index out of range");
+    SphereDev o;
+    o.radius = s.radius;
+    o.zMin = go_clamp(go_min(s.z_min, s.z_max), -s.radius, s.radius);
+    o.zMax = go_clamp(go_max(s.z_min, s.z_max), -s.radius, s.radius);
+    o.thetaMin = go_acos(go_clamp(go_min(s.z_min, s.z_max) / s.radius, -1, 1));
+    o.thetaMax = go_acos(go_clamp(go_max(s.z_min, s.z_max) / s.radius, -1, 1));
+    o.phiMax = kPi / 180.0 * go_clamp(s.phi_max_deg, 0, 360);
+    o.xf = s.object_to_world;
+    o.flags = (s.reverse_orientation ? RF_REVERSE : 0);
+    if (!(o.zMin > -o.radius) && !(o.zMax < o.radius) && o.phiMax >= 2 * kPi) o.flags |= RF_FULL;
+    spheres[i] = o;
+  }
+  std::vector<DiskDev> disks(d->n_disks);
+  for (int i = 0; i < d->n_disks; i++) {
+    const gopbrt_disk& s = d->disks[i];
+    if (!xf_ok(s.object_to_world)) return bad("disk transform index out of range");
+    DiskDev o;
+    o.height = s.height; o.radius = s.radius; o.innerRadius = s.inner_radius;
+    o.phiMax = kPi / 180.0 * go_clamp(s.phi_max_deg, 0, 360);
+    o.xf = s.object_to_world;
+    o.flags = (s.reverse_orientation ? RF_REVERSE : 0);
+    disks[i] = o;
+  }
+
+  // ---- primitives: world bounds (Primitive.WorldBound) in the reference's arithmetic
+  int64_t np = d->n_primitives;
+  std::vector<int4> prims(np);
+  std::vector<gpbvh::Box> pb(np);
+  HB world;
+  for (int64_t i = 0; i < np; i++) {
+    const gopbrt_primitive& p = d->primitives[i];
+    prims[i] = make_int4(p.shape_kind, p.shape_index, p.material, p.prim_to_world);
+    if (p.material >= d->n_materials) return bad("material index out of range");
+    if (p.prim_to_world >= d->n_transforms) return bad("prim_to_world index out of range");
+    HB b;
+    if (p.shape_kind == GOPBRT_SHAPE_SPHERE) {
+      if (p.shape_index < 0 || p.shape_index >= d->n_spheres) return bad("sphere index out of range");
+      const SphereDev& s = spheres[p.shape_index];
+      HB ob; ob.valid = true;
+      ob.mn[0] = -s.radius; ob.mn[1] = -s.radius; ob.mn[2] = s.zMin; ob.mx[0] = s.radius; ob.mx[1] = s.radius; ob.mx[2] = s.zMax;  // sphere.go:46-51
+      b = xf_bounds(m4_from(&xf[32 * (size_t)s.xf]), ob);
+    } else if (p.shape_kind == GOPBRT_SHAPE_DISK) {
+      if (p.shape_index < 0 || p.shape_index >= d->n_disks) return bad("disk index out of range");
+      const DiskDev& s = disks[p.shape_index];
+      HB ob; ob.valid = true;
+      ob.mn[0] = -s.radius; ob.mn[1] = -s.radius; ob.mn[2] = s.height; ob.mx[0] = s.radius; ob.mx[1] = s.radius; ob.mx[2] = s.height;  // disk.go:41-54
+      b = xf_bounds(m4_from(&xf[32 * (size_t)s.xf]), ob);
+    } else if (p.shape_kind == GOPBRT_SHAPE_TRIANGLE) {
+      if (p.shape_index < 0 || p.shape_index >= d->n_triangles) return bad("triangle index out of range");
+      const gopbrt_triangle& t = d->triangles[p.shape_index];
+      for (int k = 0; k < 3; k++) {
+        if (t.v[k] < 0 || t.v[k] >= d->n_vertices) return bad("vertex index out of range");
+        hb_union_point(b, mk3(d->vertices[3 * (size_t)t.v[k]], d->vertices[3 * (size_t)t.v[k] + 1], d->vertices[3 * (size_t)t.v[k] + 2]));
+      }
+      if (p.prim_to_world >= 0) return bad("TransformedPrimitive around a triangle is not supported");
+    } else {
+      return bad("unknown shape kind");
+    }
+    if (p.prim_to_world >= 0) b = xf_bounds(m4_from(&xf[32 * (size_t)p.prim_to_world]), b);  // primitive.go:127-129
+    for (int k = 0; k < 3; k++) { pb[i].mn[k] = b.mn[k]; pb[i].mx[k] = b.mx[k]; }
+    hb_union(world, b);
+  }
+
+  // ---- BVH
+  int max_prims = d->max_prims_in_node > 0 ? std::min(255, d->max_prims_in_node) : 4;
+  gpbvh::Result bvh = gpbvh::build_bvh(pb.data(), np, max_prims);
+  if (bvh.depth >= kStackDepth - 1) return bad("BVH deeper than the traversal stack");
+
+  // ---- leaf-ordered primitive records + their float64 bounds
+  std::vector<PrimRec> recs(np);
+  std::vector<double> rec_bounds(6 * (size_t)np);
+  for (int64_t r = 0; r < np; r++) {
+    uint32_t pi = bvh.order[r];
+    const gopbrt_primitive& p = d->primitives[pi];
+    PrimRec rec;
+    memset(&rec, 0, sizeof(rec));
+    rec.prim = pi;
+    rec.flags = (uint32_t)p.shape_kind;
+    if (p.shape_kind == GOPBRT_SHAPE_TRIANGLE) {
+      const gopbrt_triangle& t = d->triangles[p.shape_index];
+      for (int k = 0; k < 3; k++) for (int c = 0; c < 3; c++) rec.d[3 * k + c] = d->vertices[3 * (size_t)t.v[k] + c];
+      rec.flags |= RF_FAST | (t.reverse_orientation ? RF_REVERSE : 0);
+    } else if (p.shape_kind == GOPBRT_SHAPE_SPHERE) {
+      const SphereDev& s = spheres[p.shape_index];
+      rec.flags |= (uint32_t)(s.flags & (RF_REVERSE | RF_FULL));
+      bool fast = (s.flags & RF_FULL) && (xf_flags[s.xf] & XF_TRANSLATION) && (p.prim_to_world < 0 || (xf_flags[p.prim_to_world] & XF_TRANSLATION));
+      if (fast) {
+        rec.flags |= RF_FAST;
+        rec.d[0] = s.radius;
+        const double* inv = &xf[32 * (size_t)s.xf + 16];  // worldToObject.Matrix = objectToWorld.MatrixInverse
+        rec.d[1] = inv[3]; rec.d[2] = inv[7]; rec.d[3] = inv[11];
+        if (p.prim_to_world >= 0) {
+          const double* pinv = &xf[32 * (size_t)p.prim_to_world + 16];
+          rec.d[4] = pinv[3]; rec.d[5] = pinv[7]; rec.d[6] = pinv[11];
+          rec.flags |= RF_HAS_P2W;
+        }
+      }
+    } else {
+      rec.flags |= (uint32_t)(disks[p.shape_index].flags & RF_REVERSE);
+    }
+    recs[r] = rec;
+    for (int k = 0; k < 3; k++) { rec_bounds[6 * (size_t)r + k] = pb[pi].mn[k]; rec_bounds[6 * (size_t)r + 3 + k] = pb[pi].mx[k]; }
+  }
+
+  // ---- materials / textures / lights
+  std::vector<MaterialDev> mats(d->n_materials);
+  for (int i = 0; i < d->n_materials; i++) {
+    const gopbrt_material& m = d->materials[i];
+    if (m.tex_a >= d->n_textures || m.tex_b >= d->n_textures) return bad("texture index out of range");
+    if (m.kind < 0 || m.kind > 2 || m.tex_a < 0 || (m.kind == 2 && m.tex_b < 0)) return bad("bad material");
+    mats[i] = MaterialDev{m.kind, m.tex_a, m.tex_b, 0, m.sigma, m.eta, m.u_rough, m.v_rough};
+  }
+  std::vector<TextureDev> texs(d->n_textures);
+  for (int i = 0; i < d->n_textures; i++) {
+    const gopbrt_texture& t = d->textures[i];
+    TextureDev o;
+    o.kind = t.kind; o.mapping = t.mapping; o.tex1 = t.tex1; o.tex2 = t.tex2;
+    if (t.kind == GOPBRT_TEX_CHECKERBOARD && (t.tex1 < 0 || t.tex1 >= d->n_textures || t.tex2 < 0 || t.tex2 >= d->n_textures)) return bad("bad checkerboard children");
+    for (int k = 0; k < 3; k++) { o.rgb[k] = t.rgb[k]; o.vs[k] = t.vs[k]; o.vt[k] = t.vt[k]; }
+    o.ds = t.ds; o.dt = t.dt; o.su = t.su; o.sv = t.sv; o.du = t.du; o.dv = t.dv;
+    texs[i] = o;
+  }
+  std::vector<LightDev> lights(d->n_lights);
+  for (int i = 0; i < d->n_lights; i++) {
+    const gopbrt_light& l = d->lights[i];
+    LightDev o;
+    o.kind = l.kind; o.shape_kind = l.shape_kind; o.shape_index = l.shape_index; o.two_sided = l.two_sided;
+    for (int k = 0; k < 3; k++) { o.rgb[k] = l.rgb[k]; o.v[k] = l.v[k]; }
+    if (l.kind == GOPBRT_LIGHT_DIFFUSE_AREA) {
+      if (l.shape_kind == GOPBRT_SHAPE_SPHERE) { if (l.shape_index < 0 || l.shape_index >= d->n_spheres) return bad("light shape index"); }
+      else if (l.shape_kind == GOPBRT_SHAPE_DISK) { if (l.shape_index < 0 || l.shape_index >= d->n_disks) return bad("light shape index"); }
+      else return bad("area light shape must be a sphere or a disk");
+    }
+    lights[i] = o;
+  }
+  // NewUniformLightDistribution + NewDistribution1D (lightdistribution.go:25-34, sampling.go:11-40)
+  int nl = d->n_lights;
+  std::vector<double> cdf(nl + 1, 0.0);
+  for (int i = 1; i < nl + 1; i++) cdf[i] = cdf[i - 1] + 1.0 / (double)nl;
+  double func_int = nl ? cdf[nl] : 0.0;
+  if (func_int == 0.0) { for (int i = 1; i < nl + 1; i++) cdf[i] = (double)i / (double)nl; }
+  else { for (int i = 1; i < nl + 1; i++) cdf[i] /= func_int; }
+
+  gopbrt_scene* sc = new gopbrt_scene();
+  sc->ctx = ctx;
+  cudaStream_t st = ctx->stream;
+  std::vector<gpbvh::Node32>& nodes = bvh.nodes;
+  bool ok = sc->nodes.upload(nodes, st) == cudaSuccess && sc->recs.upload(recs, st) == cudaSuccess &&
+            sc->rec_bounds.upload(rec_bounds, st) == cudaSuccess && sc->prims.upload(prims, st) == cudaSuccess &&
+            sc->xf.upload(xf, st) == cudaSuccess && sc->xf_flags.upload(xf_flags, st) == cudaSuccess &&
+            sc->spheres.upload(spheres, st) == cudaSuccess && sc->disks.upload(disks, st) == cudaSuccess &&
+            sc->materials.upload(mats, st) == cudaSuccess && sc->textures.upload(texs, st) == cudaSuccess &&
+            sc->lights.upload(lights, st) == cudaSuccess && sc->light_cdf.upload(cdf, st) == cudaSuccess &&
+            sc->tctr.alloc(1) == cudaSuccess && cudaMemsetAsync(sc->tctr.p, 0, sizeof(TraceCounters), st) == cudaSuccess &&
+            cudaStreamSynchronize(st) == cudaSuccess;
+  if (!ok) {
+    ctx->last_error = std::string("scene upload: ") + cudaGetErrorString(cudaGetLastError());
+    delete sc;
+    return GOPBRT_ERR_CUDA;
+  }
+  DevScene& D = sc->dev;
+  D.nodes = (const float4*)sc->nodes.p; D.recs = sc->recs.p; D.rec_bounds = sc->rec_bounds.p; D.prims = sc->prims.p;
+  D.xf = sc->xf.p; D.xf_flags = sc->xf_flags.p; D.spheres = sc->spheres.p; D.disks = sc->disks.p;
+  D.materials = sc->materials.p; D.textures = sc->textures.p; D.lights = sc->lights.p; D.light_cdf = sc->light_cdf.p;
+  D.n_lights = nl; D.light_func_int = func_int; D.n_nodes = (int)nodes.size();
+  // Distant.Preprocess → Bounds3.BoundingSphere (distant.go:36-38, bounds.go:105-112)
+  D.world_radius = 0;
+  if (world.valid) {
+    V3 c = (mk3(world.mn[0], world.mn[1], world.mn[2]) + mk3(world.mx[0], world.mx[1], world.mx[2])) / 2.0;
+    bool inside = c.x >= world.mn[0] && c.x <= world.mx[0] && c.y >= world.mn[1] && c.y <= world.mx[1] && c.z >= world.mn[2] && c.z <= world.mx[2];
+    if (inside) D.world_radius = sqrt(dist2(c, mk3(world.mx[0], world.mx[1], world.mx[2])));
+    for (int k = 0; k < 3; k++) { sc->world[k] = world.mn[k]; sc->world[3 + k] = world.mx[k]; }
+  }
+  sc->bvh_nodes = nodes.size();
+  sc->bvh_depth = (uint64_t)bvh.depth;
+  *out = sc;
+  return GOPBRT_OK;
+}
+
+extern "C" void gopbrt_scene_destroy(gopbrt_scene* sc) {
+  if (!sc) return;
+  cudaSetDevice(sc->ctx->device);
+  cudaStreamSynchronize(sc->ctx->stream);
+  delete sc;
+}
+
+extern "C" int gopbrt_scene_world_bound(const gopbrt_scene* sc, double out6[6]) {
+  if (!sc || !out6) return GOPBRT_ERR_INVALID;
+  memcpy(out6, sc->world, sizeof(sc->world));
+  return GOPBRT_OK;
+}
+
+extern "C" int gopbrt_cancel(gopbrt_scene* sc) {
+  if (!sc) return GOPBRT_ERR_INVALID;
+  sc->cancel.store(1);
+  return GOPBRT_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ batched trace API
+static RaySoA soa7(double* base, long long n) {
+  RaySoA r;
+  r.ox = base; r.oy = base + n; r.oz = base + 2 * n; r.dx = base + 3 * n; r.dy = base + 4 * n; r.dz = base + 5 * n; r.tmax = base + 6 * n;
+  return r;
+}
+
+__global__ void k_rec_to_prim(DevScene sc, int* __restrict__ rec, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    int r = rec[i];
+    rec[i] = r >= 0 ? (int)sc.recs[r].prim : -1;
+  }
+}
+
+// closest hit over device-resident rays; prim_rec receives LEAF-RECORD indices (internal form)
+static int trace_closest_rec_device(gopbrt_scene* sc, int64_t n, const double* rays_soa7, int32_t* prim_rec, double* t, void* stream) {
+  if (!sc || n < 0) return GOPBRT_ERR_INVALID;
+  if (n == 0) return GOPBRT_OK;
+  gopbrt_ctx* ctx = sc->ctx;
+  cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+  // the kernel writes tHit into the tmax plane; keep the caller's rays intact by working on `t`
+  GP_CUDA(ctx, cudaMemcpyAsync(t, rays_soa7 + 6 * n, n * sizeof(double), cudaMemcpyDeviceToDevice, st));
+  RaySoA r = soa7(const_cast<double*>(rays_soa7), n);
+  r.tmax = t;
+  static int grid = 0;
+  if (!grid) grid = grid_for(ctx, (const void*)k_extend<false>, kTraceThreads);
+  long long need = (n + kTraceThreads - 1) / kTraceThreads;
+  k_extend<false><<<(int)std::min<long long>(grid, need), kTraceThreads, 0, st>>>(sc->dev, r, prim_rec, nullptr, nullptr, n, sc->tctr.p);
+  ctx->launches++;
+  GP_CUDA(ctx, cudaGetLastError());
+  return GOPBRT_OK;
+}
+
+extern "C" int gopbrt_trace_closest_device(gopbrt_scene* sc, int64_t n, const double* rays_soa7, int32_t* prim, double* t, void* stream) {
+  int rc = trace_closest_rec_device(sc, n, rays_soa7, prim, t, stream);
+  if (rc != GOPBRT_OK || n == 0) return rc;
+  gopbrt_ctx* ctx = sc->ctx;
+  cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+  k_rec_to_prim<<<ctx->sm_count * 8, 256, 0, st>>>(sc->dev, prim, n);
+  ctx->launches++;
+  GP_CUDA(ctx, cudaGetLastError());
+  return GOPBRT_OK;
+}
+
+extern "C" int gopbrt_trace_any_device(gopbrt_scene* sc, int64_t n, const double* rays_soa7, uint8_t* hit, void* stream) {
+  if (!sc || n < 0) return GOPBRT_ERR_INVALID;
+  if (n == 0) return GOPBRT_OK;
+  gopbrt_ctx* ctx = sc->ctx;
+  cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+  RaySoA r = soa7(const_cast<double*>(rays_soa7), n);
+  static int grid = 0;
+  if (!grid) grid = grid_for(ctx, (const void*)k_anyhit<false>, kTraceThreads);
+  long long need = (n + kTraceThreads - 1) / kTraceThreads;
+  k_anyhit<false><<<(int)std::min<long long>(grid, need), kTraceThreads, 0, st>>>(sc->dev, r, hit, nullptr, nullptr, n, sc->tctr.p);
+  ctx->launches++;
+  GP_CUDA(ctx, cudaGetLastError());
+  return GOPBRT_OK;
+}
+
+extern "C" int gopbrt_trace_closest(gopbrt_scene* sc, int64_t n, const double* ox, const double* oy, const double* oz, const double* dx,
+                                    const double* dy, const double* dz, const double* tmax, int32_t* prim, double* t, double* p, double* nrm) {
+  if (!sc || n < 0 || (n > 0 && (!ox || !oy || !oz || !dx || !dy || !dz || !tmax || !prim || !t))) return GOPBRT_ERR_INVALID;
+  if (n == 0) return GOPBRT_OK;
+  gopbrt_ctx* ctx = sc->ctx;
+  std::lock_guard<std::mutex> g(sc->mu);
+  GP_CUDA(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  DevBuf<double> rays, tt, pp, nn;
+  DevBuf<int> rec, pr;
+  GP_CUDA(ctx, rays.alloc(7 * (size_t)n));
+  GP_CUDA(ctx, tt.alloc(n));
+  GP_CUDA(ctx, rec.alloc(n));
+  GP_CUDA(ctx, pr.alloc(n));
+  GP_CUDA(ctx, pp.alloc(3 * (size_t)n));
+  GP_CUDA(ctx, nn.alloc(3 * (size_t)n));
+  const double* src[7] = {ox, oy, oz, dx, dy, dz, tmax};
+  for (int k = 0; k < 7; k++) GP_CUDA(ctx, cudaMemcpyAsync(rays.p + (size_t)k * n, src[k], n * sizeof(double), cudaMemcpyHostToDevice, st));
+  int rc = trace_closest_rec_device(sc, n, rays.p, rec.p, tt.p, st);
+  if (rc != GOPBRT_OK) return rc;
+  RaySoA r = soa7(rays.p, n);
+  r.tmax = tt.p;
+  k_hit_points<<<ctx->sm_count * 4, 128, 0, st>>>(sc->dev, r, rec.p, n, pr.p, pp.p, nn.p);
+  ctx->launches++;
+  GP_CUDA(ctx, cudaGetLastError());
+  GP_CUDA(ctx, cudaMemcpyAsync(prim, pr.p, n * sizeof(int), cudaMemcpyDeviceToHost, st));
+  GP_CUDA(ctx, cudaMemcpyAsync(t, tt.p, n * sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (p) GP_CUDA(ctx, cudaMemcpyAsync(p, pp.p, 3 * n * sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (nrm) GP_CUDA(ctx, cudaMemcpyAsync(nrm, nn.p, 3 * n * sizeof(double), cudaMemcpyDeviceToHost, st));
+  GP_CUDA(ctx, cudaStreamSynchronize(st));
+  return GOPBRT_OK;
+}
+
+extern "C" int gopbrt_trace_any(gopbrt_scene* sc, int64_t n, const double* ox, const double* oy, const double* oz, const double* dx,
+                                const double* dy, const double* dz, const double* tmax, uint8_t* hit) {
+  if (!sc || n < 0 || (n > 0 && (!ox || !oy || !oz || !dx || !dy || !dz || !tmax || !hit))) return GOPBRT_ERR_INVALID;
+  if (n == 0) return GOPBRT_OK;
+  gopbrt_ctx* ctx = sc->ctx;
+  std::lock_guard<std::mutex> g(sc->mu);
+  GP_CUDA(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  DevBuf<double> rays;
+  DevBuf<unsigned char> h;
+  GP_CUDA(ctx, rays.alloc(7 * (size_t)n));
+  GP_CUDA(ctx, h.alloc(n));
+  const double* src[7] = {ox, oy, oz, dx, dy, dz, tmax};
+  for (int k = 0; k < 7; k++) GP_CUDA(ctx, cudaMemcpyAsync(rays.p + (size_t)k * n, src[k], n * sizeof(double), cudaMemcpyHostToDevice, st));
+  int rc = gopbrt_trace_any_device(sc, n, rays.p, h.p, st);
+  if (rc != GOPBRT_OK) return rc;
+  GP_CUDA(ctx, cudaMemcpyAsync(hit, h.p, n, cudaMemcpyDeviceToHost, st));
+  GP_CUDA(ctx, cudaStreamSynchronize(st));
+  return GOPBRT_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ render
+static int render_impl(gopbrt_scene* sc, const gopbrt_camera* cam, const gopbrt_sampler* smp, const gopbrt_integrator* ig,
+                       const gopbrt_film* film, const gopbrt_render_options* opt, double* d_film, gopbrt_stats* stats) {
+  gopbrt_ctx* ctx = sc->ctx;
+  auto bad = [&](const char* msg) { ctx->last_error = msg; return GOPBRT_ERR_INVALID; };
+  if (ig->kind != GOPBRT_INTEGRATOR_PATH) return bad("only the Path integrator is on the hot path");
+  if (ig->light_strategy != GOPBRT_LIGHTS_UNIFORM) return bad("only the Uniform light strategy is supported");
+  if (ig->tile_size < 1) return bad("tile_size < 1");
+  if (!(film->filter_radius[0] > 0) || !(film->filter_radius[1] > 0)) return bad("filter radius must be positive");
+  if (smp->kind != GOPBRT_SAMPLER_STRATIFIED && smp->kind != GOPBRT_SAMPLER_RANDOM) return bad("unknown sampler");
+  if (smp->n_sampled_dimensions > 255 || smp->n_sampled_dimensions < 0) return bad("n_sampled_dimensions out of range");
+  int rank = opt ? opt->rank : 0, world = opt ? opt->world : 1;
+  int flags = opt ? opt->flags : 0;
+  if (world < 1 || rank < 0 || rank >= world) return bad("bad rank/world");
+  sc->cancel.store(0);
+
+  RenderParams P;
+  memset(&P, 0, sizeof(P));
+  P.raster_to_camera = m4_from(cam->raster_to_camera);
+  P.camera_to_world = m4_from(cam->camera_to_world);
+  P.lens_radius = cam->lens_radius; P.focal_distance = cam->focal_distance;
+  P.shutter_open = cam->shutter_open; P.shutter_close = cam->shutter_close;
+  P.sampler_kind = smp->kind; P.xs = smp->x_samples; P.ys = smp->y_samples; P.jitter = smp->jitter;
+  P.ndims = smp->kind == GOPBRT_SAMPLER_STRATIFIED ? smp->n_sampled_dimensions : 0;
+  P.mode = smp->mode;
+  P.spp = smp->kind == GOPBRT_SAMPLER_STRATIFIED ? smp->x_samples * smp->y_samples : smp->x_samples;
+  if (P.spp < 1) return bad("samples per pixel < 1");
+  P.max_depth = ig->max_depth; P.rr_threshold = ig->rr_threshold;
+  P.tile_size = ig->tile_size;
+  // NewFilm (film.go:43-48)
+  P.cx0 = (long long)ceil((double)film->width * film->crop[0]); P.cy0 = (long long)ceil((double)film->height * film->crop[1]);
+  P.cx1 = (long long)ceil((double)film->width * film->crop[2]); P.cy1 = (long long)ceil((double)film->height * film->crop[3]);
+  long long fw = P.cx1 - P.cx0, fh = P.cy1 - P.cy0;
+  if (fw <= 0 || fh <= 0) return bad("empty film");
+  P.ntx = (fw + P.tile_size - 1) / P.tile_size; P.nty = (fh + P.tile_size - 1) / P.tile_size;  // integrator.go:297-299
+  P.ntiles = P.ntx * P.nty;
+  P.frx = film->filter_radius[0]; P.fry = film->filter_radius[1];
+  long long tpw = std::min<long long>(fw, P.tile_size + 2 * (long long)ceil(P.frx) + 2), tph = std::min<long long>(fh, P.tile_size + 2 * (long long)ceil(P.fry) + 2);
+  P.tpw = (int)tpw; P.tph = (int)tph;
+  if (P.mode == GOPBRT_MODE_STRICT) { P.rank = rank; P.world = world; P.s_rank = 0; P.s_world = 1; }
+  else { P.rank = 0; P.world = 1; P.s_rank = rank; P.s_world = world; }
+  long long lanes_total = (P.ntiles - P.rank + P.world - 1) / P.world;
+
+  cudaStream_t st = ctx->stream;
+  GP_CUDA(ctx, cudaSetDevice(ctx->device));
+  GP_CUDA(ctx, cudaMemsetAsync(d_film, 0, (size_t)fw * fh * 4 * sizeof(double), st));
+
+  // ---- workspace
+  const int N_F64 = 7 + 7 + 7 + 3 + 2;  // ray, shadow ray, L/beta/eta, pending, pFilm
+  size_t per_lane = (size_t)N_F64 * 8 + 4 * 4 + 5 * 4 + 2 * 8 + 3 + (size_t)P.ndims * P.spp * 8 + (size_t)tpw * tph * 4 * 8;
+  size_t free_b = 0, total_b = 0;
+  GP_CUDA(ctx, cudaMemGetInfo(&free_b, &total_b));
+  Workspace& W = sc->ws;
+  size_t held = W.lanes ? (size_t)W.lanes * per_lane : 0;
+  long long cap = (long long)(((double)(free_b + held) * 0.80) / (double)per_lane);
+  if (opt && opt->max_lanes > 0) cap = std::min<long long>(cap, opt->max_lanes);
+  long long lanes = std::max<long long>(1, std::min(lanes_total, cap));
+  if (lanes > 0x7fffff00LL) lanes = 0x7fffff00LL;
+  size_t bt = (size_t)P.ndims * P.spp * lanes, bp = (size_t)tpw * tph * 4 * lanes;
+  if (W.lanes != lanes || W.bytes_tables != bt || W.bytes_tilepix != bp) {
+    W.f64.release(); W.i32.release(); W.u64.release(); W.u8.release(); W.tables.release(); W.tilepix.release();
+    GP_CUDA(ctx, W.f64.alloc((size_t)N_F64 * lanes));
+    GP_CUDA(ctx, W.i32.alloc((size_t)(4 + 5) * lanes));
+    GP_CUDA(ctx, W.u64.alloc((size_t)2 * lanes));
+    GP_CUDA(ctx, W.u8.alloc((size_t)3 * lanes));
+    GP_CUDA(ctx, W.tables.alloc(std::max<size_t>(bt, 1)));
+    GP_CUDA(ctx, W.tilepix.alloc(bp));
+    if (!W.cnt.p) GP_CUDA(ctx, W.cnt.alloc(8));
+    if (!W.rctr.p) GP_CUDA(ctx, W.rctr.alloc(1));
+    if (!W.remaining_host) {
+      GP_CUDA(ctx, cudaHostAlloc((void**)&W.remaining_host, sizeof(int), cudaHostAllocMapped));
+      GP_CUDA(ctx, cudaHostGetDevicePointer((void**)&W.remaining_dev, W.remaining_host, 0));
+    }
+    W.lanes = lanes; W.bytes_tables = bt; W.bytes_tilepix = bp;
+  }
+  Lanes L;
+  L.n = lanes;
+  double* f = W.f64.p;
+  auto plane = [&](int k) { return f + (size_t)k * lanes; };
+  L.ray = RaySoA{plane(0), plane(1), plane(2), plane(3), plane(4), plane(5), plane(6)};
+  L.sray = RaySoA{plane(7), plane(8), plane(9), plane(10), plane(11), plane(12), plane(13)};
+  L.Lr = plane(14); L.Lg = plane(15); L.Lb = plane(16); L.br = plane(17); L.bg = plane(18); L.bb = plane(19); L.eta_scale = plane(20);
+  L.pr = plane(21); L.pg = plane(22); L.pb = plane(23); L.fx = plane(24); L.fy = plane(25);
+  int* ip = W.i32.p;
+  L.hit_rec = ip; L.bounces = ip + lanes; L.pix = ip + 2 * lanes; L.sidx = ip + 3 * lanes;
+  Queues Q;
+  Q.extend = ip + 4 * lanes; Q.extend_next = ip + 5 * lanes; Q.shadow = ip + 6 * lanes; Q.regen = ip + 7 * lanes; Q.regen_next = ip + 8 * lanes;
+  Q.cnt = W.cnt.p;
+  L.rng_state = W.u64.p; L.rng_inc = W.u64.p + lanes;
+  L.occluded = W.u8.p; L.pend_gt10 = W.u8.p + lanes; L.has_sample = W.u8.p + 2 * lanes;
+  L.tables = W.tables.p; L.tilepix = W.tilepix.p;
+
+  GP_CUDA(ctx, cudaMemsetAsync(W.rctr.p, 0, sizeof(RenderCounters), st));
+  GP_CUDA(ctx, cudaMemsetAsync(sc->tctr.p, 0, sizeof(TraceCounters), st));
+  const bool count = (flags & GOPBRT_FLAG_COUNT_TRAVERSAL) != 0;
+
+  static int g_gen = 0, g_shade = 0, g_ext = 0, g_ext_c = 0, g_any = 0, g_any_c = 0;
+  if (!g_gen) {
+    g_gen = grid_for(ctx, (const void*)k_generate, 128);
+    g_shade = grid_for(ctx, (const void*)k_shade, 128);
+    g_ext = grid_for(ctx, (const void*)k_extend<false>, kTraceThreads);
+    g_ext_c = grid_for(ctx, (const void*)k_extend<true>, kTraceThreads);
+    g_any = grid_for(ctx, (const void*)k_anyhit<false>, kTraceThreads);
+    g_any_c = grid_for(ctx, (const void*)k_anyhit<true>, kTraceThreads);
+  }
+  const int g_small = ctx->sm_count * 8;
+
+  cudaEvent_t ev[2];
+  GP_CUDA(ctx, cudaEventCreate(&ev[0]));
+  GP_CUDA(ctx, cudaEventCreate(&ev[1]));
+  GP_CUDA(ctx, cudaEventRecord(ev[0], st));
+  uint64_t iterations = 0, launches0 = ctx->launches.load();
+  int rc = GOPBRT_OK;
+  for (long long base = 0; base < lanes_total && rc == GOPBRT_OK; base += lanes) {
+    P.lane_base = base;
+    P.lanes_active = std::min(lanes, lanes_total - base);
+    GP_CUDA(ctx, cudaMemsetAsync(W.tilepix.p, 0, bp * sizeof(double), st));
+    GP_CUDA(ctx, cudaMemsetAsync(W.cnt.p, 0, 8 * sizeof(int), st));
+    k_init_lanes<<<g_small, 128, 0, st>>>(L, P);
+    k_generate<<<g_gen, 128, 0, st>>>(sc->dev, L, P, Q, nullptr, nullptr, W.rctr.p);
+    ctx->launches += 2;
+    for (;;) {
+      if (count) k_extend<true><<<g_ext_c, kTraceThreads, 0, st>>>(sc->dev, L.ray, L.hit_rec, Q.extend, Q.cnt + 0, 0, sc->tctr.p);
+      else k_extend<false><<<g_ext, kTraceThreads, 0, st>>>(sc->dev, L.ray, L.hit_rec, Q.extend, Q.cnt + 0, 0, sc->tctr.p);
+      k_shade<<<g_shade, 128, 0, st>>>(sc->dev, L, P, Q, W.rctr.p);
+      if (count) k_anyhit<true><<<g_any_c, kTraceThreads, 0, st>>>(sc->dev, L.sray, L.occluded, Q.shadow, Q.cnt + 2, 0, sc->tctr.p);
+      else k_anyhit<false><<<g_any, kTraceThreads, 0, st>>>(sc->dev, L.sray, L.occluded, Q.shadow, Q.cnt + 2, 0, sc->tctr.p);
+      k_shadow_resolve<<<g_small, 128, 0, st>>>(L, Q, W.rctr.p);
+      k_advance<<<1, 32, 0, st>>>(Q, W.rctr.p, W.remaining_dev);
+      std::swap(Q.extend, Q.extend_next);
+      std::swap(Q.regen, Q.regen_next);
+      k_generate<<<g_gen, 128, 0, st>>>(sc->dev, L, P, Q, Q.regen, Q.cnt + 3, W.rctr.p);
+      ctx->launches += 6;
+      iterations++;
+      GP_CUDA(ctx, cudaStreamSynchronize(st));
+      if (*W.remaining_host == 0) break;
+      if (sc->cancel.load()) { rc = GOPBRT_ERR_CANCELLED; break; }
+    }
+    k_film_merge<<<g_small, 128, 0, st>>>(L, P, d_film);
+    ctx->launches++;
+  }
+  GP_CUDA(ctx, cudaEventRecord(ev[1], st));
+  GP_CUDA(ctx, cudaStreamSynchronize(st));
+  GP_CUDA(ctx, cudaGetLastError());
+  float ms = 0;
+  cudaEventElapsedTime(&ms, ev[0], ev[1]);
+  cudaEventDestroy(ev[0]);
+  cudaEventDestroy(ev[1]);
+  RenderCounters rcnt;
+  TraceCounters tcnt;
+  GP_CUDA(ctx, cudaMemcpy(&rcnt, W.rctr.p, sizeof(rcnt), cudaMemcpyDeviceToHost));
+  GP_CUDA(ctx, cudaMemcpy(&tcnt, sc->tctr.p, sizeof(tcnt), cudaMemcpyDeviceToHost));
+  if (stats) {
+    memset(stats, 0, sizeof(*stats));
+    stats->camera_rays = rcnt.camera_rays; stats->closest_rays = rcnt.closest_rays; stats->shadow_rays = rcnt.shadow_rays;
+    stats->dead_mis_rays = rcnt.dead_mis_rays; stats->nodes_visited = tcnt.nodes; stats->prim_tests = tcnt.prims;
+    stats->shadow_nodes_visited = tcnt.snodes; stats->shadow_prim_tests = tcnt.sprims; stats->radiance_gt10 = rcnt.radiance_gt10;
+    stats->nan_samples = rcnt.nan_samples; stats->efloat_panics = rcnt.efloat_panics + tcnt.efloat_panics;
+    stats->stack_overflows = tcnt.stack_overflows; stats->iterations = iterations; stats->launches = ctx->launches.load() - launches0;
+    stats->lanes = (uint64_t)lanes; stats->ms_total = ms; stats->bvh_nodes = sc->bvh_nodes; stats->bvh_depth = sc->bvh_depth;
+  }
+  if (rc == GOPBRT_OK && (flags & GOPBRT_FLAG_FAIL_ON_PANIC) && (rcnt.radiance_gt10 || rcnt.efloat_panics || tcnt.efloat_panics || rcnt.unsupported)) {
+    ctx->last_error = "a condition on which the reference panics was hit (see gopbrt_stats)";
+    return GOPBRT_ERR_REFERENCE_PANIC;
+  }
+  return rc;
+}
+
+extern "C" int gopbrt_render_device(gopbrt_scene* sc, const gopbrt_camera* cam, const gopbrt_sampler* smp, const gopbrt_integrator* ig,
+                                    const gopbrt_film* film, const gopbrt_render_options* opt, double* d_film, gopbrt_stats* stats) {
+  if (!sc || !cam || !smp || !ig || !film || !d_film) return GOPBRT_ERR_INVALID;
+  std::lock_guard<std::mutex> g(sc->mu);
+  return render_impl(sc, cam, smp, ig, film, opt, d_film, stats);
+}
+
+extern "C" int gopbrt_render(gopbrt_scene* sc, const gopbrt_camera* cam, const gopbrt_sampler* smp, const gopbrt_integrator* ig,
+                             const gopbrt_film* film, const gopbrt_render_options* opt, double* film_out, gopbrt_stats* stats) {
+  if (!sc || !cam || !smp || !ig || !film || !film_out) return GOPBRT_ERR_INVALID;
+  gopbrt_ctx* ctx = sc->ctx;
+  std::lock_guard<std::mutex> g(sc->mu);
+  GP_CUDA(ctx, cudaSetDevice(ctx->device));
+  long long cx0 = (long long)ceil((double)film->width * film->crop[0]), cy0 = (long long)ceil((double)film->height * film->crop[1]);
+  long long cx1 = (long long)ceil((double)film->width * film->crop[2]), cy1 = (long long)ceil((double)film->height * film->crop[3]);
+  if (cx1 <= cx0 || cy1 <= cy0) { ctx->last_error = "empty film"; return GOPBRT_ERR_INVALID; }
+  size_t n = (size_t)(cx1 - cx0) * (cy1 - cy0) * 4;
+  DevBuf<double> d_film;
+  GP_CUDA(ctx, d_film.alloc(n));
+  int rc = render_impl(sc, cam, smp, ig, film, opt, d_film.p, stats);
+  if (rc != GOPBRT_OK) return rc;
+  auto t0 = std::chrono::steady_clock::now();
+  GP_CUDA(ctx, cudaMemcpy(film_out, d_film.p, n * sizeof(double), cudaMemcpyDeviceToHost));
+  if (stats) stats->ms_download = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  return GOPBRT_OK;
+}

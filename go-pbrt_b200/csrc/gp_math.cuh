@@ -1,0 +1,367 @@
+// gp_math.cuh — float64 numeric core of libgopbrt_cuda (host + device).
+//
+// Everything on the intersection / spawn / shading path is float64 and must round exactly like the Go reference on
+// amd64 (which never contracts x*y+z): this translation unit is compiled with -fmad=false (device) and
+// -ffp-contract=off (host).  Go's math.Min/Max/Nextafter and its software Sin/Cos/Atan2/Acos (golang:1.11,
+// Cephes-derived, reached through pkg/math/math.go:21-144) are reproduced instruction for instruction so that
+// hit/miss, primitive ids, t and the shaded film agree with the reference semantics bit for bit, not just to an ulp.
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+
+#define GP_HD __host__ __device__ __forceinline__
+#define GP_D __device__ __forceinline__
+
+namespace gp {
+
+constexpr double kPi = 3.14159265358979323846264338327950288;
+constexpr double kPiOver2 = kPi / 2;  // exact scalings of the float64 Pi (pkg/math/math.go:13-14 compute the same values)
+constexpr double kPiOver4 = kPi / 4;
+constexpr double k2Pi = 2 * kPi;
+constexpr double kInvPi = 1.0 / kPi;  // float64 division, as pkg/math/math.go:10
+
+GP_HD double d_inf() {
+#ifdef __CUDA_ARCH__
+  return __longlong_as_double(0x7ff0000000000000LL);
+#else
+  return INFINITY;
+#endif
+}
+GP_HD uint64_t f2b(double x) {
+#ifdef __CUDA_ARCH__
+  return (uint64_t)__double_as_longlong(x);
+#else
+  uint64_t u; memcpy(&u, &x, 8); return u;
+#endif
+}
+GP_HD double b2f(uint64_t u) {
+#ifdef __CUDA_ARCH__
+  return __longlong_as_double((long long)u);
+#else
+  double x; memcpy(&x, &u, 8); return x;
+#endif
+}
+GP_HD bool is_nan(double x) { return x != x; }
+GP_HD bool is_inf(double x) { return fabs(x) == d_inf(); }
+GP_HD bool sign_bit(double x) { return (f2b(x) >> 63) != 0; }
+GP_HD double copy_sign(double mag, double sgn) { return b2f((f2b(mag) & 0x7fffffffffffffffULL) | (f2b(sgn) & 0x8000000000000000ULL)); }
+
+// math.Nextafter restricted to the two call shapes of pkg/math/math.go:122-128.
+// NextFloatUp(v) = Nextafter(v, v+1): NaN stays NaN; v+1 == v (|v| >= 2^53, +-Inf) returns v; 0 -> smallest denormal.
+GP_HD double next_up(double v) {
+  double y = v + 1;
+  if (is_nan(v)) return v;
+  if (v == y) return v;
+  if (v == 0) return b2f(1);
+  return (v > 0) ? b2f(f2b(v) + 1) : b2f(f2b(v) - 1);  // y > v always here
+}
+GP_HD double next_down(double v) {
+  double y = v - 1;
+  if (is_nan(v)) return v;
+  if (v == y) return v;
+  if (v == 0) return b2f(0x8000000000000001ULL);
+  return (v > 0) ? b2f(f2b(v) - 1) : b2f(f2b(v) + 1);  // y < v always here
+}
+
+// math.Min / math.Max (Go): -Inf/+Inf first, NaN-propagating, signed-zero aware — NOT fmin/fmax.
+GP_HD double go_min(double x, double y) {
+  if (x == -d_inf() || y == -d_inf()) return -d_inf();
+  if (is_nan(x) || is_nan(y)) return b2f(0x7ff8000000000001ULL);
+  if (x == 0 && x == y) return sign_bit(x) ? x : y;
+  return x < y ? x : y;
+}
+GP_HD double go_max(double x, double y) {
+  if (x == d_inf() || y == d_inf()) return d_inf();
+  if (is_nan(x) || is_nan(y)) return b2f(0x7ff8000000000001ULL);
+  if (x == 0 && x == y) return sign_bit(x) ? y : x;
+  return x > y ? x : y;
+}
+GP_HD double go_clamp(double v, double lo, double hi) {  // pkg/math/math.go:42-50
+  if (v < lo) return lo;
+  if (v > hi) return hi;
+  return v;
+}
+
+// pkg/math/math.go:17-19,82-84: MachineEpsilon = NextFloatUp(0) = 4.94e-324.  The arithmetic is carried
+// out for real (denormals are honoured by fp64 on the GPU): gamma(n) = (n*eps)/(1 - n*eps).
+GP_HD double machine_epsilon() { return b2f(1); }
+GP_HD double one_minus_epsilon() { return b2f(0x3fefffffffffffffULL); }
+GP_HD double gamma_n(double n) { double e = machine_epsilon(); return (n * e) / (1 - n * e); }
+
+// ---- Go 1.11 src/math/sin.go (Cephes sin.c): Cody-Waite Pi/4 reduction + degree-6 polynomials ----
+#define GP_PI4A 7.85398125648498535156e-1
+#define GP_PI4B 3.77489470793079817668e-8
+#define GP_PI4C 2.69515142907905952645e-15
+#define GP_M4PI 1.273239544735162542821171882678754627704620361328125
+
+GP_HD double poly_sin(double z, double zz) {
+  return z + z * zz * ((((((1.58962301576546568060e-10 * zz) + -2.50507477628578072866e-8) * zz + 2.75573136213857245213e-6) * zz +
+                          -1.98412698295895385996e-4) * zz + 8.33333333332211858878e-3) * zz + -1.66666666666666307295e-1);
+}
+GP_HD double poly_cos(double zz) {
+  return 1.0 - 0.5 * zz + zz * zz * ((((((-1.13585365213876817300e-11 * zz) + 2.08757008419747316778e-9) * zz + -2.75573141792967388112e-7) * zz +
+                                       2.48015872888517045348e-5) * zz + -1.38888888888730564116e-3) * zz + 4.16666666666665929218e-2);
+}
+GP_HD double go_cos(double x) {
+  if (is_nan(x) || is_inf(x)) return b2f(0x7ff8000000000001ULL);
+  bool sign = false;
+  x = fabs(x);
+  uint64_t j = (uint64_t)(long long)(x * GP_M4PI);
+  double y = (double)(long long)j;
+  if (j & 1) { j++; y++; }
+  j &= 7;
+  if (j > 3) { j -= 4; sign = !sign; }
+  if (j > 1) sign = !sign;
+  double z = ((x - y * GP_PI4A) - y * GP_PI4B) - y * GP_PI4C;
+  double zz = z * z;
+  y = (j == 1 || j == 2) ? poly_sin(z, zz) : poly_cos(zz);
+  return sign ? -y : y;
+}
+GP_HD double go_sin(double x) {
+  if (x == 0 || is_nan(x)) return x;
+  if (is_inf(x)) return b2f(0x7ff8000000000001ULL);
+  bool sign = false;
+  if (x < 0) { x = -x; sign = true; }
+  uint64_t j = (uint64_t)(long long)(x * GP_M4PI);
+  double y = (double)(long long)j;
+  if (j & 1) { j++; y++; }
+  j &= 7;
+  if (j > 3) { sign = !sign; j -= 4; }
+  double z = ((x - y * GP_PI4A) - y * GP_PI4B) - y * GP_PI4C;
+  double zz = z * z;
+  y = (j == 1 || j == 2) ? poly_cos(zz) : poly_sin(z, zz);
+  return sign ? -y : y;
+}
+// ---- Go src/math/atan.go (Cephes atan.c) ----
+GP_HD double go_xatan(double x) {
+  double z = x * x;
+  z = z * ((((-8.750608600031904122785e-01 * z + -1.615753718733365076637e+01) * z + -7.500855792314704667340e+01) * z +
+            -1.228866684490136173410e+02) * z + -6.485021904942025371773e+01) /
+      (((((z + 2.485846490142306297962e+01) * z + 1.650270098316988542046e+02) * z + 4.328810604912902668951e+02) * z +
+        4.853903996359136964868e+02) * z + 1.945506571482613964425e+02);
+  z = x * z + x;
+  return z;
+}
+GP_HD double go_satan(double x) {
+  const double Morebits = 6.123233995736765886130e-17;
+  const double Tan3pio8 = 2.41421356237309504880;
+  if (x <= 0.66) return go_xatan(x);
+  if (x > Tan3pio8) return kPiOver2 - go_xatan(1 / x) + Morebits;
+  return kPiOver4 + go_xatan((x - 1) / (x + 1)) + 0.5 * Morebits;
+}
+GP_HD double go_atan(double x) {
+  if (x == 0) return x;
+  if (x > 0) return go_satan(x);
+  return -go_satan(-x);
+}
+GP_HD double go_atan2(double y, double x) {  // src/math/atan2.go
+  if (is_nan(y) || is_nan(x)) return b2f(0x7ff8000000000001ULL);
+  if (y == 0) {
+    if (x >= 0 && !sign_bit(x)) return copy_sign(0.0, y);
+    return copy_sign(kPi, y);
+  }
+  if (x == 0) return copy_sign(kPiOver2, y);
+  if (is_inf(x)) {
+    if (x > 0) return is_inf(y) ? copy_sign(kPiOver4, y) : copy_sign(0.0, y);
+    return is_inf(y) ? copy_sign(3 * kPi / 4, y) : copy_sign(kPi, y);
+  }
+  if (is_inf(y)) return copy_sign(kPiOver2, y);
+  double q = go_atan(y / x);
+  if (x < 0) return q <= 0 ? q + kPi : q - kPi;
+  return q;
+}
+GP_HD double go_asin(double x) {  // src/math/asin.go
+  if (x == 0) return x;
+  bool sign = false;
+  if (x < 0) { x = -x; sign = true; }
+  if (x > 1) return b2f(0x7ff8000000000001ULL);
+  double temp = sqrt(1 - x * x);
+  if (x > 0.7) temp = kPiOver2 - go_satan(temp / x);
+  else temp = go_satan(x / temp);
+  return sign ? -temp : temp;
+}
+GP_HD double go_acos(double x) { return kPiOver2 - go_asin(x); }
+
+// ---- pkg/geometry/xyz.go:424-614 ----
+struct V3 { double x, y, z; };
+GP_HD V3 mk3(double x, double y, double z) { V3 v; v.x = x; v.y = y; v.z = z; return v; }
+GP_HD V3 operator+(V3 a, V3 b) { return mk3(a.x + b.x, a.y + b.y, a.z + b.z); }
+GP_HD V3 operator-(V3 a, V3 b) { return mk3(a.x - b.x, a.y - b.y, a.z - b.z); }
+GP_HD V3 operator*(V3 a, double s) { return mk3(a.x * s, a.y * s, a.z * s); }
+GP_HD V3 operator/(V3 a, double s) { return mk3(a.x / s, a.y / s, a.z / s); }
+GP_HD V3 vabs(V3 a) { return mk3(fabs(a.x), fabs(a.y), fabs(a.z)); }
+GP_HD double dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+GP_HD double len2(V3 a) { return a.x * a.x + a.y * a.y + a.z * a.z; }
+GP_HD double dist2(V3 self, V3 other) { return len2(other - self); }  // xyz.go:579-581
+GP_HD V3 cross(V3 a, V3 b) { return mk3((a.y * b.z) - (a.z * b.y), (a.z * b.x) - (a.x * b.z), (a.x * b.y) - (a.y * b.x)); }
+GP_HD V3 normalized(V3 a) {  // xyz.go:587-606: times 1/sqrt
+  double n2 = len2(a);
+  if (n2 > 0) {
+    double inv = 1.0 / sqrt(n2);
+    a.x *= inv; a.y *= inv; a.z *= inv;
+  }
+  return a;
+}
+GP_HD V3 faceforward(V3 n1, V3 n2) { return dot(n1, n2) < 0.0 ? n1 * -1.0 : n1; }  // geometry.go:115-120
+GP_HD double comp(V3 v, int i) { return i == 0 ? v.x : (i == 1 ? v.y : v.z); }
+// geometry.go:47-60 — divides by the squared length
+GP_HD void coordinate_system(V3 v1, V3* v2, V3* v3) {
+  if (fabs(v1.x) > fabs(v1.y)) {
+    double v = v1.x * v1.x + v1.z * v1.z;
+    *v2 = mk3(-v1.z / v, 0 / v, v1.x / v);
+  } else {
+    double v = v1.y * v1.y + v1.z * v1.z;
+    *v2 = mk3(0 / v, v1.z / v, -v1.y / v);
+  }
+  *v3 = cross(v1, *v2);
+}
+
+// ---- pkg/efloat (efloat.go, math.go) ----
+// `bad` accumulates the conditions on which efloat.Check panics (efloat.go:102-111); the kernels count them.
+struct EF { double v, lo, hi; };
+GP_HD void ef_check(const EF& f, int& bad) {
+  if (is_inf(f.lo) || is_nan(f.lo) || is_inf(f.hi) || is_nan(f.hi) || f.lo > f.hi) bad = 1;
+}
+GP_HD EF ef_new(double v, double err, int& bad) {  // efloat.go:10-22
+  EF f; f.v = v; f.lo = v; f.hi = v;
+  if (err != 0) { f.lo = next_down(v - err); f.hi = next_up(v + err); }
+  ef_check(f, bad);
+  return f;
+}
+GP_HD EF ef_add(EF f, EF o, int& bad) {
+  f.v = f.v + o.v; f.lo = next_down(f.lo + o.lo); f.hi = next_up(f.hi + o.hi);
+  ef_check(f, bad);
+  return f;
+}
+GP_HD EF ef_sub(EF f, EF o, int& bad) {
+  f.v = f.v - o.v; f.lo = next_down(f.lo - o.hi); f.hi = next_up(f.hi - o.lo);
+  ef_check(f, bad);
+  return f;
+}
+GP_HD EF ef_mul(EF f, EF o, int& bad) {
+  double p0 = f.lo * o.lo, p1 = f.hi * o.lo, p2 = f.lo * o.hi, p3 = f.hi * o.hi;
+  f.v = f.v * o.v;
+  f.lo = next_down(go_min(go_min(p0, p1), go_min(p2, p3)));
+  f.hi = next_up(go_max(go_max(p0, p1), go_max(p2, p3)));
+  ef_check(f, bad);
+  return f;
+}
+GP_HD EF ef_div(EF f, EF o, int& bad) {
+  f.v = f.v / o.v;
+  if (o.lo < 0 && o.hi > 0) { f.lo = -d_inf(); f.hi = d_inf(); }
+  else {
+    double d0 = f.lo / o.lo, d1 = f.hi / o.lo, d2 = f.lo / o.hi, d3 = f.hi / o.hi;
+    f.lo = next_down(go_min(go_min(d0, d1), go_min(d2, d3)));
+    f.hi = next_up(go_max(go_max(d0, d1), go_max(d2, d3)));
+  }
+  ef_check(f, bad);
+  return f;
+}
+GP_HD EF ef_muls(EF f, double s, int& bad) { return ef_mul(f, ef_new(s, 0.0, bad), bad); }
+GP_HD bool ef_quadratic(EF a, EF b, EF c, EF* t0, EF* t1, int& bad) {  // efloat/math.go:35-59
+  double disc = b.v * b.v - 4. * a.v * c.v;
+  if (disc < 0) return false;
+  double root = sqrt(disc);
+  EF fr = ef_new(root, machine_epsilon() * root, bad);
+  EF q = (b.v < 0) ? ef_muls(ef_sub(b, fr, bad), -0.5, bad) : ef_muls(ef_add(b, fr, bad), -0.5, bad);
+  EF r0 = ef_div(q, a, bad), r1 = ef_div(c, q, bad);
+  if (r0.v > r1.v) { EF t = r0; r0 = r1; r1 = t; }
+  *t0 = r0; *t1 = r1;
+  return true;
+}
+
+// ---- pkg/pbrt/transform.go: 4x4 row-major matrix held in registers ----
+struct M4 { double m[4][4]; };
+
+// TransformPoint (transform.go:227-247) incl. the asymmetric error expression
+GP_HD V3 xf_point(const M4& t, V3 p, V3 pe, V3* err) {
+  double xp = t.m[0][0] * p.x + t.m[0][1] * p.y + t.m[0][2] * p.z + t.m[0][3];
+  double yp = t.m[1][0] * p.x + t.m[1][1] * p.y + t.m[1][2] * p.z + t.m[1][3];
+  double zp = t.m[2][0] * p.x + t.m[2][1] * p.y + t.m[2][2] * p.z + t.m[2][3];
+  double wp = t.m[3][0] * p.x + t.m[3][1] * p.y + t.m[3][2] * p.z + t.m[3][3];
+  if (err) {
+    double g3 = gamma_n(3), g31 = gamma_n(3.0) + 1.0;
+    err->x = g31 * (fabs(t.m[0][0]) * pe.x + fabs(t.m[0][1]) * pe.y + fabs(t.m[0][2]) * pe.z) +
+             (g3 * (fabs(t.m[0][0] * p.x) + fabs(t.m[0][1]) * p.y + fabs(t.m[0][2] * p.z + fabs(t.m[0][3]))));
+    err->y = g31 * (fabs(t.m[1][0]) * pe.x + fabs(t.m[1][1]) * pe.y + fabs(t.m[1][2]) * pe.z) +
+             (g3 * (fabs(t.m[1][0] * p.x) + fabs(t.m[1][1]) * p.y + fabs(t.m[1][2] * p.z + fabs(t.m[1][3]))));
+    err->z = g31 * (fabs(t.m[2][0]) * pe.x + fabs(t.m[2][1]) * pe.y + fabs(t.m[2][2]) * pe.z) +
+             (g3 * (fabs(t.m[2][0] * p.x) + fabs(t.m[2][1]) * p.y + fabs(t.m[2][2] * p.z + fabs(t.m[2][3]))));
+  }
+  V3 np = mk3(xp, yp, zp);
+  if (wp == 1.0) return np;
+  return np / wp;
+}
+GP_HD V3 xf_vector(const M4& t, V3 v) {  // transform.go:249-255
+  return mk3(t.m[0][0] * v.x + t.m[0][1] * v.y + t.m[0][2] * v.z, t.m[1][0] * v.x + t.m[1][1] * v.y + t.m[1][2] * v.z,
+             t.m[2][0] * v.x + t.m[2][1] * v.y + t.m[2][2] * v.z);
+}
+GP_HD V3 xf_vector_err(const M4& t, V3 v, V3* err) {  // transform.go:257-269
+  double g3 = gamma_n(3);
+  err->x = g3 * (fabs(t.m[0][0] * v.x) + fabs(t.m[0][1] * v.y) + fabs(t.m[0][2] * v.z));
+  err->y = g3 * (fabs(t.m[1][0] * v.x) + fabs(t.m[1][1] * v.y) + fabs(t.m[1][2] * v.z));
+  err->z = g3 * (fabs(t.m[2][0] * v.x) + fabs(t.m[2][1] * v.y) + fabs(t.m[2][2] * v.z));
+  return xf_vector(t, v);
+}
+// TransformNormal (transform.go:271-277): transpose of the INVERSE matrix — pass the inverse here
+GP_HD V3 xf_normal_inv(const M4& inv, V3 n) {
+  return mk3(inv.m[0][0] * n.x + inv.m[1][0] * n.y + inv.m[2][0] * n.z, inv.m[0][1] * n.x + inv.m[1][1] * n.y + inv.m[2][1] * n.z,
+             inv.m[0][2] * n.x + inv.m[1][2] * n.y + inv.m[2][2] * n.z);
+}
+
+struct Ray { V3 o, d; double tmax; };
+
+// TransformRay (transform.go:279-300)
+GP_HD Ray xf_ray(const M4& t, const Ray& r, V3* oerr, V3* derr) {
+  V3 oe, de;
+  V3 o = xf_point(t, r.o, mk3(0, 0, 0), &oe);
+  V3 d = xf_vector_err(t, r.d, &de);
+  double l2 = len2(d);
+  if (l2 > 0) {
+    double dt = dot(vabs(d), oe) / l2;
+    o = o + d * dt;
+  }
+  if (oerr) *oerr = oe;
+  if (derr) *derr = de;
+  Ray out; out.o = o; out.d = d; out.tmax = r.tmax;
+  return out;
+}
+
+// Bounds3.IntersectP (bounds.go:149-185): same if-structure (NaN semantics); the robustness factor
+// 1 + 2*gamma(3) is exactly 1.0 and is multiplied for real.
+GP_HD bool slab_test(double bx0, double by0, double bz0, double bx1, double by1, double bz1, V3 o, V3 invd, int nx, int ny, int nz,
+                     double rtmax) {
+  double g = 1 + 2 * gamma_n(3);
+  double tMin = ((nx ? bx1 : bx0) - o.x) * invd.x;
+  double tMax = ((nx ? bx0 : bx1) - o.x) * invd.x;
+  double tyMin = ((ny ? by1 : by0) - o.y) * invd.y;
+  double tyMax = ((ny ? by0 : by1) - o.y) * invd.y;
+  tMax *= g;
+  tyMax *= g;
+  if (tMin > tyMax || tyMin > tMax) return false;
+  if (tyMin > tMin) tMin = tyMin;
+  if (tyMax < tMax) tMax = tyMax;
+  double tzMin = ((nz ? bz1 : bz0) - o.z) * invd.z;
+  double tzMax = ((nz ? bz0 : bz1) - o.z) * invd.z;
+  tzMax *= g;
+  if (tMin > tzMax || tzMin > tMax) return false;
+  if (tzMin > tMin) tMin = tzMin;
+  if (tzMax < tMax) tMax = tzMax;
+  return tMin < rtmax && tMax > 0;
+}
+
+// OffsetRayOrigin (ray.go:57-74)
+GP_HD V3 offset_ray_origin(V3 p, V3 pError, V3 n, V3 w) {
+  double d = dot(vabs(n), pError) * 1024.0;
+  V3 off = n * d;
+  if (dot(w, n) < 0) off = off * -1.0;
+  V3 po = p + off;
+  if (off.x > 0) po.x = next_up(po.x); else if (off.x < 0) po.x = next_down(po.x);
+  if (off.y > 0) po.y = next_up(po.y); else if (off.y < 0) po.y = next_down(po.y);
+  if (off.z > 0) po.z = next_up(po.z); else if (off.z < 0) po.z = next_down(po.z);
+  return po;
+}
+
+}  // namespace gp

@@ -1,0 +1,857 @@
+// gp_render.cuh — the wavefront path integrator: raygen+sampler, shade (materials, textures, lights), shadow
+// resolve and film kernels.  Restates pbrt.Render / renderWorker (pkg/pbrt/integrator.go:228-350), Path.Li
+// (pkg/integrator/path.go:32-157), UniformSampleOneLight / EstimateDirect (integrator.go:48-195), the samplers
+// (pkg/sampler/*.go, pkg/pbrt/{rng,sampling}.go), the BSDFs (pkg/pbrt/reflection.go), the materials / textures
+// (pkg/materials, pkg/textures, pkg/pbrt/texture.go), the lights (pkg/lights) and the film (pkg/pbrt/film.go),
+// quirks included.
+//
+// A *lane* is one independent sampler stream of the reference: in STRICT mode one image tile (Clone(seed = tile
+// index), integrator.go:318-328) whose pixels and samples are walked sequentially with the RNG state carried
+// along; pbrt.Render(…, tileSize = 1) makes every pixel its own lane.  All per-lane state is structure-of-arrays
+// with the lane index fastest, so a warp's accesses coalesce.  Stages hand lanes to each other through index
+// queues filled with warp-ballot compaction and one aggregated atomicAdd per warp.
+#pragma once
+#include "gp_trace.cuh"
+
+namespace gp {
+
+struct Lanes {
+  long long n;
+  RaySoA ray;
+  int* hit_rec;
+  RaySoA sray;
+  unsigned char* occluded;
+  double *Lr, *Lg, *Lb, *br, *bg, *bb, *eta_scale;
+  double *pr, *pg, *pb;
+  unsigned char* pend_gt10;
+  unsigned long long *rng_state, *rng_inc;
+  int *bounces, *pix, *sidx;
+  unsigned char* has_sample;
+  double *fx, *fy;
+  double* tables;   // [dim][k][lane]
+  double* tilepix;  // [tile pixel][4][lane]
+};
+
+struct RenderParams {
+  M4 raster_to_camera, camera_to_world;
+  double lens_radius, focal_distance, shutter_open, shutter_close;
+  int sampler_kind, xs, ys, jitter, ndims, mode, spp;
+  int max_depth;
+  double rr_threshold;
+  long long tile_size, ntx, nty, ntiles;
+  long long cx0, cy0, cx1, cy1;  // CroppedPixelBounds
+  double frx, fry;               // filter radius
+  int tpw, tph;                  // allocated tile-pixel-bounds extent
+  int rank, world;               // tile partition (STRICT): this rank owns tiles t with t % world == rank
+  int s_rank, s_world;           // sample partition (FAST): this rank owns samples s with s % s_world == s_rank
+  long long lane_base;           // first lane-slot (tile = (lane_base + lane) * world + rank) of this pass
+  long long lanes_active;        // lanes in use this pass
+};
+
+struct RenderCounters {
+  unsigned long long camera_rays, closest_rays, shadow_rays, dead_mis_rays, radiance_gt10, nan_samples, unsupported, efloat_panics;
+};
+
+struct Queues {
+  int *extend, *extend_next, *shadow, *regen, *regen_next;
+  int* cnt;  // [0]=extend [1]=extend_next [2]=shadow [3]=regen [4]=regen_next [5]=done lanes
+};
+
+GP_D void queue_push(int* q, int* cnt, bool pred, int v) {
+  unsigned m = __ballot_sync(0xffffffffu, pred);
+  if (m == 0) return;
+  int lane_id = threadIdx.x & 31;
+  int leader = __ffs(m) - 1;
+  int base = 0;
+  if (lane_id == leader) base = atomicAdd(cnt, __popc(m));
+  base = __shfl_sync(0xffffffffu, base, leader);
+  if (pred) q[base + __popc(m & ((1u << lane_id) - 1u))] = v;
+}
+
+// ---------------------------------------------------------------- RNG (pkg/pbrt/rng.go — a PCG32 *variant*)
+struct Smp {
+  unsigned long long state, inc;
+  int cur1, cur2, sidx;
+  long long lane;
+};
+GP_D uint32_t rng_u32(Smp& s) {
+  unsigned long long old = s.state;
+  s.state = old * 0x5851f42d4c957f2dULL + s.inc;
+  uint32_t xs = (uint32_t)(((old >> 18) ^ old) >> 27);
+  uint32_t rot = (uint32_t)(old >> 59);
+  return (xs >> rot) | (xs << ((rot + 1u) & 31u));  // sic: not a rotate (rng.go:41)
+}
+GP_D void rng_set_sequence(Smp& s, unsigned long long seed) {
+  s.state = 0;
+  s.inc = (seed << 1) | 1ULL;
+  rng_u32(s);
+  s.state += 0x853c49e6748fea9bULL;
+  rng_u32(s);
+}
+GP_D uint32_t rng_u32b(Smp& s, uint32_t b) {
+  uint32_t threshold = (~b + 1u) % b;
+  for (;;) {
+    uint32_t r = rng_u32(s);
+    if (r >= threshold) return r % b;
+  }
+}
+GP_D double rng_uniform(Smp& s) { return go_min(one_minus_epsilon(), (double)rng_u32(s) * 2.3283064365386963e-10); }
+
+GP_D uint32_t kensler_permute(uint32_t i, uint32_t l, uint32_t p) {
+  uint32_t w = l - 1;
+  w |= w >> 1; w |= w >> 2; w |= w >> 4; w |= w >> 8; w |= w >> 16;
+  do {
+    i ^= p; i *= 0xe170893d; i ^= p >> 16; i ^= (i & w) >> 4; i ^= p >> 8; i *= 0x0929eb3f; i ^= p >> 23;
+    i ^= (i & w) >> 1; i *= 1 | p >> 27; i *= 0x6935fa69; i ^= (i & w) >> 11; i *= 0x74dcb303; i ^= (i & w) >> 2;
+    i *= 0x9e501cc3; i ^= (i & w) >> 2; i *= 0xc860a3df; i &= w; i ^= i >> 5;
+  } while (i >= l);
+  return (i + p) % l;
+}
+GP_D uint32_t hash_u32(unsigned long long a, uint32_t b) {
+  unsigned long long x = a * 0x9E3779B97F4A7C15ULL + (unsigned long long)b * 0xD1B54A32D192ED03ULL + 0x632BE59BD9B4E019ULL;
+  x ^= x >> 32; x *= 0xD6E8FEB86659FD93ULL; x ^= x >> 32; x *= 0xD6E8FEB86659FD93ULL; x ^= x >> 32;
+  return (uint32_t)x;
+}
+
+// PixelSampler.Get1D / Get2D (pkg/sampler/pixel.go:60-80), RandomSampler (random.go:21-27)
+GP_D double get1d(Smp& s, const Lanes& L, const RenderParams& P, unsigned long long fast_pixel) {
+  int nd = P.sampler_kind == 0 ? P.ndims : 0;
+  if (P.mode == 1) {
+    if (s.cur1 < nd) {
+      uint32_t j = kensler_permute((uint32_t)s.sidx, (uint32_t)P.spp, hash_u32(fast_pixel, (uint32_t)s.cur1));
+      s.cur1++;
+      double delta = 0.5;
+      if (P.jitter) delta = rng_uniform(s);
+      return go_min(((double)j + delta) * (1.0 / (double)P.spp), one_minus_epsilon());
+    }
+    return rng_uniform(s);
+  }
+  if (s.cur1 < nd) {
+    double v = L.tables[((size_t)s.cur1 * P.spp + s.sidx) * L.n + s.lane];
+    s.cur1++;
+    return v;
+  }
+  return rng_uniform(s);
+}
+GP_D void get2d(Smp& s, const RenderParams& P, double* x, double* y) {
+  int nd = P.sampler_kind == 0 ? P.ndims : 0;
+  if (s.cur2 < nd) { s.cur2++; *x = 0; *y = 0; return; }  // StratifiedSample2D never writes its table
+  *x = rng_uniform(s);
+  *y = rng_uniform(s);
+}
+
+// Stratified.StartPixel (stratified.go:21-48)
+GP_D void start_pixel(Smp& s, const Lanes& L, const RenderParams& P) {
+  if (P.sampler_kind == 0 && P.mode == 0) {
+    int n = P.spp;
+    double inv = 1.0 / (double)n;
+    for (int d = 0; d < P.ndims; d++) {
+      double* tab = L.tables + (size_t)d * P.spp * L.n + s.lane;
+      for (int k = 0; k < n; k++) {  // StratifiedSample1D (sampling.go:101-110)
+        double delta = 0.5;
+        if (P.jitter) delta = rng_uniform(s);
+        tab[(size_t)k * L.n] = go_min(((double)k + delta) * inv, one_minus_epsilon());
+      }
+      for (int k = 0; k < n; k++) {  // ShuffleSamples1D (sampling.go:129-136)
+        int other = k + (int)rng_u32b(s, (uint32_t)(n - k));
+        double a = tab[(size_t)k * L.n], b = tab[(size_t)other * L.n];
+        tab[(size_t)k * L.n] = b;
+        tab[(size_t)other * L.n] = a;
+      }
+    }
+    for (int d = 0; d < P.ndims; d++) {
+      if (P.jitter)
+        for (int k = 0; k < n; k++) { rng_uniform(s); rng_uniform(s); }  // StratifiedSample2D draws, writes nothing
+      for (int k = 0; k < n; k++) rng_u32b(s, (uint32_t)(n - k));        // ShuffleSamples2D permutes zeros
+    }
+  }
+  s.sidx = 0;
+}
+
+// ---------------------------------------------------------------- sampling warps (pkg/pbrt/sampling.go)
+GP_D void concentric_sample_disk(double ux, double uy, double* ox, double* oy) {
+  double x = ux * 2.0 - 1, y = uy * 2.0 - 1;
+  if (x == 0 && y == 0) { *ox = 0; *oy = 0; return; }
+  double theta, r;
+  if (fabs(x) > fabs(y)) { r = x; theta = kPiOver4 * (y / x); }
+  else { r = y; theta = kPiOver2 - kPiOver4 * (x / y); }
+  *ox = go_cos(theta) * r;
+  *oy = go_sin(theta) * r;
+}
+GP_D V3 cosine_sample_hemisphere(double ux, double uy) {
+  double dx, dy;
+  concentric_sample_disk(ux, uy, &dx, &dy);
+  double z = sqrt(go_max(0.0, 1.0 - dx * dx - dy * dy));
+  return mk3(dx, dy, z);
+}
+GP_D V3 uniform_sample_sphere(double ux, double uy) {
+  double z = 1.0 - 2.0 * ux;
+  double r = sqrt(go_max(0, 1 - z * z));
+  double phi = 2 * kPi * uy;
+  return mk3(r * go_cos(phi), r * go_sin(phi), z);
+}
+
+// ---------------------------------------------------------------- spectrum helpers (pkg/pbrt/spectrum.go)
+struct RGB { double r, g, b; };
+GP_D RGB rgb(double r, double g, double b) { RGB c; c.r = r; c.g = g; c.b = b; return c; }
+GP_D RGB operator*(RGB a, RGB b) { return rgb(a.r * b.r, a.g * b.g, a.b * b.b); }
+GP_D RGB operator*(RGB a, double s) { return rgb(a.r * s, a.g * s, a.b * s); }
+GP_D RGB operator/(RGB a, double s) { return rgb(a.r / s, a.g / s, a.b / s); }
+GP_D RGB operator+(RGB a, RGB b) { return rgb(a.r + b.r, a.g + b.g, a.b + b.b); }
+GP_D bool is_black(RGB a) { return !(a.r != 0.0) && !(a.g != 0.0) && !(a.b != 0.0); }
+GP_D double max_comp(RGB a) { return go_max(go_max(a.r, a.g), a.b); }
+GP_D RGB clamp_rgb(RGB a, double lo, double hi) { return rgb(go_clamp(a.r, lo, hi), go_clamp(a.g, lo, hi), go_clamp(a.b, lo, hi)); }
+
+// ---------------------------------------------------------------- textures (texture.go, checkerboard.go)
+GP_D RGB tex_eval(const DevScene& sc, int id, const Hit& h) {
+  for (int guard = 0; guard < 64; guard++) {
+    const TextureDev& t = sc.textures[id];
+    if (t.kind == 0) return rgb(t.rgb[0], t.rgb[1], t.rgb[2]);
+    double s, tt;
+    if (t.mapping == 1) {  // PlanarMapping2D.Map (texture.go:42-46)
+      s = t.ds + dot(h.p, mk3(t.vs[0], t.vs[1], t.vs[2]));
+      tt = t.dt + dot(h.p, mk3(t.vt[0], t.vt[1], t.vt[2]));
+    } else {  // UVMapping2D.Map (texture.go:22-26)
+      s = t.su * h.u + t.du;
+      tt = t.sv * h.v + t.dv;
+    }
+    long long k = (long long)(floor(s) + floor(tt));  // checkerboard.go:32
+    id = (k % 2 == 0) ? t.tex1 : t.tex2;
+  }
+  return rgb(0, 0, 0);
+}
+
+// ---------------------------------------------------------------- BSDF (reflection.go)
+enum { BSDF_REFLECTION = 1, BSDF_TRANSMISSION = 2, BSDF_DIFFUSE = 4, BSDF_GLOSSY = 8, BSDF_SPECULAR = 16, BSDF_ALL = 31 };
+enum { BX_NONE = -1, BX_LAMBERT = 0, BX_OREN_NAYAR = 1, BX_SPEC_REFL_NOOP = 2, BX_FRESNEL_SPECULAR = 3 };
+// every material of the reference's working subset builds at most ONE BxDF (matte.go, mirror.go, glass.go:45-46)
+struct BSDF {
+  V3 ns, ng, ss, ts;
+  double eta;
+  int kind, type;
+  RGB r, t;
+  double a, b, etaB;
+};
+GP_D bool matches(int t, int flags) { return (t & flags) == t; }
+GP_D double fr_dielectric(double cosThetaI, double etaI, double etaT) {  // reflection.go:21-42
+  cosThetaI = go_clamp(cosThetaI, -1, 1);
+  bool entering = cosThetaI > 0;
+  if (!entering) { double t = etaI; etaI = etaT; etaT = t; cosThetaI = fabs(cosThetaI); }
+  double sinThetaI = sqrt(go_max(0, 1 - cosThetaI * cosThetaI));
+  double sinThetaT = etaI / etaT * sinThetaI;
+  if (sinThetaT >= 1) return 1;
+  double cosThetaT = sqrt(go_max(0, 1 - sinThetaT * sinThetaT));
+  double Rparl = ((etaT * cosThetaI) - (etaI * cosThetaT)) / ((etaT * cosThetaI) + (etaI * cosThetaT));
+  double Rperp = ((etaI * cosThetaI) - (etaT * cosThetaT)) / ((etaI * cosThetaI) + (etaT * cosThetaT));
+  return (Rparl * Rparl + Rperp * Rperp) / 2;
+}
+GP_D double sin2theta(V3 w) { return go_max(0, 1 - w.z * w.z); }
+GP_D double sintheta(V3 w) { return sqrt(sin2theta(w)); }
+GP_D double cosphi(V3 w) { double s = sintheta(w); return s == 0 ? 1 : go_clamp(w.x / s, -1, 1); }
+GP_D double sinphi(V3 w) { double s = sintheta(w); return s == 0 ? 0 : go_clamp(w.y / s, -1, 1); }
+
+GP_D RGB bxdf_f(const BSDF& b, V3 wo, V3 wi) {
+  if (b.kind == BX_LAMBERT) return b.r * kInvPi;  // reflection.go:589-591
+  if (b.kind == BX_OREN_NAYAR) {                   // reflection.go:628-652
+    double sinThetaI = sintheta(wi), sinThetaO = sintheta(wo);
+    double maxCos = 0.0;
+    if (sinThetaI > 1e-4 && sinThetaO > 1e-4) {
+      double sinPhiI = sinphi(wi), cosPhiI = cosphi(wi), sinPhiO = sinphi(wo), cosPhiO = cosphi(wo);
+      double dCos = cosPhiI * cosPhiO + sinPhiI * sinPhiO;
+      maxCos = go_max(0.0, dCos);
+    }
+    double sinAlpha, tanBeta;
+    if (fabs(wi.z) > fabs(wo.z)) { sinAlpha = sinThetaO; tanBeta = sinThetaO / fabs(wo.z); }
+    else { sinAlpha = sinThetaI; tanBeta = sinThetaO / fabs(wo.z); }
+    return b.r * (kInvPi * (b.a + b.b * maxCos * sinAlpha * tanBeta));
+  }
+  return rgb(0, 0, 0);
+}
+GP_D double bxdf_pdf(const BSDF& b, V3 wo, V3 wi) {
+  if (b.kind == BX_LAMBERT || b.kind == BX_OREN_NAYAR) {  // reflection.go:343-348
+    if (wo.z * wi.z > 0) return fabs(wi.z) * kInvPi;
+    return 0;
+  }
+  return 0;
+}
+GP_D V3 to_local(const BSDF& b, V3 v) { return mk3(dot(v, b.ss), dot(v, b.ts), dot(v, b.ns)); }
+
+// BSDF.F (reflection.go:164-181) / BSDF.Pdf (:255-278) for a single-BxDF BSDF
+GP_D RGB bsdf_f(const BSDF& b, V3 woW, V3 wiW, int flags) {
+  V3 wi = to_local(b, wiW), wo = to_local(b, woW);
+  if (wo.z == 0.0) return rgb(0, 0, 0);
+  bool reflect = dot(wiW, b.ng) * dot(woW, b.ng) > 0;
+  RGB f = rgb(0, 0, 0);
+  if (b.kind != BX_NONE && matches(b.type, flags) &&
+      ((reflect && (b.type & BSDF_REFLECTION) > 0) || (!reflect && (b.type & BSDF_TRANSMISSION) > 0)))
+    f = f + bxdf_f(b, wo, wi);
+  return f;
+}
+GP_D double bsdf_pdf(const BSDF& b, V3 woW, V3 wiW, int flags) {
+  if (b.kind == BX_NONE) return 0;
+  V3 wo = to_local(b, woW), wi = to_local(b, wiW);
+  if (wo.z == 0) return 0;
+  double pdf = 0;
+  int m = 0;
+  if (matches(b.type, flags)) { m++; pdf += bxdf_pdf(b, wo, wi); }
+  if (m <= 0) return 0;
+  return pdf / (double)m;
+}
+// BSDF.SampleF (reflection.go:183-253) with matchingComps in {0,1}: returns the LOCAL wi
+GP_D void bsdf_sample_f(const BSDF& b, V3 woWorld, double ux, double uy, int type, RGB* f, V3* wi, double* pdf, int* sampled) {
+  *f = rgb(0, 0, 0); *wi = mk3(0, 0, 0); *pdf = 0; *sampled = 0;
+  if (b.kind == BX_NONE || !matches(b.type, type)) return;
+  double comp = go_min(floor(ux * 1.0), 1.0 - 1);
+  double urx = go_min(ux * 1.0 - comp, one_minus_epsilon());
+  V3 wo = to_local(b, woWorld);
+  if (wo.z == 0.0) return;
+  RGB ff; V3 w; double p; int st = 0;
+  if (b.kind == BX_LAMBERT || b.kind == BX_OREN_NAYAR) {  // sampleF (reflection.go:305-314): sampledType 0
+    w = cosine_sample_hemisphere(urx, uy);
+    if (wo.z < 0) w.z *= -1;
+    p = bxdf_pdf(b, wo, w);
+    ff = bxdf_f(b, wo, w);
+  } else if (b.kind == BX_SPEC_REFL_NOOP) {  // reflection.go:557-562 + FresnelNoOp
+    w = mk3(-wo.x, -wo.y, wo.z);
+    p = 1.0;
+    ff = (rgb(1.0, 1.0, 1.0) * b.r) / fabs(w.z);
+  } else {  // FresnelSpecular.SampleF (reflection.go:482-523)
+    double F = fr_dielectric(wo.z, 1.0, b.etaB);
+    if (urx < F) {
+      w = mk3(-wo.x, -wo.y, wo.z);
+      ff = (b.r * F) / fabs(w.z);
+      p = F;
+      st = BSDF_SPECULAR | BSDF_REFLECTION;
+    } else {
+      bool entering = wo.z > 0;
+      double etaI = entering ? 1.0 : b.etaB, etaT = entering ? b.etaB : 1.0;
+      V3 n = faceforward(mk3(0, 0, 1), wo);  // Refract (reflection.go:106-118)
+      double eta = etaI / etaT;
+      double cosThetaI = dot(n, wo);
+      double sin2ThetaI = go_max(0, 1 - cosThetaI * cosThetaI);
+      double sin2ThetaT = eta * eta * sin2ThetaI;
+      if (sin2ThetaT >= 1) return;
+      double cosThetaT = sqrt(1 - sin2ThetaT);
+      w = wo * -eta + n * (eta * cosThetaI - cosThetaT);
+      RGB ft = b.t * (1 - F);
+      ft = ft * ((etaI * etaI) / (etaT / etaT));  // sic
+      ff = ft / fabs(w.z);
+      p = 1 - F;
+      st = BSDF_SPECULAR | BSDF_TRANSMISSION;
+    }
+  }
+  if (p == 0.0) return;
+  *f = ff; *wi = w; *pdf = p; *sampled = st;
+}
+
+// Material.ComputeScatteringFunctions (matte.go:21-37, mirror.go:21-32, glass.go:27-75) + NewBSDF (reflection.go:128-140)
+GP_D bool compute_scattering(const DevScene& sc, int prim, const Hit& h, BSDF* b) {
+  int mi = sc.prims[prim].z;
+  if (mi < 0) return false;  // primitive.go:73-75 panics
+  const MaterialDev& m = sc.materials[mi];
+  b->ns = h.ns; b->ng = h.n;
+  b->ss = normalized(h.sdpdu);
+  b->ts = cross(b->ns, b->ss);
+  b->kind = BX_NONE; b->type = 0; b->eta = 1.0; b->a = 0; b->b = 0; b->etaB = 1.0;
+  b->r = rgb(0, 0, 0); b->t = rgb(0, 0, 0);
+  if (m.kind == 0) {
+    RGB r = clamp_rgb(tex_eval(sc, m.tex_a, h), 0, d_inf());
+    double sig = go_clamp(m.sigma, 0, 90);
+    if (!is_black(r)) {
+      b->type = BSDF_REFLECTION | BSDF_DIFFUSE;
+      b->r = r;
+      if (sig == 0) b->kind = BX_LAMBERT;
+      else {  // NewOrenNayar (reflection.go:616-626)
+        b->kind = BX_OREN_NAYAR;
+        double s = kPi / 180.0 * sig;
+        double s2 = s * s;
+        b->a = 1.0 - (s2 / (2.0 * (s2 + 0.33)));
+        b->b = 0.45 * s2 / (s2 * 0.09);
+      }
+    }
+    return true;
+  }
+  if (m.kind == 1) {
+    RGB r = clamp_rgb(tex_eval(sc, m.tex_a, h), 0.0, d_inf());
+    if (!is_black(r)) { b->kind = BX_SPEC_REFL_NOOP; b->type = BSDF_REFLECTION | BSDF_DIFFUSE; b->r = r; }  // sic
+    return true;
+  }
+  if (m.kind == 2) {
+    b->eta = m.eta;
+    RGB R = clamp_rgb(tex_eval(sc, m.tex_a, h), 0, 1), T = clamp_rgb(tex_eval(sc, m.tex_b, h), 0, 1);
+    if (is_black(R) && is_black(T)) return true;
+    if (!(m.u_rough == 0 && m.v_rough == 0)) return false;  // microfacet branch: the reference panics
+    b->kind = BX_FRESNEL_SPECULAR;
+    b->type = BSDF_REFLECTION | BSDF_TRANSMISSION | BSDF_SPECULAR;
+    b->r = R; b->t = T; b->etaB = m.eta;
+    return true;
+  }
+  return false;
+}
+
+// ---------------------------------------------------------------- lights (pkg/lights, sphere.go:270-344, disk.go:160-170, shape.go:50-65)
+struct Intr { V3 p, perr, n; };
+GP_D void sphere_sample(const DevScene& sc, const SphereDev& s, double ux, double uy, Intr* it, double* pdf) {
+  M4 m = load_m4(sc, s.xf, false), inv = load_m4(sc, s.xf, true);
+  V3 pObj = uniform_sample_sphere(ux, uy) * s.radius;
+  V3 n = normalized(xf_normal_inv(inv, pObj));
+  if (s.flags & RF_REVERSE) n = n * -1.0;
+  pObj = pObj * (s.radius / sqrt(dist2(pObj, mk3(0, 0, 0))));
+  V3 pObjError = vabs(pObj) * gamma_n(5);
+  it->p = xf_point(m, pObj, pObjError, &it->perr);
+  it->n = n;
+  *pdf = 1.0 / (s.phiMax * s.radius * (s.zMax - s.zMin));
+}
+GP_D void sphere_sample_at(const DevScene& sc, const SphereDev& s, const Intr& ref, double ux, double uy, Intr* it, double* pdf) {
+  M4 m = load_m4(sc, s.xf, false);
+  V3 pCenter = xf_point(m, mk3(0, 0, 0), mk3(0, 0, 0), nullptr);
+  V3 pOrigin = offset_ray_origin(ref.p, ref.perr, ref.n, pCenter - ref.p);
+  if (dist2(pOrigin, pCenter) <= s.radius * s.radius) {
+    double p;
+    sphere_sample(sc, s, ux, uy, it, &p);
+    V3 wi = it->p - ref.p;
+    if (len2(wi) == 0) p = 0;
+    else {
+      wi = normalized(wi);
+      p *= dist2(ref.p, it->p) / fabs(dot(it->n, wi * -1.0));
+    }
+    if (is_inf(p)) p = 0.0;
+    *pdf = p;
+    return;
+  }
+  V3 wc = normalized(pCenter - ref.p);
+  V3 wcX, wcY;
+  coordinate_system(wc, &wcX, &wcY);
+  double radius2 = s.radius * s.radius;
+  double sinThetaMax2 = radius2 / dist2(ref.p, pCenter);
+  double cosThetaMax = sqrt(go_max(0, 1.0 - sinThetaMax2));
+  double cosTheta = (1.0 - ux) + ux * cosThetaMax;
+  double sinTheta = sqrt(go_max(0, 1 - cosTheta * cosTheta));
+  double phi = uy * 2 * kPi;
+  double dc = sqrt(dist2(ref.p, pCenter));
+  double ds = dc * cosTheta - sqrt(go_max(0, radius2 - (dc * dc) * (sinTheta * sinTheta)));
+  double cosAlpha = (dc * dc + radius2 - ds * ds) / (2.0 * dc * s.radius);
+  double sinAlpha = sqrt(go_max(0, 1.0 - cosAlpha * cosAlpha));
+  V3 x = wcX * -1.0, y = wcY * -1.0, z = wc * -1.0;
+  V3 nWorld = x * (sinAlpha * go_cos(phi)) + y * (sinAlpha * go_sin(phi)) + z * cosAlpha;  // geometry.go:66-70
+  V3 pWorld = pCenter + nWorld * s.radius;
+  it->p = pWorld;
+  it->perr = vabs(pWorld) * gamma_n(5.0);
+  it->n = nWorld;
+  if (s.flags & RF_REVERSE) it->n = it->n * -1.0;
+  *pdf = 1.0 / (2.0 * kPi * (1.0 - cosThetaMax));  // UniformConePdf (sampling.go:169-171)
+}
+GP_D void disk_sample_at(const DevScene& sc, const DiskDev& d, const Intr& ref, double ux, double uy, Intr* it, double* pdf) {
+  M4 m = load_m4(sc, d.xf, false), inv = load_m4(sc, d.xf, true);
+  double px, py;
+  concentric_sample_disk(ux, uy, &px, &py);
+  V3 pObj = mk3(px * d.radius, py * d.radius, d.height);
+  V3 n = xf_normal_inv(inv, mk3(0, 0, 1));
+  if (d.flags & RF_REVERSE) n = n * -1.0;
+  it->n = n;
+  it->p = xf_point(m, pObj, mk3(0, 0, 0), &it->perr);
+  double p = 1 / (d.phiMax * 0.5 * (d.radius * d.radius - d.innerRadius * d.innerRadius));
+  V3 wi = it->p - ref.p;
+  if (len2(wi) == 0.0) { *pdf = 0; return; }
+  wi = normalized(wi);
+  p *= dist2(ref.p, it->p) / fabs(dot(it->n, wi * -1.0));
+  if (is_inf(p)) p = 0;
+  *pdf = p;
+}
+
+struct LightSample { RGB Li; V3 wi; double pdf; Intr p1; bool delta; };
+// Point.SampleLi (point.go:44-49), Distant.SampleLi (distant.go:40-44), DiffuseAreaLight.SampleLi (diffuse.go:47-59)
+GP_D void light_sample_li(const DevScene& sc, const LightDev& l, const Intr& ref, double ux, double uy, LightSample* ls) {
+  RGB E = rgb(l.rgb[0], l.rgb[1], l.rgb[2]);
+  V3 v = mk3(l.v[0], l.v[1], l.v[2]);
+  V3 zero = mk3(0, 0, 0);
+  if (l.kind == 1) {
+    ls->wi = normalized(v - ref.p);
+    ls->pdf = 1.0;
+    ls->p1.p = v; ls->p1.perr = zero; ls->p1.n = zero;
+    ls->Li = E / dist2(v, ref.p);
+    ls->delta = true;
+  } else if (l.kind == 0) {
+    ls->p1.p = v * (2 * sc.world_radius); ls->p1.perr = zero; ls->p1.n = zero;  // sic: a fixed point
+    ls->Li = E; ls->wi = v; ls->pdf = 1; ls->delta = true;
+  } else {
+    ls->delta = false;
+    Intr ps;
+    double pdf;
+    if (l.shape_kind == RK_SPHERE) sphere_sample_at(sc, sc.spheres[l.shape_index], ref, ux, uy, &ps, &pdf);
+    else disk_sample_at(sc, sc.disks[l.shape_index], ref, ux, uy, &ps, &pdf);
+    if (pdf == 0 || len2(ps.p - ref.p) == 0) { ls->Li = rgb(0, 0, 0); ls->wi = zero; ls->pdf = 0; ls->p1 = ps; return; }
+    ls->wi = ps.p - ref.p;  // un-normalised (diffuse.go:55)
+    ls->p1 = ps;
+    ls->pdf = pdf;
+    V3 w = ls->wi * -1.0;
+    ls->Li = (l.two_sided || dot(ps.n, w) > 0) ? E : rgb(0, 0, 0);
+  }
+}
+
+// ---------------------------------------------------------------- film geometry (film.go:106-113)
+GP_D void tile_bounds(const RenderParams& P, long long tile, long long* x0, long long* y0, long long* x1, long long* y1) {
+  long long tx = tile % P.ntx, ty = tile / P.ntx;
+  *x0 = P.cx0 + tx * P.tile_size;
+  *x1 = (long long)go_min((double)(*x0 + P.tile_size), (double)P.cx1);  // integrator.go:322-325
+  *y0 = P.cy0 + ty * P.tile_size;
+  *y1 = (long long)go_min((double)(*y0 + P.tile_size), (double)P.cy1);
+}
+GP_D void tile_pixel_bounds(const RenderParams& P, long long x0, long long y0, long long x1, long long y1, long long* px0, long long* py0,
+                            long long* px1, long long* py1) {
+  long long a = (long long)ceil((double)x0 - 0.5 - P.frx), b = (long long)ceil((double)y0 - 0.5 - P.fry);
+  long long c = (long long)floor((double)x1 - 0.5 + P.frx) + 1, d = (long long)floor((double)y1 - 0.5 + P.fry) + 1;
+  *px0 = a > P.cx0 ? a : P.cx0; *py0 = b > P.cy0 ? b : P.cy0;
+  *px1 = c < P.cx1 ? c : P.cx1; *py1 = d < P.cy1 ? d : P.cy1;
+}
+
+// FilmTile.AddSample (film.go:211-248) with the box filter table (all ones, filter.go:30-32), sampleWeight 1
+GP_D void film_add_sample(const Lanes& L, const RenderParams& P, long long lane, long long tile, double fx, double fy, RGB Lc) {
+  long long x0, y0, x1, y1, bx0, by0, bx1, by1;
+  tile_bounds(P, tile, &x0, &y0, &x1, &y1);
+  tile_pixel_bounds(P, x0, y0, x1, y1, &bx0, &by0, &bx1, &by1);
+  double dx = fx - 0.5, dy = fy - 0.5;
+  double p0fx = ceil(dx - P.frx), p0fy = ceil(dy - P.fry);
+  double p1fx = floor(dx + P.frx) + 1, p1fy = floor(dy + P.fry) + 1;
+  long long p0x = (long long)go_max(p0fx, (double)bx0), p0y = (long long)go_max(p0fy, (double)by0);
+  long long p1x = (long long)go_min(p1fx, (double)bx1), p1y = (long long)go_min(p1fy, (double)by1);
+  for (long long y = p0y; y < p1y; y++)
+    for (long long x = p0x; x < p1x; x++) {
+      double fw = 1.0;
+      size_t k = (size_t)((y - by0) * P.tpw + (x - bx0)) * 4;
+      double* q = L.tilepix + k * L.n + lane;
+      RGB c = Lc * (1.0 * fw);
+      q[0] += c.r;
+      q[(size_t)L.n] += c.g;
+      q[2 * (size_t)L.n] += c.b;
+      q[3 * (size_t)L.n] += fw;
+    }
+}
+
+// ---------------------------------------------------------------- raygen + sampler
+// Retires the lane's finished sample into its film tile (renderWorker, integrator.go:252-265), advances the sampler
+// (StartNextSample / next pixel + StartPixel) and generates the next camera ray (GenerateRayDifferential,
+// camera.go:192-242; the differentials are dropped by Path.Li).  Lanes whose tile is exhausted leave the wavefront.
+__global__ void __launch_bounds__(128) k_generate(DevScene sc, Lanes L, RenderParams P, Queues Q, const int* __restrict__ in_queue,
+                                                  const int* __restrict__ in_count, RenderCounters* ctr) {
+  long long n = in_queue ? (long long)*in_count : P.lanes_active;
+  int lane_id = threadIdx.x & 31;
+  unsigned long long cam = 0, nans = 0;
+  long long warp_base0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) - lane_id;
+  for (long long base = warp_base0; base < n; base += (long long)gridDim.x * blockDim.x) {
+    long long i = base + lane_id;
+    bool valid = i < n;
+    bool go = false;
+    long long lane = 0;
+    if (valid) {
+      lane = in_queue ? in_queue[i] : i;
+      long long tile = (P.lane_base + lane) * P.world + P.rank;
+      if (L.has_sample[lane]) {
+        RGB Lc = rgb(L.Lr[lane], L.Lg[lane], L.Lb[lane]);
+        if (is_nan(Lc.r) || is_nan(Lc.g) || is_nan(Lc.b)) { Lc = rgb(0.1, 0.1, 0.1); nans++; }  // integrator.go:256-257
+        film_add_sample(L, P, lane, tile, L.fx[lane], L.fy[lane], Lc);
+        L.has_sample[lane] = 0;
+      }
+      Smp s;
+      s.state = L.rng_state[lane]; s.inc = L.rng_inc[lane]; s.sidx = L.sidx[lane]; s.cur1 = 0; s.cur2 = 0; s.lane = lane;
+      int pix = L.pix[lane];
+      long long x0, y0, x1, y1;
+      tile_bounds(P, tile, &x0, &y0, &x1, &y1);
+      long long tw = x1 - x0, area = tw * (y1 - y0);
+      bool have = false;
+      for (;;) {
+        if (pix >= 0) {
+          // PixelSampler.StartNextSample (pixel.go:48-52) + Sampler.StartNextSample (sampler.go:29-34): increments first
+          s.cur1 = 0; s.cur2 = 0;
+          s.sidx += 1;
+          if (s.sidx < P.spp) {
+            if (P.s_world > 1 && (s.sidx % P.s_world) != P.s_rank) continue;  // FAST: samples split by index
+            have = true;
+            break;
+          }
+        }
+        pix++;
+        if (pix >= area) break;
+        start_pixel(s, L, P);
+      }
+      if (have) {
+        long long px = x0 + pix % tw, py = y0 + pix / tw;
+        unsigned long long fast_pixel = (unsigned long long)((py - P.cy0) * (P.cx1 - P.cx0) + (px - P.cx0));
+        if (P.mode == 1) rng_set_sequence(s, fast_pixel * (unsigned long long)P.spp + (unsigned long long)s.sidx);
+        // GetCameraSample (sampler.go:75-80): Get2D pFilm, Get2D pLens, Get1D time
+        double ox, oy, lx, ly;
+        get2d(s, P, &ox, &oy);
+        double fx = (double)px + ox, fy = (double)py + oy;
+        get2d(s, P, &lx, &ly);
+        double time = get1d(s, L, P, fast_pixel);
+        V3 pCamera = xf_point(P.raster_to_camera, mk3(fx, fy, 0), mk3(0, 0, 0), nullptr);
+        Ray ray;
+        ray.o = mk3(0, 0, 0);
+        ray.d = normalized(pCamera);
+        ray.tmax = d_inf();
+        if (P.lens_radius > 0) {
+          double plx, ply;
+          concentric_sample_disk(lx, ly, &plx, &ply);
+          plx *= P.lens_radius; ply *= P.lens_radius;
+          double ft = P.focal_distance / ray.d.z;
+          V3 pFocus = ray.d * ft + ray.o;
+          ray.o = mk3(plx, ply, 0);
+          ray.d = normalized(pFocus - ray.o);
+        }
+        ray = xf_ray(P.camera_to_world, ray, nullptr, nullptr);
+        (void)time;  // ray.Time = Lerp(time, open, open): unused without animated transforms
+        L.ray.ox[lane] = ray.o.x; L.ray.oy[lane] = ray.o.y; L.ray.oz[lane] = ray.o.z;
+        L.ray.dx[lane] = ray.d.x; L.ray.dy[lane] = ray.d.y; L.ray.dz[lane] = ray.d.z;
+        L.ray.tmax[lane] = d_inf();
+        L.fx[lane] = fx; L.fy[lane] = fy;
+        L.Lr[lane] = 0; L.Lg[lane] = 0; L.Lb[lane] = 0;
+        L.br[lane] = 1.0; L.bg[lane] = 1.0; L.bb[lane] = 1.0;
+        L.eta_scale[lane] = 1.0;
+        L.bounces[lane] = (s.cur1 << 8) | (s.cur2 << 16);  // bounces in bits 0-7, sampler dimensions above
+        cam++;
+        go = true;
+      }
+      L.rng_state[lane] = s.state; L.rng_inc[lane] = s.inc; L.sidx[lane] = s.sidx; L.pix[lane] = pix;
+    }
+    queue_push(Q.extend, Q.cnt + 0, go, (int)lane);
+  }
+  cam = warp_sum(cam); nans = warp_sum(nans);
+  if (lane_id == 0) {
+    if (cam) atomicAdd(&ctr->camera_rays, cam);
+    if (nans) atomicAdd(&ctr->nan_samples, nans);
+  }
+}
+
+// ---------------------------------------------------------------- shade
+// One Path.Li loop body per lane (path.go:40-155) after the closest-hit query: scattering functions, one light
+// sample (UniformSampleOneLight / EstimateDirect) whose visibility test is deferred to the shadow queue, BSDF
+// sampling, throughput update, SpawnRay, Russian roulette.
+__global__ void __launch_bounds__(128) k_shade(DevScene sc, Lanes L, RenderParams P, Queues Q, RenderCounters* ctr) {
+  long long n = Q.cnt[0];
+  int lane_id = threadIdx.x & 31;
+  unsigned long long n_unsupported = 0, n_dead = 0;
+  int bad = 0;
+  long long warp_base0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) - lane_id;
+  for (long long base = warp_base0; base < n; base += (long long)gridDim.x * blockDim.x) {
+    long long i = base + lane_id;
+    bool valid = i < n;
+    bool cont = false, finished = false, shadow = false;
+    long long lane = 0;
+    if (valid) {
+      lane = Q.extend[i];
+      int packed = L.bounces[lane];
+      int bounces = (packed & 255) + 1;  // bounces++ (path.go:41)
+      int rec = L.hit_rec[lane];
+      finished = true;
+      if (rec >= 0 && bounces < P.max_depth) {  // path.go:66
+        Ray ray;
+        ray.o = mk3(L.ray.ox[lane], L.ray.oy[lane], L.ray.oz[lane]);
+        ray.d = mk3(L.ray.dx[lane], L.ray.dy[lane], L.ray.dz[lane]);
+        ray.tmax = L.ray.tmax[lane];
+        Hit h;
+        int prim;
+        hit_record(sc, rec, ray, ray.tmax, &h, &prim, bad);
+        BSDF bsdf;
+        if (!compute_scattering(sc, prim, h, &bsdf)) {
+          n_unsupported++;
+        } else {
+          Smp s;
+          s.state = L.rng_state[lane]; s.inc = L.rng_inc[lane]; s.sidx = L.sidx[lane];
+          s.cur1 = (packed >> 8) & 255; s.cur2 = (packed >> 16) & 255; s.lane = lane;
+          unsigned long long fast_pixel = 0;
+          if (P.mode == 1) {
+            long long tile = (P.lane_base + lane) * P.world + P.rank;
+            long long x0, y0, x1, y1;
+            tile_bounds(P, tile, &x0, &y0, &x1, &y1);
+            int pix = L.pix[lane];
+            long long px = x0 + pix % (x1 - x0), py = y0 + pix / (x1 - x0);
+            fast_pixel = (unsigned long long)((py - P.cy0) * (P.cx1 - P.cx0) + (px - P.cx0));
+          }
+          RGB beta = rgb(L.br[lane], L.bg[lane], L.bb[lane]);
+          Intr ref; ref.p = h.p; ref.perr = h.perr; ref.n = h.n;
+          // --- UniformSampleOneLight (integrator.go:48-77), skipped for perfectly specular BSDFs (path.go:84)
+          if (bsdf.kind != BX_NONE && matches(bsdf.type, BSDF_ALL & ~BSDF_SPECULAR)) {
+            if (sc.n_lights > 0) {
+              double u = get1d(s, L, P, fast_pixel);
+              // Distribution1D.SampleDiscrete (sampling.go:42-55) via FindInterval (pkg/math/math.go:64-80)
+              int size = sc.n_lights + 1, first = 0, len = size;
+              while (len > 0) {
+                int half = len >> 1, middle = first + half;
+                if (sc.light_cdf[middle] <= u) { first = middle + 1; len -= half + 1; }
+                else len = half;
+              }
+              int offset = (int)go_clamp((double)(first - 1), 0, (double)(size - 2));
+              double lightPdf = 0;
+              if (sc.light_func_int > 0) lightPdf = 1.0 / (sc.light_func_int / (double)sc.n_lights);
+              if (lightPdf != 0.0) {
+                double ulx, uly, usx, usy;
+                get2d(s, P, &ulx, &uly);
+                get2d(s, P, &usx, &usy);  // uScattering: drawn, used only by the dead MIS branch
+                // --- EstimateDirect (integrator.go:79-195), handleMedia = false, specular = false
+                const int flags = BSDF_ALL & ~BSDF_SPECULAR;
+                LightSample ls;
+                light_sample_li(sc, sc.lights[offset], ref, ulx, uly, &ls);
+                if (!ls.delta) n_dead++;
+                if (ls.pdf > 0 && !is_black(ls.Li)) {
+                  RGB f = bsdf_f(bsdf, h.wo, ls.wi, flags);
+                  f = f * fabs(dot(ls.wi, h.ns));
+                  double scatteringPdf = bsdf_pdf(bsdf, h.wo, ls.wi, flags);
+                  if (!is_black(f)) {
+                    RGB Ld;
+                    if (ls.delta) Ld = (f * ls.Li) / ls.pdf;
+                    else {
+                      double ff = 1.0 * ls.pdf, gg = 1.0 * scatteringPdf;  // PowerHeuristic (sampling.go:208-212)
+                      double weight = (ff * ff) / (ff * ff + gg * gg);
+                      Ld = ((f * ls.Li) * weight) / ls.pdf;
+                    }
+                    Ld = rgb(0, 0, 0) + Ld;  // Ld.AddAssign on a zero spectrum (integrator.go:123-126)
+                    // VisibilityTester.Unoccluded -> SpawnRayToInteraction (interaction.go:91-102)
+                    V3 origin = offset_ray_origin(ref.p, ref.perr, ref.n, ls.p1.p - ref.p);
+                    V3 target = offset_ray_origin(ls.p1.p, ls.p1.perr, ls.p1.n, origin - ls.p1.p);
+                    V3 d = target - origin;
+                    L.sray.ox[lane] = ref.p.x; L.sray.oy[lane] = ref.p.y; L.sray.oz[lane] = ref.p.z;
+                    L.sray.dx[lane] = d.x; L.sray.dy[lane] = d.y; L.sray.dz[lane] = d.z;
+                    L.sray.tmax[lane] = 1 - 0.0001;
+                    RGB c = beta * Ld;  // Ld := beta.Mul(...) (path.go:85)
+                    L.pr[lane] = c.r; L.pg[lane] = c.g; L.pb[lane] = c.b;
+                    L.pend_gt10[lane] = max_comp(Ld) > 10 ? 1 : 0;  // integrator.go:73-75 panics; counted when unoccluded
+                    shadow = true;
+                  }
+                }
+              }
+            }
+            if (!shadow) {
+              // L.AddAssign(beta.Mul(0)) (path.go:85-86): a no-op unless beta is not finite (0*Inf = NaN), kept for parity
+              RGB z = beta * rgb(0, 0, 0);
+              L.Lr[lane] += z.r; L.Lg[lane] += z.g; L.Lb[lane] += z.b;
+            }
+          }
+          // --- sample the BSDF for the next direction (path.go:90-117); wo = ray.Direction, sic
+          double ux, uy;
+          get2d(s, P, &ux, &uy);
+          RGB f; V3 wi; double pdf; int sflags;
+          bsdf_sample_f(bsdf, ray.d, ux, uy, BSDF_ALL, &f, &wi, &pdf, &sflags);
+          if (!(is_black(f) || pdf == 0.0)) {
+            double wiAbsDotPdf = fabs(dot(wi, h.ns)) / pdf;
+            beta = beta * (f * wiAbsDotPdf);
+            double etaScale = L.eta_scale[lane];
+            if ((sflags & BSDF_SPECULAR) > 0 && (sflags & BSDF_TRANSMISSION) > 0) {
+              double eta = bsdf.eta;
+              if (dot(ray.d, h.n) > 0) etaScale *= eta * eta;
+              else etaScale *= 1 / (eta * eta);
+              L.eta_scale[lane] = etaScale;
+            }
+            V3 o = offset_ray_origin(h.p, h.perr, h.n, wi);  // SpawnRay (interaction.go:68-77); wi is BSDF-local
+            bool alive = true;
+            RGB rrBeta = beta * etaScale;
+            if (max_comp(rrBeta) < P.rr_threshold && bounces > 3) {  // path.go:145-153
+              double q = go_max(0.05, 1 - max_comp(rrBeta));
+              if (get1d(s, L, P, fast_pixel) < q) alive = false;
+              else beta = beta / (1 - q);
+            }
+            if (alive) {
+              L.ray.ox[lane] = o.x; L.ray.oy[lane] = o.y; L.ray.oz[lane] = o.z;
+              L.ray.dx[lane] = wi.x; L.ray.dy[lane] = wi.y; L.ray.dz[lane] = wi.z;
+              L.ray.tmax[lane] = d_inf();
+              L.br[lane] = beta.r; L.bg[lane] = beta.g; L.bb[lane] = beta.b;
+              cont = true;
+              finished = false;
+            }
+          }
+          L.rng_state[lane] = s.state; L.rng_inc[lane] = s.inc;
+          packed = (s.cur1 << 8) | (s.cur2 << 16);
+        }
+      }
+      L.bounces[lane] = (packed & ~255) | bounces;
+      if (finished) L.has_sample[lane] = 1;
+    }
+    queue_push(Q.shadow, Q.cnt + 2, shadow, (int)lane);
+    queue_push(Q.extend_next, Q.cnt + 1, cont, (int)lane);
+    queue_push(Q.regen_next, Q.cnt + 4, finished && valid, (int)lane);
+  }
+  n_unsupported = warp_sum(n_unsupported); n_dead = warp_sum(n_dead);
+  if (lane_id == 0) {
+    if (n_unsupported) atomicAdd(&ctr->unsupported, n_unsupported);
+    if (n_dead) atomicAdd(&ctr->dead_mis_rays, n_dead);
+  }
+  if (bad) atomicAdd(&ctr->efloat_panics, 1ULL);
+}
+
+// adds the deferred light sample of every unoccluded shadow ray to its lane's radiance (L.AddAssign(Ld), path.go:86)
+__global__ void k_shadow_resolve(Lanes L, Queues Q, RenderCounters* ctr) {
+  long long n = Q.cnt[2];
+  unsigned long long gt10 = 0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    int lane = Q.shadow[i];
+    if (!L.occluded[lane]) {
+      L.Lr[lane] += L.pr[lane]; L.Lg[lane] += L.pg[lane]; L.Lb[lane] += L.pb[lane];
+      if (L.pend_gt10[lane]) gt10++;
+    } else {  // blocked: Li = 0, so L += beta*0 (NaN only if beta is not finite)
+      L.Lr[lane] += L.pr[lane] * 0.0; L.Lg[lane] += L.pg[lane] * 0.0; L.Lb[lane] += L.pb[lane] * 0.0;
+    }
+  }
+  if (gt10) atomicAdd(&ctr->radiance_gt10, gt10);
+}
+
+// end of a wavefront iteration: rotate the queues on the device and publish the number of lanes still in flight
+__global__ void k_advance(Queues Q, RenderCounters* ctr, int* host_visible_remaining) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    ctr->closest_rays += (unsigned long long)Q.cnt[0];
+    ctr->shadow_rays += (unsigned long long)Q.cnt[2];
+    Q.cnt[0] = Q.cnt[1];  // extend <- extend_next (the host swaps the pointers)
+    Q.cnt[1] = 0;
+    Q.cnt[2] = 0;
+    Q.cnt[3] = Q.cnt[4];  // regen <- regen_next
+    Q.cnt[4] = 0;
+    *host_visible_remaining = Q.cnt[0] + Q.cnt[3];
+  }
+}
+
+// Film.MergeFilmTile (film.go:115-132): every film pixel gathers the tiles that cover it in ascending tile order
+// (the order a single renderWorker would merge them), converting each tile's RGB sum to XYZ first (spectrum.go:35-41).
+__global__ void k_film_merge(Lanes L, RenderParams P, double* __restrict__ film) {
+  long long fw = P.cx1 - P.cx0, fh = P.cy1 - P.cy0;
+  long long npx = fw * fh;
+  long long ext = (long long)ceil(P.frx > P.fry ? P.frx : P.fry) + 1;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < npx; i += (long long)gridDim.x * blockDim.x) {
+    long long x = P.cx0 + i % fw, y = P.cy0 + i / fw;
+    double X = film[i * 4], Y = film[i * 4 + 1], Z = film[i * 4 + 2], W = film[i * 4 + 3];
+    long long ty0 = (y - ext - P.cy0) / P.tile_size, ty1 = (y + ext - P.cy0) / P.tile_size;
+    long long tx0 = (x - ext - P.cx0) / P.tile_size, tx1 = (x + ext - P.cx0) / P.tile_size;
+    if (ty0 < 0) ty0 = 0; if (tx0 < 0) tx0 = 0;
+    if (ty1 >= P.nty) ty1 = P.nty - 1; if (tx1 >= P.ntx) tx1 = P.ntx - 1;
+    for (long long ty = ty0; ty <= ty1; ty++)
+      for (long long tx = tx0; tx <= tx1; tx++) {
+        long long tile = ty * P.ntx + tx;
+        if (tile % P.world != P.rank) continue;
+        long long lane = tile / P.world - P.lane_base;
+        if (lane < 0 || lane >= P.lanes_active) continue;
+        long long x0, y0, x1, y1, bx0, by0, bx1, by1;
+        tile_bounds(P, tile, &x0, &y0, &x1, &y1);
+        tile_pixel_bounds(P, x0, y0, x1, y1, &bx0, &by0, &bx1, &by1);
+        if (x < bx0 || x >= bx1 || y < by0 || y >= by1) continue;
+        size_t k = (size_t)((y - by0) * P.tpw + (x - bx0)) * 4;
+        const double* q = L.tilepix + k * L.n + lane;
+        double r = q[0], g = q[(size_t)L.n], b = q[2 * (size_t)L.n], w = q[3 * (size_t)L.n];
+        X += 0.412453 * r + 0.357580 * g + 0.180423 * b;
+        Y += 0.212671 * r + 0.715160 * g + 0.072169 * b;
+        Z += 0.019334 * r + 0.119193 * g + 0.950227 * b;
+        W += w;
+      }
+    film[i * 4] = X; film[i * 4 + 1] = Y; film[i * 4 + 2] = Z; film[i * 4 + 3] = W;
+  }
+}
+
+// pass start: reset per-lane sampler state (Sampler.Clone(seed = tile index), pixel.go:34-42) and tile accumulators
+__global__ void k_init_lanes(Lanes L, RenderParams P) {
+  for (long long lane = (long long)blockIdx.x * blockDim.x + threadIdx.x; lane < P.lanes_active; lane += (long long)gridDim.x * blockDim.x) {
+    long long tile = (P.lane_base + lane) * P.world + P.rank;
+    Smp s;
+    s.state = 0x853c49e6748fea9bULL; s.inc = 0xda3e39cb94b95bdbULL;
+    rng_set_sequence(s, (unsigned long long)tile);
+    L.rng_state[lane] = s.state; L.rng_inc[lane] = s.inc;
+    L.pix[lane] = -1; L.sidx[lane] = 0; L.has_sample[lane] = 0; L.bounces[lane] = 0;
+  }
+}
+
+}  // namespace gp

@@ -1,0 +1,332 @@
+// gp_scene.cuh — device-resident scene layout and the shape routines of the hot path.
+//
+// HBM layout (uploaded once by gopbrt_scene_create):
+//   nodes      float4[2*N]   32-byte BVH nodes: {min.xyz (f32, rounded down), a}, {max.xyz (f32, rounded up), b}
+//                            interior: a = second child, b = axis;  leaf: a = first record, b = nPrims<<8 | axis
+//                            (same information as LinearBVHNode, pkg/accelerator/bvh.go:80-87; first child = n+1)
+//   recs       80-byte primitive records in LEAF order: {u32 kind|flags, u32 primitive id, double d[9]}
+//                            sphere (translation-only transforms): d = radius, w2o translation, p2w^-1 translation
+//                            triangle: d = p0, p1, p2 (world space);  anything else: looked up through prims/shape tables
+//   rec_bounds double[6] per record: the primitive's own float64 world bound (spheres/disks) for the parity-spec
+//                            candidate test; triangles derive it from their vertices
+//   prims      int4 per primitive id: {shape kind, shape index, material, prim_to_world transform or -1}
+//   xf         32 doubles per transform (m, minv) + flags;  sphere/disk/material/texture/light tables
+#pragma once
+#include "gp_math.cuh"
+
+namespace gp {
+
+enum : uint32_t {
+  RK_SPHERE = 0, RK_DISK = 1, RK_TRIANGLE = 2, RK_KIND_MASK = 3,
+  RF_FAST = 4,        // record carries everything the intersection needs (translation-only sphere / triangle)
+  RF_HAS_P2W = 8,     // wrapped in a TransformedPrimitive
+  RF_REVERSE = 16,    // reverseOrientation
+  RF_FULL = 32,       // full sphere / full disk: the clip test can never fire (phiMax == 2Pi exactly, zMin == -r, zMax == r)
+  RF_P2W_IDENTITY = 64
+};
+enum : int { XF_TRANSLATION = 1, XF_IDENTITY = 2 };
+
+struct __align__(16) PrimRec {
+  uint32_t flags;
+  uint32_t prim;
+  double d[9];
+};
+static_assert(sizeof(PrimRec) == 80, "PrimRec must be 80 bytes");
+
+struct SphereDev { double radius, zMin, zMax, thetaMin, thetaMax, phiMax; int xf; int flags; };
+struct DiskDev { double height, radius, innerRadius, phiMax; int xf; int flags; };
+struct MaterialDev { int kind, tex_a, tex_b, pad; double sigma, eta, u_rough, v_rough; };
+struct TextureDev { int kind, mapping, tex1, tex2; double rgb[3], vs[3], vt[3], ds, dt, su, sv, du, dv; };
+struct LightDev { int kind, shape_kind, shape_index, two_sided; double rgb[3], v[3]; };
+
+struct DevScene {
+  const float4* nodes;
+  const PrimRec* recs;
+  const double* rec_bounds;
+  const int4* prims;
+  const double* xf;        // 32 doubles each
+  const int* xf_flags;
+  const SphereDev* spheres;
+  const DiskDev* disks;
+  const MaterialDev* materials;
+  const TextureDev* textures;
+  const LightDev* lights;
+  const double* light_cdf;
+  int n_lights;
+  double light_func_int;
+  double world_radius;     // Distant.Preprocess (distant.go:36-38)
+  int n_nodes;
+};
+
+// load a transform's Matrix (inv=false) or MatrixInverse (inv=true) into registers.  Translation-only transforms are
+// synthesised from their three translation entries with literal 1.0 / 0.0 so the arithmetic below is the very same
+// sequence of IEEE operations as the general case (0*y terms are kept: they matter for NaN/Inf and signed zeros).
+GP_D M4 load_m4(const DevScene& sc, int xf, bool inv) {
+  const double* b = sc.xf + (size_t)xf * 32 + (inv ? 16 : 0);
+  M4 r;
+  if (sc.xf_flags[xf] & XF_TRANSLATION) {
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+      for (int j = 0; j < 4; j++) r.m[i][j] = (i == j) ? 1.0 : 0.0;
+    r.m[0][3] = b[3]; r.m[1][3] = b[7]; r.m[2][3] = b[11];
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+      for (int j = 0; j < 4; j++) r.m[i][j] = b[i * 4 + j];
+  }
+  return r;
+}
+GP_HD M4 translation_m4(double x, double y, double z) {
+  M4 r;
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+#pragma unroll
+    for (int j = 0; j < 4; j++) r.m[i][j] = (i == j) ? 1.0 : 0.0;
+  r.m[0][3] = x; r.m[1][3] = y; r.m[2][3] = z;
+  return r;
+}
+
+// ---- Sphere.Intersect / IntersectP root finding (sphere.go:64-95,190-218) on the OBJECT-space ray ----
+// returns false on miss; on success *t0/*t1 are the interval roots and *tsel the selected root value, *sel1 whether
+// the selected root is t1 (the reference compares pointers).
+GP_HD bool sphere_roots(const Ray& ray, V3 oe, V3 de, double radius, EF* t0, EF* t1, int& bad) {
+  EF ox = ef_new(ray.o.x, oe.x, bad), oy = ef_new(ray.o.y, oe.y, bad), oz = ef_new(ray.o.z, oe.z, bad);
+  EF dx = ef_new(ray.d.x, de.x, bad), dy = ef_new(ray.d.y, de.y, bad), dz = ef_new(ray.d.z, de.z, bad);
+  EF a = ef_add(ef_add(ef_mul(dx, dx, bad), ef_mul(dy, dy, bad), bad), ef_mul(dz, dz, bad), bad);
+  EF b = ef_muls(ef_add(ef_add(ef_mul(dx, ox, bad), ef_mul(dy, oy, bad), bad), ef_mul(dz, oz, bad), bad), 2.0, bad);
+  EF c = ef_sub(ef_add(ef_add(ef_mul(ox, ox, bad), ef_mul(oy, oy, bad), bad), ef_mul(oz, oz, bad), bad),
+                ef_muls(ef_new(radius, 0, bad), radius, bad), bad);
+  return ef_quadratic(a, b, c, t0, t1, bad);
+}
+GP_HD V3 sphere_refine(const Ray& ray, double t, double radius) {  // sphere.go:98-104
+  V3 pHit = ray.o + ray.d * t;
+  pHit = pHit * (radius / sqrt(dist2(pHit, mk3(0, 0, 0))));
+  if (pHit.x == 0.0 && pHit.y == 0.0) pHit.x = 1e-5 * radius;
+  return pHit;
+}
+GP_HD double phi_of(V3 pHit) {
+  double phi = go_atan2(pHit.y, pHit.x);
+  if (phi < 0.0) phi += 2 * kPi;
+  return phi;
+}
+// full root selection incl. the clip test.  which: 0 = t0 selected directly, 1 = t1 because t0.lo <= 0, 2 = t1 after
+// t0 was clipped (then the reference keeps the FIRST phi for u: `phi :=` shadows, sphere.go:127).
+GP_HD bool sphere_select(const Ray& ray, EF t0, EF t1, double radius, double zMin, double zMax, double phiMax, bool full, double* tHit,
+                         int* which) {
+  if (t0.hi > ray.tmax || t1.lo <= 0) return false;
+  EF ts = t0;
+  int w = 0;
+  if (ts.lo <= 0) {
+    ts = t1;
+    w = 1;
+    if (ts.hi > ray.tmax) return false;
+  }
+  if (!full) {
+    V3 pHit = sphere_refine(ray, ts.v, radius);
+    double phi = phi_of(pHit);
+    if ((zMin > -radius && pHit.z < zMin) || (zMax < radius && pHit.z > zMax) || phi > phiMax) {
+      if (w == 1) return false;
+      if (t1.hi > ray.tmax) return false;
+      ts = t1;
+      w = 2;
+      pHit = sphere_refine(ray, ts.v, radius);
+      double phi2 = phi_of(pHit);
+      if ((zMin > -radius && pHit.z < zMin) || (zMax < radius && pHit.z > zMax) || phi2 > phiMax) return false;
+    }
+  }
+  *tHit = ts.v;
+  if (which) *which = w;
+  return true;
+}
+
+// ---- Disk.Intersect / IntersectP (disk.go:64-93,127-159) on the object-space ray ----
+GP_HD bool disk_test(const Ray& ray, double height, double radius, double innerRadius, double phiMax, double* tHit) {
+  if (ray.d.z == 0) return false;
+  double t = (height - ray.o.z) / ray.d.z;
+  if (t <= 0 || t >= ray.tmax) return false;
+  V3 pHit = ray.o + ray.d * t;
+  double d2 = pHit.x * pHit.x + pHit.y * pHit.y;
+  if (d2 > radius * radius || d2 < innerRadius * innerRadius) return false;
+  double phi = go_atan2(pHit.y, pHit.x);
+  if (phi < 0) phi += 2 * kPi;
+  if (phi > phiMax) return false;
+  *tHit = t;
+  return true;
+}
+
+// ---- Triangle (new shape, defined by this backend + its oracle): watertight test in float64 ----
+GP_HD int max_dim(V3 v) { return (v.x > v.y) ? ((v.x > v.z) ? 0 : 2) : ((v.y > v.z) ? 1 : 2); }
+GP_HD V3 permute(V3 v, int x, int y, int z) { return mk3(comp(v, x), comp(v, y), comp(v, z)); }
+GP_HD bool tri_test(V3 p0, V3 p1, V3 p2, const Ray& ray, double* tHit, double* bary) {
+  V3 p0t = p0 - ray.o, p1t = p1 - ray.o, p2t = p2 - ray.o;
+  int kz = max_dim(vabs(ray.d));
+  int kx = kz + 1; if (kx == 3) kx = 0;
+  int ky = kx + 1; if (ky == 3) ky = 0;
+  V3 d = permute(ray.d, kx, ky, kz);
+  p0t = permute(p0t, kx, ky, kz); p1t = permute(p1t, kx, ky, kz); p2t = permute(p2t, kx, ky, kz);
+  double Sx = -d.x / d.z, Sy = -d.y / d.z, Sz = 1.0 / d.z;
+  p0t.x += Sx * p0t.z; p0t.y += Sy * p0t.z;
+  p1t.x += Sx * p1t.z; p1t.y += Sy * p1t.z;
+  p2t.x += Sx * p2t.z; p2t.y += Sy * p2t.z;
+  double e0 = p1t.x * p2t.y - p1t.y * p2t.x;
+  double e1 = p2t.x * p0t.y - p2t.y * p0t.x;
+  double e2 = p0t.x * p1t.y - p0t.y * p1t.x;
+  if ((e0 < 0 || e1 < 0 || e2 < 0) && (e0 > 0 || e1 > 0 || e2 > 0)) return false;
+  double det = e0 + e1 + e2;
+  if (det == 0) return false;
+  p0t.z *= Sz; p1t.z *= Sz; p2t.z *= Sz;
+  double tScaled = e0 * p0t.z + e1 * p1t.z + e2 * p2t.z;
+  if (det < 0 && (tScaled >= 0 || tScaled < ray.tmax * det)) return false;
+  if (det > 0 && (tScaled <= 0 || tScaled > ray.tmax * det)) return false;
+  double invDet = 1 / det;
+  double t = tScaled * invDet;
+  if (t <= 0 || t >= ray.tmax) return false;
+  *tHit = t;
+  if (bary) { bary[0] = e0 * invDet; bary[1] = e1 * invDet; bary[2] = e2 * invDet; }
+  return true;
+}
+
+// ---- the surface interaction fields Path.Li reads (pkg/pbrt/interaction.go:23-30,123-148) ----
+struct Hit {
+  V3 p, perr, n, wo, ns, sdpdu;
+  double u, v;
+};
+// Transform.TransformSurfaceInteraction (transform.go:302-334) on those fields, with the reference's pointer-aliasing
+// outcome: Shading.Normal is the un-normalised transform of the previous one, then FaceForward'ed.
+GP_HD void xf_hit(const M4& m, const M4& inv, Hit& h) {
+  V3 perr;
+  V3 p = xf_point(m, h.p, h.perr, &perr);
+  h.p = p; h.perr = perr;
+  h.n = normalized(xf_normal_inv(inv, h.n));
+  h.wo = normalized(xf_vector(m, h.wo));
+  h.ns = xf_normal_inv(inv, h.ns);
+  h.sdpdu = xf_vector(m, h.sdpdu);
+  h.ns = faceforward(h.ns, h.n);
+}
+
+// generic primitive test used by both traversal kernels.  Returns true and the hit t (the new r.TMax,
+// primitive.go:51,102) if the primitive is hit within ray.tmax.  `bad` collects efloat.Check panics.
+GP_D bool prim_test(const DevScene& sc, const PrimRec* rec, uint32_t flags, const Ray& wray, double* tHit, int& bad) {
+  uint32_t kind = flags & RK_KIND_MASK;
+  if (kind == RK_TRIANGLE) {
+    const double* d = rec->d;
+    return tri_test(mk3(d[0], d[1], d[2]), mk3(d[3], d[4], d[5]), mk3(d[6], d[7], d[8]), wray, tHit, nullptr);
+  }
+  Ray ray = wray;
+  if (kind == RK_SPHERE && (flags & RF_FAST)) {
+    const double* d = rec->d;
+    // TransformedPrimitive.Intersect: ray through primitiveToWorld.Inverse() (primitive.go:94-96)
+    if (flags & RF_HAS_P2W) ray = xf_ray(translation_m4(d[4], d[5], d[6]), ray, nullptr, nullptr);
+    V3 oe, de;
+    ray = xf_ray(translation_m4(d[1], d[2], d[3]), ray, &oe, &de);  // worldToObject.TransformRay (sphere.go:65)
+    EF t0, t1;
+    if (!sphere_roots(ray, oe, de, d[0], &t0, &t1, bad)) return false;
+    return sphere_select(ray, t0, t1, d[0], 0, 0, 0, true, tHit, nullptr);
+  }
+  // general path: look the shape up
+  int4 pr = sc.prims[rec->prim];
+  if (pr.w >= 0) ray = xf_ray(load_m4(sc, pr.w, true), ray, nullptr, nullptr);
+  if (kind == RK_SPHERE) {
+    SphereDev s = sc.spheres[pr.y];
+    V3 oe, de;
+    ray = xf_ray(load_m4(sc, s.xf, true), ray, &oe, &de);
+    EF t0, t1;
+    if (!sphere_roots(ray, oe, de, s.radius, &t0, &t1, bad)) return false;
+    return sphere_select(ray, t0, t1, s.radius, s.zMin, s.zMax, s.phiMax, (flags & RF_FULL) != 0, tHit, nullptr);
+  }
+  DiskDev dk = sc.disks[pr.y];
+  ray = xf_ray(load_m4(sc, dk.xf, true), ray, nullptr, nullptr);
+  return disk_test(ray, dk.height, dk.radius, dk.innerRadius, dk.phiMax, tHit);
+}
+
+// Rebuild the SurfaceInteraction of a known hit (world ray + primitive id + tHit).  The traversal kernel keeps only
+// (primitive, t); everything here is a deterministic function of those, so recomputing it in the shade stage gives
+// the same bits the reference computes inside Shape.Intersect (sphere.go:137-185, disk.go:95-123) followed by
+// TransformedPrimitive.Intersect (primitive.go:104-106).
+GP_D void hit_record(const DevScene& sc, int rec_index, const Ray& wray_in, double tHit, Hit* h, int* prim_out, int& bad) {
+  const PrimRec* rec = sc.recs + rec_index;
+  uint32_t rflags = rec->flags;
+  int prim = (int)rec->prim;
+  *prim_out = prim;
+  int4 pr = sc.prims[prim];
+  Ray ray = wray_in;
+  if (pr.x == RK_TRIANGLE) {
+    const double* d = rec->d;
+    V3 p0 = mk3(d[0], d[1], d[2]), p1 = mk3(d[3], d[4], d[5]), p2 = mk3(d[6], d[7], d[8]);
+    double t, b[3];
+    Ray r2 = ray;
+    r2.tmax = d_inf();
+    // barycentrics do not depend on tMax; the test cannot fail for a ray that hit this triangle at tHit
+    tri_test(p0, p1, p2, r2, &t, b);
+    V3 dp02 = p0 - p2, dp12 = p1 - p2;
+    double du02 = -1, dv02 = -1, du12 = 0, dv12 = -1;
+    double determinant = du02 * dv12 - dv02 * du12;
+    double invdet = 1 / determinant;
+    V3 dpdu = (dp02 * dv12 - dp12 * dv02) * invdet;
+    V3 dpdv = (dp02 * -du12 + dp12 * du02) * invdet;
+    V3 n = normalized(cross(dp02, dp12));
+    if (len2(cross(dpdu, dpdv)) == 0) { V3 tmp; coordinate_system(n, &dpdu, &tmp); }
+    V3 pAbs = vabs(p0 * b[0]) + vabs(p1 * b[1]) + vabs(p2 * b[2]);
+    h->perr = pAbs * gamma_n(7);
+    h->p = p0 * b[0] + p1 * b[1] + p2 * b[2];
+    if (rflags & RF_REVERSE) n = n * -1.0;
+    h->n = n;
+    h->wo = ray.d * -1.0;
+    h->ns = n;
+    h->sdpdu = dpdu;
+    h->u = b[0] * 0 + b[1] * 1 + b[2] * 1;
+    h->v = b[0] * 0 + b[1] * 0 + b[2] * 1;
+    return;
+  }
+  M4 p2w_inv;
+  if (pr.w >= 0) { p2w_inv = load_m4(sc, pr.w, true); ray = xf_ray(p2w_inv, ray, nullptr, nullptr); }
+  int sxf;
+  if (pr.x == RK_SPHERE) {
+    SphereDev s = sc.spheres[pr.y];
+    sxf = s.xf;
+    M4 w2o = load_m4(sc, s.xf, true);
+    V3 oe, de;
+    ray = xf_ray(w2o, ray, &oe, &de);
+    V3 pHit = sphere_refine(ray, tHit, s.radius);
+    double phi = phi_of(pHit);
+    if (!(s.flags & RF_FULL)) {
+      // partial sphere: if the reference reached tHit through the clip branch, u keeps the phi of the clipped t0 root
+      EF t0, t1;
+      if (sphere_roots(ray, oe, de, s.radius, &t0, &t1, bad) && t0.lo > 0 && tHit != t0.v) phi = phi_of(sphere_refine(ray, t0.v, s.radius));
+    }
+    double u = phi / s.phiMax;
+    double theta = go_acos(go_clamp(pHit.z / s.radius, -1, 1));
+    double v = (theta - s.thetaMin) / (s.thetaMax - s.thetaMin);
+    double zRadius = sqrt(pHit.x * pHit.x + pHit.y * pHit.y);
+    double invZ = 1.0 / zRadius;
+    double cosPhi = pHit.x * invZ, sinPhi = pHit.y * invZ;
+    V3 dpdu = mk3(-s.phiMax * pHit.y, s.phiMax * pHit.x, 0);
+    V3 dpdv = mk3(pHit.z * cosPhi, pHit.z * sinPhi, -s.radius * go_sin(theta)) * (s.thetaMax - s.thetaMin);
+    V3 n = normalized(cross(dpdu, dpdv));
+    if (s.flags & RF_REVERSE) n = n * -1.0;  // interaction.go:179-181
+    h->p = pHit; h->perr = vabs(pHit) * gamma_n(5); h->n = n; h->wo = ray.d * -1.0; h->ns = n; h->sdpdu = dpdu; h->u = u; h->v = v;
+  } else {
+    DiskDev dk = sc.disks[pr.y];
+    sxf = dk.xf;
+    ray = xf_ray(load_m4(sc, dk.xf, true), ray, nullptr, nullptr);
+    V3 pHit = ray.o + ray.d * tHit;
+    double d2 = pHit.x * pHit.x + pHit.y * pHit.y;
+    double phi = phi_of(pHit);
+    double u = phi / dk.phiMax;
+    double rHit = sqrt(d2);
+    double oneMinusV = (rHit - dk.innerRadius) / (dk.radius - dk.innerRadius);
+    double v = 1 - oneMinusV;
+    V3 dpdu = mk3(-dk.phiMax * pHit.y, dk.phiMax * pHit.x, 0);
+    V3 dpdv = mk3(pHit.x, pHit.y, 0) * ((dk.radius - dk.innerRadius) / rHit);  // normal comes out -z
+    pHit.z = dk.height;
+    V3 n = normalized(cross(dpdu, dpdv));
+    if (dk.flags & RF_REVERSE) n = n * -1.0;
+    h->p = pHit; h->perr = mk3(0, 0, 0); h->n = n; h->wo = ray.d * -1.0; h->ns = n; h->sdpdu = dpdu; h->u = u; h->v = v;
+  }
+  xf_hit(load_m4(sc, sxf, false), load_m4(sc, sxf, true), *h);  // sphere.go:185 / disk.go:110
+  if (pr.w >= 0 && !(sc.xf_flags[pr.w] & XF_IDENTITY)) xf_hit(load_m4(sc, pr.w, false), p2w_inv, *h);  // primitive.go:104-106
+}
+
+}  // namespace gp

@@ -1,0 +1,67 @@
+"""CPU-side checks of the C-ABI library: it loads, exports every symbol include/gopbrt_cuda.h declares, and refuses to
+run without a GPU (no CPU fallback).  No compute calls here."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    src = open(os.path.join(ROOT, "include", "gopbrt_cuda.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(gopbrt_[a-z_0-9]+)\s*\(", src)))
+
+
+def test_header_and_binding_agree(gp):
+    assert _declared_symbols() == sorted(gp.abi.EXPORTS)
+
+
+def test_library_exports_every_symbol(gp):
+    lib = gp.abi.load()
+    for name in _declared_symbols():
+        assert hasattr(lib, name), name
+    assert lib.gopbrt_abi_version() == 1
+
+
+def test_struct_sizes_match_header(gp):
+    a = gp.abi
+    assert C.sizeof(a.Transform) == 256 and C.sizeof(a.Sphere) == 40 and C.sizeof(a.Disk) == 40
+    assert C.sizeof(a.Triangle) == 16 and C.sizeof(a.Primitive) == 16 and C.sizeof(a.Material) == 48
+    assert C.sizeof(a.Texture) == 16 + 8 * 15 and C.sizeof(a.Light) == 16 + 48
+    assert C.sizeof(a.Camera) == 8 * 36 and C.sizeof(a.Sampler) == 24 and C.sizeof(a.Integrator) == 32
+    assert C.sizeof(a.SceneDesc) == 152
+    assert C.sizeof(a.Film) == 8 + 48 and C.sizeof(a.RenderOptions) == 16 and C.sizeof(a.Stats) == 8 * 24
+
+
+def test_no_cpu_fallback(gp):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    lib = gp.abi.load()
+    h = C.c_void_p()
+    assert lib.gopbrt_init(0, C.byref(h)) == gp.abi.ERR_CUDA and not h.value
+    with pytest.raises(RuntimeError):
+        gp.pbrt.Device(0)
+
+
+def test_product_does_not_reference_oracle():
+    # the oracle is test infrastructure: nothing under go-pbrt_b200/ may import, include, link or execute it
+    pkg = os.path.join(ROOT, "go-pbrt_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp", ".sh", ".go")):
+                txt = open(os.path.join(dp, f), errors="ignore").read()
+                assert "liboracle" not in txt and "oracle_lib" not in txt and "oracle/" not in txt.replace("its oracle", ""), f
+
+
+def test_scene_desc_flattening(gp):
+    scene, integ = gp.scenes.config1(W=64, H=36)
+    d = scene.desc()
+    assert d.n_primitives == 23 and d.n_spheres == 22 and d.n_disks == 2 and d.n_lights == 4 and d.max_prims_in_node == 2
+    assert d.n_materials == 22 and d.n_textures == 24
+    scene2, _ = gp.scenes.config2(W=64, H=36)
+    d2 = scene2.desc()
+    assert d2.n_triangles == 34 and d2.n_primitives == 36 and d2.n_vertices == 68
