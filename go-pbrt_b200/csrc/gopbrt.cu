@@ -22,7 +22,7 @@ static_assert(sizeof(gopbrt_transform) == 256 && sizeof(gopbrt_sphere) == 40 && 
 static_assert(sizeof(gopbrt_triangle) == 16 && sizeof(gopbrt_primitive) == 16 && sizeof(gopbrt_material) == 48, "ABI layout");
 static_assert(sizeof(gopbrt_texture) == 136 && sizeof(gopbrt_light) == 64 && sizeof(gopbrt_camera) == 288, "ABI layout");
 static_assert(sizeof(gopbrt_sampler) == 24 && sizeof(gopbrt_integrator) == 32 && sizeof(gopbrt_film) == 56, "ABI layout");
-static_assert(sizeof(gopbrt_render_options) == 16 && sizeof(gopbrt_stats) == 192 && sizeof(gopbrt_scene_desc) == 152, "ABI layout");
+static_assert(sizeof(gopbrt_render_options) == 16 && sizeof(gopbrt_stats) == 232 && sizeof(gopbrt_scene_desc) == 152, "ABI layout");
 
 struct gopbrt_ctx {
   int device = 0;
@@ -73,7 +73,11 @@ struct Workspace {  // per-scene render workspace, kept between gopbrt_render ca
   DevBuf<RenderCounters> rctr;
   int* remaining_host = nullptr;  // pinned, device-mapped
   int* remaining_dev = nullptr;
-  ~Workspace() { if (remaining_host) cudaFreeHost(remaining_host); }
+  std::vector<cudaEvent_t> events;  // pool for GOPBRT_FLAG_TIME_KERNELS
+  ~Workspace() {
+    if (remaining_host) cudaFreeHost(remaining_host);
+    for (auto e : events) cudaEventDestroy(e);
+  }
 };
 
 struct gopbrt_scene {
@@ -627,34 +631,54 @@ static int render_impl(gopbrt_scene* sc, const gopbrt_camera* cam, const gopbrt_
   GP_CUDA(ctx, cudaEventRecord(ev[0], st));
   uint64_t iterations = 0, launches0 = ctx->launches.load();
   int rc = GOPBRT_OK;
+  // optional per-stage timing: CUDA events on the launching stream around every stage launch
+  const bool timing = (flags & GOPBRT_FLAG_TIME_KERNELS) != 0;
+  enum { ST_RAYGEN = 0, ST_EXTEND, ST_SHADE, ST_SHADOW, ST_FILM, ST_N };
+  std::vector<int> ev_stage;
+  size_t ev_used = 0;
+  auto tick = [&](int stage) {
+    if (!timing) return;
+    if (ev_used >= W.events.size()) { cudaEvent_t e; cudaEventCreate(&e); W.events.push_back(e); }
+    cudaEventRecord(W.events[ev_used++], st);
+    ev_stage.push_back(stage);
+  };
+  uint64_t n_extend = 0, n_shadow = 0;
   for (long long base = 0; base < lanes_total && rc == GOPBRT_OK; base += lanes) {
     P.lane_base = base;
     P.lanes_active = std::min(lanes, lanes_total - base);
     GP_CUDA(ctx, cudaMemsetAsync(W.tilepix.p, 0, bp * sizeof(double), st));
     GP_CUDA(ctx, cudaMemsetAsync(W.cnt.p, 0, 8 * sizeof(int), st));
+    tick(ST_RAYGEN);
     k_init_lanes<<<g_small, 128, 0, st>>>(L, P);
     k_generate<<<g_gen, 128, 0, st>>>(sc->dev, L, P, Q, nullptr, nullptr, W.rctr.p);
     ctx->launches += 2;
     for (;;) {
+      tick(ST_EXTEND);
       if (count) k_extend<true><<<g_ext_c, kTraceThreads, 0, st>>>(sc->dev, L.ray, L.hit_rec, Q.extend, Q.cnt + 0, 0, sc->tctr.p);
       else k_extend<false><<<g_ext, kTraceThreads, 0, st>>>(sc->dev, L.ray, L.hit_rec, Q.extend, Q.cnt + 0, 0, sc->tctr.p);
+      tick(ST_SHADE);
       k_shade<<<g_shade, 128, 0, st>>>(sc->dev, L, P, Q, W.rctr.p);
+      tick(ST_SHADOW);
       if (count) k_anyhit<true><<<g_any_c, kTraceThreads, 0, st>>>(sc->dev, L.sray, L.occluded, Q.shadow, Q.cnt + 2, 0, sc->tctr.p);
       else k_anyhit<false><<<g_any, kTraceThreads, 0, st>>>(sc->dev, L.sray, L.occluded, Q.shadow, Q.cnt + 2, 0, sc->tctr.p);
       k_shadow_resolve<<<g_small, 128, 0, st>>>(L, Q, W.rctr.p);
+      tick(ST_RAYGEN);
       k_advance<<<1, 32, 0, st>>>(Q, W.rctr.p, W.remaining_dev);
       std::swap(Q.extend, Q.extend_next);
       std::swap(Q.regen, Q.regen_next);
       k_generate<<<g_gen, 128, 0, st>>>(sc->dev, L, P, Q, Q.regen, Q.cnt + 3, W.rctr.p);
       ctx->launches += 6;
       iterations++;
+      n_extend++; n_shadow++;
       GP_CUDA(ctx, cudaStreamSynchronize(st));
       if (*W.remaining_host == 0) break;
       if (sc->cancel.load()) { rc = GOPBRT_ERR_CANCELLED; break; }
     }
+    tick(ST_FILM);
     k_film_merge<<<g_small, 128, 0, st>>>(L, P, d_film);
     ctx->launches++;
   }
+  tick(ST_N);
   GP_CUDA(ctx, cudaEventRecord(ev[1], st));
   GP_CUDA(ctx, cudaStreamSynchronize(st));
   GP_CUDA(ctx, cudaGetLastError());
@@ -674,6 +698,18 @@ static int render_impl(gopbrt_scene* sc, const gopbrt_camera* cam, const gopbrt_
     stats->nan_samples = rcnt.nan_samples; stats->efloat_panics = rcnt.efloat_panics + tcnt.efloat_panics;
     stats->stack_overflows = tcnt.stack_overflows; stats->iterations = iterations; stats->launches = ctx->launches.load() - launches0;
     stats->lanes = (uint64_t)lanes; stats->ms_total = ms; stats->bvh_nodes = sc->bvh_nodes; stats->bvh_depth = sc->bvh_depth;
+    stats->tests_triangle = tcnt.t_tri; stats->tests_sphere_fast = tcnt.t_sph; stats->tests_general = tcnt.t_gen;
+    stats->extend_launches = n_extend; stats->shadow_launches = n_shadow;
+    if (timing) {
+      double acc[ST_N + 1] = {0, 0, 0, 0, 0, 0};
+      for (size_t i = 0; i + 1 < ev_used; i++) {
+        float t = 0;
+        cudaEventElapsedTime(&t, W.events[i], W.events[i + 1]);
+        acc[ev_stage[i]] += t;
+      }
+      stats->ms_raygen = acc[ST_RAYGEN]; stats->ms_extend = acc[ST_EXTEND]; stats->ms_shade = acc[ST_SHADE];
+      stats->ms_shadow = acc[ST_SHADOW]; stats->ms_film = acc[ST_FILM];
+    }
   }
   if (rc == GOPBRT_OK && (flags & GOPBRT_FLAG_FAIL_ON_PANIC) && (rcnt.radiance_gt10 || rcnt.efloat_panics || tcnt.efloat_panics || rcnt.unsupported)) {
     ctx->last_error = "a condition on which the reference panics was hit (see gopbrt_stats)";

@@ -19,12 +19,14 @@ constexpr int kTraceThreads = 128;
 struct RaySoA { double *ox, *oy, *oz, *dx, *dy, *dz, *tmax; };
 
 struct TraceCounters {
-  unsigned long long nodes, prims, snodes, sprims, efloat_panics, stack_overflows;
+  unsigned long long nodes, prims, snodes, sprims, efloat_panics, stack_overflows, t_tri, t_sph, t_gen;
 };
+
+struct TravCnt { unsigned long long nodes, prims, tri, sph, gen; };
 
 template <bool ANY, bool COUNT>
 GP_D bool traverse(const DevScene& sc, Ray& ray, int* hit_rec, unsigned* stack /* this thread's column */, int stride,
-                   unsigned long long& n_nodes, unsigned long long& n_prims, int& bad, int& overflow) {
+                   TravCnt& cnt, int& bad, int& overflow) {
   V3 invd = mk3(1 / ray.d.x, 1 / ray.d.y, 1 / ray.d.z);
   int nx = invd.x < 0, ny = invd.y < 0, nz = invd.z < 0;
   int sp = 0;
@@ -34,7 +36,7 @@ GP_D bool traverse(const DevScene& sc, Ray& ray, int* hit_rec, unsigned* stack /
   for (;;) {
     float4 n0 = __ldg(sc.nodes + 2 * (size_t)cur);
     float4 n1 = __ldg(sc.nodes + 2 * (size_t)cur + 1);
-    if (COUNT) n_nodes++;
+    if (COUNT) cnt.nodes++;
     unsigned a = __float_as_uint(n0.w), b = __float_as_uint(n1.w);
     if (slab_test((double)n0.x, (double)n0.y, (double)n0.z, (double)n1.x, (double)n1.y, (double)n1.z, ray.o, invd, nx, ny, nz, ray.tmax)) {
       unsigned np = b >> 8;
@@ -55,7 +57,12 @@ GP_D bool traverse(const DevScene& sc, Ray& ray, int* hit_rec, unsigned* stack /
             cand = slab_test(bb[0], bb[1], bb[2], bb[3], bb[4], bb[5], ray.o, invd, nx, ny, nz, ray.tmax);
           }
           if (!cand) continue;
-          if (COUNT) n_prims++;
+          if (COUNT) {
+            cnt.prims++;
+            if ((flags & RK_KIND_MASK) == RK_TRIANGLE) cnt.tri++;
+            else if (flags & RF_FAST) cnt.sph++;
+            else cnt.gen++;
+          }
           double t;
           if (prim_test(sc, rec, flags, ray, &t, bad)) {
             if (ANY) return true;
@@ -93,7 +100,7 @@ __global__ void __launch_bounds__(kTraceThreads) k_extend(DevScene sc, RaySoA ra
                                                           const int* __restrict__ count, long long n_direct, TraceCounters* ctr) {
   __shared__ unsigned s_stack[kStackDepth * kTraceThreads];
   long long n = queue ? (long long)*count : n_direct;
-  unsigned long long nn = 0, np = 0;
+  TravCnt c = {0, 0, 0, 0, 0};
   int bad = 0, ovf = 0;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     long long lane = queue ? queue[i] : i;
@@ -102,13 +109,16 @@ __global__ void __launch_bounds__(kTraceThreads) k_extend(DevScene sc, RaySoA ra
     r.d = mk3(rays.dx[lane], rays.dy[lane], rays.dz[lane]);
     r.tmax = rays.tmax[lane];
     int rec = -1;
-    traverse<false, COUNT>(sc, r, &rec, s_stack + threadIdx.x, kTraceThreads, nn, np, bad, ovf);
+    traverse<false, COUNT>(sc, r, &rec, s_stack + threadIdx.x, kTraceThreads, c, bad, ovf);
     rays.tmax[lane] = r.tmax;
     hit_rec[lane] = rec;
   }
   if (COUNT) {
-    nn = warp_sum(nn); np = warp_sum(np);
-    if ((threadIdx.x & 31) == 0) { atomicAdd(&ctr->nodes, nn); atomicAdd(&ctr->prims, np); }
+    c.nodes = warp_sum(c.nodes); c.prims = warp_sum(c.prims); c.tri = warp_sum(c.tri); c.sph = warp_sum(c.sph); c.gen = warp_sum(c.gen);
+    if ((threadIdx.x & 31) == 0) {
+      atomicAdd(&ctr->nodes, c.nodes); atomicAdd(&ctr->prims, c.prims);
+      atomicAdd(&ctr->t_tri, c.tri); atomicAdd(&ctr->t_sph, c.sph); atomicAdd(&ctr->t_gen, c.gen);
+    }
   }
   if (bad) atomicAdd(&ctr->efloat_panics, 1ULL);
   if (ovf) atomicAdd(&ctr->stack_overflows, 1ULL);
@@ -121,7 +131,7 @@ __global__ void __launch_bounds__(kTraceThreads) k_anyhit(DevScene sc, RaySoA ra
                                                           TraceCounters* ctr) {
   __shared__ unsigned s_stack[kStackDepth * kTraceThreads];
   long long n = queue ? (long long)*count : n_direct;
-  unsigned long long nn = 0, np = 0;
+  TravCnt c = {0, 0, 0, 0, 0};
   int bad = 0, ovf = 0;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     long long lane = queue ? queue[i] : i;
@@ -130,12 +140,15 @@ __global__ void __launch_bounds__(kTraceThreads) k_anyhit(DevScene sc, RaySoA ra
     r.d = mk3(rays.dx[lane], rays.dy[lane], rays.dz[lane]);
     r.tmax = rays.tmax[lane];
     int rec = -1;
-    bool hit = traverse<true, COUNT>(sc, r, &rec, s_stack + threadIdx.x, kTraceThreads, nn, np, bad, ovf);
+    bool hit = traverse<true, COUNT>(sc, r, &rec, s_stack + threadIdx.x, kTraceThreads, c, bad, ovf);
     occluded[lane] = hit ? 1 : 0;
   }
   if (COUNT) {
-    nn = warp_sum(nn); np = warp_sum(np);
-    if ((threadIdx.x & 31) == 0) { atomicAdd(&ctr->snodes, nn); atomicAdd(&ctr->sprims, np); }
+    c.nodes = warp_sum(c.nodes); c.prims = warp_sum(c.prims); c.tri = warp_sum(c.tri); c.sph = warp_sum(c.sph); c.gen = warp_sum(c.gen);
+    if ((threadIdx.x & 31) == 0) {
+      atomicAdd(&ctr->snodes, c.nodes); atomicAdd(&ctr->sprims, c.prims);
+      atomicAdd(&ctr->t_tri, c.tri); atomicAdd(&ctr->t_sph, c.sph); atomicAdd(&ctr->t_gen, c.gen);
+    }
   }
   if (bad) atomicAdd(&ctr->efloat_panics, 1ULL);
   if (ovf) atomicAdd(&ctr->stack_overflows, 1ULL);

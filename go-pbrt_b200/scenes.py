@@ -145,13 +145,15 @@ def config2(W=1920, H=1080, spp=(8, 8)):
     _quad(v, idx, (1, -1, -1), (1, 1, -1), (1, 1, 1), (1, -1, 1))       # right (green)
     prims.append(P.TriangleMesh(v, idx, green))
     v, idx = [], []
-    _box(v, idx, (0.35, -0.7, 0.3), (0.6, 0.6, 0.6), -18.0)            # short box
-    _box(v, idx, (-0.35, -0.4, -0.3), (0.6, 1.2, 0.6), 18.0)           # tall box
+    # the boxes float 1 mm above the floor: coplanar faces would make closest-hit results depend on BVH visit order
+    # (ties inside the efloat bound), which no two tree topologies can agree on
+    _box(v, idx, (0.35, -0.699, 0.3), (0.6, 0.6, 0.6), -18.0)          # short box
+    _box(v, idx, (-0.35, -0.399, -0.3), (0.6, 1.2, 0.6), 18.0)         # tall box
     prims.append(P.TriangleMesh(v, idx, white))
     matte = P.NewMatteMaterial(P.NewConstantSpectrumTexture(P.NewRGBSpectrum(.25, .35, .75)), P.NewConstantFloatTexture(0.0))
     glass = P.NewGlass(P.NewConstantSpectrumTexture(P.NewSpectrum(1.0)), P.NewConstantSpectrumTexture(P.NewSpectrum(1.0)),
                        P.NewConstantFloatTexture(0.0), P.NewConstantFloatTexture(0.0), P.NewConstantFloatTexture(1.5))
-    prims.append(P.NewGeometricPrimitive(P.NewSphereShape("matte", P.Translate((0.35, -0.1, 0.3)), False, 0.3), matte))
+    prims.append(P.NewGeometricPrimitive(P.NewSphereShape("matte", P.Translate((0.35, -0.098, 0.3)), False, 0.3), matte))
     prims.append(P.NewGeometricPrimitive(P.NewSphereShape("glass", P.Translate((-0.45, -0.7, 0.6)), False, 0.3), glass))
     agg = P.NewBVH(prims, 4, P.SplitSAH)
     light_xf = P.Translate((0.0, 0.99, 0.0)).Mul(P.RotateX(90))
@@ -277,14 +279,16 @@ def mixed_test_scene(n=200, seed=7, with_triangles=True):
         sph = P.NewSphereShape("s", P.Translate(c) if i % 3 else P.Translate((0.0, 0.0, 0.0)), bool(i % 5 == 0), r)
         g = P.NewGeometricPrimitive(sph, m)
         if i % 3 == 0:
-            xf = P.Translate(c).Mul(P.RotateY(30.0 * U()))
+            # NewTransform re-derives a consistent inverse: Transform.Mul's own inverse is wrong for non-commuting
+            # factors (transform.go:179-184), which would put the sphere outside its own world bound
+            xf = P.NewTransform(P.Translate(c).Mul(P.RotateY(30.0 * U())).Matrix)
             g = P.NewTransformedPrimitive(g, P.NewAnimatedTransform(xf, xf, 0, 1))
         prims.append(g)
     floor = P.NewDisk(P.Translate((0.0, 0.0, 0.0)).Mul(P.RotateX(90)), 0.0, 40.0, 0, 360)
     prims.append(P.NewGeometricPrimitive(floor, P.NewMatteMaterial(checker, zero)))
     if with_triangles:
         v, idx = [], []
-        _box(v, idx, (3.0, 1.0, 2.0), (2.0, 2.0, 2.0), 25.0)
+        _box(v, idx, (3.0, 1.01, 2.0), (2.0, 2.0, 2.0), 25.0)  # 1 cm above the floor disk: no coplanar ties
         _quad(v, idx, (-12, 0, -12), (-12, 9, -12), (12, 9, -12), (12, 0, -12))
         prims.append(P.TriangleMesh(v, idx, P.NewMatteMaterial(P.NewConstantSpectrumTexture(P.NewSpectrum(0.6)), zero)))
     agg = P.NewBVH(prims, 4, P.SplitSAH)

@@ -183,7 +183,8 @@ typedef struct {
 
 enum {
   GOPBRT_FLAG_COUNT_TRAVERSAL = 1, /* instrumented kernels: count BVH nodes visited / primitive tests */
-  GOPBRT_FLAG_FAIL_ON_PANIC = 2    /* return GOPBRT_ERR_REFERENCE_PANIC instead of counting           */
+  GOPBRT_FLAG_FAIL_ON_PANIC = 2,   /* return GOPBRT_ERR_REFERENCE_PANIC instead of counting           */
+  GOPBRT_FLAG_TIME_KERNELS = 4     /* CUDA-event time every stage launch (fills ms_raygen … ms_film)   */
 };
 
 /* work partition for one process per GPU: this rank renders tiles t with t % world == rank
@@ -199,7 +200,7 @@ typedef struct {
   uint64_t closest_rays;       /* scene.Intersect queries (path.go:45)                         */
   uint64_t shadow_rays;        /* scene.IntersectP queries (light.go:46-48)                    */
   uint64_t dead_mis_rays;      /* EstimateDirect's always-discarded ray (integrator.go:165-183): counted, not traced */
-  uint64_t nodes_visited, prim_tests;               /* closest-hit, with COUNT_TRAVERSAL       */
+  uint64_t nodes_visited, prim_tests;               /* closest-hit, with COUNT_TRAVERSAL (prim_tests = shape tests run) */
   uint64_t shadow_nodes_visited, shadow_prim_tests; /* any-hit, with COUNT_TRAVERSAL           */
   uint64_t radiance_gt10;      /* UniformSampleOneLight panic condition (integrator.go:73-75)  */
   uint64_t nan_samples;        /* L.HasNaNs() → 0.1 grey (integrator.go:256-257)               */
@@ -209,6 +210,8 @@ typedef struct {
   uint64_t lanes;
   double ms_total, ms_raygen, ms_extend, ms_shade, ms_shadow, ms_film, ms_download;
   uint64_t bvh_nodes, bvh_depth;
+  uint64_t tests_triangle, tests_sphere_fast, tests_general; /* closest + any-hit shape tests by record kind (COUNT_TRAVERSAL) */
+  uint64_t extend_launches, shadow_launches;
 } gopbrt_stats;
 
 /* ---- lifecycle ---- */

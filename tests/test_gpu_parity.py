@@ -10,11 +10,16 @@ pytestmark = pytest.mark.gpu
 
 
 def _cmp_closest(g, o, what):
+    """hit/miss and t bit-exact; primitive ids bit-exact except exact ties (two primitives hit at the very same t, e.g. a
+    ray through the shared edge of two triangles), which the reference resolves by BVH visit order"""
     gp_, gt, gpnt, gn = g
     op, ot, opnt, on = o
-    assert np.array_equal(gp_, op), f"{what}: {np.count_nonzero(gp_ != op)} primitive ids differ of {len(op)}"
-    assert np.array_equal(gt, ot), f"{what}: t differs (max rel {np.nanmax(np.abs(gt - ot) / np.abs(ot))})"
-    assert np.array_equal(gpnt, opnt) and np.array_equal(gn, on), f"{what}: hit point / normal differ"
+    assert np.array_equal(gp_ >= 0, op >= 0), f"{what}: hit/miss differs on {np.count_nonzero((gp_ >= 0) != (op >= 0))} rays"
+    assert np.array_equal(gt, ot), f"{what}: t differs on {np.count_nonzero(gt != ot)} rays"
+    ties = gp_ != op
+    assert np.count_nonzero(ties) <= max(1, len(op) // 20000), f"{what}: {np.count_nonzero(ties)} primitive ids differ of {len(op)}"
+    same = ~ties
+    assert np.array_equal(gpnt[same], opnt[same]) and np.array_equal(gn[same], on[same]), f"{what}: hit point / normal differ"
 
 
 TEST_RAYS = [((0, 0, 0), (0, 0, 1.0)), ((0, 0, 0), (0, 0, -1.0)), ((0, 0, 500), (0, 0, -1.0)), ((10, 10, 500), (0, 0, -1.0))]
@@ -123,12 +128,22 @@ def _render_both(gp, dev, scene, integ, tile, accel=1, **kw):
     return film, st, ofilm, ost
 
 
-def _assert_film_equal(film, ofilm, st, ost, what):
-    for k in ("camera_rays", "closest_rays", "shadow_rays"):
-        assert st[k] == ost[k], f"{what}: {k} {st[k]} != {ost[k]}"
+def _assert_film_equal(film, ofilm, st, ost, what, exact=True):
+    """STRICT-mode film parity.  exact=True: every pixel bit-identical and identical ray counts.  exact=False (scenes
+    where two tree topologies may break an exact t tie differently): the SURVEY §8d tier-2 bar — filterWeightSum exact,
+    at most 0.01 % of pixels (>= 1) may hold an outlier from a flipped path, all others bit-identical."""
+    assert st["camera_rays"] == ost["camera_rays"]
     assert np.array_equal(film[..., 3], ofilm[..., 3]), f"{what}: filterWeightSum differs"
     bad = np.count_nonzero(np.any(film != ofilm, axis=2))
-    assert bad == 0, f"{what}: {bad} of {film.shape[0] * film.shape[1]} pixels differ"
+    npx = film.shape[0] * film.shape[1]
+    if exact:
+        for k in ("closest_rays", "shadow_rays"):
+            assert st[k] == ost[k], f"{what}: {k} {st[k]} != {ost[k]}"
+        assert bad == 0, f"{what}: {bad} of {npx} pixels differ"
+    else:
+        assert bad <= max(1, npx // 10000), f"{what}: {bad} of {npx} pixels differ"
+        for k in ("closest_rays", "shadow_rays"):
+            assert abs(st[k] - ost[k]) <= max(20, ost[k] // 10000), f"{what}: {k} {st[k]} vs {ost[k]}"
 
 
 @pytest.mark.parametrize("tile", [16, 1])
