@@ -1,0 +1,281 @@
+#!/usr/bin/env python
+"""bench.py — Mrays/s and 1080p frame time of the go-pbrt hot path on N B200s, beside the CPU reference.
+
+    python bench.py --gpus N --steps K --warmup W            (N > 1: launched under torchrun, one rank per GPU)
+    python bench.py --impl reference --gpus N --steps K --warmup W
+
+A "step" is one frame: one pass of pbrt.Render's hot path (raygen+sampler -> extend -> shade -> shadow -> film) over the
+workload BASELINE.json's metric is quoted on (configs[1]): the procedural Cornell-box-style room of triangles, Path
+integrator, Stratified 8x8 ("64 spp" = 63 effective samples), 1920x1080, STRICT sampler mode with
+tileSize = 1 (one reference RNG stream per pixel: identical per-pixel sample sequences to pbrt.Render(..., 1)).
+
+value  = Mrays/s (closest-hit + any-hit queries the reference semantics require; the always-discarded MIS ray of
+         EstimateDirect is neither traced nor counted), scene resident in HBM, film left on the device; device time
+         from CUDA events on the library's stream, max over ranks.
+e2e    = the same metric through the public C-ABI call with a HOST film buffer (gopbrt_render): per-step descriptors
+         host->device, W*H*4 float64 film device->host (N > 1: NCCL film reduce to rank 0, then device->host).
+The reference arm (--impl reference) times the oracle — the C++ restatement of the Go renderer; Go itself cannot be
+built or run in this image — on the box's host cores over a bounded sample of the same workload.
+"""
+import argparse
+import ctypes as C
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "Mrays/s (closest-hit + any-hit) at 1080p, Path integrator, fixed spp"
+WORKLOADS = {
+    "config2": dict(name="config2: procedural Cornell-box-style room of triangles + matte/glass spheres, disk area light, "
+                         "Path maxDepth 10, Stratified 8x8 (63 effective spp), 1920x1080", W=1920, H=1080, spp=(8, 8)),
+    "config1": dict(name="config1: README sphere scene (internal/render/server.go), Path maxDepth 10, Stratified 4x4 "
+                         "(15 effective spp), 1920x1080", W=1920, H=1080, spp=(4, 4)),
+}
+# algorithmic bytes per unit: 32 B per BVH node visited; per shape test 72 B (triangle: 9 f64), 32 B
+# (translation-only sphere: centre + radius) or 224 B (general sphere/disk: two 3x4 f64 matrices + 4 scalars);
+# per closest-hit ray 72 B of ray I/O (read o,d,tMax = 56 B, write t + primitive = 16 B), per any-hit ray 60 B
+B_NODE, B_TRI, B_SPH, B_GEN, B_IO_CLOSEST, B_IO_ANY = 32, 72, 32, 224, 72, 60
+
+
+def build_scene(gp, args):
+    wl = WORKLOADS[args.config]
+    W, H = args.width or wl["W"], args.height or wl["H"]
+    scene, integ = getattr(gp.scenes, args.config)(W=W, H=H, spp=wl["spp"])
+    return wl, W, H, scene, integ
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) >= 8:
+                self.rows.append(f)
+
+    def __exit__(self, *a):
+        if self.proc:
+            time.sleep(0.25)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm = sorted(float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit())
+        mx = [float(r[2]) for r in self.rows if r[2].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows for i in range(4) if r[4 + i].lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(self.rows)}
+
+
+def cpu_reference(gp, args, steps, warmup, threads=None):
+    """the oracle (C++ restatement of the Go renderer) on the host cores: same scene, same spp, 1/16 of the pixels"""
+    from oracle_lib import OracleScene
+    wl = WORKLOADS[args.config]
+    W, H = (args.width or wl["W"]) // 4, (args.height or wl["H"]) // 4
+    scene, integ = getattr(gp.scenes, args.config)(W=W, H=H, spp=wl["spp"])
+    threads = threads or os.cpu_count() or 1
+    o = OracleScene(scene, 1)
+    secs, rays = [], 0
+    for i in range(warmup + steps):
+        film, st = o.render(integ, 1, threads=threads, deterministic=False)
+        if i >= warmup:
+            secs.append(st["seconds"])
+            rays = st["closest_rays"] + st["shadow_rays"]
+    o.close()
+    t = sum(secs) / max(1, len(secs))
+    return {"value": rays / t / 1e6, "unit": "Mrays/s", "cores": threads, "kind": "port",
+            "sample": f"same scene and spp at {W}x{H} (1/16 of the frame's pixels), tileSize 1, {rays} rays per step, "
+                      f"{t:.2f} s per step; C++ restatement of the Go renderer (no Go toolchain in this image)",
+            "ms_per_step": t * 1e3, "rays_per_step": rays}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--config", default="config2", choices=list(WORKLOADS))
+    ap.add_argument("--width", type=int, default=0)
+    ap.add_argument("--height", type=int, default=0)
+    ap.add_argument("--tile", type=int, default=1)
+    ap.add_argument("--mode", default="strict", choices=["strict", "fast"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    gp = importlib.import_module("go-pbrt_b200")
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        wl = WORKLOADS[args.config]
+        cb = cpu_reference(gp, args, args.steps, max(0, min(args.warmup, 1)))
+        line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "Mrays/s", "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": wl["name"], "tile_size": 1, "sampler_mode": "strict"},
+                "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                "e2e": {"value": cb["value"], "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return 0
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+    torch.cuda.set_device(local_rank)
+    P, abi = gp.pbrt, gp.abi
+    mode = abi.MODE_STRICT if args.mode == "strict" else abi.MODE_FAST
+    wl, W, H, scene, integ = build_scene(gp, args)
+    dev = P.Device(local_rank)
+    t0 = time.time()
+    g = P.GpuScene(dev, scene)
+    scene_create_s = time.time() - t0
+    film_dev = torch.zeros(H * W * 4, dtype=torch.float64, device=f"cuda:{local_rank}")
+    film_host = torch.empty(H * W * 4, dtype=torch.float64).pin_memory()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def step_device(flags):
+        """one frame, film stays on the device; returns (library stats, device ms incl. the NCCL film reduce)"""
+        st = P.Render(g, integ, args.tile, mode=mode, rank=rank, world=world, flags=flags, device_film=film_dev.data_ptr())
+        ms = st["ms_total"]
+        if world > 1:  # per-GPU films summed with ONE NCCL reduce over NVLink (north star)
+            ev0.record()
+            dist.reduce(film_dev, dst=0, op=dist.ReduceOp.SUM)
+            ev1.record()
+            torch.cuda.synchronize()
+            ms += ev0.elapsed_time(ev1)
+        return st, ms
+
+    for _ in range(max(3, args.warmup)):
+        step_device(0)
+    # instrumented (untimed) pass: V = BVH nodes visited, T = shape tests by kind
+    cst, _ = step_device(abi.FLAG_COUNT_TRAVERSAL)
+
+    barrier()
+    launches0 = dev.launches()
+    per_step_ms, stats = [], []
+    wall0 = time.time()
+    with ClockSampler(local_rank) as clocks:
+        for _ in range(args.steps):
+            st, ms = step_device(abi.FLAG_TIME_KERNELS)
+            per_step_ms.append(ms)
+            stats.append(st)
+    barrier()
+    wall = time.time() - wall0
+    launches = dev.launches() - launches0
+    rays_rank = sum(s["closest_rays"] + s["shadow_rays"] for s in stats)
+    ms_rank = sum(per_step_ms)
+
+    # ---- e2e: public C-ABI call with a host film buffer
+    desc_bytes = sum(C.sizeof(t) for t in (abi.Camera, abi.Sampler, abi.Integrator, abi.Film, abi.RenderOptions))
+    barrier()
+    e0 = time.time()
+    for _ in range(args.steps):
+        if world == 1:
+            P.Render(g, integ, args.tile, mode=mode)  # gopbrt_render: film D2H inside the call
+        else:
+            step_device(0)
+            if rank == 0:
+                film_host.copy_(film_dev, non_blocking=False)
+    barrier()
+    e2e_s = time.time() - e0
+
+    vals = torch.tensor([ms_rank, e2e_s, wall], dtype=torch.float64, device=f"cuda:{local_rank}")
+    tot = torch.tensor([float(rays_rank), float(launches)], dtype=torch.float64, device=f"cuda:{local_rank}")
+    if world > 1:
+        dist.all_reduce(vals, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    ms_total, e2e_total, wall_max = vals.tolist()
+    rays_total, launches_total = tot.tolist()
+
+    if rank == 0:
+        K = args.steps
+        value = rays_total / (ms_total / 1e3) / 1e6
+        e2e_value = rays_total / e2e_total / 1e6
+        # ---- roofline of the dominant kernel (k_extend: closest-hit traversal), rank 0, per launch
+        s_ext = sum(s["ms_extend"] for s in stats)
+        n_ext = sum(s["extend_launches"] for s in stats)
+        bytes_frame = (B_NODE * cst["nodes_visited"] + B_TRI * cst["tests_triangle"] + B_SPH * cst["tests_sphere_fast"] +
+                       B_GEN * cst["tests_general"] + B_IO_CLOSEST * cst["closest_rays"])
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        achieved = bytes_frame * K / (s_ext / 1e3) / 1e9 if s_ext > 0 else 0.0
+        roof = {"bound": "hbm", "kernel": "k_extend (closest-hit BVH traversal, fp64 slab + EFloat/watertight shape tests)",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6.65 TB/s (of fallback)",
+                "traffic": None,
+                "bytes_per_launch": bytes_frame * K / max(1, n_ext), "ms_per_launch": s_ext / max(1, n_ext), "launches": n_ext,
+                "per_ray": {"nodes_visited": cst["nodes_visited"] / max(1, cst["closest_rays"]),
+                            "shape_tests": cst["prim_tests"] / max(1, cst["closest_rays"])},
+                "stage_ms_per_step": {k: sum(s[k] for s in stats) / K for k in ("ms_raygen", "ms_extend", "ms_shade", "ms_shadow", "ms_film")}}
+        line = {"metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": K, "warmup": max(3, args.warmup),
+                "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic",
+                "config": {"workload": wl["name"], "resolution": [W, H], "tile_size": args.tile, "sampler_mode": args.mode,
+                           "paths_per_step": stats[0]["camera_rays"] * (world if mode == abi.MODE_FAST else 1),
+                           "rays_per_step": rays_total / K, "lanes": stats[0]["lanes"], "wavefront_iterations": stats[0]["iterations"],
+                           "partition": ("tiles t %% %d == rank" % world) if mode == abi.MODE_STRICT else "samples s % world == rank",
+                           "l2_policy": "per-lane path/sampler/film state of %d lanes is %.1f GB >> 126 MB L2 (inputs larger than L2)" % (
+                               stats[0]["lanes"], stats[0]["lanes"] * (26 * 8 + 9 * 4 + 16 + 3 + 4 * 64 * 8 + 36 * 8) / 1e9),
+                           "scene_create_s": scene_create_s, "bvh_nodes": stats[0]["bvh_nodes"], "bvh_depth": stats[0]["bvh_depth"],
+                           "frame_time_ms": ms_total / K, "frame_time_e2e_ms": e2e_total / K * 1e3,
+                           "wall_ms_per_step": wall_max / K * 1e3},
+                "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": desc_bytes, "d2h_bytes_per_step": H * W * 4 * 8,
+                        "ms_per_step": e2e_total / K * 1e3},
+                "gpu_launches": int(launches_total), "clocks": clocks.summary(), "roofline": roof,
+                "reference_panics": {"radiance_gt10": stats[0]["radiance_gt10"], "efloat_panics": stats[0]["efloat_panics"],
+                                     "nan_samples": stats[0]["nan_samples"]}}
+        if world == 1 and not args.no_cpu_baseline:
+            cb = cpu_reference(gp, args, 1, 0)
+            line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        print(json.dumps(line))
+    g.close()
+    dev.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

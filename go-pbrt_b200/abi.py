@@ -105,7 +105,8 @@ class Stats(C.Structure):
             "ms_total", "ms_raygen", "ms_extend", "ms_shade", "ms_shadow", "ms_film", "ms_download")] + [
                 ("bvh_nodes", C.c_uint64), ("bvh_depth", C.c_uint64), ("tests_triangle", C.c_uint64),
                 ("tests_sphere_fast", C.c_uint64), ("tests_general", C.c_uint64), ("extend_launches", C.c_uint64),
-                ("shadow_launches", C.c_uint64)]
+                ("shadow_launches", C.c_uint64), ("shadow_tests_triangle", C.c_uint64),
+                ("shadow_tests_sphere_fast", C.c_uint64), ("shadow_tests_general", C.c_uint64)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}

@@ -22,7 +22,7 @@ static_assert(sizeof(gopbrt_transform) == 256 && sizeof(gopbrt_sphere) == 40 && 
 static_assert(sizeof(gopbrt_triangle) == 16 && sizeof(gopbrt_primitive) == 16 && sizeof(gopbrt_material) == 48, "ABI layout");
 static_assert(sizeof(gopbrt_texture) == 136 && sizeof(gopbrt_light) == 64 && sizeof(gopbrt_camera) == 288, "ABI layout");
 static_assert(sizeof(gopbrt_sampler) == 24 && sizeof(gopbrt_integrator) == 32 && sizeof(gopbrt_film) == 56, "ABI layout");
-static_assert(sizeof(gopbrt_render_options) == 16 && sizeof(gopbrt_stats) == 232 && sizeof(gopbrt_scene_desc) == 152, "ABI layout");
+static_assert(sizeof(gopbrt_render_options) == 16 && sizeof(gopbrt_stats) == 256 && sizeof(gopbrt_scene_desc) == 152, "ABI layout");
 
 struct gopbrt_ctx {
   int device = 0;
@@ -96,6 +96,9 @@ struct gopbrt_scene {
   DevBuf<LightDev> lights;
   DevBuf<double> light_cdf;
   DevBuf<TraceCounters> tctr;
+  DevBuf<int> work;  // work counters of the persistent traversal warps (batched API)
+  int stack_cap = 8;
+  int grid_ext = 0, grid_ext_c = 0, grid_any = 0, grid_any_c = 0;
   double world[6] = {0, 0, 0, 0, 0, 0};
   uint64_t bvh_nodes = 0, bvh_depth = 0;
   std::atomic<int> cancel{0};
@@ -361,6 +364,7 @@ extern "C" int gopbrt_scene_create(gopbrt_ctx* ctx, const gopbrt_scene_desc* d, 
             sc->materials.upload(mats, st) == cudaSuccess && sc->textures.upload(texs, st) == cudaSuccess &&
             sc->lights.upload(lights, st) == cudaSuccess && sc->light_cdf.upload(cdf, st) == cudaSuccess &&
             sc->tctr.alloc(1) == cudaSuccess && cudaMemsetAsync(sc->tctr.p, 0, sizeof(TraceCounters), st) == cudaSuccess &&
+            sc->work.alloc(2) == cudaSuccess && cudaMemsetAsync(sc->work.p, 0, 2 * sizeof(int), st) == cudaSuccess &&
             cudaStreamSynchronize(st) == cudaSuccess;
   if (!ok) {
     ctx->last_error = std::string("scene upload: ") + cudaGetErrorString(cudaGetLastError());
@@ -382,6 +386,13 @@ extern "C" int gopbrt_scene_create(gopbrt_ctx* ctx, const gopbrt_scene_desc* d, 
   }
   sc->bvh_nodes = nodes.size();
   sc->bvh_depth = (uint64_t)bvh.depth;
+  // traversal stack: one entry per interior level (+ slack), [entry][thread] in dynamic shared memory
+  sc->stack_cap = std::max(4, bvh.depth + 2);
+  size_t smem = (size_t)sc->stack_cap * kTraceThreads * sizeof(unsigned);
+  sc->grid_ext = grid_for(ctx, (const void*)k_trace<false, false>, kTraceThreads, smem);
+  sc->grid_ext_c = grid_for(ctx, (const void*)k_trace<false, true>, kTraceThreads, smem);
+  sc->grid_any = grid_for(ctx, (const void*)k_trace<true, false>, kTraceThreads, smem);
+  sc->grid_any_c = grid_for(ctx, (const void*)k_trace<true, true>, kTraceThreads, smem);
   *out = sc;
   return GOPBRT_OK;
 }
@@ -429,10 +440,11 @@ static int trace_closest_rec_device(gopbrt_scene* sc, int64_t n, const double* r
   GP_CUDA(ctx, cudaMemcpyAsync(t, rays_soa7 + 6 * n, n * sizeof(double), cudaMemcpyDeviceToDevice, st));
   RaySoA r = soa7(const_cast<double*>(rays_soa7), n);
   r.tmax = t;
-  static int grid = 0;
-  if (!grid) grid = grid_for(ctx, (const void*)k_extend<false>, kTraceThreads);
   long long need = (n + kTraceThreads - 1) / kTraceThreads;
-  k_extend<false><<<(int)std::min<long long>(grid, need), kTraceThreads, 0, st>>>(sc->dev, r, prim_rec, nullptr, nullptr, n, sc->tctr.p);
+  size_t smem = (size_t)sc->stack_cap * kTraceThreads * sizeof(unsigned);
+  GP_CUDA(ctx, cudaMemsetAsync(sc->work.p, 0, sizeof(int), st));
+  k_trace<false, false><<<(int)std::min<long long>(sc->grid_ext, need), kTraceThreads, smem, st>>>(sc->dev, r, prim_rec, nullptr, nullptr, nullptr, n,
+                                                                                                    sc->stack_cap, sc->work.p, sc->tctr.p);
   ctx->launches++;
   GP_CUDA(ctx, cudaGetLastError());
   return GOPBRT_OK;
@@ -455,10 +467,11 @@ extern "C" int gopbrt_trace_any_device(gopbrt_scene* sc, int64_t n, const double
   gopbrt_ctx* ctx = sc->ctx;
   cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
   RaySoA r = soa7(const_cast<double*>(rays_soa7), n);
-  static int grid = 0;
-  if (!grid) grid = grid_for(ctx, (const void*)k_anyhit<false>, kTraceThreads);
   long long need = (n + kTraceThreads - 1) / kTraceThreads;
-  k_anyhit<false><<<(int)std::min<long long>(grid, need), kTraceThreads, 0, st>>>(sc->dev, r, hit, nullptr, nullptr, n, sc->tctr.p);
+  size_t smem = (size_t)sc->stack_cap * kTraceThreads * sizeof(unsigned);
+  GP_CUDA(ctx, cudaMemsetAsync(sc->work.p + 1, 0, sizeof(int), st));
+  k_trace<true, false><<<(int)std::min<long long>(sc->grid_any, need), kTraceThreads, smem, st>>>(sc->dev, r, nullptr, hit, nullptr, nullptr, n,
+                                                                                                   sc->stack_cap, sc->work.p + 1, sc->tctr.p);
   ctx->launches++;
   GP_CUDA(ctx, cudaGetLastError());
   return GOPBRT_OK;
@@ -614,15 +627,14 @@ static int render_impl(gopbrt_scene* sc, const gopbrt_camera* cam, const gopbrt_
   GP_CUDA(ctx, cudaMemsetAsync(sc->tctr.p, 0, sizeof(TraceCounters), st));
   const bool count = (flags & GOPBRT_FLAG_COUNT_TRAVERSAL) != 0;
 
-  static int g_gen = 0, g_shade = 0, g_ext = 0, g_ext_c = 0, g_any = 0, g_any_c = 0;
+  static int g_gen = 0, g_shade = 0;
   if (!g_gen) {
     g_gen = grid_for(ctx, (const void*)k_generate, 128);
     g_shade = grid_for(ctx, (const void*)k_shade, 128);
-    g_ext = grid_for(ctx, (const void*)k_extend<false>, kTraceThreads);
-    g_ext_c = grid_for(ctx, (const void*)k_extend<true>, kTraceThreads);
-    g_any = grid_for(ctx, (const void*)k_anyhit<false>, kTraceThreads);
-    g_any_c = grid_for(ctx, (const void*)k_anyhit<true>, kTraceThreads);
   }
+  const int g_ext = sc->grid_ext, g_ext_c = sc->grid_ext_c, g_any = sc->grid_any, g_any_c = sc->grid_any_c;
+  const size_t smem = (size_t)sc->stack_cap * kTraceThreads * sizeof(unsigned);
+  const int scap = sc->stack_cap;
   const int g_small = ctx->sm_count * 8;
 
   cudaEvent_t ev[2];
@@ -643,6 +655,9 @@ static int render_impl(gopbrt_scene* sc, const gopbrt_camera* cam, const gopbrt_
     ev_stage.push_back(stage);
   };
   uint64_t n_extend = 0, n_shadow = 0;
+  // debug aid: GOPBRT_ITER_LOG=<file> synchronises every iteration and logs the queue sizes (implies per-stage timing)
+  const char* iter_log_path = getenv("GOPBRT_ITER_LOG");
+  std::vector<int> iter_counts;
   for (long long base = 0; base < lanes_total && rc == GOPBRT_OK; base += lanes) {
     P.lane_base = base;
     P.lanes_active = std::min(lanes, lanes_total - base);
@@ -653,14 +668,20 @@ static int render_impl(gopbrt_scene* sc, const gopbrt_camera* cam, const gopbrt_
     k_generate<<<g_gen, 128, 0, st>>>(sc->dev, L, P, Q, nullptr, nullptr, W.rctr.p);
     ctx->launches += 2;
     for (;;) {
+      if (iter_log_path) {
+        int c[8];
+        cudaMemcpyAsync(c, Q.cnt, sizeof(c), cudaMemcpyDeviceToHost, st);
+        cudaStreamSynchronize(st);
+        iter_counts.push_back(c[0]);
+      }
       tick(ST_EXTEND);
-      if (count) k_extend<true><<<g_ext_c, kTraceThreads, 0, st>>>(sc->dev, L.ray, L.hit_rec, Q.extend, Q.cnt + 0, 0, sc->tctr.p);
-      else k_extend<false><<<g_ext, kTraceThreads, 0, st>>>(sc->dev, L.ray, L.hit_rec, Q.extend, Q.cnt + 0, 0, sc->tctr.p);
+      if (count) k_trace<false, true><<<g_ext_c, kTraceThreads, smem, st>>>(sc->dev, L.ray, L.hit_rec, nullptr, Q.extend, Q.cnt + 0, 0, scap, Q.cnt + 6, sc->tctr.p);
+      else k_trace<false, false><<<g_ext, kTraceThreads, smem, st>>>(sc->dev, L.ray, L.hit_rec, nullptr, Q.extend, Q.cnt + 0, 0, scap, Q.cnt + 6, sc->tctr.p);
       tick(ST_SHADE);
       k_shade<<<g_shade, 128, 0, st>>>(sc->dev, L, P, Q, W.rctr.p);
       tick(ST_SHADOW);
-      if (count) k_anyhit<true><<<g_any_c, kTraceThreads, 0, st>>>(sc->dev, L.sray, L.occluded, Q.shadow, Q.cnt + 2, 0, sc->tctr.p);
-      else k_anyhit<false><<<g_any, kTraceThreads, 0, st>>>(sc->dev, L.sray, L.occluded, Q.shadow, Q.cnt + 2, 0, sc->tctr.p);
+      if (count) k_trace<true, true><<<g_any_c, kTraceThreads, smem, st>>>(sc->dev, L.sray, nullptr, L.occluded, Q.shadow, Q.cnt + 2, 0, scap, Q.cnt + 7, sc->tctr.p);
+      else k_trace<true, false><<<g_any, kTraceThreads, smem, st>>>(sc->dev, L.sray, nullptr, L.occluded, Q.shadow, Q.cnt + 2, 0, scap, Q.cnt + 7, sc->tctr.p);
       k_shadow_resolve<<<g_small, 128, 0, st>>>(L, Q, W.rctr.p);
       tick(ST_RAYGEN);
       k_advance<<<1, 32, 0, st>>>(Q, W.rctr.p, W.remaining_dev);
@@ -670,6 +691,9 @@ static int render_impl(gopbrt_scene* sc, const gopbrt_camera* cam, const gopbrt_
       ctx->launches += 6;
       iterations++;
       n_extend++; n_shadow++;
+      // the host looks at the device-written "lanes still in flight" only every few iterations: an iteration over empty
+      // queues costs six near-empty launches, a synchronisation costs a full host round trip
+      if ((iterations & 3) != 0) continue;
       GP_CUDA(ctx, cudaStreamSynchronize(st));
       if (*W.remaining_host == 0) break;
       if (sc->cancel.load()) { rc = GOPBRT_ERR_CANCELLED; break; }
@@ -700,6 +724,28 @@ static int render_impl(gopbrt_scene* sc, const gopbrt_camera* cam, const gopbrt_
     stats->lanes = (uint64_t)lanes; stats->ms_total = ms; stats->bvh_nodes = sc->bvh_nodes; stats->bvh_depth = sc->bvh_depth;
     stats->tests_triangle = tcnt.t_tri; stats->tests_sphere_fast = tcnt.t_sph; stats->tests_general = tcnt.t_gen;
     stats->extend_launches = n_extend; stats->shadow_launches = n_shadow;
+    stats->shadow_tests_triangle = tcnt.st_tri; stats->shadow_tests_sphere_fast = tcnt.st_sph; stats->shadow_tests_general = tcnt.st_gen;
+    if (timing && iter_log_path) {
+      FILE* fp = fopen(iter_log_path, "w");
+      if (fp) {
+        size_t it = 0;
+        fprintf(fp, "iter,extend_rays,ms_extend,ms_shade,ms_shadow,ms_raygen\n");
+        double row[ST_N + 1] = {0, 0, 0, 0, 0, 0};
+        bool open_row = false;
+        for (size_t i = 0; i + 1 < ev_used; i++) {
+          float t = 0;
+          cudaEventElapsedTime(&t, W.events[i], W.events[i + 1]);
+          if (ev_stage[i] == ST_EXTEND) {
+            if (open_row) { fprintf(fp, "%zu,%d,%.4f,%.4f,%.4f,%.4f\n", it, it < iter_counts.size() ? iter_counts[it] : -1, row[ST_EXTEND], row[ST_SHADE], row[ST_SHADOW], row[ST_RAYGEN]); it++; }
+            for (int k = 0; k <= ST_N; k++) row[k] = 0;
+            open_row = true;
+          }
+          if (open_row) row[ev_stage[i]] += t;
+        }
+        if (open_row) fprintf(fp, "%zu,%d,%.4f,%.4f,%.4f,%.4f\n", it, it < iter_counts.size() ? iter_counts[it] : -1, row[ST_EXTEND], row[ST_SHADE], row[ST_SHADOW], row[ST_RAYGEN]);
+        fclose(fp);
+      }
+    }
     if (timing) {
       double acc[ST_N + 1] = {0, 0, 0, 0, 0, 0};
       for (size_t i = 0; i + 1 < ev_used; i++) {

@@ -48,21 +48,16 @@ GP_HD bool is_inf(double x) { return fabs(x) == d_inf(); }
 GP_HD bool sign_bit(double x) { return (f2b(x) >> 63) != 0; }
 GP_HD double copy_sign(double mag, double sgn) { return b2f((f2b(mag) & 0x7fffffffffffffffULL) | (f2b(sgn) & 0x8000000000000000ULL)); }
 
-// math.Nextafter restricted to the two call shapes of pkg/math/math.go:122-128.
-// NextFloatUp(v) = Nextafter(v, v+1): NaN stays NaN; v+1 == v (|v| >= 2^53, +-Inf) returns v; 0 -> smallest denormal.
+// math.Nextafter restricted to the two call shapes of pkg/math/math.go:122-128, branch-free.
+// NextFloatUp(v) = Nextafter(v, v+1): v+1 == v (|v| >= 2^53 on the positive side, +-Inf) returns v unchanged — NOT the
+// true next float; 0 (either sign) -> smallest positive denormal; NaN stays NaN (its payload is irrelevant).
 GP_HD double next_up(double v) {
-  double y = v + 1;
-  if (is_nan(v)) return v;
-  if (v == y) return v;
-  if (v == 0) return b2f(1);
-  return (v > 0) ? b2f(f2b(v) + 1) : b2f(f2b(v) - 1);  // y > v always here
+  double stepped = (v < 0) ? b2f(f2b(v) - 1) : b2f(f2b(fabs(v)) + 1);
+  return (v + 1 == v) ? v : stepped;
 }
 GP_HD double next_down(double v) {
-  double y = v - 1;
-  if (is_nan(v)) return v;
-  if (v == y) return v;
-  if (v == 0) return b2f(0x8000000000000001ULL);
-  return (v > 0) ? b2f(f2b(v) - 1) : b2f(f2b(v) + 1);  // y < v always here
+  double stepped = (v > 0) ? b2f(f2b(v) - 1) : b2f(f2b(-fabs(v)) + 1);
+  return (v - 1 == v) ? v : stepped;
 }
 
 // math.Min / math.Max (Go): -Inf/+Inf first, NaN-propagating, signed-zero aware — NOT fmin/fmax.
@@ -219,14 +214,18 @@ GP_HD void coordinate_system(V3 v1, V3* v2, V3* v3) {
 }
 
 // ---- pkg/efloat (efloat.go, math.go) ----
-// `bad` accumulates the conditions on which efloat.Check panics (efloat.go:102-111); the kernels count them.
+// `bad` accumulates the conditions on which efloat.Check panics (efloat.go:102-111): Inf/NaN bounds or Low > High; the
+// kernels count them (the reference process would be dead at that point, so nothing after a panic needs to agree).
+// The interval bounds use fmin/fmax instead of Go's math.Min/Max: they differ only for NaN operands (a panic either
+// way) and in the sign of a zero result, which next_down/next_up erase (both zeros step to the same denormal).
 struct EF { double v, lo, hi; };
 GP_HD void ef_check(const EF& f, int& bad) {
-  if (is_inf(f.lo) || is_nan(f.lo) || is_inf(f.hi) || is_nan(f.hi) || f.lo > f.hi) bad = 1;
+  if (!(f.lo <= f.hi && fabs(f.lo) < d_inf() && fabs(f.hi) < d_inf())) bad = 1;
 }
 GP_HD EF ef_new(double v, double err, int& bad) {  // efloat.go:10-22
-  EF f; f.v = v; f.lo = v; f.hi = v;
-  if (err != 0) { f.lo = next_down(v - err); f.hi = next_up(v + err); }
+  EF f; f.v = v;
+  f.lo = (err != 0) ? next_down(v - err) : v;
+  f.hi = (err != 0) ? next_up(v + err) : v;
   ef_check(f, bad);
   return f;
 }
@@ -243,18 +242,20 @@ GP_HD EF ef_sub(EF f, EF o, int& bad) {
 GP_HD EF ef_mul(EF f, EF o, int& bad) {
   double p0 = f.lo * o.lo, p1 = f.hi * o.lo, p2 = f.lo * o.hi, p3 = f.hi * o.hi;
   f.v = f.v * o.v;
-  f.lo = next_down(go_min(go_min(p0, p1), go_min(p2, p3)));
-  f.hi = next_up(go_max(go_max(p0, p1), go_max(p2, p3)));
+  f.lo = next_down(fmin(fmin(p0, p1), fmin(p2, p3)));
+  f.hi = next_up(fmax(fmax(p0, p1), fmax(p2, p3)));
+  if (is_nan(p0) || is_nan(p1) || is_nan(p2) || is_nan(p3)) bad = 1;  // Go's Min/Max would have propagated the NaN into Check
   ef_check(f, bad);
   return f;
 }
 GP_HD EF ef_div(EF f, EF o, int& bad) {
   f.v = f.v / o.v;
-  if (o.lo < 0 && o.hi > 0) { f.lo = -d_inf(); f.hi = d_inf(); }
+  if (o.lo < 0 && o.hi > 0) { f.lo = -d_inf(); f.hi = d_inf(); bad = 1; }
   else {
     double d0 = f.lo / o.lo, d1 = f.hi / o.lo, d2 = f.lo / o.hi, d3 = f.hi / o.hi;
-    f.lo = next_down(go_min(go_min(d0, d1), go_min(d2, d3)));
-    f.hi = next_up(go_max(go_max(d0, d1), go_max(d2, d3)));
+    f.lo = next_down(fmin(fmin(d0, d1), fmin(d2, d3)));
+    f.hi = next_up(fmax(fmax(d0, d1), fmax(d2, d3)));
+    if (is_nan(d0) || is_nan(d1) || is_nan(d2) || is_nan(d3)) bad = 1;
   }
   ef_check(f, bad);
   return f;

@@ -54,7 +54,7 @@ struct RenderCounters {
 
 struct Queues {
   int *extend, *extend_next, *shadow, *regen, *regen_next;
-  int* cnt;  // [0]=extend [1]=extend_next [2]=shadow [3]=regen [4]=regen_next [5]=done lanes
+  int* cnt;  // [0]=extend [1]=extend_next [2]=shadow [3]=regen [4]=regen_next [6]=extend work counter [7]=any-hit work counter
 };
 
 GP_D void queue_push(int* q, int* cnt, bool pred, int v) {
@@ -803,6 +803,8 @@ __global__ void k_advance(Queues Q, RenderCounters* ctr, int* host_visible_remai
     Q.cnt[2] = 0;
     Q.cnt[3] = Q.cnt[4];  // regen <- regen_next
     Q.cnt[4] = 0;
+    Q.cnt[6] = 0;  // work counters of the persistent traversal warps
+    Q.cnt[7] = 0;
     *host_visible_remaining = Q.cnt[0] + Q.cnt[3];
   }
 }

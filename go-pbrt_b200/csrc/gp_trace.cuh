@@ -19,73 +19,10 @@ constexpr int kTraceThreads = 128;
 struct RaySoA { double *ox, *oy, *oz, *dx, *dy, *dz, *tmax; };
 
 struct TraceCounters {
-  unsigned long long nodes, prims, snodes, sprims, efloat_panics, stack_overflows, t_tri, t_sph, t_gen;
+  unsigned long long nodes, prims, snodes, sprims, efloat_panics, stack_overflows, t_tri, t_sph, t_gen, st_tri, st_sph, st_gen;
 };
 
 struct TravCnt { unsigned long long nodes, prims, tri, sph, gen; };
-
-template <bool ANY, bool COUNT>
-GP_D bool traverse(const DevScene& sc, Ray& ray, int* hit_rec, unsigned* stack /* this thread's column */, int stride,
-                   TravCnt& cnt, int& bad, int& overflow) {
-  V3 invd = mk3(1 / ray.d.x, 1 / ray.d.y, 1 / ray.d.z);
-  int nx = invd.x < 0, ny = invd.y < 0, nz = invd.z < 0;
-  int sp = 0;
-  unsigned cur = 0;
-  bool any = false;
-  if (sc.n_nodes == 0) return false;
-  for (;;) {
-    float4 n0 = __ldg(sc.nodes + 2 * (size_t)cur);
-    float4 n1 = __ldg(sc.nodes + 2 * (size_t)cur + 1);
-    if (COUNT) cnt.nodes++;
-    unsigned a = __float_as_uint(n0.w), b = __float_as_uint(n1.w);
-    if (slab_test((double)n0.x, (double)n0.y, (double)n0.z, (double)n1.x, (double)n1.y, (double)n1.z, ray.o, invd, nx, ny, nz, ray.tmax)) {
-      unsigned np = b >> 8;
-      if (np > 0) {
-        for (unsigned i = 0; i < np; i++) {
-          unsigned ri = a + i;
-          const PrimRec* rec = sc.recs + ri;
-          uint32_t flags = rec->flags;
-          bool cand;
-          if ((flags & RK_KIND_MASK) == RK_TRIANGLE) {
-            const double* d = rec->d;
-            double x0 = go_min(go_min(d[0], d[3]), d[6]), x1 = go_max(go_max(d[0], d[3]), d[6]);
-            double y0 = go_min(go_min(d[1], d[4]), d[7]), y1 = go_max(go_max(d[1], d[4]), d[7]);
-            double z0 = go_min(go_min(d[2], d[5]), d[8]), z1 = go_max(go_max(d[2], d[5]), d[8]);
-            cand = slab_test(x0, y0, z0, x1, y1, z1, ray.o, invd, nx, ny, nz, ray.tmax);
-          } else {
-            const double* bb = sc.rec_bounds + (size_t)ri * 6;
-            cand = slab_test(bb[0], bb[1], bb[2], bb[3], bb[4], bb[5], ray.o, invd, nx, ny, nz, ray.tmax);
-          }
-          if (!cand) continue;
-          if (COUNT) {
-            cnt.prims++;
-            if ((flags & RK_KIND_MASK) == RK_TRIANGLE) cnt.tri++;
-            else if (flags & RF_FAST) cnt.sph++;
-            else cnt.gen++;
-          }
-          double t;
-          if (prim_test(sc, rec, flags, ray, &t, bad)) {
-            if (ANY) return true;
-            ray.tmax = t;  // r.TMax = tHit (primitive.go:51)
-            *hit_rec = (int)ri;
-            any = true;
-          }
-        }
-        if (sp == 0) break;
-        cur = stack[(--sp) * stride];
-      } else {
-        if (sp >= kStackDepth) { overflow = 1; break; }
-        int neg = (b & 3) == 0 ? nx : ((b & 3) == 1 ? ny : nz);
-        if (neg) { stack[(sp++) * stride] = cur + 1; cur = a; }
-        else { stack[(sp++) * stride] = a; cur = cur + 1; }
-      }
-    } else {
-      if (sp == 0) break;
-      cur = stack[(--sp) * stride];
-    }
-  }
-  return any;
-}
 
 GP_D unsigned long long warp_sum(unsigned long long v) {
 #pragma unroll
@@ -93,61 +30,151 @@ GP_D unsigned long long warp_sum(unsigned long long v) {
   return v;
 }
 
-// closest hit.  queue == nullptr: ray i is lane i (batched API); otherwise lane = queue[i] for i < *count.
-// out: rays.tmax[lane] = tHit (unchanged on a miss), hit_rec[lane] = leaf-record index or -1.
-template <bool COUNT>
-__global__ void __launch_bounds__(kTraceThreads) k_extend(DevScene sc, RaySoA rays, int* __restrict__ hit_rec, const int* __restrict__ queue,
-                                                          const int* __restrict__ count, long long n_direct, TraceCounters* ctr) {
-  __shared__ unsigned s_stack[kStackDepth * kTraceThreads];
-  long long n = queue ? (long long)*count : n_direct;
+constexpr int kChunkMax = 256;     // most ray indices a warp claims with one atomicAdd (fewer when the queue is short)
+constexpr int kRefillIdle = 8;     // idle lanes that trigger a refill from the warp's chunk
+
+// Persistent warps with dynamic ray replacement ("while-while" traversal):
+//   refill  idle lanes take the next ray of the warp's chunk (one atomicAdd per 256 rays), so a warp is never held
+//           hostage by its single longest ray;
+//   phase 1 every lane descends inner nodes until it holds a leaf or its traversal ends;
+//   phase 2 the lanes holding a leaf run the primitive candidates (own-bound test, then the float64/EFloat shape test)
+//           together.
+// Visit order per ray is the reference's: near child first by split axis and ray sign, far child on the stack;
+// a leaf's primitives in order with the running tMax (closest hit) or first hit wins (any hit).
+// ANY=false: rays.tmax[lane] = tHit (unchanged on a miss), hit_rec[lane] = leaf-record index or -1.
+// ANY=true : occluded[lane] = 1/0.
+// queue == nullptr: ray i is lane i (batched API); otherwise lane = queue[i] for i < *count.
+// dynamic shared memory: stack_cap * blockDim.x unsigned, [entry][thread] (bank-conflict free).
+template <bool ANY, bool COUNT>
+__global__ void __launch_bounds__(kTraceThreads, 4) k_trace(DevScene sc, RaySoA rays, int* __restrict__ hit_rec, unsigned char* __restrict__ occluded,
+                                                            const int* __restrict__ queue, const int* __restrict__ count, long long n_direct,
+                                                            int stack_cap, int* work_counter, TraceCounters* ctr) {
+  extern __shared__ unsigned s_stack[];
+  unsigned* stack = s_stack + threadIdx.x;
+  const int stride = kTraceThreads;
+  const unsigned FULL = 0xffffffffu, DONE = 0xffffffffu;
+  const int lane_id = threadIdx.x & 31;
+  const long long n = queue ? (long long)*count : n_direct;
   TravCnt c = {0, 0, 0, 0, 0};
   int bad = 0, ovf = 0;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    long long lane = queue ? queue[i] : i;
-    Ray r;
-    r.o = mk3(rays.ox[lane], rays.oy[lane], rays.oz[lane]);
-    r.d = mk3(rays.dx[lane], rays.dy[lane], rays.dz[lane]);
-    r.tmax = rays.tmax[lane];
-    int rec = -1;
-    traverse<false, COUNT>(sc, r, &rec, s_stack + threadIdx.x, kTraceThreads, c, bad, ovf);
-    rays.tmax[lane] = r.tmax;
-    hit_rec[lane] = rec;
-  }
-  if (COUNT) {
-    c.nodes = warp_sum(c.nodes); c.prims = warp_sum(c.prims); c.tri = warp_sum(c.tri); c.sph = warp_sum(c.sph); c.gen = warp_sum(c.gen);
-    if ((threadIdx.x & 31) == 0) {
-      atomicAdd(&ctr->nodes, c.nodes); atomicAdd(&ctr->prims, c.prims);
-      atomicAdd(&ctr->t_tri, c.tri); atomicAdd(&ctr->t_sph, c.sph); atomicAdd(&ctr->t_gen, c.gen);
+  // chunk size: large enough to amortise the atomic, small enough that a short queue still spreads over every warp
+  long long per_warp = n / ((long long)gridDim.x * (kTraceThreads / 32) * 2);
+  const int kChunk = per_warp >= kChunkMax ? kChunkMax : (per_warp <= 32 ? 32 : (int)(per_warp & ~31LL));
+
+  bool has_ray = false;
+  long long lane = 0;
+  Ray ray;
+  V3 invd;
+  int nx = 0, ny = 0, nz = 0, sp = 0, rec = -1;
+  unsigned cur = DONE;
+  bool hit_any = false;
+  long long w_next = 0, w_end = 0;  // warp-uniform chunk [w_next, w_end)
+  bool exhausted = false;
+
+  for (;;) {
+    // ---- refill
+    unsigned idle = __ballot_sync(FULL, !has_ray);
+    if (idle != 0 && (__popc(idle) >= kRefillIdle || idle == FULL) && !(exhausted && w_next >= w_end)) {
+      if (w_next >= w_end) {
+        int base = 0;
+        if (lane_id == 0) base = atomicAdd(work_counter, kChunk);
+        base = __shfl_sync(FULL, base, 0);
+        if ((long long)base >= n) { exhausted = true; w_next = w_end = 0; }
+        else { w_next = base; w_end = (long long)base + kChunk < n ? (long long)base + kChunk : n; }
+      }
+      long long avail = w_end - w_next;
+      int need = __popc(idle);
+      int take = (long long)need < avail ? need : (int)avail;
+      if (!has_ray) {
+        int r = __popc(idle & ((1u << lane_id) - 1u));
+        if (r < take) {
+          long long i = w_next + r;
+          lane = queue ? queue[i] : i;
+          ray.o = mk3(rays.ox[lane], rays.oy[lane], rays.oz[lane]);
+          ray.d = mk3(rays.dx[lane], rays.dy[lane], rays.dz[lane]);
+          ray.tmax = rays.tmax[lane];
+          invd = mk3(1 / ray.d.x, 1 / ray.d.y, 1 / ray.d.z);  // bvh.go:665-666
+          nx = invd.x < 0; ny = invd.y < 0; nz = invd.z < 0;
+          sp = 0; rec = -1; hit_any = false;
+          cur = sc.n_nodes > 0 ? 0u : DONE;
+          has_ray = true;
+        }
+      }
+      w_next += take;
+    }
+    if (__ballot_sync(FULL, has_ray) == 0) {
+      if (exhausted && w_next >= w_end) break;
+      continue;
+    }
+    // ---- phase 1: descend to the next leaf
+    unsigned leaf_a = 0, leaf_n = 0;
+    while (cur != DONE) {
+      float4 n0 = __ldg(sc.nodes + 2 * (size_t)cur);
+      float4 n1 = __ldg(sc.nodes + 2 * (size_t)cur + 1);
+      if (COUNT) c.nodes++;
+      unsigned a = __float_as_uint(n0.w), b = __float_as_uint(n1.w);
+      bool pass = slab_test((double)n0.x, (double)n0.y, (double)n0.z, (double)n1.x, (double)n1.y, (double)n1.z, ray.o, invd, nx, ny, nz, ray.tmax);
+      unsigned np = b >> 8;
+      if (pass && np == 0) {
+        if (sp >= stack_cap) { ovf = 1; cur = DONE; break; }
+        int neg = (b & 3) == 0 ? nx : ((b & 3) == 1 ? ny : nz);
+        if (neg) { stack[(sp++) * stride] = cur + 1; cur = a; }
+        else { stack[(sp++) * stride] = a; cur = cur + 1; }
+        continue;
+      }
+      cur = sp > 0 ? stack[(--sp) * stride] : DONE;  // a finished leaf and a missed node both continue from the stack
+      if (pass) { leaf_a = a; leaf_n = np; break; }
+    }
+    // ---- phase 2: the leaf's primitives
+    for (unsigned i = 0; i < leaf_n; i++) {
+      unsigned ri = leaf_a + i;
+      const PrimRec* prec = sc.recs + ri;
+      uint32_t flags = prec->flags;
+      bool cand;
+      if ((flags & RK_KIND_MASK) == RK_TRIANGLE) {
+        // the triangle's own float64 world bound = min/max of its vertices (finite, so fmin/fmax == Go's Min/Max up to
+        // the sign of a zero, which the slab test cannot observe)
+        const double* d = prec->d;
+        double x0 = fmin(fmin(d[0], d[3]), d[6]), x1 = fmax(fmax(d[0], d[3]), d[6]);
+        double y0 = fmin(fmin(d[1], d[4]), d[7]), y1 = fmax(fmax(d[1], d[4]), d[7]);
+        double z0 = fmin(fmin(d[2], d[5]), d[8]), z1 = fmax(fmax(d[2], d[5]), d[8]);
+        cand = slab_test(x0, y0, z0, x1, y1, z1, ray.o, invd, nx, ny, nz, ray.tmax);
+      } else {
+        const double* bb = sc.rec_bounds + (size_t)ri * 6;
+        cand = slab_test(bb[0], bb[1], bb[2], bb[3], bb[4], bb[5], ray.o, invd, nx, ny, nz, ray.tmax);
+      }
+      if (!cand) continue;
+      if (COUNT) {
+        c.prims++;
+        if ((flags & RK_KIND_MASK) == RK_TRIANGLE) c.tri++;
+        else if (flags & RF_FAST) c.sph++;
+        else c.gen++;
+      }
+      double t;
+      if (prim_test(sc, prec, flags, ray, &t, bad)) {
+        hit_any = true;
+        if (ANY) { cur = DONE; break; }
+        ray.tmax = t;  // r.TMax = tHit (primitive.go:51)
+        rec = (int)ri;
+      }
+    }
+    // ---- retire finished rays
+    if (has_ray && cur == DONE) {
+      if (ANY) occluded[lane] = hit_any ? 1 : 0;
+      else { rays.tmax[lane] = ray.tmax; hit_rec[lane] = rec; }
+      has_ray = false;
     }
   }
-  if (bad) atomicAdd(&ctr->efloat_panics, 1ULL);
-  if (ovf) atomicAdd(&ctr->stack_overflows, 1ULL);
-}
-
-// any hit over the shadow-ray queue.  occluded[lane] = 1/0.
-template <bool COUNT>
-__global__ void __launch_bounds__(kTraceThreads) k_anyhit(DevScene sc, RaySoA rays, unsigned char* __restrict__ occluded,
-                                                          const int* __restrict__ queue, const int* __restrict__ count, long long n_direct,
-                                                          TraceCounters* ctr) {
-  __shared__ unsigned s_stack[kStackDepth * kTraceThreads];
-  long long n = queue ? (long long)*count : n_direct;
-  TravCnt c = {0, 0, 0, 0, 0};
-  int bad = 0, ovf = 0;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    long long lane = queue ? queue[i] : i;
-    Ray r;
-    r.o = mk3(rays.ox[lane], rays.oy[lane], rays.oz[lane]);
-    r.d = mk3(rays.dx[lane], rays.dy[lane], rays.dz[lane]);
-    r.tmax = rays.tmax[lane];
-    int rec = -1;
-    bool hit = traverse<true, COUNT>(sc, r, &rec, s_stack + threadIdx.x, kTraceThreads, c, bad, ovf);
-    occluded[lane] = hit ? 1 : 0;
-  }
   if (COUNT) {
     c.nodes = warp_sum(c.nodes); c.prims = warp_sum(c.prims); c.tri = warp_sum(c.tri); c.sph = warp_sum(c.sph); c.gen = warp_sum(c.gen);
-    if ((threadIdx.x & 31) == 0) {
-      atomicAdd(&ctr->snodes, c.nodes); atomicAdd(&ctr->sprims, c.prims);
-      atomicAdd(&ctr->t_tri, c.tri); atomicAdd(&ctr->t_sph, c.sph); atomicAdd(&ctr->t_gen, c.gen);
+    if (lane_id == 0) {
+      if (ANY) {
+        atomicAdd(&ctr->snodes, c.nodes); atomicAdd(&ctr->sprims, c.prims);
+        atomicAdd(&ctr->st_tri, c.tri); atomicAdd(&ctr->st_sph, c.sph); atomicAdd(&ctr->st_gen, c.gen);
+      } else {
+        atomicAdd(&ctr->nodes, c.nodes); atomicAdd(&ctr->prims, c.prims);
+        atomicAdd(&ctr->t_tri, c.tri); atomicAdd(&ctr->t_sph, c.sph); atomicAdd(&ctr->t_gen, c.gen);
+      }
     }
   }
   if (bad) atomicAdd(&ctr->efloat_panics, 1ULL);

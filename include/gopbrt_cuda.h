@@ -210,8 +210,9 @@ typedef struct {
   uint64_t lanes;
   double ms_total, ms_raygen, ms_extend, ms_shade, ms_shadow, ms_film, ms_download;
   uint64_t bvh_nodes, bvh_depth;
-  uint64_t tests_triangle, tests_sphere_fast, tests_general; /* closest + any-hit shape tests by record kind (COUNT_TRAVERSAL) */
+  uint64_t tests_triangle, tests_sphere_fast, tests_general; /* closest-hit shape tests by record kind (COUNT_TRAVERSAL) */
   uint64_t extend_launches, shadow_launches;
+  uint64_t shadow_tests_triangle, shadow_tests_sphere_fast, shadow_tests_general; /* any-hit, same split */
 } gopbrt_stats;
 
 /* ---- lifecycle ---- */
