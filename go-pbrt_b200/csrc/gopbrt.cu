@@ -64,10 +64,10 @@ struct DevBuf {
 struct Workspace {  // per-scene render workspace, kept between gopbrt_render calls of the same shape
   long long lanes = 0;
   size_t bytes_tables = 0, bytes_tilepix = 0;
-  DevBuf<double> f64;     // all double planes
-  DevBuf<int> i32;        // int planes + queues
-  DevBuf<unsigned long long> u64;
-  DevBuf<unsigned char> u8;
+  DevBuf<RayRec> ray;
+  DevBuf<ShadowRec> sray;
+  DevBuf<PathRec> path;
+  DevBuf<int> i32;        // queues
   DevBuf<double> tables, tilepix;
   DevBuf<int> cnt;
   DevBuf<RenderCounters> rctr;
@@ -389,10 +389,10 @@ extern "C" int gopbrt_scene_create(gopbrt_ctx* ctx, const gopbrt_scene_desc* d, 
   // traversal stack: one entry per interior level (+ slack), [entry][thread] in dynamic shared memory
   sc->stack_cap = std::max(4, bvh.depth + 2);
   size_t smem = (size_t)sc->stack_cap * kTraceThreads * sizeof(unsigned);
-  sc->grid_ext = grid_for(ctx, (const void*)k_trace<false, false>, kTraceThreads, smem);
-  sc->grid_ext_c = grid_for(ctx, (const void*)k_trace<false, true>, kTraceThreads, smem);
-  sc->grid_any = grid_for(ctx, (const void*)k_trace<true, false>, kTraceThreads, smem);
-  sc->grid_any_c = grid_for(ctx, (const void*)k_trace<true, true>, kTraceThreads, smem);
+  sc->grid_ext = grid_for(ctx, (const void*)k_trace<0, false>, kTraceThreads, smem);
+  sc->grid_ext_c = grid_for(ctx, (const void*)k_trace<0, true>, kTraceThreads, smem);
+  sc->grid_any = grid_for(ctx, (const void*)k_trace<2, false>, kTraceThreads, smem);
+  sc->grid_any_c = grid_for(ctx, (const void*)k_trace<2, true>, kTraceThreads, smem);
   *out = sc;
   return GOPBRT_OK;
 }
@@ -423,42 +423,31 @@ static RaySoA soa7(double* base, long long n) {
   return r;
 }
 
-__global__ void k_rec_to_prim(DevScene sc, int* __restrict__ rec, long long n) {
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    int r = rec[i];
-    rec[i] = r >= 0 ? (int)sc.recs[r].prim : -1;
-  }
-}
-
-// closest hit over device-resident rays; prim_rec receives LEAF-RECORD indices (internal form)
-static int trace_closest_rec_device(gopbrt_scene* sc, int64_t n, const double* rays_soa7, int32_t* prim_rec, double* t, void* stream) {
-  if (!sc || n < 0) return GOPBRT_ERR_INVALID;
-  if (n == 0) return GOPBRT_OK;
+// closest hit over device-resident SoA rays: packs them into RayRec, traces, unpacks.  prim (may be null) receives
+// primitive ids, rec (may be null) leaf-record indices, t the hit distance (tmax where nothing was hit).
+static int trace_closest_soa_device(gopbrt_scene* sc, int64_t n, const double* rays_soa7, int32_t* prim, int32_t* rec, double* t, cudaStream_t st) {
   gopbrt_ctx* ctx = sc->ctx;
-  cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
-  // the kernel writes tHit into the tmax plane; keep the caller's rays intact by working on `t`
-  GP_CUDA(ctx, cudaMemcpyAsync(t, rays_soa7 + 6 * n, n * sizeof(double), cudaMemcpyDeviceToDevice, st));
+  DevBuf<RayRec> recs;
+  GP_CUDA(ctx, recs.alloc((size_t)n));
   RaySoA r = soa7(const_cast<double*>(rays_soa7), n);
-  r.tmax = t;
+  int gs = ctx->sm_count * 8;
+  k_pack_rays<<<gs, 256, 0, st>>>(r, recs.p, n);
   long long need = (n + kTraceThreads - 1) / kTraceThreads;
   size_t smem = (size_t)sc->stack_cap * kTraceThreads * sizeof(unsigned);
   GP_CUDA(ctx, cudaMemsetAsync(sc->work.p, 0, sizeof(int), st));
-  k_trace<false, false><<<(int)std::min<long long>(sc->grid_ext, need), kTraceThreads, smem, st>>>(sc->dev, r, prim_rec, nullptr, nullptr, nullptr, n,
-                                                                                                    sc->stack_cap, sc->work.p, sc->tctr.p);
-  ctx->launches++;
+  k_trace<0, false><<<(int)std::min<long long>(sc->grid_ext, need), kTraceThreads, smem, st>>>(sc->dev, recs.p, nullptr, nullptr, nullptr, nullptr, nullptr, n,
+                                                                                                sc->stack_cap, sc->work.p, sc->tctr.p, nullptr);
+  k_unpack_hits<<<gs, 256, 0, st>>>(sc->dev, recs.p, prim, rec, t, n);
+  ctx->launches += 3;
   GP_CUDA(ctx, cudaGetLastError());
+  GP_CUDA(ctx, cudaStreamSynchronize(st));  // recs is freed on return
   return GOPBRT_OK;
 }
 
 extern "C" int gopbrt_trace_closest_device(gopbrt_scene* sc, int64_t n, const double* rays_soa7, int32_t* prim, double* t, void* stream) {
-  int rc = trace_closest_rec_device(sc, n, rays_soa7, prim, t, stream);
-  if (rc != GOPBRT_OK || n == 0) return rc;
-  gopbrt_ctx* ctx = sc->ctx;
-  cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
-  k_rec_to_prim<<<ctx->sm_count * 8, 256, 0, st>>>(sc->dev, prim, n);
-  ctx->launches++;
-  GP_CUDA(ctx, cudaGetLastError());
-  return GOPBRT_OK;
+  if (!sc || n < 0) return GOPBRT_ERR_INVALID;
+  if (n == 0) return GOPBRT_OK;
+  return trace_closest_soa_device(sc, n, rays_soa7, prim, nullptr, t, stream ? (cudaStream_t)stream : sc->ctx->stream);
 }
 
 extern "C" int gopbrt_trace_any_device(gopbrt_scene* sc, int64_t n, const double* rays_soa7, uint8_t* hit, void* stream) {
@@ -466,14 +455,18 @@ extern "C" int gopbrt_trace_any_device(gopbrt_scene* sc, int64_t n, const double
   if (n == 0) return GOPBRT_OK;
   gopbrt_ctx* ctx = sc->ctx;
   cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+  DevBuf<RayRec> recs;
+  GP_CUDA(ctx, recs.alloc((size_t)n));
   RaySoA r = soa7(const_cast<double*>(rays_soa7), n);
+  k_pack_rays<<<ctx->sm_count * 8, 256, 0, st>>>(r, recs.p, n);
   long long need = (n + kTraceThreads - 1) / kTraceThreads;
   size_t smem = (size_t)sc->stack_cap * kTraceThreads * sizeof(unsigned);
   GP_CUDA(ctx, cudaMemsetAsync(sc->work.p + 1, 0, sizeof(int), st));
-  k_trace<true, false><<<(int)std::min<long long>(sc->grid_any, need), kTraceThreads, smem, st>>>(sc->dev, r, nullptr, hit, nullptr, nullptr, n,
-                                                                                                   sc->stack_cap, sc->work.p + 1, sc->tctr.p);
-  ctx->launches++;
+  k_trace<1, false><<<(int)std::min<long long>(sc->grid_any, need), kTraceThreads, smem, st>>>(sc->dev, recs.p, nullptr, nullptr, hit, nullptr, nullptr, n,
+                                                                                                sc->stack_cap, sc->work.p + 1, sc->tctr.p, nullptr);
+  ctx->launches += 2;
   GP_CUDA(ctx, cudaGetLastError());
+  GP_CUDA(ctx, cudaStreamSynchronize(st));
   return GOPBRT_OK;
 }
 
@@ -495,7 +488,7 @@ extern "C" int gopbrt_trace_closest(gopbrt_scene* sc, int64_t n, const double* o
   GP_CUDA(ctx, nn.alloc(3 * (size_t)n));
   const double* src[7] = {ox, oy, oz, dx, dy, dz, tmax};
   for (int k = 0; k < 7; k++) GP_CUDA(ctx, cudaMemcpyAsync(rays.p + (size_t)k * n, src[k], n * sizeof(double), cudaMemcpyHostToDevice, st));
-  int rc = trace_closest_rec_device(sc, n, rays.p, rec.p, tt.p, st);
+  int rc = trace_closest_soa_device(sc, n, rays.p, nullptr, rec.p, tt.p, st);
   if (rc != GOPBRT_OK) return rc;
   RaySoA r = soa7(rays.p, n);
   r.tmax = tt.p;
@@ -579,8 +572,7 @@ static int render_impl(gopbrt_scene* sc, const gopbrt_camera* cam, const gopbrt_
   GP_CUDA(ctx, cudaMemsetAsync(d_film, 0, (size_t)fw * fh * 4 * sizeof(double), st));
 
   // ---- workspace
-  const int N_F64 = 7 + 7 + 7 + 3 + 2;  // ray, shadow ray, L/beta/eta, pending, pFilm
-  size_t per_lane = (size_t)N_F64 * 8 + 4 * 4 + 5 * 4 + 2 * 8 + 3 + (size_t)P.ndims * P.spp * 8 + (size_t)tpw * tph * 4 * 8;
+  size_t per_lane = sizeof(RayRec) + sizeof(ShadowRec) + sizeof(PathRec) + 5 * 4 + (size_t)P.ndims * P.spp * 8 + (size_t)tpw * tph * 4 * 8;
   size_t free_b = 0, total_b = 0;
   GP_CUDA(ctx, cudaMemGetInfo(&free_b, &total_b));
   Workspace& W = sc->ws;
@@ -591,11 +583,11 @@ static int render_impl(gopbrt_scene* sc, const gopbrt_camera* cam, const gopbrt_
   if (lanes > 0x7fffff00LL) lanes = 0x7fffff00LL;
   size_t bt = (size_t)P.ndims * P.spp * lanes, bp = (size_t)tpw * tph * 4 * lanes;
   if (W.lanes != lanes || W.bytes_tables != bt || W.bytes_tilepix != bp) {
-    W.f64.release(); W.i32.release(); W.u64.release(); W.u8.release(); W.tables.release(); W.tilepix.release();
-    GP_CUDA(ctx, W.f64.alloc((size_t)N_F64 * lanes));
-    GP_CUDA(ctx, W.i32.alloc((size_t)(4 + 5) * lanes));
-    GP_CUDA(ctx, W.u64.alloc((size_t)2 * lanes));
-    GP_CUDA(ctx, W.u8.alloc((size_t)3 * lanes));
+    W.ray.release(); W.sray.release(); W.path.release(); W.i32.release(); W.tables.release(); W.tilepix.release();
+    GP_CUDA(ctx, W.ray.alloc((size_t)lanes));
+    GP_CUDA(ctx, W.sray.alloc((size_t)lanes));
+    GP_CUDA(ctx, W.path.alloc((size_t)lanes));
+    GP_CUDA(ctx, W.i32.alloc((size_t)5 * lanes));
     GP_CUDA(ctx, W.tables.alloc(std::max<size_t>(bt, 1)));
     GP_CUDA(ctx, W.tilepix.alloc(bp));
     if (!W.cnt.p) GP_CUDA(ctx, W.cnt.alloc(8));
@@ -608,19 +600,11 @@ static int render_impl(gopbrt_scene* sc, const gopbrt_camera* cam, const gopbrt_
   }
   Lanes L;
   L.n = lanes;
-  double* f = W.f64.p;
-  auto plane = [&](int k) { return f + (size_t)k * lanes; };
-  L.ray = RaySoA{plane(0), plane(1), plane(2), plane(3), plane(4), plane(5), plane(6)};
-  L.sray = RaySoA{plane(7), plane(8), plane(9), plane(10), plane(11), plane(12), plane(13)};
-  L.Lr = plane(14); L.Lg = plane(15); L.Lb = plane(16); L.br = plane(17); L.bg = plane(18); L.bb = plane(19); L.eta_scale = plane(20);
-  L.pr = plane(21); L.pg = plane(22); L.pb = plane(23); L.fx = plane(24); L.fy = plane(25);
+  L.ray = W.ray.p; L.sray = W.sray.p; L.path = W.path.p;
   int* ip = W.i32.p;
-  L.hit_rec = ip; L.bounces = ip + lanes; L.pix = ip + 2 * lanes; L.sidx = ip + 3 * lanes;
   Queues Q;
-  Q.extend = ip + 4 * lanes; Q.extend_next = ip + 5 * lanes; Q.shadow = ip + 6 * lanes; Q.regen = ip + 7 * lanes; Q.regen_next = ip + 8 * lanes;
+  Q.extend = ip; Q.extend_next = ip + lanes; Q.shadow = ip + 2 * lanes; Q.regen = ip + 3 * lanes; Q.regen_next = ip + 4 * lanes;
   Q.cnt = W.cnt.p;
-  L.rng_state = W.u64.p; L.rng_inc = W.u64.p + lanes;
-  L.occluded = W.u8.p; L.pend_gt10 = W.u8.p + lanes; L.has_sample = W.u8.p + 2 * lanes;
   L.tables = W.tables.p; L.tilepix = W.tilepix.p;
 
   GP_CUDA(ctx, cudaMemsetAsync(W.rctr.p, 0, sizeof(RenderCounters), st));
@@ -675,20 +659,19 @@ static int render_impl(gopbrt_scene* sc, const gopbrt_camera* cam, const gopbrt_
         iter_counts.push_back(c[0]);
       }
       tick(ST_EXTEND);
-      if (count) k_trace<false, true><<<g_ext_c, kTraceThreads, smem, st>>>(sc->dev, L.ray, L.hit_rec, nullptr, Q.extend, Q.cnt + 0, 0, scap, Q.cnt + 6, sc->tctr.p);
-      else k_trace<false, false><<<g_ext, kTraceThreads, smem, st>>>(sc->dev, L.ray, L.hit_rec, nullptr, Q.extend, Q.cnt + 0, 0, scap, Q.cnt + 6, sc->tctr.p);
+      if (count) k_trace<0, true><<<g_ext_c, kTraceThreads, smem, st>>>(sc->dev, L.ray, nullptr, nullptr, nullptr, Q.extend, Q.cnt + 0, 0, scap, Q.cnt + 6, sc->tctr.p, nullptr);
+      else k_trace<0, false><<<g_ext, kTraceThreads, smem, st>>>(sc->dev, L.ray, nullptr, nullptr, nullptr, Q.extend, Q.cnt + 0, 0, scap, Q.cnt + 6, sc->tctr.p, nullptr);
       tick(ST_SHADE);
       k_shade<<<g_shade, 128, 0, st>>>(sc->dev, L, P, Q, W.rctr.p);
       tick(ST_SHADOW);
-      if (count) k_trace<true, true><<<g_any_c, kTraceThreads, smem, st>>>(sc->dev, L.sray, nullptr, L.occluded, Q.shadow, Q.cnt + 2, 0, scap, Q.cnt + 7, sc->tctr.p);
-      else k_trace<true, false><<<g_any, kTraceThreads, smem, st>>>(sc->dev, L.sray, nullptr, L.occluded, Q.shadow, Q.cnt + 2, 0, scap, Q.cnt + 7, sc->tctr.p);
-      k_shadow_resolve<<<g_small, 128, 0, st>>>(L, Q, W.rctr.p);
+      if (count) k_trace<2, true><<<g_any_c, kTraceThreads, smem, st>>>(sc->dev, nullptr, L.sray, L.path, nullptr, Q.shadow, Q.cnt + 2, 0, scap, Q.cnt + 7, sc->tctr.p, &W.rctr.p->radiance_gt10);
+      else k_trace<2, false><<<g_any, kTraceThreads, smem, st>>>(sc->dev, nullptr, L.sray, L.path, nullptr, Q.shadow, Q.cnt + 2, 0, scap, Q.cnt + 7, sc->tctr.p, &W.rctr.p->radiance_gt10);
       tick(ST_RAYGEN);
       k_advance<<<1, 32, 0, st>>>(Q, W.rctr.p, W.remaining_dev);
       std::swap(Q.extend, Q.extend_next);
       std::swap(Q.regen, Q.regen_next);
       k_generate<<<g_gen, 128, 0, st>>>(sc->dev, L, P, Q, Q.regen, Q.cnt + 3, W.rctr.p);
-      ctx->launches += 6;
+      ctx->launches += 5;
       iterations++;
       n_extend++; n_shadow++;
       // the host looks at the device-written "lanes still in flight" only every few iterations: an iteration over empty

@@ -17,19 +17,11 @@ namespace gp {
 
 struct Lanes {
   long long n;
-  RaySoA ray;
-  int* hit_rec;
-  RaySoA sray;
-  unsigned char* occluded;
-  double *Lr, *Lg, *Lb, *br, *bg, *bb, *eta_scale;
-  double *pr, *pg, *pb;
-  unsigned char* pend_gt10;
-  unsigned long long *rng_state, *rng_inc;
-  int *bounces, *pix, *sidx;
-  unsigned char* has_sample;
-  double *fx, *fy;
-  double* tables;   // [dim][k][lane]
-  double* tilepix;  // [tile pixel][4][lane]
+  RayRec* ray;      // current path segment + closest-hit result
+  ShadowRec* sray;  // pending visibility segment + gated light sample
+  PathRec* path;    // throughput, radiance, sampler stream
+  double* tables;   // [dim][k][lane] stratified 1-D tables
+  double* tilepix;  // [tile pixel][4][lane] FilmTile accumulators
 };
 
 struct RenderParams {
@@ -546,15 +538,16 @@ __global__ void __launch_bounds__(128) k_generate(DevScene sc, Lanes L, RenderPa
     if (valid) {
       lane = in_queue ? in_queue[i] : i;
       long long tile = (P.lane_base + lane) * P.world + P.rank;
-      if (L.has_sample[lane]) {
-        RGB Lc = rgb(L.Lr[lane], L.Lg[lane], L.Lb[lane]);
+      PathRec pt = L.path[lane];
+      if (pt.has_sample) {
+        RGB Lc = rgb(pt.Lr, pt.Lg, pt.Lb);
         if (is_nan(Lc.r) || is_nan(Lc.g) || is_nan(Lc.b)) { Lc = rgb(0.1, 0.1, 0.1); nans++; }  // integrator.go:256-257
-        film_add_sample(L, P, lane, tile, L.fx[lane], L.fy[lane], Lc);
-        L.has_sample[lane] = 0;
+        film_add_sample(L, P, lane, tile, pt.fx, pt.fy, Lc);
+        pt.has_sample = 0;
       }
       Smp s;
-      s.state = L.rng_state[lane]; s.inc = L.rng_inc[lane]; s.sidx = L.sidx[lane]; s.cur1 = 0; s.cur2 = 0; s.lane = lane;
-      int pix = L.pix[lane];
+      s.state = pt.rng_state; s.inc = pt.rng_inc; s.sidx = pt.sidx; s.cur1 = 0; s.cur2 = 0; s.lane = lane;
+      int pix = pt.pix;
       long long x0, y0, x1, y1;
       tile_bounds(P, tile, &x0, &y0, &x1, &y1);
       long long tw = x1 - x0, area = tw * (y1 - y0);
@@ -600,18 +593,20 @@ __global__ void __launch_bounds__(128) k_generate(DevScene sc, Lanes L, RenderPa
         }
         ray = xf_ray(P.camera_to_world, ray, nullptr, nullptr);
         (void)time;  // ray.Time = Lerp(time, open, open): unused without animated transforms
-        L.ray.ox[lane] = ray.o.x; L.ray.oy[lane] = ray.o.y; L.ray.oz[lane] = ray.o.z;
-        L.ray.dx[lane] = ray.d.x; L.ray.dy[lane] = ray.d.y; L.ray.dz[lane] = ray.d.z;
-        L.ray.tmax[lane] = d_inf();
-        L.fx[lane] = fx; L.fy[lane] = fy;
-        L.Lr[lane] = 0; L.Lg[lane] = 0; L.Lb[lane] = 0;
-        L.br[lane] = 1.0; L.bg[lane] = 1.0; L.bb[lane] = 1.0;
-        L.eta_scale[lane] = 1.0;
-        L.bounces[lane] = (s.cur1 << 8) | (s.cur2 << 16);  // bounces in bits 0-7, sampler dimensions above
+        RayRec rr;
+        rr.ox = ray.o.x; rr.oy = ray.o.y; rr.oz = ray.o.z; rr.dx = ray.d.x; rr.dy = ray.d.y; rr.dz = ray.d.z;
+        rr.tmax = d_inf(); rr.hit_rec = -1; rr.pad = 0;
+        L.ray[lane] = rr;
+        pt.fx = fx; pt.fy = fy;
+        pt.Lr = 0; pt.Lg = 0; pt.Lb = 0;
+        pt.br = 1.0; pt.bg = 1.0; pt.bb = 1.0;
+        pt.eta_scale = 1.0;
+        pt.bounces = (s.cur1 << 8) | (s.cur2 << 16);  // bounces in bits 0-7, sampler dimensions above
         cam++;
         go = true;
       }
-      L.rng_state[lane] = s.state; L.rng_inc[lane] = s.inc; L.sidx[lane] = s.sidx; L.pix[lane] = pix;
+      pt.rng_state = s.state; pt.rng_inc = s.inc; pt.sidx = s.sidx; pt.pix = pix;
+      L.path[lane] = pt;
     }
     queue_push(Q.extend, Q.cnt + 0, go, (int)lane);
   }
@@ -639,15 +634,17 @@ __global__ void __launch_bounds__(128) k_shade(DevScene sc, Lanes L, RenderParam
     long long lane = 0;
     if (valid) {
       lane = Q.extend[i];
-      int packed = L.bounces[lane];
+      PathRec pt = L.path[lane];
+      RayRec rr = L.ray[lane];
+      int packed = pt.bounces;
       int bounces = (packed & 255) + 1;  // bounces++ (path.go:41)
-      int rec = L.hit_rec[lane];
+      int rec = rr.hit_rec;
       finished = true;
       if (rec >= 0 && bounces < P.max_depth) {  // path.go:66
         Ray ray;
-        ray.o = mk3(L.ray.ox[lane], L.ray.oy[lane], L.ray.oz[lane]);
-        ray.d = mk3(L.ray.dx[lane], L.ray.dy[lane], L.ray.dz[lane]);
-        ray.tmax = L.ray.tmax[lane];
+        ray.o = mk3(rr.ox, rr.oy, rr.oz);
+        ray.d = mk3(rr.dx, rr.dy, rr.dz);
+        ray.tmax = rr.tmax;
         Hit h;
         int prim;
         hit_record(sc, rec, ray, ray.tmax, &h, &prim, bad);
@@ -656,18 +653,18 @@ __global__ void __launch_bounds__(128) k_shade(DevScene sc, Lanes L, RenderParam
           n_unsupported++;
         } else {
           Smp s;
-          s.state = L.rng_state[lane]; s.inc = L.rng_inc[lane]; s.sidx = L.sidx[lane];
+          s.state = pt.rng_state; s.inc = pt.rng_inc; s.sidx = pt.sidx;
           s.cur1 = (packed >> 8) & 255; s.cur2 = (packed >> 16) & 255; s.lane = lane;
           unsigned long long fast_pixel = 0;
           if (P.mode == 1) {
             long long tile = (P.lane_base + lane) * P.world + P.rank;
             long long x0, y0, x1, y1;
             tile_bounds(P, tile, &x0, &y0, &x1, &y1);
-            int pix = L.pix[lane];
+            int pix = pt.pix;
             long long px = x0 + pix % (x1 - x0), py = y0 + pix / (x1 - x0);
             fast_pixel = (unsigned long long)((py - P.cy0) * (P.cx1 - P.cx0) + (px - P.cx0));
           }
-          RGB beta = rgb(L.br[lane], L.bg[lane], L.bb[lane]);
+          RGB beta = rgb(pt.br, pt.bg, pt.bb);
           Intr ref; ref.p = h.p; ref.perr = h.perr; ref.n = h.n;
           // --- UniformSampleOneLight (integrator.go:48-77), skipped for perfectly specular BSDFs (path.go:84)
           if (bsdf.kind != BX_NONE && matches(bsdf.type, BSDF_ALL & ~BSDF_SPECULAR)) {
@@ -709,12 +706,13 @@ __global__ void __launch_bounds__(128) k_shade(DevScene sc, Lanes L, RenderParam
                     V3 origin = offset_ray_origin(ref.p, ref.perr, ref.n, ls.p1.p - ref.p);
                     V3 target = offset_ray_origin(ls.p1.p, ls.p1.perr, ls.p1.n, origin - ls.p1.p);
                     V3 d = target - origin;
-                    L.sray.ox[lane] = ref.p.x; L.sray.oy[lane] = ref.p.y; L.sray.oz[lane] = ref.p.z;
-                    L.sray.dx[lane] = d.x; L.sray.dy[lane] = d.y; L.sray.dz[lane] = d.z;
-                    L.sray.tmax[lane] = 1 - 0.0001;
                     RGB c = beta * Ld;  // Ld := beta.Mul(...) (path.go:85)
-                    L.pr[lane] = c.r; L.pg[lane] = c.g; L.pb[lane] = c.b;
-                    L.pend_gt10[lane] = max_comp(Ld) > 10 ? 1 : 0;  // integrator.go:73-75 panics; counted when unoccluded
+                    ShadowRec sr;
+                    sr.ox = ref.p.x; sr.oy = ref.p.y; sr.oz = ref.p.z; sr.dx = d.x; sr.dy = d.y; sr.dz = d.z;  // tMax = 1 - ShadowEpsilon
+                    sr.pr = c.r; sr.pg = c.g; sr.pb = c.b;
+                    sr.gt10 = max_comp(Ld) > 10 ? 1 : 0;  // integrator.go:73-75 panics; counted when unoccluded
+                    sr.pad = 0; sr.pad2[0] = 0; sr.pad2[1] = 0;
+                    L.sray[lane] = sr;
                     shadow = true;
                   }
                 }
@@ -723,7 +721,7 @@ __global__ void __launch_bounds__(128) k_shade(DevScene sc, Lanes L, RenderParam
             if (!shadow) {
               // L.AddAssign(beta.Mul(0)) (path.go:85-86): a no-op unless beta is not finite (0*Inf = NaN), kept for parity
               RGB z = beta * rgb(0, 0, 0);
-              L.Lr[lane] += z.r; L.Lg[lane] += z.g; L.Lb[lane] += z.b;
+              pt.Lr += z.r; pt.Lg += z.g; pt.Lb += z.b;
             }
           }
           // --- sample the BSDF for the next direction (path.go:90-117); wo = ray.Direction, sic
@@ -734,12 +732,12 @@ __global__ void __launch_bounds__(128) k_shade(DevScene sc, Lanes L, RenderParam
           if (!(is_black(f) || pdf == 0.0)) {
             double wiAbsDotPdf = fabs(dot(wi, h.ns)) / pdf;
             beta = beta * (f * wiAbsDotPdf);
-            double etaScale = L.eta_scale[lane];
+            double etaScale = pt.eta_scale;
             if ((sflags & BSDF_SPECULAR) > 0 && (sflags & BSDF_TRANSMISSION) > 0) {
               double eta = bsdf.eta;
               if (dot(ray.d, h.n) > 0) etaScale *= eta * eta;
               else etaScale *= 1 / (eta * eta);
-              L.eta_scale[lane] = etaScale;
+              pt.eta_scale = etaScale;
             }
             V3 o = offset_ray_origin(h.p, h.perr, h.n, wi);  // SpawnRay (interaction.go:68-77); wi is BSDF-local
             bool alive = true;
@@ -750,20 +748,22 @@ __global__ void __launch_bounds__(128) k_shade(DevScene sc, Lanes L, RenderParam
               else beta = beta / (1 - q);
             }
             if (alive) {
-              L.ray.ox[lane] = o.x; L.ray.oy[lane] = o.y; L.ray.oz[lane] = o.z;
-              L.ray.dx[lane] = wi.x; L.ray.dy[lane] = wi.y; L.ray.dz[lane] = wi.z;
-              L.ray.tmax[lane] = d_inf();
-              L.br[lane] = beta.r; L.bg[lane] = beta.g; L.bb[lane] = beta.b;
+              RayRec nr;
+              nr.ox = o.x; nr.oy = o.y; nr.oz = o.z; nr.dx = wi.x; nr.dy = wi.y; nr.dz = wi.z;
+              nr.tmax = d_inf(); nr.hit_rec = -1; nr.pad = 0;
+              L.ray[lane] = nr;
+              pt.br = beta.r; pt.bg = beta.g; pt.bb = beta.b;
               cont = true;
               finished = false;
             }
           }
-          L.rng_state[lane] = s.state; L.rng_inc[lane] = s.inc;
+          pt.rng_state = s.state; pt.rng_inc = s.inc;
           packed = (s.cur1 << 8) | (s.cur2 << 16);
         }
       }
-      L.bounces[lane] = (packed & ~255) | bounces;
-      if (finished) L.has_sample[lane] = 1;
+      pt.bounces = (packed & ~255) | bounces;
+      if (finished) pt.has_sample = 1;
+      L.path[lane] = pt;
     }
     queue_push(Q.shadow, Q.cnt + 2, shadow, (int)lane);
     queue_push(Q.extend_next, Q.cnt + 1, cont, (int)lane);
@@ -775,22 +775,6 @@ __global__ void __launch_bounds__(128) k_shade(DevScene sc, Lanes L, RenderParam
     if (n_dead) atomicAdd(&ctr->dead_mis_rays, n_dead);
   }
   if (bad) atomicAdd(&ctr->efloat_panics, 1ULL);
-}
-
-// adds the deferred light sample of every unoccluded shadow ray to its lane's radiance (L.AddAssign(Ld), path.go:86)
-__global__ void k_shadow_resolve(Lanes L, Queues Q, RenderCounters* ctr) {
-  long long n = Q.cnt[2];
-  unsigned long long gt10 = 0;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    int lane = Q.shadow[i];
-    if (!L.occluded[lane]) {
-      L.Lr[lane] += L.pr[lane]; L.Lg[lane] += L.pg[lane]; L.Lb[lane] += L.pb[lane];
-      if (L.pend_gt10[lane]) gt10++;
-    } else {  // blocked: Li = 0, so L += beta*0 (NaN only if beta is not finite)
-      L.Lr[lane] += L.pr[lane] * 0.0; L.Lg[lane] += L.pg[lane] * 0.0; L.Lb[lane] += L.pb[lane] * 0.0;
-    }
-  }
-  if (gt10) atomicAdd(&ctr->radiance_gt10, gt10);
 }
 
 // end of a wavefront iteration: rotate the queues on the device and publish the number of lanes still in flight
@@ -851,8 +835,12 @@ __global__ void k_init_lanes(Lanes L, RenderParams P) {
     Smp s;
     s.state = 0x853c49e6748fea9bULL; s.inc = 0xda3e39cb94b95bdbULL;
     rng_set_sequence(s, (unsigned long long)tile);
-    L.rng_state[lane] = s.state; L.rng_inc[lane] = s.inc;
-    L.pix[lane] = -1; L.sidx[lane] = 0; L.has_sample[lane] = 0; L.bounces[lane] = 0;
+    PathRec pt;
+    pt.br = pt.bg = pt.bb = 1.0; pt.Lr = pt.Lg = pt.Lb = 0; pt.eta_scale = 1.0; pt.fx = pt.fy = 0;
+    pt.rng_state = s.state; pt.rng_inc = s.inc;
+    pt.pix = -1; pt.sidx = 0; pt.has_sample = 0; pt.bounces = 0;
+    pt.pad[0] = pt.pad[1] = pt.pad[2] = 0;
+    L.path[lane] = pt;
   }
 }
 

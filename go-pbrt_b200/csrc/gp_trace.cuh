@@ -18,6 +18,28 @@ constexpr int kTraceThreads = 128;
 
 struct RaySoA { double *ox, *oy, *oz, *dx, *dy, *dz, *tmax; };
 
+// Per-lane state is array-of-records, grouped by the stage that touches it.  The wavefront's active set is SPARSE
+// (a stage sees a few percent to a few tens of percent of the lanes, picked through an index queue), so a
+// plane-per-field layout would pull a whole 32-byte sector for every 8-byte field; with one aligned record per lane
+// every sector that is fetched is fully used, and a record moves with 16-byte vector loads/stores.
+struct __align__(32) RayRec {     // extend: in o,d,tmax; out tmax (= tHit), hit_rec.  64 B = 2 sectors
+  double ox, oy, oz, dx, dy, dz, tmax;
+  int hit_rec, pad;
+};
+struct __align__(32) ShadowRec {  // shade -> shadow: the visibility segment + the light sample it gates.  96 B = 3 sectors
+  double ox, oy, oz, dx, dy, dz;
+  double pr, pg, pb;              // beta * Ld, added to the path radiance if the segment is unoccluded
+  int gt10, pad;
+  double pad2[2];
+};
+struct __align__(32) PathRec {    // Path.Li loop state + sampler stream of the lane.  128 B = 4 sectors
+  double br, bg, bb, Lr, Lg, Lb, eta_scale, fx, fy;
+  unsigned long long rng_state, rng_inc;
+  int bounces, pix, sidx, has_sample;
+  double pad[3];
+};
+static_assert(sizeof(RayRec) == 64 && sizeof(ShadowRec) == 96 && sizeof(PathRec) == 128, "lane record layout");
+
 struct TraceCounters {
   unsigned long long nodes, prims, snodes, sprims, efloat_panics, stack_overflows, t_tri, t_sph, t_gen, st_tri, st_sph, st_gen;
 };
@@ -45,10 +67,15 @@ constexpr int kRefillIdle = 8;     // idle lanes that trigger a refill from the 
 // ANY=true : occluded[lane] = 1/0.
 // queue == nullptr: ray i is lane i (batched API); otherwise lane = queue[i] for i < *count.
 // dynamic shared memory: stack_cap * blockDim.x unsigned, [entry][thread] (bank-conflict free).
-template <bool ANY, bool COUNT>
-__global__ void __launch_bounds__(kTraceThreads, 4) k_trace(DevScene sc, RaySoA rays, int* __restrict__ hit_rec, unsigned char* __restrict__ occluded,
+// MODE 0: closest hit over RayRec.  MODE 1: any hit over RayRec, occluded[lane] = 1/0 (batched API).
+// MODE 2: any hit over the render's ShadowRec queue, resolved in place: an unoccluded segment adds its deferred light
+//         sample to the lane's radiance (L.AddAssign(Ld), path.go:86).
+template <int MODE, bool COUNT>
+__global__ void __launch_bounds__(kTraceThreads, 4) k_trace(DevScene sc, RayRec* __restrict__ rays, const ShadowRec* __restrict__ srays,
+                                                            PathRec* __restrict__ paths, unsigned char* __restrict__ occluded,
                                                             const int* __restrict__ queue, const int* __restrict__ count, long long n_direct,
-                                                            int stack_cap, int* work_counter, TraceCounters* ctr) {
+                                                            int stack_cap, int* work_counter, TraceCounters* ctr, unsigned long long* gt10_counter) {
+  constexpr bool ANY = MODE != 0;
   extern __shared__ unsigned s_stack[];
   unsigned* stack = s_stack + threadIdx.x;
   const int stride = kTraceThreads;
@@ -57,6 +84,7 @@ __global__ void __launch_bounds__(kTraceThreads, 4) k_trace(DevScene sc, RaySoA 
   const long long n = queue ? (long long)*count : n_direct;
   TravCnt c = {0, 0, 0, 0, 0};
   int bad = 0, ovf = 0;
+  unsigned long long gt10 = 0;
   // chunk size: large enough to amortise the atomic, small enough that a short queue still spreads over every warp
   long long per_warp = n / ((long long)gridDim.x * (kTraceThreads / 32) * 2);
   const int kChunk = per_warp >= kChunkMax ? kChunkMax : (per_warp <= 32 ? 32 : (int)(per_warp & ~31LL));
@@ -90,9 +118,19 @@ __global__ void __launch_bounds__(kTraceThreads, 4) k_trace(DevScene sc, RaySoA 
         if (r < take) {
           long long i = w_next + r;
           lane = queue ? queue[i] : i;
-          ray.o = mk3(rays.ox[lane], rays.oy[lane], rays.oz[lane]);
-          ray.d = mk3(rays.dx[lane], rays.dy[lane], rays.dz[lane]);
-          ray.tmax = rays.tmax[lane];
+          if (MODE == 2) {
+            const double2* q = (const double2*)(srays + lane);
+            double2 a = q[0], b = q[1], c2 = q[2];
+            ray.o = mk3(a.x, a.y, b.x);
+            ray.d = mk3(b.y, c2.x, c2.y);
+            ray.tmax = 1 - 0.0001;  // 1 - ShadowEpsilon (interaction.go:99)
+          } else {
+            const double2* q = (const double2*)(rays + lane);
+            double2 a = q[0], b = q[1], c2 = q[2], d2 = q[3];
+            ray.o = mk3(a.x, a.y, b.x);
+            ray.d = mk3(b.y, c2.x, c2.y);
+            ray.tmax = d2.x;
+          }
           invd = mk3(1 / ray.d.x, 1 / ray.d.y, 1 / ray.d.z);  // bvh.go:665-666
           nx = invd.x < 0; ny = invd.y < 0; nz = invd.z < 0;
           sp = 0; rec = -1; hit_any = false;
@@ -160,8 +198,24 @@ __global__ void __launch_bounds__(kTraceThreads, 4) k_trace(DevScene sc, RaySoA 
     }
     // ---- retire finished rays
     if (has_ray && cur == DONE) {
-      if (ANY) occluded[lane] = hit_any ? 1 : 0;
-      else { rays.tmax[lane] = ray.tmax; hit_rec[lane] = rec; }
+      if (MODE == 0) {
+        double2 out;
+        out.x = ray.tmax;
+        out.y = __longlong_as_double((long long)(unsigned)rec);  // {hit_rec, pad} share the record's last 8 bytes
+        ((double2*)(rays + lane))[3] = out;
+      } else if (MODE == 1) {
+        occluded[lane] = hit_any ? 1 : 0;
+      } else {
+        const ShadowRec* sr = srays + lane;
+        PathRec* pt = paths + lane;
+        double pr = sr->pr, pg = sr->pg, pb = sr->pb;
+        if (!hit_any) {
+          pt->Lr += pr; pt->Lg += pg; pt->Lb += pb;
+          if (sr->gt10) gt10++;
+        } else {  // blocked: Li = 0, so L += beta*0 (NaN only if beta is not finite)
+          pt->Lr += pr * 0.0; pt->Lg += pg * 0.0; pt->Lb += pb * 0.0;
+        }
+      }
       has_ray = false;
     }
   }
@@ -179,6 +233,26 @@ __global__ void __launch_bounds__(kTraceThreads, 4) k_trace(DevScene sc, RaySoA 
   }
   if (bad) atomicAdd(&ctr->efloat_panics, 1ULL);
   if (ovf) atomicAdd(&ctr->stack_overflows, 1ULL);
+  if (MODE == 2 && gt10) atomicAdd(gt10_counter, gt10);
+}
+
+// SoA <-> record packing for the batched API (host arrays are SoA float64)
+__global__ void k_pack_rays(RaySoA in, RayRec* __restrict__ out, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    RayRec r;
+    r.ox = in.ox[i]; r.oy = in.oy[i]; r.oz = in.oz[i]; r.dx = in.dx[i]; r.dy = in.dy[i]; r.dz = in.dz[i]; r.tmax = in.tmax[i];
+    r.hit_rec = -1; r.pad = 0;
+    out[i] = r;
+  }
+}
+// prim[i] = primitive id (or -1), t[i] = tHit
+__global__ void k_unpack_hits(DevScene sc, const RayRec* __restrict__ in, int* __restrict__ prim, int* __restrict__ rec_out, double* __restrict__ t, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    int r = in[i].hit_rec;
+    if (prim) prim[i] = r >= 0 ? (int)sc.recs[r].prim : -1;
+    if (rec_out) rec_out[i] = r;
+    t[i] = in[i].tmax;
+  }
 }
 
 // world-space hit point and geometric normal for the batched Aggregate.Intersect API (gopbrt_trace_closest)
