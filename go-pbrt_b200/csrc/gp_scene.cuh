@@ -159,14 +159,22 @@ GP_HD bool disk_test(const Ray& ray, double height, double radius, double innerR
 // ---- Triangle (new shape, defined by this backend + its oracle): watertight test in float64 ----
 GP_HD int max_dim(V3 v) { return (v.x > v.y) ? ((v.x > v.z) ? 0 : 2) : ((v.y > v.z) ? 1 : 2); }
 GP_HD V3 permute(V3 v, int x, int y, int z) { return mk3(comp(v, x), comp(v, y), comp(v, z)); }
-GP_HD bool tri_test(V3 p0, V3 p1, V3 p2, const Ray& ray, double* tHit, double* bary) {
+// per-ray part of the watertight test (depends on the ray direction only): permutation and shear constants
+struct TriRay { int kx, ky, kz; double Sx, Sy, Sz; };
+GP_HD TriRay tri_ray_setup(V3 dir) {
+  TriRay tr;
+  tr.kz = max_dim(vabs(dir));
+  tr.kx = tr.kz + 1; if (tr.kx == 3) tr.kx = 0;
+  tr.ky = tr.kx + 1; if (tr.ky == 3) tr.ky = 0;
+  V3 d = permute(dir, tr.kx, tr.ky, tr.kz);
+  tr.Sx = -d.x / d.z; tr.Sy = -d.y / d.z; tr.Sz = 1.0 / d.z;
+  return tr;
+}
+GP_HD bool tri_test_pre(V3 p0, V3 p1, V3 p2, const Ray& ray, const TriRay& tr, double* tHit, double* bary) {
   V3 p0t = p0 - ray.o, p1t = p1 - ray.o, p2t = p2 - ray.o;
-  int kz = max_dim(vabs(ray.d));
-  int kx = kz + 1; if (kx == 3) kx = 0;
-  int ky = kx + 1; if (ky == 3) ky = 0;
-  V3 d = permute(ray.d, kx, ky, kz);
+  int kx = tr.kx, ky = tr.ky, kz = tr.kz;
   p0t = permute(p0t, kx, ky, kz); p1t = permute(p1t, kx, ky, kz); p2t = permute(p2t, kx, ky, kz);
-  double Sx = -d.x / d.z, Sy = -d.y / d.z, Sz = 1.0 / d.z;
+  double Sx = tr.Sx, Sy = tr.Sy, Sz = tr.Sz;
   p0t.x += Sx * p0t.z; p0t.y += Sy * p0t.z;
   p1t.x += Sx * p1t.z; p1t.y += Sy * p1t.z;
   p2t.x += Sx * p2t.z; p2t.y += Sy * p2t.z;
@@ -186,6 +194,9 @@ GP_HD bool tri_test(V3 p0, V3 p1, V3 p2, const Ray& ray, double* tHit, double* b
   *tHit = t;
   if (bary) { bary[0] = e0 * invDet; bary[1] = e1 * invDet; bary[2] = e2 * invDet; }
   return true;
+}
+GP_HD bool tri_test(V3 p0, V3 p1, V3 p2, const Ray& ray, double* tHit, double* bary) {
+  return tri_test_pre(p0, p1, p2, ray, tri_ray_setup(ray.d), tHit, bary);
 }
 
 // ---- the surface interaction fields Path.Li reads (pkg/pbrt/interaction.go:23-30,123-148) ----
@@ -208,12 +219,9 @@ GP_HD void xf_hit(const M4& m, const M4& inv, Hit& h) {
 
 // generic primitive test used by both traversal kernels.  Returns true and the hit t (the new r.TMax,
 // primitive.go:51,102) if the primitive is hit within ray.tmax.  `bad` collects efloat.Check panics.
-GP_D bool prim_test(const DevScene& sc, const PrimRec* rec, uint32_t flags, const Ray& wray, double* tHit, int& bad) {
+// sphere / disk test (the long float64 + EFloat path); triangles are tested inline by the traversal kernel
+GP_D bool quadric_test(const DevScene& sc, const PrimRec* rec, uint32_t flags, const Ray& wray, double* tHit, int& bad) {
   uint32_t kind = flags & RK_KIND_MASK;
-  if (kind == RK_TRIANGLE) {
-    const double* d = rec->d;
-    return tri_test(mk3(d[0], d[1], d[2]), mk3(d[3], d[4], d[5]), mk3(d[6], d[7], d[8]), wray, tHit, nullptr);
-  }
   Ray ray = wray;
   if (kind == RK_SPHERE && (flags & RF_FAST)) {
     const double* d = rec->d;

@@ -54,6 +54,7 @@ GP_D unsigned long long warp_sum(unsigned long long v) {
 
 constexpr int kChunkMax = 256;     // most ray indices a warp claims with one atomicAdd (fewer when the queue is short)
 constexpr int kRefillIdle = 8;     // idle lanes that trigger a refill from the warp's chunk
+constexpr int kQuadricBatch = 8;   // parked sphere/disk tests that trigger their batched execution
 
 // Persistent warps with dynamic ray replacement ("while-while" traversal):
 //   refill  idle lanes take the next ray of the warp's chunk (one atomicAdd per 256 rays), so a warp is never held
@@ -93,8 +94,10 @@ __global__ void __launch_bounds__(kTraceThreads, 4) k_trace(DevScene sc, RayRec*
   long long lane = 0;
   Ray ray;
   V3 invd;
-  int nx = 0, ny = 0, nz = 0, sp = 0, rec = -1;
-  unsigned cur = DONE;
+  int nx = 0, ny = 0, nz = 0, sp = 0, rec = -1, pending = -1;
+  unsigned cur = DONE, leaf_a = 0, leaf_n = 0, leaf_i = 0;
+  TriRay tray;
+  tray.kx = tray.ky = tray.kz = 0; tray.Sx = tray.Sy = tray.Sz = 0;
   bool hit_any = false;
   long long w_next = 0, w_end = 0;  // warp-uniform chunk [w_next, w_end)
   bool exhausted = false;
@@ -133,7 +136,8 @@ __global__ void __launch_bounds__(kTraceThreads, 4) k_trace(DevScene sc, RayRec*
           }
           invd = mk3(1 / ray.d.x, 1 / ray.d.y, 1 / ray.d.z);  // bvh.go:665-666
           nx = invd.x < 0; ny = invd.y < 0; nz = invd.z < 0;
-          sp = 0; rec = -1; hit_any = false;
+          tray = tri_ray_setup(ray.d);
+          sp = 0; rec = -1; hit_any = false; pending = -1; leaf_n = 0; leaf_i = 0;
           cur = sc.n_nodes > 0 ? 0u : DONE;
           has_ray = true;
         }
@@ -144,60 +148,78 @@ __global__ void __launch_bounds__(kTraceThreads, 4) k_trace(DevScene sc, RayRec*
       if (exhausted && w_next >= w_end) break;
       continue;
     }
-    // ---- phase 1: descend to the next leaf
-    unsigned leaf_a = 0, leaf_n = 0;
-    while (cur != DONE) {
-      float4 n0 = __ldg(sc.nodes + 2 * (size_t)cur);
-      float4 n1 = __ldg(sc.nodes + 2 * (size_t)cur + 1);
-      if (COUNT) c.nodes++;
-      unsigned a = __float_as_uint(n0.w), b = __float_as_uint(n1.w);
-      bool pass = slab_test((double)n0.x, (double)n0.y, (double)n0.z, (double)n1.x, (double)n1.y, (double)n1.z, ray.o, invd, nx, ny, nz, ray.tmax);
-      unsigned np = b >> 8;
-      if (pass && np == 0) {
-        if (sp >= stack_cap) { ovf = 1; cur = DONE; break; }
-        int neg = (b & 3) == 0 ? nx : ((b & 3) == 1 ? ny : nz);
-        if (neg) { stack[(sp++) * stride] = cur + 1; cur = a; }
-        else { stack[(sp++) * stride] = a; cur = cur + 1; }
-        continue;
+    // ---- phase 1: descend to the next leaf (lanes that still have leaf candidates or a deferred test skip this)
+    if (leaf_i >= leaf_n && pending < 0) {
+      leaf_n = 0; leaf_i = 0;
+      while (cur != DONE) {
+        float4 n0 = __ldg(sc.nodes + 2 * (size_t)cur);
+        float4 n1 = __ldg(sc.nodes + 2 * (size_t)cur + 1);
+        if (COUNT) c.nodes++;
+        unsigned a = __float_as_uint(n0.w), b = __float_as_uint(n1.w);
+        bool pass = slab_test((double)n0.x, (double)n0.y, (double)n0.z, (double)n1.x, (double)n1.y, (double)n1.z, ray.o, invd, nx, ny, nz, ray.tmax);
+        unsigned np = b >> 8;
+        if (pass && np == 0) {
+          if (sp >= stack_cap) { ovf = 1; cur = DONE; break; }
+          int neg = (b & 3) == 0 ? nx : ((b & 3) == 1 ? ny : nz);
+          if (neg) { stack[(sp++) * stride] = cur + 1; cur = a; }
+          else { stack[(sp++) * stride] = a; cur = cur + 1; }
+          continue;
+        }
+        cur = sp > 0 ? stack[(--sp) * stride] : DONE;  // a finished leaf and a missed node both continue from the stack
+        if (pass) { leaf_a = a; leaf_n = np; break; }
       }
-      cur = sp > 0 ? stack[(--sp) * stride] : DONE;  // a finished leaf and a missed node both continue from the stack
-      if (pass) { leaf_a = a; leaf_n = np; break; }
     }
-    // ---- phase 2: the leaf's primitives
-    for (unsigned i = 0; i < leaf_n; i++) {
-      unsigned ri = leaf_a + i;
+    // ---- phase 2: the leaf's candidates in order; triangles are tested here, a sphere/disk candidate is parked in
+    //      `pending` (the lane stops at it, so the per-ray test order and running tMax stay the reference's)
+    while (pending < 0 && leaf_i < leaf_n) {
+      unsigned ri = leaf_a + leaf_i;
+      leaf_i++;
       const PrimRec* prec = sc.recs + ri;
       uint32_t flags = prec->flags;
-      bool cand;
       if ((flags & RK_KIND_MASK) == RK_TRIANGLE) {
-        // the triangle's own float64 world bound = min/max of its vertices (finite, so fmin/fmax == Go's Min/Max up to
-        // the sign of a zero, which the slab test cannot observe)
-        const double* d = prec->d;
-        double x0 = fmin(fmin(d[0], d[3]), d[6]), x1 = fmax(fmax(d[0], d[3]), d[6]);
-        double y0 = fmin(fmin(d[1], d[4]), d[7]), y1 = fmax(fmax(d[1], d[4]), d[7]);
-        double z0 = fmin(fmin(d[2], d[5]), d[8]), z1 = fmax(fmax(d[2], d[5]), d[8]);
-        cand = slab_test(x0, y0, z0, x1, y1, z1, ray.o, invd, nx, ny, nz, ray.tmax);
+        // own float64 world bound = min/max of the vertices (finite, so fmin/fmax == Go's Min/Max up to the sign of a
+        // zero, which the slab test cannot observe)
+        const double2* q = (const double2*)prec;
+        double2 v0 = q[0], v1 = q[1], v2 = q[2], v3 = q[3], v4 = q[4];  // {flags|prim, d0} {d1,d2} {d3,d4} {d5,d6} {d7,d8}
+        V3 p0 = mk3(v0.y, v1.x, v1.y), p1 = mk3(v2.x, v2.y, v3.x), p2 = mk3(v3.y, v4.x, v4.y);
+        double x0 = fmin(fmin(p0.x, p1.x), p2.x), x1 = fmax(fmax(p0.x, p1.x), p2.x);
+        double y0 = fmin(fmin(p0.y, p1.y), p2.y), y1 = fmax(fmax(p0.y, p1.y), p2.y);
+        double z0 = fmin(fmin(p0.z, p1.z), p2.z), z1 = fmax(fmax(p0.z, p1.z), p2.z);
+        if (!slab_test(x0, y0, z0, x1, y1, z1, ray.o, invd, nx, ny, nz, ray.tmax)) continue;
+        if (COUNT) { c.prims++; c.tri++; }
+        double t;
+        if (tri_test_pre(p0, p1, p2, ray, tray, &t, nullptr)) {
+          hit_any = true;
+          if (ANY) { cur = DONE; leaf_i = leaf_n; break; }
+          ray.tmax = t;  // r.TMax = tHit (primitive.go:51)
+          rec = (int)ri;
+        }
       } else {
         const double* bb = sc.rec_bounds + (size_t)ri * 6;
-        cand = slab_test(bb[0], bb[1], bb[2], bb[3], bb[4], bb[5], ray.o, invd, nx, ny, nz, ray.tmax);
+        if (!slab_test(bb[0], bb[1], bb[2], bb[3], bb[4], bb[5], ray.o, invd, nx, ny, nz, ray.tmax)) continue;
+        if (COUNT) { c.prims++; if (flags & RF_FAST) c.sph++; else c.gen++; }
+        pending = (int)ri;
       }
-      if (!cand) continue;
-      if (COUNT) {
-        c.prims++;
-        if ((flags & RK_KIND_MASK) == RK_TRIANGLE) c.tri++;
-        else if (flags & RF_FAST) c.sph++;
-        else c.gen++;
-      }
-      double t;
-      if (prim_test(sc, prec, flags, ray, &t, bad)) {
-        hit_any = true;
-        if (ANY) { cur = DONE; break; }
-        ray.tmax = t;  // r.TMax = tHit (primitive.go:51)
-        rec = (int)ri;
+    }
+    // ---- phase 3: the parked sphere/disk tests, run together once enough lanes hold one or nobody else can advance
+    {
+      unsigned pm = __ballot_sync(FULL, pending >= 0);
+      unsigned runnable = __ballot_sync(FULL, has_ray && pending < 0 && !(cur == DONE && leaf_i >= leaf_n));
+      if (pm != 0 && (__popc(pm) >= kQuadricBatch || runnable == 0)) {
+        if (pending >= 0) {
+          const PrimRec* prec = sc.recs + pending;
+          double t;
+          if (quadric_test(sc, prec, prec->flags, ray, &t, bad)) {
+            hit_any = true;
+            if (ANY) { cur = DONE; leaf_i = leaf_n; }
+            else { ray.tmax = t; rec = pending; }
+          }
+          pending = -1;
+        }
       }
     }
     // ---- retire finished rays
-    if (has_ray && cur == DONE) {
+    if (has_ray && cur == DONE && leaf_i >= leaf_n && pending < 0) {
       if (MODE == 0) {
         double2 out;
         out.x = ray.tmax;
