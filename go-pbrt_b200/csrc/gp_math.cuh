@@ -13,6 +13,7 @@
 
 #define GP_HD __host__ __device__ __forceinline__
 #define GP_D __device__ __forceinline__
+#define GP_HD_NOINLINE __host__ __device__ __noinline__
 
 namespace gp {
 
@@ -99,7 +100,7 @@ GP_HD double poly_cos(double zz) {
   return 1.0 - 0.5 * zz + zz * zz * ((((((-1.13585365213876817300e-11 * zz) + 2.08757008419747316778e-9) * zz + -2.75573141792967388112e-7) * zz +
                                        2.48015872888517045348e-5) * zz + -1.38888888888730564116e-3) * zz + 4.16666666666665929218e-2);
 }
-GP_HD double go_cos(double x) {
+GP_HD_NOINLINE static double go_cos(double x) {
   if (is_nan(x) || is_inf(x)) return b2f(0x7ff8000000000001ULL);
   bool sign = false;
   x = fabs(x);
@@ -114,7 +115,7 @@ GP_HD double go_cos(double x) {
   y = (j == 1 || j == 2) ? poly_sin(z, zz) : poly_cos(zz);
   return sign ? -y : y;
 }
-GP_HD double go_sin(double x) {
+GP_HD_NOINLINE static double go_sin(double x) {
   if (x == 0 || is_nan(x)) return x;
   if (is_inf(x)) return b2f(0x7ff8000000000001ULL);
   bool sign = false;
@@ -151,7 +152,7 @@ GP_HD double go_atan(double x) {
   if (x > 0) return go_satan(x);
   return -go_satan(-x);
 }
-GP_HD double go_atan2(double y, double x) {  // src/math/atan2.go
+GP_HD_NOINLINE static double go_atan2(double y, double x) {  // src/math/atan2.go
   if (is_nan(y) || is_nan(x)) return b2f(0x7ff8000000000001ULL);
   if (y == 0) {
     if (x >= 0 && !sign_bit(x)) return copy_sign(0.0, y);
@@ -177,7 +178,7 @@ GP_HD double go_asin(double x) {  // src/math/asin.go
   else temp = go_satan(x / temp);
   return sign ? -temp : temp;
 }
-GP_HD double go_acos(double x) { return kPiOver2 - go_asin(x); }
+GP_HD_NOINLINE static double go_acos(double x) { return kPiOver2 - go_asin(x); }
 
 // ---- pkg/geometry/xyz.go:424-614 ----
 struct V3 { double x, y, z; };

@@ -394,7 +394,7 @@ GP_D void sphere_sample(const DevScene& sc, const SphereDev& s, double ux, doubl
   it->n = n;
   *pdf = 1.0 / (s.phiMax * s.radius * (s.zMax - s.zMin));
 }
-GP_D void sphere_sample_at(const DevScene& sc, const SphereDev& s, const Intr& ref, double ux, double uy, Intr* it, double* pdf) {
+__device__ __noinline__ static void sphere_sample_at(const DevScene& sc, const SphereDev& s, const Intr& ref, double ux, double uy, Intr* it, double* pdf) {
   M4 m = load_m4(sc, s.xf, false);
   V3 pCenter = xf_point(m, mk3(0, 0, 0), mk3(0, 0, 0), nullptr);
   V3 pOrigin = offset_ray_origin(ref.p, ref.perr, ref.n, pCenter - ref.p);
@@ -433,7 +433,7 @@ GP_D void sphere_sample_at(const DevScene& sc, const SphereDev& s, const Intr& r
   if (s.flags & RF_REVERSE) it->n = it->n * -1.0;
   *pdf = 1.0 / (2.0 * kPi * (1.0 - cosThetaMax));  // UniformConePdf (sampling.go:169-171)
 }
-GP_D void disk_sample_at(const DevScene& sc, const DiskDev& d, const Intr& ref, double ux, double uy, Intr* it, double* pdf) {
+__device__ __noinline__ static void disk_sample_at(const DevScene& sc, const DiskDev& d, const Intr& ref, double ux, double uy, Intr* it, double* pdf) {
   M4 m = load_m4(sc, d.xf, false), inv = load_m4(sc, d.xf, true);
   double px, py;
   concentric_sample_disk(ux, uy, &px, &py);
@@ -621,7 +621,7 @@ __global__ void __launch_bounds__(128) k_generate(DevScene sc, Lanes L, RenderPa
 // One Path.Li loop body per lane (path.go:40-155) after the closest-hit query: scattering functions, one light
 // sample (UniformSampleOneLight / EstimateDirect) whose visibility test is deferred to the shadow queue, BSDF
 // sampling, throughput update, SpawnRay, Russian roulette.
-__global__ void __launch_bounds__(128) k_shade(DevScene sc, Lanes L, RenderParams P, Queues Q, RenderCounters* ctr) {
+__global__ void __launch_bounds__(128, 3) k_shade(DevScene sc, Lanes L, RenderParams P, Queues Q, RenderCounters* ctr) {
   long long n = Q.cnt[0];
   int lane_id = threadIdx.x & 31;
   unsigned long long n_unsupported = 0, n_dead = 0;
