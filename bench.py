@@ -218,12 +218,12 @@ def main():
     e2e_s = time.time() - e0
 
     vals = torch.tensor([ms_rank, e2e_s, wall], dtype=torch.float64, device=f"cuda:{local_rank}")
-    tot = torch.tensor([float(rays_rank), float(launches)], dtype=torch.float64, device=f"cuda:{local_rank}")
+    tot = torch.tensor([float(rays_rank), float(launches), float(stats[0]["camera_rays"])], dtype=torch.float64, device=f"cuda:{local_rank}")
     if world > 1:
         dist.all_reduce(vals, op=dist.ReduceOp.MAX)
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
     ms_total, e2e_total, wall_max = vals.tolist()
-    rays_total, launches_total = tot.tolist()
+    rays_total, launches_total, paths_total = tot.tolist()
 
     if rank == 0:
         K = args.steps
@@ -253,7 +253,7 @@ def main():
                 "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic",
                 "config": {"workload": wl["name"], "resolution": [W, H], "tile_size": args.tile, "sampler_mode": args.mode,
-                           "paths_per_step": stats[0]["camera_rays"] * (world if mode == abi.MODE_FAST else 1),
+                           "paths_per_step": int(paths_total),
                            "rays_per_step": rays_total / K, "lanes": stats[0]["lanes"], "wavefront_iterations": stats[0]["iterations"],
                            "partition": ("tiles t %% %d == rank" % world) if mode == abi.MODE_STRICT else "samples s % world == rank",
                            "l2_policy": "per-lane path/sampler/film state of %d lanes is %.1f GB >> 126 MB L2 (inputs larger than L2)" % (
