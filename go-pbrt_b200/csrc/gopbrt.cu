@@ -572,7 +572,7 @@ static int render_impl(gopbrt_scene* sc, const gopbrt_camera* cam, const gopbrt_
   GP_CUDA(ctx, cudaMemsetAsync(d_film, 0, (size_t)fw * fh * 4 * sizeof(double), st));
 
   // ---- workspace
-  size_t per_lane = sizeof(RayRec) + sizeof(ShadowRec) + sizeof(PathRec) + 5 * 4 + (size_t)P.ndims * P.spp * 8 + (size_t)tpw * tph * 4 * 8;
+  size_t per_lane = sizeof(RayRec) + sizeof(ShadowRec) + sizeof(PathRec) + 6 * 4 + (size_t)P.ndims * P.spp * 8 + (size_t)tpw * tph * 4 * 8;
   size_t free_b = 0, total_b = 0;
   GP_CUDA(ctx, cudaMemGetInfo(&free_b, &total_b));
   Workspace& W = sc->ws;
@@ -587,7 +587,7 @@ static int render_impl(gopbrt_scene* sc, const gopbrt_camera* cam, const gopbrt_
     GP_CUDA(ctx, W.ray.alloc((size_t)lanes));
     GP_CUDA(ctx, W.sray.alloc((size_t)lanes));
     GP_CUDA(ctx, W.path.alloc((size_t)lanes));
-    GP_CUDA(ctx, W.i32.alloc((size_t)5 * lanes));
+    GP_CUDA(ctx, W.i32.alloc((size_t)6 * lanes));
     GP_CUDA(ctx, W.tables.alloc(std::max<size_t>(bt, 1)));
     GP_CUDA(ctx, W.tilepix.alloc(bp));
     if (!W.cnt.p) GP_CUDA(ctx, W.cnt.alloc(8));
@@ -603,7 +603,7 @@ static int render_impl(gopbrt_scene* sc, const gopbrt_camera* cam, const gopbrt_
   L.ray = W.ray.p; L.sray = W.sray.p; L.path = W.path.p;
   int* ip = W.i32.p;
   Queues Q;
-  Q.extend = ip; Q.extend_next = ip + lanes; Q.shadow = ip + 2 * lanes; Q.regen = ip + 3 * lanes; Q.regen_next = ip + 4 * lanes;
+  Q.extend = ip; Q.extend_next = ip + lanes; Q.shadow = ip + 2 * lanes; Q.regen = ip + 3 * lanes; Q.regen_next = ip + 4 * lanes; Q.shade = ip + 5 * lanes;
   Q.cnt = W.cnt.p;
   L.tables = W.tables.p; L.tilepix = W.tilepix.p;
 
@@ -659,9 +659,10 @@ static int render_impl(gopbrt_scene* sc, const gopbrt_camera* cam, const gopbrt_
         iter_counts.push_back(c[0]);
       }
       tick(ST_EXTEND);
-      if (count) k_trace<0, true><<<g_ext_c, kTraceThreads, smem, st>>>(sc->dev, L.ray, nullptr, nullptr, nullptr, Q.extend, Q.cnt + 0, 0, scap, Q.cnt + 6, sc->tctr.p, nullptr);
-      else k_trace<0, false><<<g_ext, kTraceThreads, smem, st>>>(sc->dev, L.ray, nullptr, nullptr, nullptr, Q.extend, Q.cnt + 0, 0, scap, Q.cnt + 6, sc->tctr.p, nullptr);
+      if (count) k_trace<0, true><<<g_ext_c, kTraceThreads, smem, st>>>(sc->dev, L.ray, nullptr, L.path, nullptr, Q.extend, Q.cnt + 0, 0, scap, Q.cnt + 6, sc->tctr.p, nullptr);
+      else k_trace<0, false><<<g_ext, kTraceThreads, smem, st>>>(sc->dev, L.ray, nullptr, L.path, nullptr, Q.extend, Q.cnt + 0, 0, scap, Q.cnt + 6, sc->tctr.p, nullptr);
       tick(ST_SHADE);
+      k_split_hits<<<g_small, 256, 0, st>>>(L, Q);
       k_shade<<<g_shade, 128, 0, st>>>(sc->dev, L, P, Q, W.rctr.p);
       tick(ST_SHADOW);
       if (count) k_trace<2, true><<<g_any_c, kTraceThreads, smem, st>>>(sc->dev, nullptr, L.sray, L.path, nullptr, Q.shadow, Q.cnt + 2, 0, scap, Q.cnt + 7, sc->tctr.p, &W.rctr.p->radiance_gt10);
@@ -671,7 +672,7 @@ static int render_impl(gopbrt_scene* sc, const gopbrt_camera* cam, const gopbrt_
       std::swap(Q.extend, Q.extend_next);
       std::swap(Q.regen, Q.regen_next);
       k_generate<<<g_gen, 128, 0, st>>>(sc->dev, L, P, Q, Q.regen, Q.cnt + 3, W.rctr.p);
-      ctx->launches += 5;
+      ctx->launches += 6;
       iterations++;
       n_extend++; n_shadow++;
       // the host looks at the device-written "lanes still in flight" only every few iterations: an iteration over empty
@@ -699,8 +700,8 @@ static int render_impl(gopbrt_scene* sc, const gopbrt_camera* cam, const gopbrt_
   GP_CUDA(ctx, cudaMemcpy(&tcnt, sc->tctr.p, sizeof(tcnt), cudaMemcpyDeviceToHost));
   if (stats) {
     memset(stats, 0, sizeof(*stats));
-    stats->camera_rays = rcnt.camera_rays; stats->closest_rays = rcnt.closest_rays; stats->shadow_rays = rcnt.shadow_rays;
-    stats->dead_mis_rays = rcnt.dead_mis_rays; stats->nodes_visited = tcnt.nodes; stats->prim_tests = tcnt.prims;
+    stats->camera_rays = rcnt.camera_rays; stats->closest_rays = rcnt.closest_rays + rcnt.root_culled; stats->shadow_rays = rcnt.shadow_rays;
+    stats->dead_mis_rays = rcnt.dead_mis_rays; stats->nodes_visited = tcnt.nodes + (count ? rcnt.root_culled : 0); stats->prim_tests = tcnt.prims;
     stats->shadow_nodes_visited = tcnt.snodes; stats->shadow_prim_tests = tcnt.sprims; stats->radiance_gt10 = rcnt.radiance_gt10;
     stats->nan_samples = rcnt.nan_samples; stats->efloat_panics = rcnt.efloat_panics + tcnt.efloat_panics;
     stats->stack_overflows = tcnt.stack_overflows; stats->iterations = iterations; stats->launches = ctx->launches.load() - launches0;

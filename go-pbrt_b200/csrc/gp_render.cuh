@@ -42,11 +42,12 @@ struct RenderParams {
 
 struct RenderCounters {
   unsigned long long camera_rays, closest_rays, shadow_rays, dead_mis_rays, radiance_gt10, nan_samples, unsupported, efloat_panics;
+  unsigned long long root_culled;  // scene.Intersect queries answered by the root-bound test inside raygen
 };
 
 struct Queues {
-  int *extend, *extend_next, *shadow, *regen, *regen_next;
-  int* cnt;  // [0]=extend [1]=extend_next [2]=shadow [3]=regen [4]=regen_next [6]=extend work counter [7]=any-hit work counter
+  int *extend, *extend_next, *shadow, *regen, *regen_next, *shade;
+  int* cnt;  // [0]=extend [1]=extend_next [2]=shadow [3]=regen [4]=regen_next [5]=shade (hits) [6]=extend work counter [7]=any-hit work counter
 };
 
 GP_D void queue_push(int* q, int* cnt, bool pred, int v) {
@@ -384,7 +385,7 @@ GP_D bool compute_scattering(const DevScene& sc, int prim, const Hit& h, BSDF* b
 // ---------------------------------------------------------------- lights (pkg/lights, sphere.go:270-344, disk.go:160-170, shape.go:50-65)
 struct Intr { V3 p, perr, n; };
 GP_D void sphere_sample(const DevScene& sc, const SphereDev& s, double ux, double uy, Intr* it, double* pdf) {
-  M4 m = load_m4(sc, s.xf, false), inv = load_m4(sc, s.xf, true);
+  M4 m = load_m4_plain(sc, s.xf, false), inv = load_m4_plain(sc, s.xf, true);
   V3 pObj = uniform_sample_sphere(ux, uy) * s.radius;
   V3 n = normalized(xf_normal_inv(inv, pObj));
   if (s.flags & RF_REVERSE) n = n * -1.0;
@@ -395,7 +396,7 @@ GP_D void sphere_sample(const DevScene& sc, const SphereDev& s, double ux, doubl
   *pdf = 1.0 / (s.phiMax * s.radius * (s.zMax - s.zMin));
 }
 __device__ __noinline__ static void sphere_sample_at(const DevScene& sc, const SphereDev& s, const Intr& ref, double ux, double uy, Intr* it, double* pdf) {
-  M4 m = load_m4(sc, s.xf, false);
+  M4 m = load_m4_plain(sc, s.xf, false);
   V3 pCenter = xf_point(m, mk3(0, 0, 0), mk3(0, 0, 0), nullptr);
   V3 pOrigin = offset_ray_origin(ref.p, ref.perr, ref.n, pCenter - ref.p);
   if (dist2(pOrigin, pCenter) <= s.radius * s.radius) {
@@ -434,7 +435,7 @@ __device__ __noinline__ static void sphere_sample_at(const DevScene& sc, const S
   *pdf = 1.0 / (2.0 * kPi * (1.0 - cosThetaMax));  // UniformConePdf (sampling.go:169-171)
 }
 __device__ __noinline__ static void disk_sample_at(const DevScene& sc, const DiskDev& d, const Intr& ref, double ux, double uy, Intr* it, double* pdf) {
-  M4 m = load_m4(sc, d.xf, false), inv = load_m4(sc, d.xf, true);
+  M4 m = load_m4_plain(sc, d.xf, false), inv = load_m4_plain(sc, d.xf, true);
   double px, py;
   concentric_sample_disk(ux, uy, &px, &py);
   V3 pObj = mk3(px * d.radius, py * d.radius, d.height);
@@ -507,15 +508,19 @@ GP_D void film_add_sample(const Lanes& L, const RenderParams& P, long long lane,
   double p1fx = floor(dx + P.frx) + 1, p1fy = floor(dy + P.fry) + 1;
   long long p0x = (long long)go_max(p0fx, (double)bx0), p0y = (long long)go_max(p0fy, (double)by0);
   long long p1x = (long long)go_min(p1fx, (double)bx1), p1y = (long long)go_min(p1fy, (double)by1);
+  // contribSum += L*w*f with L == +0 leaves the (never negative-zero) sums untouched: only the weight moves
+  bool zero = Lc.r == 0 && Lc.g == 0 && Lc.b == 0 && !sign_bit(Lc.r) && !sign_bit(Lc.g) && !sign_bit(Lc.b);
   for (long long y = p0y; y < p1y; y++)
     for (long long x = p0x; x < p1x; x++) {
       double fw = 1.0;
       size_t k = (size_t)((y - by0) * P.tpw + (x - bx0)) * 4;
       double* q = L.tilepix + k * L.n + lane;
-      RGB c = Lc * (1.0 * fw);
-      q[0] += c.r;
-      q[(size_t)L.n] += c.g;
-      q[2 * (size_t)L.n] += c.b;
+      if (!zero) {
+        RGB c = Lc * (1.0 * fw);
+        q[0] += c.r;
+        q[(size_t)L.n] += c.g;
+        q[2 * (size_t)L.n] += c.b;
+      }
       q[3 * (size_t)L.n] += fw;
     }
 }
@@ -528,7 +533,7 @@ __global__ void __launch_bounds__(128) k_generate(DevScene sc, Lanes L, RenderPa
                                                   const int* __restrict__ in_count, RenderCounters* ctr) {
   long long n = in_queue ? (long long)*in_count : P.lanes_active;
   int lane_id = threadIdx.x & 31;
-  unsigned long long cam = 0, nans = 0;
+  unsigned long long cam = 0, nans = 0, culled = 0;
   long long warp_base0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) - lane_id;
   for (long long base = warp_base0; base < n; base += (long long)gridDim.x * blockDim.x) {
     long long i = base + lane_id;
@@ -539,11 +544,10 @@ __global__ void __launch_bounds__(128) k_generate(DevScene sc, Lanes L, RenderPa
       lane = in_queue ? in_queue[i] : i;
       long long tile = (P.lane_base + lane) * P.world + P.rank;
       PathRec pt = L.path[lane];
-      if (pt.has_sample) {
+      if (in_queue != nullptr) {  // every lane of the regeneration queue carries a finished sample
         RGB Lc = rgb(pt.Lr, pt.Lg, pt.Lb);
         if (is_nan(Lc.r) || is_nan(Lc.g) || is_nan(Lc.b)) { Lc = rgb(0.1, 0.1, 0.1); nans++; }  // integrator.go:256-257
         film_add_sample(L, P, lane, tile, pt.fx, pt.fy, Lc);
-        pt.has_sample = 0;
       }
       Smp s;
       s.state = pt.rng_state; s.inc = pt.rng_inc; s.sidx = pt.sidx; s.cur1 = 0; s.cur2 = 0; s.lane = lane;
@@ -551,23 +555,27 @@ __global__ void __launch_bounds__(128) k_generate(DevScene sc, Lanes L, RenderPa
       long long x0, y0, x1, y1;
       tile_bounds(P, tile, &x0, &y0, &x1, &y1);
       long long tw = x1 - x0, area = tw * (y1 - y0);
-      bool have = false;
-      for (;;) {
-        if (pix >= 0) {
-          // PixelSampler.StartNextSample (pixel.go:48-52) + Sampler.StartNextSample (sampler.go:29-34): increments first
-          s.cur1 = 0; s.cur2 = 0;
-          s.sidx += 1;
-          if (s.sidx < P.spp) {
-            if (P.s_world > 1 && (s.sidx % P.s_world) != P.s_rank) continue;  // FAST: samples split by index
-            have = true;
-            break;
+      // root bound of the BVH (node 0), exactly what the extend stage would test first
+      float4 rn0 = make_float4(0, 0, 0, 0), rn1 = make_float4(0, 0, 0, 0);
+      if (sc.n_nodes > 0) { rn0 = __ldg(sc.nodes); rn1 = __ldg(sc.nodes + 1); }
+      for (;;) {  // samples whose camera ray misses the root bound are finished on the spot (see below)
+        bool have = false;
+        for (;;) {
+          if (pix >= 0) {
+            // PixelSampler.StartNextSample (pixel.go:48-52) + Sampler.StartNextSample (sampler.go:29-34): increments first
+            s.cur1 = 0; s.cur2 = 0;
+            s.sidx += 1;
+            if (s.sidx < P.spp) {
+              if (P.s_world > 1 && (s.sidx % P.s_world) != P.s_rank) continue;  // FAST: samples split by index
+              have = true;
+              break;
+            }
           }
+          pix++;
+          if (pix >= area) break;
+          start_pixel(s, L, P);
         }
-        pix++;
-        if (pix >= area) break;
-        start_pixel(s, L, P);
-      }
-      if (have) {
+        if (!have) break;
         long long px = x0 + pix % tw, py = y0 + pix / tw;
         unsigned long long fast_pixel = (unsigned long long)((py - P.cy0) * (P.cx1 - P.cx0) + (px - P.cx0));
         if (P.mode == 1) rng_set_sequence(s, fast_pixel * (unsigned long long)P.spp + (unsigned long long)s.sidx);
@@ -593,6 +601,18 @@ __global__ void __launch_bounds__(128) k_generate(DevScene sc, Lanes L, RenderPa
         }
         ray = xf_ray(P.camera_to_world, ray, nullptr, nullptr);
         (void)time;  // ray.Time = Lerp(time, open, open): unused without animated transforms
+        cam++;
+        // BVH.Intersect's first step (bvh.go:673-675): the root node's slab test.  A camera ray that fails it hits
+        // nothing, Path.Li returns L = 0 after that one scene.Intersect query (path.go:45,66) and draws no further
+        // samples, so the sample is added to the film right here instead of travelling through extend and back.
+        V3 invd = mk3(1 / ray.d.x, 1 / ray.d.y, 1 / ray.d.z);
+        bool enters = sc.n_nodes > 0 && slab_test((double)rn0.x, (double)rn0.y, (double)rn0.z, (double)rn1.x, (double)rn1.y, (double)rn1.z,
+                                                   ray.o, invd, invd.x < 0, invd.y < 0, invd.z < 0, ray.tmax);
+        if (!enters) {
+          culled++;
+          film_add_sample(L, P, lane, tile, fx, fy, rgb(0, 0, 0));
+          continue;
+        }
         RayRec rr;
         rr.ox = ray.o.x; rr.oy = ray.o.y; rr.oz = ray.o.z; rr.dx = ray.d.x; rr.dy = ray.d.y; rr.dz = ray.d.z;
         rr.tmax = d_inf(); rr.hit_rec = -1; rr.pad = 0;
@@ -602,18 +622,37 @@ __global__ void __launch_bounds__(128) k_generate(DevScene sc, Lanes L, RenderPa
         pt.br = 1.0; pt.bg = 1.0; pt.bb = 1.0;
         pt.eta_scale = 1.0;
         pt.bounces = (s.cur1 << 8) | (s.cur2 << 16);  // bounces in bits 0-7, sampler dimensions above
-        cam++;
         go = true;
+        break;
       }
       pt.rng_state = s.state; pt.rng_inc = s.inc; pt.sidx = s.sidx; pt.pix = pix;
       L.path[lane] = pt;
     }
     queue_push(Q.extend, Q.cnt + 0, go, (int)lane);
   }
-  cam = warp_sum(cam); nans = warp_sum(nans);
+  cam = warp_sum(cam); nans = warp_sum(nans); culled = warp_sum(culled);
   if (lane_id == 0) {
     if (cam) atomicAdd(&ctr->camera_rays, cam);
     if (nans) atomicAdd(&ctr->nan_samples, nans);
+    if (culled) atomicAdd(&ctr->root_culled, culled);
+  }
+}
+
+// ---------------------------------------------------------------- split the extend queue by outcome
+// A ray that escaped the scene ends its path (path.go:66): its lane goes straight to the regeneration queue; only real
+// hits reach the shade stage.  Order-preserving warp-ballot compaction (the queue order is roughly pixel order, which
+// keeps the rays of a warp coherent in the next extend).
+__global__ void __launch_bounds__(256) k_split_hits(Lanes L, Queues Q) {
+  long long n = Q.cnt[0];
+  int lane_id = threadIdx.x & 31;
+  long long warp_base0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) - lane_id;
+  for (long long base = warp_base0; base < n; base += (long long)gridDim.x * blockDim.x) {
+    long long i = base + lane_id;
+    bool valid = i < n;
+    int lane = 0, rec = -1;
+    if (valid) { lane = Q.extend[i]; rec = L.ray[lane].hit_rec; }
+    queue_push(Q.shade, Q.cnt + 5, valid && rec >= 0, lane);
+    queue_push(Q.regen_next, Q.cnt + 4, valid && rec < 0, lane);
   }
 }
 
@@ -622,7 +661,7 @@ __global__ void __launch_bounds__(128) k_generate(DevScene sc, Lanes L, RenderPa
 // sample (UniformSampleOneLight / EstimateDirect) whose visibility test is deferred to the shadow queue, BSDF
 // sampling, throughput update, SpawnRay, Russian roulette.
 __global__ void __launch_bounds__(128, 3) k_shade(DevScene sc, Lanes L, RenderParams P, Queues Q, RenderCounters* ctr) {
-  long long n = Q.cnt[0];
+  long long n = Q.cnt[5];  // lanes whose ray hit something (the extend stage already retired the misses)
   int lane_id = threadIdx.x & 31;
   unsigned long long n_unsupported = 0, n_dead = 0;
   int bad = 0;
@@ -633,7 +672,7 @@ __global__ void __launch_bounds__(128, 3) k_shade(DevScene sc, Lanes L, RenderPa
     bool cont = false, finished = false, shadow = false;
     long long lane = 0;
     if (valid) {
-      lane = Q.extend[i];
+      lane = Q.shade[i];
       PathRec pt = L.path[lane];
       RayRec rr = L.ray[lane];
       int packed = pt.bounces;
@@ -762,7 +801,6 @@ __global__ void __launch_bounds__(128, 3) k_shade(DevScene sc, Lanes L, RenderPa
         }
       }
       pt.bounces = (packed & ~255) | bounces;
-      if (finished) pt.has_sample = 1;
       L.path[lane] = pt;
     }
     queue_push(Q.shadow, Q.cnt + 2, shadow, (int)lane);
@@ -787,6 +825,7 @@ __global__ void k_advance(Queues Q, RenderCounters* ctr, int* host_visible_remai
     Q.cnt[2] = 0;
     Q.cnt[3] = Q.cnt[4];  // regen <- regen_next
     Q.cnt[4] = 0;
+    Q.cnt[5] = 0;
     Q.cnt[6] = 0;  // work counters of the persistent traversal warps
     Q.cnt[7] = 0;
     *host_visible_remaining = Q.cnt[0] + Q.cnt[3];

@@ -78,6 +78,17 @@ GP_D M4 load_m4(const DevScene& sc, int xf, bool inv) {
   }
   return r;
 }
+// plain 16-load variant (no translation special case): same values, half the code; used by the shade stage
+GP_D M4 load_m4_plain(const DevScene& sc, int xf, bool inv) {
+  const double2* b = (const double2*)(sc.xf + (size_t)xf * 32 + (inv ? 16 : 0));
+  M4 r;
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    double2 lo = __ldg(b + 2 * i), hi = __ldg(b + 2 * i + 1);
+    r.m[i][0] = lo.x; r.m[i][1] = lo.y; r.m[i][2] = hi.x; r.m[i][3] = hi.y;
+  }
+  return r;
+}
 GP_HD M4 translation_m4(double x, double y, double z) {
   M4 r;
 #pragma unroll
@@ -289,12 +300,12 @@ GP_D void hit_record(const DevScene& sc, int rec_index, const Ray& wray_in, doub
     return;
   }
   M4 p2w_inv;
-  if (pr.w >= 0) { p2w_inv = load_m4(sc, pr.w, true); ray = xf_ray(p2w_inv, ray, nullptr, nullptr); }
+  if (pr.w >= 0) { p2w_inv = load_m4_plain(sc, pr.w, true); ray = xf_ray(p2w_inv, ray, nullptr, nullptr); }
   int sxf;
   if (pr.x == RK_SPHERE) {
     SphereDev s = sc.spheres[pr.y];
     sxf = s.xf;
-    M4 w2o = load_m4(sc, s.xf, true);
+    M4 w2o = load_m4_plain(sc, s.xf, true);
     V3 oe, de;
     ray = xf_ray(w2o, ray, &oe, &de);
     V3 pHit = sphere_refine(ray, tHit, s.radius);
@@ -318,7 +329,7 @@ GP_D void hit_record(const DevScene& sc, int rec_index, const Ray& wray_in, doub
   } else {
     DiskDev dk = sc.disks[pr.y];
     sxf = dk.xf;
-    ray = xf_ray(load_m4(sc, dk.xf, true), ray, nullptr, nullptr);
+    ray = xf_ray(load_m4_plain(sc, dk.xf, true), ray, nullptr, nullptr);
     V3 pHit = ray.o + ray.d * tHit;
     double d2 = pHit.x * pHit.x + pHit.y * pHit.y;
     double phi = phi_of(pHit);
@@ -333,8 +344,8 @@ GP_D void hit_record(const DevScene& sc, int rec_index, const Ray& wray_in, doub
     if (dk.flags & RF_REVERSE) n = n * -1.0;
     h->p = pHit; h->perr = mk3(0, 0, 0); h->n = n; h->wo = ray.d * -1.0; h->ns = n; h->sdpdu = dpdu; h->u = u; h->v = v;
   }
-  xf_hit(load_m4(sc, sxf, false), load_m4(sc, sxf, true), *h);  // sphere.go:185 / disk.go:110
-  if (pr.w >= 0 && !(sc.xf_flags[pr.w] & XF_IDENTITY)) xf_hit(load_m4(sc, pr.w, false), p2w_inv, *h);  // primitive.go:104-106
+  xf_hit(load_m4_plain(sc, sxf, false), load_m4_plain(sc, sxf, true), *h);  // sphere.go:185 / disk.go:110
+  if (pr.w >= 0 && !(sc.xf_flags[pr.w] & XF_IDENTITY)) xf_hit(load_m4_plain(sc, pr.w, false), p2w_inv, *h);  // primitive.go:104-106
 }
 
 }  // namespace gp

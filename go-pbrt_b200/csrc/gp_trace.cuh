@@ -219,7 +219,8 @@ __global__ void __launch_bounds__(kTraceThreads, 4) k_trace(DevScene sc, RayRec*
       }
     }
     // ---- retire finished rays
-    if (has_ray && cur == DONE && leaf_i >= leaf_n && pending < 0) {
+    bool retire = has_ray && cur == DONE && leaf_i >= leaf_n && pending < 0;
+    if (retire) {
       if (MODE == 0) {
         double2 out;
         out.x = ray.tmax;
