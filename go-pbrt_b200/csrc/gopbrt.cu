@@ -310,6 +310,13 @@ extern "C" int gopbrt_scene_create(gopbrt_ctx* ctx, const gopbrt_scene_desc* d, 
     } else {
       rec.flags |= (uint32_t)(disks[p.shape_index].flags & RF_REVERSE);
     }
+    {  // shade class (used to bin the shade queue so that warps shade one kind of hit)
+      uint32_t cls = (p.shape_kind == GOPBRT_SHAPE_TRIANGLE) ? 0u : 2u;
+      bool lambert = p.material >= 0 && p.material < d->n_materials && d->materials[p.material].kind == GOPBRT_MAT_MATTE &&
+                     !(go_clamp(d->materials[p.material].sigma, 0, 90) != 0);
+      if (!lambert) cls |= 1u;
+      rec.flags |= cls << RF_CLASS_SHIFT;
+    }
     recs[r] = rec;
     for (int k = 0; k < 3; k++) { rec_bounds[6 * (size_t)r + k] = pb[pi].mn[k]; rec_bounds[6 * (size_t)r + 3 + k] = pb[pi].mx[k]; }
   }
@@ -572,7 +579,7 @@ static int render_impl(gopbrt_scene* sc, const gopbrt_camera* cam, const gopbrt_
   GP_CUDA(ctx, cudaMemsetAsync(d_film, 0, (size_t)fw * fh * 4 * sizeof(double), st));
 
   // ---- workspace
-  size_t per_lane = sizeof(RayRec) + sizeof(ShadowRec) + sizeof(PathRec) + 6 * 4 + (size_t)P.ndims * P.spp * 8 + (size_t)tpw * tph * 4 * 8;
+  size_t per_lane = sizeof(RayRec) + sizeof(ShadowRec) + sizeof(PathRec) + 9 * 4 + (size_t)P.ndims * P.spp * 8 + (size_t)tpw * tph * 4 * 8;
   size_t free_b = 0, total_b = 0;
   GP_CUDA(ctx, cudaMemGetInfo(&free_b, &total_b));
   Workspace& W = sc->ws;
@@ -587,10 +594,10 @@ static int render_impl(gopbrt_scene* sc, const gopbrt_camera* cam, const gopbrt_
     GP_CUDA(ctx, W.ray.alloc((size_t)lanes));
     GP_CUDA(ctx, W.sray.alloc((size_t)lanes));
     GP_CUDA(ctx, W.path.alloc((size_t)lanes));
-    GP_CUDA(ctx, W.i32.alloc((size_t)6 * lanes));
+    GP_CUDA(ctx, W.i32.alloc((size_t)9 * lanes));
     GP_CUDA(ctx, W.tables.alloc(std::max<size_t>(bt, 1)));
     GP_CUDA(ctx, W.tilepix.alloc(bp));
-    if (!W.cnt.p) GP_CUDA(ctx, W.cnt.alloc(8));
+    if (!W.cnt.p) GP_CUDA(ctx, W.cnt.alloc(16));
     if (!W.rctr.p) GP_CUDA(ctx, W.rctr.alloc(1));
     if (!W.remaining_host) {
       GP_CUDA(ctx, cudaHostAlloc((void**)&W.remaining_host, sizeof(int), cudaHostAllocMapped));
@@ -603,7 +610,7 @@ static int render_impl(gopbrt_scene* sc, const gopbrt_camera* cam, const gopbrt_
   L.ray = W.ray.p; L.sray = W.sray.p; L.path = W.path.p;
   int* ip = W.i32.p;
   Queues Q;
-  Q.extend = ip; Q.extend_next = ip + lanes; Q.shadow = ip + 2 * lanes; Q.regen = ip + 3 * lanes; Q.regen_next = ip + 4 * lanes; Q.shade = ip + 5 * lanes;
+  Q.extend = ip; Q.extend_next = ip + lanes; Q.shadow = ip + 2 * lanes; Q.regen = ip + 3 * lanes; Q.regen_next = ip + 4 * lanes; Q.shade[0] = ip + 5 * lanes; Q.shade[1] = ip + 6 * lanes; Q.shade[2] = ip + 7 * lanes; Q.shade[3] = ip + 8 * lanes;
   Q.cnt = W.cnt.p;
   L.tables = W.tables.p; L.tilepix = W.tilepix.p;
 
@@ -646,7 +653,7 @@ static int render_impl(gopbrt_scene* sc, const gopbrt_camera* cam, const gopbrt_
     P.lane_base = base;
     P.lanes_active = std::min(lanes, lanes_total - base);
     GP_CUDA(ctx, cudaMemsetAsync(W.tilepix.p, 0, bp * sizeof(double), st));
-    GP_CUDA(ctx, cudaMemsetAsync(W.cnt.p, 0, 8 * sizeof(int), st));
+    GP_CUDA(ctx, cudaMemsetAsync(W.cnt.p, 0, 16 * sizeof(int), st));
     tick(ST_RAYGEN);
     k_init_lanes<<<g_small, 128, 0, st>>>(L, P);
     k_generate<<<g_gen, 128, 0, st>>>(sc->dev, L, P, Q, nullptr, nullptr, W.rctr.p);

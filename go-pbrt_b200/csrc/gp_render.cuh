@@ -46,7 +46,8 @@ struct RenderCounters {
 };
 
 struct Queues {
-  int *extend, *extend_next, *shadow, *regen, *regen_next, *shade;
+  int *extend, *extend_next, *shadow, *regen, *regen_next;
+  int* shade[4];  // hit lanes binned by shade class (counts in cnt[8..11])
   int* cnt;  // [0]=extend [1]=extend_next [2]=shadow [3]=regen [4]=regen_next [5]=shade (hits) [6]=extend work counter [7]=any-hit work counter
 };
 
@@ -649,9 +650,15 @@ __global__ void __launch_bounds__(256) k_split_hits(Lanes L, Queues Q) {
   for (long long base = warp_base0; base < n; base += (long long)gridDim.x * blockDim.x) {
     long long i = base + lane_id;
     bool valid = i < n;
-    int lane = 0, rec = -1;
-    if (valid) { lane = Q.extend[i]; rec = L.ray[lane].hit_rec; }
-    queue_push(Q.shade, Q.cnt + 5, valid && rec >= 0, lane);
+    int lane = 0, rec = -1, cls = 0;
+    if (valid) {
+      lane = Q.extend[i];
+      int2 rc = *(const int2*)&L.ray[lane].hit_rec;  // {hit_rec, shade class}
+      rec = rc.x; cls = rc.y;
+    }
+    bool hit = valid && rec >= 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) queue_push(Q.shade[k], Q.cnt + 8 + k, hit && cls == k, lane);
     queue_push(Q.regen_next, Q.cnt + 4, valid && rec < 0, lane);
   }
 }
@@ -661,18 +668,28 @@ __global__ void __launch_bounds__(256) k_split_hits(Lanes L, Queues Q) {
 // sample (UniformSampleOneLight / EstimateDirect) whose visibility test is deferred to the shadow queue, BSDF
 // sampling, throughput update, SpawnRay, Russian roulette.
 __global__ void __launch_bounds__(128, 3) k_shade(DevScene sc, Lanes L, RenderParams P, Queues Q, RenderCounters* ctr) {
-  long long n = Q.cnt[5];  // lanes whose ray hit something (the extend stage already retired the misses)
+  // lanes whose ray hit something, binned by shade class: the kernel walks the four bins back to back, each starting on
+  // a warp boundary, so that (almost) every warp shades one kind of hit
+  long long n0 = Q.cnt[8], n1 = Q.cnt[9], n2 = Q.cnt[10], n3 = Q.cnt[11];
+  long long o1 = (n0 + 31) & ~31LL, o2 = o1 + ((n1 + 31) & ~31LL), o3 = o2 + ((n2 + 31) & ~31LL);
+  long long n = o3 + n3;
   int lane_id = threadIdx.x & 31;
   unsigned long long n_unsupported = 0, n_dead = 0;
   int bad = 0;
   long long warp_base0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) - lane_id;
   for (long long base = warp_base0; base < n; base += (long long)gridDim.x * blockDim.x) {
     long long i = base + lane_id;
-    bool valid = i < n;
+    const int* bin_q;
+    long long bi;
+    if (i >= o3) { bin_q = Q.shade[3]; bi = i - o3; if (bi >= n3) bi = -1; }
+    else if (i >= o2) { bin_q = Q.shade[2]; bi = i - o2; if (bi >= n2) bi = -1; }
+    else if (i >= o1) { bin_q = Q.shade[1]; bi = i - o1; if (bi >= n1) bi = -1; }
+    else { bin_q = Q.shade[0]; bi = i; if (bi >= n0) bi = -1; }
+    bool valid = i < n && bi >= 0;
     bool cont = false, finished = false, shadow = false;
     long long lane = 0;
     if (valid) {
-      lane = Q.shade[i];
+      lane = bin_q[bi];
       PathRec pt = L.path[lane];
       RayRec rr = L.ray[lane];
       int packed = pt.bounces;
@@ -825,7 +842,7 @@ __global__ void k_advance(Queues Q, RenderCounters* ctr, int* host_visible_remai
     Q.cnt[2] = 0;
     Q.cnt[3] = Q.cnt[4];  // regen <- regen_next
     Q.cnt[4] = 0;
-    Q.cnt[5] = 0;
+    Q.cnt[8] = 0; Q.cnt[9] = 0; Q.cnt[10] = 0; Q.cnt[11] = 0;
     Q.cnt[6] = 0;  // work counters of the persistent traversal warps
     Q.cnt[7] = 0;
     *host_visible_remaining = Q.cnt[0] + Q.cnt[3];

@@ -22,7 +22,8 @@ enum : uint32_t {
   RF_HAS_P2W = 8,     // wrapped in a TransformedPrimitive
   RF_REVERSE = 16,    // reverseOrientation
   RF_FULL = 32,       // full sphere / full disk: the clip test can never fire (phiMax == 2Pi exactly, zMin == -r, zMax == r)
-  RF_P2W_IDENTITY = 64
+  RF_P2W_IDENTITY = 64,
+  RF_CLASS_SHIFT = 8, RF_CLASS_MASK = 3u << 8  // shade class: bit 0 = material is not plain Lambert, bit 1 = sphere/disk hit
 };
 enum : int { XF_TRANSLATION = 1, XF_IDENTITY = 2 };
 

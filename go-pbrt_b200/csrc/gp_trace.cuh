@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(kTraceThreads, 4) k_trace(DevScene sc, RayRec*
   long long lane = 0;
   Ray ray;
   V3 invd;
-  int nx = 0, ny = 0, nz = 0, sp = 0, rec = -1, pending = -1;
+  int nx = 0, ny = 0, nz = 0, sp = 0, rec = -1, pending = -1, rec_cls = 0;
   unsigned cur = DONE, leaf_a = 0, leaf_n = 0, leaf_i = 0;
   TriRay tray;
   tray.kx = tray.ky = tray.kz = 0; tray.Sx = tray.Sy = tray.Sz = 0;
@@ -193,6 +193,7 @@ __global__ void __launch_bounds__(kTraceThreads, 4) k_trace(DevScene sc, RayRec*
           if (ANY) { cur = DONE; leaf_i = leaf_n; break; }
           ray.tmax = t;  // r.TMax = tHit (primitive.go:51)
           rec = (int)ri;
+          rec_cls = (int)((flags & RF_CLASS_MASK) >> RF_CLASS_SHIFT);
         }
       } else {
         const double* bb = sc.rec_bounds + (size_t)ri * 6;
@@ -212,7 +213,7 @@ __global__ void __launch_bounds__(kTraceThreads, 4) k_trace(DevScene sc, RayRec*
           if (quadric_test(sc, prec, prec->flags, ray, &t, bad)) {
             hit_any = true;
             if (ANY) { cur = DONE; leaf_i = leaf_n; }
-            else { ray.tmax = t; rec = pending; }
+            else { ray.tmax = t; rec = pending; rec_cls = (int)((prec->flags & RF_CLASS_MASK) >> RF_CLASS_SHIFT); }
           }
           pending = -1;
         }
@@ -224,7 +225,7 @@ __global__ void __launch_bounds__(kTraceThreads, 4) k_trace(DevScene sc, RayRec*
       if (MODE == 0) {
         double2 out;
         out.x = ray.tmax;
-        out.y = __longlong_as_double((long long)(unsigned)rec);  // {hit_rec, pad} share the record's last 8 bytes
+        out.y = __longlong_as_double((long long)(((unsigned long long)(unsigned)rec_cls << 32) | (unsigned)rec));  // {hit_rec, shade class}
         ((double2*)(rays + lane))[3] = out;
       } else if (MODE == 1) {
         occluded[lane] = hit_any ? 1 : 0;
