@@ -22,7 +22,7 @@ static_assert(sizeof(gopbrt_transform) == 256 && sizeof(gopbrt_sphere) == 40 && 
 static_assert(sizeof(gopbrt_triangle) == 16 && sizeof(gopbrt_primitive) == 16 && sizeof(gopbrt_material) == 48, "ABI layout");
 static_assert(sizeof(gopbrt_texture) == 136 && sizeof(gopbrt_light) == 64 && sizeof(gopbrt_camera) == 288, "ABI layout");
 static_assert(sizeof(gopbrt_sampler) == 24 && sizeof(gopbrt_integrator) == 32 && sizeof(gopbrt_film) == 56, "ABI layout");
-static_assert(sizeof(gopbrt_render_options) == 16 && sizeof(gopbrt_stats) == 256 && sizeof(gopbrt_scene_desc) == 152, "ABI layout");
+static_assert(sizeof(gopbrt_render_options) == 16 && sizeof(gopbrt_stats) == 272 && sizeof(gopbrt_scene_desc) == 152, "ABI layout");
 
 struct gopbrt_ctx {
   int device = 0;
@@ -613,6 +613,7 @@ static int render_impl(gopbrt_scene* sc, const gopbrt_camera* cam, const gopbrt_
   Q.extend = ip; Q.extend_next = ip + lanes; Q.shadow = ip + 2 * lanes; Q.regen = ip + 3 * lanes; Q.regen_next = ip + 4 * lanes; Q.shade[0] = ip + 5 * lanes; Q.shade[1] = ip + 6 * lanes; Q.shade[2] = ip + 7 * lanes; Q.shade[3] = ip + 8 * lanes;
   Q.cnt = W.cnt.p;
   L.tables = W.tables.p; L.tilepix = W.tilepix.p;
+  L.tile_stride = (long long)tpw * tph * 4;
 
   GP_CUDA(ctx, cudaMemsetAsync(W.rctr.p, 0, sizeof(RenderCounters), st));
   GP_CUDA(ctx, cudaMemsetAsync(sc->tctr.p, 0, sizeof(TraceCounters), st));
@@ -636,7 +637,7 @@ static int render_impl(gopbrt_scene* sc, const gopbrt_camera* cam, const gopbrt_
   int rc = GOPBRT_OK;
   // optional per-stage timing: CUDA events on the launching stream around every stage launch
   const bool timing = (flags & GOPBRT_FLAG_TIME_KERNELS) != 0;
-  enum { ST_RAYGEN = 0, ST_EXTEND, ST_SHADE, ST_SHADOW, ST_FILM, ST_N };
+  enum { ST_RAYGEN = 0, ST_EXTEND, ST_SHADE, ST_SHADOW, ST_FILM, ST_TAIL, ST_N };
   std::vector<int> ev_stage;
   size_t ev_used = 0;
   auto tick = [&](int stage) {
@@ -645,7 +646,10 @@ static int render_impl(gopbrt_scene* sc, const gopbrt_camera* cam, const gopbrt_
     cudaEventRecord(W.events[ev_used++], st);
     ev_stage.push_back(stage);
   };
-  uint64_t n_extend = 0, n_shadow = 0;
+  uint64_t n_extend = 0, n_shadow = 0, tail_used = 0;
+  // The tail kernel is bit-exact but, measured on config 2, slower than the wavefront it replaces (its lanes diverge
+  // across stages inside a warp): it stays opt-in (GOPBRT_FLAG_TAIL), off by default.
+  const int tail_lanes = (opt && (opt->flags & GOPBRT_FLAG_TAIL)) ? 49152 : 0;
   // debug aid: GOPBRT_ITER_LOG=<file> synchronises every iteration and logs the queue sizes (implies per-stage timing)
   const char* iter_log_path = getenv("GOPBRT_ITER_LOG");
   std::vector<int> iter_counts;
@@ -688,6 +692,17 @@ static int render_impl(gopbrt_scene* sc, const gopbrt_camera* cam, const gopbrt_
       GP_CUDA(ctx, cudaStreamSynchronize(st));
       if (*W.remaining_host == 0) break;
       if (sc->cancel.load()) { rc = GOPBRT_ERR_CANCELLED; break; }
+      if (!count && *W.remaining_host <= tail_lanes) {
+        // few lanes left: finish them one thread per lane instead of hundreds of near-empty wavefront iterations
+        tick(ST_TAIL);
+        static int g_tail = 0;
+        if (!g_tail) g_tail = grid_for(ctx, (const void*)k_tail, 128, (size_t)kStackDepth * 128 * sizeof(unsigned));
+        size_t tsm = (size_t)scap * 128 * sizeof(unsigned);
+        k_tail<<<std::max(g_tail, ctx->sm_count * 2), 128, tsm, st>>>(sc->dev, L, P, Q, scap, W.rctr.p, sc->tctr.p);
+        ctx->launches++;
+        tail_used++;
+        break;
+      }
     }
     tick(ST_FILM);
     k_film_merge<<<g_small, 128, 0, st>>>(L, P, d_film);
@@ -715,13 +730,14 @@ static int render_impl(gopbrt_scene* sc, const gopbrt_camera* cam, const gopbrt_
     stats->lanes = (uint64_t)lanes; stats->ms_total = ms; stats->bvh_nodes = sc->bvh_nodes; stats->bvh_depth = sc->bvh_depth;
     stats->tests_triangle = tcnt.t_tri; stats->tests_sphere_fast = tcnt.t_sph; stats->tests_general = tcnt.t_gen;
     stats->extend_launches = n_extend; stats->shadow_launches = n_shadow;
+    stats->tail_launches = tail_used;
     stats->shadow_tests_triangle = tcnt.st_tri; stats->shadow_tests_sphere_fast = tcnt.st_sph; stats->shadow_tests_general = tcnt.st_gen;
     if (timing && iter_log_path) {
       FILE* fp = fopen(iter_log_path, "w");
       if (fp) {
         size_t it = 0;
         fprintf(fp, "iter,extend_rays,ms_extend,ms_shade,ms_shadow,ms_raygen\n");
-        double row[ST_N + 1] = {0, 0, 0, 0, 0, 0};
+        double row[ST_N + 1] = {0, 0, 0, 0, 0, 0, 0};
         bool open_row = false;
         for (size_t i = 0; i + 1 < ev_used; i++) {
           float t = 0;
@@ -738,12 +754,13 @@ static int render_impl(gopbrt_scene* sc, const gopbrt_camera* cam, const gopbrt_
       }
     }
     if (timing) {
-      double acc[ST_N + 1] = {0, 0, 0, 0, 0, 0};
+      double acc[ST_N + 1] = {0, 0, 0, 0, 0, 0, 0};
       for (size_t i = 0; i + 1 < ev_used; i++) {
         float t = 0;
         cudaEventElapsedTime(&t, W.events[i], W.events[i + 1]);
         acc[ev_stage[i]] += t;
       }
+      stats->ms_tail = acc[ST_TAIL];
       stats->ms_raygen = acc[ST_RAYGEN]; stats->ms_extend = acc[ST_EXTEND]; stats->ms_shade = acc[ST_SHADE];
       stats->ms_shadow = acc[ST_SHADOW]; stats->ms_film = acc[ST_FILM];
     }

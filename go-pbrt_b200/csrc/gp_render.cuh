@@ -21,7 +21,8 @@ struct Lanes {
   ShadowRec* sray;  // pending visibility segment + gated light sample
   PathRec* path;    // throughput, radiance, sampler stream
   double* tables;   // [dim][k][lane] stratified 1-D tables
-  double* tilepix;  // [tile pixel][4][lane] FilmTile accumulators
+  double* tilepix;  // [lane][tile pixel][4] FilmTile accumulators (one contiguous record per lane)
+  long long tile_stride;  // doubles per lane = tpw * tph * 4
 };
 
 struct RenderParams {
@@ -515,18 +516,114 @@ GP_D void film_add_sample(const Lanes& L, const RenderParams& P, long long lane,
     for (long long x = p0x; x < p1x; x++) {
       double fw = 1.0;
       size_t k = (size_t)((y - by0) * P.tpw + (x - bx0)) * 4;
-      double* q = L.tilepix + k * L.n + lane;
+      double* q = L.tilepix + (size_t)lane * L.tile_stride + k;
       if (!zero) {
         RGB c = Lc * (1.0 * fw);
         q[0] += c.r;
-        q[(size_t)L.n] += c.g;
-        q[2 * (size_t)L.n] += c.b;
+        q[1] += c.g;
+        q[2] += c.b;
       }
-      q[3 * (size_t)L.n] += fw;
+      q[3] += fw;
     }
 }
 
 // ---------------------------------------------------------------- raygen + sampler
+// One lane's raygen step: retires the lane's finished sample into its film tile (renderWorker, integrator.go:252-265),
+// advances the sampler (StartNextSample / next pixel + StartPixel) and generates the next camera ray
+// (GenerateRayDifferential, camera.go:192-242; the differentials are dropped by Path.Li).  Returns false when the
+// lane's tile is exhausted.
+GP_D bool generate_lane(const DevScene& sc, const Lanes& L, const RenderParams& P, long long lane, bool have_sample,
+                        unsigned long long& cam, unsigned long long& nans, unsigned long long& culled) {
+  bool go = false;
+  long long tile = (P.lane_base + lane) * P.world + P.rank;
+  PathRec pt = L.path[lane];
+  if (have_sample) {  // every lane of the regeneration queue carries a finished sample
+    RGB Lc = rgb(pt.Lr, pt.Lg, pt.Lb);
+    if (is_nan(Lc.r) || is_nan(Lc.g) || is_nan(Lc.b)) { Lc = rgb(0.1, 0.1, 0.1); nans++; }  // integrator.go:256-257
+    film_add_sample(L, P, lane, tile, pt.fx, pt.fy, Lc);
+  }
+  Smp s;
+  s.state = pt.rng_state; s.inc = pt.rng_inc; s.sidx = pt.sidx; s.cur1 = 0; s.cur2 = 0; s.lane = lane;
+  int pix = pt.pix;
+  long long x0, y0, x1, y1;
+  tile_bounds(P, tile, &x0, &y0, &x1, &y1);
+  long long tw = x1 - x0, area = tw * (y1 - y0);
+  // root bound of the BVH (node 0), exactly what the extend stage would test first
+  float4 rn0 = make_float4(0, 0, 0, 0), rn1 = make_float4(0, 0, 0, 0);
+  if (sc.n_nodes > 0) { rn0 = __ldg(sc.nodes); rn1 = __ldg(sc.nodes + 1); }
+  for (;;) {  // samples whose camera ray misses the root bound are finished on the spot (see below)
+    bool have = false;
+    for (;;) {
+      if (pix >= 0) {
+        // PixelSampler.StartNextSample (pixel.go:48-52) + Sampler.StartNextSample (sampler.go:29-34): increments first
+        s.cur1 = 0; s.cur2 = 0;
+        s.sidx += 1;
+        if (s.sidx < P.spp) {
+          if (P.s_world > 1 && (s.sidx % P.s_world) != P.s_rank) continue;  // FAST: samples split by index
+          have = true;
+          break;
+        }
+      }
+      pix++;
+      if (pix >= area) break;
+      start_pixel(s, L, P);
+    }
+    if (!have) break;
+    long long px = x0 + pix % tw, py = y0 + pix / tw;
+    unsigned long long fast_pixel = (unsigned long long)((py - P.cy0) * (P.cx1 - P.cx0) + (px - P.cx0));
+    if (P.mode == 1) rng_set_sequence(s, fast_pixel * (unsigned long long)P.spp + (unsigned long long)s.sidx);
+    // GetCameraSample (sampler.go:75-80): Get2D pFilm, Get2D pLens, Get1D time
+    double ox, oy, lx, ly;
+    get2d(s, P, &ox, &oy);
+    double fx = (double)px + ox, fy = (double)py + oy;
+    get2d(s, P, &lx, &ly);
+    double time = get1d(s, L, P, fast_pixel);
+    V3 pCamera = xf_point(P.raster_to_camera, mk3(fx, fy, 0), mk3(0, 0, 0), nullptr);
+    Ray ray;
+    ray.o = mk3(0, 0, 0);
+    ray.d = normalized(pCamera);
+    ray.tmax = d_inf();
+    if (P.lens_radius > 0) {
+      double plx, ply;
+      concentric_sample_disk(lx, ly, &plx, &ply);
+      plx *= P.lens_radius; ply *= P.lens_radius;
+      double ft = P.focal_distance / ray.d.z;
+      V3 pFocus = ray.d * ft + ray.o;
+      ray.o = mk3(plx, ply, 0);
+      ray.d = normalized(pFocus - ray.o);
+    }
+    ray = xf_ray(P.camera_to_world, ray, nullptr, nullptr);
+    (void)time;  // ray.Time = Lerp(time, open, open): unused without animated transforms
+    cam++;
+    // BVH.Intersect's first step (bvh.go:673-675): the root node's slab test.  A camera ray that fails it hits
+    // nothing, Path.Li returns L = 0 after that one scene.Intersect query (path.go:45,66) and draws no further
+    // samples, so the sample is added to the film right here instead of travelling through extend and back.
+    V3 invd = mk3(1 / ray.d.x, 1 / ray.d.y, 1 / ray.d.z);
+    bool enters = sc.n_nodes > 0 && slab_test((double)rn0.x, (double)rn0.y, (double)rn0.z, (double)rn1.x, (double)rn1.y, (double)rn1.z,
+                                               ray.o, invd, invd.x < 0, invd.y < 0, invd.z < 0, ray.tmax);
+    if (!enters) {
+      culled++;
+      film_add_sample(L, P, lane, tile, fx, fy, rgb(0, 0, 0));
+      continue;
+    }
+    RayRec rr;
+    rr.ox = ray.o.x; rr.oy = ray.o.y; rr.oz = ray.o.z; rr.dx = ray.d.x; rr.dy = ray.d.y; rr.dz = ray.d.z;
+    rr.tmax = d_inf(); rr.hit_rec = -1; rr.pad = 0;
+    L.ray[lane] = rr;
+    pt.fx = fx; pt.fy = fy;
+    pt.Lr = 0; pt.Lg = 0; pt.Lb = 0;
+    pt.br = 1.0; pt.bg = 1.0; pt.bb = 1.0;
+    pt.eta_scale = 1.0;
+    pt.bounces = (s.cur1 << 8) | (s.cur2 << 16);  // bounces in bits 0-7, sampler dimensions above
+    go = true;
+    break;
+  }
+  pt.rng_state = s.state; pt.rng_inc = s.inc; pt.sidx = s.sidx; pt.pix = pix;
+  L.path[lane] = pt;
+  return go;
+}
+
+
 // Retires the lane's finished sample into its film tile (renderWorker, integrator.go:252-265), advances the sampler
 // (StartNextSample / next pixel + StartPixel) and generates the next camera ray (GenerateRayDifferential,
 // camera.go:192-242; the differentials are dropped by Path.Li).  Lanes whose tile is exhausted leave the wavefront.
@@ -543,91 +640,7 @@ __global__ void __launch_bounds__(128) k_generate(DevScene sc, Lanes L, RenderPa
     long long lane = 0;
     if (valid) {
       lane = in_queue ? in_queue[i] : i;
-      long long tile = (P.lane_base + lane) * P.world + P.rank;
-      PathRec pt = L.path[lane];
-      if (in_queue != nullptr) {  // every lane of the regeneration queue carries a finished sample
-        RGB Lc = rgb(pt.Lr, pt.Lg, pt.Lb);
-        if (is_nan(Lc.r) || is_nan(Lc.g) || is_nan(Lc.b)) { Lc = rgb(0.1, 0.1, 0.1); nans++; }  // integrator.go:256-257
-        film_add_sample(L, P, lane, tile, pt.fx, pt.fy, Lc);
-      }
-      Smp s;
-      s.state = pt.rng_state; s.inc = pt.rng_inc; s.sidx = pt.sidx; s.cur1 = 0; s.cur2 = 0; s.lane = lane;
-      int pix = pt.pix;
-      long long x0, y0, x1, y1;
-      tile_bounds(P, tile, &x0, &y0, &x1, &y1);
-      long long tw = x1 - x0, area = tw * (y1 - y0);
-      // root bound of the BVH (node 0), exactly what the extend stage would test first
-      float4 rn0 = make_float4(0, 0, 0, 0), rn1 = make_float4(0, 0, 0, 0);
-      if (sc.n_nodes > 0) { rn0 = __ldg(sc.nodes); rn1 = __ldg(sc.nodes + 1); }
-      for (;;) {  // samples whose camera ray misses the root bound are finished on the spot (see below)
-        bool have = false;
-        for (;;) {
-          if (pix >= 0) {
-            // PixelSampler.StartNextSample (pixel.go:48-52) + Sampler.StartNextSample (sampler.go:29-34): increments first
-            s.cur1 = 0; s.cur2 = 0;
-            s.sidx += 1;
-            if (s.sidx < P.spp) {
-              if (P.s_world > 1 && (s.sidx % P.s_world) != P.s_rank) continue;  // FAST: samples split by index
-              have = true;
-              break;
-            }
-          }
-          pix++;
-          if (pix >= area) break;
-          start_pixel(s, L, P);
-        }
-        if (!have) break;
-        long long px = x0 + pix % tw, py = y0 + pix / tw;
-        unsigned long long fast_pixel = (unsigned long long)((py - P.cy0) * (P.cx1 - P.cx0) + (px - P.cx0));
-        if (P.mode == 1) rng_set_sequence(s, fast_pixel * (unsigned long long)P.spp + (unsigned long long)s.sidx);
-        // GetCameraSample (sampler.go:75-80): Get2D pFilm, Get2D pLens, Get1D time
-        double ox, oy, lx, ly;
-        get2d(s, P, &ox, &oy);
-        double fx = (double)px + ox, fy = (double)py + oy;
-        get2d(s, P, &lx, &ly);
-        double time = get1d(s, L, P, fast_pixel);
-        V3 pCamera = xf_point(P.raster_to_camera, mk3(fx, fy, 0), mk3(0, 0, 0), nullptr);
-        Ray ray;
-        ray.o = mk3(0, 0, 0);
-        ray.d = normalized(pCamera);
-        ray.tmax = d_inf();
-        if (P.lens_radius > 0) {
-          double plx, ply;
-          concentric_sample_disk(lx, ly, &plx, &ply);
-          plx *= P.lens_radius; ply *= P.lens_radius;
-          double ft = P.focal_distance / ray.d.z;
-          V3 pFocus = ray.d * ft + ray.o;
-          ray.o = mk3(plx, ply, 0);
-          ray.d = normalized(pFocus - ray.o);
-        }
-        ray = xf_ray(P.camera_to_world, ray, nullptr, nullptr);
-        (void)time;  // ray.Time = Lerp(time, open, open): unused without animated transforms
-        cam++;
-        // BVH.Intersect's first step (bvh.go:673-675): the root node's slab test.  A camera ray that fails it hits
-        // nothing, Path.Li returns L = 0 after that one scene.Intersect query (path.go:45,66) and draws no further
-        // samples, so the sample is added to the film right here instead of travelling through extend and back.
-        V3 invd = mk3(1 / ray.d.x, 1 / ray.d.y, 1 / ray.d.z);
-        bool enters = sc.n_nodes > 0 && slab_test((double)rn0.x, (double)rn0.y, (double)rn0.z, (double)rn1.x, (double)rn1.y, (double)rn1.z,
-                                                   ray.o, invd, invd.x < 0, invd.y < 0, invd.z < 0, ray.tmax);
-        if (!enters) {
-          culled++;
-          film_add_sample(L, P, lane, tile, fx, fy, rgb(0, 0, 0));
-          continue;
-        }
-        RayRec rr;
-        rr.ox = ray.o.x; rr.oy = ray.o.y; rr.oz = ray.o.z; rr.dx = ray.d.x; rr.dy = ray.d.y; rr.dz = ray.d.z;
-        rr.tmax = d_inf(); rr.hit_rec = -1; rr.pad = 0;
-        L.ray[lane] = rr;
-        pt.fx = fx; pt.fy = fy;
-        pt.Lr = 0; pt.Lg = 0; pt.Lb = 0;
-        pt.br = 1.0; pt.bg = 1.0; pt.bb = 1.0;
-        pt.eta_scale = 1.0;
-        pt.bounces = (s.cur1 << 8) | (s.cur2 << 16);  // bounces in bits 0-7, sampler dimensions above
-        go = true;
-        break;
-      }
-      pt.rng_state = s.state; pt.rng_inc = s.inc; pt.sidx = s.sidx; pt.pix = pix;
-      L.path[lane] = pt;
+      go = generate_lane(sc, L, P, lane, in_queue != nullptr, cam, nans, culled);
     }
     queue_push(Q.extend, Q.cnt + 0, go, (int)lane);
   }
@@ -664,6 +677,141 @@ __global__ void __launch_bounds__(256) k_split_hits(Lanes L, Queues Q) {
 }
 
 // ---------------------------------------------------------------- shade
+// One Path.Li loop body for one lane (path.go:40-155) after its closest-hit query.  Sets cont (the path continues with a
+// new ray in L.ray[lane]), finished (the sample is complete) and shadow (a visibility segment is pending in L.sray[lane]).
+GP_D void shade_lane(const DevScene& sc, const Lanes& L, const RenderParams& P, long long lane, bool& cont, bool& finished, bool& shadow,
+                     unsigned long long& n_unsupported, unsigned long long& n_dead, int& bad) {
+  PathRec pt = L.path[lane];
+  RayRec rr = L.ray[lane];
+  int packed = pt.bounces;
+  int bounces = (packed & 255) + 1;  // bounces++ (path.go:41)
+  int rec = rr.hit_rec;
+  finished = true;
+  if (rec >= 0 && bounces < P.max_depth) {  // path.go:66
+    Ray ray;
+    ray.o = mk3(rr.ox, rr.oy, rr.oz);
+    ray.d = mk3(rr.dx, rr.dy, rr.dz);
+    ray.tmax = rr.tmax;
+    Hit h;
+    int prim;
+    hit_record(sc, rec, ray, ray.tmax, &h, &prim, bad);
+    BSDF bsdf;
+    if (!compute_scattering(sc, prim, h, &bsdf)) {
+      n_unsupported++;
+    } else {
+      Smp s;
+      s.state = pt.rng_state; s.inc = pt.rng_inc; s.sidx = pt.sidx;
+      s.cur1 = (packed >> 8) & 255; s.cur2 = (packed >> 16) & 255; s.lane = lane;
+      unsigned long long fast_pixel = 0;
+      if (P.mode == 1) {
+        long long tile = (P.lane_base + lane) * P.world + P.rank;
+        long long x0, y0, x1, y1;
+        tile_bounds(P, tile, &x0, &y0, &x1, &y1);
+        int pix = pt.pix;
+        long long px = x0 + pix % (x1 - x0), py = y0 + pix / (x1 - x0);
+        fast_pixel = (unsigned long long)((py - P.cy0) * (P.cx1 - P.cx0) + (px - P.cx0));
+      }
+      RGB beta = rgb(pt.br, pt.bg, pt.bb);
+      Intr ref; ref.p = h.p; ref.perr = h.perr; ref.n = h.n;
+      // --- UniformSampleOneLight (integrator.go:48-77), skipped for perfectly specular BSDFs (path.go:84)
+      if (bsdf.kind != BX_NONE && matches(bsdf.type, BSDF_ALL & ~BSDF_SPECULAR)) {
+        if (sc.n_lights > 0) {
+          double u = get1d(s, L, P, fast_pixel);
+          // Distribution1D.SampleDiscrete (sampling.go:42-55) via FindInterval (pkg/math/math.go:64-80)
+          int size = sc.n_lights + 1, first = 0, len = size;
+          while (len > 0) {
+            int half = len >> 1, middle = first + half;
+            if (sc.light_cdf[middle] <= u) { first = middle + 1; len -= half + 1; }
+            else len = half;
+          }
+          int offset = (int)go_clamp((double)(first - 1), 0, (double)(size - 2));
+          double lightPdf = 0;
+          if (sc.light_func_int > 0) lightPdf = 1.0 / (sc.light_func_int / (double)sc.n_lights);
+          if (lightPdf != 0.0) {
+            double ulx, uly, usx, usy;
+            get2d(s, P, &ulx, &uly);
+            get2d(s, P, &usx, &usy);  // uScattering: drawn, used only by the dead MIS branch
+            // --- EstimateDirect (integrator.go:79-195), handleMedia = false, specular = false
+            const int flags = BSDF_ALL & ~BSDF_SPECULAR;
+            LightSample ls;
+            light_sample_li(sc, sc.lights[offset], ref, ulx, uly, &ls);
+            if (!ls.delta) n_dead++;
+            if (ls.pdf > 0 && !is_black(ls.Li)) {
+              RGB f = bsdf_f(bsdf, h.wo, ls.wi, flags);
+              f = f * fabs(dot(ls.wi, h.ns));
+              double scatteringPdf = bsdf_pdf(bsdf, h.wo, ls.wi, flags);
+              if (!is_black(f)) {
+                RGB Ld;
+                if (ls.delta) Ld = (f * ls.Li) / ls.pdf;
+                else {
+                  double ff = 1.0 * ls.pdf, gg = 1.0 * scatteringPdf;  // PowerHeuristic (sampling.go:208-212)
+                  double weight = (ff * ff) / (ff * ff + gg * gg);
+                  Ld = ((f * ls.Li) * weight) / ls.pdf;
+                }
+                Ld = rgb(0, 0, 0) + Ld;  // Ld.AddAssign on a zero spectrum (integrator.go:123-126)
+                // VisibilityTester.Unoccluded -> SpawnRayToInteraction (interaction.go:91-102)
+                V3 origin = offset_ray_origin(ref.p, ref.perr, ref.n, ls.p1.p - ref.p);
+                V3 target = offset_ray_origin(ls.p1.p, ls.p1.perr, ls.p1.n, origin - ls.p1.p);
+                V3 d = target - origin;
+                RGB c = beta * Ld;  // Ld := beta.Mul(...) (path.go:85)
+                ShadowRec sr;
+                sr.ox = ref.p.x; sr.oy = ref.p.y; sr.oz = ref.p.z; sr.dx = d.x; sr.dy = d.y; sr.dz = d.z;  // tMax = 1 - ShadowEpsilon
+                sr.pr = c.r; sr.pg = c.g; sr.pb = c.b;
+                sr.gt10 = max_comp(Ld) > 10 ? 1 : 0;  // integrator.go:73-75 panics; counted when unoccluded
+                sr.pad = 0; sr.pad2[0] = 0; sr.pad2[1] = 0;
+                L.sray[lane] = sr;
+                shadow = true;
+              }
+            }
+          }
+        }
+        if (!shadow) {
+          // L.AddAssign(beta.Mul(0)) (path.go:85-86): a no-op unless beta is not finite (0*Inf = NaN), kept for parity
+          RGB z = beta * rgb(0, 0, 0);
+          pt.Lr += z.r; pt.Lg += z.g; pt.Lb += z.b;
+        }
+      }
+      // --- sample the BSDF for the next direction (path.go:90-117); wo = ray.Direction, sic
+      double ux, uy;
+      get2d(s, P, &ux, &uy);
+      RGB f; V3 wi; double pdf; int sflags;
+      bsdf_sample_f(bsdf, ray.d, ux, uy, BSDF_ALL, &f, &wi, &pdf, &sflags);
+      if (!(is_black(f) || pdf == 0.0)) {
+        double wiAbsDotPdf = fabs(dot(wi, h.ns)) / pdf;
+        beta = beta * (f * wiAbsDotPdf);
+        double etaScale = pt.eta_scale;
+        if ((sflags & BSDF_SPECULAR) > 0 && (sflags & BSDF_TRANSMISSION) > 0) {
+          double eta = bsdf.eta;
+          if (dot(ray.d, h.n) > 0) etaScale *= eta * eta;
+          else etaScale *= 1 / (eta * eta);
+          pt.eta_scale = etaScale;
+        }
+        V3 o = offset_ray_origin(h.p, h.perr, h.n, wi);  // SpawnRay (interaction.go:68-77); wi is BSDF-local
+        bool alive = true;
+        RGB rrBeta = beta * etaScale;
+        if (max_comp(rrBeta) < P.rr_threshold && bounces > 3) {  // path.go:145-153
+          double q = go_max(0.05, 1 - max_comp(rrBeta));
+          if (get1d(s, L, P, fast_pixel) < q) alive = false;
+          else beta = beta / (1 - q);
+        }
+        if (alive) {
+          RayRec nr;
+          nr.ox = o.x; nr.oy = o.y; nr.oz = o.z; nr.dx = wi.x; nr.dy = wi.y; nr.dz = wi.z;
+          nr.tmax = d_inf(); nr.hit_rec = -1; nr.pad = 0;
+          L.ray[lane] = nr;
+          pt.br = beta.r; pt.bg = beta.g; pt.bb = beta.b;
+          cont = true;
+          finished = false;
+        }
+      }
+      pt.rng_state = s.state; pt.rng_inc = s.inc;
+      packed = (s.cur1 << 8) | (s.cur2 << 16);
+    }
+  }
+  pt.bounces = (packed & ~255) | bounces;
+  L.path[lane] = pt;
+}
+
 // One Path.Li loop body per lane (path.go:40-155) after the closest-hit query: scattering functions, one light
 // sample (UniformSampleOneLight / EstimateDirect) whose visibility test is deferred to the shadow queue, BSDF
 // sampling, throughput update, SpawnRay, Russian roulette.
@@ -690,135 +838,7 @@ __global__ void __launch_bounds__(128, 3) k_shade(DevScene sc, Lanes L, RenderPa
     long long lane = 0;
     if (valid) {
       lane = bin_q[bi];
-      PathRec pt = L.path[lane];
-      RayRec rr = L.ray[lane];
-      int packed = pt.bounces;
-      int bounces = (packed & 255) + 1;  // bounces++ (path.go:41)
-      int rec = rr.hit_rec;
-      finished = true;
-      if (rec >= 0 && bounces < P.max_depth) {  // path.go:66
-        Ray ray;
-        ray.o = mk3(rr.ox, rr.oy, rr.oz);
-        ray.d = mk3(rr.dx, rr.dy, rr.dz);
-        ray.tmax = rr.tmax;
-        Hit h;
-        int prim;
-        hit_record(sc, rec, ray, ray.tmax, &h, &prim, bad);
-        BSDF bsdf;
-        if (!compute_scattering(sc, prim, h, &bsdf)) {
-          n_unsupported++;
-        } else {
-          Smp s;
-          s.state = pt.rng_state; s.inc = pt.rng_inc; s.sidx = pt.sidx;
-          s.cur1 = (packed >> 8) & 255; s.cur2 = (packed >> 16) & 255; s.lane = lane;
-          unsigned long long fast_pixel = 0;
-          if (P.mode == 1) {
-            long long tile = (P.lane_base + lane) * P.world + P.rank;
-            long long x0, y0, x1, y1;
-            tile_bounds(P, tile, &x0, &y0, &x1, &y1);
-            int pix = pt.pix;
-            long long px = x0 + pix % (x1 - x0), py = y0 + pix / (x1 - x0);
-            fast_pixel = (unsigned long long)((py - P.cy0) * (P.cx1 - P.cx0) + (px - P.cx0));
-          }
-          RGB beta = rgb(pt.br, pt.bg, pt.bb);
-          Intr ref; ref.p = h.p; ref.perr = h.perr; ref.n = h.n;
-          // --- UniformSampleOneLight (integrator.go:48-77), skipped for perfectly specular BSDFs (path.go:84)
-          if (bsdf.kind != BX_NONE && matches(bsdf.type, BSDF_ALL & ~BSDF_SPECULAR)) {
-            if (sc.n_lights > 0) {
-              double u = get1d(s, L, P, fast_pixel);
-              // Distribution1D.SampleDiscrete (sampling.go:42-55) via FindInterval (pkg/math/math.go:64-80)
-              int size = sc.n_lights + 1, first = 0, len = size;
-              while (len > 0) {
-                int half = len >> 1, middle = first + half;
-                if (sc.light_cdf[middle] <= u) { first = middle + 1; len -= half + 1; }
-                else len = half;
-              }
-              int offset = (int)go_clamp((double)(first - 1), 0, (double)(size - 2));
-              double lightPdf = 0;
-              if (sc.light_func_int > 0) lightPdf = 1.0 / (sc.light_func_int / (double)sc.n_lights);
-              if (lightPdf != 0.0) {
-                double ulx, uly, usx, usy;
-                get2d(s, P, &ulx, &uly);
-                get2d(s, P, &usx, &usy);  // uScattering: drawn, used only by the dead MIS branch
-                // --- EstimateDirect (integrator.go:79-195), handleMedia = false, specular = false
-                const int flags = BSDF_ALL & ~BSDF_SPECULAR;
-                LightSample ls;
-                light_sample_li(sc, sc.lights[offset], ref, ulx, uly, &ls);
-                if (!ls.delta) n_dead++;
-                if (ls.pdf > 0 && !is_black(ls.Li)) {
-                  RGB f = bsdf_f(bsdf, h.wo, ls.wi, flags);
-                  f = f * fabs(dot(ls.wi, h.ns));
-                  double scatteringPdf = bsdf_pdf(bsdf, h.wo, ls.wi, flags);
-                  if (!is_black(f)) {
-                    RGB Ld;
-                    if (ls.delta) Ld = (f * ls.Li) / ls.pdf;
-                    else {
-                      double ff = 1.0 * ls.pdf, gg = 1.0 * scatteringPdf;  // PowerHeuristic (sampling.go:208-212)
-                      double weight = (ff * ff) / (ff * ff + gg * gg);
-                      Ld = ((f * ls.Li) * weight) / ls.pdf;
-                    }
-                    Ld = rgb(0, 0, 0) + Ld;  // Ld.AddAssign on a zero spectrum (integrator.go:123-126)
-                    // VisibilityTester.Unoccluded -> SpawnRayToInteraction (interaction.go:91-102)
-                    V3 origin = offset_ray_origin(ref.p, ref.perr, ref.n, ls.p1.p - ref.p);
-                    V3 target = offset_ray_origin(ls.p1.p, ls.p1.perr, ls.p1.n, origin - ls.p1.p);
-                    V3 d = target - origin;
-                    RGB c = beta * Ld;  // Ld := beta.Mul(...) (path.go:85)
-                    ShadowRec sr;
-                    sr.ox = ref.p.x; sr.oy = ref.p.y; sr.oz = ref.p.z; sr.dx = d.x; sr.dy = d.y; sr.dz = d.z;  // tMax = 1 - ShadowEpsilon
-                    sr.pr = c.r; sr.pg = c.g; sr.pb = c.b;
-                    sr.gt10 = max_comp(Ld) > 10 ? 1 : 0;  // integrator.go:73-75 panics; counted when unoccluded
-                    sr.pad = 0; sr.pad2[0] = 0; sr.pad2[1] = 0;
-                    L.sray[lane] = sr;
-                    shadow = true;
-                  }
-                }
-              }
-            }
-            if (!shadow) {
-              // L.AddAssign(beta.Mul(0)) (path.go:85-86): a no-op unless beta is not finite (0*Inf = NaN), kept for parity
-              RGB z = beta * rgb(0, 0, 0);
-              pt.Lr += z.r; pt.Lg += z.g; pt.Lb += z.b;
-            }
-          }
-          // --- sample the BSDF for the next direction (path.go:90-117); wo = ray.Direction, sic
-          double ux, uy;
-          get2d(s, P, &ux, &uy);
-          RGB f; V3 wi; double pdf; int sflags;
-          bsdf_sample_f(bsdf, ray.d, ux, uy, BSDF_ALL, &f, &wi, &pdf, &sflags);
-          if (!(is_black(f) || pdf == 0.0)) {
-            double wiAbsDotPdf = fabs(dot(wi, h.ns)) / pdf;
-            beta = beta * (f * wiAbsDotPdf);
-            double etaScale = pt.eta_scale;
-            if ((sflags & BSDF_SPECULAR) > 0 && (sflags & BSDF_TRANSMISSION) > 0) {
-              double eta = bsdf.eta;
-              if (dot(ray.d, h.n) > 0) etaScale *= eta * eta;
-              else etaScale *= 1 / (eta * eta);
-              pt.eta_scale = etaScale;
-            }
-            V3 o = offset_ray_origin(h.p, h.perr, h.n, wi);  // SpawnRay (interaction.go:68-77); wi is BSDF-local
-            bool alive = true;
-            RGB rrBeta = beta * etaScale;
-            if (max_comp(rrBeta) < P.rr_threshold && bounces > 3) {  // path.go:145-153
-              double q = go_max(0.05, 1 - max_comp(rrBeta));
-              if (get1d(s, L, P, fast_pixel) < q) alive = false;
-              else beta = beta / (1 - q);
-            }
-            if (alive) {
-              RayRec nr;
-              nr.ox = o.x; nr.oy = o.y; nr.oz = o.z; nr.dx = wi.x; nr.dy = wi.y; nr.dz = wi.z;
-              nr.tmax = d_inf(); nr.hit_rec = -1; nr.pad = 0;
-              L.ray[lane] = nr;
-              pt.br = beta.r; pt.bg = beta.g; pt.bb = beta.b;
-              cont = true;
-              finished = false;
-            }
-          }
-          pt.rng_state = s.state; pt.rng_inc = s.inc;
-          packed = (s.cur1 << 8) | (s.cur2 << 16);
-        }
-      }
-      pt.bounces = (packed & ~255) | bounces;
-      L.path[lane] = pt;
+      shade_lane(sc, L, P, lane, cont, finished, shadow, n_unsupported, n_dead, bad);
     }
     queue_push(Q.shadow, Q.cnt + 2, shadow, (int)lane);
     queue_push(Q.extend_next, Q.cnt + 1, cont, (int)lane);
@@ -830,6 +850,70 @@ __global__ void __launch_bounds__(128, 3) k_shade(DevScene sc, Lanes L, RenderPa
     if (n_dead) atomicAdd(&ctr->dead_mis_rays, n_dead);
   }
   if (bad) atomicAdd(&ctr->efloat_panics, 1ULL);
+}
+
+// ---------------------------------------------------------------- tail
+// Once only a few tens of thousands of lanes are still in flight the wavefront cannot fill the GPU any more: every
+// iteration then costs six nearly empty launches, and in STRICT mode the last lanes still need hundreds of iterations
+// (a pixel's samples are sequential).  The tail kernel gives each remaining lane to one thread, which runs the very
+// same per-lane steps (generate_lane, the reference-ordered traversal, shade_lane, shadow resolve) back to back until
+// the lane's tile is exhausted.  Same arithmetic, same order per lane => same film bits.
+__global__ void __launch_bounds__(128) k_tail(DevScene sc, Lanes L, RenderParams P, Queues Q, int stack_cap, RenderCounters* ctr, TraceCounters* tctr) {
+  extern __shared__ unsigned s_tail_stack[];
+  unsigned* stack = s_tail_stack + threadIdx.x;
+  const int stride = 128;
+  long long n = Q.cnt[0];
+  unsigned long long cam = 0, nans = 0, culled = 0, n_unsupported = 0, n_dead = 0, closest = 0, shadows = 0, gt10 = 0;
+  int bad = 0, ovf = 0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    long long lane = Q.extend[i];
+    bool need_gen = false;
+    for (;;) {
+      if (need_gen && !generate_lane(sc, L, P, lane, true, cam, nans, culled)) break;
+      RayRec rr = L.ray[lane];
+      Ray ray;
+      ray.o = mk3(rr.ox, rr.oy, rr.oz); ray.d = mk3(rr.dx, rr.dy, rr.dz); ray.tmax = rr.tmax;
+      int rec = -1, cls = 0;
+      closest++;
+      trace_single<false>(sc, ray, &rec, &cls, stack, stride, stack_cap, bad, ovf);
+      if (rec < 0) { need_gen = true; continue; }  // escaped: the sample is finished (path.go:66)
+      L.ray[lane].tmax = ray.tmax;
+      L.ray[lane].hit_rec = rec;
+      L.ray[lane].pad = cls;
+      bool cont = false, finished = false, shadow = false;
+      shade_lane(sc, L, P, lane, cont, finished, shadow, n_unsupported, n_dead, bad);
+      if (shadow) {
+        shadows++;
+        ShadowRec sr = L.sray[lane];
+        Ray r2;
+        r2.o = mk3(sr.ox, sr.oy, sr.oz); r2.d = mk3(sr.dx, sr.dy, sr.dz); r2.tmax = 1 - 0.0001;
+        int r2rec = -1, r2cls = 0;
+        bool occluded = trace_single<true>(sc, r2, &r2rec, &r2cls, stack, stride, stack_cap, bad, ovf);
+        PathRec* pt = L.path + lane;
+        if (!occluded) {
+          pt->Lr += sr.pr; pt->Lg += sr.pg; pt->Lb += sr.pb;
+          if (sr.gt10) gt10++;
+        } else {
+          pt->Lr += sr.pr * 0.0; pt->Lg += sr.pg * 0.0; pt->Lb += sr.pb * 0.0;
+        }
+      }
+      need_gen = !cont;
+    }
+  }
+  cam = warp_sum(cam); nans = warp_sum(nans); culled = warp_sum(culled); n_unsupported = warp_sum(n_unsupported); n_dead = warp_sum(n_dead);
+  closest = warp_sum(closest); shadows = warp_sum(shadows); gt10 = warp_sum(gt10);
+  if ((threadIdx.x & 31) == 0) {
+    if (cam) atomicAdd(&ctr->camera_rays, cam);
+    if (nans) atomicAdd(&ctr->nan_samples, nans);
+    if (culled) atomicAdd(&ctr->root_culled, culled);
+    if (n_unsupported) atomicAdd(&ctr->unsupported, n_unsupported);
+    if (n_dead) atomicAdd(&ctr->dead_mis_rays, n_dead);
+    if (closest) atomicAdd(&ctr->closest_rays, closest);
+    if (shadows) atomicAdd(&ctr->shadow_rays, shadows);
+    if (gt10) atomicAdd(&ctr->radiance_gt10, gt10);
+  }
+  if (bad) atomicAdd(&ctr->efloat_panics, 1ULL);
+  if (ovf) atomicAdd(&tctr->stack_overflows, 1ULL);
 }
 
 // end of a wavefront iteration: rotate the queues on the device and publish the number of lanes still in flight
@@ -873,8 +957,8 @@ __global__ void k_film_merge(Lanes L, RenderParams P, double* __restrict__ film)
         tile_pixel_bounds(P, x0, y0, x1, y1, &bx0, &by0, &bx1, &by1);
         if (x < bx0 || x >= bx1 || y < by0 || y >= by1) continue;
         size_t k = (size_t)((y - by0) * P.tpw + (x - bx0)) * 4;
-        const double* q = L.tilepix + k * L.n + lane;
-        double r = q[0], g = q[(size_t)L.n], b = q[2 * (size_t)L.n], w = q[3 * (size_t)L.n];
+        const double* q = L.tilepix + (size_t)lane * L.tile_stride + k;
+        double r = q[0], g = q[1], b = q[2], w = q[3];
         X += 0.412453 * r + 0.357580 * g + 0.180423 * b;
         Y += 0.212671 * r + 0.715160 * g + 0.072169 * b;
         Z += 0.019334 * r + 0.119193 * g + 0.950227 * b;

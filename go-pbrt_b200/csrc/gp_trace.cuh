@@ -260,6 +260,67 @@ __global__ void __launch_bounds__(kTraceThreads, 4) k_trace(DevScene sc, RayRec*
   if (MODE == 2 && gt10) atomicAdd(gt10_counter, gt10);
 }
 
+// plain one-ray-per-thread traversal with the same per-ray visit and test order as k_trace (used by the tail kernel, where
+// too few lanes are left for the wavefront to fill the machine)
+template <bool ANY>
+GP_D bool trace_single(const DevScene& sc, Ray& ray, int* rec_out, int* cls_out, unsigned* stack, int stride, int stack_cap, int& bad, int& ovf) {
+  const unsigned DONE = 0xffffffffu;
+  V3 invd = mk3(1 / ray.d.x, 1 / ray.d.y, 1 / ray.d.z);
+  int nx = invd.x < 0, ny = invd.y < 0, nz = invd.z < 0;
+  TriRay tray = tri_ray_setup(ray.d);
+  int sp = 0;
+  unsigned cur = sc.n_nodes > 0 ? 0u : DONE;
+  bool any = false;
+  while (cur != DONE) {
+    unsigned leaf_a = 0, leaf_n = 0;
+    while (cur != DONE) {
+      float4 n0 = __ldg(sc.nodes + 2 * (size_t)cur);
+      float4 n1 = __ldg(sc.nodes + 2 * (size_t)cur + 1);
+      unsigned a = __float_as_uint(n0.w), b = __float_as_uint(n1.w);
+      bool pass = slab_test((double)n0.x, (double)n0.y, (double)n0.z, (double)n1.x, (double)n1.y, (double)n1.z, ray.o, invd, nx, ny, nz, ray.tmax);
+      unsigned np = b >> 8;
+      if (pass && np == 0) {
+        if (sp >= stack_cap) { ovf = 1; cur = DONE; break; }
+        int neg = (b & 3) == 0 ? nx : ((b & 3) == 1 ? ny : nz);
+        if (neg) { stack[(sp++) * stride] = cur + 1; cur = a; }
+        else { stack[(sp++) * stride] = a; cur = cur + 1; }
+        continue;
+      }
+      cur = sp > 0 ? stack[(--sp) * stride] : DONE;
+      if (pass) { leaf_a = a; leaf_n = np; break; }
+    }
+    for (unsigned i = 0; i < leaf_n; i++) {
+      unsigned ri = leaf_a + i;
+      const PrimRec* prec = sc.recs + ri;
+      uint32_t flags = prec->flags;
+      double t;
+      bool hit;
+      if ((flags & RK_KIND_MASK) == RK_TRIANGLE) {
+        const double2* q = (const double2*)prec;
+        double2 v0 = q[0], v1 = q[1], v2 = q[2], v3 = q[3], v4 = q[4];
+        V3 p0 = mk3(v0.y, v1.x, v1.y), p1 = mk3(v2.x, v2.y, v3.x), p2 = mk3(v3.y, v4.x, v4.y);
+        double x0 = fmin(fmin(p0.x, p1.x), p2.x), x1 = fmax(fmax(p0.x, p1.x), p2.x);
+        double y0 = fmin(fmin(p0.y, p1.y), p2.y), y1 = fmax(fmax(p0.y, p1.y), p2.y);
+        double z0 = fmin(fmin(p0.z, p1.z), p2.z), z1 = fmax(fmax(p0.z, p1.z), p2.z);
+        if (!slab_test(x0, y0, z0, x1, y1, z1, ray.o, invd, nx, ny, nz, ray.tmax)) continue;
+        hit = tri_test_pre(p0, p1, p2, ray, tray, &t, nullptr);
+      } else {
+        const double* bb = sc.rec_bounds + (size_t)ri * 6;
+        if (!slab_test(bb[0], bb[1], bb[2], bb[3], bb[4], bb[5], ray.o, invd, nx, ny, nz, ray.tmax)) continue;
+        hit = quadric_test(sc, prec, flags, ray, &t, bad);
+      }
+      if (hit) {
+        if (ANY) return true;
+        any = true;
+        ray.tmax = t;
+        *rec_out = (int)ri;
+        *cls_out = (int)((flags & RF_CLASS_MASK) >> RF_CLASS_SHIFT);
+      }
+    }
+  }
+  return any;
+}
+
 // SoA <-> record packing for the batched API (host arrays are SoA float64)
 __global__ void k_pack_rays(RaySoA in, RayRec* __restrict__ out, long long n) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {

@@ -184,7 +184,8 @@ typedef struct {
 enum {
   GOPBRT_FLAG_COUNT_TRAVERSAL = 1, /* instrumented kernels: count BVH nodes visited / primitive tests */
   GOPBRT_FLAG_FAIL_ON_PANIC = 2,   /* return GOPBRT_ERR_REFERENCE_PANIC instead of counting           */
-  GOPBRT_FLAG_TIME_KERNELS = 4     /* CUDA-event time every stage launch (fills ms_raygen … ms_film)   */
+  GOPBRT_FLAG_TIME_KERNELS = 4,    /* CUDA-event time every stage launch (fills ms_raygen … ms_tail)   */
+  GOPBRT_FLAG_TAIL = 8             /* finish the last <= 49152 lanes with the one-thread-per-lane tail kernel */
 };
 
 /* work partition for one process per GPU: this rank renders tiles t with t % world == rank
@@ -213,6 +214,8 @@ typedef struct {
   uint64_t tests_triangle, tests_sphere_fast, tests_general; /* closest-hit shape tests by record kind (COUNT_TRAVERSAL) */
   uint64_t extend_launches, shadow_launches;
   uint64_t shadow_tests_triangle, shadow_tests_sphere_fast, shadow_tests_general; /* any-hit, same split */
+  uint64_t tail_launches;      /* 1 if the frame's last lanes were finished by the tail kernel */
+  double ms_tail;
 } gopbrt_stats;
 
 /* ---- lifecycle ---- */

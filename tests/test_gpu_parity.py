@@ -124,6 +124,7 @@ def _render_both(gp, dev, scene, integ, tile, accel=1, **kw):
     film = integ.GetCamera().GetFilm().pixels.copy()
     s = OracleScene(scene, accel)
     ofilm, ost = s.render(integ, tile, mode=kw.get("mode", 0))
+    assert st["efloat_panics"] == 0 and st["stack_overflows"] == 0
     g.close(); s.close()
     return film, st, ofilm, ost
 
@@ -146,21 +147,26 @@ def _assert_film_equal(film, ofilm, st, ost, what, exact=True):
             assert abs(st[k] - ost[k]) <= max(20, ost[k] // 10000), f"{what}: {k} {st[k]} vs {ost[k]}"
 
 
+@pytest.mark.parametrize("tail", [False, True])
 @pytest.mark.parametrize("tile", [16, 1])
-def test_config1_film_bit_exact(gp, dev, tile):
+def test_config1_film_bit_exact(gp, dev, tile, tail):
     # README scene, Stratified(4,4), Path(maxDepth 10): STRICT mode reproduces pbrt.Render(…, tileSize) sample for sample.
     # Tier-2 bar of SURVEY §8d is relative RMSE <= 1e-6; we hold the stricter bit-exact bar, vs the reference-BVH oracle.
     scene, integ = gp.scenes.config1(W=320, H=180)
-    film, st, ofilm, ost = _render_both(gp, dev, scene, integ, tile, accel=0)
-    _assert_film_equal(film, ofilm, st, ost, f"config1 tile={tile}")
+    # tail=False keeps the wavefront running to the last lane (the default); tail=True lets the one-thread-per-lane tail
+    # kernel finish the frame once <= 49152 lanes are in flight (here: after the first few iterations)
+    film, st, ofilm, ost = _render_both(gp, dev, scene, integ, tile, accel=0, flags=gp.abi.FLAG_TAIL if tail else 0)
+    assert st["tail_launches"] == (1 if tail else 0)
+    _assert_film_equal(film, ofilm, st, ost, f"config1 tile={tile} tail={tail}")
     assert st["camera_rays"] == 320 * 180 * 15
 
 
+@pytest.mark.parametrize("tail", [False, True])
 @pytest.mark.parametrize("tile", [8, 1])
-def test_mixed_scene_film_bit_exact(gp, dev, tile):
+def test_mixed_scene_film_bit_exact(gp, dev, tile, tail):
     scene = gp.scenes.mixed_test_scene(150)
     integ = gp.scenes.test_integrator(160, 96, spp=(3, 3), maxDepth=8)
-    film, st, ofilm, ost = _render_both(gp, dev, scene, integ, tile)
+    film, st, ofilm, ost = _render_both(gp, dev, scene, integ, tile, flags=gp.abi.FLAG_TAIL if tail else 0)
     _assert_film_equal(film, ofilm, st, ost, f"mixed tile={tile}")
 
 
