@@ -229,3 +229,77 @@ def test_full_size_properties_config1(gp, dev):
     gp.pbrt.Render(g, integ, 1)
     assert np.array_equal(first, integ.GetCamera().GetFilm().pixels)
     g.close()
+
+
+def test_random_sampler_and_thin_lens_film_bit_exact(gp, dev):
+    # sampler.RandomSampler (random.go): every dimension from the RNG, so pFilm is jittered and the box-filter footprint
+    # varies per sample; lensRadius > 0 exercises ConcentricSampleDisk in GenerateRayDifferential (camera.go:201-212)
+    P = gp.pbrt
+    scene = gp.scenes.mixed_test_scene(60, seed=3)
+    integ = gp.scenes.test_integrator(80, 48, maxDepth=5)
+    cam = integ.GetCamera()
+    cam.lensRadius, cam.focalDistance = 0.15, 20.0
+    integ.sampler = P.NewRandomSampler(6)
+    for tile in (1, 8):
+        film, st, ofilm, ost = _render_both(gp, dev, scene, integ, tile)
+        _assert_film_equal(film, ofilm, st, ost, f"random sampler + lens tile={tile}")
+        assert st["camera_rays"] == 80 * 48 * 5
+
+
+def test_partial_spheres_and_disks_bit_exact(gp, dev):
+    # zMin/zMax/phiMax clipping (sphere.go:111-135, disk.go:86-93): root switching, the shadowed-phi quirk,
+    # annulus and sector disks — rays and a small film
+    P = gp.pbrt
+    zero = P.NewConstantFloatTexture(0.0)
+    uv = P.NewCheckerboard2D(P.NewUvMapping2D(6.0, 6.0, 0.0, 0.0), P.NewConstantSpectrumTexture(P.NewSpectrum(0.8)),
+                             P.NewConstantSpectrumTexture(P.NewRGBSpectrum(0.2, 0.5, 0.9)))
+    m = P.NewMatteMaterial(uv, zero)
+    prims = []
+    rng = gp.scenes.RNG(21)
+    for i in range(40):
+        c = (-6 + 12 * rng.UniformFloat(), 0.5 + 4 * rng.UniformFloat(), -6 + 12 * rng.UniformFloat())
+        r = 0.4 + 0.8 * rng.UniformFloat()
+        s = P.Sphere("p", P.Translate(c), bool(i % 2), r, zMin=-r * rng.UniformFloat(), zMax=r * (0.2 + 0.8 * rng.UniformFloat()),
+                     phiMax=60.0 + 300.0 * rng.UniformFloat())
+        prims.append(P.NewGeometricPrimitive(s, m))
+    for i in range(10):
+        xf = P.NewTransform(P.Translate((-5 + 10 * rng.UniformFloat(), 0.2 + 3 * rng.UniformFloat(), -5 + 10 * rng.UniformFloat())).Mul(
+            P.RotateX(90.0 * rng.UniformFloat())).Matrix)
+        prims.append(P.NewGeometricPrimitive(P.NewDisk(xf, 0.1, 1.5, 0.5 * rng.UniformFloat(), 90.0 + 270.0 * rng.UniformFloat()), m))
+    prims.append(P.NewGeometricPrimitive(P.NewDisk(P.NewTransform(P.RotateX(90).Matrix), 0.0, 30.0, 0, 360), P.NewMatteMaterial(
+        P.NewConstantSpectrumTexture(P.NewSpectrum(0.5)), zero)))
+    scene = P.NewScene(P.NewBVH(prims, 4, P.SplitSAH), [P.NewPoint(P.Translate((3.0, 9.0, 4.0)), None, P.NewSpectrum(80)),
+                                                          P.NewDistant(P.Translate((0.0, 0.0, 0.0)), P.NewSpectrum(0.4), (1.0, 1.0, -0.5))])
+    g = P.GpuScene(dev, scene)
+    s = OracleScene(scene, 1)
+    rs = np.random.default_rng(9)
+    n = 100000
+    o = rs.uniform(-8, 8, size=(n, 3)); o[:, 1] = rs.uniform(0, 7, size=n)
+    d = rs.normal(size=(n, 3))
+    G, O = g.Intersect(o, d), s.intersect(o, d)
+    _cmp_closest(G, O, "partial shapes")
+    assert np.count_nonzero(O[0] >= 0) > n // 10
+    assert np.array_equal(g.IntersectP(o, d), s.intersect_p(o, d))
+    g.close(); s.close()
+    integ = gp.scenes.test_integrator(96, 60, spp=(2, 2), pos=(10.0, 6.0, 10.0), look=(0.0, 1.5, 0.0), maxDepth=5)
+    film, st, ofilm, ost = _render_both(gp, dev, scene, integ, 1)
+    _assert_film_equal(film, ofilm, st, ost, "partial shapes film")
+
+
+def test_fast_mode_sample_partition_sums_to_single(gp, dev):
+    # FAST mode splits the work by SAMPLE index (north star): rank films sum to the single-rank film up to summation order
+    scene = gp.scenes.mixed_test_scene(50, seed=9)
+    integ = gp.scenes.test_integrator(96, 54, spp=(3, 3), maxDepth=5)
+    g = gp.pbrt.GpuScene(dev, scene)
+    gp.pbrt.Render(g, integ, 1, mode=gp.abi.MODE_FAST)
+    single = integ.GetCamera().GetFilm().pixels.copy()
+    acc = np.zeros_like(single)
+    paths = 0
+    for r in range(4):
+        st = gp.pbrt.Render(g, integ, 1, mode=gp.abi.MODE_FAST, rank=r, world=4)
+        acc += integ.GetCamera().GetFilm().pixels
+        paths += st["camera_rays"]
+    assert paths == 96 * 54 * 8
+    assert np.array_equal(acc[..., 3], single[..., 3])
+    assert np.allclose(acc, single, rtol=1e-12, atol=0)
+    g.close()
