@@ -354,6 +354,48 @@ GP_HD bool slab_test(double bx0, double by0, double bz0, double bx1, double by1,
   return tMin < rtmax && tMax > 0;
 }
 
+// ---- conservative float32 slab test for BVH NODES ----
+// Node boxes are float32, rounded outward from the float64 union of their primitives' bounds.  Exact float64 decisions
+// are made per primitive (own-bound test + shape test), so a node test only has to be a SUPERSET of the reference's
+// float64 slab test: it may pass a box the exact test would reject, never the other way round.  This one brackets the
+// ray with float32 intervals (origin and 1/d rounded down and up once per ray) and evaluates the slab distances with
+// directed rounding: lb <= exact tNear, ub >= exact tFar on every axis.  NaNs (0*inf) compare false and therefore pass.
+struct RayF32 { float olo[3], ohi[3], ilo[3], ihi[3]; };
+GP_D RayF32 ray_f32(V3 o, V3 invd) {
+  RayF32 r;
+  r.olo[0] = __double2float_rd(o.x); r.ohi[0] = __double2float_ru(o.x);
+  r.olo[1] = __double2float_rd(o.y); r.ohi[1] = __double2float_ru(o.y);
+  r.olo[2] = __double2float_rd(o.z); r.ohi[2] = __double2float_ru(o.z);
+  r.ilo[0] = __double2float_rd(invd.x); r.ihi[0] = __double2float_ru(invd.x);
+  r.ilo[1] = __double2float_rd(invd.y); r.ihi[1] = __double2float_ru(invd.y);
+  r.ilo[2] = __double2float_rd(invd.z); r.ihi[2] = __double2float_ru(invd.z);
+  return r;
+}
+GP_D void slab_axis_f32(float bmin, float bmax, float olo, float ohi, float ilo, float ihi, int neg, float* near_lb, float* far_ub) {
+  float nlo = __fsub_rd(bmin, ohi);  // <= (exact box min - exact origin)
+  float nhi = __fsub_ru(bmax, olo);  // >= (exact box max - exact origin)
+  if (!neg) {  // 1/d >= 0: near plane = min, far plane = max
+    *near_lb = __fmul_rd(nlo, nlo >= 0.f ? ilo : ihi);
+    *far_ub = __fmul_ru(nhi, nhi >= 0.f ? ihi : ilo);
+  } else {     // 1/d < 0: near plane = max, far plane = min
+    *near_lb = __fmul_rd(nhi, nhi >= 0.f ? ilo : ihi);
+    *far_ub = __fmul_ru(nlo, nlo >= 0.f ? ihi : ilo);
+  }
+}
+GP_D bool slab_test_f32_maybe(float4 n0, float4 n1, const RayF32& r, int nx, int ny, int nz, float tmax_ub) {
+  float a0, b0, a1, b1, a2, b2;
+  slab_axis_f32(n0.x, n1.x, r.olo[0], r.ohi[0], r.ilo[0], r.ihi[0], nx, &a0, &b0);
+  slab_axis_f32(n0.y, n1.y, r.olo[1], r.ohi[1], r.ilo[1], r.ihi[1], ny, &a1, &b1);
+  slab_axis_f32(n0.z, n1.z, r.olo[2], r.ohi[2], r.ilo[2], r.ihi[2], nz, &a2, &b2);
+  float tnear = fmaxf(fmaxf(a0, a1), a2);  // fmaxf/fminf drop NaNs: an unknown axis only loosens the bracket
+  float tfar = fminf(fminf(b0, b1), b2);
+  // reject only what the exact test is certain to reject: near > far on some axis pair, tMin >= r.TMax, or tMax <= 0
+  if (tnear > tfar) return false;
+  if (tnear >= tmax_ub) return false;
+  if (tfar <= 0.f) return false;
+  return true;
+}
+
 // OffsetRayOrigin (ray.go:57-74)
 GP_HD V3 offset_ray_origin(V3 p, V3 pError, V3 n, V3 w) {
   double d = dot(vabs(n), pError) * 1024.0;

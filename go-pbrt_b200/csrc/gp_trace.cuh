@@ -98,6 +98,8 @@ __global__ void __launch_bounds__(kTraceThreads, 4) k_trace(DevScene sc, RayRec*
   unsigned cur = DONE, leaf_a = 0, leaf_n = 0, leaf_i = 0;
   TriRay tray;
   tray.kx = tray.ky = tray.kz = 0; tray.Sx = tray.Sy = tray.Sz = 0;
+  RayF32 rf;
+  float tmax_ub = 0.f;
   bool hit_any = false;
   long long w_next = 0, w_end = 0;  // warp-uniform chunk [w_next, w_end)
   bool exhausted = false;
@@ -137,6 +139,8 @@ __global__ void __launch_bounds__(kTraceThreads, 4) k_trace(DevScene sc, RayRec*
           invd = mk3(1 / ray.d.x, 1 / ray.d.y, 1 / ray.d.z);  // bvh.go:665-666
           nx = invd.x < 0; ny = invd.y < 0; nz = invd.z < 0;
           tray = tri_ray_setup(ray.d);
+          rf = ray_f32(ray.o, invd);
+          tmax_ub = __double2float_ru(ray.tmax);
           sp = 0; rec = -1; hit_any = false; pending = -1; leaf_n = 0; leaf_i = 0;
           cur = sc.n_nodes > 0 ? 0u : DONE;
           has_ray = true;
@@ -156,7 +160,7 @@ __global__ void __launch_bounds__(kTraceThreads, 4) k_trace(DevScene sc, RayRec*
         float4 n1 = __ldg(sc.nodes + 2 * (size_t)cur + 1);
         if (COUNT) c.nodes++;
         unsigned a = __float_as_uint(n0.w), b = __float_as_uint(n1.w);
-        bool pass = slab_test((double)n0.x, (double)n0.y, (double)n0.z, (double)n1.x, (double)n1.y, (double)n1.z, ray.o, invd, nx, ny, nz, ray.tmax);
+        bool pass = slab_test_f32_maybe(n0, n1, rf, nx, ny, nz, tmax_ub);
         unsigned np = b >> 8;
         if (pass && np == 0) {
           if (sp >= stack_cap) { ovf = 1; cur = DONE; break; }
@@ -192,6 +196,7 @@ __global__ void __launch_bounds__(kTraceThreads, 4) k_trace(DevScene sc, RayRec*
           hit_any = true;
           if (ANY) { cur = DONE; leaf_i = leaf_n; break; }
           ray.tmax = t;  // r.TMax = tHit (primitive.go:51)
+          tmax_ub = __double2float_ru(t);
           rec = (int)ri;
           rec_cls = (int)((flags & RF_CLASS_MASK) >> RF_CLASS_SHIFT);
         }
@@ -213,7 +218,7 @@ __global__ void __launch_bounds__(kTraceThreads, 4) k_trace(DevScene sc, RayRec*
           if (quadric_test(sc, prec, prec->flags, ray, &t, bad)) {
             hit_any = true;
             if (ANY) { cur = DONE; leaf_i = leaf_n; }
-            else { ray.tmax = t; rec = pending; rec_cls = (int)((prec->flags & RF_CLASS_MASK) >> RF_CLASS_SHIFT); }
+            else { ray.tmax = t; tmax_ub = __double2float_ru(t); rec = pending; rec_cls = (int)((prec->flags & RF_CLASS_MASK) >> RF_CLASS_SHIFT); }
           }
           pending = -1;
         }
@@ -268,6 +273,7 @@ GP_D bool trace_single(const DevScene& sc, Ray& ray, int* rec_out, int* cls_out,
   V3 invd = mk3(1 / ray.d.x, 1 / ray.d.y, 1 / ray.d.z);
   int nx = invd.x < 0, ny = invd.y < 0, nz = invd.z < 0;
   TriRay tray = tri_ray_setup(ray.d);
+  RayF32 rf = ray_f32(ray.o, invd);
   int sp = 0;
   unsigned cur = sc.n_nodes > 0 ? 0u : DONE;
   bool any = false;
@@ -277,7 +283,7 @@ GP_D bool trace_single(const DevScene& sc, Ray& ray, int* rec_out, int* cls_out,
       float4 n0 = __ldg(sc.nodes + 2 * (size_t)cur);
       float4 n1 = __ldg(sc.nodes + 2 * (size_t)cur + 1);
       unsigned a = __float_as_uint(n0.w), b = __float_as_uint(n1.w);
-      bool pass = slab_test((double)n0.x, (double)n0.y, (double)n0.z, (double)n1.x, (double)n1.y, (double)n1.z, ray.o, invd, nx, ny, nz, ray.tmax);
+      bool pass = slab_test_f32_maybe(n0, n1, rf, nx, ny, nz, __double2float_ru(ray.tmax));
       unsigned np = b >> 8;
       if (pass && np == 0) {
         if (sp >= stack_cap) { ovf = 1; cur = DONE; break; }
