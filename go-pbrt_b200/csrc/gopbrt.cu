@@ -395,7 +395,7 @@ extern "C" int gopbrt_scene_create(gopbrt_ctx* ctx, const gopbrt_scene_desc* d, 
   sc->bvh_depth = (uint64_t)bvh.depth;
   // traversal stack: one entry per interior level (+ slack), [entry][thread] in dynamic shared memory
   sc->stack_cap = std::max(4, bvh.depth + 2);
-  size_t smem = (size_t)sc->stack_cap * kTraceThreads * sizeof(unsigned);
+  size_t smem = (size_t)sc->stack_cap * kTraceThreads * 2 * sizeof(unsigned);  // two words (a, b) per stacked node
   sc->grid_ext = grid_for(ctx, (const void*)k_trace<0, false>, kTraceThreads, smem);
   sc->grid_ext_c = grid_for(ctx, (const void*)k_trace<0, true>, kTraceThreads, smem);
   sc->grid_any = grid_for(ctx, (const void*)k_trace<2, false>, kTraceThreads, smem);
@@ -440,7 +440,7 @@ static int trace_closest_soa_device(gopbrt_scene* sc, int64_t n, const double* r
   int gs = ctx->sm_count * 8;
   k_pack_rays<<<gs, 256, 0, st>>>(r, recs.p, n);
   long long need = (n + kTraceThreads - 1) / kTraceThreads;
-  size_t smem = (size_t)sc->stack_cap * kTraceThreads * sizeof(unsigned);
+  size_t smem = (size_t)sc->stack_cap * kTraceThreads * 2 * sizeof(unsigned);
   GP_CUDA(ctx, cudaMemsetAsync(sc->work.p, 0, sizeof(int), st));
   k_trace<0, false><<<(int)std::min<long long>(sc->grid_ext, need), kTraceThreads, smem, st>>>(sc->dev, recs.p, nullptr, nullptr, nullptr, nullptr, nullptr, n,
                                                                                                 sc->stack_cap, sc->work.p, sc->tctr.p, nullptr);
@@ -467,7 +467,7 @@ extern "C" int gopbrt_trace_any_device(gopbrt_scene* sc, int64_t n, const double
   RaySoA r = soa7(const_cast<double*>(rays_soa7), n);
   k_pack_rays<<<ctx->sm_count * 8, 256, 0, st>>>(r, recs.p, n);
   long long need = (n + kTraceThreads - 1) / kTraceThreads;
-  size_t smem = (size_t)sc->stack_cap * kTraceThreads * sizeof(unsigned);
+  size_t smem = (size_t)sc->stack_cap * kTraceThreads * 2 * sizeof(unsigned);
   GP_CUDA(ctx, cudaMemsetAsync(sc->work.p + 1, 0, sizeof(int), st));
   k_trace<1, false><<<(int)std::min<long long>(sc->grid_any, need), kTraceThreads, smem, st>>>(sc->dev, recs.p, nullptr, nullptr, hit, nullptr, nullptr, n,
                                                                                                 sc->stack_cap, sc->work.p + 1, sc->tctr.p, nullptr);
@@ -625,7 +625,7 @@ static int render_impl(gopbrt_scene* sc, const gopbrt_camera* cam, const gopbrt_
     g_shade = grid_for(ctx, (const void*)k_shade, 128);
   }
   const int g_ext = sc->grid_ext, g_ext_c = sc->grid_ext_c, g_any = sc->grid_any, g_any_c = sc->grid_any_c;
-  const size_t smem = (size_t)sc->stack_cap * kTraceThreads * sizeof(unsigned);
+  const size_t smem = (size_t)sc->stack_cap * kTraceThreads * 2 * sizeof(unsigned);
   const int scap = sc->stack_cap;
   const int g_small = ctx->sm_count * 8;
 
@@ -696,8 +696,8 @@ static int render_impl(gopbrt_scene* sc, const gopbrt_camera* cam, const gopbrt_
         // few lanes left: finish them one thread per lane instead of hundreds of near-empty wavefront iterations
         tick(ST_TAIL);
         static int g_tail = 0;
-        if (!g_tail) g_tail = grid_for(ctx, (const void*)k_tail, 128, (size_t)kStackDepth * 128 * sizeof(unsigned));
-        size_t tsm = (size_t)scap * 128 * sizeof(unsigned);
+        if (!g_tail) g_tail = grid_for(ctx, (const void*)k_tail, 128, (size_t)kStackDepth * 128 * 2 * sizeof(unsigned));
+        size_t tsm = (size_t)scap * 128 * 2 * sizeof(unsigned);
         k_tail<<<std::max(g_tail, ctx->sm_count * 2), 128, tsm, st>>>(sc->dev, L, P, Q, scap, W.rctr.p, sc->tctr.p);
         ctx->launches++;
         tail_used++;

@@ -3,13 +3,14 @@
 // The reference's RecursiveBuild is degenerate (SplitSAH only ever uses buckets 0 and 11, depth ~N/2, and
 // its [64]-entry traversal stack overflows beyond ~100 primitives), so the tree is this backend's own: binned SAH
 // (16 bins, all three axes), median fallback, bounded depth, built top-down with the large subtrees fanned out over
-// host threads, flattened depth-first into the reference's linear layout (first child = n+1, second child stored).
+// host threads, flattened into 32-byte node records with the two children of a node adjacent (see flatten_pairs).
 // Any tree that never culls a primitive whose own bound passes reproduces the reference's hits, and the
 // node boxes written here are float32 rounded OUTWARD of the float64 union, so they never do.
 #pragma once
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
+#include <cstring>
 #include <thread>
 #include <vector>
 
@@ -141,23 +142,38 @@ struct Result {
   int depth = 0;
 };
 
-static void flatten(const std::vector<BNode>& in, int64_t i, std::vector<Node32>& out) {
-  size_t my = out.size();
-  out.emplace_back();
-  const BNode& n = in[i];
+// 32-byte node record of BNode i: interior {a = index of its FIRST child (the second is a+1), b = split axis},
+// leaf {a = first primitive record, b = nPrims<<8 | axis}.
+static Node32 make_record(const BNode& n) {
   Node32 o;
   for (int k = 0; k < 3; k++) { o.mn[k] = round_down(n.b.mn[k]); o.mx[k] = round_up(n.b.mx[k]); }
-  if (n.n > 0) {
-    o.a = (uint32_t)n.first;
-    o.b = ((uint32_t)n.n << 8) | (uint32_t)n.axis;
-    out[my] = o;
+  o.a = (uint32_t)n.first;
+  o.b = n.n > 0 ? (((uint32_t)n.n << 8) | (uint32_t)n.axis) : (uint32_t)n.axis;
+  return o;
+}
+// Sibling-adjacent layout: out[0] is the root; the two children of an interior node sit next to each other
+// (64 contiguous bytes), so one fetch brings both child boxes and a traversal step needs one dependent memory
+// round trip per tree LEVEL instead of one per node.  Subtrees are laid out depth-first for locality.
+static void flatten_pairs(const std::vector<BNode>& in, int64_t i, size_t slot, std::vector<Node32>& out) {
+  const BNode& n = in[i];
+  Node32 rec = make_record(n);
+  if (n.n == 0) {
+    size_t pair = out.size();
+    out.emplace_back();
+    out.emplace_back();
+    rec.a = (uint32_t)pair;
+    out[slot] = rec;
+    flatten_pairs(in, n.left, pair, out);
+    flatten_pairs(in, n.right, pair + 1, out);
   } else {
-    flatten(in, n.left, out);
-    o.a = (uint32_t)out.size();
-    o.b = (uint32_t)n.axis;
-    out[my] = o;
-    flatten(in, n.right, out);
+    out[slot] = rec;
   }
+}
+static void flatten(const std::vector<BNode>& in, int64_t root, std::vector<Node32>& out) {
+  out.emplace_back();  // [0] root
+  out.emplace_back();  // [1] padding: sibling pairs start at even indices, i.e. on 64-byte boundaries
+  memset(&out[1], 0, sizeof(Node32));
+  flatten_pairs(in, root, 0, out);
 }
 
 // Top of the tree serially until there are enough independent subtrees, then one host thread per subtree.

@@ -80,7 +80,7 @@ __global__ void __launch_bounds__(kTraceThreads, 4) k_trace(DevScene sc, RayRec*
   extern __shared__ unsigned s_stack[];
   unsigned* stack = s_stack + threadIdx.x;
   const int stride = kTraceThreads;
-  const unsigned FULL = 0xffffffffu, DONE = 0xffffffffu;
+  const unsigned FULL = 0xffffffffu;
   const int lane_id = threadIdx.x & 31;
   const long long n = queue ? (long long)*count : n_direct;
   TravCnt c = {0, 0, 0, 0, 0};
@@ -95,7 +95,8 @@ __global__ void __launch_bounds__(kTraceThreads, 4) k_trace(DevScene sc, RayRec*
   Ray ray;
   V3 invd;
   int nx = 0, ny = 0, nz = 0, sp = 0, rec = -1, pending = -1, rec_cls = 0;
-  unsigned cur = DONE, leaf_a = 0, leaf_n = 0, leaf_i = 0;
+  unsigned cur_a = 0, cur_b = 0, leaf_a = 0, leaf_n = 0, leaf_i = 0;
+  bool have_cur = false;  // (cur_a, cur_b) = record words of a node whose box has already passed
   TriRay tray;
   tray.kx = tray.ky = tray.kz = 0; tray.Sx = tray.Sy = tray.Sz = 0;
   RayF32 rf;
@@ -142,7 +143,12 @@ __global__ void __launch_bounds__(kTraceThreads, 4) k_trace(DevScene sc, RayRec*
           rf = ray_f32(ray.o, invd);
           tmax_ub = __double2float_ru(ray.tmax);
           sp = 0; rec = -1; hit_any = false; pending = -1; leaf_n = 0; leaf_i = 0;
-          cur = sc.n_nodes > 0 ? 0u : DONE;
+          have_cur = false;
+          if (sc.n_nodes > 0) {  // the root's own box (bvh.go:673-675)
+            float4 r0 = __ldg(sc.nodes), r1 = __ldg(sc.nodes + 1);
+            if (COUNT) c.nodes++;
+            if (slab_test_f32_maybe(r0, r1, rf, nx, ny, nz, tmax_ub)) { cur_a = __float_as_uint(r0.w); cur_b = __float_as_uint(r1.w); have_cur = true; }
+          }
           has_ray = true;
         }
       }
@@ -152,25 +158,42 @@ __global__ void __launch_bounds__(kTraceThreads, 4) k_trace(DevScene sc, RayRec*
       if (exhausted && w_next >= w_end) break;
       continue;
     }
-    // ---- phase 1: descend to the next leaf (lanes that still have leaf candidates or a deferred test skip this)
+    // ---- phase 1: descend to the next leaf (lanes that still have leaf candidates or a deferred test skip this).
+    //      One step fetches BOTH children of the current node (adjacent 32-byte records = one 64-byte access) and tests
+    //      their boxes; the near child by split axis and ray sign goes first, the far one is stacked if it passed.
     if (leaf_i >= leaf_n && pending < 0) {
       leaf_n = 0; leaf_i = 0;
-      while (cur != DONE) {
-        float4 n0 = __ldg(sc.nodes + 2 * (size_t)cur);
-        float4 n1 = __ldg(sc.nodes + 2 * (size_t)cur + 1);
-        if (COUNT) c.nodes++;
-        unsigned a = __float_as_uint(n0.w), b = __float_as_uint(n1.w);
-        bool pass = slab_test_f32_maybe(n0, n1, rf, nx, ny, nz, tmax_ub);
-        unsigned np = b >> 8;
-        if (pass && np == 0) {
-          if (sp >= stack_cap) { ovf = 1; cur = DONE; break; }
-          int neg = (b & 3) == 0 ? nx : ((b & 3) == 1 ? ny : nz);
-          if (neg) { stack[(sp++) * stride] = cur + 1; cur = a; }
-          else { stack[(sp++) * stride] = a; cur = cur + 1; }
-          continue;
+      while (have_cur) {
+        unsigned np = cur_b >> 8;
+        if (np > 0) {  // a leaf: hand it to phase 2, continue from the stack afterwards
+          leaf_a = cur_a; leaf_n = np;
+          if (sp > 0) { --sp; cur_a = stack[(2 * sp) * stride]; cur_b = stack[(2 * sp + 1) * stride]; }
+          else have_cur = false;
+          break;
         }
-        cur = sp > 0 ? stack[(--sp) * stride] : DONE;  // a finished leaf and a missed node both continue from the stack
-        if (pass) { leaf_a = a; leaf_n = np; break; }
+        const float4* pp = sc.nodes + 2 * (size_t)cur_a;
+        float4 l0 = __ldg(pp), l1 = __ldg(pp + 1), r0 = __ldg(pp + 2), r1 = __ldg(pp + 3);
+        if (COUNT) c.nodes += 2;
+        bool pl = slab_test_f32_maybe(l0, l1, rf, nx, ny, nz, tmax_ub);
+        bool pr = slab_test_f32_maybe(r0, r1, rf, nx, ny, nz, tmax_ub);
+        int axis = cur_b & 3;
+        int neg = axis == 0 ? nx : (axis == 1 ? ny : nz);
+        unsigned la = __float_as_uint(l0.w), lb = __float_as_uint(l1.w), ra = __float_as_uint(r0.w), rb = __float_as_uint(r1.w);
+        unsigned fa = neg ? ra : la, fb = neg ? rb : lb, sa = neg ? la : ra, sb = neg ? lb : rb;
+        bool pf = neg ? pr : pl, ps = neg ? pl : pr;
+        if (pf) {
+          if (ps) {
+            if (sp >= stack_cap) { ovf = 1; have_cur = false; sp = 0; break; }
+            stack[(2 * sp) * stride] = sa; stack[(2 * sp + 1) * stride] = sb; ++sp;
+          }
+          cur_a = fa; cur_b = fb;
+        } else if (ps) {
+          cur_a = sa; cur_b = sb;
+        } else if (sp > 0) {
+          --sp; cur_a = stack[(2 * sp) * stride]; cur_b = stack[(2 * sp + 1) * stride];
+        } else {
+          have_cur = false;
+        }
       }
     }
     // ---- phase 2: the leaf's candidates in order; triangles are tested here, a sphere/disk candidate is parked in
@@ -194,7 +217,7 @@ __global__ void __launch_bounds__(kTraceThreads, 4) k_trace(DevScene sc, RayRec*
         double t;
         if (tri_test_pre(p0, p1, p2, ray, tray, &t, nullptr)) {
           hit_any = true;
-          if (ANY) { cur = DONE; leaf_i = leaf_n; break; }
+          if (ANY) { have_cur = false; leaf_i = leaf_n; break; }
           ray.tmax = t;  // r.TMax = tHit (primitive.go:51)
           tmax_ub = __double2float_ru(t);
           rec = (int)ri;
@@ -210,14 +233,14 @@ __global__ void __launch_bounds__(kTraceThreads, 4) k_trace(DevScene sc, RayRec*
     // ---- phase 3: the parked sphere/disk tests, run together once enough lanes hold one or nobody else can advance
     {
       unsigned pm = __ballot_sync(FULL, pending >= 0);
-      unsigned runnable = __ballot_sync(FULL, has_ray && pending < 0 && !(cur == DONE && leaf_i >= leaf_n));
+      unsigned runnable = __ballot_sync(FULL, has_ray && pending < 0 && !(!have_cur && leaf_i >= leaf_n));
       if (pm != 0 && (__popc(pm) >= kQuadricBatch || runnable == 0)) {
         if (pending >= 0) {
           const PrimRec* prec = sc.recs + pending;
           double t;
           if (quadric_test(sc, prec, prec->flags, ray, &t, bad)) {
             hit_any = true;
-            if (ANY) { cur = DONE; leaf_i = leaf_n; }
+            if (ANY) { have_cur = false; leaf_i = leaf_n; }
             else { ray.tmax = t; tmax_ub = __double2float_ru(t); rec = pending; rec_cls = (int)((prec->flags & RF_CLASS_MASK) >> RF_CLASS_SHIFT); }
           }
           pending = -1;
@@ -225,7 +248,7 @@ __global__ void __launch_bounds__(kTraceThreads, 4) k_trace(DevScene sc, RayRec*
       }
     }
     // ---- retire finished rays
-    bool retire = has_ray && cur == DONE && leaf_i >= leaf_n && pending < 0;
+    bool retire = has_ray && !have_cur && leaf_i >= leaf_n && pending < 0;
     if (retire) {
       if (MODE == 0) {
         double2 out;
@@ -269,31 +292,51 @@ __global__ void __launch_bounds__(kTraceThreads, 4) k_trace(DevScene sc, RayRec*
 // too few lanes are left for the wavefront to fill the machine)
 template <bool ANY>
 GP_D bool trace_single(const DevScene& sc, Ray& ray, int* rec_out, int* cls_out, unsigned* stack, int stride, int stack_cap, int& bad, int& ovf) {
-  const unsigned DONE = 0xffffffffu;
   V3 invd = mk3(1 / ray.d.x, 1 / ray.d.y, 1 / ray.d.z);
   int nx = invd.x < 0, ny = invd.y < 0, nz = invd.z < 0;
   TriRay tray = tri_ray_setup(ray.d);
   RayF32 rf = ray_f32(ray.o, invd);
   int sp = 0;
-  unsigned cur = sc.n_nodes > 0 ? 0u : DONE;
+  unsigned cur_a = 0, cur_b = 0;
+  bool have_cur = false;
+  if (sc.n_nodes > 0) {
+    float4 r0 = __ldg(sc.nodes), r1 = __ldg(sc.nodes + 1);
+    if (slab_test_f32_maybe(r0, r1, rf, nx, ny, nz, __double2float_ru(ray.tmax))) { cur_a = __float_as_uint(r0.w); cur_b = __float_as_uint(r1.w); have_cur = true; }
+  }
   bool any = false;
-  while (cur != DONE) {
+  while (have_cur) {
     unsigned leaf_a = 0, leaf_n = 0;
-    while (cur != DONE) {
-      float4 n0 = __ldg(sc.nodes + 2 * (size_t)cur);
-      float4 n1 = __ldg(sc.nodes + 2 * (size_t)cur + 1);
-      unsigned a = __float_as_uint(n0.w), b = __float_as_uint(n1.w);
-      bool pass = slab_test_f32_maybe(n0, n1, rf, nx, ny, nz, __double2float_ru(ray.tmax));
-      unsigned np = b >> 8;
-      if (pass && np == 0) {
-        if (sp >= stack_cap) { ovf = 1; cur = DONE; break; }
-        int neg = (b & 3) == 0 ? nx : ((b & 3) == 1 ? ny : nz);
-        if (neg) { stack[(sp++) * stride] = cur + 1; cur = a; }
-        else { stack[(sp++) * stride] = a; cur = cur + 1; }
-        continue;
+    float tub = __double2float_ru(ray.tmax);
+    while (have_cur) {
+      unsigned np = cur_b >> 8;
+      if (np > 0) {
+        leaf_a = cur_a; leaf_n = np;
+        if (sp > 0) { --sp; cur_a = stack[(2 * sp) * stride]; cur_b = stack[(2 * sp + 1) * stride]; }
+        else have_cur = false;
+        break;
       }
-      cur = sp > 0 ? stack[(--sp) * stride] : DONE;
-      if (pass) { leaf_a = a; leaf_n = np; break; }
+      const float4* pp = sc.nodes + 2 * (size_t)cur_a;
+      float4 l0 = __ldg(pp), l1 = __ldg(pp + 1), r0 = __ldg(pp + 2), r1 = __ldg(pp + 3);
+      bool pl = slab_test_f32_maybe(l0, l1, rf, nx, ny, nz, tub);
+      bool pr = slab_test_f32_maybe(r0, r1, rf, nx, ny, nz, tub);
+      int axis = cur_b & 3;
+      int neg = axis == 0 ? nx : (axis == 1 ? ny : nz);
+      unsigned la = __float_as_uint(l0.w), lb = __float_as_uint(l1.w), ra = __float_as_uint(r0.w), rb = __float_as_uint(r1.w);
+      unsigned fa = neg ? ra : la, fb = neg ? rb : lb, sa = neg ? la : ra, sb = neg ? lb : rb;
+      bool pf = neg ? pr : pl, ps = neg ? pl : pr;
+      if (pf) {
+        if (ps) {
+          if (sp >= stack_cap) { ovf = 1; have_cur = false; sp = 0; break; }
+          stack[(2 * sp) * stride] = sa; stack[(2 * sp + 1) * stride] = sb; ++sp;
+        }
+        cur_a = fa; cur_b = fb;
+      } else if (ps) {
+        cur_a = sa; cur_b = sb;
+      } else if (sp > 0) {
+        --sp; cur_a = stack[(2 * sp) * stride]; cur_b = stack[(2 * sp + 1) * stride];
+      } else {
+        have_cur = false;
+      }
     }
     for (unsigned i = 0; i < leaf_n; i++) {
       unsigned ri = leaf_a + i;
