@@ -232,8 +232,10 @@ def main():
         # ---- roofline of the dominant kernel (k_extend: closest-hit traversal), rank 0, per launch
         s_ext = sum(s["ms_extend"] for s in stats)
         n_ext = sum(s["extend_launches"] for s in stats)
-        bytes_frame = (B_NODE * cst["nodes_visited"] + B_TRI * cst["tests_triangle"] + B_SPH * cst["tests_sphere_fast"] +
-                       B_GEN * cst["tests_general"] + B_IO_CLOSEST * cst["closest_rays"])
+        # rays the extend kernel itself processed: camera rays that miss the BVH root are answered inside raygen
+        ext_rays = cst["closest_rays"] - cst["root_culled_rays"]
+        bytes_frame = (B_NODE * (cst["nodes_visited"] - cst["root_culled_rays"]) + B_TRI * cst["tests_triangle"] +
+                       B_SPH * cst["tests_sphere_fast"] + B_GEN * cst["tests_general"] + B_IO_CLOSEST * ext_rays)
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -241,13 +243,23 @@ def main():
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
         achieved = bytes_frame * K / (s_ext / 1e3) / 1e9 if s_ext > 0 else 0.0
+        # DRAM bytes per launch of the extend kernel: (dram__bytes_read.sum + dram__bytes_write.sum) / rays of the launch
+        # captured with `ncu --set full` (profiles/r01_traffic.json), scaled to this run's average rays per launch
+        traffic = None
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+            if tj.get("workload") == args.config:
+                traffic = tj["dram_bytes_per_ray"] * ext_rays / max(1, n_ext / K)
+        except Exception:
+            pass
         roof = {"bound": "hbm", "kernel": "k_extend (closest-hit BVH traversal, fp64 slab + EFloat/watertight shape tests)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6.65 TB/s (of fallback)",
-                "traffic": None,
+                "traffic": traffic,
                 "bytes_per_launch": bytes_frame * K / max(1, n_ext), "ms_per_launch": s_ext / max(1, n_ext), "launches": n_ext,
-                "per_ray": {"nodes_visited": cst["nodes_visited"] / max(1, cst["closest_rays"]),
-                            "shape_tests": cst["prim_tests"] / max(1, cst["closest_rays"])},
+                "extend_rays_per_step": ext_rays,
+                "per_ray": {"nodes_visited": (cst["nodes_visited"] - cst["root_culled_rays"]) / max(1, ext_rays),
+                            "shape_tests": cst["prim_tests"] / max(1, ext_rays)},
                 "stage_ms_per_step": {k: sum(s[k] for s in stats) / K for k in ("ms_raygen", "ms_extend", "ms_shade", "ms_shadow", "ms_film")}}
         line = {"metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": K, "warmup": max(3, args.warmup),
                 "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",

@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "csrc", "libgopbrt_cuda.so")
+LIB_PATH = os.environ.get("GOPBRT_LIB") or os.path.join(HERE, "csrc", "libgopbrt_cuda.so")  # GOPBRT_LIB: A/B-test a variant build
 
 OK, ERR_INVALID, ERR_CUDA, ERR_CANCELLED, ERR_REFERENCE_PANIC, ERR_UNSUPPORTED = range(6)
 SHAPE_SPHERE, SHAPE_DISK, SHAPE_TRIANGLE = 0, 1, 2
@@ -107,7 +107,7 @@ class Stats(C.Structure):
                 ("tests_sphere_fast", C.c_uint64), ("tests_general", C.c_uint64), ("extend_launches", C.c_uint64),
                 ("shadow_launches", C.c_uint64), ("shadow_tests_triangle", C.c_uint64),
                 ("shadow_tests_sphere_fast", C.c_uint64), ("shadow_tests_general", C.c_uint64), ("tail_launches", C.c_uint64),
-                ("ms_tail", C.c_double)]
+                ("ms_tail", C.c_double), ("root_culled_rays", C.c_uint64)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}

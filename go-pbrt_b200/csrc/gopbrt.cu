@@ -22,7 +22,7 @@ static_assert(sizeof(gopbrt_transform) == 256 && sizeof(gopbrt_sphere) == 40 && 
 static_assert(sizeof(gopbrt_triangle) == 16 && sizeof(gopbrt_primitive) == 16 && sizeof(gopbrt_material) == 48, "ABI layout");
 static_assert(sizeof(gopbrt_texture) == 136 && sizeof(gopbrt_light) == 64 && sizeof(gopbrt_camera) == 288, "ABI layout");
 static_assert(sizeof(gopbrt_sampler) == 24 && sizeof(gopbrt_integrator) == 32 && sizeof(gopbrt_film) == 56, "ABI layout");
-static_assert(sizeof(gopbrt_render_options) == 16 && sizeof(gopbrt_stats) == 272 && sizeof(gopbrt_scene_desc) == 152, "ABI layout");
+static_assert(sizeof(gopbrt_render_options) == 16 && sizeof(gopbrt_stats) == 280 && sizeof(gopbrt_scene_desc) == 152, "ABI layout");
 
 struct gopbrt_ctx {
   int device = 0;
@@ -731,6 +731,7 @@ static int render_impl(gopbrt_scene* sc, const gopbrt_camera* cam, const gopbrt_
     stats->tests_triangle = tcnt.t_tri; stats->tests_sphere_fast = tcnt.t_sph; stats->tests_general = tcnt.t_gen;
     stats->extend_launches = n_extend; stats->shadow_launches = n_shadow;
     stats->tail_launches = tail_used;
+    stats->root_culled_rays = rcnt.root_culled;
     stats->shadow_tests_triangle = tcnt.st_tri; stats->shadow_tests_sphere_fast = tcnt.st_sph; stats->shadow_tests_general = tcnt.st_gen;
     if (timing && iter_log_path) {
       FILE* fp = fopen(iter_log_path, "w");

@@ -54,6 +54,10 @@ GP_D unsigned long long warp_sum(unsigned long long v) {
 
 constexpr int kChunkMax = 256;     // most ray indices a warp claims with one atomicAdd (fewer when the queue is short)
 constexpr int kRefillIdle = 8;     // idle lanes that trigger a refill from the warp's chunk
+#ifndef GP_DESCEND_STEPS
+#define GP_DESCEND_STEPS 8
+#endif
+constexpr int kDescendSteps = GP_DESCEND_STEPS;
 constexpr int kQuadricBatch = 8;   // parked sphere/disk tests that trigger their batched execution
 
 // Persistent warps with dynamic ray replacement ("while-while" traversal):
@@ -163,7 +167,9 @@ __global__ void __launch_bounds__(kTraceThreads, 4) k_trace(DevScene sc, RayRec*
     //      their boxes; the near child by split axis and ray sign goes first, the far one is stacked if it passed.
     if (leaf_i >= leaf_n && pending < 0) {
       leaf_n = 0; leaf_i = 0;
-      while (have_cur) {
+      // at most kDescendSteps node steps per round: lanes that already hold a leaf are not kept waiting for the one lane
+      // with a long descent (it simply continues in the next round)
+      for (int step = 0; step < kDescendSteps && have_cur; step++) {
         unsigned np = cur_b >> 8;
         if (np > 0) {  // a leaf: hand it to phase 2, continue from the stack afterwards
           leaf_a = cur_a; leaf_n = np;

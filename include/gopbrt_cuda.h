@@ -216,6 +216,7 @@ typedef struct {
   uint64_t shadow_tests_triangle, shadow_tests_sphere_fast, shadow_tests_general; /* any-hit, same split */
   uint64_t tail_launches;      /* 1 if the frame's last lanes were finished by the tail kernel */
   double ms_tail;
+  uint64_t root_culled_rays;   /* closest_rays answered by the BVH-root slab test inside raygen (never reach the extend kernel) */
 } gopbrt_stats;
 
 /* ---- lifecycle ---- */

@@ -33,7 +33,7 @@ def test_struct_sizes_match_header(gp):
     assert C.sizeof(a.Texture) == 16 + 8 * 15 and C.sizeof(a.Light) == 16 + 48
     assert C.sizeof(a.Camera) == 8 * 36 and C.sizeof(a.Sampler) == 24 and C.sizeof(a.Integrator) == 32
     assert C.sizeof(a.SceneDesc) == 152
-    assert C.sizeof(a.Film) == 8 + 48 and C.sizeof(a.RenderOptions) == 16 and C.sizeof(a.Stats) == 8 * 34
+    assert C.sizeof(a.Film) == 8 + 48 and C.sizeof(a.RenderOptions) == 16 and C.sizeof(a.Stats) == 8 * 35
 
 
 def test_no_cpu_fallback(gp):
