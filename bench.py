@@ -127,6 +127,9 @@ def main():
     ap.add_argument("--tile", type=int, default=1)
     ap.add_argument("--mode", default="strict", choices=["strict", "fast"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile", action="store_true",
+                    help="profiling run for ncu: exactly --warmup warm-up frames (0 allowed), --steps timed frames, "
+                         "no instrumented pass, no e2e pass, no CPU baseline; the JSON line is NOT a bench value")
     args = ap.parse_args()
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
@@ -162,6 +165,7 @@ def main():
     scene_create_s = time.time() - t0
     film_dev = torch.zeros(H * W * 4, dtype=torch.float64, device=f"cuda:{local_rank}")
     film_host = torch.empty(H * W * 4, dtype=torch.float64).pin_memory()
+    film_host_np = film_host.numpy()
 
     def barrier():
         torch.cuda.synchronize()
@@ -183,8 +187,16 @@ def main():
             ms += ev0.elapsed_time(ev1)
         return st, ms
 
-    for _ in range(max(3, args.warmup)):
+    for _ in range(args.warmup if args.profile else max(3, args.warmup)):
         step_device(0)
+    if args.profile:
+        for _ in range(args.steps):
+            st, ms = step_device(abi.FLAG_TIME_KERNELS)
+        if rank == 0:
+            print(json.dumps({"profile_run": True, "ms_per_step": ms, "stage_ms": {k: st[k] for k in ("ms_raygen", "ms_extend", "ms_shade", "ms_shadow", "ms_film")}}))
+        g.close()
+        dev.close()
+        return 0
     # instrumented (untimed) pass: V = BVH nodes visited, T = shape tests by kind
     cst, _ = step_device(abi.FLAG_COUNT_TRAVERSAL)
 
@@ -209,7 +221,7 @@ def main():
     e0 = time.time()
     for _ in range(args.steps):
         if world == 1:
-            P.Render(g, integ, args.tile, mode=mode)  # gopbrt_render: film D2H inside the call
+            P.Render(g, integ, args.tile, mode=mode, out=film_host_np)  # gopbrt_render: film D2H (into pinned host memory) inside the call
         else:
             step_device(0)
             if rank == 0:

@@ -715,10 +715,11 @@ class GpuScene:
         return hit.astype(bool)
 
 
-def Render(gpu_scene, integrator, tileSize, mode=abi.MODE_STRICT, rank=0, world=1, flags=0, max_lanes=0, device_film=None):
+def Render(gpu_scene, integrator, tileSize, mode=abi.MODE_STRICT, rank=0, world=1, flags=0, max_lanes=0, device_film=None, out=None):
     """pbrt.Render(ctx, integrator, scene, tileSize) (integrator.go:291-350) on the GPU.  Fills camera.Film.pixels with
     the (H', W', 4) float64 film {X, Y, Z sums, filterWeightSum} and returns gopbrt_stats as a dict.
-    device_film: optional CUDA device pointer (int) of H'*W'*4 doubles — the film then stays on the device."""
+    device_film: optional CUDA device pointer (int) of H'*W'*4 doubles — the film then stays on the device.
+    out: optional preallocated float64 array of the film's shape (e.g. a view of pinned host memory) to receive the film."""
     cam = integrator.GetCamera()
     film = cam.GetFilm()
     lib = gpu_scene.dev.lib
@@ -729,7 +730,11 @@ def Render(gpu_scene, integrator, tileSize, mode=abi.MODE_STRICT, rank=0, world=
         rc = lib.gopbrt_render_device(gpu_scene.h, C.byref(c), C.byref(s), C.byref(i), C.byref(f), C.byref(o),
                                       C.c_void_p(device_film), C.byref(st))
     else:
-        film.pixels = np.empty(film.shape(), dtype=np.float64)
+        if out is not None:
+            assert out.dtype == np.float64 and out.size == int(np.prod(film.shape())) and out.flags["C_CONTIGUOUS"]
+            film.pixels = out.reshape(film.shape())
+        else:
+            film.pixels = np.empty(film.shape(), dtype=np.float64)
         rc = lib.gopbrt_render(gpu_scene.h, C.byref(c), C.byref(s), C.byref(i), C.byref(f), C.byref(o),
                                film.pixels.ctypes.data_as(abi.dp), C.byref(st))
     if rc != abi.OK:
