@@ -14,6 +14,7 @@
 #include "../../include/gopbrt_cuda.h"
 #include "gp_bvh.h"
 #include "gp_render.cuh"
+#include "gp_trace_pool.cuh"
 
 using namespace gp;
 
@@ -80,6 +81,9 @@ struct Workspace {  // per-scene render workspace, kept between gopbrt_render ca
   }
 };
 
+typedef void (*trace_fn)(DevScene, RayRec*, const ShadowRec*, PathRec*, unsigned char*, const int*, const int*, long long, int, int*,
+                         TraceCounters*, unsigned long long*);
+
 struct gopbrt_scene {
   gopbrt_ctx* ctx = nullptr;
   DevScene dev{};
@@ -98,7 +102,10 @@ struct gopbrt_scene {
   DevBuf<TraceCounters> tctr;
   DevBuf<int> work;  // work counters of the persistent traversal warps (batched API)
   int stack_cap = 8;
-  int grid_ext = 0, grid_ext_c = 0, grid_any = 0, grid_any_c = 0;
+  // traversal kernels of this scene: [0] extend, [1] extend + counters, [2] shadow, [3] shadow + counters, [4] batched any-hit
+  trace_fn trace_k[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  int trace_grid[5] = {0, 0, 0, 0, 0};
+  size_t trace_smem = 0;
   double world[6] = {0, 0, 0, 0, 0, 0};
   uint64_t bvh_nodes = 0, bvh_depth = 0;
   std::atomic<int> cancel{0};
@@ -395,11 +402,25 @@ extern "C" int gopbrt_scene_create(gopbrt_ctx* ctx, const gopbrt_scene_desc* d, 
   sc->bvh_depth = (uint64_t)bvh.depth;
   // traversal stack: one entry per interior level (+ slack), [entry][thread] in dynamic shared memory
   sc->stack_cap = std::max(4, bvh.depth + 2);
-  size_t smem = (size_t)sc->stack_cap * kTraceThreads * 2 * sizeof(unsigned);  // two words (a, b) per stacked node
-  sc->grid_ext = grid_for(ctx, (const void*)k_trace<0, false>, kTraceThreads, smem);
-  sc->grid_ext_c = grid_for(ctx, (const void*)k_trace<0, true>, kTraceThreads, smem);
-  sc->grid_any = grid_for(ctx, (const void*)k_trace<2, false>, kTraceThreads, smem);
-  sc->grid_any_c = grid_for(ctx, (const void*)k_trace<2, true>, kTraceThreads, smem);
+  sc->stack_cap = std::min(sc->stack_cap, 250);
+  // the default is the one-ray-per-thread persistent-warp kernels (gp_trace.cuh); GOPBRT_TRACE=pool selects the
+  // experimental pooled kernels (gp_trace_pool.cuh: same results, measured slower — see DESIGN.md §4), whose per-warp
+  // ray pools need the opt-in shared-memory carve-out
+  const char* tsel = getenv("GOPBRT_TRACE");
+  if (!(tsel && strcmp(tsel, "pool") == 0)) {
+    sc->trace_smem = (size_t)sc->stack_cap * kTraceThreads * 2 * sizeof(unsigned);  // two words (a, b) per stacked node
+    sc->trace_k[0] = k_trace<0, false>; sc->trace_k[1] = k_trace<0, true>; sc->trace_k[2] = k_trace<2, false>;
+    sc->trace_k[3] = k_trace<2, true>; sc->trace_k[4] = k_trace<1, false>;
+  } else {
+    sc->trace_smem = pool_smem_bytes(sc->stack_cap);
+    sc->trace_k[0] = k_trace_pool<0, false>; sc->trace_k[1] = k_trace_pool<0, true>; sc->trace_k[2] = k_trace_pool<2, false>;
+    sc->trace_k[3] = k_trace_pool<2, true>; sc->trace_k[4] = k_trace_pool<1, false>;
+  }
+  for (int k = 0; k < 5; k++) {
+    if (sc->trace_smem > 48 * 1024)
+      GP_CUDA(ctx, cudaFuncSetAttribute((const void*)sc->trace_k[k], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sc->trace_smem));
+    sc->trace_grid[k] = grid_for(ctx, (const void*)sc->trace_k[k], kTraceThreads, sc->trace_smem);
+  }
   *out = sc;
   return GOPBRT_OK;
 }
@@ -440,9 +461,9 @@ static int trace_closest_soa_device(gopbrt_scene* sc, int64_t n, const double* r
   int gs = ctx->sm_count * 8;
   k_pack_rays<<<gs, 256, 0, st>>>(r, recs.p, n);
   long long need = (n + kTraceThreads - 1) / kTraceThreads;
-  size_t smem = (size_t)sc->stack_cap * kTraceThreads * 2 * sizeof(unsigned);
+  size_t smem = sc->trace_smem;
   GP_CUDA(ctx, cudaMemsetAsync(sc->work.p, 0, sizeof(int), st));
-  k_trace<0, false><<<(int)std::min<long long>(sc->grid_ext, need), kTraceThreads, smem, st>>>(sc->dev, recs.p, nullptr, nullptr, nullptr, nullptr, nullptr, n,
+  sc->trace_k[0]<<<(int)std::min<long long>(sc->trace_grid[0], need), kTraceThreads, smem, st>>>(sc->dev, recs.p, nullptr, nullptr, nullptr, nullptr, nullptr, n,
                                                                                                 sc->stack_cap, sc->work.p, sc->tctr.p, nullptr);
   k_unpack_hits<<<gs, 256, 0, st>>>(sc->dev, recs.p, prim, rec, t, n);
   ctx->launches += 3;
@@ -467,9 +488,9 @@ extern "C" int gopbrt_trace_any_device(gopbrt_scene* sc, int64_t n, const double
   RaySoA r = soa7(const_cast<double*>(rays_soa7), n);
   k_pack_rays<<<ctx->sm_count * 8, 256, 0, st>>>(r, recs.p, n);
   long long need = (n + kTraceThreads - 1) / kTraceThreads;
-  size_t smem = (size_t)sc->stack_cap * kTraceThreads * 2 * sizeof(unsigned);
+  size_t smem = sc->trace_smem;
   GP_CUDA(ctx, cudaMemsetAsync(sc->work.p + 1, 0, sizeof(int), st));
-  k_trace<1, false><<<(int)std::min<long long>(sc->grid_any, need), kTraceThreads, smem, st>>>(sc->dev, recs.p, nullptr, nullptr, hit, nullptr, nullptr, n,
+  sc->trace_k[4]<<<(int)std::min<long long>(sc->trace_grid[4], need), kTraceThreads, smem, st>>>(sc->dev, recs.p, nullptr, nullptr, hit, nullptr, nullptr, n,
                                                                                                 sc->stack_cap, sc->work.p + 1, sc->tctr.p, nullptr);
   ctx->launches += 2;
   GP_CUDA(ctx, cudaGetLastError());
@@ -624,8 +645,8 @@ static int render_impl(gopbrt_scene* sc, const gopbrt_camera* cam, const gopbrt_
     g_gen = grid_for(ctx, (const void*)k_generate, 128);
     g_shade = grid_for(ctx, (const void*)k_shade, 128);
   }
-  const int g_ext = sc->grid_ext, g_ext_c = sc->grid_ext_c, g_any = sc->grid_any, g_any_c = sc->grid_any_c;
-  const size_t smem = (size_t)sc->stack_cap * kTraceThreads * 2 * sizeof(unsigned);
+  const size_t smem = sc->trace_smem;
+  const int k_ext = count ? 1 : 0, k_any = count ? 3 : 2;
   const int scap = sc->stack_cap;
   const int g_small = ctx->sm_count * 8;
 
@@ -670,14 +691,12 @@ static int render_impl(gopbrt_scene* sc, const gopbrt_camera* cam, const gopbrt_
         iter_counts.push_back(c[0]);
       }
       tick(ST_EXTEND);
-      if (count) k_trace<0, true><<<g_ext_c, kTraceThreads, smem, st>>>(sc->dev, L.ray, nullptr, L.path, nullptr, Q.extend, Q.cnt + 0, 0, scap, Q.cnt + 6, sc->tctr.p, nullptr);
-      else k_trace<0, false><<<g_ext, kTraceThreads, smem, st>>>(sc->dev, L.ray, nullptr, L.path, nullptr, Q.extend, Q.cnt + 0, 0, scap, Q.cnt + 6, sc->tctr.p, nullptr);
+      sc->trace_k[k_ext]<<<sc->trace_grid[k_ext], kTraceThreads, smem, st>>>(sc->dev, L.ray, nullptr, L.path, nullptr, Q.extend, Q.cnt + 0, 0, scap, Q.cnt + 6, sc->tctr.p, nullptr);
       tick(ST_SHADE);
       k_split_hits<<<g_small, 256, 0, st>>>(L, Q);
       k_shade<<<g_shade, 128, 0, st>>>(sc->dev, L, P, Q, W.rctr.p);
       tick(ST_SHADOW);
-      if (count) k_trace<2, true><<<g_any_c, kTraceThreads, smem, st>>>(sc->dev, nullptr, L.sray, L.path, nullptr, Q.shadow, Q.cnt + 2, 0, scap, Q.cnt + 7, sc->tctr.p, &W.rctr.p->radiance_gt10);
-      else k_trace<2, false><<<g_any, kTraceThreads, smem, st>>>(sc->dev, nullptr, L.sray, L.path, nullptr, Q.shadow, Q.cnt + 2, 0, scap, Q.cnt + 7, sc->tctr.p, &W.rctr.p->radiance_gt10);
+      sc->trace_k[k_any]<<<sc->trace_grid[k_any], kTraceThreads, smem, st>>>(sc->dev, nullptr, L.sray, L.path, nullptr, Q.shadow, Q.cnt + 2, 0, scap, Q.cnt + 7, sc->tctr.p, &W.rctr.p->radiance_gt10);
       tick(ST_RAYGEN);
       k_advance<<<1, 32, 0, st>>>(Q, W.rctr.p, W.remaining_dev);
       std::swap(Q.extend, Q.extend_next);

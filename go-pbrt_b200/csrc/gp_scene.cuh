@@ -104,6 +104,21 @@ GP_HD M4 translation_m4(double x, double y, double z) {
 // returns false on miss; on success *t0/*t1 are the interval roots and *tsel the selected root value, *sel1 whether
 // the selected root is t1 (the reference compares pointers).
 GP_HD bool sphere_roots(const Ray& ray, V3 oe, V3 de, double radius, EF* t0, EF* t1, int& bad) {
+  // Early miss.  efloat.Quadratic returns false as soon as the PLAIN discriminant b.v*b.v - 4*a.v*c.v is negative
+  // (efloat/math.go:36-40), and the .v components of a, b, c are ordinary float64 arithmetic in the order written below
+  // (efloat.go Add/Sub/Mul keep .v = plain op), so a miss is decided bit-exactly without any interval bound.  It is
+  // taken only when every operand is far from overflow, which rules out every efloat.Check panic on the skipped path.
+  {
+    double ox = ray.o.x, oy = ray.o.y, oz = ray.o.z, dx = ray.d.x, dy = ray.d.y, dz = ray.d.z;
+    double m = fmax(fmax(fmax(fabs(ox), fabs(oy)), fmax(fabs(oz), fabs(dx))), fmax(fmax(fabs(dy), fabs(dz)), fabs(radius)));
+    double me = fmax(fmax(fmax(fabs(oe.x), fabs(oe.y)), fmax(fabs(oe.z), fabs(de.x))), fmax(fabs(de.y), fabs(de.z)));
+    if (m < 1e100 && me < 1e100) {
+      double av = ((dx * dx) + (dy * dy)) + (dz * dz);
+      double bv = (((dx * ox) + (dy * oy)) + (dz * oz)) * 2.0;
+      double cv = (((ox * ox) + (oy * oy)) + (oz * oz)) - (radius * radius);
+      if (bv * bv - 4. * av * cv < 0) return false;
+    }
+  }
   EF ox = ef_new(ray.o.x, oe.x, bad), oy = ef_new(ray.o.y, oe.y, bad), oz = ef_new(ray.o.z, oe.z, bad);
   EF dx = ef_new(ray.d.x, de.x, bad), dy = ef_new(ray.d.y, de.y, bad), dz = ef_new(ray.d.z, de.z, bad);
   EF a = ef_add(ef_add(ef_mul(dx, dx, bad), ef_mul(dy, dy, bad), bad), ef_mul(dz, dz, bad), bad);

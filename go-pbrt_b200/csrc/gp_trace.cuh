@@ -210,14 +210,14 @@ __global__ void __launch_bounds__(kTraceThreads, 4) k_trace(DevScene sc, RayRec*
       const PrimRec* prec = sc.recs + ri;
       uint32_t flags = prec->flags;
       if ((flags & RK_KIND_MASK) == RK_TRIANGLE) {
-        // own float64 world bound = min/max of the vertices (finite, so fmin/fmax == Go's Min/Max up to the sign of a
-        // zero, which the slab test cannot observe)
+        // own float64 world bound = min/max of the (finite) vertices: a compare-select equals Go's Min/Max up to the
+        // sign of a zero, which the slab test cannot observe
         const double2* q = (const double2*)prec;
         double2 v0 = q[0], v1 = q[1], v2 = q[2], v3 = q[3], v4 = q[4];  // {flags|prim, d0} {d1,d2} {d3,d4} {d5,d6} {d7,d8}
         V3 p0 = mk3(v0.y, v1.x, v1.y), p1 = mk3(v2.x, v2.y, v3.x), p2 = mk3(v3.y, v4.x, v4.y);
-        double x0 = fmin(fmin(p0.x, p1.x), p2.x), x1 = fmax(fmax(p0.x, p1.x), p2.x);
-        double y0 = fmin(fmin(p0.y, p1.y), p2.y), y1 = fmax(fmax(p0.y, p1.y), p2.y);
-        double z0 = fmin(fmin(p0.z, p1.z), p2.z), z1 = fmax(fmax(p0.z, p1.z), p2.z);
+        double x0 = p0.x < p1.x ? p0.x : p1.x, x1 = p0.x < p1.x ? p1.x : p0.x; x0 = p2.x < x0 ? p2.x : x0; x1 = p2.x > x1 ? p2.x : x1;
+        double y0 = p0.y < p1.y ? p0.y : p1.y, y1 = p0.y < p1.y ? p1.y : p0.y; y0 = p2.y < y0 ? p2.y : y0; y1 = p2.y > y1 ? p2.y : y1;
+        double z0 = p0.z < p1.z ? p0.z : p1.z, z1 = p0.z < p1.z ? p1.z : p0.z; z0 = p2.z < z0 ? p2.z : z0; z1 = p2.z > z1 ? p2.z : z1;
         if (!slab_test(x0, y0, z0, x1, y1, z1, ray.o, invd, nx, ny, nz, ray.tmax)) continue;
         if (COUNT) { c.prims++; c.tri++; }
         double t;

@@ -1,0 +1,24 @@
+"""A/B timing of the traversal kernels: renders the named configs and prints per-stage CUDA-event times.
+GOPBRT_TRACE=warp|pool and GOPBRT_LIB=<variant .so> select what runs.  Usage: ab_trace.py tag config2 [config4 ...]"""
+import importlib, json, os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+gp = importlib.import_module("go-pbrt_b200")
+P = gp.pbrt
+tag = sys.argv[1]
+dev = P.Device(0)
+for name in sys.argv[2:]:
+    scene, integ = getattr(gp.scenes, name)()
+    g = P.GpuScene(dev, scene)
+    P.Render(g, integ, 1)
+    xf = int(os.environ.get("AB_FLAGS", "0"))
+    t = P.Render(g, integ, 1, flags=gp.abi.FLAG_TIME_KERNELS | xf)
+    t = P.Render(g, integ, 1, flags=gp.abi.FLAG_TIME_KERNELS | xf)
+    film = integ.GetCamera().GetFilm().pixels
+    import hashlib
+    out = dict(tag=tag, trace=os.environ.get("GOPBRT_TRACE", "pool"), config=name, ms_total=round(t["ms_total"], 2),
+               mrays=round((t["closest_rays"] + t["shadow_rays"]) / t["ms_total"] / 1e3, 1),
+               stage={k[3:]: round(t[k], 2) for k in ("ms_raygen", "ms_extend", "ms_shade", "ms_shadow")},
+               iters=t["iterations"], ms_tail=round(t.get("ms_tail", 0), 2), rays=t["closest_rays"] + t["shadow_rays"], ovf=t["stack_overflows"], film_sha=hashlib.sha1(film.tobytes()).hexdigest()[:12])
+    print(json.dumps(out), flush=True)
+    g.close()
