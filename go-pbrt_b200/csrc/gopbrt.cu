@@ -14,7 +14,6 @@
 #include "../../include/gopbrt_cuda.h"
 #include "gp_bvh.h"
 #include "gp_render.cuh"
-#include "gp_trace_pool.cuh"
 
 using namespace gp;
 
@@ -75,9 +74,16 @@ struct Workspace {  // per-scene render workspace, kept between gopbrt_render ca
   int* remaining_host = nullptr;  // pinned, device-mapped
   int* remaining_dev = nullptr;
   std::vector<cudaEvent_t> events;  // pool for GOPBRT_FLAG_TIME_KERNELS
+  DevBuf<double> film;              // device film of gopbrt_render (host-film entry point), kept between calls
+  // CUDA graph of kGraphIters wavefront iterations, re-used while the launch arguments stay the same
+  cudaGraphExec_t graph_exec = nullptr;
+  std::vector<unsigned char> graph_key;
+  cudaEvent_t graph_ev[2] = {nullptr, nullptr};
   ~Workspace() {
     if (remaining_host) cudaFreeHost(remaining_host);
     for (auto e : events) cudaEventDestroy(e);
+    if (graph_exec) cudaGraphExecDestroy(graph_exec);
+    for (auto e : graph_ev) if (e) cudaEventDestroy(e);
   }
 };
 
@@ -400,22 +406,12 @@ extern "C" int gopbrt_scene_create(gopbrt_ctx* ctx, const gopbrt_scene_desc* d, 
   }
   sc->bvh_nodes = nodes.size();
   sc->bvh_depth = (uint64_t)bvh.depth;
-  // traversal stack: one entry per interior level (+ slack), [entry][thread] in dynamic shared memory
-  sc->stack_cap = std::max(4, bvh.depth + 2);
-  sc->stack_cap = std::min(sc->stack_cap, 250);
-  // the default is the one-ray-per-thread persistent-warp kernels (gp_trace.cuh); GOPBRT_TRACE=pool selects the
-  // experimental pooled kernels (gp_trace_pool.cuh: same results, measured slower — see DESIGN.md §4), whose per-warp
-  // ray pools need the opt-in shared-memory carve-out
-  const char* tsel = getenv("GOPBRT_TRACE");
-  if (!(tsel && strcmp(tsel, "pool") == 0)) {
-    sc->trace_smem = (size_t)sc->stack_cap * kTraceThreads * 2 * sizeof(unsigned);  // two words (a, b) per stacked node
-    sc->trace_k[0] = k_trace<0, false>; sc->trace_k[1] = k_trace<0, true>; sc->trace_k[2] = k_trace<2, false>;
-    sc->trace_k[3] = k_trace<2, true>; sc->trace_k[4] = k_trace<1, false>;
-  } else {
-    sc->trace_smem = pool_smem_bytes(sc->stack_cap);
-    sc->trace_k[0] = k_trace_pool<0, false>; sc->trace_k[1] = k_trace_pool<0, true>; sc->trace_k[2] = k_trace_pool<2, false>;
-    sc->trace_k[3] = k_trace_pool<2, true>; sc->trace_k[4] = k_trace_pool<1, false>;
-  }
+  // traversal stack, [entry][thread] in dynamic shared memory: a step over a 4-record child group (two tree levels)
+  // stacks at most three records
+  sc->stack_cap = std::min(250, 3 * ((bvh.depth + 2) / 2) + 4);
+  sc->trace_smem = (size_t)sc->stack_cap * kTraceThreads * 2 * sizeof(unsigned);  // two words (a, b) per stacked node
+  sc->trace_k[0] = k_trace<0, false>; sc->trace_k[1] = k_trace<0, true>; sc->trace_k[2] = k_trace<2, false>;
+  sc->trace_k[3] = k_trace<2, true>; sc->trace_k[4] = k_trace<1, false>;
   for (int k = 0; k < 5; k++) {
     if (sc->trace_smem > 48 * 1024)
       GP_CUDA(ctx, cudaFuncSetAttribute((const void*)sc->trace_k[k], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sc->trace_smem));
@@ -569,7 +565,7 @@ static int render_impl(gopbrt_scene* sc, const gopbrt_camera* cam, const gopbrt_
   sc->cancel.store(0);
 
   RenderParams P;
-  memset(&P, 0, sizeof(P));
+  memset(&P, 0, sizeof(P));  // padding too: the struct is part of the CUDA-graph cache key
   P.raster_to_camera = m4_from(cam->raster_to_camera);
   P.camera_to_world = m4_from(cam->camera_to_world);
   P.lens_radius = cam->lens_radius; P.focal_distance = cam->focal_distance;
@@ -627,10 +623,12 @@ static int render_impl(gopbrt_scene* sc, const gopbrt_camera* cam, const gopbrt_
     W.lanes = lanes; W.bytes_tables = bt; W.bytes_tilepix = bp;
   }
   Lanes L;
+  memset(&L, 0, sizeof(L));
   L.n = lanes;
   L.ray = W.ray.p; L.sray = W.sray.p; L.path = W.path.p;
   int* ip = W.i32.p;
   Queues Q;
+  memset(&Q, 0, sizeof(Q));
   Q.extend = ip; Q.extend_next = ip + lanes; Q.shadow = ip + 2 * lanes; Q.regen = ip + 3 * lanes; Q.regen_next = ip + 4 * lanes; Q.shade[0] = ip + 5 * lanes; Q.shade[1] = ip + 6 * lanes; Q.shade[2] = ip + 7 * lanes; Q.shade[3] = ip + 8 * lanes;
   Q.cnt = W.cnt.p;
   L.tables = W.tables.p; L.tilepix = W.tilepix.p;
@@ -649,6 +647,7 @@ static int render_impl(gopbrt_scene* sc, const gopbrt_camera* cam, const gopbrt_
   const int k_ext = count ? 1 : 0, k_any = count ? 3 : 2;
   const int scap = sc->stack_cap;
   const int g_small = ctx->sm_count * 8;
+  constexpr int kGraphIters = 8;
 
   cudaEvent_t ev[2];
   GP_CUDA(ctx, cudaEventCreate(&ev[0]));
@@ -683,7 +682,58 @@ static int render_impl(gopbrt_scene* sc, const gopbrt_camera* cam, const gopbrt_
     k_init_lanes<<<g_small, 128, 0, st>>>(L, P);
     k_generate<<<g_gen, 128, 0, st>>>(sc->dev, L, P, Q, nullptr, nullptr, W.rctr.p);
     ctx->launches += 2;
-    for (;;) {
+    // Wavefront iterations as a CUDA graph of kGraphIters iterations (6 launches each): in STRICT mode the last lanes
+    // need hundreds of iterations over nearly empty queues, where the cost of an iteration IS its launch latency.
+    // One graph stays queued ahead of the one the host is waiting for, so the device never idles on the host.
+    const bool use_graph = !timing && !iter_log_path && !count && tail_lanes == 0 && !getenv("GOPBRT_NO_GRAPH");
+    if (use_graph) {
+      auto enqueue_iteration = [&]() {
+        sc->trace_k[k_ext]<<<sc->trace_grid[k_ext], kTraceThreads, smem, st>>>(sc->dev, L.ray, nullptr, L.path, nullptr, Q.extend, Q.cnt + 0, 0, scap, Q.cnt + 6, sc->tctr.p, nullptr);
+        k_split_hits<<<g_small, 256, 0, st>>>(L, Q);
+        k_shade<<<g_shade, 128, 0, st>>>(sc->dev, L, P, Q, W.rctr.p);
+        sc->trace_k[k_any]<<<sc->trace_grid[k_any], kTraceThreads, smem, st>>>(sc->dev, nullptr, L.sray, L.path, nullptr, Q.shadow, Q.cnt + 2, 0, scap, Q.cnt + 7, sc->tctr.p, &W.rctr.p->radiance_gt10);
+        k_advance<<<1, 32, 0, st>>>(Q, W.rctr.p, W.remaining_dev);
+        std::swap(Q.extend, Q.extend_next);
+        std::swap(Q.regen, Q.regen_next);
+        k_generate<<<g_gen, 128, 0, st>>>(sc->dev, L, P, Q, Q.regen, Q.cnt + 3, W.rctr.p);
+      };
+      // key: everything the captured launches were given by value
+      std::vector<unsigned char> key(sizeof(L) + sizeof(P) + sizeof(Q) + sizeof(sc->dev) + 8 * sizeof(int) + sizeof(size_t));
+      {
+        unsigned char* kp = key.data();
+        memcpy(kp, &L, sizeof(L)); kp += sizeof(L);
+        memcpy(kp, &P, sizeof(P)); kp += sizeof(P);
+        memcpy(kp, &Q, sizeof(Q)); kp += sizeof(Q);
+        memcpy(kp, &sc->dev, sizeof(sc->dev)); kp += sizeof(sc->dev);
+        int gk[8] = {sc->trace_grid[k_ext], sc->trace_grid[k_any], g_small, g_shade, g_gen, scap, k_ext, k_any};
+        memcpy(kp, gk, sizeof(gk)); kp += sizeof(gk);
+        memcpy(kp, &smem, sizeof(size_t));
+      }
+      if (!W.graph_exec || W.graph_key != key) {
+        if (W.graph_exec) { cudaGraphExecDestroy(W.graph_exec); W.graph_exec = nullptr; }
+        cudaGraph_t graph = nullptr;
+        GP_CUDA(ctx, cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+        for (int k = 0; k < kGraphIters; k++) enqueue_iteration();  // kGraphIters is even: the queue pointers end where they started
+        GP_CUDA(ctx, cudaStreamEndCapture(st, &graph));
+        cudaError_t ge = cudaGraphInstantiate(&W.graph_exec, graph, 0);
+        cudaGraphDestroy(graph);
+        GP_CUDA(ctx, ge);
+        W.graph_key = key;
+      }
+      for (auto& e : W.graph_ev) if (!e) GP_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      for (uint64_t k = 0;; k++) {
+        GP_CUDA(ctx, cudaGraphLaunch(W.graph_exec, st));
+        GP_CUDA(ctx, cudaEventRecord(W.graph_ev[k & 1], st));
+        ctx->launches += 6 * kGraphIters;
+        iterations += kGraphIters; n_extend += kGraphIters; n_shadow += kGraphIters;
+        if (k == 0) continue;
+        GP_CUDA(ctx, cudaEventSynchronize(W.graph_ev[(k - 1) & 1]));  // graph k-1 is done, graph k is running or queued
+        if (*W.remaining_host == 0) break;
+        if (sc->cancel.load()) { rc = GOPBRT_ERR_CANCELLED; break; }
+      }
+      GP_CUDA(ctx, cudaStreamSynchronize(st));
+    }
+    for (; !use_graph;) {
       if (iter_log_path) {
         int c[8];
         cudaMemcpyAsync(c, Q.cnt, sizeof(c), cudaMemcpyDeviceToHost, st);
@@ -809,8 +859,8 @@ extern "C" int gopbrt_render(gopbrt_scene* sc, const gopbrt_camera* cam, const g
   long long cx1 = (long long)ceil((double)film->width * film->crop[2]), cy1 = (long long)ceil((double)film->height * film->crop[3]);
   if (cx1 <= cx0 || cy1 <= cy0) { ctx->last_error = "empty film"; return GOPBRT_ERR_INVALID; }
   size_t n = (size_t)(cx1 - cx0) * (cy1 - cy0) * 4;
-  DevBuf<double> d_film;
-  GP_CUDA(ctx, d_film.alloc(n));
+  DevBuf<double>& d_film = sc->ws.film;
+  if (d_film.n != n) { d_film.release(); GP_CUDA(ctx, d_film.alloc(n)); }
   int rc = render_impl(sc, cam, smp, ig, film, opt, d_film.p, stats);
   if (rc != GOPBRT_OK) return rc;
   auto t0 = std::chrono::steady_clock::now();

@@ -3,7 +3,7 @@
 // The reference's RecursiveBuild is degenerate (SplitSAH only ever uses buckets 0 and 11, depth ~N/2, and
 // its [64]-entry traversal stack overflows beyond ~100 primitives), so the tree is this backend's own: binned SAH
 // (16 bins, all three axes), median fallback, bounded depth, built top-down with the large subtrees fanned out over
-// host threads, flattened into 32-byte node records with the two children of a node adjacent (see flatten_pairs).
+// host threads, flattened into 32-byte node records in groups of four grandchildren (see flatten_quads).
 // Any tree that never culls a primitive whose own bound passes reproduces the reference's hits, and the
 // node boxes written here are float32 rounded OUTWARD of the float64 union, so they never do.
 #pragma once
@@ -142,8 +142,9 @@ struct Result {
   int depth = 0;
 };
 
-// 32-byte node record of BNode i: interior {a = index of its FIRST child (the second is a+1), b = split axis},
-// leaf {a = first primitive record, b = nPrims<<8 | axis}.
+// 32-byte record of BNode i.  leaf: {a = first primitive record, b = nPrims<<8 | axis}.
+// interior: {a = index of its 4-record CHILD GROUP, b = axis0 | axis1<<2 | axis2<<4 | L_expanded<<6 | R_expanded<<7}
+// (b>>8 == 0 marks an interior record), filled in by flatten_quads.
 static Node32 make_record(const BNode& n) {
   Node32 o;
   for (int k = 0; k < 3; k++) { o.mn[k] = round_down(n.b.mn[k]); o.mx[k] = round_up(n.b.mx[k]); }
@@ -151,29 +152,44 @@ static Node32 make_record(const BNode& n) {
   o.b = n.n > 0 ? (((uint32_t)n.n << 8) | (uint32_t)n.axis) : (uint32_t)n.axis;
   return o;
 }
-// Sibling-adjacent layout: out[0] is the root; the two children of an interior node sit next to each other
-// (64 contiguous bytes), so one fetch brings both child boxes and a traversal step needs one dependent memory
-// round trip per tree LEVEL instead of one per node.  Subtrees are laid out depth-first for locality.
-static void flatten_pairs(const std::vector<BNode>& in, int64_t i, size_t slot, std::vector<Node32>& out) {
+static Node32 empty_record() {
+  Node32 o;
+  for (int k = 0; k < 3; k++) { o.mn[k] = INFINITY; o.mx[k] = -INFINITY; }
+  o.a = 0; o.b = 0;
+  return o;
+}
+// Child-group layout ("quads"): the binary tree is kept as built, but an interior node's record points at a group of
+// FOUR adjacent 32-byte records (128 contiguous, 128-byte aligned bytes): slots 0,1 = the children of its left child
+// (or slot 0 = the left child itself when that is a leaf, slot 1 empty), slots 2,3 likewise for the right child.
+// One fetch therefore brings two tree levels, and a traversal step needs one dependent memory round trip per TWO
+// levels.  The three split axes ride in the parent's record, so the traversal visits the (up to four) children in
+// exactly the binary tree's near-first order.  The skipped middle boxes only ever culled what their children's boxes
+// cull too (a child box lies inside its parent's), so the set and order of visited leaves is unchanged.
+// Subtrees are laid out depth-first for locality.
+static void flatten_quads(const std::vector<BNode>& in, int64_t i, size_t slot, std::vector<Node32>& out) {
   const BNode& n = in[i];
   Node32 rec = make_record(n);
   if (n.n == 0) {
-    size_t pair = out.size();
-    out.emplace_back();
-    out.emplace_back();
-    rec.a = (uint32_t)pair;
+    size_t g = out.size();
+    for (int k = 0; k < 4; k++) out.push_back(empty_record());
+    const BNode& L = in[n.left];
+    const BNode& R = in[n.right];
+    uint32_t le = L.n == 0, re = R.n == 0;
+    rec.a = (uint32_t)g;
+    rec.b = (uint32_t)n.axis | ((uint32_t)(le ? L.axis : 0) << 2) | ((uint32_t)(re ? R.axis : 0) << 4) | (le << 6) | (re << 7);
     out[slot] = rec;
-    flatten_pairs(in, n.left, pair, out);
-    flatten_pairs(in, n.right, pair + 1, out);
+    if (le) { flatten_quads(in, L.left, g, out); flatten_quads(in, L.right, g + 1, out); }
+    else flatten_quads(in, n.left, g, out);
+    if (re) { flatten_quads(in, R.left, g + 2, out); flatten_quads(in, R.right, g + 3, out); }
+    else flatten_quads(in, n.right, g + 2, out);
   } else {
     out[slot] = rec;
   }
 }
 static void flatten(const std::vector<BNode>& in, int64_t root, std::vector<Node32>& out) {
-  out.emplace_back();  // [0] root
-  out.emplace_back();  // [1] padding: sibling pairs start at even indices, i.e. on 64-byte boundaries
-  memset(&out[1], 0, sizeof(Node32));
-  flatten_pairs(in, root, 0, out);
+  out.push_back(empty_record());  // [0] root record
+  for (int k = 0; k < 3; k++) out.push_back(empty_record());  // [1..3] padding: child groups start on 128-byte boundaries
+  flatten_quads(in, root, 0, out);
 }
 
 // Top of the tree serially until there are enough independent subtrees, then one host thread per subtree.

@@ -3,7 +3,8 @@
 //
 // One thread per ray; persistent grid (a multiple of the SM count) striding over the queue.  The traversal stack
 // lives in shared memory, interleaved [entry][thread] so a warp's pushes/pops hit 32 distinct banks.
-// Node fetch = two 16-byte loads of a 32-byte node.  Node boxes are float32 rounded OUTWARD from the float64 union of
+// Node fetch = float4 loads of 32-byte records; an inner node's record points at a 128-byte group holding the records
+// of its (up to four) grandchildren, so one fetch brings two tree levels.  Node boxes are float32 rounded OUTWARD from the float64 union of
 // the primitives' bounds and tested with the reference's float64 slab test, so a node is entered whenever the
 // reference's own (float64) box would be; at the leaf each primitive is admitted only if ITS OWN float64 world bound
 // passes Bounds3.IntersectP with the running tMax — the topology-independent parity spec of SURVEY §8a — and then
@@ -59,6 +60,48 @@ constexpr int kRefillIdle = 8;     // idle lanes that trigger a refill from the 
 #endif
 constexpr int kDescendSteps = GP_DESCEND_STEPS;
 constexpr int kQuadricBatch = 8;   // parked sphere/disk tests that trigger their batched execution
+
+// One traversal step from an inner node whose box has passed: fetch its 4-record child group (128 contiguous bytes:
+// slots 0,1 = children of the left child, or the left child itself + an empty slot when it is a leaf; slots 2,3
+// likewise for the right child), test the (up to four) float32 boxes, continue with the first passing child in the
+// binary tree's near-first order — near side of the node's own split axis first, inside each side the near child of
+// that side's split axis first — and stack the other passing ones so that they pop in that same order.
+// (cur_a, cur_b) are the record words of the current node on entry and of the next node on exit (have_cur = false
+// when the traversal is over).  Returns the number of child records tested.
+GP_D int quad_step(const DevScene& sc, unsigned& cur_a, unsigned& cur_b, bool& have_cur, int& sp, unsigned* stack, int stride, int stack_cap,
+                   const RayF32& rf, int nx, int ny, int nz, float tub, int& ovf) {
+  const float4* pp = sc.nodes + 2 * (size_t)cur_a;
+  float4 c0a = __ldg(pp), c0b = __ldg(pp + 1), c1a = __ldg(pp + 2), c1b = __ldg(pp + 3);
+  float4 c2a = __ldg(pp + 4), c2b = __ldg(pp + 5), c3a = __ldg(pp + 6), c3b = __ldg(pp + 7);
+  const bool le = (cur_b & 64u) != 0, re = (cur_b & 128u) != 0;
+  bool p0 = slab_test_f32_maybe(c0a, c0b, rf, nx, ny, nz, tub);
+  bool p1 = le && slab_test_f32_maybe(c1a, c1b, rf, nx, ny, nz, tub);
+  bool p2 = slab_test_f32_maybe(c2a, c2b, rf, nx, ny, nz, tub);
+  bool p3 = re && slab_test_f32_maybe(c3a, c3b, rf, nx, ny, nz, tub);
+  const int ax0 = cur_b & 3, ax1 = (cur_b >> 2) & 3, ax2 = (cur_b >> 4) & 3;
+  const bool n0 = (ax0 == 0 ? nx : (ax0 == 1 ? ny : nz)) != 0;
+  const bool n1 = (ax1 == 0 ? nx : (ax1 == 1 ? ny : nz)) != 0;
+  const bool n2 = (ax2 == 0 ? nx : (ax2 == 1 ? ny : nz)) != 0;
+  unsigned a0 = __float_as_uint(c0a.w), b0 = __float_as_uint(c0b.w), a1 = __float_as_uint(c1a.w), b1 = __float_as_uint(c1b.w);
+  unsigned a2 = __float_as_uint(c2a.w), b2 = __float_as_uint(c2b.w), a3 = __float_as_uint(c3a.w), b3 = __float_as_uint(c3b.w);
+  // left side in visit order (lf first, ls second), right side likewise
+  unsigned lfa = n1 ? a1 : a0, lfb = n1 ? b1 : b0, lsa = n1 ? a0 : a1, lsb = n1 ? b0 : b1;
+  bool plf = n1 ? p1 : p0, pls = n1 ? p0 : p1;
+  unsigned rfa = n2 ? a3 : a2, rfb = n2 ? b3 : b2, rsa = n2 ? a2 : a3, rsb = n2 ? b2 : b3;
+  bool prf = n2 ? p3 : p2, prs = n2 ? p2 : p3;
+  // o0..o3: the four children in visit order
+  unsigned o0a = n0 ? rfa : lfa, o0b = n0 ? rfb : lfb, o1a = n0 ? rsa : lsa, o1b = n0 ? rsb : lsb;
+  unsigned o2a = n0 ? lfa : rfa, o2b = n0 ? lfb : rfb, o3a = n0 ? lsa : rsa, o3b = n0 ? lsb : rsb;
+  bool q0 = n0 ? prf : plf, q1 = n0 ? prs : pls, q2 = n0 ? plf : prf, q3 = n0 ? pls : prs;
+  if (sp + 3 > stack_cap) { ovf = 1; have_cur = false; sp = 0; return 2 + (le ? 1 : 0) + (re ? 1 : 0); }
+  if (q3) { stack[(2 * sp) * stride] = o3a; stack[(2 * sp + 1) * stride] = o3b; ++sp; }
+  if (q2) { stack[(2 * sp) * stride] = o2a; stack[(2 * sp + 1) * stride] = o2b; ++sp; }
+  if (q1) { stack[(2 * sp) * stride] = o1a; stack[(2 * sp + 1) * stride] = o1b; ++sp; }
+  if (q0) { cur_a = o0a; cur_b = o0b; }
+  else if (sp > 0) { --sp; cur_a = stack[(2 * sp) * stride]; cur_b = stack[(2 * sp + 1) * stride]; }
+  else have_cur = false;
+  return 2 + (le ? 1 : 0) + (re ? 1 : 0);
+}
 
 // Persistent warps with dynamic ray replacement ("while-while" traversal):
 //   refill  idle lanes take the next ray of the warp's chunk (one atomicAdd per 256 rays), so a warp is never held
@@ -163,8 +206,7 @@ __global__ void __launch_bounds__(kTraceThreads, 4) k_trace(DevScene sc, RayRec*
       continue;
     }
     // ---- phase 1: descend to the next leaf (lanes that still have leaf candidates or a deferred test skip this).
-    //      One step fetches BOTH children of the current node (adjacent 32-byte records = one 64-byte access) and tests
-    //      their boxes; the near child by split axis and ray sign goes first, the far one is stacked if it passed.
+    //      One step (quad_step) fetches the 128-byte group of the current node's grandchildren and tests their boxes.
     if (leaf_i >= leaf_n && pending < 0) {
       leaf_n = 0; leaf_i = 0;
       // at most kDescendSteps node steps per round: lanes that already hold a leaf are not kept waiting for the one lane
@@ -177,29 +219,8 @@ __global__ void __launch_bounds__(kTraceThreads, 4) k_trace(DevScene sc, RayRec*
           else have_cur = false;
           break;
         }
-        const float4* pp = sc.nodes + 2 * (size_t)cur_a;
-        float4 l0 = __ldg(pp), l1 = __ldg(pp + 1), r0 = __ldg(pp + 2), r1 = __ldg(pp + 3);
-        if (COUNT) c.nodes += 2;
-        bool pl = slab_test_f32_maybe(l0, l1, rf, nx, ny, nz, tmax_ub);
-        bool pr = slab_test_f32_maybe(r0, r1, rf, nx, ny, nz, tmax_ub);
-        int axis = cur_b & 3;
-        int neg = axis == 0 ? nx : (axis == 1 ? ny : nz);
-        unsigned la = __float_as_uint(l0.w), lb = __float_as_uint(l1.w), ra = __float_as_uint(r0.w), rb = __float_as_uint(r1.w);
-        unsigned fa = neg ? ra : la, fb = neg ? rb : lb, sa = neg ? la : ra, sb = neg ? lb : rb;
-        bool pf = neg ? pr : pl, ps = neg ? pl : pr;
-        if (pf) {
-          if (ps) {
-            if (sp >= stack_cap) { ovf = 1; have_cur = false; sp = 0; break; }
-            stack[(2 * sp) * stride] = sa; stack[(2 * sp + 1) * stride] = sb; ++sp;
-          }
-          cur_a = fa; cur_b = fb;
-        } else if (ps) {
-          cur_a = sa; cur_b = sb;
-        } else if (sp > 0) {
-          --sp; cur_a = stack[(2 * sp) * stride]; cur_b = stack[(2 * sp + 1) * stride];
-        } else {
-          have_cur = false;
-        }
+        int tested = quad_step(sc, cur_a, cur_b, have_cur, sp, stack, stride, stack_cap, rf, nx, ny, nz, tmax_ub, ovf);
+        if (COUNT) c.nodes += tested;
       }
     }
     // ---- phase 2: the leaf's candidates in order; triangles are tested here, a sphere/disk candidate is parked in
@@ -321,28 +342,7 @@ GP_D bool trace_single(const DevScene& sc, Ray& ray, int* rec_out, int* cls_out,
         else have_cur = false;
         break;
       }
-      const float4* pp = sc.nodes + 2 * (size_t)cur_a;
-      float4 l0 = __ldg(pp), l1 = __ldg(pp + 1), r0 = __ldg(pp + 2), r1 = __ldg(pp + 3);
-      bool pl = slab_test_f32_maybe(l0, l1, rf, nx, ny, nz, tub);
-      bool pr = slab_test_f32_maybe(r0, r1, rf, nx, ny, nz, tub);
-      int axis = cur_b & 3;
-      int neg = axis == 0 ? nx : (axis == 1 ? ny : nz);
-      unsigned la = __float_as_uint(l0.w), lb = __float_as_uint(l1.w), ra = __float_as_uint(r0.w), rb = __float_as_uint(r1.w);
-      unsigned fa = neg ? ra : la, fb = neg ? rb : lb, sa = neg ? la : ra, sb = neg ? lb : rb;
-      bool pf = neg ? pr : pl, ps = neg ? pl : pr;
-      if (pf) {
-        if (ps) {
-          if (sp >= stack_cap) { ovf = 1; have_cur = false; sp = 0; break; }
-          stack[(2 * sp) * stride] = sa; stack[(2 * sp + 1) * stride] = sb; ++sp;
-        }
-        cur_a = fa; cur_b = fb;
-      } else if (ps) {
-        cur_a = sa; cur_b = sb;
-      } else if (sp > 0) {
-        --sp; cur_a = stack[(2 * sp) * stride]; cur_b = stack[(2 * sp + 1) * stride];
-      } else {
-        have_cur = false;
-      }
+      quad_step(sc, cur_a, cur_b, have_cur, sp, stack, stride, stack_cap, rf, nx, ny, nz, tub, ovf);
     }
     for (unsigned i = 0; i < leaf_n; i++) {
       unsigned ri = leaf_a + i;

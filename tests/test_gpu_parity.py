@@ -303,25 +303,3 @@ def test_fast_mode_sample_partition_sums_to_single(gp, dev):
     assert np.array_equal(acc[..., 3], single[..., 3])
     assert np.allclose(acc, single, rtol=1e-12, atol=0)
     g.close()
-
-
-def test_pooled_traversal_kernels_bit_exact(gp, dev, monkeypatch):
-    # GOPBRT_TRACE=pool (read at scene creation) selects the experimental pooled traversal kernels (gp_trace_pool.cuh):
-    # same per-ray visit order and arithmetic as the default kernels, so rays AND films must be bit-identical
-    monkeypatch.setenv("GOPBRT_TRACE", "pool")
-    scene = gp.scenes.mixed_test_scene(300)
-    g = gp.pbrt.GpuScene(dev, scene)
-    s = OracleScene(scene, 1)
-    rng = np.random.default_rng(11)
-    n = 100000
-    o = rng.uniform(-15, 15, size=(n, 3)); o[:, 1] = rng.uniform(0, 12, size=n)
-    d = rng.normal(size=(n, 3))
-    tm = np.where(rng.uniform(size=n) < 0.3, rng.uniform(1, 30, size=n), np.inf)
-    _cmp_closest(g.Intersect(o, d, tm), s.intersect(o, d, tm), "pooled random")
-    assert np.array_equal(g.IntersectP(o, d, tm), s.intersect_p(o, d, tm))
-    for k in (1, 31, 33, 257):  # ragged batches: fewer rays than one warp's pool, chunk boundaries
-        _cmp_closest(g.Intersect(o[:k], d[:k], tm[:k]), s.intersect(o[:k], d[:k], tm[:k]), f"pooled {k} rays")
-    g.close(); s.close()
-    scene, integ = gp.scenes.config2(W=96, H=54, spp=(3, 3))
-    film, st, ofilm, ost = _render_both(gp, dev, scene, integ, 1)
-    _assert_film_equal(film, ofilm, st, ost, "config2 pooled")
