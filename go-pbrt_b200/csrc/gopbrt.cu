@@ -589,14 +589,27 @@ static int render_impl(gopbrt_scene* sc, const gopbrt_camera* cam, const gopbrt_
   P.tpw = (int)tpw; P.tph = (int)tph;
   if (P.mode == GOPBRT_MODE_STRICT) { P.rank = rank; P.world = world; P.s_rank = 0; P.s_world = 1; }
   else { P.rank = 0; P.world = 1; P.s_rank = rank; P.s_world = world; }
-  long long lanes_total = (P.ntiles - P.rank + P.world - 1) / P.world;
+  // FAST mode: a pixel's samples are independent, so a tile can be worked on by several lanes at once ("lane groups",
+  // each taking every groups-th sample of this rank's share).  That turns the long per-lane sample chains of a 64-spp
+  // frame — hundreds of wavefront iterations whose tail runs nearly empty — into many short ones, paid for with lane
+  // state in HBM.  Bits 8..15 of the flags choose the group count; 0 = automatic (about 8 samples per lane).
+  P.groups = 1;
+  if (P.mode == GOPBRT_MODE_FAST) {
+    int want = (flags >> 8) & 0xff;
+    int share = (P.spp - 1 + P.s_world - 1) / P.s_world;  // samples 1..spp-1 of every pixel, split over the ranks
+    if (want == 0) want = std::max(1, std::min(8, share / 8));
+    P.groups = std::max(1, std::min(want, std::max(1, share)));
+  }
+  long long lanes_total = ((P.ntiles - P.rank + P.world - 1) / P.world) * P.groups;
 
   cudaStream_t st = ctx->stream;
   GP_CUDA(ctx, cudaSetDevice(ctx->device));
   GP_CUDA(ctx, cudaMemsetAsync(d_film, 0, (size_t)fw * fh * 4 * sizeof(double), st));
 
   // ---- workspace
-  size_t per_lane = sizeof(RayRec) + sizeof(ShadowRec) + sizeof(PathRec) + 9 * 4 + (size_t)P.ndims * P.spp * 8 + (size_t)tpw * tph * 4 * 8;
+  // the stratified 1-D tables exist only in STRICT mode (FAST derives a sample's stratum from a hashed permutation)
+  const size_t table_doubles = P.mode == GOPBRT_MODE_FAST ? 0 : (size_t)P.ndims * P.spp;
+  size_t per_lane = sizeof(RayRec) + sizeof(ShadowRec) + sizeof(PathRec) + 9 * 4 + table_doubles * 8 + (size_t)tpw * tph * 4 * 8;
   size_t free_b = 0, total_b = 0;
   GP_CUDA(ctx, cudaMemGetInfo(&free_b, &total_b));
   Workspace& W = sc->ws;
@@ -605,7 +618,7 @@ static int render_impl(gopbrt_scene* sc, const gopbrt_camera* cam, const gopbrt_
   if (opt && opt->max_lanes > 0) cap = std::min<long long>(cap, opt->max_lanes);
   long long lanes = std::max<long long>(1, std::min(lanes_total, cap));
   if (lanes > 0x7fffff00LL) lanes = 0x7fffff00LL;
-  size_t bt = (size_t)P.ndims * P.spp * lanes, bp = (size_t)tpw * tph * 4 * lanes;
+  size_t bt = table_doubles * lanes, bp = (size_t)tpw * tph * 4 * lanes;
   if (W.lanes != lanes || W.bytes_tables != bt || W.bytes_tilepix != bp) {
     W.ray.release(); W.sray.release(); W.path.release(); W.i32.release(); W.tables.release(); W.tilepix.release();
     GP_CUDA(ctx, W.ray.alloc((size_t)lanes));

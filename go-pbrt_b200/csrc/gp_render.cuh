@@ -37,7 +37,9 @@ struct RenderParams {
   int tpw, tph;                  // allocated tile-pixel-bounds extent
   int rank, world;               // tile partition (STRICT): this rank owns tiles t with t % world == rank
   int s_rank, s_world;           // sample partition (FAST): this rank owns samples s with s % s_world == s_rank
-  long long lane_base;           // first lane-slot (tile = (lane_base + lane) * world + rank) of this pass
+  int groups;                    // FAST: lanes per tile; lane-slot k works on tile k / groups and, of this rank's samples,
+                                 // on those with s % (s_world * groups) == s_rank * groups + k % groups  (1 in STRICT mode)
+  long long lane_base;           // first lane-slot (tile = ((lane_base + lane) / groups) * world + rank) of this pass
   long long lanes_active;        // lanes in use this pass
 };
 
@@ -535,7 +537,8 @@ GP_D void film_add_sample(const Lanes& L, const RenderParams& P, long long lane,
 GP_D bool generate_lane(const DevScene& sc, const Lanes& L, const RenderParams& P, long long lane, bool have_sample,
                         unsigned long long& cam, unsigned long long& nans, unsigned long long& culled) {
   bool go = false;
-  long long tile = (P.lane_base + lane) * P.world + P.rank;
+  long long tile = ((P.lane_base + lane) / P.groups) * P.world + P.rank;
+  const int s_mod = P.s_world * P.groups, s_res = P.s_rank * P.groups + (int)((P.lane_base + lane) % P.groups);
   PathRec pt = L.path[lane];
   if (have_sample) {  // every lane of the regeneration queue carries a finished sample
     RGB Lc = rgb(pt.Lr, pt.Lg, pt.Lb);
@@ -559,7 +562,7 @@ GP_D bool generate_lane(const DevScene& sc, const Lanes& L, const RenderParams& 
         s.cur1 = 0; s.cur2 = 0;
         s.sidx += 1;
         if (s.sidx < P.spp) {
-          if (P.s_world > 1 && (s.sidx % P.s_world) != P.s_rank) continue;  // FAST: samples split by index
+          if (s_mod > 1 && (s.sidx % s_mod) != s_res) continue;  // FAST: samples split by index (over ranks, then lane groups)
           have = true;
           break;
         }
@@ -704,7 +707,7 @@ GP_D void shade_lane(const DevScene& sc, const Lanes& L, const RenderParams& P, 
       s.cur1 = (packed >> 8) & 255; s.cur2 = (packed >> 16) & 255; s.lane = lane;
       unsigned long long fast_pixel = 0;
       if (P.mode == 1) {
-        long long tile = (P.lane_base + lane) * P.world + P.rank;
+        long long tile = ((P.lane_base + lane) / P.groups) * P.world + P.rank;
         long long x0, y0, x1, y1;
         tile_bounds(P, tile, &x0, &y0, &x1, &y1);
         int pix = pt.pix;
@@ -950,19 +953,21 @@ __global__ void k_film_merge(Lanes L, RenderParams P, double* __restrict__ film)
       for (long long tx = tx0; tx <= tx1; tx++) {
         long long tile = ty * P.ntx + tx;
         if (tile % P.world != P.rank) continue;
-        long long lane = tile / P.world - P.lane_base;
-        if (lane < 0 || lane >= P.lanes_active) continue;
         long long x0, y0, x1, y1, bx0, by0, bx1, by1;
         tile_bounds(P, tile, &x0, &y0, &x1, &y1);
         tile_pixel_bounds(P, x0, y0, x1, y1, &bx0, &by0, &bx1, &by1);
         if (x < bx0 || x >= bx1 || y < by0 || y >= by1) continue;
         size_t k = (size_t)((y - by0) * P.tpw + (x - bx0)) * 4;
-        const double* q = L.tilepix + (size_t)lane * L.tile_stride + k;
-        double r = q[0], g = q[1], b = q[2], w = q[3];
-        X += 0.412453 * r + 0.357580 * g + 0.180423 * b;
-        Y += 0.212671 * r + 0.715160 * g + 0.072169 * b;
-        Z += 0.019334 * r + 0.119193 * g + 0.950227 * b;
-        W += w;
+        for (int grp = 0; grp < P.groups; grp++) {  // the tile's lane groups in ascending order (one group in STRICT mode)
+          long long lane = (tile / P.world) * P.groups + grp - P.lane_base;
+          if (lane < 0 || lane >= P.lanes_active) continue;
+          const double* q = L.tilepix + (size_t)lane * L.tile_stride + k;
+          double r = q[0], g = q[1], b = q[2], w = q[3];
+          X += 0.412453 * r + 0.357580 * g + 0.180423 * b;
+          Y += 0.212671 * r + 0.715160 * g + 0.072169 * b;
+          Z += 0.019334 * r + 0.119193 * g + 0.950227 * b;
+          W += w;
+        }
       }
     film[i * 4] = X; film[i * 4 + 1] = Y; film[i * 4 + 2] = Z; film[i * 4 + 3] = W;
   }
@@ -971,7 +976,7 @@ __global__ void k_film_merge(Lanes L, RenderParams P, double* __restrict__ film)
 // pass start: reset per-lane sampler state (Sampler.Clone(seed = tile index), pixel.go:34-42) and tile accumulators
 __global__ void k_init_lanes(Lanes L, RenderParams P) {
   for (long long lane = (long long)blockIdx.x * blockDim.x + threadIdx.x; lane < P.lanes_active; lane += (long long)gridDim.x * blockDim.x) {
-    long long tile = (P.lane_base + lane) * P.world + P.rank;
+    long long tile = ((P.lane_base + lane) / P.groups) * P.world + P.rank;
     Smp s;
     s.state = 0x853c49e6748fea9bULL; s.inc = 0xda3e39cb94b95bdbULL;
     rng_set_sequence(s, (unsigned long long)tile);

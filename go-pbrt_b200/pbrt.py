@@ -715,16 +715,17 @@ class GpuScene:
         return hit.astype(bool)
 
 
-def Render(gpu_scene, integrator, tileSize, mode=abi.MODE_STRICT, rank=0, world=1, flags=0, max_lanes=0, device_film=None, out=None):
+def Render(gpu_scene, integrator, tileSize, mode=abi.MODE_STRICT, rank=0, world=1, flags=0, max_lanes=0, device_film=None, out=None, groups=0):
     """pbrt.Render(ctx, integrator, scene, tileSize) (integrator.go:291-350) on the GPU.  Fills camera.Film.pixels with
     the (H', W', 4) float64 film {X, Y, Z sums, filterWeightSum} and returns gopbrt_stats as a dict.
     device_film: optional CUDA device pointer (int) of H'*W'*4 doubles — the film then stays on the device.
-    out: optional preallocated float64 array of the film's shape (e.g. a view of pinned host memory) to receive the film."""
+    out: optional preallocated float64 array of the film's shape (e.g. a view of pinned host memory) to receive the film.
+    groups: FAST mode only — lane groups per pixel tile (GOPBRT_FLAG_GROUPS_*), 0 = automatic."""
     cam = integrator.GetCamera()
     film = cam.GetFilm()
     lib = gpu_scene.dev.lib
     c, s, i, f = cam.abi(), integrator.GetSampler().abi(mode), integrator.abi(tileSize), film.abi()
-    o = abi.RenderOptions(rank, world, flags, max_lanes)
+    o = abi.RenderOptions(rank, world, flags | ((int(groups) & 0xff) << 8), max_lanes)
     st = abi.Stats()
     if device_film is not None:
         rc = lib.gopbrt_render_device(gpu_scene.h, C.byref(c), C.byref(s), C.byref(i), C.byref(f), C.byref(o),

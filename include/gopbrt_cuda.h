@@ -185,7 +185,11 @@ enum {
   GOPBRT_FLAG_COUNT_TRAVERSAL = 1, /* instrumented kernels: count BVH nodes visited / primitive tests */
   GOPBRT_FLAG_FAIL_ON_PANIC = 2,   /* return GOPBRT_ERR_REFERENCE_PANIC instead of counting           */
   GOPBRT_FLAG_TIME_KERNELS = 4,    /* CUDA-event time every stage launch (fills ms_raygen … ms_tail)   */
-  GOPBRT_FLAG_TAIL = 8             /* finish the last <= 49152 lanes with the one-thread-per-lane tail kernel */
+  GOPBRT_FLAG_TAIL = 8,            /* finish the last <= 49152 lanes with the one-thread-per-lane tail kernel */
+  /* bits 8..15: GOPBRT_MODE_FAST only — lane groups per pixel tile (each group renders every n-th sample of the
+   * rank's share, into its own FilmTile; the groups are merged in ascending order).  0 = automatic. */
+  GOPBRT_FLAG_GROUPS_SHIFT = 8,
+  GOPBRT_FLAG_GROUPS_MASK = 0xff00
 };
 
 /* work partition for one process per GPU: this rank renders tiles t with t % world == rank

@@ -10,17 +10,18 @@ dev = P.Device(0)
 for name in sys.argv[2:]:
     scene, integ = getattr(gp.scenes, name)()
     g = P.GpuScene(dev, scene)
-    P.Render(g, integ, 1)
     xf = int(os.environ.get("AB_FLAGS", "0"))
-    t = P.Render(g, integ, 1, flags=gp.abi.FLAG_TIME_KERNELS | xf)
-    t = P.Render(g, integ, 1, flags=gp.abi.FLAG_TIME_KERNELS | xf)
-    p0 = P.Render(g, integ, 1, flags=xf)
-    p0 = P.Render(g, integ, 1, flags=xf)
+    kw = dict(mode=int(os.environ.get("AB_MODE", "0")), groups=int(os.environ.get("AB_GROUPS", "0")))
+    P.Render(g, integ, 1, **kw)
+    t = P.Render(g, integ, 1, flags=gp.abi.FLAG_TIME_KERNELS | xf, **kw)
+    t = P.Render(g, integ, 1, flags=gp.abi.FLAG_TIME_KERNELS | xf, **kw)
+    p0 = P.Render(g, integ, 1, flags=xf, **kw)
+    p0 = P.Render(g, integ, 1, flags=xf, **kw)
     film = integ.GetCamera().GetFilm().pixels
     import hashlib
     out = dict(tag=tag, trace=os.environ.get("GOPBRT_TRACE", "pool"), config=name, ms_plain=round(p0["ms_total"], 2), plain_iters=p0["iterations"], ms_total=round(t["ms_total"], 2),
                mrays=round((t["closest_rays"] + t["shadow_rays"]) / t["ms_total"] / 1e3, 1),
                stage={k[3:]: round(t[k], 2) for k in ("ms_raygen", "ms_extend", "ms_shade", "ms_shadow")},
-               iters=t["iterations"], ms_tail=round(t.get("ms_tail", 0), 2), rays=t["closest_rays"] + t["shadow_rays"], ovf=t["stack_overflows"], film_sha=hashlib.sha1(film.tobytes()).hexdigest()[:12])
+               iters=t["iterations"], lanes=t["lanes"], ms_tail=round(t.get("ms_tail", 0), 2), rays=t["closest_rays"] + t["shadow_rays"], ovf=t["stack_overflows"], film_sha=hashlib.sha1(film.tobytes()).hexdigest()[:12])
     print(json.dumps(out), flush=True)
     g.close()

@@ -303,3 +303,31 @@ def test_fast_mode_sample_partition_sums_to_single(gp, dev):
     assert np.array_equal(acc[..., 3], single[..., 3])
     assert np.allclose(acc, single, rtol=1e-12, atol=0)
     g.close()
+
+
+def test_fast_mode_lane_groups_sum_to_single(gp, dev):
+    # FAST mode, several lanes per pixel tile (each takes every n-th sample): same paths, same weights, film equal to the
+    # one-lane-per-tile film up to summation order; also combined with the 2-rank sample split
+    scene, integ = gp.scenes.config2(W=96, H=54, spp=(4, 4))
+    g = gp.pbrt.GpuScene(dev, scene)
+    st1 = gp.pbrt.Render(g, integ, 1, mode=gp.abi.MODE_FAST, groups=1)
+    single = integ.GetCamera().GetFilm().pixels.copy()
+    for groups in (2, 5, 15, 40):
+        st = gp.pbrt.Render(g, integ, 1, mode=gp.abi.MODE_FAST, groups=groups)
+        film = integ.GetCamera().GetFilm().pixels
+        assert st["camera_rays"] == st1["camera_rays"] == 96 * 54 * 15
+        assert st["closest_rays"] == st1["closest_rays"] and st["shadow_rays"] == st1["shadow_rays"]
+        assert st["lanes"] == 96 * 54 * min(groups, 15)
+        assert np.array_equal(film[..., 3], single[..., 3])
+        assert np.allclose(film, single, rtol=1e-12, atol=0)
+    acc = np.zeros_like(single)
+    for r in range(2):
+        gp.pbrt.Render(g, integ, 1, mode=gp.abi.MODE_FAST, rank=r, world=2, groups=3)
+        acc += integ.GetCamera().GetFilm().pixels
+    assert np.array_equal(acc[..., 3], single[..., 3])
+    assert np.allclose(acc, single, rtol=1e-12, atol=0)
+    # a pass that does not hold all lanes at once (max_lanes splits tiles' groups over passes)
+    gp.pbrt.Render(g, integ, 1, mode=gp.abi.MODE_FAST, groups=4, max_lanes=7001)
+    film = integ.GetCamera().GetFilm().pixels
+    assert np.array_equal(film[..., 3], single[..., 3]) and np.allclose(film, single, rtol=1e-12, atol=0)
+    g.close()
