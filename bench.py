@@ -6,8 +6,10 @@
 
 A "step" is one frame: one pass of pbrt.Render's hot path (raygen+sampler -> extend -> shade -> shadow -> film) over the
 workload BASELINE.json's metric is quoted on (configs[1]): the procedural Cornell-box-style room of triangles, Path
-integrator, Stratified 8x8 ("64 spp" = 63 effective samples), 1920x1080, STRICT sampler mode with
-tileSize = 1 (one reference RNG stream per pixel: identical per-pixel sample sequences to pbrt.Render(..., 1)).
+integrator, Stratified 8x8 ("64 spp" = 63 effective samples), 1920x1080.  Sampler mode: FAST by default at
+every N (counter-based streams per (pixel, sample): the north star's split by sample index across GPUs, lane groups inside
+one GPU); --mode strict = one reference RNG stream per pixel (identical per-pixel sample sequences to
+pbrt.Render(..., tileSize=1)), also reported beside the headline at N = 1 ("strict_mode").
 
 value  = Mrays/s (closest-hit + any-hit queries the reference semantics require; the always-discarded MIS ray of
          EstimateDirect is neither traced nor counted), scene resident in HBM, film left on the device; device time
@@ -154,7 +156,10 @@ def main():
     ap.add_argument("--width", type=int, default=0)
     ap.add_argument("--height", type=int, default=0)
     ap.add_argument("--tile", type=int, default=1)
-    ap.add_argument("--mode", default="strict", choices=["strict", "fast"])
+    ap.add_argument("--mode", default="fast", choices=["strict", "fast"],
+                    help="fast (default): counter-based sampler, a pixel's samples are independent -> lane groups on one GPU, "
+                         "split by sample index across GPUs (north star); strict: the unmodified reference's per-pixel RNG "
+                         "streams (tileSize 1), tiles split across GPUs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-deep-bvh", action="store_true", help="skip the config-4 (10 M triangles) extend-kernel roofline")
     ap.add_argument("--profile", action="store_true",
@@ -252,9 +257,12 @@ def main():
     desc_bytes = sum(C.sizeof(t) for t in (abi.Camera, abi.Sampler, abi.Integrator, abi.Film, abi.RenderOptions))
     barrier()
     e0 = time.time()
+    e2e_parts = {"ms_device": 0.0, "ms_download": 0.0}
     for _ in range(args.steps):
         if world == 1:
-            P.Render(g, integ, args.tile, mode=mode, out=film_host_np)  # gopbrt_render: film D2H (into pinned host memory) inside the call
+            est = P.Render(g, integ, args.tile, mode=mode, out=film_host_np)  # gopbrt_render: film D2H (into pinned host memory) inside the call
+            e2e_parts["ms_device"] += est["ms_total"] / args.steps
+            e2e_parts["ms_download"] += est.get("ms_download", 0.0) / args.steps
         else:
             step_device(0)
             if rank == 0:
@@ -316,15 +324,23 @@ def main():
                            "rays_per_step": rays_total / K, "lanes": stats[0]["lanes"], "wavefront_iterations": stats[0]["iterations"],
                            "partition": ("tiles t %% %d == rank" % world) if mode == abi.MODE_STRICT else "samples s % world == rank",
                            "l2_policy": "per-lane path/sampler/film state of %d lanes is %.1f GB >> 126 MB L2 (inputs larger than L2)" % (
-                               stats[0]["lanes"], stats[0]["lanes"] * (26 * 8 + 9 * 4 + 16 + 3 + 4 * 64 * 8 + 36 * 8) / 1e9),
+                               stats[0]["lanes"], stats[0]["lanes"] * (64 + 96 + 128 + 36 + (0 if mode == abi.MODE_FAST else 4 * 64 * 8) + 288) / 1e9),
                            "scene_create_s": scene_create_s, "bvh_nodes": stats[0]["bvh_nodes"], "bvh_depth": stats[0]["bvh_depth"],
                            "frame_time_ms": ms_total / K, "frame_time_e2e_ms": e2e_total / K * 1e3,
                            "wall_ms_per_step": wall_max / K * 1e3},
                 "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": desc_bytes, "d2h_bytes_per_step": H * W * 4 * 8,
-                        "ms_per_step": e2e_total / K * 1e3},
+                        "ms_per_step": e2e_total / K * 1e3, **({k: v for k, v in e2e_parts.items()} if world == 1 else {})},
                 "gpu_launches": int(launches_total), "clocks": clocks.summary(), "roofline": roof,
                 "reference_panics": {"radiance_gt10": stats[0]["radiance_gt10"], "efloat_panics": stats[0]["efloat_panics"],
                                      "nan_samples": stats[0]["nan_samples"]}}
+        if world == 1 and mode == abi.MODE_FAST:
+            # the same frame in STRICT mode (the unmodified reference's per-pixel sample sequences, pbrt.Render(..., tileSize=1))
+            sm = [P.Render(g, integ, args.tile, mode=abi.MODE_STRICT, device_film=film_dev.data_ptr()) for _ in range(K + 1)][1:]
+            line["strict_mode"] = {"value": sum(x["closest_rays"] + x["shadow_rays"] for x in sm) / sum(x["ms_total"] for x in sm) / 1e3,
+                                   "unit": "Mrays/s", "ms_per_step": sum(x["ms_total"] for x in sm) / K,
+                                   "wavefront_iterations": sm[0]["iterations"], "lanes": sm[0]["lanes"],
+                                   "note": "bit-exact against the oracle's STRICT mode (tests/test_gpu_parity.py); FAST is bit-exact "
+                                           "against the oracle's FAST mode and statistically equivalent"}
         if world == 1 and not args.no_deep_bvh:
             line["roofline_deep_bvh"] = deep_bvh_roofline(gp, dev, peak)
         if world == 1 and not args.no_cpu_baseline:

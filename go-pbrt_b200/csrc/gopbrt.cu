@@ -585,7 +585,10 @@ static int render_impl(gopbrt_scene* sc, const gopbrt_camera* cam, const gopbrt_
   P.ntx = (fw + P.tile_size - 1) / P.tile_size; P.nty = (fh + P.tile_size - 1) / P.tile_size;  // integrator.go:297-299
   P.ntiles = P.ntx * P.nty;
   P.frx = film->filter_radius[0]; P.fry = film->filter_radius[1];
-  long long tpw = std::min<long long>(fw, P.tile_size + 2 * (long long)ceil(P.frx) + 2), tph = std::min<long long>(fh, P.tile_size + 2 * (long long)ceil(P.fry) + 2);
+  // extent of a tile's pixel bounds (GetFilmTile, film.go:106-113): [ceil(x0 - 0.5 - r), floor(x1 - 0.5 + r) + 1) with x1 - x0 <= tileSize
+  // and integer x0, so the widest tile needs exactly this many columns / rows
+  long long tpw = std::min<long long>(fw, (long long)floor((double)P.tile_size - 0.5 + P.frx) + 1 - (long long)ceil(-0.5 - P.frx));
+  long long tph = std::min<long long>(fh, (long long)floor((double)P.tile_size - 0.5 + P.fry) + 1 - (long long)ceil(-0.5 - P.fry));
   P.tpw = (int)tpw; P.tph = (int)tph;
   if (P.mode == GOPBRT_MODE_STRICT) { P.rank = rank; P.world = world; P.s_rank = 0; P.s_world = 1; }
   else { P.rank = 0; P.world = 1; P.s_rank = rank; P.s_world = world; }
