@@ -37,6 +37,12 @@ METRIC = "Mrays/s (closest-hit + any-hit) at 1080p, Path integrator, fixed spp"
 WORKLOADS = {
     "config2": dict(name="config2: procedural Cornell-box-style room of triangles + matte/glass spheres, disk area light, "
                          "Path maxDepth 10, Stratified 8x8 (63 effective spp), 1920x1080", W=1920, H=1080, spp=(8, 8)),
+    "config3": dict(name="config3: random 100k-sphere field, mixed materials, 8 sphere area lights + distant light, Path maxDepth 10, "
+                         "Stratified 16x16 (255 effective spp), 1920x1080", W=1920, H=1080, spp=(16, 16)),
+    "config4": dict(name="config4: 10 M-triangle heightfield (2237x2237 grid), Path maxDepth 10, Stratified 4x4 (15 effective spp), "
+                         "1920x1080", W=1920, H=1080, spp=(4, 4)),
+    "config5": dict(name="config5: 10 M-triangle heightfield, Path maxDepth 10, Stratified 32x32 (1023 effective spp), 3840x2160, "
+                         "samples split across the GPUs + one NCCL film reduce", W=3840, H=2160, spp=(32, 32)),
     "config1": dict(name="config1: README sphere scene (internal/render/server.go), Path maxDepth 10, Stratified 4x4 "
                          "(15 effective spp), 1920x1080", W=1920, H=1080, spp=(4, 4)),
 }
@@ -161,6 +167,7 @@ def main():
                          "split by sample index across GPUs (north star); strict: the unmodified reference's per-pixel RNG "
                          "streams (tileSize 1), tiles split across GPUs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--min-warmup", type=int, default=3, help="lower bound on warm-up frames (supplementary long-frame workloads only)")
     ap.add_argument("--no-deep-bvh", action="store_true", help="skip the config-4 (10 M triangles) extend-kernel roofline")
     ap.add_argument("--profile", action="store_true",
                     help="profiling run for ncu: exactly --warmup warm-up frames (0 allowed), --steps timed frames, "
@@ -222,7 +229,7 @@ def main():
             ms += ev0.elapsed_time(ev1)
         return st, ms
 
-    for _ in range(args.warmup if args.profile else max(3, args.warmup)):
+    for _ in range(args.warmup if args.profile else max(args.min_warmup, args.warmup)):
         step_device(0)
     if args.profile:
         for _ in range(args.steps):
@@ -316,7 +323,7 @@ def main():
                 "per_ray": {"nodes_visited": (cst["nodes_visited"] - cst["root_culled_rays"]) / max(1, ext_rays),
                             "shape_tests": cst["prim_tests"] / max(1, ext_rays)},
                 "stage_ms_per_step": {k: sum(s[k] for s in stage_stats) / KS for k in ("ms_raygen", "ms_extend", "ms_shade", "ms_shadow", "ms_film")}}
-        line = {"metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": K, "warmup": max(3, args.warmup),
+        line = {"metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": K, "warmup": max(args.min_warmup, args.warmup),
                 "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic",
                 "config": {"workload": wl["name"], "resolution": [W, H], "tile_size": args.tile, "sampler_mode": args.mode,
