@@ -65,6 +65,23 @@ GP_D void queue_push(int* q, int* cnt, bool pred, int v) {
   if (pred) q[base + __popc(m & ((1u << lane_id) - 1u))] = v;
 }
 
+// three pushes of one warp with ONE atomic round trip: lanes 0/1/2 reserve the space of queue A/B/C at the same time
+GP_D void queue_push3(int* qa, int* ca, bool pa, int* qb, int* cb, bool pb, int* qc, int* cc, bool pc, int v) {
+  const unsigned FULL = 0xffffffffu;
+  unsigned ma = __ballot_sync(FULL, pa), mb = __ballot_sync(FULL, pb), mc = __ballot_sync(FULL, pc);
+  if ((ma | mb | mc) == 0) return;
+  int lane_id = threadIdx.x & 31;
+  int base = 0;
+  if (lane_id == 0 && ma) base = atomicAdd(ca, __popc(ma));
+  if (lane_id == 1 && mb) base = atomicAdd(cb, __popc(mb));
+  if (lane_id == 2 && mc) base = atomicAdd(cc, __popc(mc));
+  int ba = __shfl_sync(FULL, base, 0), bb = __shfl_sync(FULL, base, 1), bc = __shfl_sync(FULL, base, 2);
+  unsigned lt = (1u << lane_id) - 1u;
+  if (pa) qa[ba + __popc(ma & lt)] = v;
+  if (pb) qb[bb + __popc(mb & lt)] = v;
+  if (pc) qc[bc + __popc(mc & lt)] = v;
+}
+
 // ---------------------------------------------------------------- RNG (pkg/pbrt/rng.go — a PCG32 *variant*)
 struct Smp {
   unsigned long long state, inc;
@@ -630,7 +647,16 @@ GP_D bool generate_lane(const DevScene& sc, const Lanes& L, const RenderParams& 
 // Retires the lane's finished sample into its film tile (renderWorker, integrator.go:252-265), advances the sampler
 // (StartNextSample / next pixel + StartPixel) and generates the next camera ray (GenerateRayDifferential,
 // camera.go:192-242; the differentials are dropped by Path.Li).  Lanes whose tile is exhausted leave the wavefront.
-__global__ void __launch_bounds__(128) k_generate(DevScene sc, Lanes L, RenderParams P, Queues Q, const int* __restrict__ in_queue,
+#ifndef GP_GEN_MINBLOCKS
+#define GP_GEN_MINBLOCKS 1
+#endif
+#ifndef GP_GEN_TILE_PREFETCH
+#define GP_GEN_TILE_PREFETCH 0
+#endif
+#ifndef GP_SPLIT_BLOCKAGG
+#define GP_SPLIT_BLOCKAGG 1
+#endif
+__global__ void __launch_bounds__(128, GP_GEN_MINBLOCKS) k_generate(DevScene sc, Lanes L, RenderParams P, Queues Q, const int* __restrict__ in_queue,
                                                   const int* __restrict__ in_count, RenderCounters* ctr) {
   long long n = in_queue ? (long long)*in_count : P.lanes_active;
   int lane_id = threadIdx.x & 31;
@@ -643,6 +669,13 @@ __global__ void __launch_bounds__(128) k_generate(DevScene sc, Lanes L, RenderPa
     long long lane = 0;
     if (valid) {
       lane = in_queue ? in_queue[i] : i;
+      if (GP_GEN_TILE_PREFETCH && in_queue) {
+        // the lane's FilmTile record is read-modified-written once its PathRec (sample position) has arrived: start
+        // pulling it in now, in the shadow of the PathRec load, instead of after it
+        const char* tp = (const char*)(L.tilepix + (size_t)lane * L.tile_stride);
+        size_t nb = (size_t)L.tile_stride * 8;
+        for (size_t o = 0; o < nb; o += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(tp + o));
+      }
       go = generate_lane(sc, L, P, lane, in_queue != nullptr, cam, nans, culled);
     }
     queue_push(Q.extend, Q.cnt + 0, go, (int)lane);
@@ -662,6 +695,43 @@ __global__ void __launch_bounds__(128) k_generate(DevScene sc, Lanes L, RenderPa
 __global__ void __launch_bounds__(256) k_split_hits(Lanes L, Queues Q) {
   long long n = Q.cnt[0];
   int lane_id = threadIdx.x & 31;
+#if GP_SPLIT_BLOCKAGG
+  // one atomicAdd per CTA and output queue instead of one per warp: the five counters are single addresses, and at
+  // several million lanes per launch the per-warp atomics on them serialise
+  __shared__ int s_cnt[8][5];
+  __shared__ int s_base[5];
+  const int warp = threadIdx.x >> 5;
+  for (long long cbase = (long long)blockIdx.x * blockDim.x; cbase < n; cbase += (long long)gridDim.x * blockDim.x) {
+    long long i = cbase + threadIdx.x;
+    bool valid = i < n;
+    int lane = 0, rec = -1, cls = 0;
+    if (valid) {
+      lane = Q.extend[i];
+      int2 rc = *(const int2*)&L.ray[lane].hit_rec;  // {hit_rec, shade class}
+      rec = rc.x; cls = rc.y;
+    }
+    int bin = !valid ? -1 : (rec >= 0 ? cls : 4);
+    unsigned m[5];
+#pragma unroll
+    for (int k = 0; k < 5; k++) { m[k] = __ballot_sync(0xffffffffu, bin == k); if (lane_id == 0) s_cnt[warp][k] = __popc(m[k]); }
+    __syncthreads();
+    if (threadIdx.x < 5) {
+      int tot = 0;
+      for (int w = 0; w < 8; w++) tot += s_cnt[w][threadIdx.x];
+      int* cnt = threadIdx.x < 4 ? Q.cnt + 8 + threadIdx.x : Q.cnt + 4;
+      s_base[threadIdx.x] = tot ? atomicAdd(cnt, tot) : 0;
+    }
+    __syncthreads();
+    if (bin >= 0) {
+      int off = s_base[bin];
+      for (int w = 0; w < warp; w++) off += s_cnt[w][bin];
+      unsigned mm = bin == 0 ? m[0] : (bin == 1 ? m[1] : (bin == 2 ? m[2] : (bin == 3 ? m[3] : m[4])));
+      int* q = bin < 4 ? Q.shade[bin] : Q.regen_next;
+      q[off + __popc(mm & ((1u << lane_id) - 1u))] = lane;
+    }
+    __syncthreads();
+  }
+#else
   long long warp_base0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) - lane_id;
   for (long long base = warp_base0; base < n; base += (long long)gridDim.x * blockDim.x) {
     long long i = base + lane_id;
@@ -677,6 +747,7 @@ __global__ void __launch_bounds__(256) k_split_hits(Lanes L, Queues Q) {
     for (int k = 0; k < 4; k++) queue_push(Q.shade[k], Q.cnt + 8 + k, hit && cls == k, lane);
     queue_push(Q.regen_next, Q.cnt + 4, valid && rec < 0, lane);
   }
+#endif
 }
 
 // ---------------------------------------------------------------- shade
@@ -843,9 +914,7 @@ __global__ void __launch_bounds__(128, 3) k_shade(DevScene sc, Lanes L, RenderPa
       lane = bin_q[bi];
       shade_lane(sc, L, P, lane, cont, finished, shadow, n_unsupported, n_dead, bad);
     }
-    queue_push(Q.shadow, Q.cnt + 2, shadow, (int)lane);
-    queue_push(Q.extend_next, Q.cnt + 1, cont, (int)lane);
-    queue_push(Q.regen_next, Q.cnt + 4, finished && valid, (int)lane);
+    queue_push3(Q.shadow, Q.cnt + 2, shadow, Q.extend_next, Q.cnt + 1, cont, Q.regen_next, Q.cnt + 4, finished && valid, (int)lane);
   }
   n_unsupported = warp_sum(n_unsupported); n_dead = warp_sum(n_dead);
   if (lane_id == 0) {
