@@ -82,6 +82,37 @@ GP_D void queue_push3(int* qa, int* ca, bool pa, int* qb, int* cb, bool pb, int*
   if (pc) qc[bc + __popc(mc & lt)] = v;
 }
 
+// CTA-wide pushes (every thread of the CTA must call them, inside CTA-uniform control flow): one atomic per CTA and
+// queue, and the CTA's entries land in the queue as one contiguous run in thread order, which keeps neighbouring lanes
+// (neighbouring pixels / sample groups) next to each other for the stage that consumes the queue.
+#ifndef GP_BLOCK_PUSH
+#define GP_BLOCK_PUSH 1
+#endif
+template <int NQ>
+GP_D void block_push(int* const (&q)[NQ], int* const (&cnt)[NQ], const bool (&pred)[NQ], int v, int (*s_cnt)[NQ], int* s_base) {
+  const unsigned FULL = 0xffffffffu;
+  const int lane_id = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  unsigned m[NQ];
+#pragma unroll
+  for (int k = 0; k < NQ; k++) { m[k] = __ballot_sync(FULL, pred[k]); if (lane_id == 0) s_cnt[warp][k] = __popc(m[k]); }
+  __syncthreads();
+  if (threadIdx.x < NQ) {
+    int tot = 0;
+    for (int w = 0; w < nwarps; w++) tot += s_cnt[w][threadIdx.x];
+    s_base[threadIdx.x] = tot ? atomicAdd(cnt[threadIdx.x], tot) : 0;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < NQ; k++) {
+    if (pred[k]) {
+      int off = s_base[k];
+      for (int w = 0; w < warp; w++) off += s_cnt[w][k];
+      q[k][off + __popc(m[k] & ((1u << lane_id) - 1u))] = v;
+    }
+  }
+  __syncthreads();
+}
+
 // ---------------------------------------------------------------- RNG (pkg/pbrt/rng.go — a PCG32 *variant*)
 struct Smp {
   unsigned long long state, inc;
@@ -661,24 +692,31 @@ __global__ void __launch_bounds__(128, GP_GEN_MINBLOCKS) k_generate(DevScene sc,
   long long n = in_queue ? (long long)*in_count : P.lanes_active;
   int lane_id = threadIdx.x & 31;
   unsigned long long cam = 0, nans = 0, culled = 0;
+#if GP_BLOCK_PUSH
+  __shared__ int s_cnt[4][1];
+  __shared__ int s_base[1];
+  for (long long cbase = (long long)blockIdx.x * blockDim.x; cbase < n; cbase += (long long)gridDim.x * blockDim.x) {
+    long long i = cbase + threadIdx.x;
+#else
   long long warp_base0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) - lane_id;
   for (long long base = warp_base0; base < n; base += (long long)gridDim.x * blockDim.x) {
     long long i = base + lane_id;
+#endif
     bool valid = i < n;
     bool go = false;
     long long lane = 0;
     if (valid) {
       lane = in_queue ? in_queue[i] : i;
-      if (GP_GEN_TILE_PREFETCH && in_queue) {
-        // the lane's FilmTile record is read-modified-written once its PathRec (sample position) has arrived: start
-        // pulling it in now, in the shadow of the PathRec load, instead of after it
-        const char* tp = (const char*)(L.tilepix + (size_t)lane * L.tile_stride);
-        size_t nb = (size_t)L.tile_stride * 8;
-        for (size_t o = 0; o < nb; o += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(tp + o));
-      }
       go = generate_lane(sc, L, P, lane, in_queue != nullptr, cam, nans, culled);
     }
+#if GP_BLOCK_PUSH
+    int* const qs[1] = {Q.extend};
+    int* const cs[1] = {Q.cnt + 0};
+    const bool ps[1] = {go};
+    block_push<1>(qs, cs, ps, (int)lane, s_cnt, s_base);
+#else
     queue_push(Q.extend, Q.cnt + 0, go, (int)lane);
+#endif
   }
   cam = warp_sum(cam); nans = warp_sum(nans); culled = warp_sum(culled);
   if (lane_id == 0) {
@@ -898,9 +936,16 @@ __global__ void __launch_bounds__(128, 3) k_shade(DevScene sc, Lanes L, RenderPa
   int lane_id = threadIdx.x & 31;
   unsigned long long n_unsupported = 0, n_dead = 0;
   int bad = 0;
+#if GP_BLOCK_PUSH
+  __shared__ int s_cnt[4][3];
+  __shared__ int s_base[3];
+  for (long long cbase = (long long)blockIdx.x * blockDim.x; cbase < n; cbase += (long long)gridDim.x * blockDim.x) {
+    long long i = cbase + threadIdx.x;
+#else
   long long warp_base0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) - lane_id;
   for (long long base = warp_base0; base < n; base += (long long)gridDim.x * blockDim.x) {
     long long i = base + lane_id;
+#endif
     const int* bin_q;
     long long bi;
     if (i >= o3) { bin_q = Q.shade[3]; bi = i - o3; if (bi >= n3) bi = -1; }
@@ -914,7 +959,14 @@ __global__ void __launch_bounds__(128, 3) k_shade(DevScene sc, Lanes L, RenderPa
       lane = bin_q[bi];
       shade_lane(sc, L, P, lane, cont, finished, shadow, n_unsupported, n_dead, bad);
     }
+#if GP_BLOCK_PUSH
+    int* const qs[3] = {Q.shadow, Q.extend_next, Q.regen_next};
+    int* const cs[3] = {Q.cnt + 2, Q.cnt + 1, Q.cnt + 4};
+    const bool ps[3] = {shadow, cont, finished && valid};
+    block_push<3>(qs, cs, ps, (int)lane, s_cnt, s_base);
+#else
     queue_push3(Q.shadow, Q.cnt + 2, shadow, Q.extend_next, Q.cnt + 1, cont, Q.regen_next, Q.cnt + 4, finished && valid, (int)lane);
+#endif
   }
   n_unsupported = warp_sum(n_unsupported); n_dead = warp_sum(n_dead);
   if (lane_id == 0) {
