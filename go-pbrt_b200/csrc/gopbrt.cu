@@ -68,7 +68,7 @@ struct Workspace {  // per-scene render workspace, kept between gopbrt_render ca
   DevBuf<ShadowRec> sray;
   DevBuf<PathRec> path;
   DevBuf<int> i32;        // queues
-  DevBuf<double> tables, tilepix;
+  DevBuf<double> tables, tilepix, frames;
   DevBuf<int> cnt;
   DevBuf<RenderCounters> rctr;
   int* remaining_host = nullptr;  // pinned, device-mapped
@@ -553,8 +553,15 @@ static int render_impl(gopbrt_scene* sc, const gopbrt_camera* cam, const gopbrt_
                        const gopbrt_film* film, const gopbrt_render_options* opt, double* d_film, gopbrt_stats* stats) {
   gopbrt_ctx* ctx = sc->ctx;
   auto bad = [&](const char* msg) { ctx->last_error = msg; return GOPBRT_ERR_INVALID; };
-  if (ig->kind != GOPBRT_INTEGRATOR_PATH) return bad("only the Path integrator is on the hot path");
-  if (ig->light_strategy != GOPBRT_LIGHTS_UNIFORM) return bad("only the Uniform light strategy is supported");
+  if (ig->kind == GOPBRT_INTEGRATOR_PATH) {
+    if (ig->light_strategy != GOPBRT_LIGHTS_UNIFORM) return bad("Path: only the Uniform light strategy is supported");
+  } else if (ig->kind == GOPBRT_INTEGRATOR_DIRECT_LIGHTING) {
+    if (ig->light_strategy != GOPBRT_DL_SAMPLE_ONE) {
+      ctx->last_error = "DirectLighting: only UniformSampleOne runs on the GPU (UniformSampleAll needs one shadow segment per light)";
+      return GOPBRT_ERR_UNSUPPORTED;
+    }
+    if (ig->max_depth > 250) return bad("DirectLighting: max_depth out of range");
+  } else return bad("unknown integrator kind");
   if (ig->tile_size < 1) return bad("tile_size < 1");
   if (!(film->filter_radius[0] > 0) || !(film->filter_radius[1] > 0)) return bad("filter radius must be positive");
   if (smp->kind != GOPBRT_SAMPLER_STRATIFIED && smp->kind != GOPBRT_SAMPLER_RANDOM) return bad("unknown sampler");
@@ -576,6 +583,8 @@ static int render_impl(gopbrt_scene* sc, const gopbrt_camera* cam, const gopbrt_
   P.spp = smp->kind == GOPBRT_SAMPLER_STRATIFIED ? smp->x_samples * smp->y_samples : smp->x_samples;
   if (P.spp < 1) return bad("samples per pixel < 1");
   P.max_depth = ig->max_depth; P.rr_threshold = ig->rr_threshold;
+  P.integrator = ig->kind;
+  P.direct_levels = std::max(1, ig->max_depth / 2);
   P.tile_size = ig->tile_size;
   // NewFilm (film.go:43-48)
   P.cx0 = (long long)ceil((double)film->width * film->crop[0]); P.cy0 = (long long)ceil((double)film->height * film->crop[1]);
@@ -612,7 +621,8 @@ static int render_impl(gopbrt_scene* sc, const gopbrt_camera* cam, const gopbrt_
   // ---- workspace
   // the stratified 1-D tables exist only in STRICT mode (FAST derives a sample's stratum from a hashed permutation)
   const size_t table_doubles = P.mode == GOPBRT_MODE_FAST ? 0 : (size_t)P.ndims * P.spp;
-  size_t per_lane = sizeof(RayRec) + sizeof(ShadowRec) + sizeof(PathRec) + 9 * 4 + table_doubles * 8 + (size_t)tpw * tph * 4 * 8;
+  const size_t frame_doubles = P.integrator == GOPBRT_INTEGRATOR_DIRECT_LIGHTING ? (size_t)P.direct_levels * 8 : 0;
+  size_t per_lane = sizeof(RayRec) + sizeof(ShadowRec) + sizeof(PathRec) + 9 * 4 + table_doubles * 8 + (size_t)tpw * tph * 4 * 8 + frame_doubles * 8;
   size_t free_b = 0, total_b = 0;
   GP_CUDA(ctx, cudaMemGetInfo(&free_b, &total_b));
   Workspace& W = sc->ws;
@@ -622,14 +632,15 @@ static int render_impl(gopbrt_scene* sc, const gopbrt_camera* cam, const gopbrt_
   long long lanes = std::max<long long>(1, std::min(lanes_total, cap));
   if (lanes > 0x7fffff00LL) lanes = 0x7fffff00LL;
   size_t bt = table_doubles * lanes, bp = (size_t)tpw * tph * 4 * lanes;
-  if (W.lanes != lanes || W.bytes_tables != bt || W.bytes_tilepix != bp) {
-    W.ray.release(); W.sray.release(); W.path.release(); W.i32.release(); W.tables.release(); W.tilepix.release();
+  if (W.lanes != lanes || W.bytes_tables != bt || W.bytes_tilepix != bp || W.frames.n != frame_doubles * (size_t)lanes) {
+    W.ray.release(); W.sray.release(); W.path.release(); W.i32.release(); W.tables.release(); W.tilepix.release(); W.frames.release();
     GP_CUDA(ctx, W.ray.alloc((size_t)lanes));
     GP_CUDA(ctx, W.sray.alloc((size_t)lanes));
     GP_CUDA(ctx, W.path.alloc((size_t)lanes));
     GP_CUDA(ctx, W.i32.alloc((size_t)9 * lanes));
     GP_CUDA(ctx, W.tables.alloc(std::max<size_t>(bt, 1)));
     GP_CUDA(ctx, W.tilepix.alloc(bp));
+    GP_CUDA(ctx, W.frames.alloc(frame_doubles * (size_t)lanes));
     if (!W.cnt.p) GP_CUDA(ctx, W.cnt.alloc(16));
     if (!W.rctr.p) GP_CUDA(ctx, W.rctr.alloc(1));
     if (!W.remaining_host) {
@@ -647,7 +658,7 @@ static int render_impl(gopbrt_scene* sc, const gopbrt_camera* cam, const gopbrt_
   memset(&Q, 0, sizeof(Q));
   Q.extend = ip; Q.extend_next = ip + lanes; Q.shadow = ip + 2 * lanes; Q.regen = ip + 3 * lanes; Q.regen_next = ip + 4 * lanes; Q.shade[0] = ip + 5 * lanes; Q.shade[1] = ip + 6 * lanes; Q.shade[2] = ip + 7 * lanes; Q.shade[3] = ip + 8 * lanes;
   Q.cnt = W.cnt.p;
-  L.tables = W.tables.p; L.tilepix = W.tilepix.p;
+  L.tables = W.tables.p; L.tilepix = W.tilepix.p; L.frames = W.frames.p;
   L.tile_stride = (long long)tpw * tph * 4;
 
   GP_CUDA(ctx, cudaMemsetAsync(W.rctr.p, 0, sizeof(RenderCounters), st));
@@ -657,7 +668,7 @@ static int render_impl(gopbrt_scene* sc, const gopbrt_camera* cam, const gopbrt_
   static int g_gen = 0, g_shade = 0;
   if (!g_gen) {
     g_gen = grid_for(ctx, (const void*)k_generate, 128);
-    g_shade = grid_for(ctx, (const void*)k_shade, 128);
+    g_shade = grid_for(ctx, (const void*)k_shade<0>, 128);
   }
   const size_t smem = sc->trace_smem;
   const int k_ext = count ? 1 : 0, k_any = count ? 3 : 2;
@@ -685,7 +696,7 @@ static int render_impl(gopbrt_scene* sc, const gopbrt_camera* cam, const gopbrt_
   uint64_t n_extend = 0, n_shadow = 0, tail_used = 0;
   // The tail kernel is bit-exact but, measured on config 2, slower than the wavefront it replaces (its lanes diverge
   // across stages inside a warp): it stays opt-in (GOPBRT_FLAG_TAIL), off by default.
-  const int tail_lanes = (opt && (opt->flags & GOPBRT_FLAG_TAIL)) ? 49152 : 0;
+  const int tail_lanes = (opt && (opt->flags & GOPBRT_FLAG_TAIL) && P.integrator == GOPBRT_INTEGRATOR_PATH) ? 49152 : 0;
   // debug aid: GOPBRT_ITER_LOG=<file> synchronises every iteration and logs the queue sizes (implies per-stage timing)
   const char* iter_log_path = getenv("GOPBRT_ITER_LOG");
   std::vector<int> iter_counts;
@@ -706,7 +717,8 @@ static int render_impl(gopbrt_scene* sc, const gopbrt_camera* cam, const gopbrt_
       auto enqueue_iteration = [&]() {
         sc->trace_k[k_ext]<<<sc->trace_grid[k_ext], kTraceThreads, smem, st>>>(sc->dev, L.ray, nullptr, L.path, nullptr, Q.extend, Q.cnt + 0, 0, scap, Q.cnt + 6, sc->tctr.p, nullptr);
         k_split_hits<<<g_small, 256, 0, st>>>(L, Q);
-        k_shade<<<g_shade, 128, 0, st>>>(sc->dev, L, P, Q, W.rctr.p);
+        if (P.integrator == 0) k_shade<0><<<g_shade, 128, 0, st>>>(sc->dev, L, P, Q, W.rctr.p);
+        else k_shade<1><<<g_shade, 128, 0, st>>>(sc->dev, L, P, Q, W.rctr.p);
         sc->trace_k[k_any]<<<sc->trace_grid[k_any], kTraceThreads, smem, st>>>(sc->dev, nullptr, L.sray, L.path, nullptr, Q.shadow, Q.cnt + 2, 0, scap, Q.cnt + 7, sc->tctr.p, &W.rctr.p->radiance_gt10);
         k_advance<<<1, 32, 0, st>>>(Q, W.rctr.p, W.remaining_dev);
         std::swap(Q.extend, Q.extend_next);
@@ -760,7 +772,8 @@ static int render_impl(gopbrt_scene* sc, const gopbrt_camera* cam, const gopbrt_
       sc->trace_k[k_ext]<<<sc->trace_grid[k_ext], kTraceThreads, smem, st>>>(sc->dev, L.ray, nullptr, L.path, nullptr, Q.extend, Q.cnt + 0, 0, scap, Q.cnt + 6, sc->tctr.p, nullptr);
       tick(ST_SHADE);
       k_split_hits<<<g_small, 256, 0, st>>>(L, Q);
-      k_shade<<<g_shade, 128, 0, st>>>(sc->dev, L, P, Q, W.rctr.p);
+      if (P.integrator == 0) k_shade<0><<<g_shade, 128, 0, st>>>(sc->dev, L, P, Q, W.rctr.p);
+      else k_shade<1><<<g_shade, 128, 0, st>>>(sc->dev, L, P, Q, W.rctr.p);
       tick(ST_SHADOW);
       sc->trace_k[k_any]<<<sc->trace_grid[k_any], kTraceThreads, smem, st>>>(sc->dev, nullptr, L.sray, L.path, nullptr, Q.shadow, Q.cnt + 2, 0, scap, Q.cnt + 7, sc->tctr.p, &W.rctr.p->radiance_gt10);
       tick(ST_RAYGEN);

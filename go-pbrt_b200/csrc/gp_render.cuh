@@ -23,6 +23,7 @@ struct Lanes {
   double* tables;   // [dim][k][lane] stratified 1-D tables
   double* tilepix;  // [lane][tile pixel][4] FilmTile accumulators (one contiguous record per lane)
   long long tile_stride;  // doubles per lane = tpw * tph * 4
+  double* frames;   // DirectLighting only: [lane][level][8] = {D.rgb, f.rgb, c, -} of the Li recursion (see shade_lane_direct)
 };
 
 struct RenderParams {
@@ -30,6 +31,8 @@ struct RenderParams {
   double lens_radius, focal_distance, shutter_open, shutter_close;
   int sampler_kind, xs, ys, jitter, ndims, mode, spp;
   int max_depth;
+  int integrator;                // 0 = Path, 1 = DirectLighting (UniformSampleOne)
+  int direct_levels;             // DirectLighting: frames per lane = max(1, maxDepth / 2)
   double rr_threshold;
   long long tile_size, ntx, nty, ntiles;
   long long cx0, cy0, cx1, cy1;  // CroppedPixelBounds
@@ -268,7 +271,7 @@ GP_D RGB tex_eval(const DevScene& sc, int id, const Hit& h) {
 
 // ---------------------------------------------------------------- BSDF (reflection.go)
 enum { BSDF_REFLECTION = 1, BSDF_TRANSMISSION = 2, BSDF_DIFFUSE = 4, BSDF_GLOSSY = 8, BSDF_SPECULAR = 16, BSDF_ALL = 31 };
-enum { BX_NONE = -1, BX_LAMBERT = 0, BX_OREN_NAYAR = 1, BX_SPEC_REFL_NOOP = 2, BX_FRESNEL_SPECULAR = 3 };
+enum { BX_NONE = -1, BX_LAMBERT = 0, BX_OREN_NAYAR = 1, BX_SPEC_REFL_NOOP = 2, BX_FRESNEL_SPECULAR = 3, BX_GLASS_SPLIT = 4 };
 // every material of the reference's working subset builds at most ONE BxDF (matte.go, mirror.go, glass.go:45-46)
 struct BSDF {
   V3 ns, ng, ss, ts;
@@ -390,7 +393,7 @@ GP_D void bsdf_sample_f(const BSDF& b, V3 woWorld, double ux, double uy, int typ
 }
 
 // Material.ComputeScatteringFunctions (matte.go:21-37, mirror.go:21-32, glass.go:27-75) + NewBSDF (reflection.go:128-140)
-GP_D bool compute_scattering(const DevScene& sc, int prim, const Hit& h, BSDF* b) {
+GP_D bool compute_scattering(const DevScene& sc, int prim, const Hit& h, BSDF* b, bool allowMultipleLobes = true) {
   int mi = sc.prims[prim].z;
   if (mi < 0) return false;  // primitive.go:73-75 panics
   const MaterialDev& m = sc.materials[mi];
@@ -426,6 +429,16 @@ GP_D bool compute_scattering(const DevScene& sc, int prim, const Hit& h, BSDF* b
     RGB R = clamp_rgb(tex_eval(sc, m.tex_a, h), 0, 1), T = clamp_rgb(tex_eval(sc, m.tex_b, h), 0, 1);
     if (is_black(R) && is_black(T)) return true;
     if (!(m.u_rough == 0 && m.v_rough == 0)) return false;  // microfacet branch: the reference panics
+    if (!allowMultipleLobes) {
+      // glass.go:57-72: SpecularReflection(R, FresnelDielectric) — typed Reflection|Diffuse (reflection.go:540),
+      // F = 0, Pdf = 0 — plus SpecularTransmission(T) typed Transmission|Specular.  `type` carries the reflection lobe
+      // (the only one a non-specular query can match); the transmission lobe is present iff T is not black (b->t).
+      b->kind = BX_GLASS_SPLIT;
+      b->type = is_black(R) ? 0 : (BSDF_REFLECTION | BSDF_DIFFUSE);
+      b->r = R; b->t = T; b->etaB = m.eta;
+      if (is_black(R)) b->kind = is_black(T) ? BX_NONE : BX_GLASS_SPLIT;
+      return true;
+    }
     b->kind = BX_FRESNEL_SPECULAR;
     b->type = BSDF_REFLECTION | BSDF_TRANSMISSION | BSDF_SPECULAR;
     b->r = R; b->t = T; b->etaB = m.eta;
@@ -582,6 +595,8 @@ GP_D void film_add_sample(const Lanes& L, const RenderParams& P, long long lane,
 // advances the sampler (StartNextSample / next pixel + StartPixel) and generates the next camera ray
 // (GenerateRayDifferential, camera.go:192-242; the differentials are dropped by Path.Li).  Returns false when the
 // lane's tile is exhausted.
+struct PathRec;
+GP_D RGB direct_unwind(const Lanes& L, const RenderParams& P, long long lane, const PathRec& pt);  // DirectLighting, defined below
 GP_D bool generate_lane(const DevScene& sc, const Lanes& L, const RenderParams& P, long long lane, bool have_sample,
                         unsigned long long& cam, unsigned long long& nans, unsigned long long& culled) {
   bool go = false;
@@ -589,7 +604,7 @@ GP_D bool generate_lane(const DevScene& sc, const Lanes& L, const RenderParams& 
   const int s_mod = P.s_world * P.groups, s_res = P.s_rank * P.groups + (int)((P.lane_base + lane) % P.groups);
   PathRec pt = L.path[lane];
   if (have_sample) {  // every lane of the regeneration queue carries a finished sample
-    RGB Lc = rgb(pt.Lr, pt.Lg, pt.Lb);
+    RGB Lc = P.integrator == 1 ? direct_unwind(L, P, lane, pt) : rgb(pt.Lr, pt.Lg, pt.Lb);
     if (is_nan(Lc.r) || is_nan(Lc.g) || is_nan(Lc.b)) { Lc = rgb(0.1, 0.1, 0.1); nans++; }  // integrator.go:256-257
     film_add_sample(L, P, lane, tile, pt.fx, pt.fy, Lc);
   }
@@ -924,9 +939,171 @@ GP_D void shade_lane(const DevScene& sc, const Lanes& L, const RenderParams& P, 
   L.path[lane] = pt;
 }
 
+// ---------------------------------------------------------------- DirectLighting (pkg/integrator/directlighting.go)
+// DirectLighting.Li (directlighting.go:62-104) is a recursion: L = direct(si) + SpecularReflect + SpecularTransmit, each
+// specular term being f * Li(child) * |wi.ns| / pdf (integrator.go:352-422) with the child entered two depth units down.
+// With the reference's BxDF typing the Reflection|Specular query never matches anything (SpecularReflection is typed
+// Reflection|Diffuse) and the Transmission|Specular query matches only smooth glass, so the recursion is a
+// CHAIN.  The wavefront walks it forwards, one level per iteration, and keeps per level the frame {D, f, c}: D = the
+// level's direct light (it arrives through the shadow stage, so it is filed when the next level starts or when the
+// sample retires), f and c = the specular term's factors.  The sample's radiance is the chain unwound backwards,
+// L_j = D_j + (f_j * L_{j+1}) * c_j — the very additions and multiplications of the recursion, in its order.
+// The ray differentials the reference threads through feed nothing these materials and textures read.
+constexpr int kDirectHitBit = 1 << 24;  // PathRec.bounces: the chain ended AT a hit (its D is still in pt.L at retire)
+
+GP_D void shade_lane_direct(const DevScene& sc, const Lanes& L, const RenderParams& P, long long lane, bool& cont, bool& finished, bool& shadow,
+                            unsigned long long& n_unsupported, unsigned long long& n_dead, int& bad) {
+  PathRec pt = L.path[lane];
+  RayRec rr = L.ray[lane];
+  int packed = pt.bounces;
+  const int level = packed & 255;  // frames filed so far == specular bounces taken; Li's depth argument is 2 * level
+  double* fr = L.frames + ((size_t)lane * P.direct_levels) * 8;
+  finished = true;
+  packed |= kDirectHitBit;
+  if (level > 0) {  // the previous level's direct light is complete now: file it, start this level's sum at zero
+    fr[(level - 1) * 8 + 0] = pt.Lr; fr[(level - 1) * 8 + 1] = pt.Lg; fr[(level - 1) * 8 + 2] = pt.Lb;
+    pt.Lr = 0; pt.Lg = 0; pt.Lb = 0;
+  }
+  Ray ray;
+  ray.o = mk3(rr.ox, rr.oy, rr.oz);
+  ray.d = mk3(rr.dx, rr.dy, rr.dz);
+  ray.tmax = rr.tmax;
+  Hit h;
+  int prim;
+  hit_record(sc, rr.hit_rec, ray, ray.tmax, &h, &prim, bad);
+  BSDF bsdf;
+  if (!compute_scattering(sc, prim, h, &bsdf, false)) {
+    n_unsupported++;
+  } else {
+    Smp s;
+    s.state = pt.rng_state; s.inc = pt.rng_inc; s.sidx = pt.sidx;
+    s.cur1 = (packed >> 8) & 255; s.cur2 = (packed >> 16) & 255; s.lane = lane;
+    unsigned long long fast_pixel = 0;
+    if (P.mode == 1) {
+      long long tile = ((P.lane_base + lane) / P.groups) * P.world + P.rank;
+      long long x0, y0, x1, y1;
+      tile_bounds(P, tile, &x0, &y0, &x1, &y1);
+      int pix = pt.pix;
+      long long px = x0 + pix % (x1 - x0), py = y0 + pix / (x1 - x0);
+      fast_pixel = (unsigned long long)((py - P.cy0) * (P.cx1 - P.cx0) + (px - P.cx0));
+    }
+    Intr ref; ref.p = h.p; ref.perr = h.perr; ref.n = h.n;
+    // --- L += UniformSampleOneLight(si, ...) (directlighting.go:85-90, integrator.go:48-77): unconditional here
+    if (sc.n_lights > 0) {
+      double u = get1d(s, L, P, fast_pixel);
+      int size = sc.n_lights + 1, first = 0, len = size;
+      while (len > 0) {  // Distribution1D.SampleDiscrete (sampling.go:42-55) via FindInterval (pkg/math/math.go:64-80)
+        int half = len >> 1, middle = first + half;
+        if (sc.light_cdf[middle] <= u) { first = middle + 1; len -= half + 1; }
+        else len = half;
+      }
+      int offset = (int)go_clamp((double)(first - 1), 0, (double)(size - 2));
+      double lightPdf = 0;
+      if (sc.light_func_int > 0) lightPdf = 1.0 / (sc.light_func_int / (double)sc.n_lights);
+      if (lightPdf != 0.0) {
+        double ulx, uly, usx, usy;
+        get2d(s, P, &ulx, &uly);
+        get2d(s, P, &usx, &usy);
+        const int flags = BSDF_ALL & ~BSDF_SPECULAR;  // EstimateDirect (integrator.go:79-195), specular = false
+        LightSample ls;
+        light_sample_li(sc, sc.lights[offset], ref, ulx, uly, &ls);
+        if (!ls.delta) n_dead++;
+        if (ls.pdf > 0 && !is_black(ls.Li)) {
+          RGB f = bsdf_f(bsdf, h.wo, ls.wi, flags);
+          f = f * fabs(dot(ls.wi, h.ns));
+          double scatteringPdf = bsdf_pdf(bsdf, h.wo, ls.wi, flags);
+          if (!is_black(f)) {
+            RGB Ld;
+            if (ls.delta) Ld = (f * ls.Li) / ls.pdf;
+            else {
+              double ff = 1.0 * ls.pdf, gg = 1.0 * scatteringPdf;  // PowerHeuristic (sampling.go:208-212)
+              double weight = (ff * ff) / (ff * ff + gg * gg);
+              Ld = ((f * ls.Li) * weight) / ls.pdf;
+            }
+            Ld = rgb(0, 0, 0) + Ld;
+            V3 origin = offset_ray_origin(ref.p, ref.perr, ref.n, ls.p1.p - ref.p);
+            V3 target = offset_ray_origin(ls.p1.p, ls.p1.perr, ls.p1.n, origin - ls.p1.p);
+            V3 d = target - origin;
+            ShadowRec sr;
+            sr.ox = ref.p.x; sr.oy = ref.p.y; sr.oz = ref.p.z; sr.dx = d.x; sr.dy = d.y; sr.dz = d.z;
+            sr.pr = Ld.r; sr.pg = Ld.g; sr.pb = Ld.b;   // L.AddAssign(Ld) on this level's zero sum
+            sr.gt10 = max_comp(Ld) > 10 ? 1 : 0;        // integrator.go:73-75 panics; counted when unoccluded
+            sr.pad = 1;                                 // an occluded segment contributes nothing at all (Li set to 0, :117-121)
+            sr.pad2[0] = 0; sr.pad2[1] = 0;
+            L.sray[lane] = sr;
+            shadow = true;
+          }
+        }
+      }
+    }
+    // --- specular recursion (directlighting.go:98-102): both terms draw their Get2D before anything else
+    if (2 * level + 1 < P.max_depth) {
+      double u1x, u1y, u2x, u2y;
+      get2d(s, P, &u1x, &u1y);  // SpecularReflect: BSDF.SampleF(wo, u, Reflection|Specular) matches no BxDF -> Spectrum(0)
+      get2d(s, P, &u2x, &u2y);  // SpecularTransmit: BSDF.SampleF(wo, u, Transmission|Specular)
+      if (bsdf.kind == BX_GLASS_SPLIT && !is_black(bsdf.t)) {
+        V3 wo = to_local(bsdf, h.wo);  // si.Wo (integrator.go:391), NOT the un-negated ray direction Path uses
+        if (wo.z != 0.0) {
+          // SpecularTransmission.SampleF (reflection.go:428-451), mode == Radiance; one matching component, so the
+          // remapped sample is unused and pdf stays 1
+          bool entering = wo.z > 0;
+          double etaI = entering ? 1.0 : bsdf.etaB, etaT = entering ? bsdf.etaB : 1.0;
+          V3 n = faceforward(mk3(0, 0, 1), wo);
+          double eta = etaI / etaT;
+          double cosThetaI = dot(n, wo);
+          double sin2ThetaI = go_max(0, 1 - cosThetaI * cosThetaI);
+          double sin2ThetaT = eta * eta * sin2ThetaI;
+          if (!(sin2ThetaT >= 1)) {
+            double cosThetaT = sqrt(1 - sin2ThetaT);
+            V3 wi = wo * -eta + n * (eta * cosThetaI - cosThetaT);
+            double F = fr_dielectric(wi.z, 1.0, bsdf.etaB);
+            RGB ft = bsdf.t * rgb(1.0 - F, 1.0 - F, 1.0 - F);
+            ft = ft * ((etaI * etaI) / (etaT * etaT));
+            RGB f = ft / fabs(wi.z);
+            const double pdf = 1;
+            double ad = fabs(dot(wi, h.ns));  // wi is BSDF-local, used as world
+            if (pdf > 0 && !is_black(f) && ad != 0.0) {
+              V3 o = offset_ray_origin(h.p, h.perr, h.n, wi);  // si.SpawnRay(wi)
+              RayRec nr;
+              nr.ox = o.x; nr.oy = o.y; nr.oz = o.z; nr.dx = wi.x; nr.dy = wi.y; nr.dz = wi.z;
+              nr.tmax = d_inf(); nr.hit_rec = -1; nr.pad = 0;
+              L.ray[lane] = nr;
+              fr[level * 8 + 3] = f.r; fr[level * 8 + 4] = f.g; fr[level * 8 + 5] = f.b; fr[level * 8 + 6] = ad / pdf;
+              cont = true;
+              finished = false;
+              packed = (packed & ~(255 | kDirectHitBit)) | (level + 1);
+            }
+          }
+        }
+      }
+    }
+    pt.rng_state = s.state; pt.rng_inc = s.inc;
+    packed = (packed & ~((255 << 8) | (255 << 16))) | (s.cur1 << 8) | (s.cur2 << 16);
+  }
+  pt.bounces = packed;
+  L.path[lane] = pt;
+}
+
+// the radiance of a finished DirectLighting sample: the chain of frames unwound (see shade_lane_direct)
+GP_D RGB direct_unwind(const Lanes& L, const RenderParams& P, long long lane, const PathRec& pt) {
+  const int level = pt.bounces & 255;
+  const bool at_hit = (pt.bounces & kDirectHitBit) != 0;
+  const double* fr = L.frames + ((size_t)lane * P.direct_levels) * 8;
+  // at a hit: pt.L is that level's own direct light.  Otherwise the last ray escaped: its Li is the sum of the lights'
+  // Le = 0, and pt.L is still the previous level's direct light.
+  RGB Ln = at_hit ? rgb(pt.Lr, pt.Lg, pt.Lb) : rgb(0, 0, 0);
+  for (int j = level - 1; j >= 0; j--) {
+    RGB D = (j == level - 1 && !at_hit) ? rgb(pt.Lr, pt.Lg, pt.Lb) : rgb(fr[j * 8], fr[j * 8 + 1], fr[j * 8 + 2]);
+    RGB f = rgb(fr[j * 8 + 3], fr[j * 8 + 4], fr[j * 8 + 5]);
+    Ln = D + (f * Ln) * fr[j * 8 + 6];  // L.AddAssign(f.Mul(s.Li(...)).MulScalar(wi.AbsDot(ns) / pdf))
+  }
+  return Ln;
+}
+
 // One Path.Li loop body per lane (path.go:40-155) after the closest-hit query: scattering functions, one light
 // sample (UniformSampleOneLight / EstimateDirect) whose visibility test is deferred to the shadow queue, BSDF
 // sampling, throughput update, SpawnRay, Russian roulette.
+template <int INTEG>
 __global__ void __launch_bounds__(128, 3) k_shade(DevScene sc, Lanes L, RenderParams P, Queues Q, RenderCounters* ctr) {
   // lanes whose ray hit something, binned by shade class: the kernel walks the four bins back to back, each starting on
   // a warp boundary, so that (almost) every warp shades one kind of hit
@@ -957,7 +1134,8 @@ __global__ void __launch_bounds__(128, 3) k_shade(DevScene sc, Lanes L, RenderPa
     long long lane = 0;
     if (valid) {
       lane = bin_q[bi];
-      shade_lane(sc, L, P, lane, cont, finished, shadow, n_unsupported, n_dead, bad);
+      if (INTEG == 0) shade_lane(sc, L, P, lane, cont, finished, shadow, n_unsupported, n_dead, bad);
+      else shade_lane_direct(sc, L, P, lane, cont, finished, shadow, n_unsupported, n_dead, bad);
     }
 #if GP_BLOCK_PUSH
     int* const qs[3] = {Q.shadow, Q.extend_next, Q.regen_next};

@@ -291,8 +291,8 @@ __global__ void __launch_bounds__(kTraceThreads, 4) k_trace(DevScene sc, RayRec*
         if (!hit_any) {
           pt->Lr += pr; pt->Lg += pg; pt->Lb += pb;
           if (sr->gt10) gt10++;
-        } else {  // blocked: Li = 0, so L += beta*0 (NaN only if beta is not finite)
-          pt->Lr += pr * 0.0; pt->Lg += pg * 0.0; pt->Lb += pb * 0.0;
+        } else if (!sr->pad) {  // Path, blocked: Li = 0, so L += beta*0 (NaN only if beta is not finite);
+          pt->Lr += pr * 0.0; pt->Lg += pg * 0.0; pt->Lb += pb * 0.0;  // DirectLighting (pad = 1) adds nothing at all
         }
       }
       has_ray = false;

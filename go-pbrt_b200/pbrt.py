@@ -637,6 +637,31 @@ class Path:  # path.go:10-26
 
 NewPath = Path
 
+UniformSampleAll, UniformSampleOne = 1, 2  # directlighting.go:12-15
+
+
+class DirectLighting:  # directlighting.go:17-36
+    """integrator.NewDirectLighting(strategy, maxDepth, camera, sampler, pixelBounds).  Preprocess (directlighting.go:46-60)
+    requests sample arrays on the prototype sampler only; the per-tile clones never see them (pixel.go:34-42), so nothing
+    of it reaches the hot path."""
+
+    def __init__(self, strategy, maxDepth, camera, sampler, pixelBounds=None):
+        if strategy not in (UniformSampleAll, UniformSampleOne):
+            raise ValueError("unknown lighting strategy (directlighting.go:92-94 panics)")
+        self.strategy, self.maxDepth, self.camera, self.sampler = strategy, maxDepth, camera, sampler
+
+    def GetCamera(self):
+        return self.camera
+
+    def GetSampler(self):
+        return self.sampler
+
+    def abi(self, tileSize):
+        return abi.Integrator(1, self.maxDepth, 0.0, self.strategy, 0, tileSize)
+
+
+NewDirectLighting = DirectLighting
+
 
 class Device:
     """gopbrt_ctx: one per process and GPU."""

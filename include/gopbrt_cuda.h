@@ -160,8 +160,14 @@ typedef struct {
   int32_t mode;
 } gopbrt_sampler;
 
-enum { GOPBRT_INTEGRATOR_PATH = 0 };
+enum {
+  GOPBRT_INTEGRATOR_PATH = 0,            /* integrator.Path (pkg/integrator/path.go:32-157)                              */
+  GOPBRT_INTEGRATOR_DIRECT_LIGHTING = 1  /* integrator.DirectLighting (pkg/integrator/directlighting.go:62-104)          */
+};
+/* light_strategy: Path -> the LightSampleStrategy of lightdistribution.go:5-9 (only Uniform = 1 is reachable);
+ * DirectLighting -> its LightStrategy (directlighting.go:12-15): 1 = UniformSampleAll, 2 = UniformSampleOne */
 enum { GOPBRT_LIGHTS_UNIFORM = 1 };
+enum { GOPBRT_DL_SAMPLE_ALL = 1, GOPBRT_DL_SAMPLE_ONE = 2 };
 
 /* integrator.NewPath(maxDepth, camera, sampler, pixelBounds, rrThreshold, strategy) (path.go:10-18) and
  * the tileSize argument of pbrt.Render (integrator.go:291). */

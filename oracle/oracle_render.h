@@ -238,7 +238,7 @@ static inline RGB tex_eval(const Scene& sc, int id, const Hit& h) {
 
 // ---------------------------------------------------------------- BSDF (reflection.go)
 enum { BSDF_REFLECTION = 1, BSDF_TRANSMISSION = 2, BSDF_DIFFUSE = 4, BSDF_GLOSSY = 8, BSDF_SPECULAR = 16, BSDF_ALL = 31 };
-enum { BX_LAMBERT = 0, BX_OREN_NAYAR = 1, BX_SPEC_REFL_NOOP = 2, BX_FRESNEL_SPECULAR = 3 };
+enum { BX_LAMBERT = 0, BX_OREN_NAYAR = 1, BX_SPEC_REFL_NOOP = 2, BX_FRESNEL_SPECULAR = 3, BX_SPEC_REFL_DIELECTRIC = 4, BX_SPEC_TRANS = 5 };
 struct BxDF { int kind, type; RGB r, t; double a = 0, b = 0, etaA = 1, etaB = 1; };
 struct BSDF {
   double eta = 1;
@@ -341,6 +341,34 @@ static inline void bxdf_sample_f(const BxDF& b, V3 wo, P2 u, RGB* f, V3* wi, dou
       *sampled = BSDF_SPECULAR | BSDF_TRANSMISSION;
       return;
     }
+    case BX_SPEC_REFL_DIELECTRIC: {  // SpecularReflection with FresnelDielectric (reflection.go:557-562, :398-403)
+      V3 w{-wo.x, -wo.y, wo.z};
+      *wi = w;
+      *pdf = 1.0;
+      *f = sdivs(smul(RGB(fr_dielectric(w.z, b.etaA, b.etaB)), b.r), std::fabs(w.z));
+      *sampled = 0;
+      return;
+    }
+    case BX_SPEC_TRANS: {  // SpecularTransmission.SampleF (reflection.go:428-451), mode == Radiance
+      bool entering = wo.z > 0;
+      double etaI = entering ? b.etaA : b.etaB, etaT = entering ? b.etaB : b.etaA;
+      V3 n = faceforward(V3{0, 0, 1}, wo);
+      double eta = etaI / etaT;
+      double cosThetaI = dot(n, wo);
+      double sin2ThetaI = gm::Max(0, 1 - cosThetaI * cosThetaI);
+      double sin2ThetaT = eta * eta * sin2ThetaI;
+      if (sin2ThetaT >= 1) { *f = RGB(0); *wi = V3{}; *pdf = 0; *sampled = 0; return; }
+      double cosThetaT = std::sqrt(1 - sin2ThetaT);
+      V3 w = add(muls(wo, -eta), muls(n, eta * cosThetaI - cosThetaT));
+      double F = fr_dielectric(w.z, b.etaA, b.etaB);
+      RGB ft = smul(b.t, RGB(1.0 - F));
+      ft = smuls(ft, (etaI * etaI) / (etaT * etaT));
+      *wi = w;
+      *f = sdivs(ft, std::fabs(w.z));
+      *pdf = 1;
+      *sampled = 0;  // sic (reflection.go:451)
+      return;
+    }
   }
 }
 
@@ -424,7 +452,7 @@ struct RenderStats {
 };
 
 // Material.ComputeScatteringFunctions (matte.go:21-37, mirror.go:21-32, glass.go:27-75) + NewBSDF (reflection.go:128-140)
-static inline bool compute_scattering(const Scene& sc, const Hit& h, BSDF* b, RenderStats* st) {
+static inline bool compute_scattering(const Scene& sc, const Hit& h, BSDF* b, RenderStats* st, bool allowMultipleLobes = true) {
   int mi = sc.prims[h.prim].material;
   if (mi < 0) { st->unsupported_material++; return false; }  // primitive.go:73-75 panics
   const gopbrt_material& m = sc.materials[mi];
@@ -471,11 +499,29 @@ static inline bool compute_scattering(const Scene& sc, const Hit& h, BSDF* b, Re
       if (sblack(R) && sblack(T)) return true;
       bool isSpecular = m.u_rough == 0 && m.v_rough == 0;
       if (!isSpecular) { st->unsupported_material++; return false; }  // microfacet branch panics in the reference
-      BxDF x;
-      x.kind = BX_FRESNEL_SPECULAR;
-      x.type = BSDF_REFLECTION | BSDF_TRANSMISSION | BSDF_SPECULAR;
-      x.r = R; x.t = T; x.etaA = 1.0; x.etaB = m.eta;
-      b->bx[b->n++] = x;
+      if (allowMultipleLobes) {
+        BxDF x;
+        x.kind = BX_FRESNEL_SPECULAR;
+        x.type = BSDF_REFLECTION | BSDF_TRANSMISSION | BSDF_SPECULAR;
+        x.r = R; x.t = T; x.etaA = 1.0; x.etaB = m.eta;
+        b->bx[b->n++] = x;
+        return true;
+      }
+      // glass.go:57-72: separate lobes.  SpecularReflection is typed Reflection|Diffuse (reflection.go:540)
+      if (!sblack(R)) {
+        BxDF x;
+        x.kind = BX_SPEC_REFL_DIELECTRIC;
+        x.type = BSDF_REFLECTION | BSDF_DIFFUSE;
+        x.r = R; x.etaA = 1.0; x.etaB = m.eta;
+        b->bx[b->n++] = x;
+      }
+      if (!sblack(T)) {
+        BxDF x;
+        x.kind = BX_SPEC_TRANS;
+        x.type = BSDF_TRANSMISSION | BSDF_SPECULAR;
+        x.t = T; x.etaA = 1.0; x.etaB = m.eta;
+        b->bx[b->n++] = x;
+      }
       return true;
     }
   }
@@ -696,6 +742,61 @@ static inline RGB path_li(const Scene& sc, Ray ray, Sampler& smp, const Integ& i
   return L;
 }
 
+// ---------------------------------------------------------------- DirectLighting (pkg/integrator/directlighting.go)
+// UniformSampleAllLights (integrator.go:23-46).  The sample arrays DirectLighting.Preprocess requests live on the
+// prototype sampler only: PixelSampler.clone / RandomSampler.Clone build a fresh Sampler (pixel.go:34-42, random.go:33-37),
+// so every worker's Get2DArray returns nil without consuming anything and each light takes the single-sample branch.
+static inline RGB uniform_sample_all_lights(const Scene& sc, const Hit& h, const BSDF& bsdf, Sampler& smp, RenderStats* st) {
+  RGB L(0);
+  for (size_t j = 0; j < sc.lights.size(); j++) {
+    P2 uLight = smp.get2d();
+    P2 uScattering = smp.get2d();
+    L = sadd(L, estimate_direct(sc, h, bsdf, uScattering, sc.lights[j], uLight, st));
+  }
+  return L;
+}
+struct DirectCfg { int maxDepth; int strategy; };  // strategy: 1 = UniformSampleAll, 2 = UniformSampleOne (directlighting.go:12-15)
+static inline RGB direct_li(const Scene& sc, Ray ray, Sampler& smp, const DirectCfg& cfg, int depth, RenderStats* st);
+// SamplerIntegratorSpecularReflect / SpecularTransmit (integrator.go:352-422); `type` = BSDF_REFLECTION or
+// BSDF_TRANSMISSION | BSDF_SPECULAR.  The ray differentials they propagate feed nothing Li reads (the textures of the
+// path ignore them), so they are not carried.  s.Li is entered with depth+1 on top of the depth+1 the caller passed.
+static inline RGB specular_bounce(const Scene& sc, const Hit& isect, const BSDF& bsdf, Sampler& smp, const DirectCfg& cfg, int type,
+                                  int depth, RenderStats* st) {
+  P2 u = smp.get2d();
+  RGB f; V3 wi; double pdf; int sampled;
+  bsdf_sample_f(bsdf, isect.wo, u, type, &f, &wi, &pdf, &sampled);
+  if (pdf > 0 && !sblack(f) && absdot(wi, isect.ns) != 0.0) {
+    Ray rd = spawn_ray(Intr{isect.p, isect.perr, isect.n}, wi, isect.time);  // wi is BSDF-local, used as world
+    return smuls(smul(f, direct_li(sc, rd, smp, cfg, depth + 1, st)), absdot(wi, isect.ns) / pdf);
+  }
+  return RGB(0);
+}
+// DirectLighting.Li (directlighting.go:62-104).  Light.Le and SurfaceInteraction.Le are identically zero.
+static inline RGB direct_li(const Scene& sc, Ray ray, Sampler& smp, const DirectCfg& cfg, int depth, RenderStats* st) {
+  RGB L(0);
+  Hit isect;
+  TravStats ts;
+  st->closest_rays++;
+  bool found = scene_intersect(sc, ray, &isect, &ts);
+  st->nodes += ts.nodes; st->prims += ts.prims;
+  if (!found) {
+    for (size_t i = 0; i < sc.lights.size(); i++) L = sadd(L, RGB(0));
+    return L;
+  }
+  BSDF bsdf;
+  if (!compute_scattering(sc, isect, &bsdf, st, false)) return L;  // the reference panics (nil material / microfacet glass)
+  L = sadd(L, RGB(0));  // si.Le(si.Wo)
+  if (!sc.lights.empty()) {
+    if (cfg.strategy == 1) L = sadd(L, uniform_sample_all_lights(sc, isect, bsdf, smp, st));
+    else L = sadd(L, uniform_sample_one_light(sc, isect, bsdf, smp, st));
+  }
+  if (depth + 1 < cfg.maxDepth) {
+    L = sadd(L, specular_bounce(sc, isect, bsdf, smp, cfg, BSDF_REFLECTION | BSDF_SPECULAR, depth + 1, st));
+    L = sadd(L, specular_bounce(sc, isect, bsdf, smp, cfg, BSDF_TRANSMISSION | BSDF_SPECULAR, depth + 1, st));
+  }
+  return L;
+}
+
 // ---------------------------------------------------------------- camera (camera.go:192-242)
 static inline Ray camera_ray(const gopbrt_camera& c, P2 pFilm, P2 pLens, double time) {
   Xf r2c, c2w;
@@ -805,6 +906,7 @@ static inline void render(const Scene& sc, const gopbrt_camera& cam, const gopbr
   RenderStats total;
   std::vector<std::vector<FilmTile>> done(std::max(1, opt.threads));
   Integ ig{icfg.max_depth, icfg.rr_threshold};
+  DirectCfg dcfg{icfg.max_depth, icfg.light_strategy};
   auto worker = [&](int tid) {
     RenderStats st;
     Sampler smp;
@@ -832,7 +934,7 @@ static inline void render(const Scene& sc, const gopbrt_camera& cam, const gopbr
             double time = smp.get1d();
             Ray ray = camera_ray(cam, pFilm, pLens, time);
             st.camera_rays++;
-            RGB L = path_li(sc, ray, smp, ig, &st);
+            RGB L = icfg.kind == GOPBRT_INTEGRATOR_DIRECT_LIGHTING ? direct_li(sc, ray, smp, dcfg, 0, &st) : path_li(sc, ray, smp, ig, &st);
             if (snan(L)) { L = RGB(0.1); st.nan_samples++; }  // integrator.go:256-257 (the Y() guards are dead)
             film_add_sample(fc, tile, pFilm, L, 1.0);
           }

@@ -31,6 +31,9 @@ def cases(gp):
     out["mixed_tile8"] = (sc, S.test_integrator(48, 32, spp=(3, 3), maxDepth=5), 8, gp.abi.MODE_STRICT)
     sc = S.mixed_test_scene(60, seed=21)
     out["mixed_fast"] = (sc, S.test_integrator(48, 32, spp=(3, 3), maxDepth=5), 1, gp.abi.MODE_FAST)
+    sc, ig = S.config2(W=48, H=27, spp=(3, 3))
+    dl = gp.pbrt.NewDirectLighting(gp.pbrt.UniformSampleOne, 5, ig.GetCamera(), ig.GetSampler(), None)
+    out["config2_direct_one"] = (sc, dl, 1, gp.abi.MODE_STRICT)
     return out
 
 

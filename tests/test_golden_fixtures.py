@@ -21,7 +21,7 @@ def golden():
     return np.load(os.path.join(HERE, "golden", "hotpath_golden.npz"))
 
 
-CASES = ["config1_tile16", "config1_tile1", "config2_tile1", "mixed_tile8", "mixed_fast"]
+CASES = ["config1_tile16", "config1_tile1", "config2_tile1", "mixed_tile8", "mixed_fast", "config2_direct_one"]
 
 
 @pytest.mark.parametrize("name", CASES)

@@ -331,3 +331,40 @@ def test_fast_mode_lane_groups_sum_to_single(gp, dev):
     film = integ.GetCamera().GetFilm().pixels
     assert np.array_equal(film[..., 3], single[..., 3]) and np.allclose(film, single, rtol=1e-12, atol=0)
     g.close()
+
+
+@pytest.mark.parametrize("maxDepth", [5, 4, 1])
+def test_direct_lighting_film_bit_exact(gp, dev, maxDepth):
+    # integrator.DirectLighting (directlighting.go:62-104), UniformSampleOne: the specular-transmission chain through the
+    # glass sphere of config 2 is a recursion in the reference and a chain of frames on the GPU — same additions and
+    # multiplications in the same order, so STRICT films are bit-identical
+    P = gp.pbrt
+    scene, integ = gp.scenes.config2(W=96, H=54, spp=(3, 3))
+    dl = P.NewDirectLighting(P.UniformSampleOne, maxDepth, integ.GetCamera(), integ.GetSampler(), None)
+    film, st, ofilm, ost = _render_both(gp, dev, scene, dl, 1)
+    _assert_film_equal(film, ofilm, st, ost, f"direct lighting maxDepth {maxDepth}")
+    if maxDepth > 1:
+        assert st["closest_rays"] > st["camera_rays"]  # the glass sphere was entered
+    else:
+        assert st["closest_rays"] == st["camera_rays"]
+
+
+def test_direct_lighting_mixed_scene_tiles_and_fast_mode(gp, dev):
+    P = gp.pbrt
+    scene = gp.scenes.mixed_test_scene(120, seed=13)
+    base = gp.scenes.test_integrator(96, 64, spp=(3, 3), maxDepth=5)
+    dl = P.NewDirectLighting(P.UniformSampleOne, 6, base.GetCamera(), base.GetSampler(), None)
+    film, st, ofilm, ost = _render_both(gp, dev, scene, dl, 8)
+    _assert_film_equal(film, ofilm, st, ost, "direct lighting mixed tile 8", exact=False)
+    film, st, ofilm, ost = _render_both(gp, dev, scene, dl, 1, mode=gp.abi.MODE_FAST)
+    _assert_film_equal(film, ofilm, st, ost, "direct lighting mixed fast", exact=False)
+
+
+def test_direct_lighting_sample_all_is_refused_not_faked(gp, dev):
+    P = gp.pbrt
+    scene, integ = gp.scenes.config2(W=32, H=18, spp=(2, 2))
+    dl = P.NewDirectLighting(P.UniformSampleAll, 5, integ.GetCamera(), integ.GetSampler(), None)
+    g = P.GpuScene(dev, scene)
+    with pytest.raises(RuntimeError):
+        P.Render(g, dl, 1)
+    g.close()
