@@ -69,6 +69,7 @@ struct Workspace {  // per-scene render workspace, kept between gopbrt_render ca
   DevBuf<PathRec> path;
   DevBuf<int> i32;        // queues
   DevBuf<double> tables, tilepix, frames;
+  DevBuf<unsigned char> occl;
   DevBuf<int> cnt;
   DevBuf<RenderCounters> rctr;
   int* remaining_host = nullptr;  // pinned, device-mapped
@@ -108,9 +109,10 @@ struct gopbrt_scene {
   DevBuf<TraceCounters> tctr;
   DevBuf<int> work;  // work counters of the persistent traversal warps (batched API)
   int stack_cap = 8;
-  // traversal kernels of this scene: [0] extend, [1] extend + counters, [2] shadow, [3] shadow + counters, [4] batched any-hit
-  trace_fn trace_k[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
-  int trace_grid[5] = {0, 0, 0, 0, 0};
+  // traversal kernels of this scene: [0] extend, [1] extend + counters, [2] shadow, [3] shadow + counters, [4] batched any-hit,
+  // [5] per-segment shadow (DirectLighting / UniformSampleAll), [6] the same + counters
+  trace_fn trace_k[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  int trace_grid[7] = {0, 0, 0, 0, 0, 0, 0};
   size_t trace_smem = 0;
   double world[6] = {0, 0, 0, 0, 0, 0};
   uint64_t bvh_nodes = 0, bvh_depth = 0;
@@ -412,7 +414,8 @@ extern "C" int gopbrt_scene_create(gopbrt_ctx* ctx, const gopbrt_scene_desc* d, 
   sc->trace_smem = (size_t)sc->stack_cap * kTraceThreads * 2 * sizeof(unsigned);  // two words (a, b) per stacked node
   sc->trace_k[0] = k_trace<0, false>; sc->trace_k[1] = k_trace<0, true>; sc->trace_k[2] = k_trace<2, false>;
   sc->trace_k[3] = k_trace<2, true>; sc->trace_k[4] = k_trace<1, false>;
-  for (int k = 0; k < 5; k++) {
+  sc->trace_k[5] = k_trace<3, false>; sc->trace_k[6] = k_trace<3, true>;
+  for (int k = 0; k < 7; k++) {
     if (sc->trace_smem > 48 * 1024)
       GP_CUDA(ctx, cudaFuncSetAttribute((const void*)sc->trace_k[k], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sc->trace_smem));
     sc->trace_grid[k] = grid_for(ctx, (const void*)sc->trace_k[k], kTraceThreads, sc->trace_smem);
@@ -556,8 +559,9 @@ static int render_impl(gopbrt_scene* sc, const gopbrt_camera* cam, const gopbrt_
   if (ig->kind == GOPBRT_INTEGRATOR_PATH) {
     if (ig->light_strategy != GOPBRT_LIGHTS_UNIFORM) return bad("Path: only the Uniform light strategy is supported");
   } else if (ig->kind == GOPBRT_INTEGRATOR_DIRECT_LIGHTING) {
-    if (ig->light_strategy != GOPBRT_DL_SAMPLE_ONE) {
-      ctx->last_error = "DirectLighting: only UniformSampleOne runs on the GPU (UniformSampleAll needs one shadow segment per light)";
+    if (ig->light_strategy != GOPBRT_DL_SAMPLE_ONE && ig->light_strategy != GOPBRT_DL_SAMPLE_ALL) return bad("DirectLighting: unknown lighting strategy");
+    if (ig->light_strategy == GOPBRT_DL_SAMPLE_ALL && sc->dev.n_lights > 31) {
+      ctx->last_error = "DirectLighting/UniformSampleAll: more than 31 lights (one shadow segment per light and lane)";
       return GOPBRT_ERR_UNSUPPORTED;
     }
     if (ig->max_depth > 250) return bad("DirectLighting: max_depth out of range");
@@ -585,6 +589,9 @@ static int render_impl(gopbrt_scene* sc, const gopbrt_camera* cam, const gopbrt_
   P.max_depth = ig->max_depth; P.rr_threshold = ig->rr_threshold;
   P.integrator = ig->kind;
   P.direct_levels = std::max(1, ig->max_depth / 2);
+  const bool direct_all = ig->kind == GOPBRT_INTEGRATOR_DIRECT_LIGHTING && ig->light_strategy == GOPBRT_DL_SAMPLE_ALL;
+  P.n_seg = direct_all ? std::max(1, sc->dev.n_lights) : 1;
+  P.direct_all = direct_all ? 1 : 0;
   P.tile_size = ig->tile_size;
   // NewFilm (film.go:43-48)
   P.cx0 = (long long)ceil((double)film->width * film->crop[0]); P.cy0 = (long long)ceil((double)film->height * film->crop[1]);
@@ -622,7 +629,8 @@ static int render_impl(gopbrt_scene* sc, const gopbrt_camera* cam, const gopbrt_
   // the stratified 1-D tables exist only in STRICT mode (FAST derives a sample's stratum from a hashed permutation)
   const size_t table_doubles = P.mode == GOPBRT_MODE_FAST ? 0 : (size_t)P.ndims * P.spp;
   const size_t frame_doubles = P.integrator == GOPBRT_INTEGRATOR_DIRECT_LIGHTING ? (size_t)P.direct_levels * 8 : 0;
-  size_t per_lane = sizeof(RayRec) + sizeof(ShadowRec) + sizeof(PathRec) + 9 * 4 + table_doubles * 8 + (size_t)tpw * tph * 4 * 8 + frame_doubles * 8;
+  const size_t n_seg = (size_t)P.n_seg;  // shadow segments (and shadow-queue entries) per lane
+  size_t per_lane = sizeof(RayRec) + n_seg * (sizeof(ShadowRec) + 1) + sizeof(PathRec) + (8 + n_seg) * 4 + table_doubles * 8 + (size_t)tpw * tph * 4 * 8 + frame_doubles * 8;
   size_t free_b = 0, total_b = 0;
   GP_CUDA(ctx, cudaMemGetInfo(&free_b, &total_b));
   Workspace& W = sc->ws;
@@ -630,14 +638,15 @@ static int render_impl(gopbrt_scene* sc, const gopbrt_camera* cam, const gopbrt_
   long long cap = (long long)(((double)(free_b + held) * 0.80) / (double)per_lane);
   if (opt && opt->max_lanes > 0) cap = std::min<long long>(cap, opt->max_lanes);
   long long lanes = std::max<long long>(1, std::min(lanes_total, cap));
-  if (lanes > 0x7fffff00LL) lanes = 0x7fffff00LL;
+  if (lanes * (long long)n_seg > 0x7fffff00LL) lanes = 0x7fffff00LL / (long long)n_seg;
   size_t bt = table_doubles * lanes, bp = (size_t)tpw * tph * 4 * lanes;
-  if (W.lanes != lanes || W.bytes_tables != bt || W.bytes_tilepix != bp || W.frames.n != frame_doubles * (size_t)lanes) {
-    W.ray.release(); W.sray.release(); W.path.release(); W.i32.release(); W.tables.release(); W.tilepix.release(); W.frames.release();
+  if (W.lanes != lanes || W.bytes_tables != bt || W.bytes_tilepix != bp || W.frames.n != frame_doubles * (size_t)lanes || W.sray.n != n_seg * (size_t)lanes) {
+    W.ray.release(); W.sray.release(); W.path.release(); W.i32.release(); W.tables.release(); W.tilepix.release(); W.frames.release(); W.occl.release();
     GP_CUDA(ctx, W.ray.alloc((size_t)lanes));
-    GP_CUDA(ctx, W.sray.alloc((size_t)lanes));
+    GP_CUDA(ctx, W.sray.alloc(n_seg * (size_t)lanes));
+    GP_CUDA(ctx, W.occl.alloc(direct_all ? n_seg * (size_t)lanes : 0));
     GP_CUDA(ctx, W.path.alloc((size_t)lanes));
-    GP_CUDA(ctx, W.i32.alloc((size_t)9 * lanes));
+    GP_CUDA(ctx, W.i32.alloc((8 + n_seg) * (size_t)lanes));
     GP_CUDA(ctx, W.tables.alloc(std::max<size_t>(bt, 1)));
     GP_CUDA(ctx, W.tilepix.alloc(bp));
     GP_CUDA(ctx, W.frames.alloc(frame_doubles * (size_t)lanes));
@@ -656,9 +665,10 @@ static int render_impl(gopbrt_scene* sc, const gopbrt_camera* cam, const gopbrt_
   int* ip = W.i32.p;
   Queues Q;
   memset(&Q, 0, sizeof(Q));
-  Q.extend = ip; Q.extend_next = ip + lanes; Q.shadow = ip + 2 * lanes; Q.regen = ip + 3 * lanes; Q.regen_next = ip + 4 * lanes; Q.shade[0] = ip + 5 * lanes; Q.shade[1] = ip + 6 * lanes; Q.shade[2] = ip + 7 * lanes; Q.shade[3] = ip + 8 * lanes;
+  Q.extend = ip; Q.extend_next = ip + lanes; Q.regen = ip + 2 * lanes; Q.regen_next = ip + 3 * lanes; Q.shade[0] = ip + 4 * lanes; Q.shade[1] = ip + 5 * lanes; Q.shade[2] = ip + 6 * lanes; Q.shade[3] = ip + 7 * lanes;
+  Q.shadow = ip + 8 * lanes;  // n_seg entries per lane
   Q.cnt = W.cnt.p;
-  L.tables = W.tables.p; L.tilepix = W.tilepix.p; L.frames = W.frames.p;
+  L.tables = W.tables.p; L.tilepix = W.tilepix.p; L.frames = W.frames.p; L.occl = W.occl.p;
   L.tile_stride = (long long)tpw * tph * 4;
 
   GP_CUDA(ctx, cudaMemsetAsync(W.rctr.p, 0, sizeof(RenderCounters), st));
@@ -671,7 +681,8 @@ static int render_impl(gopbrt_scene* sc, const gopbrt_camera* cam, const gopbrt_
     g_shade = grid_for(ctx, (const void*)k_shade<0>, 128);
   }
   const size_t smem = sc->trace_smem;
-  const int k_ext = count ? 1 : 0, k_any = count ? 3 : 2;
+  const int k_ext = count ? 1 : 0, k_any = direct_all ? (count ? 6 : 5) : (count ? 3 : 2);
+  const int shade_kind = P.integrator == GOPBRT_INTEGRATOR_PATH ? 0 : (direct_all ? 2 : 1);
   const int scap = sc->stack_cap;
   const int g_small = ctx->sm_count * 8;
   constexpr int kGraphIters = 8;
@@ -717,23 +728,24 @@ static int render_impl(gopbrt_scene* sc, const gopbrt_camera* cam, const gopbrt_
       auto enqueue_iteration = [&]() {
         sc->trace_k[k_ext]<<<sc->trace_grid[k_ext], kTraceThreads, smem, st>>>(sc->dev, L.ray, nullptr, L.path, nullptr, Q.extend, Q.cnt + 0, 0, scap, Q.cnt + 6, sc->tctr.p, nullptr);
         k_split_hits<<<g_small, 256, 0, st>>>(L, Q);
-        if (P.integrator == 0) k_shade<0><<<g_shade, 128, 0, st>>>(sc->dev, L, P, Q, W.rctr.p);
-        else k_shade<1><<<g_shade, 128, 0, st>>>(sc->dev, L, P, Q, W.rctr.p);
-        sc->trace_k[k_any]<<<sc->trace_grid[k_any], kTraceThreads, smem, st>>>(sc->dev, nullptr, L.sray, L.path, nullptr, Q.shadow, Q.cnt + 2, 0, scap, Q.cnt + 7, sc->tctr.p, &W.rctr.p->radiance_gt10);
+        if (shade_kind == 0) k_shade<0><<<g_shade, 128, 0, st>>>(sc->dev, L, P, Q, W.rctr.p);
+        else if (shade_kind == 1) k_shade<1><<<g_shade, 128, 0, st>>>(sc->dev, L, P, Q, W.rctr.p);
+        else k_shade<2><<<g_shade, 128, 0, st>>>(sc->dev, L, P, Q, W.rctr.p);
+        sc->trace_k[k_any]<<<sc->trace_grid[k_any], kTraceThreads, smem, st>>>(sc->dev, nullptr, L.sray, L.path, L.occl, Q.shadow, Q.cnt + 2, 0, scap, Q.cnt + 7, sc->tctr.p, &W.rctr.p->radiance_gt10);
         k_advance<<<1, 32, 0, st>>>(Q, W.rctr.p, W.remaining_dev);
         std::swap(Q.extend, Q.extend_next);
         std::swap(Q.regen, Q.regen_next);
         k_generate<<<g_gen, 128, 0, st>>>(sc->dev, L, P, Q, Q.regen, Q.cnt + 3, W.rctr.p);
       };
       // key: everything the captured launches were given by value
-      std::vector<unsigned char> key(sizeof(L) + sizeof(P) + sizeof(Q) + sizeof(sc->dev) + 8 * sizeof(int) + sizeof(size_t));
+      std::vector<unsigned char> key(sizeof(L) + sizeof(P) + sizeof(Q) + sizeof(sc->dev) + 9 * sizeof(int) + sizeof(size_t));
       {
         unsigned char* kp = key.data();
         memcpy(kp, &L, sizeof(L)); kp += sizeof(L);
         memcpy(kp, &P, sizeof(P)); kp += sizeof(P);
         memcpy(kp, &Q, sizeof(Q)); kp += sizeof(Q);
         memcpy(kp, &sc->dev, sizeof(sc->dev)); kp += sizeof(sc->dev);
-        int gk[8] = {sc->trace_grid[k_ext], sc->trace_grid[k_any], g_small, g_shade, g_gen, scap, k_ext, k_any};
+        int gk[9] = {sc->trace_grid[k_ext], sc->trace_grid[k_any], g_small, g_shade, g_gen, scap, k_ext, k_any, shade_kind};
         memcpy(kp, gk, sizeof(gk)); kp += sizeof(gk);
         memcpy(kp, &smem, sizeof(size_t));
       }
@@ -772,10 +784,11 @@ static int render_impl(gopbrt_scene* sc, const gopbrt_camera* cam, const gopbrt_
       sc->trace_k[k_ext]<<<sc->trace_grid[k_ext], kTraceThreads, smem, st>>>(sc->dev, L.ray, nullptr, L.path, nullptr, Q.extend, Q.cnt + 0, 0, scap, Q.cnt + 6, sc->tctr.p, nullptr);
       tick(ST_SHADE);
       k_split_hits<<<g_small, 256, 0, st>>>(L, Q);
-      if (P.integrator == 0) k_shade<0><<<g_shade, 128, 0, st>>>(sc->dev, L, P, Q, W.rctr.p);
-      else k_shade<1><<<g_shade, 128, 0, st>>>(sc->dev, L, P, Q, W.rctr.p);
+      if (shade_kind == 0) k_shade<0><<<g_shade, 128, 0, st>>>(sc->dev, L, P, Q, W.rctr.p);
+      else if (shade_kind == 1) k_shade<1><<<g_shade, 128, 0, st>>>(sc->dev, L, P, Q, W.rctr.p);
+      else k_shade<2><<<g_shade, 128, 0, st>>>(sc->dev, L, P, Q, W.rctr.p);
       tick(ST_SHADOW);
-      sc->trace_k[k_any]<<<sc->trace_grid[k_any], kTraceThreads, smem, st>>>(sc->dev, nullptr, L.sray, L.path, nullptr, Q.shadow, Q.cnt + 2, 0, scap, Q.cnt + 7, sc->tctr.p, &W.rctr.p->radiance_gt10);
+      sc->trace_k[k_any]<<<sc->trace_grid[k_any], kTraceThreads, smem, st>>>(sc->dev, nullptr, L.sray, L.path, L.occl, Q.shadow, Q.cnt + 2, 0, scap, Q.cnt + 7, sc->tctr.p, &W.rctr.p->radiance_gt10);
       tick(ST_RAYGEN);
       k_advance<<<1, 32, 0, st>>>(Q, W.rctr.p, W.remaining_dev);
       std::swap(Q.extend, Q.extend_next);

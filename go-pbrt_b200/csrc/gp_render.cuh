@@ -24,6 +24,7 @@ struct Lanes {
   double* tilepix;  // [lane][tile pixel][4] FilmTile accumulators (one contiguous record per lane)
   long long tile_stride;  // doubles per lane = tpw * tph * 4
   double* frames;   // DirectLighting only: [lane][level][8] = {D.rgb, f.rgb, c, -} of the Li recursion (see shade_lane_direct)
+  unsigned char* occl;  // DirectLighting / UniformSampleAll only: [lane][segment] visibility results of the shadow stage
 };
 
 struct RenderParams {
@@ -33,6 +34,8 @@ struct RenderParams {
   int max_depth;
   int integrator;                // 0 = Path, 1 = DirectLighting (UniformSampleOne)
   int direct_levels;             // DirectLighting: frames per lane = max(1, maxDepth / 2)
+  int n_seg;                     // shadow segments per lane: 1, or the number of lights for DirectLighting / UniformSampleAll
+  int direct_all;                // DirectLighting strategy is UniformSampleAll (segments are collected by the shade stage)
   double rr_threshold;
   long long tile_size, ntx, nty, ntiles;
   long long cx0, cy0, cx1, cy1;  // CroppedPixelBounds
@@ -681,6 +684,7 @@ GP_D bool generate_lane(const DevScene& sc, const Lanes& L, const RenderParams& 
     pt.br = 1.0; pt.bg = 1.0; pt.bb = 1.0;
     pt.eta_scale = 1.0;
     pt.bounces = (s.cur1 << 8) | (s.cur2 << 16);  // bounces in bits 0-7, sampler dimensions above
+    pt.has_sample = 0;  // DirectLighting / UniformSampleAll: no shadow segments pending
     go = true;
     break;
   }
@@ -951,10 +955,29 @@ GP_D void shade_lane(const DevScene& sc, const Lanes& L, const RenderParams& P, 
 // The ray differentials the reference threads through feed nothing these materials and textures read.
 constexpr int kDirectHitBit = 1 << 24;  // PathRec.bounces: the chain ended AT a hit (its D is still in pt.L at retire)
 
+// UniformSampleAll: the level's direct light is the sum over the lights, in light order, of the segments the shadow
+// stage found unoccluded (L.AddAssign(EstimateDirect(...)) per light, integrator.go:23-46); pt.has_sample holds the
+// mask of the segments that were emitted.  UniformSampleOne: the shadow stage has already added its single segment.
+GP_D void direct_collect(const Lanes& L, const RenderParams& P, long long lane, PathRec& pt) {
+  if (!P.direct_all) return;
+  unsigned mask = (unsigned)pt.has_sample;
+  for (int j = 0; j < P.n_seg; j++) {
+    if (!((mask >> j) & 1u)) continue;
+    size_t e = (size_t)lane * P.n_seg + j;
+    if (L.occl[e]) continue;
+    const ShadowRec* sr = L.sray + e;
+    pt.Lr += sr->pr; pt.Lg += sr->pg; pt.Lb += sr->pb;
+  }
+  pt.has_sample = 0;
+}
+
+// ALL = true: returns in seg_mask the segments (one per light) written to L.sray[lane * n_seg + j]
+template <bool ALL>
 GP_D void shade_lane_direct(const DevScene& sc, const Lanes& L, const RenderParams& P, long long lane, bool& cont, bool& finished, bool& shadow,
-                            unsigned long long& n_unsupported, unsigned long long& n_dead, int& bad) {
+                            unsigned& seg_mask, unsigned long long& n_unsupported, unsigned long long& n_dead, int& bad) {
   PathRec pt = L.path[lane];
   RayRec rr = L.ray[lane];
+  if (ALL) direct_collect(L, P, lane, pt);
   int packed = pt.bounces;
   const int level = packed & 255;  // frames filed so far == specular bounces taken; Li's depth argument is 2 * level
   double* fr = L.frames + ((size_t)lane * P.direct_levels) * 8;
@@ -988,19 +1011,27 @@ GP_D void shade_lane_direct(const DevScene& sc, const Lanes& L, const RenderPara
       fast_pixel = (unsigned long long)((py - P.cy0) * (P.cx1 - P.cx0) + (px - P.cx0));
     }
     Intr ref; ref.p = h.p; ref.perr = h.perr; ref.n = h.n;
-    // --- L += UniformSampleOneLight(si, ...) (directlighting.go:85-90, integrator.go:48-77): unconditional here
+    // --- direct light (directlighting.go:85-96): UniformSampleOneLight (integrator.go:48-77) or, ALL, every light once
+    //     (UniformSampleAllLights' single-sample branch, integrator.go:31-36: uLight then uScattering per light)
     if (sc.n_lights > 0) {
-      double u = get1d(s, L, P, fast_pixel);
-      int size = sc.n_lights + 1, first = 0, len = size;
-      while (len > 0) {  // Distribution1D.SampleDiscrete (sampling.go:42-55) via FindInterval (pkg/math/math.go:64-80)
-        int half = len >> 1, middle = first + half;
-        if (sc.light_cdf[middle] <= u) { first = middle + 1; len -= half + 1; }
-        else len = half;
+      int offset = 0;
+      bool sample = true;
+      if (!ALL) {
+        double u = get1d(s, L, P, fast_pixel);
+        int size = sc.n_lights + 1, first = 0, len = size;
+        while (len > 0) {  // Distribution1D.SampleDiscrete (sampling.go:42-55) via FindInterval (pkg/math/math.go:64-80)
+          int half = len >> 1, middle = first + half;
+          if (sc.light_cdf[middle] <= u) { first = middle + 1; len -= half + 1; }
+          else len = half;
+        }
+        offset = (int)go_clamp((double)(first - 1), 0, (double)(size - 2));
+        double lightPdf = 0;
+        if (sc.light_func_int > 0) lightPdf = 1.0 / (sc.light_func_int / (double)sc.n_lights);
+        sample = lightPdf != 0.0;
       }
-      int offset = (int)go_clamp((double)(first - 1), 0, (double)(size - 2));
-      double lightPdf = 0;
-      if (sc.light_func_int > 0) lightPdf = 1.0 / (sc.light_func_int / (double)sc.n_lights);
-      if (lightPdf != 0.0) {
+      const int n_loop = ALL ? sc.n_lights : 1;
+      for (int j = 0; j < n_loop && sample; j++) {
+        if (ALL) offset = j;
         double ulx, uly, usx, usy;
         get2d(s, P, &ulx, &uly);
         get2d(s, P, &usx, &usy);
@@ -1026,15 +1057,16 @@ GP_D void shade_lane_direct(const DevScene& sc, const Lanes& L, const RenderPara
             V3 d = target - origin;
             ShadowRec sr;
             sr.ox = ref.p.x; sr.oy = ref.p.y; sr.oz = ref.p.z; sr.dx = d.x; sr.dy = d.y; sr.dz = d.z;
-            sr.pr = Ld.r; sr.pg = Ld.g; sr.pb = Ld.b;   // L.AddAssign(Ld) on this level's zero sum
-            sr.gt10 = max_comp(Ld) > 10 ? 1 : 0;        // integrator.go:73-75 panics; counted when unoccluded
+            sr.pr = Ld.r; sr.pg = Ld.g; sr.pb = Ld.b;   // L.AddAssign(Ld) on this level's sum
+            sr.gt10 = (!ALL && max_comp(Ld) > 10) ? 1 : 0;  // integrator.go:73-75 (UniformSampleOneLight only) panics; counted when unoccluded
             sr.pad = 1;                                 // an occluded segment contributes nothing at all (Li set to 0, :117-121)
             sr.pad2[0] = 0; sr.pad2[1] = 0;
-            L.sray[lane] = sr;
-            shadow = true;
+            if (ALL) { L.sray[(size_t)lane * P.n_seg + j] = sr; seg_mask |= 1u << j; }
+            else { L.sray[lane] = sr; shadow = true; }
           }
         }
       }
+      if (ALL) pt.has_sample = (int)seg_mask;
     }
     // --- specular recursion (directlighting.go:98-102): both terms draw their Get2D before anything else
     if (2 * level + 1 < P.max_depth) {
@@ -1085,7 +1117,9 @@ GP_D void shade_lane_direct(const DevScene& sc, const Lanes& L, const RenderPara
 }
 
 // the radiance of a finished DirectLighting sample: the chain of frames unwound (see shade_lane_direct)
-GP_D RGB direct_unwind(const Lanes& L, const RenderParams& P, long long lane, const PathRec& pt) {
+GP_D RGB direct_unwind(const Lanes& L, const RenderParams& P, long long lane, const PathRec& pt_in) {
+  PathRec pt = pt_in;
+  direct_collect(L, P, lane, pt);
   const int level = pt.bounces & 255;
   const bool at_hit = (pt.bounces & kDirectHitBit) != 0;
   const double* fr = L.frames + ((size_t)lane * P.direct_levels) * 8;
@@ -1131,11 +1165,16 @@ __global__ void __launch_bounds__(128, 3) k_shade(DevScene sc, Lanes L, RenderPa
     else { bin_q = Q.shade[0]; bi = i; if (bi >= n0) bi = -1; }
     bool valid = i < n && bi >= 0;
     bool cont = false, finished = false, shadow = false;
+    unsigned seg_mask = 0;
     long long lane = 0;
     if (valid) {
       lane = bin_q[bi];
       if (INTEG == 0) shade_lane(sc, L, P, lane, cont, finished, shadow, n_unsupported, n_dead, bad);
-      else shade_lane_direct(sc, L, P, lane, cont, finished, shadow, n_unsupported, n_dead, bad);
+      else if (INTEG == 1) shade_lane_direct<false>(sc, L, P, lane, cont, finished, shadow, seg_mask, n_unsupported, n_dead, bad);
+      else shade_lane_direct<true>(sc, L, P, lane, cont, finished, shadow, seg_mask, n_unsupported, n_dead, bad);
+    }
+    if (INTEG == 2) {  // UniformSampleAll: one shadow-queue entry per emitted segment (entry = lane * n_seg + light)
+      for (int j = 0; j < P.n_seg; j++) queue_push(Q.shadow, Q.cnt + 2, (seg_mask >> j) & 1u, (int)(lane * P.n_seg + j));
     }
 #if GP_BLOCK_PUSH
     int* const qs[3] = {Q.shadow, Q.extend_next, Q.regen_next};

@@ -116,6 +116,8 @@ GP_D int quad_step(const DevScene& sc, unsigned& cur_a, unsigned& cur_b, bool& h
 // queue == nullptr: ray i is lane i (batched API); otherwise lane = queue[i] for i < *count.
 // dynamic shared memory: stack_cap * blockDim.x unsigned, [entry][thread] (bank-conflict free).
 // MODE 0: closest hit over RayRec.  MODE 1: any hit over RayRec, occluded[lane] = 1/0 (batched API).
+// MODE 3: any hit over ShadowRec segments (queue entries index srays and occluded directly), occluded[e] = 1/0:
+//         DirectLighting / UniformSampleAll, whose per-light segments are summed in light order by the shade stage.
 // MODE 2: any hit over the render's ShadowRec queue, resolved in place: an unoccluded segment adds its deferred light
 //         sample to the lane's radiance (L.AddAssign(Ld), path.go:86).
 template <int MODE, bool COUNT>
@@ -171,7 +173,7 @@ __global__ void __launch_bounds__(kTraceThreads, 4) k_trace(DevScene sc, RayRec*
         if (r < take) {
           long long i = w_next + r;
           lane = queue ? queue[i] : i;
-          if (MODE == 2) {
+          if (MODE >= 2) {
             const double2* q = (const double2*)(srays + lane);
             double2 a = q[0], b = q[1], c2 = q[2];
             ray.o = mk3(a.x, a.y, b.x);
@@ -282,7 +284,7 @@ __global__ void __launch_bounds__(kTraceThreads, 4) k_trace(DevScene sc, RayRec*
         out.x = ray.tmax;
         out.y = __longlong_as_double((long long)(((unsigned long long)(unsigned)rec_cls << 32) | (unsigned)rec));  // {hit_rec, shade class}
         ((double2*)(rays + lane))[3] = out;
-      } else if (MODE == 1) {
+      } else if (MODE == 1 || MODE == 3) {
         occluded[lane] = hit_any ? 1 : 0;
       } else {
         const ShadowRec* sr = srays + lane;

@@ -360,11 +360,20 @@ def test_direct_lighting_mixed_scene_tiles_and_fast_mode(gp, dev):
     _assert_film_equal(film, ofilm, st, ost, "direct lighting mixed fast", exact=False)
 
 
-def test_direct_lighting_sample_all_is_refused_not_faked(gp, dev):
+def test_direct_lighting_sample_all_film_bit_exact(gp, dev):
+    # UniformSampleAllLights (integrator.go:23-46): the cloned per-tile samplers carry no sample arrays (pixel.go:34-42),
+    # so it is one sample per light for every light — on the GPU one shadow segment per light, summed in light order
     P = gp.pbrt
-    scene, integ = gp.scenes.config2(W=32, H=18, spp=(2, 2))
+    scene = gp.scenes.mixed_test_scene(120, seed=13)
+    base = gp.scenes.test_integrator(96, 64, spp=(3, 3), maxDepth=5)
+    dl = P.NewDirectLighting(P.UniformSampleAll, 5, base.GetCamera(), base.GetSampler(), None)
+    assert len(scene.lights) > 1
+    film, st, ofilm, ost = _render_both(gp, dev, scene, dl, 8)
+    _assert_film_equal(film, ofilm, st, ost, "direct lighting sample-all mixed tile 8", exact=False)
+    assert st["shadow_rays"] > st["closest_rays"]  # several segments per hit
+    film, st, ofilm, ost = _render_both(gp, dev, scene, dl, 1, mode=gp.abi.MODE_FAST)
+    _assert_film_equal(film, ofilm, st, ost, "direct lighting sample-all mixed fast", exact=False)
+    scene, integ = gp.scenes.config2(W=96, H=54, spp=(3, 3))  # one light: a single segment per lane, same collection path
     dl = P.NewDirectLighting(P.UniformSampleAll, 5, integ.GetCamera(), integ.GetSampler(), None)
-    g = P.GpuScene(dev, scene)
-    with pytest.raises(RuntimeError):
-        P.Render(g, dl, 1)
-    g.close()
+    film, st, ofilm, ost = _render_both(gp, dev, scene, dl, 1)
+    _assert_film_equal(film, ofilm, st, ost, "direct lighting sample-all config2")
