@@ -70,6 +70,7 @@ struct Workspace {  // per-scene render workspace, kept between gopbrt_render ca
   DevBuf<int> i32;        // queues
   DevBuf<double> tables, tilepix, frames;
   DevBuf<unsigned char> occl;
+  DevBuf<unsigned char> codes;  // per extend-queue position: the hit's shade class or 4 = escaped (extend -> split)
   DevBuf<int> cnt;
   DevBuf<RenderCounters> rctr;
   int* remaining_host = nullptr;  // pinned, device-mapped
@@ -630,7 +631,7 @@ static int render_impl(gopbrt_scene* sc, const gopbrt_camera* cam, const gopbrt_
   const size_t table_doubles = P.mode == GOPBRT_MODE_FAST ? 0 : (size_t)P.ndims * P.spp;
   const size_t frame_doubles = P.integrator == GOPBRT_INTEGRATOR_DIRECT_LIGHTING ? (size_t)P.direct_levels * 8 : 0;
   const size_t n_seg = (size_t)P.n_seg;  // shadow segments (and shadow-queue entries) per lane
-  size_t per_lane = sizeof(RayRec) + n_seg * (sizeof(ShadowRec) + 1) + sizeof(PathRec) + (8 + n_seg) * 4 + table_doubles * 8 + (size_t)tpw * tph * 4 * 8 + frame_doubles * 8;
+  size_t per_lane = sizeof(RayRec) + n_seg * (sizeof(ShadowRec) + 1) + sizeof(PathRec) + (8 + n_seg) * 4 + 1 + table_doubles * 8 + (size_t)tpw * tph * 4 * 8 + frame_doubles * 8;
   size_t free_b = 0, total_b = 0;
   GP_CUDA(ctx, cudaMemGetInfo(&free_b, &total_b));
   Workspace& W = sc->ws;
@@ -641,12 +642,13 @@ static int render_impl(gopbrt_scene* sc, const gopbrt_camera* cam, const gopbrt_
   if (lanes * (long long)n_seg > 0x7fffff00LL) lanes = 0x7fffff00LL / (long long)n_seg;
   size_t bt = table_doubles * lanes, bp = (size_t)tpw * tph * 4 * lanes;
   if (W.lanes != lanes || W.bytes_tables != bt || W.bytes_tilepix != bp || W.frames.n != frame_doubles * (size_t)lanes || W.sray.n != n_seg * (size_t)lanes) {
-    W.ray.release(); W.sray.release(); W.path.release(); W.i32.release(); W.tables.release(); W.tilepix.release(); W.frames.release(); W.occl.release();
+    W.ray.release(); W.sray.release(); W.path.release(); W.i32.release(); W.tables.release(); W.tilepix.release(); W.frames.release(); W.occl.release(); W.codes.release();
     GP_CUDA(ctx, W.ray.alloc((size_t)lanes));
     GP_CUDA(ctx, W.sray.alloc(n_seg * (size_t)lanes));
     GP_CUDA(ctx, W.occl.alloc(direct_all ? n_seg * (size_t)lanes : 0));
     GP_CUDA(ctx, W.path.alloc((size_t)lanes));
     GP_CUDA(ctx, W.i32.alloc((8 + n_seg) * (size_t)lanes));
+    GP_CUDA(ctx, W.codes.alloc((size_t)lanes));
     GP_CUDA(ctx, W.tables.alloc(std::max<size_t>(bt, 1)));
     GP_CUDA(ctx, W.tilepix.alloc(bp));
     GP_CUDA(ctx, W.frames.alloc(frame_doubles * (size_t)lanes));
@@ -726,8 +728,8 @@ static int render_impl(gopbrt_scene* sc, const gopbrt_camera* cam, const gopbrt_
     const bool use_graph = !timing && !iter_log_path && !count && tail_lanes == 0 && !getenv("GOPBRT_NO_GRAPH");
     if (use_graph) {
       auto enqueue_iteration = [&]() {
-        sc->trace_k[k_ext]<<<sc->trace_grid[k_ext], kTraceThreads, smem, st>>>(sc->dev, L.ray, nullptr, L.path, nullptr, Q.extend, Q.cnt + 0, 0, scap, Q.cnt + 6, sc->tctr.p, nullptr);
-        k_split_hits<<<g_small, 256, 0, st>>>(L, Q);
+        sc->trace_k[k_ext]<<<sc->trace_grid[k_ext], kTraceThreads, smem, st>>>(sc->dev, L.ray, nullptr, L.path, W.codes.p, Q.extend, Q.cnt + 0, 0, scap, Q.cnt + 6, sc->tctr.p, nullptr);
+        k_split_hits<<<g_small, 256, 0, st>>>(L, Q, W.codes.p);
         if (shade_kind == 0) k_shade<0><<<g_shade, 128, 0, st>>>(sc->dev, L, P, Q, W.rctr.p);
         else if (shade_kind == 1) k_shade<1><<<g_shade, 128, 0, st>>>(sc->dev, L, P, Q, W.rctr.p);
         else k_shade<2><<<g_shade, 128, 0, st>>>(sc->dev, L, P, Q, W.rctr.p);
@@ -781,9 +783,9 @@ static int render_impl(gopbrt_scene* sc, const gopbrt_camera* cam, const gopbrt_
         iter_counts.push_back(c[0]);
       }
       tick(ST_EXTEND);
-      sc->trace_k[k_ext]<<<sc->trace_grid[k_ext], kTraceThreads, smem, st>>>(sc->dev, L.ray, nullptr, L.path, nullptr, Q.extend, Q.cnt + 0, 0, scap, Q.cnt + 6, sc->tctr.p, nullptr);
+      sc->trace_k[k_ext]<<<sc->trace_grid[k_ext], kTraceThreads, smem, st>>>(sc->dev, L.ray, nullptr, L.path, W.codes.p, Q.extend, Q.cnt + 0, 0, scap, Q.cnt + 6, sc->tctr.p, nullptr);
       tick(ST_SHADE);
-      k_split_hits<<<g_small, 256, 0, st>>>(L, Q);
+      k_split_hits<<<g_small, 256, 0, st>>>(L, Q, W.codes.p);
       if (shade_kind == 0) k_shade<0><<<g_shade, 128, 0, st>>>(sc->dev, L, P, Q, W.rctr.p);
       else if (shade_kind == 1) k_shade<1><<<g_shade, 128, 0, st>>>(sc->dev, L, P, Q, W.rctr.p);
       else k_shade<2><<<g_shade, 128, 0, st>>>(sc->dev, L, P, Q, W.rctr.p);

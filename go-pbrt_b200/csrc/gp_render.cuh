@@ -703,9 +703,6 @@ GP_D bool generate_lane(const DevScene& sc, const Lanes& L, const RenderParams& 
 #ifndef GP_GEN_TILE_PREFETCH
 #define GP_GEN_TILE_PREFETCH 0
 #endif
-#ifndef GP_SPLIT_BLOCKAGG
-#define GP_SPLIT_BLOCKAGG 1
-#endif
 __global__ void __launch_bounds__(128, GP_GEN_MINBLOCKS) k_generate(DevScene sc, Lanes L, RenderParams P, Queues Q, const int* __restrict__ in_queue,
                                                   const int* __restrict__ in_count, RenderCounters* ctr) {
   long long n = in_queue ? (long long)*in_count : P.lanes_active;
@@ -749,10 +746,9 @@ __global__ void __launch_bounds__(128, GP_GEN_MINBLOCKS) k_generate(DevScene sc,
 // A ray that escaped the scene ends its path (path.go:66): its lane goes straight to the regeneration queue; only real
 // hits reach the shade stage.  Order-preserving warp-ballot compaction (the queue order is roughly pixel order, which
 // keeps the rays of a warp coherent in the next extend).
-__global__ void __launch_bounds__(256) k_split_hits(Lanes L, Queues Q) {
+__global__ void __launch_bounds__(256) k_split_hits(Lanes L, Queues Q, const unsigned char* __restrict__ codes) {
   long long n = Q.cnt[0];
   int lane_id = threadIdx.x & 31;
-#if GP_SPLIT_BLOCKAGG
   // one atomicAdd per CTA and output queue instead of one per warp: the five counters are single addresses, and at
   // several million lanes per launch the per-warp atomics on them serialise
   __shared__ int s_cnt[8][5];
@@ -764,8 +760,11 @@ __global__ void __launch_bounds__(256) k_split_hits(Lanes L, Queues Q) {
     int lane = 0, rec = -1, cls = 0;
     if (valid) {
       lane = Q.extend[i];
-      int2 rc = *(const int2*)&L.ray[lane].hit_rec;  // {hit_rec, shade class}
-      rec = rc.x; cls = rc.y;
+      if (codes) { int c = codes[i]; rec = c < 4 ? 0 : -1; cls = c; }  // filed by the extend kernel under the queue position
+      else {
+        int2 rc = *(const int2*)&L.ray[lane].hit_rec;  // {hit_rec, shade class}
+        rec = rc.x; cls = rc.y;
+      }
     }
     int bin = !valid ? -1 : (rec >= 0 ? cls : 4);
     unsigned m[5];
@@ -788,23 +787,6 @@ __global__ void __launch_bounds__(256) k_split_hits(Lanes L, Queues Q) {
     }
     __syncthreads();
   }
-#else
-  long long warp_base0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) - lane_id;
-  for (long long base = warp_base0; base < n; base += (long long)gridDim.x * blockDim.x) {
-    long long i = base + lane_id;
-    bool valid = i < n;
-    int lane = 0, rec = -1, cls = 0;
-    if (valid) {
-      lane = Q.extend[i];
-      int2 rc = *(const int2*)&L.ray[lane].hit_rec;  // {hit_rec, shade class}
-      rec = rc.x; cls = rc.y;
-    }
-    bool hit = valid && rec >= 0;
-#pragma unroll
-    for (int k = 0; k < 4; k++) queue_push(Q.shade[k], Q.cnt + 8 + k, hit && cls == k, lane);
-    queue_push(Q.regen_next, Q.cnt + 4, valid && rec < 0, lane);
-  }
-#endif
 }
 
 // ---------------------------------------------------------------- shade

@@ -141,6 +141,7 @@ __global__ void __launch_bounds__(kTraceThreads, 4) k_trace(DevScene sc, RayRec*
 
   bool has_ray = false;
   long long lane = 0;
+  int qpos = 0;  // the ray's position in the queue (MODE 0: the hit code is filed under it for k_split_hits)
   Ray ray;
   V3 invd;
   int nx = 0, ny = 0, nz = 0, sp = 0, rec = -1, pending = -1, rec_cls = 0;
@@ -173,6 +174,7 @@ __global__ void __launch_bounds__(kTraceThreads, 4) k_trace(DevScene sc, RayRec*
         if (r < take) {
           long long i = w_next + r;
           lane = queue ? queue[i] : i;
+          qpos = (int)i;
           if (MODE >= 2) {
             const double2* q = (const double2*)(srays + lane);
             double2 a = q[0], b = q[1], c2 = q[2];
@@ -284,6 +286,9 @@ __global__ void __launch_bounds__(kTraceThreads, 4) k_trace(DevScene sc, RayRec*
         out.x = ray.tmax;
         out.y = __longlong_as_double((long long)(((unsigned long long)(unsigned)rec_cls << 32) | (unsigned)rec));  // {hit_rec, shade class}
         ((double2*)(rays + lane))[3] = out;
+        // MODE 0 with `occluded` set: one byte per QUEUE POSITION — shade class 0..3 of the hit, 4 = escaped — so that
+        // the split stage streams over the queue and never touches the ray records
+        if (occluded) occluded[qpos] = rec >= 0 ? (unsigned char)rec_cls : (unsigned char)4;
       } else if (MODE == 1 || MODE == 3) {
         occluded[lane] = hit_any ? 1 : 0;
       } else {
