@@ -54,9 +54,12 @@ GP_D unsigned long long warp_sum(unsigned long long v) {
 }
 
 constexpr int kChunkMax = 256;     // most ray indices a warp claims with one atomicAdd (fewer when the queue is short)
-constexpr int kRefillIdle = 8;     // idle lanes that trigger a refill from the warp's chunk
+#ifndef GP_REFILL_IDLE
+#define GP_REFILL_IDLE 16
+#endif
+constexpr int kRefillIdle = GP_REFILL_IDLE;     // idle lanes that trigger a refill from the warp's chunk
 #ifndef GP_DESCEND_STEPS
-#define GP_DESCEND_STEPS 8
+#define GP_DESCEND_STEPS 16
 #endif
 constexpr int kDescendSteps = GP_DESCEND_STEPS;
 constexpr int kQuadricBatch = 8;   // parked sphere/disk tests that trigger their batched execution
