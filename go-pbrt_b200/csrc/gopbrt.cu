@@ -602,10 +602,13 @@ static int render_impl(gopbrt_scene* sc, const gopbrt_camera* cam, const gopbrt_
   P.ntx = (fw + P.tile_size - 1) / P.tile_size; P.nty = (fh + P.tile_size - 1) / P.tile_size;  // integrator.go:297-299
   P.ntiles = P.ntx * P.nty;
   P.frx = film->filter_radius[0]; P.fry = film->filter_radius[1];
-  // extent of a tile's pixel bounds (GetFilmTile, film.go:106-113): [ceil(x0 - 0.5 - r), floor(x1 - 0.5 + r) + 1) with x1 - x0 <= tileSize
-  // and integer x0, so the widest tile needs exactly this many columns / rows
-  long long tpw = std::min<long long>(fw, (long long)floor((double)P.tile_size - 0.5 + P.frx) + 1 - (long long)ceil(-0.5 - P.frx));
-  long long tph = std::min<long long>(fh, (long long)floor((double)P.tile_size - 0.5 + P.fry) + 1 - (long long)ceil(-0.5 - P.fry));
+  // Columns / rows of a tile's pixel bounds (GetFilmTile, film.go:106-113: [ceil(x0 - 0.5 - r), floor(x1 - 0.5 + r) + 1), x0
+  // integer, x1 - x0 <= tileSize) that AddSample can actually touch: samples lie strictly below x1, so the last pixel a
+  // sample reaches is ceil(x1 - 0.5 + r) - 1 — one short of the bound when x1 - 0.5 + r is an integer (box filter r = 0.5).
+  // The untouched last column / row stays zero in the reference's tile and adds exactly nothing in MergeFilmTile, so it is
+  // not stored: tileSize 1 with the box filter needs 2 x 2 pixels = one 128-byte line per lane.
+  long long tpw = std::min<long long>(fw, (long long)ceil((double)P.tile_size - 0.5 + P.frx) - (long long)ceil(-0.5 - P.frx));
+  long long tph = std::min<long long>(fh, (long long)ceil((double)P.tile_size - 0.5 + P.fry) - (long long)ceil(-0.5 - P.fry));
   P.tpw = (int)tpw; P.tph = (int)tph;
   if (P.mode == GOPBRT_MODE_STRICT) { P.rank = rank; P.world = world; P.s_rank = 0; P.s_world = 1; }
   else { P.rank = 0; P.world = 1; P.s_rank = rank; P.s_world = world; }

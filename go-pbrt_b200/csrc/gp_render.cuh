@@ -1277,6 +1277,7 @@ __global__ void k_film_merge(Lanes L, RenderParams P, double* __restrict__ film)
         tile_bounds(P, tile, &x0, &y0, &x1, &y1);
         tile_pixel_bounds(P, x0, y0, x1, y1, &bx0, &by0, &bx1, &by1);
         if (x < bx0 || x >= bx1 || y < by0 || y >= by1) continue;
+        if (x - bx0 >= P.tpw || y - by0 >= P.tph) continue;  // the bound's last column / row: never touched by a sample, not stored
         size_t k = (size_t)((y - by0) * P.tpw + (x - bx0)) * 4;
         for (int grp = 0; grp < P.groups; grp++) {  // the tile's lane groups in ascending order (one group in STRICT mode)
           long long lane = (tile / P.world) * P.groups + grp - P.lane_base;

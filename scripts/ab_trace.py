@@ -8,7 +8,8 @@ P = gp.pbrt
 tag = sys.argv[1]
 dev = P.Device(0)
 for name in sys.argv[2:]:
-    scene, integ = getattr(gp.scenes, name)()
+    dims = {k: int(os.environ[e]) for k, e in (('W', 'AB_W'), ('H', 'AB_H')) if e in os.environ}
+    scene, integ = getattr(gp.scenes, name)(**dims)
     g = P.GpuScene(dev, scene)
     xf = int(os.environ.get("AB_FLAGS", "0"))
     kw = dict(mode=int(os.environ.get("AB_MODE", "0")), groups=int(os.environ.get("AB_GROUPS", "0")))
@@ -22,6 +23,6 @@ for name in sys.argv[2:]:
     out = dict(tag=tag, trace=os.environ.get("GOPBRT_TRACE", "pool"), config=name, ms_plain=round(p0["ms_total"], 2), plain_iters=p0["iterations"], ms_total=round(t["ms_total"], 2),
                mrays=round((t["closest_rays"] + t["shadow_rays"]) / t["ms_total"] / 1e3, 1),
                stage={k[3:]: round(t[k], 2) for k in ("ms_raygen", "ms_extend", "ms_shade", "ms_shadow")},
-               iters=t["iterations"], lanes=t["lanes"], ms_tail=round(t.get("ms_tail", 0), 2), rays=t["closest_rays"] + t["shadow_rays"], ovf=t["stack_overflows"], film_sha=hashlib.sha1(film.tobytes()).hexdigest()[:12])
+               iters=t["iterations"], lanes=t["lanes"], ms_tail=round(t.get("ms_tail", 0), 2), paths=t["camera_rays"], rays=t["closest_rays"] + t["shadow_rays"], ovf=t["stack_overflows"], film_sha=hashlib.sha1(film.tobytes()).hexdigest()[:12])
     print(json.dumps(out), flush=True)
     g.close()
