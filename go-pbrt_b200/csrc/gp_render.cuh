@@ -698,7 +698,7 @@ GP_D bool generate_lane(const DevScene& sc, const Lanes& L, const RenderParams& 
 // (StartNextSample / next pixel + StartPixel) and generates the next camera ray (GenerateRayDifferential,
 // camera.go:192-242; the differentials are dropped by Path.Li).  Lanes whose tile is exhausted leave the wavefront.
 #ifndef GP_GEN_MINBLOCKS
-#define GP_GEN_MINBLOCKS 1
+#define GP_GEN_MINBLOCKS 4
 #endif
 #ifndef GP_GEN_TILE_PREFETCH
 #define GP_GEN_TILE_PREFETCH 0
