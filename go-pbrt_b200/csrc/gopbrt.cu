@@ -615,12 +615,12 @@ static int render_impl(gopbrt_scene* sc, const gopbrt_camera* cam, const gopbrt_
   // FAST mode: a pixel's samples are independent, so a tile can be worked on by several lanes at once ("lane groups",
   // each taking every groups-th sample of this rank's share).  That turns the long per-lane sample chains of a 64-spp
   // frame — hundreds of wavefront iterations whose tail runs nearly empty — into many short ones, paid for with lane
-  // state in HBM.  Bits 8..15 of the flags choose the group count; 0 = automatic (about 8 samples per lane).
+  // state in HBM.  Bits 8..15 of the flags choose the group count; 0 = automatic.
   P.groups = 1;
   if (P.mode == GOPBRT_MODE_FAST) {
     int want = (flags >> 8) & 0xff;
     int share = (P.spp - 1 + P.s_world - 1) / P.s_world;  // samples 1..spp-1 of every pixel, split over the ranks
-    if (want == 0) want = std::max(1, std::min(8, share / 8));
+    if (want == 0) want = std::max(1, std::min(8, (share + 3) / 4));  // about 4-8 samples per lane
     P.groups = std::max(1, std::min(want, std::max(1, share)));
   }
   long long lanes_total = ((P.ntiles - P.rank + P.world - 1) / P.world) * P.groups;

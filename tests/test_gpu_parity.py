@@ -123,7 +123,7 @@ def _render_both(gp, dev, scene, integ, tile, accel=1, **kw):
     st = gp.pbrt.Render(g, integ, tile, **kw)
     film = integ.GetCamera().GetFilm().pixels.copy()
     s = OracleScene(scene, accel)
-    ofilm, ost = s.render(integ, tile, mode=kw.get("mode", 0))
+    ofilm, ost = s.render(integ, tile, mode=kw.get("mode", 0))  # one lane per tile: FAST callers pass groups=1 for bit parity
     assert st["efloat_panics"] == 0 and st["stack_overflows"] == 0
     g.close(); s.close()
     return film, st, ofilm, ost
@@ -188,7 +188,7 @@ def test_config2_cornell_film_bit_exact(gp, dev):
 def test_fast_mode_film_bit_exact_and_statistically_close_to_strict(gp, dev):
     scene = gp.scenes.mixed_test_scene(80, seed=5)
     integ = gp.scenes.test_integrator(96, 64, spp=(4, 4), maxDepth=5)
-    film, st, ofilm, ost = _render_both(gp, dev, scene, integ, 1, mode=gp.abi.MODE_FAST)
+    film, st, ofilm, ost = _render_both(gp, dev, scene, integ, 1, mode=gp.abi.MODE_FAST, groups=1)
     _assert_film_equal(film, ofilm, st, ost, "fast mode")
 
 
@@ -356,7 +356,7 @@ def test_direct_lighting_mixed_scene_tiles_and_fast_mode(gp, dev):
     dl = P.NewDirectLighting(P.UniformSampleOne, 6, base.GetCamera(), base.GetSampler(), None)
     film, st, ofilm, ost = _render_both(gp, dev, scene, dl, 8)
     _assert_film_equal(film, ofilm, st, ost, "direct lighting mixed tile 8", exact=False)
-    film, st, ofilm, ost = _render_both(gp, dev, scene, dl, 1, mode=gp.abi.MODE_FAST)
+    film, st, ofilm, ost = _render_both(gp, dev, scene, dl, 1, mode=gp.abi.MODE_FAST, groups=1)
     _assert_film_equal(film, ofilm, st, ost, "direct lighting mixed fast", exact=False)
 
 
@@ -371,7 +371,7 @@ def test_direct_lighting_sample_all_film_bit_exact(gp, dev):
     film, st, ofilm, ost = _render_both(gp, dev, scene, dl, 8)
     _assert_film_equal(film, ofilm, st, ost, "direct lighting sample-all mixed tile 8", exact=False)
     assert st["shadow_rays"] > st["closest_rays"]  # several segments per hit
-    film, st, ofilm, ost = _render_both(gp, dev, scene, dl, 1, mode=gp.abi.MODE_FAST)
+    film, st, ofilm, ost = _render_both(gp, dev, scene, dl, 1, mode=gp.abi.MODE_FAST, groups=1)
     _assert_film_equal(film, ofilm, st, ost, "direct lighting sample-all mixed fast", exact=False)
     scene, integ = gp.scenes.config2(W=96, H=54, spp=(3, 3))  # one light: a single segment per lane, same collection path
     dl = P.NewDirectLighting(P.UniformSampleAll, 5, integ.GetCamera(), integ.GetSampler(), None)
