@@ -644,7 +644,8 @@ static int render_impl(gopbrt_scene* sc, const gopbrt_camera* cam, const gopbrt_
   long long lanes = std::max<long long>(1, std::min(lanes_total, cap));
   if (lanes * (long long)n_seg > 0x7fffff00LL) lanes = 0x7fffff00LL / (long long)n_seg;
   size_t bt = table_doubles * lanes, bp = (size_t)tpw * tph * 4 * lanes;
-  if (W.lanes != lanes || W.bytes_tables != bt || W.bytes_tilepix != bp || W.frames.n != frame_doubles * (size_t)lanes || W.sray.n != n_seg * (size_t)lanes) {
+  if (W.lanes != lanes || W.bytes_tables != bt || W.bytes_tilepix != bp || W.frames.n != frame_doubles * (size_t)lanes || W.sray.n != n_seg * (size_t)lanes ||
+      W.occl.n != (direct_all ? n_seg * (size_t)lanes : 0) || W.codes.n != (size_t)lanes) {
     W.ray.release(); W.sray.release(); W.path.release(); W.i32.release(); W.tables.release(); W.tilepix.release(); W.frames.release(); W.occl.release(); W.codes.release();
     GP_CUDA(ctx, W.ray.alloc((size_t)lanes));
     GP_CUDA(ctx, W.sray.alloc(n_seg * (size_t)lanes));

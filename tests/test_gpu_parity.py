@@ -377,3 +377,27 @@ def test_direct_lighting_sample_all_film_bit_exact(gp, dev):
     dl = P.NewDirectLighting(P.UniformSampleAll, 5, integ.GetCamera(), integ.GetSampler(), None)
     film, st, ofilm, ost = _render_both(gp, dev, scene, dl, 1)
     _assert_film_equal(film, ofilm, st, ost, "direct lighting sample-all config2")
+
+
+def test_one_scene_many_render_shapes_reuses_the_workspace(gp, dev):
+    # the per-scene workspace is kept between gopbrt_render calls: integrators, strategies, modes and film sizes taken in
+    # turn on ONE scene handle must each still match a fresh handle bit for bit
+    P = gp.pbrt
+    scene, integ = gp.scenes.config2(W=48, H=27, spp=(3, 3))
+    cam, smp = integ.GetCamera(), integ.GetSampler()
+    variants = [("path", integ, dict()), ("one", P.NewDirectLighting(P.UniformSampleOne, 5, cam, smp, None), dict()),
+                ("all", P.NewDirectLighting(P.UniformSampleAll, 5, cam, smp, None), dict()),
+                ("path fast", integ, dict(mode=gp.abi.MODE_FAST, groups=2)),
+                ("all fast", P.NewDirectLighting(P.UniformSampleAll, 4, cam, smp, None), dict(mode=gp.abi.MODE_FAST)),
+                ("path again", integ, dict()), ("path tail", integ, dict(flags=gp.abi.FLAG_TAIL)),
+                ("path counted", integ, dict(flags=gp.abi.FLAG_COUNT_TRAVERSAL | gp.abi.FLAG_TIME_KERNELS))]
+    shared = P.GpuScene(dev, scene)
+    for name, ig, kw in variants:
+        P.Render(shared, ig, 1, **kw)
+        a = ig.GetCamera().GetFilm().pixels.copy()
+        fresh = P.GpuScene(dev, scene)
+        P.Render(fresh, ig, 1, **kw)
+        b = ig.GetCamera().GetFilm().pixels.copy()
+        fresh.close()
+        assert np.array_equal(a, b), name
+    shared.close()
