@@ -31,6 +31,10 @@ struct gopbrt_ctx {
   std::string last_error;
   std::atomic<uint64_t> launches{0};
   std::mutex mu;
+  // Every scene handle of a device context submits to ONE stream (and the render loop captures CUDA graphs on it), so
+  // device work of concurrent calls — each gRPC request of the reference renders on its own goroutine with its own scene,
+  // SURVEY §8b — is serialised per context; gopbrt_cancel stays lock-free.
+  std::mutex run_mu;
 };
 
 #define GP_CUDA(ctx, call)                                                                               \
@@ -206,6 +210,7 @@ extern "C" int gopbrt_scene_create(gopbrt_ctx* ctx, const gopbrt_scene_desc* d, 
   if (!ctx || !d || !out) return GOPBRT_ERR_INVALID;
   *out = nullptr;
   std::lock_guard<std::mutex> g(ctx->mu);
+  std::lock_guard<std::mutex> grun(ctx->run_mu);
   GP_CUDA(ctx, cudaSetDevice(ctx->device));
   auto bad = [&](const char* msg) { ctx->last_error = msg; return GOPBRT_ERR_INVALID; };
   if (d->n_primitives < 0 || d->n_primitives > 0x7fffffff) return bad("n_primitives out of range");
@@ -427,6 +432,7 @@ extern "C" int gopbrt_scene_create(gopbrt_ctx* ctx, const gopbrt_scene_desc* d, 
 
 extern "C" void gopbrt_scene_destroy(gopbrt_scene* sc) {
   if (!sc) return;
+  std::lock_guard<std::mutex> grun(sc->ctx->run_mu);
   cudaSetDevice(sc->ctx->device);
   cudaStreamSynchronize(sc->ctx->stream);
   delete sc;
@@ -475,12 +481,19 @@ static int trace_closest_soa_device(gopbrt_scene* sc, int64_t n, const double* r
 extern "C" int gopbrt_trace_closest_device(gopbrt_scene* sc, int64_t n, const double* rays_soa7, int32_t* prim, double* t, void* stream) {
   if (!sc || n < 0) return GOPBRT_ERR_INVALID;
   if (n == 0) return GOPBRT_OK;
+  std::lock_guard<std::mutex> grun(sc->ctx->run_mu);
   return trace_closest_soa_device(sc, n, rays_soa7, prim, nullptr, t, stream ? (cudaStream_t)stream : sc->ctx->stream);
 }
 
+static int trace_any_soa_device(gopbrt_scene* sc, int64_t n, const double* rays_soa7, uint8_t* hit, void* stream);
 extern "C" int gopbrt_trace_any_device(gopbrt_scene* sc, int64_t n, const double* rays_soa7, uint8_t* hit, void* stream) {
   if (!sc || n < 0) return GOPBRT_ERR_INVALID;
   if (n == 0) return GOPBRT_OK;
+  std::lock_guard<std::mutex> grun(sc->ctx->run_mu);
+  return trace_any_soa_device(sc, n, rays_soa7, hit, stream);
+}
+// callers hold the context's run_mu
+static int trace_any_soa_device(gopbrt_scene* sc, int64_t n, const double* rays_soa7, uint8_t* hit, void* stream) {
   gopbrt_ctx* ctx = sc->ctx;
   cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
   DevBuf<RayRec> recs;
@@ -504,6 +517,7 @@ extern "C" int gopbrt_trace_closest(gopbrt_scene* sc, int64_t n, const double* o
   if (n == 0) return GOPBRT_OK;
   gopbrt_ctx* ctx = sc->ctx;
   std::lock_guard<std::mutex> g(sc->mu);
+  std::lock_guard<std::mutex> grun(sc->ctx->run_mu);
   GP_CUDA(ctx, cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
   DevBuf<double> rays, tt, pp, nn;
@@ -537,6 +551,7 @@ extern "C" int gopbrt_trace_any(gopbrt_scene* sc, int64_t n, const double* ox, c
   if (n == 0) return GOPBRT_OK;
   gopbrt_ctx* ctx = sc->ctx;
   std::lock_guard<std::mutex> g(sc->mu);
+  std::lock_guard<std::mutex> grun(sc->ctx->run_mu);
   GP_CUDA(ctx, cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
   DevBuf<double> rays;
@@ -545,7 +560,7 @@ extern "C" int gopbrt_trace_any(gopbrt_scene* sc, int64_t n, const double* ox, c
   GP_CUDA(ctx, h.alloc(n));
   const double* src[7] = {ox, oy, oz, dx, dy, dz, tmax};
   for (int k = 0; k < 7; k++) GP_CUDA(ctx, cudaMemcpyAsync(rays.p + (size_t)k * n, src[k], n * sizeof(double), cudaMemcpyHostToDevice, st));
-  int rc = gopbrt_trace_any_device(sc, n, rays.p, h.p, st);
+  int rc = trace_any_soa_device(sc, n, rays.p, h.p, st);
   if (rc != GOPBRT_OK) return rc;
   GP_CUDA(ctx, cudaMemcpyAsync(hit, h.p, n, cudaMemcpyDeviceToHost, st));
   GP_CUDA(ctx, cudaStreamSynchronize(st));
@@ -894,6 +909,7 @@ extern "C" int gopbrt_render_device(gopbrt_scene* sc, const gopbrt_camera* cam, 
                                     const gopbrt_film* film, const gopbrt_render_options* opt, double* d_film, gopbrt_stats* stats) {
   if (!sc || !cam || !smp || !ig || !film || !d_film) return GOPBRT_ERR_INVALID;
   std::lock_guard<std::mutex> g(sc->mu);
+  std::lock_guard<std::mutex> grun(sc->ctx->run_mu);
   return render_impl(sc, cam, smp, ig, film, opt, d_film, stats);
 }
 
@@ -902,6 +918,7 @@ extern "C" int gopbrt_render(gopbrt_scene* sc, const gopbrt_camera* cam, const g
   if (!sc || !cam || !smp || !ig || !film || !film_out) return GOPBRT_ERR_INVALID;
   gopbrt_ctx* ctx = sc->ctx;
   std::lock_guard<std::mutex> g(sc->mu);
+  std::lock_guard<std::mutex> grun(sc->ctx->run_mu);
   GP_CUDA(ctx, cudaSetDevice(ctx->device));
   long long cx0 = (long long)ceil((double)film->width * film->crop[0]), cy0 = (long long)ceil((double)film->height * film->crop[1]);
   long long cx1 = (long long)ceil((double)film->width * film->crop[2]), cy1 = (long long)ceil((double)film->height * film->crop[3]);

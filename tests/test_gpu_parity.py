@@ -401,3 +401,34 @@ def test_one_scene_many_render_shapes_reuses_the_workspace(gp, dev):
         fresh.close()
         assert np.array_equal(a, b), name
     shared.close()
+
+
+def test_concurrent_renders_on_one_device_context(gp, dev):
+    # each gRPC request of the reference renders on its own goroutine with its own scene: two host threads,
+    # two scene handles, one device context — both films must equal their serial renders
+    import threading
+    P = gp.pbrt
+    jobs = []
+    for k, (W, H) in enumerate([(64, 40), (48, 27), (80, 45)]):
+        scene, integ = gp.scenes.config2(W=W, H=H, spp=(3, 3))
+        g = P.GpuScene(dev, scene)
+        P.Render(g, integ, 1)
+        jobs.append((g, integ, integ.GetCamera().GetFilm().pixels.copy()))
+    out, errs = [None] * len(jobs), []
+
+    def work(i):
+        try:
+            g, integ, _ = jobs[i]
+            for _ in range(3):
+                P.Render(g, integ, 1)
+            out[i] = integ.GetCamera().GetFilm().pixels.copy()
+        except Exception as e:  # noqa: BLE001
+            errs.append(e)
+
+    th = [threading.Thread(target=work, args=(i,)) for i in range(len(jobs))]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert not errs, errs
+    for i, (g, integ, ref) in enumerate(jobs):
+        assert np.array_equal(out[i], ref)
+        g.close()
