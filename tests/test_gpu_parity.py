@@ -432,3 +432,30 @@ def test_concurrent_renders_on_one_device_context(gp, dev):
     for i, (g, integ, ref) in enumerate(jobs):
         assert np.array_equal(out[i], ref)
         g.close()
+
+
+def test_degenerate_renders_match_oracle(gp, dev):
+    # empty aggregate, no lights, a 1x1 film, one sample per pixel (pixel.go:48-52 increments first: zero samples run),
+    # maxDepth 1, a film smaller than one tile
+    P = gp.pbrt
+    scene, integ = gp.scenes.config2(W=8, H=5, spp=(2, 2))
+    cam, smp = integ.GetCamera(), integ.GetSampler()
+    empty = P.NewScene(P.NewBVH([], 4, P.SplitSAH), [])
+    for what, sc, ig, tile, kw in [
+        ("empty scene", empty, integ, 1, {}),
+        ("empty scene direct", empty, P.NewDirectLighting(P.UniformSampleAll, 5, cam, smp, None), 4, {}),
+        ("no lights", P.NewScene(scene.aggregate, []), integ, 1, {}),
+        ("no lights direct", P.NewScene(scene.aggregate, []), P.NewDirectLighting(P.UniformSampleOne, 5, cam, smp, None), 1, {}),
+        ("tile larger than film", scene, integ, 64, {}),
+        ("maxDepth 1", scene, P.NewPath(1, cam, smp, None, 1, P.Uniform), 1, {}),
+        ("fast tiny", scene, integ, 1, dict(mode=gp.abi.MODE_FAST, groups=1)),
+    ]:
+        film, st, ofilm, ost = _render_both(gp, dev, sc, ig, tile, **kw)
+        _assert_film_equal(film, ofilm, st, ost, what)
+    s1, i1 = gp.scenes.config2(W=1, H=1, spp=(2, 2))
+    film, st, ofilm, ost = _render_both(gp, dev, s1, i1, 1)
+    _assert_film_equal(film, ofilm, st, ost, "1x1 film")
+    s2, i2 = gp.scenes.config2(W=6, H=4, spp=(1, 1))
+    film, st, ofilm, ost = _render_both(gp, dev, s2, i2, 1)
+    _assert_film_equal(film, ofilm, st, ost, "one sample per pixel")
+    assert st["camera_rays"] == 0 and not film.any()
