@@ -2,6 +2,11 @@
 // libgopbrt_cuda.so (include/gopbrt_cuda.h).  SOURCE ONLY: this image has no Go toolchain (SURVEY.md §0.1), so the file
 // is neither compiled nor tested here; the tested host is go-pbrt_b200/pbrt.py, which flattens scenes the same way.
 //
+// Integrator kinds: integ.kind = GOPBRT_INTEGRATOR_PATH (integrator.NewPath) or GOPBRT_INTEGRATOR_DIRECT_LIGHTING
+// (integrator.NewDirectLighting; light_strategy = GOPBRT_DL_SAMPLE_ALL / GOPBRT_DL_SAMPLE_ONE).  Sampler modes: STRICT reproduces
+// the reference's per-tile RNG streams; FAST (counter-based, needs the matching Go Sampler of INTEGRATION.md §3) splits a
+// pixel's samples across GPUs (opt.rank / opt.world) and across lane groups inside a GPU (opt.flags bits 8..15, 0 = automatic).
+//
 // It replaces two call sites of internal/render/server.go:
 //   agg := accelerator.NewBVH(primitives, 2, accelerator.SplitSAH); scene := pbrt.NewScene(agg, ls)   (:104,:132)
 //       -> scene, err := gopbrt.NewScene(dev, desc)

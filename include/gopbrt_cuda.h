@@ -35,6 +35,9 @@ enum {
 
 typedef struct gopbrt_ctx gopbrt_ctx;     /* one per process+device                         */
 typedef struct gopbrt_scene gopbrt_scene; /* immutable after create; shareable across threads */
+/* Threading: every entry point may be called from any host thread (each gRPC request of the reference renders on its own
+ * goroutine with its own scene, internal/render/server.go).  Device work of the scene handles of ONE gopbrt_ctx is
+ * serialised inside the library (one stream, CUDA-graph capture); gopbrt_cancel never blocks. */
 
 /* pbrt.Transform {Matrix, MatrixInverse} (pkg/pbrt/transform.go:144-146), row-major, passed
  * verbatim: the library never recomputes an inverse (the host's may be "wrong"). */
@@ -169,8 +172,9 @@ enum {
 enum { GOPBRT_LIGHTS_UNIFORM = 1 };
 enum { GOPBRT_DL_SAMPLE_ALL = 1, GOPBRT_DL_SAMPLE_ONE = 2 };
 
-/* integrator.NewPath(maxDepth, camera, sampler, pixelBounds, rrThreshold, strategy) (path.go:10-18) and
- * the tileSize argument of pbrt.Render (integrator.go:291). */
+/* integrator.NewPath(maxDepth, camera, sampler, pixelBounds, rrThreshold, strategy) (path.go:10-18) or
+ * integrator.NewDirectLighting(strategy, maxDepth, camera, sampler, pixelBounds) (directlighting.go:27-35; rr_threshold
+ * unused), and the tileSize argument of pbrt.Render (integrator.go:291). */
 typedef struct {
   int32_t kind;
   int32_t max_depth;
