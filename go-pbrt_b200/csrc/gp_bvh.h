@@ -10,11 +10,26 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
+#include <new>
 #include <thread>
 #include <vector>
 
+#ifdef GPBVH_TIMING
+#include <chrono>
+#include <cstdio>
+#endif
+
 namespace gpbvh {
+
+#ifdef GPBVH_TIMING
+#define GPBVH_TICK(label) do { auto now_ = std::chrono::steady_clock::now(); fprintf(stderr, "[gpbvh] %-22s %.3f s\n", label, std::chrono::duration<double>(now_ - tick_).count()); tick_ = now_; } while (0)
+#define GPBVH_TICK_INIT auto tick_ = std::chrono::steady_clock::now()
+#else
+#define GPBVH_TICK(label) do {} while (0)
+#define GPBVH_TICK_INIT do {} while (0)
+#endif
 
 struct Box { double mn[3], mx[3]; };
 struct Node32 { float mn[3]; uint32_t a; float mx[3]; uint32_t b; };  // the 32-byte device node
@@ -47,12 +62,13 @@ struct Builder {
   int max_prims = 4;
   int max_depth_seen = 0;
 
-  // builds [start,end) into `out`, returns the root index within `out`
-  int64_t build(std::vector<BNode>& out, int64_t start, int64_t end, int depth, int* maxd) {
-    int64_t me = (int64_t)out.size();
-    out.emplace_back();
+  // builds [start,end) into the node pool `out` from *used on (a range of n primitives never needs more than 2n - 1
+  // nodes), returns the root's index in the pool
+  int64_t build(BNode* out, int64_t* used, int64_t start, int64_t end, int depth, int* maxd) {
+    int64_t me = (*used)++;
+    new (&out[me]) BNode();
     if (depth > *maxd) *maxd = depth;
-    Box b, cb;
+    Box b;
     box_init(b);
     float cmn[3] = {INFINITY, INFINITY, INFINITY}, cmx[3] = {-INFINITY, -INFINITY, -INFINITY};
     for (int64_t i = start; i < end; i++) {
@@ -128,8 +144,8 @@ struct Builder {
                        [&](uint32_t a, uint32_t c) { return cen[3 * (size_t)a + best_axis] < cen[3 * (size_t)c + best_axis]; });
     }
     out[me].axis = best_axis;
-    int64_t l = build(out, start, mid, depth + 1, maxd);
-    int64_t r = build(out, mid, end, depth + 1, maxd);
+    int64_t l = build(out, used, start, mid, depth + 1, maxd);
+    int64_t r = build(out, used, mid, end, depth + 1, maxd);
     out[me].left = l;
     out[me].right = r;
     return me;
@@ -166,7 +182,7 @@ static Node32 empty_record() {
 // exactly the binary tree's near-first order.  The skipped middle boxes only ever culled what their children's boxes
 // cull too (a child box lies inside its parent's), so the set and order of visited leaves is unchanged.
 // Subtrees are laid out depth-first for locality.
-static void flatten_quads(const std::vector<BNode>& in, int64_t i, size_t slot, std::vector<Node32>& out) {
+static void flatten_quads(const BNode* in, int64_t i, size_t slot, std::vector<Node32>& out) {
   const BNode& n = in[i];
   Node32 rec = make_record(n);
   if (n.n == 0) {
@@ -186,16 +202,76 @@ static void flatten_quads(const std::vector<BNode>& in, int64_t i, size_t slot, 
     out[slot] = rec;
   }
 }
-static void flatten(const std::vector<BNode>& in, int64_t root, std::vector<Node32>& out) {
-  out.push_back(empty_record());  // [0] root record
-  for (int k = 0; k < 3; k++) out.push_back(empty_record());  // [1..3] padding: child groups start on 128-byte boundaries
-  flatten_quads(in, root, 0, out);
+// records flatten_quads appends for the subtree entered at node i (four per interior node reached at a slot)
+static size_t quad_records(const BNode* in, int64_t i) {
+  const BNode& n = in[i];
+  if (n.n != 0) return 0;
+  const BNode& L = in[n.left];
+  const BNode& R = in[n.right];
+  size_t c = 4;
+  if (L.n == 0) c += quad_records(in, L.left) + quad_records(in, L.right);
+  if (R.n == 0) c += quad_records(in, R.left) + quad_records(in, R.right);
+  return c;
+}
+// flatten_quads into a pre-sized array: `cursor` is where this subtree's next group goes.  Same layout, record for
+// record, as the appending version; subtrees below `fork_depth` slot levels are deferred to `tasks` (node, slot, first
+// group index) so that they can be written concurrently.
+struct QuadTask { int64_t node; size_t slot, cursor; };
+static void flatten_quads_at(const BNode* in, int64_t i, size_t slot, Node32* out, size_t& cursor, int fork_depth,
+                             std::vector<QuadTask>* tasks) {
+  const BNode& n = in[i];
+  if (n.n != 0) { out[slot] = make_record(n); return; }
+  if (tasks && fork_depth == 0) {
+    tasks->push_back({i, slot, cursor});
+    cursor += quad_records(in, i);
+    return;
+  }
+  Node32 rec = make_record(n);
+  size_t g = cursor;
+  cursor += 4;
+  for (int k = 0; k < 4; k++) out[g + k] = empty_record();
+  const BNode& L = in[n.left];
+  const BNode& R = in[n.right];
+  uint32_t le = L.n == 0, re = R.n == 0;
+  rec.a = (uint32_t)g;
+  rec.b = (uint32_t)n.axis | ((uint32_t)(le ? L.axis : 0) << 2) | ((uint32_t)(re ? R.axis : 0) << 4) | (le << 6) | (re << 7);
+  out[slot] = rec;
+  int fd = fork_depth > 0 ? fork_depth - 1 : 0;
+  if (le) { flatten_quads_at(in, L.left, g, out, cursor, fd, tasks); flatten_quads_at(in, L.right, g + 1, out, cursor, fd, tasks); }
+  else flatten_quads_at(in, n.left, g, out, cursor, fd, tasks);
+  if (re) { flatten_quads_at(in, R.left, g + 2, out, cursor, fd, tasks); flatten_quads_at(in, R.right, g + 3, out, cursor, fd, tasks); }
+  else flatten_quads_at(in, n.right, g + 2, out, cursor, fd, tasks);
+}
+static void flatten(const BNode* in, size_t n_nodes, int64_t root, std::vector<Node32>& out) {
+  size_t total = 4 + quad_records(in, root);
+  out.assign(total, empty_record());  // [0] root record, [1..3] padding: child groups start on 128-byte boundaries
+  size_t cursor = 4;
+  unsigned hw = std::thread::hardware_concurrency();
+  if (n_nodes < 200000 || hw < 2) {
+    flatten_quads_at(in, root, 0, out.data(), cursor, 0, nullptr);
+    return;
+  }
+  std::vector<QuadTask> tasks;
+  flatten_quads_at(in, root, 0, out.data(), cursor, 4, &tasks);  // top 4 slot levels (<= 256 subtrees) serially
+  std::vector<std::thread> th;
+  std::atomic<size_t> next{0};
+  for (unsigned t = 0; t < hw; t++)
+    th.emplace_back([&]() {
+      for (;;) {
+        size_t k = next.fetch_add(1);
+        if (k >= tasks.size()) break;
+        size_t c = tasks[k].cursor;
+        flatten_quads_at(in, tasks[k].node, tasks[k].slot, out.data(), c, 0, nullptr);
+      }
+    });
+  for (auto& t : th) t.join();
 }
 
 // Top of the tree serially until there are enough independent subtrees, then one host thread per subtree.
 static Result build_bvh(const Box* bounds, int64_t n, int max_prims) {
   Result res;
   if (n == 0) return res;
+  GPBVH_TICK_INIT;
   Builder B;
   B.bounds = bounds;
   B.max_prims = max_prims;
@@ -205,13 +281,27 @@ static Result build_bvh(const Box* bounds, int64_t n, int max_prims) {
     B.idx[i] = (uint32_t)i;
     for (int k = 0; k < 3; k++) B.cen[3 * (size_t)i + k] = (float)(0.5 * bounds[i].mn[k] + 0.5 * bounds[i].mx[k]);
   }
+  GPBVH_TICK("centroids");
   unsigned hw = std::thread::hardware_concurrency();
   if (hw == 0) hw = 4;
-  std::vector<BNode> nodes;
+  // One uninitialised node pool for the whole tree: a range of k primitives never needs more than 2k - 1 nodes, so the
+  // slab built by a thread owns pool[2 * first primitive ...) and writes absolute indices — nothing is copied or
+  // re-indexed afterwards.  The pool has gaps (only the pages that are written get touched); the flattened output
+  // follows the links, so its layout does not depend on where the nodes sit.
+  struct Pool {
+    BNode* p;
+    explicit Pool(size_t count) : p((BNode*)malloc(count * sizeof(BNode))) {}
+    ~Pool() { free(p); }
+  } pool(2 * (size_t)n + 512);
+  if (!pool.p) return res;
+  BNode* nodes = pool.p;
   int maxd = 0;
+  int64_t root = 0;
+  size_t n_nodes = 0;
   if (n < 200000 || hw < 2) {
-    nodes.reserve(2 * (size_t)n / std::max(1, max_prims) + 16);
-    B.build(nodes, 0, n, 0, &maxd);
+    int64_t used = 0;
+    root = B.build(nodes, &used, 0, n, 0, &maxd);
+    n_nodes = (size_t)used;
   } else {
     // split the index range into 2^k slabs by repeated median on the widest axis, build each slab on its own thread,
     // then join the slab roots under a small top tree
@@ -241,8 +331,9 @@ static Result build_bvh(const Box* bounds, int64_t n, int max_prims) {
       }
       for (auto& t : th) t.join();
     }
+    GPBVH_TICK("median top levels");
     size_t ns = lv[levels].size();
-    std::vector<std::vector<BNode>> sub(ns);
+    std::vector<int64_t> sub_root(ns), sub_used(ns);
     std::vector<int> subd(ns, 0);
     {
       std::vector<std::thread> th;
@@ -252,24 +343,18 @@ static Result build_bvh(const Box* bounds, int64_t n, int max_prims) {
           for (;;) {
             size_t r = next.fetch_add(1);
             if (r >= ns) break;
-            sub[r].reserve(2 * (size_t)(lv[levels][r].e - lv[levels][r].s) / std::max(1, max_prims) + 16);
-            B.build(sub[r], lv[levels][r].s, lv[levels][r].e, levels, &subd[r]);
+            int64_t used = 2 * lv[levels][r].s;  // this slab's region of the pool
+            int64_t first = used;
+            sub_root[r] = B.build(nodes, &used, lv[levels][r].s, lv[levels][r].e, levels, &subd[r]);
+            sub_used[r] = used - first;
           }
         });
       for (auto& t : th) t.join();
     }
-    // stitch: top tree nodes first (recursively), subtrees appended with index fix-up
-    std::vector<int64_t> sub_root(ns);
-    for (size_t r = 0; r < ns; r++) {
-      int64_t base = (int64_t)nodes.size();
-      sub_root[r] = base;
-      for (auto bn : sub[r]) {
-        if (bn.left >= 0) { bn.left += base; bn.right += base; }
-        nodes.push_back(bn);
-      }
-      std::vector<BNode>().swap(sub[r]);
-      if (subd[r] > maxd) maxd = subd[r];
-    }
+    GPBVH_TICK("subtree builds");
+    for (size_t r = 0; r < ns; r++) { n_nodes += (size_t)sub_used[r]; if (subd[r] > maxd) maxd = subd[r]; }
+    // the top tree over the slab roots lives behind the last slab's region
+    int64_t top = 2 * n;
     std::vector<int64_t> cur = sub_root;
     for (int l = levels - 1; l >= 0; l--) {
       std::vector<int64_t> up(lv[l].size());
@@ -280,20 +365,17 @@ static Result build_bvh(const Box* bounds, int64_t n, int max_prims) {
         bn.axis = lv[l][r].axis;
         bn.b = nodes[bn.left].b;
         box_add(bn.b, nodes[bn.right].b);
-        up[r] = (int64_t)nodes.size();
-        nodes.push_back(bn);
+        up[r] = top;
+        new (&nodes[top++]) BNode(bn);
+        n_nodes++;
       }
       cur = up;
     }
-    // move the root to a known place: flatten() takes the root index
-    res.nodes.reserve(nodes.size());
-    flatten(nodes, cur[0], res.nodes);
-    res.order = B.idx;
-    res.depth = maxd;
-    return res;
+    root = cur[0];
+    GPBVH_TICK("top tree");
   }
-  res.nodes.reserve(nodes.size());
-  flatten(nodes, 0, res.nodes);
+  flatten(nodes, n_nodes, root, res.nodes);
+  GPBVH_TICK("flatten");
   res.order = B.idx;
   res.depth = maxd;
   return res;
