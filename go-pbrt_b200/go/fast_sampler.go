@@ -1,8 +1,8 @@
 // FastStratified is the Go half of GOPBRT_MODE_FAST: a pbrt.Sampler whose every (pixel, sample) is an independent stream,
 // so that the GPU may split a pixel's samples across GPUs and lane groups (include/gopbrt_cuda.h) and the CPU renderer, run
 // with this sampler, draws the very same numbers.  SOURCE ONLY (no Go toolchain in this image, SURVEY.md §0.1); the
-// arithmetic below is what oracle/oracle_render.h (Sampler, FAST branch) and go-pbrt_b200/csrc/gp_render.cuh (get1d / get2d /
-// generate_lane) implement and test against each other bit for bit.
+// arithmetic below is what go-pbrt_b200/csrc/gp_render.cuh (get1d / get2d / generate_lane) implements; the repository's CPU
+// checker restates the same sampler and the two are tested against each other bit for bit (tests/test_gpu_parity.py).
 //
 // Differences to sampler.Stratified (pkg/sampler/stratified.go), all confined to the sampler:
 //   - StartNextSample reseeds the generator: rng.SetSequence(pixelIndex*spp + sampleIndex) (pixelIndex is row-major over
