@@ -9,6 +9,7 @@
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/gopbrt_cuda.h"
@@ -35,6 +36,7 @@ struct gopbrt_ctx {
   // device work of concurrent calls — each gRPC request of the reference renders on its own goroutine with its own scene,
   // SURVEY §8b — is serialised per context; gopbrt_cancel stays lock-free.
   std::mutex run_mu;
+  int grid_gen = 0, grid_shade[3] = {0, 0, 0}, grid_tail = 0;  // persistent grids of this device (SMs x resident CTAs)
 };
 
 #define GP_CUDA(ctx, call)                                                                               \
@@ -206,6 +208,18 @@ static HB xf_bounds(const M4& m, const HB& b) {
   return r;
 }
 
+// fn(begin, end, chunk index) over [0, n) on the host's cores (one chunk per thread, in index order)
+template <class F>
+static void parallel_chunks(int64_t n, F fn, int* n_chunks_out = nullptr) {
+  unsigned hw = std::thread::hardware_concurrency();
+  int nt = (n < 100000 || hw < 2) ? 1 : (int)std::min<unsigned>(hw, 64);
+  if (n_chunks_out) *n_chunks_out = nt;
+  if (nt == 1) { fn((int64_t)0, n, 0); return; }
+  std::vector<std::thread> th;
+  for (int t = 0; t < nt; t++) th.emplace_back([=]() { fn(n * t / nt, n * (t + 1) / nt, t); });
+  for (auto& t : th) t.join();
+}
+
 extern "C" int gopbrt_scene_create(gopbrt_ctx* ctx, const gopbrt_scene_desc* d, gopbrt_scene** out) {
   if (!ctx || !d || !out) return GOPBRT_ERR_INVALID;
   *out = nullptr;
@@ -260,38 +274,51 @@ extern "C" int gopbrt_scene_create(gopbrt_ctx* ctx, const gopbrt_scene_desc* d, 
   std::vector<int4> prims(np);
   std::vector<gpbvh::Box> pb(np);
   HB world;
-  for (int64_t i = 0; i < np; i++) {
-    const gopbrt_primitive& p = d->primitives[i];
-    prims[i] = make_int4(p.shape_kind, p.shape_index, p.material, p.prim_to_world);
-    if (p.material >= d->n_materials) return bad("material index out of range");
-    if (p.prim_to_world >= d->n_transforms) return bad("prim_to_world index out of range");
-    HB b;
-    if (p.shape_kind == GOPBRT_SHAPE_SPHERE) {
-      if (p.shape_index < 0 || p.shape_index >= d->n_spheres) return bad("sphere index out of range");
-      const SphereDev& s = spheres[p.shape_index];
-      HB ob; ob.valid = true;
-      ob.mn[0] = -s.radius; ob.mn[1] = -s.radius; ob.mn[2] = s.zMin; ob.mx[0] = s.radius; ob.mx[1] = s.radius; ob.mx[2] = s.zMax;  // sphere.go:46-51
-      b = xf_bounds(m4_from(&xf[32 * (size_t)s.xf]), ob);
-    } else if (p.shape_kind == GOPBRT_SHAPE_DISK) {
-      if (p.shape_index < 0 || p.shape_index >= d->n_disks) return bad("disk index out of range");
-      const DiskDev& s = disks[p.shape_index];
-      HB ob; ob.valid = true;
-      ob.mn[0] = -s.radius; ob.mn[1] = -s.radius; ob.mn[2] = s.height; ob.mx[0] = s.radius; ob.mx[1] = s.radius; ob.mx[2] = s.height;  // disk.go:41-54
-      b = xf_bounds(m4_from(&xf[32 * (size_t)s.xf]), ob);
-    } else if (p.shape_kind == GOPBRT_SHAPE_TRIANGLE) {
-      if (p.shape_index < 0 || p.shape_index >= d->n_triangles) return bad("triangle index out of range");
-      const gopbrt_triangle& t = d->triangles[p.shape_index];
-      for (int k = 0; k < 3; k++) {
-        if (t.v[k] < 0 || t.v[k] >= d->n_vertices) return bad("vertex index out of range");
-        hb_union_point(b, mk3(d->vertices[3 * (size_t)t.v[k]], d->vertices[3 * (size_t)t.v[k] + 1], d->vertices[3 * (size_t)t.v[k] + 2]));
+  {
+    std::vector<HB> part(64);
+    std::vector<const char*> err(64, nullptr);
+    int n_chunks = 1;
+    parallel_chunks(np, [&](int64_t i0, int64_t i1, int chunk) {
+      HB& wpart = part[chunk];
+      auto bad = [&](const char* msg) { err[chunk] = msg; return; };
+      for (int64_t i = i0; i < i1; i++) {
+        const gopbrt_primitive& p = d->primitives[i];
+        prims[i] = make_int4(p.shape_kind, p.shape_index, p.material, p.prim_to_world);
+        if (p.material >= d->n_materials) return bad("material index out of range");
+        if (p.prim_to_world >= d->n_transforms) return bad("prim_to_world index out of range");
+        HB b;
+        if (p.shape_kind == GOPBRT_SHAPE_SPHERE) {
+          if (p.shape_index < 0 || p.shape_index >= d->n_spheres) return bad("sphere index out of range");
+          const SphereDev& s = spheres[p.shape_index];
+          HB ob; ob.valid = true;
+          ob.mn[0] = -s.radius; ob.mn[1] = -s.radius; ob.mn[2] = s.zMin; ob.mx[0] = s.radius; ob.mx[1] = s.radius; ob.mx[2] = s.zMax;  // sphere.go:46-51
+          b = xf_bounds(m4_from(&xf[32 * (size_t)s.xf]), ob);
+        } else if (p.shape_kind == GOPBRT_SHAPE_DISK) {
+          if (p.shape_index < 0 || p.shape_index >= d->n_disks) return bad("disk index out of range");
+          const DiskDev& s = disks[p.shape_index];
+          HB ob; ob.valid = true;
+          ob.mn[0] = -s.radius; ob.mn[1] = -s.radius; ob.mn[2] = s.height; ob.mx[0] = s.radius; ob.mx[1] = s.radius; ob.mx[2] = s.height;  // disk.go:41-54
+          b = xf_bounds(m4_from(&xf[32 * (size_t)s.xf]), ob);
+        } else if (p.shape_kind == GOPBRT_SHAPE_TRIANGLE) {
+          if (p.shape_index < 0 || p.shape_index >= d->n_triangles) return bad("triangle index out of range");
+          const gopbrt_triangle& t = d->triangles[p.shape_index];
+          for (int k = 0; k < 3; k++) {
+            if (t.v[k] < 0 || t.v[k] >= d->n_vertices) return bad("vertex index out of range");
+            hb_union_point(b, mk3(d->vertices[3 * (size_t)t.v[k]], d->vertices[3 * (size_t)t.v[k] + 1], d->vertices[3 * (size_t)t.v[k] + 2]));
+          }
+          if (p.prim_to_world >= 0) return bad("TransformedPrimitive around a triangle is not supported");
+        } else {
+          return bad("unknown shape kind");
+        }
+        if (p.prim_to_world >= 0) b = xf_bounds(m4_from(&xf[32 * (size_t)p.prim_to_world]), b);  // primitive.go:127-129
+        for (int k = 0; k < 3; k++) { pb[i].mn[k] = b.mn[k]; pb[i].mx[k] = b.mx[k]; }
+        hb_union(wpart, b);
       }
-      if (p.prim_to_world >= 0) return bad("TransformedPrimitive around a triangle is not supported");
-    } else {
-      return bad("unknown shape kind");
+    }, &n_chunks);
+    for (int c = 0; c < n_chunks; c++) {
+      if (err[c]) return bad(err[c]);
+      if (part[c].valid) hb_union(world, part[c]);  // chunks in index order: the same union sequence, merely bracketed
     }
-    if (p.prim_to_world >= 0) b = xf_bounds(m4_from(&xf[32 * (size_t)p.prim_to_world]), b);  // primitive.go:127-129
-    for (int k = 0; k < 3; k++) { pb[i].mn[k] = b.mn[k]; pb[i].mx[k] = b.mx[k]; }
-    hb_union(world, b);
   }
 
   // ---- BVH
@@ -302,7 +329,8 @@ extern "C" int gopbrt_scene_create(gopbrt_ctx* ctx, const gopbrt_scene_desc* d, 
   // ---- leaf-ordered primitive records + their float64 bounds
   std::vector<PrimRec> recs(np);
   std::vector<double> rec_bounds(6 * (size_t)np);
-  for (int64_t r = 0; r < np; r++) {
+  parallel_chunks(np, [&](int64_t r0, int64_t r1, int) {
+  for (int64_t r = r0; r < r1; r++) {
     uint32_t pi = bvh.order[r];
     const gopbrt_primitive& p = d->primitives[pi];
     PrimRec rec;
@@ -341,6 +369,7 @@ extern "C" int gopbrt_scene_create(gopbrt_ctx* ctx, const gopbrt_scene_desc* d, 
     recs[r] = rec;
     for (int k = 0; k < 3; k++) { rec_bounds[6 * (size_t)r + k] = pb[pi].mn[k]; rec_bounds[6 * (size_t)r + 3 + k] = pb[pi].mx[k]; }
   }
+  });
 
   // ---- materials / textures / lights
   std::vector<MaterialDev> mats(d->n_materials);
@@ -696,16 +725,18 @@ static int render_impl(gopbrt_scene* sc, const gopbrt_camera* cam, const gopbrt_
   GP_CUDA(ctx, cudaMemsetAsync(sc->tctr.p, 0, sizeof(TraceCounters), st));
   const bool count = (flags & GOPBRT_FLAG_COUNT_TRAVERSAL) != 0;
 
-  static int g_gen = 0, g_shade = 0;
-  if (!g_gen) {
-    g_gen = grid_for(ctx, (const void*)k_generate, 128);
-    g_shade = grid_for(ctx, (const void*)k_shade<0>, 128);
+  if (!ctx->grid_gen) {
+    ctx->grid_gen = grid_for(ctx, (const void*)k_generate, 128);
+    ctx->grid_shade[0] = grid_for(ctx, (const void*)k_shade<0>, 128);
+    ctx->grid_shade[1] = grid_for(ctx, (const void*)k_shade<1>, 128);
+    ctx->grid_shade[2] = grid_for(ctx, (const void*)k_shade<2>, 128);
   }
   const size_t smem = sc->trace_smem;
   const int k_ext = count ? 1 : 0, k_any = direct_all ? (count ? 6 : 5) : (count ? 3 : 2);
   const int shade_kind = P.integrator == GOPBRT_INTEGRATOR_PATH ? 0 : (direct_all ? 2 : 1);
   const int scap = sc->stack_cap;
   const int g_small = ctx->sm_count * 8;
+  const int g_gen = ctx->grid_gen, g_shade = ctx->grid_shade[shade_kind];
   constexpr int kGraphIters = 8;
 
   cudaEvent_t ev[2];
@@ -827,8 +858,8 @@ static int render_impl(gopbrt_scene* sc, const gopbrt_camera* cam, const gopbrt_
       if (!count && *W.remaining_host <= tail_lanes) {
         // few lanes left: finish them one thread per lane instead of hundreds of near-empty wavefront iterations
         tick(ST_TAIL);
-        static int g_tail = 0;
-        if (!g_tail) g_tail = grid_for(ctx, (const void*)k_tail, 128, (size_t)kStackDepth * 128 * 2 * sizeof(unsigned));
+        if (!ctx->grid_tail) ctx->grid_tail = grid_for(ctx, (const void*)k_tail, 128, (size_t)kStackDepth * 128 * 2 * sizeof(unsigned));
+        const int g_tail = ctx->grid_tail;
         size_t tsm = (size_t)scap * 128 * 2 * sizeof(unsigned);
         k_tail<<<std::max(g_tail, ctx->sm_count * 2), 128, tsm, st>>>(sc->dev, L, P, Q, scap, W.rctr.p, sc->tctr.p);
         ctx->launches++;
