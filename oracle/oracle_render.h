@@ -1,7 +1,7 @@
 // ORACLE — test infrastructure only.  Nothing under go-pbrt_b200/ may include, link or call this.
 //
-// oracle_render.h: CPU restatement of the reference's sampler / camera / BSDF / light / Path.Li / film code
-// (SURVEY.md §8a rows a1-a3, a11-a16).  PARITY UNPINNED: the reference holds no golden value for any of this
+// oracle_render.h: CPU restatement of the reference's sampler / camera / BSDF / light / Path.Li / DirectLighting.Li /
+// film code.  PARITY UNPINNED: the reference holds no golden value for any of this
 //  and cannot be run here; this file follows the cited lines character by character, quirks included.
 #pragma once
 #include <mutex>
