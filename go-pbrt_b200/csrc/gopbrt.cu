@@ -769,9 +769,8 @@ static int render_impl(gopbrt_scene* sc, const gopbrt_camera* cam, const gopbrt_
     GP_CUDA(ctx, cudaMemsetAsync(W.tilepix.p, 0, bp * sizeof(double), st));
     GP_CUDA(ctx, cudaMemsetAsync(W.cnt.p, 0, 16 * sizeof(int), st));
     tick(ST_RAYGEN);
-    k_init_lanes<<<g_small, 128, 0, st>>>(L, P);
     k_generate<<<g_gen, 128, 0, st>>>(sc->dev, L, P, Q, nullptr, nullptr, W.rctr.p);
-    ctx->launches += 2;
+    ctx->launches += 1;
     // Wavefront iterations as a CUDA graph of kGraphIters iterations (6 launches each): in STRICT mode the last lanes
     // need hundreds of iterations over nearly empty queues, where the cost of an iteration IS its launch latency.
     // One graph stays queued ahead of the one the host is waiting for, so the device never idles on the host.

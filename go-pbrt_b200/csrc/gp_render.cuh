@@ -599,13 +599,14 @@ GP_D void film_add_sample(const Lanes& L, const RenderParams& P, long long lane,
 // (GenerateRayDifferential, camera.go:192-242; the differentials are dropped by Path.Li).  Returns false when the
 // lane's tile is exhausted.
 struct PathRec;
+GP_D PathRec initial_path(const RenderParams& P, long long lane);  // defined below
 GP_D RGB direct_unwind(const Lanes& L, const RenderParams& P, long long lane, const PathRec& pt);  // DirectLighting, defined below
 GP_D bool generate_lane(const DevScene& sc, const Lanes& L, const RenderParams& P, long long lane, bool have_sample,
                         unsigned long long& cam, unsigned long long& nans, unsigned long long& culled) {
   bool go = false;
   long long tile = ((P.lane_base + lane) / P.groups) * P.world + P.rank;
   const int s_mod = P.s_world * P.groups, s_res = P.s_rank * P.groups + (int)((P.lane_base + lane) % P.groups);
-  PathRec pt = L.path[lane];
+  PathRec pt = have_sample ? L.path[lane] : initial_path(P, lane);  // the pass's first launch starts every lane from scratch
   if (have_sample) {  // every lane of the regeneration queue carries a finished sample
     RGB Lc = P.integrator == 1 ? direct_unwind(L, P, lane, pt) : rgb(pt.Lr, pt.Lg, pt.Lb);
     if (is_nan(Lc.r) || is_nan(Lc.g) || is_nan(Lc.b)) { Lc = rgb(0.1, 0.1, 0.1); nans++; }  // integrator.go:256-257
@@ -1294,20 +1295,19 @@ __global__ void k_film_merge(Lanes L, RenderParams P, double* __restrict__ film)
   }
 }
 
-// pass start: reset per-lane sampler state (Sampler.Clone(seed = tile index), pixel.go:34-42) and tile accumulators
-__global__ void k_init_lanes(Lanes L, RenderParams P) {
-  for (long long lane = (long long)blockIdx.x * blockDim.x + threadIdx.x; lane < P.lanes_active; lane += (long long)gridDim.x * blockDim.x) {
-    long long tile = ((P.lane_base + lane) / P.groups) * P.world + P.rank;
-    Smp s;
-    s.state = 0x853c49e6748fea9bULL; s.inc = 0xda3e39cb94b95bdbULL;
-    rng_set_sequence(s, (unsigned long long)tile);
-    PathRec pt;
-    pt.br = pt.bg = pt.bb = 1.0; pt.Lr = pt.Lg = pt.Lb = 0; pt.eta_scale = 1.0; pt.fx = pt.fy = 0;
-    pt.rng_state = s.state; pt.rng_inc = s.inc;
-    pt.pix = -1; pt.sidx = 0; pt.has_sample = 0; pt.bounces = 0;
-    pt.pad[0] = pt.pad[1] = pt.pad[2] = 0;
-    L.path[lane] = pt;
-  }
+// pass start: the lane's initial sampler / path state (Sampler.Clone(seed = tile index), pixel.go:34-42); the first raygen
+// launch of a pass builds it in registers instead of reading it back from memory
+GP_D PathRec initial_path(const RenderParams& P, long long lane) {
+  long long tile = ((P.lane_base + lane) / P.groups) * P.world + P.rank;
+  Smp s;
+  s.state = 0x853c49e6748fea9bULL; s.inc = 0xda3e39cb94b95bdbULL;
+  rng_set_sequence(s, (unsigned long long)tile);
+  PathRec pt;
+  pt.br = pt.bg = pt.bb = 1.0; pt.Lr = pt.Lg = pt.Lb = 0; pt.eta_scale = 1.0; pt.fx = pt.fy = 0;
+  pt.rng_state = s.state; pt.rng_inc = s.inc;
+  pt.pix = -1; pt.sidx = 0; pt.has_sample = 0; pt.bounces = 0;
+  pt.pad[0] = pt.pad[1] = pt.pad[2] = 0;
+  return pt;
 }
 
 }  // namespace gp
