@@ -219,6 +219,18 @@ GP_D void start_pixel(Smp& s, const Lanes& L, const RenderParams& P) {
   s.sidx = 0;
 }
 
+// Quotient / remainder of non-negative 64-bit integers.  Tile, pixel and lane indices nearly always fit 32 bits, where the
+// hardware-assisted unsigned division is a few instructions; the generic 64-bit division is an ~100-instruction
+// subroutine, and the per-lane index arithmetic of raygen and shade used eight of them per sample.
+GP_D long long div_nn(long long a, long long b) {
+  if ((((unsigned long long)a | (unsigned long long)b) >> 32) == 0) return (long long)((unsigned)a / (unsigned)b);
+  return a / b;
+}
+GP_D long long mod_nn(long long a, long long b) {
+  if ((((unsigned long long)a | (unsigned long long)b) >> 32) == 0) return (long long)((unsigned)a % (unsigned)b);
+  return a % b;
+}
+
 // ---------------------------------------------------------------- sampling warps (pkg/pbrt/sampling.go)
 GP_D void concentric_sample_disk(double ux, double uy, double* ox, double* oy) {
   double x = ux * 2.0 - 1, y = uy * 2.0 - 1;
@@ -552,7 +564,7 @@ GP_D void light_sample_li(const DevScene& sc, const LightDev& l, const Intr& ref
 
 // ---------------------------------------------------------------- film geometry (film.go:106-113)
 GP_D void tile_bounds(const RenderParams& P, long long tile, long long* x0, long long* y0, long long* x1, long long* y1) {
-  long long tx = tile % P.ntx, ty = tile / P.ntx;
+  long long ty = div_nn(tile, P.ntx), tx = tile - ty * P.ntx;
   *x0 = P.cx0 + tx * P.tile_size;
   *x1 = (long long)go_min((double)(*x0 + P.tile_size), (double)P.cx1);  // integrator.go:322-325
   *y0 = P.cy0 + ty * P.tile_size;
@@ -604,8 +616,9 @@ GP_D RGB direct_unwind(const Lanes& L, const RenderParams& P, long long lane, co
 GP_D bool generate_lane(const DevScene& sc, const Lanes& L, const RenderParams& P, long long lane, bool have_sample,
                         unsigned long long& cam, unsigned long long& nans, unsigned long long& culled) {
   bool go = false;
-  long long tile = ((P.lane_base + lane) / P.groups) * P.world + P.rank;
-  const int s_mod = P.s_world * P.groups, s_res = P.s_rank * P.groups + (int)((P.lane_base + lane) % P.groups);
+  const long long slot = P.lane_base + lane, slot_tile = P.groups == 1 ? slot : div_nn(slot, P.groups);
+  long long tile = slot_tile * P.world + P.rank;
+  const int s_mod = P.s_world * P.groups, s_res = P.s_rank * P.groups + (int)(slot - slot_tile * P.groups);
   PathRec pt = have_sample ? L.path[lane] : initial_path(P, lane);  // the pass's first launch starts every lane from scratch
   if (have_sample) {  // every lane of the regeneration queue carries a finished sample
     RGB Lc = P.integrator == 1 ? direct_unwind(L, P, lane, pt) : rgb(pt.Lr, pt.Lg, pt.Lb);
@@ -628,8 +641,15 @@ GP_D bool generate_lane(const DevScene& sc, const Lanes& L, const RenderParams& 
         // PixelSampler.StartNextSample (pixel.go:48-52) + Sampler.StartNextSample (sampler.go:29-34): increments first
         s.cur1 = 0; s.cur2 = 0;
         s.sidx += 1;
+        if (s_mod > 1) {
+          // FAST: samples split by index (over ranks, then lane groups) — step straight to this lane's next sample.
+          // (Searching for it one index at a time let the lanes of a warp leave the search at different iterations and
+          // run the whole camera-ray body one lane group at a time: 4 of 32 lanes active in a pass's first launch.)
+          int d = s_res - s.sidx % s_mod;
+          if (d < 0) d += s_mod;
+          s.sidx += d;
+        }
         if (s.sidx < P.spp) {
-          if (s_mod > 1 && (s.sidx % s_mod) != s_res) continue;  // FAST: samples split by index (over ranks, then lane groups)
           have = true;
           break;
         }
@@ -639,7 +659,8 @@ GP_D bool generate_lane(const DevScene& sc, const Lanes& L, const RenderParams& 
       start_pixel(s, L, P);
     }
     if (!have) break;
-    long long px = x0 + pix % tw, py = y0 + pix / tw;
+    long long prow = tw == 1 ? pix : div_nn(pix, tw);
+    long long px = x0 + (pix - prow * tw), py = y0 + prow;
     unsigned long long fast_pixel = (unsigned long long)((py - P.cy0) * (P.cx1 - P.cx0) + (px - P.cx0));
     if (P.mode == 1) rng_set_sequence(s, fast_pixel * (unsigned long long)P.spp + (unsigned long long)s.sidx);
     // GetCameraSample (sampler.go:75-80): Get2D pFilm, Get2D pLens, Get1D time
@@ -818,11 +839,12 @@ GP_D void shade_lane(const DevScene& sc, const Lanes& L, const RenderParams& P, 
       s.cur1 = (packed >> 8) & 255; s.cur2 = (packed >> 16) & 255; s.lane = lane;
       unsigned long long fast_pixel = 0;
       if (P.mode == 1) {
-        long long tile = ((P.lane_base + lane) / P.groups) * P.world + P.rank;
+        long long tile = (P.groups == 1 ? P.lane_base + lane : div_nn(P.lane_base + lane, P.groups)) * P.world + P.rank;
         long long x0, y0, x1, y1;
         tile_bounds(P, tile, &x0, &y0, &x1, &y1);
         int pix = pt.pix;
-        long long px = x0 + pix % (x1 - x0), py = y0 + pix / (x1 - x0);
+        long long prow = div_nn(pix, x1 - x0);
+        long long px = x0 + (pix - prow * (x1 - x0)), py = y0 + prow;
         fast_pixel = (unsigned long long)((py - P.cy0) * (P.cx1 - P.cx0) + (px - P.cx0));
       }
       RGB beta = rgb(pt.br, pt.bg, pt.bb);
@@ -986,11 +1008,12 @@ GP_D void shade_lane_direct(const DevScene& sc, const Lanes& L, const RenderPara
     s.cur1 = (packed >> 8) & 255; s.cur2 = (packed >> 16) & 255; s.lane = lane;
     unsigned long long fast_pixel = 0;
     if (P.mode == 1) {
-      long long tile = ((P.lane_base + lane) / P.groups) * P.world + P.rank;
+      long long tile = (P.groups == 1 ? P.lane_base + lane : div_nn(P.lane_base + lane, P.groups)) * P.world + P.rank;
       long long x0, y0, x1, y1;
       tile_bounds(P, tile, &x0, &y0, &x1, &y1);
       int pix = pt.pix;
-      long long px = x0 + pix % (x1 - x0), py = y0 + pix / (x1 - x0);
+      long long prow = div_nn(pix, x1 - x0);
+      long long px = x0 + (pix - prow * (x1 - x0)), py = y0 + prow;
       fast_pixel = (unsigned long long)((py - P.cy0) * (P.cx1 - P.cx0) + (px - P.cx0));
     }
     Intr ref; ref.p = h.p; ref.perr = h.perr; ref.n = h.n;
@@ -1264,7 +1287,8 @@ __global__ void k_film_merge(Lanes L, RenderParams P, double* __restrict__ film)
   long long npx = fw * fh;
   long long ext = (long long)ceil(P.frx > P.fry ? P.frx : P.fry) + 1;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < npx; i += (long long)gridDim.x * blockDim.x) {
-    long long x = P.cx0 + i % fw, y = P.cy0 + i / fw;
+    long long frow = div_nn(i, fw);
+    long long x = P.cx0 + (i - frow * fw), y = P.cy0 + frow;
     double X = film[i * 4], Y = film[i * 4 + 1], Z = film[i * 4 + 2], W = film[i * 4 + 3];
     long long ty0 = (y - ext - P.cy0) / P.tile_size, ty1 = (y + ext - P.cy0) / P.tile_size;
     long long tx0 = (x - ext - P.cx0) / P.tile_size, tx1 = (x + ext - P.cx0) / P.tile_size;
@@ -1298,7 +1322,7 @@ __global__ void k_film_merge(Lanes L, RenderParams P, double* __restrict__ film)
 // pass start: the lane's initial sampler / path state (Sampler.Clone(seed = tile index), pixel.go:34-42); the first raygen
 // launch of a pass builds it in registers instead of reading it back from memory
 GP_D PathRec initial_path(const RenderParams& P, long long lane) {
-  long long tile = ((P.lane_base + lane) / P.groups) * P.world + P.rank;
+  long long tile = (P.groups == 1 ? P.lane_base + lane : div_nn(P.lane_base + lane, P.groups)) * P.world + P.rank;
   Smp s;
   s.state = 0x853c49e6748fea9bULL; s.inc = 0xda3e39cb94b95bdbULL;
   rng_set_sequence(s, (unsigned long long)tile);
