@@ -186,6 +186,16 @@ GP_HD bool disk_test(const Ray& ray, double height, double radius, double innerR
 // ---- Triangle (new shape, defined by this backend + its oracle): watertight test in float64 ----
 GP_HD int max_dim(V3 v) { return (v.x > v.y) ? ((v.x > v.z) ? 0 : 2) : ((v.y > v.z) ? 1 : 2); }
 GP_HD V3 permute(V3 v, int x, int y, int z) { return mk3(comp(v, x), comp(v, y), comp(v, z)); }
+// The watertight test only ever permutes cyclically — (kx, ky, kz) = (kz+1, kz+2, kz) mod 3 — so the permutation is a
+// three-way choice keyed by kz.  Done with bit masks on the float64 bit patterns: a pure selection (bit-exact), and
+// branch-free by construction (the generic comp() chain compiled to ~370 instructions of divergent code per triangle).
+GP_HD V3 permute_cyclic(V3 v, int kz) {
+  const uint64_t m0 = (uint64_t)0 - (uint64_t)(kz == 0), m1 = (uint64_t)0 - (uint64_t)(kz == 1), m2 = ~(m0 | m1);
+  const uint64_t x = f2b(v.x), y = f2b(v.y), z = f2b(v.z);
+  return mk3(b2f((y & m0) | (z & m1) | (x & m2)),   // component kx: y, z, x for kz = 0, 1, 2
+             b2f((z & m0) | (x & m1) | (y & m2)),   // component ky
+             b2f((x & m0) | (y & m1) | (z & m2)));  // component kz
+}
 // per-ray part of the watertight test (depends on the ray direction only): permutation and shear constants
 struct TriRay { int kx, ky, kz; double Sx, Sy, Sz; };
 GP_HD TriRay tri_ray_setup(V3 dir) {
@@ -193,14 +203,15 @@ GP_HD TriRay tri_ray_setup(V3 dir) {
   tr.kz = max_dim(vabs(dir));
   tr.kx = tr.kz + 1; if (tr.kx == 3) tr.kx = 0;
   tr.ky = tr.kx + 1; if (tr.ky == 3) tr.ky = 0;
-  V3 d = permute(dir, tr.kx, tr.ky, tr.kz);
+  V3 d = permute_cyclic(dir, tr.kz);
   tr.Sx = -d.x / d.z; tr.Sy = -d.y / d.z; tr.Sz = 1.0 / d.z;
   return tr;
 }
 GP_HD bool tri_test_pre(V3 p0, V3 p1, V3 p2, const Ray& ray, const TriRay& tr, double* tHit, double* bary) {
   V3 p0t = p0 - ray.o, p1t = p1 - ray.o, p2t = p2 - ray.o;
   int kx = tr.kx, ky = tr.ky, kz = tr.kz;
-  p0t = permute(p0t, kx, ky, kz); p1t = permute(p1t, kx, ky, kz); p2t = permute(p2t, kx, ky, kz);
+  p0t = permute_cyclic(p0t, kz); p1t = permute_cyclic(p1t, kz); p2t = permute_cyclic(p2t, kz);
+  (void)kx; (void)ky;
   double Sx = tr.Sx, Sy = tr.Sy, Sz = tr.Sz;
   p0t.x += Sx * p0t.z; p0t.y += Sy * p0t.z;
   p1t.x += Sx * p1t.z; p1t.y += Sy * p1t.z;
@@ -208,7 +219,7 @@ GP_HD bool tri_test_pre(V3 p0, V3 p1, V3 p2, const Ray& ray, const TriRay& tr, d
   double e0 = p1t.x * p2t.y - p1t.y * p2t.x;
   double e1 = p2t.x * p0t.y - p2t.y * p0t.x;
   double e2 = p0t.x * p1t.y - p0t.y * p1t.x;
-  if ((e0 < 0 || e1 < 0 || e2 < 0) && (e0 > 0 || e1 > 0 || e2 > 0)) return false;
+  if (((e0 < 0) | (e1 < 0) | (e2 < 0)) & ((e0 > 0) | (e1 > 0) | (e2 > 0))) return false;  // same truth table, no short-circuit branches
   double det = e0 + e1 + e2;
   if (det == 0) return false;
   p0t.z *= Sz; p1t.z *= Sz; p2t.z *= Sz;
