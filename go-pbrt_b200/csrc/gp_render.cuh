@@ -71,29 +71,9 @@ GP_D void queue_push(int* q, int* cnt, bool pred, int v) {
   if (pred) q[base + __popc(m & ((1u << lane_id) - 1u))] = v;
 }
 
-// three pushes of one warp with ONE atomic round trip: lanes 0/1/2 reserve the space of queue A/B/C at the same time
-GP_D void queue_push3(int* qa, int* ca, bool pa, int* qb, int* cb, bool pb, int* qc, int* cc, bool pc, int v) {
-  const unsigned FULL = 0xffffffffu;
-  unsigned ma = __ballot_sync(FULL, pa), mb = __ballot_sync(FULL, pb), mc = __ballot_sync(FULL, pc);
-  if ((ma | mb | mc) == 0) return;
-  int lane_id = threadIdx.x & 31;
-  int base = 0;
-  if (lane_id == 0 && ma) base = atomicAdd(ca, __popc(ma));
-  if (lane_id == 1 && mb) base = atomicAdd(cb, __popc(mb));
-  if (lane_id == 2 && mc) base = atomicAdd(cc, __popc(mc));
-  int ba = __shfl_sync(FULL, base, 0), bb = __shfl_sync(FULL, base, 1), bc = __shfl_sync(FULL, base, 2);
-  unsigned lt = (1u << lane_id) - 1u;
-  if (pa) qa[ba + __popc(ma & lt)] = v;
-  if (pb) qb[bb + __popc(mb & lt)] = v;
-  if (pc) qc[bc + __popc(mc & lt)] = v;
-}
-
 // CTA-wide pushes (every thread of the CTA must call them, inside CTA-uniform control flow): one atomic per CTA and
 // queue, and the CTA's entries land in the queue as one contiguous run in thread order, which keeps neighbouring lanes
 // (neighbouring pixels / sample groups) next to each other for the stage that consumes the queue.
-#ifndef GP_BLOCK_PUSH
-#define GP_BLOCK_PUSH 1
-#endif
 template <int NQ>
 GP_D void block_push(int* const (&q)[NQ], int* const (&cnt)[NQ], const bool (&pred)[NQ], int v, int (*s_cnt)[NQ], int* s_base) {
   const unsigned FULL = 0xffffffffu;
@@ -719,27 +699,15 @@ GP_D bool generate_lane(const DevScene& sc, const Lanes& L, const RenderParams& 
 // Retires the lane's finished sample into its film tile (renderWorker, integrator.go:252-265), advances the sampler
 // (StartNextSample / next pixel + StartPixel) and generates the next camera ray (GenerateRayDifferential,
 // camera.go:192-242; the differentials are dropped by Path.Li).  Lanes whose tile is exhausted leave the wavefront.
-#ifndef GP_GEN_MINBLOCKS
-#define GP_GEN_MINBLOCKS 4
-#endif
-#ifndef GP_GEN_TILE_PREFETCH
-#define GP_GEN_TILE_PREFETCH 0
-#endif
-__global__ void __launch_bounds__(128, GP_GEN_MINBLOCKS) k_generate(DevScene sc, Lanes L, RenderParams P, Queues Q, const int* __restrict__ in_queue,
+__global__ void __launch_bounds__(128, 4) k_generate(DevScene sc, Lanes L, RenderParams P, Queues Q, const int* __restrict__ in_queue,
                                                   const int* __restrict__ in_count, RenderCounters* ctr) {
   long long n = in_queue ? (long long)*in_count : P.lanes_active;
   int lane_id = threadIdx.x & 31;
   unsigned long long cam = 0, nans = 0, culled = 0;
-#if GP_BLOCK_PUSH
   __shared__ int s_cnt[4][1];
   __shared__ int s_base[1];
   for (long long cbase = (long long)blockIdx.x * blockDim.x; cbase < n; cbase += (long long)gridDim.x * blockDim.x) {
     long long i = cbase + threadIdx.x;
-#else
-  long long warp_base0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) - lane_id;
-  for (long long base = warp_base0; base < n; base += (long long)gridDim.x * blockDim.x) {
-    long long i = base + lane_id;
-#endif
     bool valid = i < n;
     bool go = false;
     long long lane = 0;
@@ -747,14 +715,10 @@ __global__ void __launch_bounds__(128, GP_GEN_MINBLOCKS) k_generate(DevScene sc,
       lane = in_queue ? in_queue[i] : i;
       go = generate_lane(sc, L, P, lane, in_queue != nullptr, cam, nans, culled);
     }
-#if GP_BLOCK_PUSH
     int* const qs[1] = {Q.extend};
     int* const cs[1] = {Q.cnt + 0};
     const bool ps[1] = {go};
     block_push<1>(qs, cs, ps, (int)lane, s_cnt, s_base);
-#else
-    queue_push(Q.extend, Q.cnt + 0, go, (int)lane);
-#endif
   }
   cam = warp_sum(cam); nans = warp_sum(nans); culled = warp_sum(culled);
   if (lane_id == 0) {
@@ -1153,16 +1117,10 @@ __global__ void __launch_bounds__(128, 3) k_shade(DevScene sc, Lanes L, RenderPa
   int lane_id = threadIdx.x & 31;
   unsigned long long n_unsupported = 0, n_dead = 0;
   int bad = 0;
-#if GP_BLOCK_PUSH
   __shared__ int s_cnt[4][3];
   __shared__ int s_base[3];
   for (long long cbase = (long long)blockIdx.x * blockDim.x; cbase < n; cbase += (long long)gridDim.x * blockDim.x) {
     long long i = cbase + threadIdx.x;
-#else
-  long long warp_base0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) - lane_id;
-  for (long long base = warp_base0; base < n; base += (long long)gridDim.x * blockDim.x) {
-    long long i = base + lane_id;
-#endif
     const int* bin_q;
     long long bi;
     if (i >= o3) { bin_q = Q.shade[3]; bi = i - o3; if (bi >= n3) bi = -1; }
@@ -1182,14 +1140,10 @@ __global__ void __launch_bounds__(128, 3) k_shade(DevScene sc, Lanes L, RenderPa
     if (INTEG == 2) {  // UniformSampleAll: one shadow-queue entry per emitted segment (entry = lane * n_seg + light)
       for (int j = 0; j < P.n_seg; j++) queue_push(Q.shadow, Q.cnt + 2, (seg_mask >> j) & 1u, (int)(lane * P.n_seg + j));
     }
-#if GP_BLOCK_PUSH
     int* const qs[3] = {Q.shadow, Q.extend_next, Q.regen_next};
     int* const cs[3] = {Q.cnt + 2, Q.cnt + 1, Q.cnt + 4};
     const bool ps[3] = {shadow, cont, finished && valid};
     block_push<3>(qs, cs, ps, (int)lane, s_cnt, s_base);
-#else
-    queue_push3(Q.shadow, Q.cnt + 2, shadow, Q.extend_next, Q.cnt + 1, cont, Q.regen_next, Q.cnt + 4, finished && valid, (int)lane);
-#endif
   }
   n_unsupported = warp_sum(n_unsupported); n_dead = warp_sum(n_dead);
   if (lane_id == 0) {

@@ -62,7 +62,10 @@ constexpr int kRefillIdle = GP_REFILL_IDLE;     // idle lanes that trigger a ref
 #define GP_DESCEND_STEPS 16
 #endif
 constexpr int kDescendSteps = GP_DESCEND_STEPS;
-constexpr int kQuadricBatch = 8;   // parked sphere/disk tests that trigger their batched execution
+#ifndef GP_QUADRIC_BATCH
+#define GP_QUADRIC_BATCH 8
+#endif
+constexpr int kQuadricBatch = GP_QUADRIC_BATCH;   // parked sphere/disk tests that trigger their batched execution
 
 // One traversal step from an inner node whose box has passed: fetch its 4-record child group (128 contiguous bytes:
 // slots 0,1 = children of the left child, or the left child itself + an empty slot when it is a leaf; slots 2,3
