@@ -262,6 +262,8 @@ def main():
 
     # ---- e2e: public C-ABI call with a host film buffer
     desc_bytes = sum(C.sizeof(t) for t in (abi.Camera, abi.Sampler, abi.Integrator, abi.Film, abi.RenderOptions))
+    if world == 1:  # one untimed call through the host-film entry point: it allocates that path's device film on first use
+        P.Render(g, integ, args.tile, mode=mode, out=film_host_np)
     barrier()
     e0 = time.time()
     e2e_parts = {"ms_device": 0.0, "ms_download": 0.0}

@@ -675,6 +675,15 @@ static int render_impl(gopbrt_scene* sc, const gopbrt_camera* cam, const gopbrt_
   }
   long long lanes_total = ((P.ntiles - P.rank + P.world - 1) / P.world) * P.groups;
 
+  // GOPBRT_HOST_TIMING=1: host wall-clock of the call's phases on stderr (tuning aid)
+  const bool host_timing = getenv("GOPBRT_HOST_TIMING") != nullptr;
+  auto hw0 = std::chrono::steady_clock::now();
+  auto hw_tick = [&](const char* what) {
+    if (!host_timing) return;
+    auto now = std::chrono::steady_clock::now();
+    fprintf(stderr, "[gopbrt host] %-18s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(now - hw0).count());
+    hw0 = now;
+  };
   cudaStream_t st = ctx->stream;
   GP_CUDA(ctx, cudaSetDevice(ctx->device));
   GP_CUDA(ctx, cudaMemsetAsync(d_film, 0, (size_t)fw * fh * 4 * sizeof(double), st));
@@ -714,6 +723,7 @@ static int render_impl(gopbrt_scene* sc, const gopbrt_camera* cam, const gopbrt_
     }
     W.lanes = lanes; W.bytes_tables = bt; W.bytes_tilepix = bp;
   }
+  hw_tick("workspace");
   Lanes L;
   memset(&L, 0, sizeof(L));
   L.n = lanes;
@@ -817,6 +827,7 @@ static int render_impl(gopbrt_scene* sc, const gopbrt_camera* cam, const gopbrt_
         GP_CUDA(ctx, ge);
         W.graph_key = key;
       }
+      hw_tick("graph lookup/build");
       for (auto& e : W.graph_ev) if (!e) GP_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
       for (uint64_t k = 0;; k++) {
         GP_CUDA(ctx, cudaGraphLaunch(W.graph_exec, st));
@@ -877,8 +888,10 @@ static int render_impl(gopbrt_scene* sc, const gopbrt_camera* cam, const gopbrt_
     ctx->launches++;
   }
   tick(ST_N);
+  hw_tick("wavefront loop");
   GP_CUDA(ctx, cudaEventRecord(ev[1], st));
   GP_CUDA(ctx, cudaStreamSynchronize(st));
+  hw_tick("final sync");
   GP_CUDA(ctx, cudaGetLastError());
   float ms = 0;
   cudaEventElapsedTime(&ms, ev[0], ev[1]);
@@ -934,6 +947,7 @@ static int render_impl(gopbrt_scene* sc, const gopbrt_camera* cam, const gopbrt_
       stats->ms_shadow = acc[ST_SHADOW]; stats->ms_film = acc[ST_FILM];
     }
   }
+  hw_tick("stats");
   if (rc == GOPBRT_OK && (flags & GOPBRT_FLAG_FAIL_ON_PANIC) && (rcnt.radiance_gt10 || rcnt.efloat_panics || tcnt.efloat_panics || rcnt.unsupported)) {
     ctx->last_error = "a condition on which the reference panics was hit (see gopbrt_stats)";
     return GOPBRT_ERR_REFERENCE_PANIC;
