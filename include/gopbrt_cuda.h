@@ -132,7 +132,8 @@ typedef struct {
   int32_t n_materials;   const gopbrt_material* materials;
   int32_t n_textures;    const gopbrt_texture* textures;
   int32_t n_lights;      const gopbrt_light* lights;
-  int32_t max_prims_in_node; /* NewBVH's maxPrimsInNode (bvh.go:223); 0 = library default */
+  int32_t max_prims_in_node; /* NewBVH's maxPrimsInNode (bvh.go:223), an upper bound on a leaf: the library's own tree
+                                uses min(this, 2) primitives per leaf (results do not depend on the tree); 0 = default */
   int32_t flags;
 } gopbrt_scene_desc;
 
