@@ -570,11 +570,33 @@ GP_D void film_add_sample(const Lanes& L, const RenderParams& P, long long lane,
   long long p1x = (long long)go_min(p1fx, (double)bx1), p1y = (long long)go_min(p1fy, (double)by1);
   // contribSum += L*w*f with L == +0 leaves the (never negative-zero) sums untouched: only the weight moves
   bool zero = Lc.r == 0 && Lc.g == 0 && Lc.b == 0 && !sign_bit(Lc.r) && !sign_bit(Lc.g) && !sign_bit(Lc.b);
+  double* tile_px = L.tilepix + (size_t)lane * L.tile_stride;
+  if (p1x - p0x == 2 && p1y - p0y == 2 && P.tpw == 2 && p0x == bx0 && p0y == by0) {
+    // The usual footprint: the lane's whole 2 x 2 FilmTile = one 128-byte line.  All of it is read before any of it is
+    // written: a store into the line would otherwise push the next pixel's load back out to L2, one serialised round
+    // trip per pixel.  The per-pixel sums are independent, so the order of the accesses changes no bit.
+    double2* qp = (double2*)tile_px;
+    double2 v[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) v[i] = qp[i];
+    const double fw = 1.0;
+    if (!zero) {
+      RGB c = Lc * (1.0 * fw);
+#pragma unroll
+      for (int i = 0; i < 4; i++) { v[2 * i].x += c.r; v[2 * i].y += c.g; v[2 * i + 1].x += c.b; }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) v[2 * i + 1].y += fw;
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+      if (!zero || (i & 1)) qp[i] = v[i];
+    return;
+  }
   for (long long y = p0y; y < p1y; y++)
     for (long long x = p0x; x < p1x; x++) {
       double fw = 1.0;
       size_t k = (size_t)((y - by0) * P.tpw + (x - bx0)) * 4;
-      double* q = L.tilepix + (size_t)lane * L.tile_stride + k;
+      double* q = tile_px + k;
       if (!zero) {
         RGB c = Lc * (1.0 * fw);
         q[0] += c.r;
