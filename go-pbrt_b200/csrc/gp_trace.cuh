@@ -1,12 +1,12 @@
 // gp_trace.cuh — BVH traversal kernels: `extend` (closest hit == BVH.Intersect, pkg/accelerator/bvh.go:659-712) and
-// `shadow` (any hit == BVH.IntersectP, bvh.go:713-765) over coalesced SoA ray queues.
+// `shadow` (any hit == BVH.IntersectP, bvh.go:713-765) over index queues of per-lane ray records.
 //
 // One thread per ray; persistent grid (a multiple of the SM count) striding over the queue.  The traversal stack
 // lives in shared memory, interleaved [entry][thread] so a warp's pushes/pops hit 32 distinct banks.
 // Node fetch = float4 loads of 32-byte records; an inner node's record points at a 128-byte group holding the records
-// of its (up to four) grandchildren, so one fetch brings two tree levels.  Node boxes are float32 rounded OUTWARD from the float64 union of
-// the primitives' bounds and tested with the reference's float64 slab test, so a node is entered whenever the
-// reference's own (float64) box would be; at the leaf each primitive is admitted only if ITS OWN float64 world bound
+// of its (up to four) grandchildren, so one fetch brings two tree levels.  Node boxes are float32 rounded OUTWARD from the
+// float64 union of the primitives' bounds and tested with a conservative float32 slab test (directed rounding), so a node
+// is entered whenever the reference's own (float64) box would be; at the leaf each primitive is admitted only if ITS OWN float64 world bound
 // passes Bounds3.IntersectP with the running tMax — the topology-independent parity spec of SURVEY §8a — and then
 // gets the float64/EFloat shape test.  Near child first by split axis and ray sign, as the reference.
 #pragma once
@@ -117,7 +117,8 @@ GP_D int quad_step(const DevScene& sc, unsigned& cur_a, unsigned& cur_b, bool& h
 //           together.
 // Visit order per ray is the reference's: near child first by split axis and ray sign, far child on the stack;
 // a leaf's primitives in order with the running tMax (closest hit) or first hit wins (any hit).
-// ANY=false: rays.tmax[lane] = tHit (unchanged on a miss), hit_rec[lane] = leaf-record index or -1.
+// ANY=false: rays[lane].tmax = tHit (unchanged on a miss), rays[lane].hit_rec = leaf-record index or -1; if `occluded` is
+//            set (render loop) it also receives, per QUEUE POSITION, the hit's shade class or 4 for a miss (k_split_hits).
 // ANY=true : occluded[lane] = 1/0.
 // queue == nullptr: ray i is lane i (batched API); otherwise lane = queue[i] for i < *count.
 // dynamic shared memory: stack_cap * blockDim.x unsigned, [entry][thread] (bank-conflict free).
