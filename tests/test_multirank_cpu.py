@@ -15,7 +15,7 @@ import torch.multiprocessing as mp
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _worker(rank, world, port, mode, q):
+def _worker(rank, world, port, mode, direct, q):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import importlib
@@ -25,6 +25,8 @@ def _worker(rank, world, port, mode, q):
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     scene, integ = gp.scenes.config1(W=64, H=36)
+    if direct:  # integrator.DirectLighting, every light sampled (UniformSampleAll)
+        integ = gp.pbrt.NewDirectLighting(gp.pbrt.UniformSampleAll, 5, integ.GetCamera(), integ.GetSampler(), None)
     o = OracleScene(scene, 1)
     film, st = o.render(integ, 1, mode=mode, rank=rank, world=world, threads=2)
     t = torch.from_numpy(film.copy())
@@ -38,15 +40,15 @@ def _worker(rank, world, port, mode, q):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("mode", [0, 1])
-def test_two_rank_gloo_partition_and_reduce(mode):
+@pytest.mark.parametrize("mode,direct", [(0, False), (1, False), (1, True)])
+def test_two_rank_gloo_partition_and_reduce(mode, direct):
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
     port = s.getsockname()[1]
     s.close()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, mode, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, mode, direct, q)) for r in range(2)]
     for p in procs:
         p.start()
     summed, single, paths, paths1 = q.get(timeout=240)
