@@ -452,6 +452,7 @@ extern "C" int gopbrt_scene_create(gopbrt_ctx* ctx, const gopbrt_scene_desc* d, 
   // traversal stack, [entry][thread] in dynamic shared memory: a step over a 4-record child group (two tree levels)
   // stacks at most three records
   sc->stack_cap = std::min(250, 3 * ((bvh.depth + 2) / 2) + 4);
+  if (const char* e = getenv("GOPBRT_STACK_CAP")) sc->stack_cap = std::max(4, atoi(e));  // tuning aid (overflows are counted)
   sc->trace_smem = (size_t)sc->stack_cap * kTraceThreads * 2 * sizeof(unsigned);  // two words (a, b) per stacked node
   sc->trace_k[0] = k_trace<0, false>; sc->trace_k[1] = k_trace<0, true>; sc->trace_k[2] = k_trace<2, false>;
   sc->trace_k[3] = k_trace<2, true>; sc->trace_k[4] = k_trace<1, false>;
@@ -778,7 +779,7 @@ static int render_impl(gopbrt_scene* sc, const gopbrt_camera* cam, const gopbrt_
   const int tail_lanes = (opt && (opt->flags & GOPBRT_FLAG_TAIL) && P.integrator == GOPBRT_INTEGRATOR_PATH) ? 49152 : 0;
   // debug aid: GOPBRT_ITER_LOG=<file> synchronises every iteration and logs the queue sizes (implies per-stage timing)
   const char* iter_log_path = getenv("GOPBRT_ITER_LOG");
-  std::vector<int> iter_counts;
+  std::vector<int> iter_counts, iter_shadow, iter_hits;
   for (long long base = 0; base < lanes_total && rc == GOPBRT_OK; base += lanes) {
     P.lane_base = base;
     P.lanes_active = std::min(lanes, lanes_total - base);
@@ -855,6 +856,13 @@ static int render_impl(gopbrt_scene* sc, const gopbrt_camera* cam, const gopbrt_
       if (shade_kind == 0) k_shade<0><<<g_shade, 128, 0, st>>>(sc->dev, L, P, Q, W.rctr.p);
       else if (shade_kind == 1) k_shade<1><<<g_shade, 128, 0, st>>>(sc->dev, L, P, Q, W.rctr.p);
       else k_shade<2><<<g_shade, 128, 0, st>>>(sc->dev, L, P, Q, W.rctr.p);
+      if (iter_log_path) {
+        int c[12];
+        cudaMemcpyAsync(c, Q.cnt, sizeof(c), cudaMemcpyDeviceToHost, st);
+        cudaStreamSynchronize(st);
+        iter_shadow.push_back(c[2]);
+        iter_hits.push_back(c[8] + c[9] + c[10] + c[11]);
+      }
       tick(ST_SHADOW);
       sc->trace_k[k_any]<<<sc->trace_grid[k_any], kTraceThreads, smem, st>>>(sc->dev, nullptr, L.sray, L.path, L.occl, Q.shadow, Q.cnt + 2, 0, scap, Q.cnt + 7, sc->tctr.p, &W.rctr.p->radiance_gt10);
       tick(ST_RAYGEN);
@@ -918,20 +926,20 @@ static int render_impl(gopbrt_scene* sc, const gopbrt_camera* cam, const gopbrt_
       FILE* fp = fopen(iter_log_path, "w");
       if (fp) {
         size_t it = 0;
-        fprintf(fp, "iter,extend_rays,ms_extend,ms_shade,ms_shadow,ms_raygen\n");
+        fprintf(fp, "iter,extend_rays,hits,shadow_rays,ms_extend,ms_shade,ms_shadow,ms_raygen\n");
         double row[ST_N + 1] = {0, 0, 0, 0, 0, 0, 0};
         bool open_row = false;
         for (size_t i = 0; i + 1 < ev_used; i++) {
           float t = 0;
           cudaEventElapsedTime(&t, W.events[i], W.events[i + 1]);
           if (ev_stage[i] == ST_EXTEND) {
-            if (open_row) { fprintf(fp, "%zu,%d,%.4f,%.4f,%.4f,%.4f\n", it, it < iter_counts.size() ? iter_counts[it] : -1, row[ST_EXTEND], row[ST_SHADE], row[ST_SHADOW], row[ST_RAYGEN]); it++; }
+            if (open_row) { fprintf(fp, "%zu,%d,%d,%d,%.4f,%.4f,%.4f,%.4f\n", it, it < iter_counts.size() ? iter_counts[it] : -1, it < iter_hits.size() ? iter_hits[it] : -1, it < iter_shadow.size() ? iter_shadow[it] : -1, row[ST_EXTEND], row[ST_SHADE], row[ST_SHADOW], row[ST_RAYGEN]); it++; }
             for (int k = 0; k <= ST_N; k++) row[k] = 0;
             open_row = true;
           }
           if (open_row) row[ev_stage[i]] += t;
         }
-        if (open_row) fprintf(fp, "%zu,%d,%.4f,%.4f,%.4f,%.4f\n", it, it < iter_counts.size() ? iter_counts[it] : -1, row[ST_EXTEND], row[ST_SHADE], row[ST_SHADOW], row[ST_RAYGEN]);
+        if (open_row) fprintf(fp, "%zu,%d,%d,%d,%.4f,%.4f,%.4f,%.4f\n", it, it < iter_counts.size() ? iter_counts[it] : -1, it < iter_hits.size() ? iter_hits[it] : -1, it < iter_shadow.size() ? iter_shadow[it] : -1, row[ST_EXTEND], row[ST_SHADE], row[ST_SHADOW], row[ST_RAYGEN]);
         fclose(fp);
       }
     }

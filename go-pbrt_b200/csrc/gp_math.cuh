@@ -357,43 +357,52 @@ GP_HD bool slab_test(double bx0, double by0, double bz0, double bx1, double by1,
 // ---- conservative float32 slab test for BVH NODES ----
 // Node boxes are float32, rounded outward from the float64 union of their primitives' bounds.  Exact float64 decisions
 // are made per primitive (own-bound test + shape test), so a node test only has to be a SUPERSET of the reference's
-// float64 slab test: it may pass a box the exact test would reject, never the other way round.  This one brackets the
-// ray with float32 intervals (origin and 1/d rounded down and up once per ray) and evaluates the slab distances with
-// directed rounding: lb <= exact tNear, ub >= exact tFar on every axis.  NaNs (0*inf) compare false and therefore pass.
-struct RayF32 { float olo[3], ohi[3], ilo[3], ihi[3]; };
+// float64 slab test (bounds.go:149-185) applied to any primitive bound inside the box: it may pass a box the exact test
+// would reject, never the other way round.  Per axis, with s = sign(1/d):
+//   dn = RD(s*b_near - s*o) <= s*(B_near - o),  lb = RD(dn * RD|1/d|)      (a lower bound of the exact tNear when dn >= 0)
+//   df = RU(s*b_far  - s*o) >= s*(B_far  - o),  ub = RU(df * RU|1/d|)      (an upper bound of the exact tFar  when df >= 0)
+// for every primitive bound B inside the node box b.  The two cases the magnitudes do not cover are harmless:
+//   dn < 0: lb is merely <= 0; a non-positive tNear can only reject through "tNear > tFar" with tFar < 0, where the exact
+//           test fails its own "tMax > 0" — or through "tNear >= r.TMax", which needs r.TMax <= 0: such rays are retired
+//           before traversal (no shape test can return a hit with t <= 0);
+//   df < 0: every primitive inside has an exact tFar < 0 on this axis and fails "tMax > 0" in the reference.
+// NaNs (0*inf, inf-inf) compare false and therefore pass, as they do in the reference's comparisons.
+struct RayF32 {
+  float c_lo[3], c_hi[3];    // RD(-s*o), RU(-s*o)
+  float ia_lo[3], ia_hi[3];  // RD|1/d|, RU|1/d|
+  float sgn[3];              // s = -1 where 1/d < 0 (bounds.go:150: dirIsNeg), else +1
+};
 GP_D RayF32 ray_f32(V3 o, V3 invd) {
   RayF32 r;
-  r.olo[0] = __double2float_rd(o.x); r.ohi[0] = __double2float_ru(o.x);
-  r.olo[1] = __double2float_rd(o.y); r.ohi[1] = __double2float_ru(o.y);
-  r.olo[2] = __double2float_rd(o.z); r.ohi[2] = __double2float_ru(o.z);
-  r.ilo[0] = __double2float_rd(invd.x); r.ihi[0] = __double2float_ru(invd.x);
-  r.ilo[1] = __double2float_rd(invd.y); r.ihi[1] = __double2float_ru(invd.y);
-  r.ilo[2] = __double2float_rd(invd.z); r.ihi[2] = __double2float_ru(invd.z);
+  const double oo[3] = {o.x, o.y, o.z}, ii[3] = {invd.x, invd.y, invd.z};
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    const bool neg = ii[k] < 0;
+    const double so = neg ? oo[k] : -oo[k];  // -s*o
+    r.c_lo[k] = __double2float_rd(so);
+    r.c_hi[k] = __double2float_ru(so);
+    const double ia = fabs(ii[k]);
+    r.ia_lo[k] = __double2float_rd(ia);
+    r.ia_hi[k] = __double2float_ru(ia);
+    r.sgn[k] = neg ? -1.f : 1.f;
+  }
   return r;
 }
-GP_D void slab_axis_f32(float bmin, float bmax, float olo, float ohi, float ilo, float ihi, int neg, float* near_lb, float* far_ub) {
-  float nlo = __fsub_rd(bmin, ohi);  // <= (exact box min - exact origin)
-  float nhi = __fsub_ru(bmax, olo);  // >= (exact box max - exact origin)
-  if (!neg) {  // 1/d >= 0: near plane = min, far plane = max
-    *near_lb = __fmul_rd(nlo, nlo >= 0.f ? ilo : ihi);
-    *far_ub = __fmul_ru(nhi, nhi >= 0.f ? ihi : ilo);
-  } else {     // 1/d < 0: near plane = max, far plane = min
-    *near_lb = __fmul_rd(nhi, nhi >= 0.f ? ilo : ihi);
-    *far_ub = __fmul_ru(nlo, nlo >= 0.f ? ihi : ilo);
-  }
-}
 GP_D bool slab_test_f32_maybe(float4 n0, float4 n1, const RayF32& r, int nx, int ny, int nz, float tmax_ub) {
-  float a0, b0, a1, b1, a2, b2;
-  slab_axis_f32(n0.x, n1.x, r.olo[0], r.ohi[0], r.ilo[0], r.ihi[0], nx, &a0, &b0);
-  slab_axis_f32(n0.y, n1.y, r.olo[1], r.ohi[1], r.ilo[1], r.ihi[1], ny, &a1, &b1);
-  slab_axis_f32(n0.z, n1.z, r.olo[2], r.ohi[2], r.ilo[2], r.ihi[2], nz, &a2, &b2);
-  float tnear = fmaxf(fmaxf(a0, a1), a2);  // fmaxf/fminf drop NaNs: an unknown axis only loosens the bracket
-  float tfar = fminf(fminf(b0, b1), b2);
+  // near / far plane per axis (bounds.go:151-152: bounds[dirIsNeg] / bounds[1 - dirIsNeg])
+  const float nxp = nx ? n1.x : n0.x, fxp = nx ? n0.x : n1.x;
+  const float nyp = ny ? n1.y : n0.y, fyp = ny ? n0.y : n1.y;
+  const float nzp = nz ? n1.z : n0.z, fzp = nz ? n0.z : n1.z;
+  const float a0 = __fmul_rd(__fmaf_rd(nxp, r.sgn[0], r.c_lo[0]), r.ia_lo[0]);
+  const float a1 = __fmul_rd(__fmaf_rd(nyp, r.sgn[1], r.c_lo[1]), r.ia_lo[1]);
+  const float a2 = __fmul_rd(__fmaf_rd(nzp, r.sgn[2], r.c_lo[2]), r.ia_lo[2]);
+  const float b0 = __fmul_ru(__fmaf_ru(fxp, r.sgn[0], r.c_hi[0]), r.ia_hi[0]);
+  const float b1 = __fmul_ru(__fmaf_ru(fyp, r.sgn[1], r.c_hi[1]), r.ia_hi[1]);
+  const float b2 = __fmul_ru(__fmaf_ru(fzp, r.sgn[2], r.c_hi[2]), r.ia_hi[2]);
+  const float tnear = fmaxf(fmaxf(a0, a1), a2);  // fmaxf/fminf drop NaNs: an unknown axis only loosens the bracket
+  const float tfar = fminf(fminf(b0, b1), b2);
   // reject only what the exact test is certain to reject: near > far on some axis pair, tMin >= r.TMax, or tMax <= 0
-  if (tnear > tfar) return false;
-  if (tnear >= tmax_ub) return false;
-  if (tfar <= 0.f) return false;
-  return true;
+  return !(tnear > tfar) & !(tnear >= tmax_ub) & !(tfar <= 0.f);
 }
 
 // OffsetRayOrigin (ray.go:57-74)

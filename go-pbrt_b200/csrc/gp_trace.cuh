@@ -127,8 +127,11 @@ GP_D int quad_step(const DevScene& sc, unsigned& cur_a, unsigned& cur_b, bool& h
 //         DirectLighting / UniformSampleAll, whose per-light segments are summed in light order by the shade stage.
 // MODE 2: any hit over the render's ShadowRec queue, resolved in place: an unoccluded segment adds its deferred light
 //         sample to the lane's radiance (L.AddAssign(Ld), path.go:86).
+#ifndef GP_TRACE_BLOCKS
+#define GP_TRACE_BLOCKS 4
+#endif
 template <int MODE, bool COUNT>
-__global__ void __launch_bounds__(kTraceThreads, 4) k_trace(DevScene sc, RayRec* __restrict__ rays, const ShadowRec* __restrict__ srays,
+__global__ void __launch_bounds__(kTraceThreads, GP_TRACE_BLOCKS) k_trace(DevScene sc, RayRec* __restrict__ rays, const ShadowRec* __restrict__ srays,
                                                             PathRec* __restrict__ paths, unsigned char* __restrict__ occluded,
                                                             const int* __restrict__ queue, const int* __restrict__ count, long long n_direct,
                                                             int stack_cap, int* work_counter, TraceCounters* ctr, unsigned long long* gt10_counter) {
@@ -153,6 +156,7 @@ __global__ void __launch_bounds__(kTraceThreads, 4) k_trace(DevScene sc, RayRec*
   V3 invd;
   int nx = 0, ny = 0, nz = 0, sp = 0, rec = -1, pending = -1, rec_cls = 0;
   unsigned cur_a = 0, cur_b = 0, leaf_a = 0, leaf_n = 0, leaf_i = 0;
+  unsigned leaf2_a = 0, leaf2_n = 0;  // a second leaf, found while other lanes of the warp were still looking for their first
   bool have_cur = false;  // (cur_a, cur_b) = record words of a node whose box has already passed
   TriRay tray;
   tray.kx = tray.ky = tray.kz = 0; tray.Sx = tray.Sy = tray.Sz = 0;
@@ -202,7 +206,10 @@ __global__ void __launch_bounds__(kTraceThreads, 4) k_trace(DevScene sc, RayRec*
           tmax_ub = __double2float_ru(ray.tmax);
           sp = 0; rec = -1; hit_any = false; pending = -1; leaf_n = 0; leaf_i = 0;
           have_cur = false;
-          if (sc.n_nodes > 0) {  // the root's own box (bvh.go:673-675)
+          leaf2_n = 0;
+          // r.TMax <= 0 (or NaN): no shape test can return a hit (every one of them rejects t <= 0 and t >= tMax) and the
+          // reference's root test already fails tMin < r.TMax unless the origin is inside — the ray is a miss without traversal
+          if (sc.n_nodes > 0 && ray.tmax > 0) {  // the root's own box (bvh.go:673-675)
             float4 r0 = __ldg(sc.nodes), r1 = __ldg(sc.nodes + 1);
             if (COUNT) c.nodes++;
             if (slab_test_f32_maybe(r0, r1, rf, nx, ny, nz, tmax_ub)) { cur_a = __float_as_uint(r0.w); cur_b = __float_as_uint(r1.w); have_cur = true; }
@@ -218,25 +225,47 @@ __global__ void __launch_bounds__(kTraceThreads, 4) k_trace(DevScene sc, RayRec*
     }
     // ---- phase 1: descend to the next leaf (lanes that still have leaf candidates or a deferred test skip this).
     //      One step (quad_step) fetches the 128-byte group of the current node's grandchildren and tests their boxes.
-    if (leaf_i >= leaf_n && pending < 0) {
-      leaf_n = 0; leaf_i = 0;
-      // at most kDescendSteps node steps per round: lanes that already hold a leaf are not kept waiting for the one lane
-      // with a long descent (it simply continues in the next round)
-      for (int step = 0; step < kDescendSteps && have_cur; step++) {
-        unsigned np = cur_b >> 8;
-        if (np > 0) {  // a leaf: hand it to phase 2, continue from the stack afterwards
-          leaf_a = cur_a; leaf_n = np;
-          if (sp > 0) { --sp; cur_a = stack[(2 * sp) * stride]; cur_b = stack[(2 * sp + 1) * stride]; }
-          else have_cur = false;
-          break;
+    //      The warp leaves the phase once no lane is still LOOKING for a leaf; until then a lane that has found its leaf
+    //      keeps descending to its next one (leaf2) instead of idling.  That is speculative only in the sense that the
+    //      first leaf may shorten tMax: every candidate of the second leaf is still tested against the running tMax,
+    //      and the closest hit over all candidates does not depend on the order the leaves were reached in (exact t
+    //      ties aside, which no two tree layouts agree on anyway).
+    {
+      const bool in_leaf = leaf_i < leaf_n || pending >= 0;
+      if (!in_leaf) {
+        leaf_i = 0;
+        if (leaf2_n) { leaf_a = leaf2_a; leaf_n = leaf2_n; leaf2_n = 0; }  // (left over when a parked sphere/disk test cut phase 2 short)
+        else leaf_n = 0;
+      }
+      for (int step = 0; step < kDescendSteps; step++) {
+        const bool looking = has_ray && !in_leaf && leaf_n == 0 && have_cur;
+        if (__ballot_sync(FULL, looking) == 0) break;
+#ifdef GP_NO_SPEC
+        if (looking) {
+#else
+        if (has_ray && !in_leaf && have_cur && leaf2_n == 0) {
+#endif
+          unsigned np = cur_b >> 8;
+          if (np > 0) {  // a leaf: keep it for phase 2, continue from the stack
+            if (leaf_n == 0) { leaf_a = cur_a; leaf_n = np; }
+            else { leaf2_a = cur_a; leaf2_n = np; }
+            if (sp > 0) { --sp; cur_a = stack[(2 * sp) * stride]; cur_b = stack[(2 * sp + 1) * stride]; }
+            else have_cur = false;
+          } else {
+            int tested = quad_step(sc, cur_a, cur_b, have_cur, sp, stack, stride, stack_cap, rf, nx, ny, nz, tmax_ub, ovf);
+            if (COUNT) c.nodes += tested;
+          }
         }
-        int tested = quad_step(sc, cur_a, cur_b, have_cur, sp, stack, stride, stack_cap, rf, nx, ny, nz, tmax_ub, ovf);
-        if (COUNT) c.nodes += tested;
       }
     }
     // ---- phase 2: the leaf's candidates in order; triangles are tested here, a sphere/disk candidate is parked in
     //      `pending` (the lane stops at it, so the per-ray test order and running tMax stay the reference's)
-    while (pending < 0 && leaf_i < leaf_n) {
+    for (;;) {
+      if (pending >= 0) break;
+      if (leaf_i >= leaf_n) {
+        if (leaf2_n == 0) break;
+        leaf_a = leaf2_a; leaf_n = leaf2_n; leaf_i = 0; leaf2_n = 0;
+      }
       unsigned ri = leaf_a + leaf_i;
       leaf_i++;
       const PrimRec* prec = sc.recs + ri;
@@ -255,7 +284,7 @@ __global__ void __launch_bounds__(kTraceThreads, 4) k_trace(DevScene sc, RayRec*
         double t;
         if (tri_test_pre(p0, p1, p2, ray, tray, &t, nullptr)) {
           hit_any = true;
-          if (ANY) { have_cur = false; leaf_i = leaf_n; break; }
+          if (ANY) { have_cur = false; leaf_i = leaf_n; leaf2_n = 0; break; }
           ray.tmax = t;  // r.TMax = tHit (primitive.go:51)
           tmax_ub = __double2float_ru(t);
           rec = (int)ri;
@@ -271,14 +300,14 @@ __global__ void __launch_bounds__(kTraceThreads, 4) k_trace(DevScene sc, RayRec*
     // ---- phase 3: the parked sphere/disk tests, run together once enough lanes hold one or nobody else can advance
     {
       unsigned pm = __ballot_sync(FULL, pending >= 0);
-      unsigned runnable = __ballot_sync(FULL, has_ray && pending < 0 && !(!have_cur && leaf_i >= leaf_n));
+      unsigned runnable = __ballot_sync(FULL, has_ray && pending < 0 && !(!have_cur && leaf_i >= leaf_n && leaf2_n == 0));
       if (pm != 0 && (__popc(pm) >= kQuadricBatch || runnable == 0)) {
         if (pending >= 0) {
           const PrimRec* prec = sc.recs + pending;
           double t;
           if (quadric_test(sc, prec, prec->flags, ray, &t, bad)) {
             hit_any = true;
-            if (ANY) { have_cur = false; leaf_i = leaf_n; }
+            if (ANY) { have_cur = false; leaf_i = leaf_n; leaf2_n = 0; }
             else { ray.tmax = t; tmax_ub = __double2float_ru(t); rec = pending; rec_cls = (int)((prec->flags & RF_CLASS_MASK) >> RF_CLASS_SHIFT); }
           }
           pending = -1;
@@ -286,7 +315,7 @@ __global__ void __launch_bounds__(kTraceThreads, 4) k_trace(DevScene sc, RayRec*
       }
     }
     // ---- retire finished rays
-    bool retire = has_ray && !have_cur && leaf_i >= leaf_n && pending < 0;
+    bool retire = has_ray && !have_cur && leaf_i >= leaf_n && leaf2_n == 0 && pending < 0;
     if (retire) {
       if (MODE == 0) {
         double2 out;
@@ -340,7 +369,7 @@ GP_D bool trace_single(const DevScene& sc, Ray& ray, int* rec_out, int* cls_out,
   int sp = 0;
   unsigned cur_a = 0, cur_b = 0;
   bool have_cur = false;
-  if (sc.n_nodes > 0) {
+  if (sc.n_nodes > 0 && ray.tmax > 0) {
     float4 r0 = __ldg(sc.nodes), r1 = __ldg(sc.nodes + 1);
     if (slab_test_f32_maybe(r0, r1, rf, nx, ny, nz, __double2float_ru(ray.tmax))) { cur_a = __float_as_uint(r0.w); cur_b = __float_as_uint(r1.w); have_cur = true; }
   }

@@ -440,6 +440,9 @@ static inline void bsdf_sample_f(const BSDF& b, V3 woWorld, P2 u, int type, RGB*
   *f = ff; *wi = w; *pdf = p; *sampled = st;
 }
 
+// debug aid (ORACLE_TRACE=<file>, single-threaded renders only): one line per scene.Intersect / EstimateDirect event
+static FILE* g_trace = nullptr;
+
 struct RenderStats {
   uint64_t camera_rays = 0, closest_rays = 0, shadow_rays = 0, dead_mis_rays = 0;
   uint64_t nodes = 0, prims = 0, snodes = 0, sprims = 0;
@@ -651,6 +654,9 @@ static inline RGB estimate_direct(const Scene& sc, const Hit& h, const BSDF& bsd
     RGB f = bsdf_f(bsdf, h.wo, ls.wi, flags);
     f = smuls(f, absdot(ls.wi, h.ns));
     double scatteringPdf = bsdf_pdf(bsdf, h.wo, ls.wi, flags);
+    if (g_trace)
+      fprintf(g_trace, "  E pdf=%a Li=%a f=%a,%a,%a wi=%a,%a,%a ng=%a,%a,%a wo=%a,%a,%a ns=%a,%a,%a p=%a,%a,%a u=%a,%a shadow=%d\n", ls.pdf, ls.Li.c[0], f.c[0], f.c[1], f.c[2],
+              ls.wi.x, ls.wi.y, ls.wi.z, bsdf.ng.x, bsdf.ng.y, bsdf.ng.z, h.wo.x, h.wo.y, h.wo.z, h.ns.x, h.ns.y, h.ns.z, h.p.x, h.p.y, h.p.z, uLight.x, uLight.y, (int)!sblack(f));
     if (!sblack(f)) {
       RGB Li = ls.Li;
       Ray sr = spawn_ray_to(ref, ls.p1, h.time);  // VisibilityTester.Unoccluded (light.go:46-48)
@@ -710,6 +716,7 @@ static inline RGB path_li(const Scene& sc, Ray ray, Sampler& smp, const Integ& i
     st->closest_rays++;
     bool found = scene_intersect(sc, ray, &isect, &ts);
     st->nodes += ts.nodes; st->prims += ts.prims;
+    if (g_trace) fprintf(g_trace, "C sample=%d bounce=%d found=%d prim=%d shadow_so_far=%llu\n", smp.idx, bounces, (int)found, found ? isect.prim : -1, (unsigned long long)st->shadow_rays);
     // emission (path.go:48-63) is identically zero
     if (!found || bounces >= ig.maxDepth) break;
     BSDF bsdf;
@@ -893,6 +900,8 @@ struct RenderOpts {
 // pbrt.Render + renderWorker (integrator.go:228-350)
 static inline void render(const Scene& sc, const gopbrt_camera& cam, const gopbrt_sampler& scfg, const gopbrt_integrator& icfg,
                           const gopbrt_film& fcfg, const RenderOpts& opt, double* film, RenderStats* stats_out) {
+  g_trace = nullptr;
+  if (const char* tp = getenv("ORACLE_TRACE")) if (opt.threads <= 1) g_trace = fopen(tp, "w");
   FilmCfg fc = film_cfg(fcfg);
   Bounds2i sb = fc.cropped;  // GetSampleBounds returns CroppedPixelBounds (film.go:84-95)
   int64_t ts = icfg.tile_size;
@@ -956,6 +965,7 @@ static inline void render(const Scene& sc, const gopbrt_camera& cam, const gopbr
     for (auto* t : all) film_merge(fc, *t, film);
   }
   if (stats_out) *stats_out = total;
+  if (g_trace) { fclose(g_trace); g_trace = nullptr; }
 }
 
 }  // namespace oracle
