@@ -17,7 +17,7 @@ MAP_UV, MAP_PLANAR = 0, 1
 LIGHT_DISTANT, LIGHT_POINT, LIGHT_DIFFUSE_AREA = 0, 1, 2
 SAMPLER_STRATIFIED, SAMPLER_RANDOM = 0, 1
 MODE_STRICT, MODE_FAST = 0, 1
-FLAG_COUNT_TRAVERSAL, FLAG_FAIL_ON_PANIC, FLAG_TIME_KERNELS, FLAG_TAIL = 1, 2, 4, 8
+FLAG_COUNT_TRAVERSAL, FLAG_FAIL_ON_PANIC, FLAG_TIME_KERNELS = 1, 2, 4
 
 d16 = C.c_double * 16
 d3 = C.c_double * 3
@@ -106,8 +106,8 @@ class Stats(C.Structure):
                 ("bvh_nodes", C.c_uint64), ("bvh_depth", C.c_uint64), ("tests_triangle", C.c_uint64),
                 ("tests_sphere_fast", C.c_uint64), ("tests_general", C.c_uint64), ("extend_launches", C.c_uint64),
                 ("shadow_launches", C.c_uint64), ("shadow_tests_triangle", C.c_uint64),
-                ("shadow_tests_sphere_fast", C.c_uint64), ("shadow_tests_general", C.c_uint64), ("tail_launches", C.c_uint64),
-                ("ms_tail", C.c_double), ("root_culled_rays", C.c_uint64)]
+                ("shadow_tests_sphere_fast", C.c_uint64), ("shadow_tests_general", C.c_uint64), ("reserved0", C.c_uint64),
+                ("reserved1", C.c_double), ("root_culled_rays", C.c_uint64)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}

@@ -36,7 +36,8 @@ struct gopbrt_ctx {
   // device work of concurrent calls — each gRPC request of the reference renders on its own goroutine with its own scene,
   // SURVEY §8b — is serialised per context; gopbrt_cancel stays lock-free.
   std::mutex run_mu;
-  int grid_gen = 0, grid_shade[3] = {0, 0, 0}, grid_tail = 0;  // persistent grids of this device (SMs x resident CTAs)
+  int grid_gen = 0, grid_shade[3] = {0, 0, 0};  // persistent grids of this device (SMs x resident CTAs)
+  size_t trace_smem_limit = 0;  // largest dynamic shared memory size the traversal kernels have been opted into (> 48 KB only)
 };
 
 #define GP_CUDA(ctx, call)                                                                               \
@@ -102,6 +103,7 @@ struct gopbrt_scene {
   gopbrt_ctx* ctx = nullptr;
   DevScene dev{};
   DevBuf<gpbvh::Node32> nodes;
+  DevBuf<gpbvh::Node32> flat;  // small scenes: the flat aggregate's table (k_trace_flat)
   DevBuf<PrimRec> recs;
   DevBuf<double> rec_bounds;
   DevBuf<int4> prims;
@@ -377,6 +379,23 @@ extern "C" int gopbrt_scene_create(gopbrt_ctx* ctx, const gopbrt_scene_desc* d, 
   }
   });
 
+  // ---- flat aggregate (scenes of at most kFlatMax primitives): one table entry per leaf-ordered record, triangles first
+  std::vector<gpbvh::Node32> flat;
+  unsigned long long flat_tri_mask = 0;
+  if (np > 0 && np <= kFlatMax && !getenv("GOPBRT_NO_FLAT")) {
+    for (int pass = 0; pass < 2; pass++)
+      for (int64_t r = 0; r < np; r++) {
+        const bool tri = (recs[r].flags & RK_KIND_MASK) == RK_TRIANGLE;
+        if (tri != (pass == 0)) continue;
+        gpbvh::Node32 e;
+        for (int k = 0; k < 3; k++) { e.mn[k] = gpbvh::round_down(rec_bounds[6 * (size_t)r + k]); e.mx[k] = gpbvh::round_up(rec_bounds[6 * (size_t)r + 3 + k]); }
+        e.a = (uint32_t)r;
+        e.b = recs[r].flags;
+        if (tri) flat_tri_mask |= 1ULL << flat.size();
+        flat.push_back(e);
+      }
+  }
+
   // ---- materials / textures / lights
   std::vector<MaterialDev> mats(d->n_materials);
   for (int i = 0; i < d->n_materials; i++) {
@@ -420,7 +439,7 @@ extern "C" int gopbrt_scene_create(gopbrt_ctx* ctx, const gopbrt_scene_desc* d, 
   sc->ctx = ctx;
   cudaStream_t st = ctx->stream;
   std::vector<gpbvh::Node32>& nodes = bvh.nodes;
-  bool ok = sc->nodes.upload(nodes, st) == cudaSuccess && sc->recs.upload(recs, st) == cudaSuccess &&
+  bool ok = sc->nodes.upload(nodes, st) == cudaSuccess && sc->flat.upload(flat, st) == cudaSuccess && sc->recs.upload(recs, st) == cudaSuccess &&
             sc->rec_bounds.upload(rec_bounds, st) == cudaSuccess && sc->prims.upload(prims, st) == cudaSuccess &&
             sc->xf.upload(xf, st) == cudaSuccess && sc->xf_flags.upload(xf_flags, st) == cudaSuccess &&
             sc->spheres.upload(spheres, st) == cudaSuccess && sc->disks.upload(disks, st) == cudaSuccess &&
@@ -439,6 +458,7 @@ extern "C" int gopbrt_scene_create(gopbrt_ctx* ctx, const gopbrt_scene_desc* d, 
   D.xf = sc->xf.p; D.xf_flags = sc->xf_flags.p; D.spheres = sc->spheres.p; D.disks = sc->disks.p;
   D.materials = sc->materials.p; D.textures = sc->textures.p; D.lights = sc->lights.p; D.light_cdf = sc->light_cdf.p;
   D.n_lights = nl; D.light_func_int = func_int; D.n_nodes = (int)nodes.size();
+  D.flat = (const float4*)sc->flat.p; D.n_flat = (int)flat.size(); D.flat_tri_mask = flat_tri_mask;
   // Distant.Preprocess → Bounds3.BoundingSphere (distant.go:36-38, bounds.go:105-112)
   D.world_radius = 0;
   if (world.valid) {
@@ -457,11 +477,24 @@ extern "C" int gopbrt_scene_create(gopbrt_ctx* ctx, const gopbrt_scene_desc* d, 
   sc->trace_k[0] = k_trace<0, false>; sc->trace_k[1] = k_trace<0, true>; sc->trace_k[2] = k_trace<2, false>;
   sc->trace_k[3] = k_trace<2, true>; sc->trace_k[4] = k_trace<1, false>;
   sc->trace_k[5] = k_trace<3, false>; sc->trace_k[6] = k_trace<3, true>;
-  for (int k = 0; k < 7; k++) {
-    if (sc->trace_smem > 48 * 1024)
-      GP_CUDA(ctx, cudaFuncSetAttribute((const void*)sc->trace_k[k], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sc->trace_smem));
-    sc->trace_grid[k] = grid_for(ctx, (const void*)sc->trace_k[k], kTraceThreads, sc->trace_smem);
+  if (D.n_flat > 0) {  // small scene: the flat aggregate answers every query (no traversal stack)
+    sc->trace_k[0] = k_trace_flat<0, false>; sc->trace_k[1] = k_trace_flat<0, true>; sc->trace_k[2] = k_trace_flat<2, false>;
+    sc->trace_k[3] = k_trace_flat<2, true>; sc->trace_k[4] = k_trace_flat<1, false>;
+    sc->trace_k[5] = k_trace_flat<3, false>; sc->trace_k[6] = k_trace_flat<3, true>;
+    sc->trace_smem = 0;
   }
+  // cudaFuncAttributeMaxDynamicSharedMemorySize belongs to the kernel, not to the scene: it only ever grows (a later, shallower
+  // scene must not lower the limit under a deeper one that is still alive)
+  if (sc->trace_smem > 48 * 1024 && sc->trace_smem > ctx->trace_smem_limit) {
+    const void* ks[7] = {(const void*)k_trace<0, false>, (const void*)k_trace<0, true>, (const void*)k_trace<2, false>, (const void*)k_trace<2, true>,
+                         (const void*)k_trace<1, false>, (const void*)k_trace<3, false>, (const void*)k_trace<3, true>};
+    for (const void* k : ks) {
+      cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sc->trace_smem);
+      if (e != cudaSuccess) { ctx->last_error = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e); delete sc; return GOPBRT_ERR_CUDA; }
+    }
+    ctx->trace_smem_limit = sc->trace_smem;
+  }
+  for (int k = 0; k < 7; k++) sc->trace_grid[k] = grid_for(ctx, (const void*)sc->trace_k[k], kTraceThreads, sc->trace_smem);
   *out = sc;
   return GOPBRT_OK;
 }
@@ -773,10 +806,7 @@ static int render_impl(gopbrt_scene* sc, const gopbrt_camera* cam, const gopbrt_
     cudaEventRecord(W.events[ev_used++], st);
     ev_stage.push_back(stage);
   };
-  uint64_t n_extend = 0, n_shadow = 0, tail_used = 0;
-  // The tail kernel is bit-exact but, measured on config 2, slower than the wavefront it replaces (its lanes diverge
-  // across stages inside a warp): it stays opt-in (GOPBRT_FLAG_TAIL), off by default.
-  const int tail_lanes = (opt && (opt->flags & GOPBRT_FLAG_TAIL) && P.integrator == GOPBRT_INTEGRATOR_PATH) ? 49152 : 0;
+  uint64_t n_extend = 0, n_shadow = 0;
   // debug aid: GOPBRT_ITER_LOG=<file> synchronises every iteration and logs the queue sizes (implies per-stage timing)
   const char* iter_log_path = getenv("GOPBRT_ITER_LOG");
   std::vector<int> iter_counts, iter_shadow, iter_hits;
@@ -791,7 +821,7 @@ static int render_impl(gopbrt_scene* sc, const gopbrt_camera* cam, const gopbrt_
     // Wavefront iterations as a CUDA graph of kGraphIters iterations (6 launches each): in STRICT mode the last lanes
     // need hundreds of iterations over nearly empty queues, where the cost of an iteration IS its launch latency.
     // One graph stays queued ahead of the one the host is waiting for, so the device never idles on the host.
-    const bool use_graph = !timing && !iter_log_path && !count && tail_lanes == 0 && !getenv("GOPBRT_NO_GRAPH");
+    const bool use_graph = !timing && !iter_log_path && !count && !getenv("GOPBRT_NO_GRAPH");
     if (use_graph) {
       auto enqueue_iteration = [&]() {
         sc->trace_k[k_ext]<<<sc->trace_grid[k_ext], kTraceThreads, smem, st>>>(sc->dev, L.ray, nullptr, L.path, W.codes.p, Q.extend, Q.cnt + 0, 0, scap, Q.cnt + 6, sc->tctr.p, nullptr);
@@ -879,17 +909,6 @@ static int render_impl(gopbrt_scene* sc, const gopbrt_camera* cam, const gopbrt_
       GP_CUDA(ctx, cudaStreamSynchronize(st));
       if (*W.remaining_host == 0) break;
       if (sc->cancel.load()) { rc = GOPBRT_ERR_CANCELLED; break; }
-      if (!count && *W.remaining_host <= tail_lanes) {
-        // few lanes left: finish them one thread per lane instead of hundreds of near-empty wavefront iterations
-        tick(ST_TAIL);
-        if (!ctx->grid_tail) ctx->grid_tail = grid_for(ctx, (const void*)k_tail, 128, (size_t)kStackDepth * 128 * 2 * sizeof(unsigned));
-        const int g_tail = ctx->grid_tail;
-        size_t tsm = (size_t)scap * 128 * 2 * sizeof(unsigned);
-        k_tail<<<std::max(g_tail, ctx->sm_count * 2), 128, tsm, st>>>(sc->dev, L, P, Q, scap, W.rctr.p, sc->tctr.p);
-        ctx->launches++;
-        tail_used++;
-        break;
-      }
     }
     tick(ST_FILM);
     k_film_merge<<<g_small, 128, 0, st>>>(L, P, d_film);
@@ -919,7 +938,6 @@ static int render_impl(gopbrt_scene* sc, const gopbrt_camera* cam, const gopbrt_
     stats->lanes = (uint64_t)lanes; stats->ms_total = ms; stats->bvh_nodes = sc->bvh_nodes; stats->bvh_depth = sc->bvh_depth;
     stats->tests_triangle = tcnt.t_tri; stats->tests_sphere_fast = tcnt.t_sph; stats->tests_general = tcnt.t_gen;
     stats->extend_launches = n_extend; stats->shadow_launches = n_shadow;
-    stats->tail_launches = tail_used;
     stats->root_culled_rays = rcnt.root_culled;
     stats->shadow_tests_triangle = tcnt.st_tri; stats->shadow_tests_sphere_fast = tcnt.st_sph; stats->shadow_tests_general = tcnt.st_gen;
     if (timing && iter_log_path) {
@@ -950,7 +968,6 @@ static int render_impl(gopbrt_scene* sc, const gopbrt_camera* cam, const gopbrt_
         cudaEventElapsedTime(&t, W.events[i], W.events[i + 1]);
         acc[ev_stage[i]] += t;
       }
-      stats->ms_tail = acc[ST_TAIL];
       stats->ms_raygen = acc[ST_RAYGEN]; stats->ms_extend = acc[ST_EXTEND]; stats->ms_shade = acc[ST_SHADE];
       stats->ms_shadow = acc[ST_SHADOW]; stats->ms_film = acc[ST_FILM];
     }

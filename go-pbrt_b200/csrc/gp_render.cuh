@@ -1175,70 +1175,6 @@ __global__ void __launch_bounds__(128, 3) k_shade(DevScene sc, Lanes L, RenderPa
   if (bad) atomicAdd(&ctr->efloat_panics, 1ULL);
 }
 
-// ---------------------------------------------------------------- tail
-// Once only a few tens of thousands of lanes are still in flight the wavefront cannot fill the GPU any more: every
-// iteration then costs six nearly empty launches, and in STRICT mode the last lanes still need hundreds of iterations
-// (a pixel's samples are sequential).  The tail kernel gives each remaining lane to one thread, which runs the very
-// same per-lane steps (generate_lane, the reference-ordered traversal, shade_lane, shadow resolve) back to back until
-// the lane's tile is exhausted.  Same arithmetic, same order per lane => same film bits.
-__global__ void __launch_bounds__(128) k_tail(DevScene sc, Lanes L, RenderParams P, Queues Q, int stack_cap, RenderCounters* ctr, TraceCounters* tctr) {
-  extern __shared__ unsigned s_tail_stack[];
-  unsigned* stack = s_tail_stack + threadIdx.x;
-  const int stride = 128;
-  long long n = Q.cnt[0];
-  unsigned long long cam = 0, nans = 0, culled = 0, n_unsupported = 0, n_dead = 0, closest = 0, shadows = 0, gt10 = 0;
-  int bad = 0, ovf = 0;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    long long lane = Q.extend[i];
-    bool need_gen = false;
-    for (;;) {
-      if (need_gen && !generate_lane(sc, L, P, lane, true, cam, nans, culled)) break;
-      RayRec rr = L.ray[lane];
-      Ray ray;
-      ray.o = mk3(rr.ox, rr.oy, rr.oz); ray.d = mk3(rr.dx, rr.dy, rr.dz); ray.tmax = rr.tmax;
-      int rec = -1, cls = 0;
-      closest++;
-      trace_single<false>(sc, ray, &rec, &cls, stack, stride, stack_cap, bad, ovf);
-      if (rec < 0) { need_gen = true; continue; }  // escaped: the sample is finished (path.go:66)
-      L.ray[lane].tmax = ray.tmax;
-      L.ray[lane].hit_rec = rec;
-      L.ray[lane].pad = cls;
-      bool cont = false, finished = false, shadow = false;
-      shade_lane(sc, L, P, lane, cont, finished, shadow, n_unsupported, n_dead, bad);
-      if (shadow) {
-        shadows++;
-        ShadowRec sr = L.sray[lane];
-        Ray r2;
-        r2.o = mk3(sr.ox, sr.oy, sr.oz); r2.d = mk3(sr.dx, sr.dy, sr.dz); r2.tmax = 1 - 0.0001;
-        int r2rec = -1, r2cls = 0;
-        bool occluded = trace_single<true>(sc, r2, &r2rec, &r2cls, stack, stride, stack_cap, bad, ovf);
-        PathRec* pt = L.path + lane;
-        if (!occluded) {
-          pt->Lr += sr.pr; pt->Lg += sr.pg; pt->Lb += sr.pb;
-          if (sr.gt10) gt10++;
-        } else {
-          pt->Lr += sr.pr * 0.0; pt->Lg += sr.pg * 0.0; pt->Lb += sr.pb * 0.0;
-        }
-      }
-      need_gen = !cont;
-    }
-  }
-  cam = warp_sum(cam); nans = warp_sum(nans); culled = warp_sum(culled); n_unsupported = warp_sum(n_unsupported); n_dead = warp_sum(n_dead);
-  closest = warp_sum(closest); shadows = warp_sum(shadows); gt10 = warp_sum(gt10);
-  if ((threadIdx.x & 31) == 0) {
-    if (cam) atomicAdd(&ctr->camera_rays, cam);
-    if (nans) atomicAdd(&ctr->nan_samples, nans);
-    if (culled) atomicAdd(&ctr->root_culled, culled);
-    if (n_unsupported) atomicAdd(&ctr->unsupported, n_unsupported);
-    if (n_dead) atomicAdd(&ctr->dead_mis_rays, n_dead);
-    if (closest) atomicAdd(&ctr->closest_rays, closest);
-    if (shadows) atomicAdd(&ctr->shadow_rays, shadows);
-    if (gt10) atomicAdd(&ctr->radiance_gt10, gt10);
-  }
-  if (bad) atomicAdd(&ctr->efloat_panics, 1ULL);
-  if (ovf) atomicAdd(&tctr->stack_overflows, 1ULL);
-}
-
 // end of a wavefront iteration: rotate the queues on the device and publish the number of lanes still in flight
 __global__ void k_advance(Queues Q, RenderCounters* ctr, int* host_visible_remaining) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {

@@ -57,6 +57,11 @@ struct DevScene {
   double light_func_int;
   double world_radius;     // Distant.Preprocess (distant.go:36-38)
   int n_nodes;
+  // flat aggregate of small scenes (k_trace_flat): per primitive two float4 {min.xyz f32 rounded down, record index},
+  // {max.xyz f32 rounded up, record flags}; triangles first (bit k of flat_tri_mask set), then spheres / disks
+  const float4* flat;
+  int n_flat;
+  unsigned long long flat_tri_mask;
 };
 
 // load a transform's Matrix (inv=false) or MatrixInverse (inv=true) into registers.  Translation-only transforms are

@@ -53,6 +53,25 @@ GP_D unsigned long long warp_sum(unsigned long long v) {
   return v;
 }
 
+// ---- closest hit, order-independent (DESIGN §2 "parity spec") ----
+// The closest hit of a ray is the minimum tHit over all primitives whose own float64 bound AND shape test pass with the
+// ray's ORIGINAL tMax; two candidates with bit-identical tHit go to the lower primitive index.  The reference mutates
+// r.TMax as it goes (primitive.go:51), which gives the same hit except where two candidates' distances differ by less
+// than the rounding of the slab / shape arithmetic (coplanar faces, grazing hits within the EFloat bound): there the
+// reference's answer depends on its own tree's visit order, and so would this backend's on its tree, its flat table or
+// its traversal schedule.  Stated this way the result is a function of the ray and the scene alone.
+// The running best distance is used only to SKIP work that cannot win: nodes and candidates are culled against
+// tBest * (1 + 2^-20) — a candidate whose own bound starts beyond that is farther than the best hit by far more than
+// any rounding — never against tBest itself.
+constexpr double kCullSlack = 1.0 + 9.5367431640625e-07;  // 1 + 2^-20
+GP_D double cull_tmax(bool hit_any, double t_best, double t_orig) {
+  double c = t_best * kCullSlack;
+  return (hit_any && c < t_orig) ? c : t_orig;
+}
+GP_D bool closer_hit(const DevScene& sc, double t, unsigned ri, double t_best, int rec) {
+  return t < t_best || (t == t_best && rec >= 0 && sc.recs[ri].prim < sc.recs[rec].prim);
+}
+
 constexpr int kChunkMax = 256;     // most ray indices a warp claims with one atomicAdd (fewer when the queue is short)
 #ifndef GP_REFILL_IDLE
 #define GP_REFILL_IDLE 16
@@ -163,6 +182,7 @@ __global__ void __launch_bounds__(kTraceThreads, GP_TRACE_BLOCKS) k_trace(DevSce
   RayF32 rf;
   float tmax_ub = 0.f;
   bool hit_any = false;
+  double t_best = 0;  // closest tHit so far (ray.tmax keeps the ray's original tMax)
   long long w_next = 0, w_end = 0;  // warp-uniform chunk [w_next, w_end)
   bool exhausted = false;
 
@@ -204,6 +224,7 @@ __global__ void __launch_bounds__(kTraceThreads, GP_TRACE_BLOCKS) k_trace(DevSce
           tray = tri_ray_setup(ray.d);
           rf = ray_f32(ray.o, invd);
           tmax_ub = __double2float_ru(ray.tmax);
+          t_best = ray.tmax;
           sp = 0; rec = -1; hit_any = false; pending = -1; leaf_n = 0; leaf_i = 0;
           have_cur = false;
           leaf2_n = 0;
@@ -279,20 +300,22 @@ __global__ void __launch_bounds__(kTraceThreads, GP_TRACE_BLOCKS) k_trace(DevSce
         double x0 = p0.x < p1.x ? p0.x : p1.x, x1 = p0.x < p1.x ? p1.x : p0.x; x0 = p2.x < x0 ? p2.x : x0; x1 = p2.x > x1 ? p2.x : x1;
         double y0 = p0.y < p1.y ? p0.y : p1.y, y1 = p0.y < p1.y ? p1.y : p0.y; y0 = p2.y < y0 ? p2.y : y0; y1 = p2.y > y1 ? p2.y : y1;
         double z0 = p0.z < p1.z ? p0.z : p1.z, z1 = p0.z < p1.z ? p1.z : p0.z; z0 = p2.z < z0 ? p2.z : z0; z1 = p2.z > z1 ? p2.z : z1;
-        if (!slab_test(x0, y0, z0, x1, y1, z1, ray.o, invd, nx, ny, nz, ray.tmax)) continue;
+        if (!slab_test(x0, y0, z0, x1, y1, z1, ray.o, invd, nx, ny, nz, cull_tmax(hit_any, t_best, ray.tmax))) continue;
         if (COUNT) { c.prims++; c.tri++; }
         double t;
         if (tri_test_pre(p0, p1, p2, ray, tray, &t, nullptr)) {
-          hit_any = true;
-          if (ANY) { have_cur = false; leaf_i = leaf_n; leaf2_n = 0; break; }
-          ray.tmax = t;  // r.TMax = tHit (primitive.go:51)
-          tmax_ub = __double2float_ru(t);
-          rec = (int)ri;
-          rec_cls = (int)((flags & RF_CLASS_MASK) >> RF_CLASS_SHIFT);
+          if (ANY) { hit_any = true; have_cur = false; leaf_i = leaf_n; leaf2_n = 0; break; }
+          if (closer_hit(sc, t, ri, t_best, rec)) {
+            hit_any = true;
+            t_best = t;
+            tmax_ub = __double2float_ru(cull_tmax(true, t, ray.tmax));
+            rec = (int)ri;
+            rec_cls = (int)((flags & RF_CLASS_MASK) >> RF_CLASS_SHIFT);
+          }
         }
       } else {
         const double* bb = sc.rec_bounds + (size_t)ri * 6;
-        if (!slab_test(bb[0], bb[1], bb[2], bb[3], bb[4], bb[5], ray.o, invd, nx, ny, nz, ray.tmax)) continue;
+        if (!slab_test(bb[0], bb[1], bb[2], bb[3], bb[4], bb[5], ray.o, invd, nx, ny, nz, cull_tmax(hit_any, t_best, ray.tmax))) continue;
         if (COUNT) { c.prims++; if (flags & RF_FAST) c.sph++; else c.gen++; }
         pending = (int)ri;
       }
@@ -306,9 +329,14 @@ __global__ void __launch_bounds__(kTraceThreads, GP_TRACE_BLOCKS) k_trace(DevSce
           const PrimRec* prec = sc.recs + pending;
           double t;
           if (quadric_test(sc, prec, prec->flags, ray, &t, bad)) {
-            hit_any = true;
-            if (ANY) { have_cur = false; leaf_i = leaf_n; leaf2_n = 0; }
-            else { ray.tmax = t; tmax_ub = __double2float_ru(t); rec = pending; rec_cls = (int)((prec->flags & RF_CLASS_MASK) >> RF_CLASS_SHIFT); }
+            if (ANY) { hit_any = true; have_cur = false; leaf_i = leaf_n; leaf2_n = 0; }
+            else if (closer_hit(sc, t, (unsigned)pending, t_best, rec)) {
+              hit_any = true;
+              t_best = t;
+              tmax_ub = __double2float_ru(cull_tmax(true, t, ray.tmax));
+              rec = pending;
+              rec_cls = (int)((prec->flags & RF_CLASS_MASK) >> RF_CLASS_SHIFT);
+            }
           }
           pending = -1;
         }
@@ -319,7 +347,7 @@ __global__ void __launch_bounds__(kTraceThreads, GP_TRACE_BLOCKS) k_trace(DevSce
     if (retire) {
       if (MODE == 0) {
         double2 out;
-        out.x = ray.tmax;
+        out.x = t_best;  // tHit, or the original tMax on a miss
         out.y = __longlong_as_double((long long)(((unsigned long long)(unsigned)rec_cls << 32) | (unsigned)rec));  // {hit_rec, shade class}
         ((double2*)(rays + lane))[3] = out;
         // MODE 0 with `occluded` set: one byte per QUEUE POSITION — shade class 0..3 of the hit, 4 = escaped — so that
@@ -358,65 +386,153 @@ __global__ void __launch_bounds__(kTraceThreads, GP_TRACE_BLOCKS) k_trace(DevSce
   if (MODE == 2 && gt10) atomicAdd(gt10_counter, gt10);
 }
 
-// plain one-ray-per-thread traversal with the same per-ray visit and test order as k_trace (used by the tail kernel, where
-// too few lanes are left for the wavefront to fill the machine)
-template <bool ANY>
-GP_D bool trace_single(const DevScene& sc, Ray& ray, int* rec_out, int* cls_out, unsigned* stack, int stride, int stack_cap, int& bad, int& ovf) {
-  V3 invd = mk3(1 / ray.d.x, 1 / ray.d.y, 1 / ray.d.z);
-  int nx = invd.x < 0, ny = invd.y < 0, nz = invd.z < 0;
-  TriRay tray = tri_ray_setup(ray.d);
-  RayF32 rf = ray_f32(ray.o, invd);
-  int sp = 0;
-  unsigned cur_a = 0, cur_b = 0;
-  bool have_cur = false;
-  if (sc.n_nodes > 0 && ray.tmax > 0) {
-    float4 r0 = __ldg(sc.nodes), r1 = __ldg(sc.nodes + 1);
-    if (slab_test_f32_maybe(r0, r1, rf, nx, ny, nz, __double2float_ru(ray.tmax))) { cur_a = __float_as_uint(r0.w); cur_b = __float_as_uint(r1.w); have_cur = true; }
-  }
-  bool any = false;
-  while (have_cur) {
-    unsigned leaf_a = 0, leaf_n = 0;
-    float tub = __double2float_ru(ray.tmax);
-    while (have_cur) {
-      unsigned np = cur_b >> 8;
-      if (np > 0) {
-        leaf_a = cur_a; leaf_n = np;
-        if (sp > 0) { --sp; cur_a = stack[(2 * sp) * stride]; cur_b = stack[(2 * sp + 1) * stride]; }
-        else have_cur = false;
-        break;
-      }
-      quad_step(sc, cur_a, cur_b, have_cur, sp, stack, stride, stack_cap, rf, nx, ny, nz, tub, ovf);
+// ---- flat aggregate for small scenes ----------------------------------------------------------------------------
+// With a few dozen primitives (BASELINE configs 1 and 2: 23 and 36) a tree buys nothing on a 32-wide machine: its rays
+// leave the node loop at different steps and the warp runs at a third of its lanes.  For scenes of at most kFlatMax
+// primitives the aggregate is therefore a flat table — the brute-force list of the reference's accelerator.Simple
+// (pkg/accelerator/simple.go:47-79) behind a conservative filter: every lane tests ALL primitive bounds (float32,
+// rounded outward, the same superset test as the BVH nodes) in one warp-uniform loop over a table held in shared
+// memory, which leaves a bit mask of candidates; the candidates then get what they get in the tree: the own float64
+// bound test with the running tMax (the parity spec of SURVEY §8a) and the float64/EFloat shape test, triangles first,
+// spheres/disks after, so that the lanes of a warp run the same kind of test together.  The closest hit over the
+// candidates does not depend on the order they are tested in (exact t ties aside).
+constexpr int kFlatMax = 64;
+
+template <int MODE, bool COUNT>
+__global__ void __launch_bounds__(kTraceThreads, 4) k_trace_flat(DevScene sc, RayRec* __restrict__ rays, const ShadowRec* __restrict__ srays,
+                                                                 PathRec* __restrict__ paths, unsigned char* __restrict__ occluded,
+                                                                 const int* __restrict__ queue, const int* __restrict__ count, long long n_direct,
+                                                                 int stack_cap, int* work_counter, TraceCounters* ctr, unsigned long long* gt10_counter) {
+  constexpr bool ANY = MODE != 0;
+  __shared__ float4 s_tab[2 * kFlatMax];
+  const int nf = sc.n_flat;
+  for (int i = threadIdx.x; i < 2 * nf; i += blockDim.x) s_tab[i] = sc.flat[i];
+  __syncthreads();
+  const long long n = queue ? (long long)*count : n_direct;
+  const unsigned long long tri_mask = sc.flat_tri_mask;
+  TravCnt c = {0, 0, 0, 0, 0};
+  int bad = 0;
+  unsigned long long gt10 = 0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const long long lane = queue ? queue[i] : i;
+    Ray ray;
+    if (MODE >= 2) {
+      const double2* q = (const double2*)(srays + lane);
+      double2 a = q[0], b = q[1], c2 = q[2];
+      ray.o = mk3(a.x, a.y, b.x);
+      ray.d = mk3(b.y, c2.x, c2.y);
+      ray.tmax = 1 - 0.0001;  // 1 - ShadowEpsilon (interaction.go:99)
+    } else {
+      const double2* q = (const double2*)(rays + lane);
+      double2 a = q[0], b = q[1], c2 = q[2], d2 = q[3];
+      ray.o = mk3(a.x, a.y, b.x);
+      ray.d = mk3(b.y, c2.x, c2.y);
+      ray.tmax = d2.x;
     }
-    for (unsigned i = 0; i < leaf_n; i++) {
-      unsigned ri = leaf_a + i;
-      const PrimRec* prec = sc.recs + ri;
-      uint32_t flags = prec->flags;
-      double t;
-      bool hit;
-      if ((flags & RK_KIND_MASK) == RK_TRIANGLE) {
-        const double2* q = (const double2*)prec;
+    const V3 invd = mk3(1 / ray.d.x, 1 / ray.d.y, 1 / ray.d.z);  // bvh.go:665-666
+    const int nx = invd.x < 0, ny = invd.y < 0, nz = invd.z < 0;
+    const RayF32 rf = ray_f32(ray.o, invd);
+    float tmax_ub = __double2float_ru(ray.tmax);
+    unsigned long long mask = 0;
+    if (ray.tmax > 0) {  // see k_trace: a ray with tMax <= 0 (or NaN) cannot hit anything
+#pragma unroll 4
+      for (int k = 0; k < nf; k++)
+        mask |= (unsigned long long)slab_test_f32_maybe(s_tab[2 * k], s_tab[2 * k + 1], rf, nx, ny, nz, tmax_ub) << k;
+      if (COUNT) c.nodes += nf;
+    }
+    int rec = -1, rec_cls = 0;
+    bool hit_any = false;
+    double t_best = ray.tmax;  // see closer_hit: ray.tmax keeps the original tMax
+    // triangles
+    unsigned long long m = mask & tri_mask;
+    if (m) {
+      const TriRay tray = tri_ray_setup(ray.d);
+      while (m) {
+        const int k = __ffsll((long long)m) - 1;
+        m &= m - 1;
+        const float4 t0 = s_tab[2 * k], t1 = s_tab[2 * k + 1];
+        if (!ANY && hit_any && !slab_test_f32_maybe(t0, t1, rf, nx, ny, nz, tmax_ub)) continue;  // behind the hit found meanwhile
+        const unsigned ri = __float_as_uint(t0.w);
+        const double2* q = (const double2*)(sc.recs + ri);
         double2 v0 = q[0], v1 = q[1], v2 = q[2], v3 = q[3], v4 = q[4];
         V3 p0 = mk3(v0.y, v1.x, v1.y), p1 = mk3(v2.x, v2.y, v3.x), p2 = mk3(v3.y, v4.x, v4.y);
-        double x0 = fmin(fmin(p0.x, p1.x), p2.x), x1 = fmax(fmax(p0.x, p1.x), p2.x);
-        double y0 = fmin(fmin(p0.y, p1.y), p2.y), y1 = fmax(fmax(p0.y, p1.y), p2.y);
-        double z0 = fmin(fmin(p0.z, p1.z), p2.z), z1 = fmax(fmax(p0.z, p1.z), p2.z);
-        if (!slab_test(x0, y0, z0, x1, y1, z1, ray.o, invd, nx, ny, nz, ray.tmax)) continue;
-        hit = tri_test_pre(p0, p1, p2, ray, tray, &t, nullptr);
-      } else {
-        const double* bb = sc.rec_bounds + (size_t)ri * 6;
-        if (!slab_test(bb[0], bb[1], bb[2], bb[3], bb[4], bb[5], ray.o, invd, nx, ny, nz, ray.tmax)) continue;
-        hit = quadric_test(sc, prec, flags, ray, &t, bad);
+        double x0 = p0.x < p1.x ? p0.x : p1.x, x1 = p0.x < p1.x ? p1.x : p0.x; x0 = p2.x < x0 ? p2.x : x0; x1 = p2.x > x1 ? p2.x : x1;
+        double y0 = p0.y < p1.y ? p0.y : p1.y, y1 = p0.y < p1.y ? p1.y : p0.y; y0 = p2.y < y0 ? p2.y : y0; y1 = p2.y > y1 ? p2.y : y1;
+        double z0 = p0.z < p1.z ? p0.z : p1.z, z1 = p0.z < p1.z ? p1.z : p0.z; z0 = p2.z < z0 ? p2.z : z0; z1 = p2.z > z1 ? p2.z : z1;
+        if (!slab_test(x0, y0, z0, x1, y1, z1, ray.o, invd, nx, ny, nz, cull_tmax(hit_any, t_best, ray.tmax))) continue;
+        if (COUNT) { c.prims++; c.tri++; }
+        double t;
+        if (tri_test_pre(p0, p1, p2, ray, tray, &t, nullptr)) {
+          if (ANY) { hit_any = true; break; }
+          if (closer_hit(sc, t, ri, t_best, rec)) {
+            hit_any = true;
+            t_best = t;
+            tmax_ub = __double2float_ru(cull_tmax(true, t, ray.tmax));
+            rec = (int)ri;
+            rec_cls = (int)((__float_as_uint(t1.w) & RF_CLASS_MASK) >> RF_CLASS_SHIFT);
+          }
+        }
       }
-      if (hit) {
-        if (ANY) return true;
-        any = true;
-        ray.tmax = t;
-        *rec_out = (int)ri;
-        *cls_out = (int)((flags & RF_CLASS_MASK) >> RF_CLASS_SHIFT);
+    }
+    // spheres and disks
+    m = (ANY && hit_any) ? 0ULL : (mask & ~tri_mask);
+    while (m) {
+      const int k = __ffsll((long long)m) - 1;
+      m &= m - 1;
+      const float4 t0 = s_tab[2 * k], t1 = s_tab[2 * k + 1];
+      if (!ANY && hit_any && !slab_test_f32_maybe(t0, t1, rf, nx, ny, nz, tmax_ub)) continue;
+      const unsigned ri = __float_as_uint(t0.w);
+      const uint32_t flags = __float_as_uint(t1.w);
+      const double* bb = sc.rec_bounds + (size_t)ri * 6;
+      if (!slab_test(bb[0], bb[1], bb[2], bb[3], bb[4], bb[5], ray.o, invd, nx, ny, nz, cull_tmax(hit_any, t_best, ray.tmax))) continue;
+      if (COUNT) { c.prims++; if (flags & RF_FAST) c.sph++; else c.gen++; }
+      double t;
+      if (quadric_test(sc, sc.recs + ri, flags, ray, &t, bad)) {
+        if (ANY) { hit_any = true; break; }
+        if (closer_hit(sc, t, ri, t_best, rec)) {
+          hit_any = true;
+          t_best = t;
+          tmax_ub = __double2float_ru(cull_tmax(true, t, ray.tmax));
+          rec = (int)ri;
+          rec_cls = (int)((flags & RF_CLASS_MASK) >> RF_CLASS_SHIFT);
+        }
+      }
+    }
+    // retire (same record layout as k_trace)
+    if (MODE == 0) {
+      double2 out;
+      out.x = t_best;
+      out.y = __longlong_as_double((long long)(((unsigned long long)(unsigned)rec_cls << 32) | (unsigned)rec));
+      ((double2*)(rays + lane))[3] = out;
+      if (occluded) occluded[i] = rec >= 0 ? (unsigned char)rec_cls : (unsigned char)4;
+    } else if (MODE == 1 || MODE == 3) {
+      occluded[lane] = hit_any ? 1 : 0;
+    } else {
+      const ShadowRec* sr = srays + lane;
+      PathRec* pt = paths + lane;
+      double pr = sr->pr, pg = sr->pg, pb = sr->pb;
+      if (!hit_any) {
+        pt->Lr += pr; pt->Lg += pg; pt->Lb += pb;
+        if (sr->gt10) gt10++;
+      } else if (!sr->pad) {
+        pt->Lr += pr * 0.0; pt->Lg += pg * 0.0; pt->Lb += pb * 0.0;
       }
     }
   }
-  return any;
+  if (COUNT) {
+    c.nodes = warp_sum(c.nodes); c.prims = warp_sum(c.prims); c.tri = warp_sum(c.tri); c.sph = warp_sum(c.sph); c.gen = warp_sum(c.gen);
+    if ((threadIdx.x & 31) == 0) {
+      if (ANY) {
+        atomicAdd(&ctr->snodes, c.nodes); atomicAdd(&ctr->sprims, c.prims);
+        atomicAdd(&ctr->st_tri, c.tri); atomicAdd(&ctr->st_sph, c.sph); atomicAdd(&ctr->st_gen, c.gen);
+      } else {
+        atomicAdd(&ctr->nodes, c.nodes); atomicAdd(&ctr->prims, c.prims);
+        atomicAdd(&ctr->t_tri, c.tri); atomicAdd(&ctr->t_sph, c.sph); atomicAdd(&ctr->t_gen, c.gen);
+      }
+    }
+  }
+  if (bad) atomicAdd(&ctr->efloat_panics, 1ULL);
+  if (MODE == 2 && gt10) atomicAdd(gt10_counter, gt10);
 }
 
 // SoA <-> record packing for the batched API (host arrays are SoA float64)

@@ -195,8 +195,8 @@ typedef struct {
 enum {
   GOPBRT_FLAG_COUNT_TRAVERSAL = 1, /* instrumented kernels: count BVH nodes visited / primitive tests */
   GOPBRT_FLAG_FAIL_ON_PANIC = 2,   /* return GOPBRT_ERR_REFERENCE_PANIC instead of counting           */
-  GOPBRT_FLAG_TIME_KERNELS = 4,    /* CUDA-event time every stage launch (fills ms_raygen … ms_tail)   */
-  GOPBRT_FLAG_TAIL = 8,            /* finish the last <= 49152 lanes with the one-thread-per-lane tail kernel */
+  GOPBRT_FLAG_TIME_KERNELS = 4,    /* CUDA-event time every stage launch (fills ms_raygen … ms_film)   */
+  /* 8: reserved (was GOPBRT_FLAG_TAIL in ABI 1 drafts; ignored) */
   /* bits 8..15: GOPBRT_MODE_FAST only — lane groups per pixel tile (each group renders every n-th sample of the
    * rank's share, into its own FilmTile; the groups are merged in ascending order).  0 = automatic. */
   GOPBRT_FLAG_GROUPS_SHIFT = 8,
@@ -229,8 +229,8 @@ typedef struct {
   uint64_t tests_triangle, tests_sphere_fast, tests_general; /* closest-hit shape tests by record kind (COUNT_TRAVERSAL) */
   uint64_t extend_launches, shadow_launches;
   uint64_t shadow_tests_triangle, shadow_tests_sphere_fast, shadow_tests_general; /* any-hit, same split */
-  uint64_t tail_launches;      /* 1 if the frame's last lanes were finished by the tail kernel */
-  double ms_tail;
+  uint64_t reserved0;          /* (was tail_launches; always 0) */
+  double reserved1;            /* (was ms_tail; always 0) */
   uint64_t root_culled_rays;   /* closest_rays answered by the BVH-root slab test inside raygen (never reach the extend kernel) */
 } gopbrt_stats;
 

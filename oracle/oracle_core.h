@@ -729,11 +729,68 @@ static inline void build_accel(Scene& sc) {
 
 struct TravStats { uint64_t nodes = 0, prims = 0; };
 
-// BVH.Intersect (bvh.go:659-712).  accel_mode 0 keeps the reference's fixed [64] stack: an overflow is where Go
-// would panic with index-out-of-range — counted, traversal abandoned.
+// Closest hit of accel modes 1 (own tree) and 2 (brute force): the ORDER-INDEPENDENT statement of the parity spec
+//  — over all primitives whose own float64 bound and shape test pass with the ray's ORIGINAL tMax,
+// the minimum tHit; bit-identical tHit goes to the lower primitive index.  It equals the reference's running-tMax rule
+// (primitive.go:51, kept verbatim in accel mode 0 below) except where two candidates' distances differ by less than the
+// rounding of the slab / shape arithmetic — coplanar faces, grazing hits within the EFloat bound — where the reference's
+// answer depends on its own tree's visit order.  The running best distance only culls what cannot win, with a 2^-20 slack.
+static inline bool scene_intersect_canonical(const Scene& sc, Ray& ray, Hit* hit, TravStats* ts, V3 invd, const int neg[3]) {
+  const double t_orig = ray.tmax, slack = 1.0 + 9.5367431640625e-07;
+  double t_best = t_orig;
+  int best = -1;
+  Hit best_hit;
+  auto cull_ray = [&]() {
+    Ray rc = ray;
+    double c = t_best * slack;
+    rc.tmax = (best >= 0 && c < t_orig) ? c : t_orig;
+    return rc;
+  };
+  auto candidate = [&](int pi) {
+    if (!b3_intersect_p(sc.prim_bounds[pi], cull_ray(), invd, neg)) return;
+    if (ts) ts->prims++;
+    Ray r2 = ray;  // original tMax
+    Hit h;
+    if (prim_intersect(sc, pi, r2, &h)) {
+      if (r2.tmax < t_best || (r2.tmax == t_best && pi < best)) { t_best = r2.tmax; best = pi; best_hit = h; }
+    }
+  };
+  if (sc.brute()) {
+    for (size_t i = 0; i < sc.prims.size(); i++) candidate((int)i);
+  } else if (!sc.nodes.empty()) {
+    uint64_t toVisit = 0, cur = 0;
+    uint64_t stack[256];
+    for (;;) {
+      const Scene::Node& node = sc.nodes[cur];
+      if (ts) ts->nodes++;
+      if (b3_intersect_p(node.b, cull_ray(), invd, neg)) {
+        if (node.nPrims > 0) {
+          for (uint64_t i = 0; i < node.nPrims; i++) candidate(sc.ordered[node.primOffset + i]);
+          if (toVisit == 0) break;
+          cur = stack[--toVisit];
+        } else {
+          if (toVisit >= 256) { g_counters.stack_overflows.fetch_add(1); break; }
+          if (neg[node.axis]) { stack[toVisit++] = cur + 1; cur = node.second; }
+          else { stack[toVisit++] = node.second; cur = cur + 1; }
+        }
+      } else {
+        if (toVisit == 0) break;
+        cur = stack[--toVisit];
+      }
+    }
+  }
+  if (best < 0) return false;
+  ray.tmax = t_best;
+  if (hit) *hit = best_hit;
+  return true;
+}
+
+// BVH.Intersect (bvh.go:659-712).  accel_mode 0 is the reference itself: running tMax, its own visit order and its fixed
+// [64] stack (an overflow is where Go would panic with index-out-of-range — counted, traversal abandoned).
 static inline bool scene_intersect(const Scene& sc, Ray& ray, Hit* hit, TravStats* ts = nullptr) {
   V3 invd{1 / ray.d.x, 1 / ray.d.y, 1 / ray.d.z};
   int neg[3] = {invd.x < 0, invd.y < 0, invd.z < 0};
+  if (sc.own_bound_test) return scene_intersect_canonical(sc, ray, hit, ts, invd, neg);
   if (sc.brute()) {  // accelerator.Simple ordering is by distance; here: plain loop with running tMax
     bool any = false;
     for (size_t i = 0; i < sc.prims.size(); i++) {

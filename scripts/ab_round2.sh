@@ -1,13 +1,10 @@
-run() { # tag lib env...
-  tag=$1; lib=$2; shift 2
+python -m pytest tests -m gpu -x -q > gpurun_out/gputest_b.log 2>&1; tail -3 gpurun_out/gputest_b.log
+run() { tag=$1; lib=$2; shift 2
   if [ -n "$lib" ]; then export GOPBRT_LIB=$PWD/go-pbrt_b200/csrc/variants/lib_$lib.so; else unset GOPBRT_LIB; fi
-  env "$@" AB_MODE=1 python scripts/ab_trace.py "$tag" $CFGS 2>&1 | grep '^{'
+  env "$@" python scripts/ab_trace.py "$tag" $CFGS 2>&1 | grep '^{'
 }
-CFGS="config4"
-run base "" X=1
-run base_cap24 "" GOPBRT_STACK_CAP=24
-run base_cap16 "" GOPBRT_STACK_CAP=16
-run b5_cap24 b5 GOPBRT_STACK_CAP=24
-run b6_cap24 b6 GOPBRT_STACK_CAP=24
-run b8_cap24 b8 GOPBRT_STACK_CAP=24
-run b8_cap16 b8 GOPBRT_STACK_CAP=16
+CFGS="config2 config1 config4"
+run new_fast "" AB_MODE=1
+run new_strict "" AB_MODE=0
+CFGS="config2"
+run bvh_fast "" AB_MODE=1 GOPBRT_NO_FLAT=1
