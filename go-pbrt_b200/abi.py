@@ -19,6 +19,13 @@ SAMPLER_STRATIFIED, SAMPLER_RANDOM = 0, 1
 MODE_STRICT, MODE_FAST = 0, 1
 FLAG_COUNT_TRAVERSAL, FLAG_FAIL_ON_PANIC, FLAG_TIME_KERNELS = 1, 2, 4
 
+# function ids of the self-test hook gopbrt_kat_eval (csrc/gp_kat.cuh: KAT_*)
+KAT_IDS = {n: i for i, n in enumerate([
+    "fr_dielectric", "oren_nayar_f", "fresnel_specular_sample_f", "concentric_sample_disk", "cosine_sample_hemisphere", "lambert_sample_f",
+    "offset_ray_origin", "coordinate_system", "sample_discrete_uniform", "rgb_to_xyz", "film_add_sample", "rng_u32", "rng_uniform",
+    "rng_u32b", "stratified_start_pixel", "light_sample_li", "spawn_ray_to", "camera_ray"])}
+LIGHTS_UNIFORM, LIGHTS_POWER, LIGHTS_SPATIAL = 1, 2, 4
+
 d16 = C.c_double * 16
 d3 = C.c_double * 3
 
@@ -117,7 +124,7 @@ class Stats(C.Structure):
 EXPORTS = ["gopbrt_abi_version", "gopbrt_init", "gopbrt_shutdown", "gopbrt_last_error", "gopbrt_scene_create",
            "gopbrt_scene_destroy", "gopbrt_scene_world_bound", "gopbrt_trace_closest", "gopbrt_trace_any",
            "gopbrt_trace_closest_device", "gopbrt_trace_any_device", "gopbrt_render", "gopbrt_render_device",
-           "gopbrt_cancel", "gopbrt_launch_count"]
+           "gopbrt_cancel", "gopbrt_launch_count", "gopbrt_kat_eval"]
 
 _lib = None
 dp = C.POINTER(C.c_double)
@@ -153,6 +160,8 @@ def load(path=None):
     lib.gopbrt_render.argtypes = rargs + [dp, C.POINTER(Stats)]
     lib.gopbrt_render_device.argtypes = rargs + [C.c_void_p, C.POINTER(Stats)]
     lib.gopbrt_cancel.argtypes = [C.c_void_p]
+    lib.gopbrt_kat_eval.argtypes = [C.c_void_p, C.c_int, dp, C.c_int, dp, C.c_int]
+    lib.gopbrt_kat_eval.restype = C.c_int
     lib.gopbrt_launch_count.argtypes = [C.c_void_p]
     lib.gopbrt_launch_count.restype = C.c_uint64
     if lib.gopbrt_abi_version() != 1:

@@ -15,6 +15,7 @@
 #include "../../include/gopbrt_cuda.h"
 #include "gp_bvh.h"
 #include "gp_render.cuh"
+#include "gp_kat.cuh"
 
 using namespace gp;
 
@@ -36,7 +37,7 @@ struct gopbrt_ctx {
   // device work of concurrent calls — each gRPC request of the reference renders on its own goroutine with its own scene,
   // SURVEY §8b — is serialised per context; gopbrt_cancel stays lock-free.
   std::mutex run_mu;
-  int grid_gen = 0, grid_shade[3] = {0, 0, 0};  // persistent grids of this device (SMs x resident CTAs)
+  int grid_gen[8] = {0, 0, 0, 0, 0, 0, 0, 0}, grid_shade[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};  // persistent grids of this device (SMs x resident CTAs)
   size_t trace_smem_limit = 0;  // largest dynamic shared memory size the traversal kernels have been opted into (> 48 KB only)
 };
 
@@ -118,6 +119,7 @@ struct gopbrt_scene {
   DevBuf<TraceCounters> tctr;
   DevBuf<int> work;  // work counters of the persistent traversal warps (batched API)
   int stack_cap = 8;
+  unsigned class_mask = 0;  // shade classes (RF_CLASS_*) that occur among the scene's primitives
   // traversal kernels of this scene: [0] extend, [1] extend + counters, [2] shadow, [3] shadow + counters, [4] batched any-hit,
   // [5] per-segment shadow (DirectLighting / UniformSampleAll), [6] the same + counters
   trace_fn trace_k[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -208,6 +210,16 @@ static HB xf_bounds(const M4& m, const HB& b) {
     hb_union_point(r, xf_point(m, c, mk3(0, 0, 0), nullptr));
   }
   return r;
+}
+
+// NewUniformLightDistribution + NewDistribution1D (lightdistribution.go:25-34, sampling.go:11-40): func[i] = 1; returns FuncInt
+static double uniform_light_cdf(int nl, std::vector<double>& cdf) {
+  cdf.assign(nl + 1, 0.0);
+  for (int i = 1; i < nl + 1; i++) cdf[i] = cdf[i - 1] + 1.0 / (double)nl;
+  double func_int = nl ? cdf[nl] : 0.0;
+  if (func_int == 0.0) { for (int i = 1; i < nl + 1; i++) cdf[i] = (double)i / (double)nl; }
+  else { for (int i = 1; i < nl + 1; i++) cdf[i] /= func_int; }
+  return func_int;
 }
 
 // fn(begin, end, chunk index) over [0, n) on the host's cores (one chunk per thread, in index order)
@@ -427,13 +439,9 @@ extern "C" int gopbrt_scene_create(gopbrt_ctx* ctx, const gopbrt_scene_desc* d, 
     }
     lights[i] = o;
   }
-  // NewUniformLightDistribution + NewDistribution1D (lightdistribution.go:25-34, sampling.go:11-40)
   int nl = d->n_lights;
-  std::vector<double> cdf(nl + 1, 0.0);
-  for (int i = 1; i < nl + 1; i++) cdf[i] = cdf[i - 1] + 1.0 / (double)nl;
-  double func_int = nl ? cdf[nl] : 0.0;
-  if (func_int == 0.0) { for (int i = 1; i < nl + 1; i++) cdf[i] = (double)i / (double)nl; }
-  else { for (int i = 1; i < nl + 1; i++) cdf[i] /= func_int; }
+  std::vector<double> cdf;
+  double func_int = uniform_light_cdf(nl, cdf);
 
   gopbrt_scene* sc = new gopbrt_scene();
   sc->ctx = ctx;
@@ -467,6 +475,7 @@ extern "C" int gopbrt_scene_create(gopbrt_ctx* ctx, const gopbrt_scene_desc* d, 
     if (inside) D.world_radius = sqrt(dist2(c, mk3(world.mx[0], world.mx[1], world.mx[2])));
     for (int k = 0; k < 3; k++) { sc->world[k] = world.mn[k]; sc->world[3 + k] = world.mx[k]; }
   }
+  for (const PrimRec& r : recs) sc->class_mask |= 1u << ((r.flags & RF_CLASS_MASK) >> RF_CLASS_SHIFT);
   sc->bvh_nodes = nodes.size();
   sc->bvh_depth = (uint64_t)bvh.depth;
   // traversal stack, [entry][thread] in dynamic shared memory: a step over a 4-record child group (two tree levels)
@@ -636,13 +645,42 @@ extern "C" int gopbrt_trace_any(gopbrt_scene* sc, int64_t n, const double* ox, c
   return GOPBRT_OK;
 }
 
+// Film geometry of a render: NewFilm's cropped pixel bounds (film.go:43-48), pbrt.Render's tile grid (integrator.go:297-299)
+// and the extent of a lane's FilmTile storage.  Returns an error text, or nullptr.
+static const char* film_params(const gopbrt_film* film, int64_t tile_size, RenderParams& P) {
+  if (tile_size < 1) return "tile_size < 1";
+  if (!(film->filter_radius[0] > 0) || !(film->filter_radius[1] > 0)) return "filter radius must be positive";
+  P.tile_size = tile_size;
+  P.cx0 = (long long)ceil((double)film->width * film->crop[0]); P.cy0 = (long long)ceil((double)film->height * film->crop[1]);
+  P.cx1 = (long long)ceil((double)film->width * film->crop[2]); P.cy1 = (long long)ceil((double)film->height * film->crop[3]);
+  long long fw = P.cx1 - P.cx0, fh = P.cy1 - P.cy0;
+  if (fw <= 0 || fh <= 0) return "empty film";
+  P.ntx = (fw + P.tile_size - 1) / P.tile_size; P.nty = (fh + P.tile_size - 1) / P.tile_size;  // integrator.go:297-299
+  P.ntiles = P.ntx * P.nty;
+  P.frx = film->filter_radius[0]; P.fry = film->filter_radius[1];
+  // Columns / rows of a tile's pixel bounds (GetFilmTile, film.go:106-113: [ceil(x0 - 0.5 - r), floor(x1 - 0.5 + r) + 1), x0
+  // integer, x1 - x0 <= tileSize) that AddSample can actually touch: samples lie strictly below x1, so the last pixel a
+  // sample reaches is ceil(x1 - 0.5 + r) - 1 — one short of the bound when x1 - 0.5 + r is an integer (box filter r = 0.5).
+  // The untouched last column / row stays zero in the reference's tile and adds exactly nothing in MergeFilmTile, so it is
+  // not stored: tileSize 1 with the box filter needs 2 x 2 pixels = one 128-byte line per lane.
+  long long tpw = std::min<long long>(fw, (long long)ceil((double)P.tile_size - 0.5 + P.frx) - (long long)ceil(-0.5 - P.frx));
+  long long tph = std::min<long long>(fh, (long long)ceil((double)P.tile_size - 0.5 + P.fry) - (long long)ceil(-0.5 - P.fry));
+  P.tpw = (int)tpw; P.tph = (int)tph;
+  return nullptr;
+}
+
 // ------------------------------------------------------------------------------------------------ render
 static int render_impl(gopbrt_scene* sc, const gopbrt_camera* cam, const gopbrt_sampler* smp, const gopbrt_integrator* ig,
                        const gopbrt_film* film, const gopbrt_render_options* opt, double* d_film, gopbrt_stats* stats) {
   gopbrt_ctx* ctx = sc->ctx;
   auto bad = [&](const char* msg) { ctx->last_error = msg; return GOPBRT_ERR_INVALID; };
   if (ig->kind == GOPBRT_INTEGRATOR_PATH) {
-    if (ig->light_strategy != GOPBRT_LIGHTS_UNIFORM) return bad("Path: only the Uniform light strategy is supported");
+    if (ig->light_strategy == GOPBRT_LIGHTS_SPATIAL) {  // CreateLightSampleDistribution returns nil (lightdistribution.go:11-19): Path.Li panics
+      ctx->last_error = "Path: LightSampleStrategy Spatial has no distribution in the reference (nil LightDistribution, path.go:80 panics)";
+      return GOPBRT_ERR_UNSUPPORTED;
+    }
+    if (ig->light_strategy != GOPBRT_LIGHTS_UNIFORM && ig->light_strategy != GOPBRT_LIGHTS_POWER) return bad("Path: unknown light sample strategy");
+    if (ig->max_depth > 255) return bad("Path: max_depth out of range (the bounce count is kept in 8 bits)");
   } else if (ig->kind == GOPBRT_INTEGRATOR_DIRECT_LIGHTING) {
     if (ig->light_strategy != GOPBRT_DL_SAMPLE_ONE && ig->light_strategy != GOPBRT_DL_SAMPLE_ALL) return bad("DirectLighting: unknown lighting strategy");
     if (ig->light_strategy == GOPBRT_DL_SAMPLE_ALL && sc->dev.n_lights > 31) {
@@ -651,8 +689,6 @@ static int render_impl(gopbrt_scene* sc, const gopbrt_camera* cam, const gopbrt_
     }
     if (ig->max_depth > 250) return bad("DirectLighting: max_depth out of range");
   } else return bad("unknown integrator kind");
-  if (ig->tile_size < 1) return bad("tile_size < 1");
-  if (!(film->filter_radius[0] > 0) || !(film->filter_radius[1] > 0)) return bad("filter radius must be positive");
   if (smp->kind != GOPBRT_SAMPLER_STRATIFIED && smp->kind != GOPBRT_SAMPLER_RANDOM) return bad("unknown sampler");
   if (smp->n_sampled_dimensions > 255 || smp->n_sampled_dimensions < 0) return bad("n_sampled_dimensions out of range");
   int rank = opt ? opt->rank : 0, world = opt ? opt->world : 1;
@@ -677,23 +713,12 @@ static int render_impl(gopbrt_scene* sc, const gopbrt_camera* cam, const gopbrt_
   const bool direct_all = ig->kind == GOPBRT_INTEGRATOR_DIRECT_LIGHTING && ig->light_strategy == GOPBRT_DL_SAMPLE_ALL;
   P.n_seg = direct_all ? std::max(1, sc->dev.n_lights) : 1;
   P.direct_all = direct_all ? 1 : 0;
-  P.tile_size = ig->tile_size;
-  // NewFilm (film.go:43-48)
-  P.cx0 = (long long)ceil((double)film->width * film->crop[0]); P.cy0 = (long long)ceil((double)film->height * film->crop[1]);
-  P.cx1 = (long long)ceil((double)film->width * film->crop[2]); P.cy1 = (long long)ceil((double)film->height * film->crop[3]);
+  P.light_power = (ig->kind == GOPBRT_INTEGRATOR_PATH && ig->light_strategy == GOPBRT_LIGHTS_POWER) ? 1 : 0;
+  // every sample of a lane through the integer corner of the lane's one pixel, filter weight 1: see film_add_uniform
+  P.uniform_fp = (ig->tile_size == 1 && smp->kind == GOPBRT_SAMPLER_STRATIFIED && smp->n_sampled_dimensions >= 1 && !getenv("GOPBRT_NO_UNIFORM_FP")) ? 1 : 0;
+  if (const char* ferr = film_params(film, ig->tile_size, P)) return bad(ferr);
   long long fw = P.cx1 - P.cx0, fh = P.cy1 - P.cy0;
-  if (fw <= 0 || fh <= 0) return bad("empty film");
-  P.ntx = (fw + P.tile_size - 1) / P.tile_size; P.nty = (fh + P.tile_size - 1) / P.tile_size;  // integrator.go:297-299
-  P.ntiles = P.ntx * P.nty;
-  P.frx = film->filter_radius[0]; P.fry = film->filter_radius[1];
-  // Columns / rows of a tile's pixel bounds (GetFilmTile, film.go:106-113: [ceil(x0 - 0.5 - r), floor(x1 - 0.5 + r) + 1), x0
-  // integer, x1 - x0 <= tileSize) that AddSample can actually touch: samples lie strictly below x1, so the last pixel a
-  // sample reaches is ceil(x1 - 0.5 + r) - 1 — one short of the bound when x1 - 0.5 + r is an integer (box filter r = 0.5).
-  // The untouched last column / row stays zero in the reference's tile and adds exactly nothing in MergeFilmTile, so it is
-  // not stored: tileSize 1 with the box filter needs 2 x 2 pixels = one 128-byte line per lane.
-  long long tpw = std::min<long long>(fw, (long long)ceil((double)P.tile_size - 0.5 + P.frx) - (long long)ceil(-0.5 - P.frx));
-  long long tph = std::min<long long>(fh, (long long)ceil((double)P.tile_size - 0.5 + P.fry) - (long long)ceil(-0.5 - P.fry));
-  P.tpw = (int)tpw; P.tph = (int)tph;
+  long long tpw = P.tpw, tph = P.tph;
   if (P.mode == GOPBRT_MODE_STRICT) { P.rank = rank; P.world = world; P.s_rank = 0; P.s_world = 1; }
   else { P.rank = 0; P.world = 1; P.s_rank = rank; P.s_world = world; }
   // FAST mode: a pixel's samples are independent, so a tile can be worked on by several lanes at once ("lane groups",
@@ -727,7 +752,7 @@ static int render_impl(gopbrt_scene* sc, const gopbrt_camera* cam, const gopbrt_
   const size_t table_doubles = P.mode == GOPBRT_MODE_FAST ? 0 : (size_t)P.ndims * P.spp;
   const size_t frame_doubles = P.integrator == GOPBRT_INTEGRATOR_DIRECT_LIGHTING ? (size_t)P.direct_levels * 8 : 0;
   const size_t n_seg = (size_t)P.n_seg;  // shadow segments (and shadow-queue entries) per lane
-  size_t per_lane = sizeof(RayRec) + n_seg * (sizeof(ShadowRec) + 1) + sizeof(PathRec) + (8 + n_seg) * 4 + 1 + table_doubles * 8 + (size_t)tpw * tph * 4 * 8 + frame_doubles * 8;
+  size_t per_lane = sizeof(RayRec) + n_seg * (sizeof(ShadowRec) + 1) + sizeof(PathRec) + (8 + n_seg) * 4 + 1 + table_doubles * 8 + (P.uniform_fp ? 0 : (size_t)tpw * tph * 4 * 8) + frame_doubles * 8;
   size_t free_b = 0, total_b = 0;
   GP_CUDA(ctx, cudaMemGetInfo(&free_b, &total_b));
   Workspace& W = sc->ws;
@@ -736,7 +761,7 @@ static int render_impl(gopbrt_scene* sc, const gopbrt_camera* cam, const gopbrt_
   if (opt && opt->max_lanes > 0) cap = std::min<long long>(cap, opt->max_lanes);
   long long lanes = std::max<long long>(1, std::min(lanes_total, cap));
   if (lanes * (long long)n_seg > 0x7fffff00LL) lanes = 0x7fffff00LL / (long long)n_seg;
-  size_t bt = table_doubles * lanes, bp = (size_t)tpw * tph * 4 * lanes;
+  size_t bt = table_doubles * lanes, bp = P.uniform_fp ? 0 : (size_t)tpw * tph * 4 * lanes;
   if (W.lanes != lanes || W.bytes_tables != bt || W.bytes_tilepix != bp || W.frames.n != frame_doubles * (size_t)lanes || W.sray.n != n_seg * (size_t)lanes ||
       W.occl.n != (direct_all ? n_seg * (size_t)lanes : 0) || W.codes.n != (size_t)lanes) {
     W.ray.release(); W.sray.release(); W.path.release(); W.i32.release(); W.tables.release(); W.tilepix.release(); W.frames.release(); W.occl.release(); W.codes.release();
@@ -775,18 +800,31 @@ static int render_impl(gopbrt_scene* sc, const gopbrt_camera* cam, const gopbrt_
   GP_CUDA(ctx, cudaMemsetAsync(sc->tctr.p, 0, sizeof(TraceCounters), st));
   const bool count = (flags & GOPBRT_FLAG_COUNT_TRAVERSAL) != 0;
 
-  if (!ctx->grid_gen) {
-    ctx->grid_gen = grid_for(ctx, (const void*)k_generate, 128);
-    ctx->grid_shade[0] = grid_for(ctx, (const void*)k_shade<0>, 128);
-    ctx->grid_shade[1] = grid_for(ctx, (const void*)k_shade<1>, 128);
-    ctx->grid_shade[2] = grid_for(ctx, (const void*)k_shade<2>, 128);
-  }
+  // stage kernels of this render: raygen by (sampler mode, integrator), shade by (integrator / strategy, sampler mode) and,
+  // for Path, one launch per shade class
+  typedef void (*gen_fn)(DevScene, Lanes, RenderParams, Queues, const int*, const int*, RenderCounters*);
+  typedef void (*shade_fn)(DevScene, Lanes, RenderParams, Queues, RenderCounters*);
+  static const gen_fn gen_tab[8] = {k_generate<0, 0, 0>, k_generate<0, 1, 0>, k_generate<1, 0, 0>, k_generate<1, 1, 0>,
+                                    k_generate<0, 0, 1>, k_generate<0, 1, 1>, k_generate<1, 0, 1>, k_generate<1, 1, 1>};
+  static const shade_fn shade_tab[12] = {k_shade<0, 0, 0>, k_shade<0, 0, 1>, k_shade<0, 0, 2>, k_shade<0, 0, 3>,
+                                         k_shade<0, 1, 0>, k_shade<0, 1, 1>, k_shade<0, 1, 2>, k_shade<0, 1, 3>,
+                                         k_shade<1, 0, -1>, k_shade<1, 1, -1>, k_shade<2, 0, -1>, k_shade<2, 1, -1>};
+  const int fast = P.mode == GOPBRT_MODE_FAST ? 1 : 0;
+  const int gen_i = P.uniform_fp * 4 + fast * 2 + (P.integrator == GOPBRT_INTEGRATOR_PATH ? 0 : 1);
+  const int shade_kind = P.integrator == GOPBRT_INTEGRATOR_PATH ? 0 : (direct_all ? 2 : 1);
+  const int shade_i0 = shade_kind == 0 ? fast * 4 : 8 + (shade_kind - 1) * 2 + fast;
+  int shade_list[4] = {shade_i0, 0, 0, 0}, n_shade = 0;  // Path: one launch per shade class that occurs in the scene
+  if (shade_kind == 0) { for (int k = 0; k < 4; k++) if ((sc->class_mask >> k) & 1u) shade_list[n_shade++] = shade_i0 + k; }
+  else n_shade = 1;
+  if (!ctx->grid_gen[gen_i]) ctx->grid_gen[gen_i] = grid_for(ctx, (const void*)gen_tab[gen_i], 128);
+  for (int k = 0; k < n_shade; k++)
+    if (!ctx->grid_shade[shade_list[k]]) ctx->grid_shade[shade_list[k]] = grid_for(ctx, (const void*)shade_tab[shade_list[k]], 128);
+  const gen_fn k_gen = gen_tab[gen_i];
   const size_t smem = sc->trace_smem;
   const int k_ext = count ? 1 : 0, k_any = direct_all ? (count ? 6 : 5) : (count ? 3 : 2);
-  const int shade_kind = P.integrator == GOPBRT_INTEGRATOR_PATH ? 0 : (direct_all ? 2 : 1);
   const int scap = sc->stack_cap;
   const int g_small = ctx->sm_count * 8;
-  const int g_gen = ctx->grid_gen, g_shade = ctx->grid_shade[shade_kind];
+  const int g_gen = ctx->grid_gen[gen_i];
   constexpr int kGraphIters = 8;
 
   cudaEvent_t ev[2];
@@ -813,10 +851,10 @@ static int render_impl(gopbrt_scene* sc, const gopbrt_camera* cam, const gopbrt_
   for (long long base = 0; base < lanes_total && rc == GOPBRT_OK; base += lanes) {
     P.lane_base = base;
     P.lanes_active = std::min(lanes, lanes_total - base);
-    GP_CUDA(ctx, cudaMemsetAsync(W.tilepix.p, 0, bp * sizeof(double), st));
+    if (bp) GP_CUDA(ctx, cudaMemsetAsync(W.tilepix.p, 0, bp * sizeof(double), st));
     GP_CUDA(ctx, cudaMemsetAsync(W.cnt.p, 0, 16 * sizeof(int), st));
     tick(ST_RAYGEN);
-    k_generate<<<g_gen, 128, 0, st>>>(sc->dev, L, P, Q, nullptr, nullptr, W.rctr.p);
+    k_gen<<<g_gen, 128, 0, st>>>(sc->dev, L, P, Q, nullptr, nullptr, W.rctr.p);
     ctx->launches += 1;
     // Wavefront iterations as a CUDA graph of kGraphIters iterations (6 launches each): in STRICT mode the last lanes
     // need hundreds of iterations over nearly empty queues, where the cost of an iteration IS its launch latency.
@@ -826,14 +864,12 @@ static int render_impl(gopbrt_scene* sc, const gopbrt_camera* cam, const gopbrt_
       auto enqueue_iteration = [&]() {
         sc->trace_k[k_ext]<<<sc->trace_grid[k_ext], kTraceThreads, smem, st>>>(sc->dev, L.ray, nullptr, L.path, W.codes.p, Q.extend, Q.cnt + 0, 0, scap, Q.cnt + 6, sc->tctr.p, nullptr);
         k_split_hits<<<g_small, 256, 0, st>>>(L, Q, W.codes.p);
-        if (shade_kind == 0) k_shade<0><<<g_shade, 128, 0, st>>>(sc->dev, L, P, Q, W.rctr.p);
-        else if (shade_kind == 1) k_shade<1><<<g_shade, 128, 0, st>>>(sc->dev, L, P, Q, W.rctr.p);
-        else k_shade<2><<<g_shade, 128, 0, st>>>(sc->dev, L, P, Q, W.rctr.p);
+        for (int k = 0; k < n_shade; k++) shade_tab[shade_list[k]]<<<ctx->grid_shade[shade_list[k]], 128, 0, st>>>(sc->dev, L, P, Q, W.rctr.p);
         sc->trace_k[k_any]<<<sc->trace_grid[k_any], kTraceThreads, smem, st>>>(sc->dev, nullptr, L.sray, L.path, L.occl, Q.shadow, Q.cnt + 2, 0, scap, Q.cnt + 7, sc->tctr.p, &W.rctr.p->radiance_gt10);
         k_advance<<<1, 32, 0, st>>>(Q, W.rctr.p, W.remaining_dev);
         std::swap(Q.extend, Q.extend_next);
         std::swap(Q.regen, Q.regen_next);
-        k_generate<<<g_gen, 128, 0, st>>>(sc->dev, L, P, Q, Q.regen, Q.cnt + 3, W.rctr.p);
+        k_gen<<<g_gen, 128, 0, st>>>(sc->dev, L, P, Q, Q.regen, Q.cnt + 3, W.rctr.p);
       };
       // key: everything the captured launches were given by value
       std::vector<unsigned char> key(sizeof(L) + sizeof(P) + sizeof(Q) + sizeof(sc->dev) + 9 * sizeof(int) + sizeof(size_t));
@@ -843,7 +879,7 @@ static int render_impl(gopbrt_scene* sc, const gopbrt_camera* cam, const gopbrt_
         memcpy(kp, &P, sizeof(P)); kp += sizeof(P);
         memcpy(kp, &Q, sizeof(Q)); kp += sizeof(Q);
         memcpy(kp, &sc->dev, sizeof(sc->dev)); kp += sizeof(sc->dev);
-        int gk[9] = {sc->trace_grid[k_ext], sc->trace_grid[k_any], g_small, g_shade, g_gen, scap, k_ext, k_any, shade_kind};
+        int gk[9] = {sc->trace_grid[k_ext], sc->trace_grid[k_any], g_small, shade_i0 * 16 + (int)sc->class_mask, g_gen, scap, k_ext, k_any, gen_i};
         memcpy(kp, gk, sizeof(gk)); kp += sizeof(gk);
         memcpy(kp, &smem, sizeof(size_t));
       }
@@ -863,7 +899,7 @@ static int render_impl(gopbrt_scene* sc, const gopbrt_camera* cam, const gopbrt_
       for (uint64_t k = 0;; k++) {
         GP_CUDA(ctx, cudaGraphLaunch(W.graph_exec, st));
         GP_CUDA(ctx, cudaEventRecord(W.graph_ev[k & 1], st));
-        ctx->launches += 6 * kGraphIters;
+        ctx->launches += (uint64_t)(5 + n_shade) * kGraphIters;
         iterations += kGraphIters; n_extend += kGraphIters; n_shadow += kGraphIters;
         if (k == 0) continue;
         GP_CUDA(ctx, cudaEventSynchronize(W.graph_ev[(k - 1) & 1]));  // graph k-1 is done, graph k is running or queued
@@ -883,9 +919,7 @@ static int render_impl(gopbrt_scene* sc, const gopbrt_camera* cam, const gopbrt_
       sc->trace_k[k_ext]<<<sc->trace_grid[k_ext], kTraceThreads, smem, st>>>(sc->dev, L.ray, nullptr, L.path, W.codes.p, Q.extend, Q.cnt + 0, 0, scap, Q.cnt + 6, sc->tctr.p, nullptr);
       tick(ST_SHADE);
       k_split_hits<<<g_small, 256, 0, st>>>(L, Q, W.codes.p);
-      if (shade_kind == 0) k_shade<0><<<g_shade, 128, 0, st>>>(sc->dev, L, P, Q, W.rctr.p);
-      else if (shade_kind == 1) k_shade<1><<<g_shade, 128, 0, st>>>(sc->dev, L, P, Q, W.rctr.p);
-      else k_shade<2><<<g_shade, 128, 0, st>>>(sc->dev, L, P, Q, W.rctr.p);
+      for (int k = 0; k < n_shade; k++) shade_tab[shade_list[k]]<<<ctx->grid_shade[shade_list[k]], 128, 0, st>>>(sc->dev, L, P, Q, W.rctr.p);
       if (iter_log_path) {
         int c[12];
         cudaMemcpyAsync(c, Q.cnt, sizeof(c), cudaMemcpyDeviceToHost, st);
@@ -899,8 +933,8 @@ static int render_impl(gopbrt_scene* sc, const gopbrt_camera* cam, const gopbrt_
       k_advance<<<1, 32, 0, st>>>(Q, W.rctr.p, W.remaining_dev);
       std::swap(Q.extend, Q.extend_next);
       std::swap(Q.regen, Q.regen_next);
-      k_generate<<<g_gen, 128, 0, st>>>(sc->dev, L, P, Q, Q.regen, Q.cnt + 3, W.rctr.p);
-      ctx->launches += 6;
+      k_gen<<<g_gen, 128, 0, st>>>(sc->dev, L, P, Q, Q.regen, Q.cnt + 3, W.rctr.p);
+      ctx->launches += 5 + n_shade;
       iterations++;
       n_extend++; n_shadow++;
       // the host looks at the device-written "lanes still in flight" only every few iterations: an iteration over empty
@@ -1007,4 +1041,63 @@ extern "C" int gopbrt_render(gopbrt_scene* sc, const gopbrt_camera* cam, const g
   GP_CUDA(ctx, cudaMemcpy(film_out, d_film.p, n * sizeof(double), cudaMemcpyDeviceToHost));
   if (stats) stats->ms_download = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
   return GOPBRT_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ self-test hook
+// Evaluates one device function of the raygen / shade / film stages on the GPU (gp_kat.cuh).  Returns the number of
+// doubles written to `out`, or a negative GOPBRT_ERR_* code.
+extern "C" int gopbrt_kat_eval(gopbrt_scene* sc, int fn, const double* in, int n_in, double* out, int n_out) {
+  if (!sc || !in || !out || n_in < 0 || n_in > 64 || n_out < 1 || n_out > 4096 || fn < 0 || fn >= KAT_N) return -GOPBRT_ERR_INVALID;
+  gopbrt_ctx* ctx = sc->ctx;
+  std::lock_guard<std::mutex> g(sc->mu);
+  std::lock_guard<std::mutex> grun(ctx->run_mu);
+  auto cuda_fail = [&](cudaError_t e) { ctx->last_error = std::string("gopbrt_kat_eval: ") + cudaGetErrorString(e); return -GOPBRT_ERR_CUDA; };
+  cudaError_t e = cudaSetDevice(ctx->device);
+  if (e != cudaSuccess) return cuda_fail(e);
+  RenderParams P;
+  memset(&P, 0, sizeof(P));
+  std::vector<double> scratch(1, 0.0);
+  if (fn == KAT_SAMPLE_DISCRETE_UNIFORM && n_in == 2) {
+    int nl = (int)in[0];
+    if (nl < 1 || nl > 1024) return -GOPBRT_ERR_INVALID;
+    std::vector<double> cdf;
+    double fi = uniform_light_cdf(nl, cdf);
+    scratch.assign(1, fi);
+    scratch.insert(scratch.end(), cdf.begin(), cdf.end());
+  } else if (fn == KAT_FILM_ADD_SAMPLE && n_in == 11) {
+    gopbrt_film f;
+    f.width = (int)in[0]; f.height = (int)in[1];
+    f.crop[0] = 0; f.crop[1] = 0; f.crop[2] = 1; f.crop[3] = 1;
+    f.filter_radius[0] = in[3]; f.filter_radius[1] = in[4];
+    if (const char* msg = film_params(&f, (int64_t)in[2], P)) { ctx->last_error = msg; return -GOPBRT_ERR_INVALID; }
+    P.world = 1; P.groups = 1; P.s_world = 1;
+    if (in[5] < 0 || in[5] >= (double)P.ntiles) return -GOPBRT_ERR_INVALID;
+    scratch.assign((size_t)P.tpw * P.tph * 4, 0.0);
+  } else if (fn == KAT_STRATIFIED_START_PIXEL && n_in == 5) {
+    P.sampler_kind = GOPBRT_SAMPLER_STRATIFIED; P.mode = GOPBRT_MODE_STRICT;
+    P.xs = (int)in[1]; P.ys = (int)in[2]; P.jitter = (int)in[3]; P.ndims = (int)in[4];
+    P.spp = P.xs * P.ys;
+    if (P.spp < 1 || P.spp > 4096 || P.ndims < 0 || P.ndims > 16) return -GOPBRT_ERR_INVALID;
+    scratch.assign((size_t)std::max(1, P.ndims * P.spp), 0.0);
+  } else if (fn == KAT_CAMERA_RAY && n_in == 38) {
+    P.raster_to_camera = m4_from(in); P.camera_to_world = m4_from(in + 16);
+    P.lens_radius = in[32]; P.focal_distance = in[33];
+  }
+  DevBuf<double> d_in, d_out, d_scratch;
+  DevBuf<int> d_n;
+  cudaStream_t st = ctx->stream;
+  if ((e = d_in.alloc(std::max(1, n_in))) != cudaSuccess || (e = d_out.alloc(n_out)) != cudaSuccess || (e = d_scratch.alloc(scratch.size())) != cudaSuccess ||
+      (e = d_n.alloc(1)) != cudaSuccess)
+    return cuda_fail(e);
+  if (n_in && (e = cudaMemcpyAsync(d_in.p, in, n_in * sizeof(double), cudaMemcpyHostToDevice, st)) != cudaSuccess) return cuda_fail(e);
+  if ((e = cudaMemcpyAsync(d_scratch.p, scratch.data(), scratch.size() * sizeof(double), cudaMemcpyHostToDevice, st)) != cudaSuccess) return cuda_fail(e);
+  if ((e = cudaMemsetAsync(d_out.p, 0, n_out * sizeof(double), st)) != cudaSuccess) return cuda_fail(e);
+  k_kat<<<1, 32, 0, st>>>(sc->dev, fn, d_in.p, n_in, d_out.p, n_out, d_scratch.p, P, d_n.p);
+  ctx->launches++;
+  int n = -1;
+  if ((e = cudaMemcpyAsync(&n, d_n.p, sizeof(int), cudaMemcpyDeviceToHost, st)) != cudaSuccess) return cuda_fail(e);
+  if ((e = cudaMemcpyAsync(out, d_out.p, n_out * sizeof(double), cudaMemcpyDeviceToHost, st)) != cudaSuccess) return cuda_fail(e);
+  if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return cuda_fail(e);
+  if (n < 0) { ctx->last_error = "gopbrt_kat_eval: bad argument count for this function"; return -GOPBRT_ERR_INVALID; }
+  return n;
 }

@@ -36,6 +36,9 @@ struct RenderParams {
   int direct_levels;             // DirectLighting: frames per lane = max(1, maxDepth / 2)
   int n_seg;                     // shadow segments per lane: 1, or the number of lights for DirectLighting / UniformSampleAll
   int direct_all;                // DirectLighting strategy is UniformSampleAll (segments are collected by the shade stage)
+  int uniform_fp;                // every sample of a lane has the same film footprint and weight: the lane's FilmTile is kept as one
+                                 // RGB sum in PathRec.pad (see film_add_uniform) instead of a tile record in `tilepix`
+  int light_power;               // Path with LightSampleStrategy Power (lightdistribution.go:44-68, bugs included: no light is ever sampled)
   double rr_threshold;
   long long tile_size, ntx, nty, ntiles;
   long long cx0, cy0, cx1, cy1;  // CroppedPixelBounds
@@ -293,8 +296,8 @@ GP_D double sintheta(V3 w) { return sqrt(sin2theta(w)); }
 GP_D double cosphi(V3 w) { double s = sintheta(w); return s == 0 ? 1 : go_clamp(w.x / s, -1, 1); }
 GP_D double sinphi(V3 w) { double s = sintheta(w); return s == 0 ? 0 : go_clamp(w.y / s, -1, 1); }
 
-GP_D RGB bxdf_f(const BSDF& b, V3 wo, V3 wi) {
-  if (b.kind == BX_LAMBERT) return b.r * kInvPi;  // reflection.go:589-591
+GP_D RGB bxdf_f(const BSDF& b, V3 wo, V3 wi, bool lambert_only = false) {
+  if (lambert_only || b.kind == BX_LAMBERT) return b.r * kInvPi;  // reflection.go:589-591
   if (b.kind == BX_OREN_NAYAR) {                   // reflection.go:628-652
     double sinThetaI = sintheta(wi), sinThetaO = sintheta(wo);
     double maxCos = 0.0;
@@ -310,8 +313,8 @@ GP_D RGB bxdf_f(const BSDF& b, V3 wo, V3 wi) {
   }
   return rgb(0, 0, 0);
 }
-GP_D double bxdf_pdf(const BSDF& b, V3 wo, V3 wi) {
-  if (b.kind == BX_LAMBERT || b.kind == BX_OREN_NAYAR) {  // reflection.go:343-348
+GP_D double bxdf_pdf(const BSDF& b, V3 wo, V3 wi, bool lambert_only = false) {
+  if (lambert_only || b.kind == BX_LAMBERT || b.kind == BX_OREN_NAYAR) {  // reflection.go:343-348
     if (wo.z * wi.z > 0) return fabs(wi.z) * kInvPi;
     return 0;
   }
@@ -320,28 +323,28 @@ GP_D double bxdf_pdf(const BSDF& b, V3 wo, V3 wi) {
 GP_D V3 to_local(const BSDF& b, V3 v) { return mk3(dot(v, b.ss), dot(v, b.ts), dot(v, b.ns)); }
 
 // BSDF.F (reflection.go:164-181) / BSDF.Pdf (:255-278) for a single-BxDF BSDF
-GP_D RGB bsdf_f(const BSDF& b, V3 woW, V3 wiW, int flags) {
+GP_D RGB bsdf_f(const BSDF& b, V3 woW, V3 wiW, int flags, bool lambert_only = false) {
   V3 wi = to_local(b, wiW), wo = to_local(b, woW);
   if (wo.z == 0.0) return rgb(0, 0, 0);
   bool reflect = dot(wiW, b.ng) * dot(woW, b.ng) > 0;
   RGB f = rgb(0, 0, 0);
   if (b.kind != BX_NONE && matches(b.type, flags) &&
       ((reflect && (b.type & BSDF_REFLECTION) > 0) || (!reflect && (b.type & BSDF_TRANSMISSION) > 0)))
-    f = f + bxdf_f(b, wo, wi);
+    f = f + bxdf_f(b, wo, wi, lambert_only);
   return f;
 }
-GP_D double bsdf_pdf(const BSDF& b, V3 woW, V3 wiW, int flags) {
+GP_D double bsdf_pdf(const BSDF& b, V3 woW, V3 wiW, int flags, bool lambert_only = false) {
   if (b.kind == BX_NONE) return 0;
   V3 wo = to_local(b, woW), wi = to_local(b, wiW);
   if (wo.z == 0) return 0;
   double pdf = 0;
   int m = 0;
-  if (matches(b.type, flags)) { m++; pdf += bxdf_pdf(b, wo, wi); }
+  if (matches(b.type, flags)) { m++; pdf += bxdf_pdf(b, wo, wi, lambert_only); }
   if (m <= 0) return 0;
   return pdf / (double)m;
 }
 // BSDF.SampleF (reflection.go:183-253) with matchingComps in {0,1}: returns the LOCAL wi
-GP_D void bsdf_sample_f(const BSDF& b, V3 woWorld, double ux, double uy, int type, RGB* f, V3* wi, double* pdf, int* sampled) {
+GP_D void bsdf_sample_f(const BSDF& b, V3 woWorld, double ux, double uy, int type, RGB* f, V3* wi, double* pdf, int* sampled, bool lambert_only = false) {
   *f = rgb(0, 0, 0); *wi = mk3(0, 0, 0); *pdf = 0; *sampled = 0;
   if (b.kind == BX_NONE || !matches(b.type, type)) return;
   double comp = go_min(floor(ux * 1.0), 1.0 - 1);
@@ -349,11 +352,11 @@ GP_D void bsdf_sample_f(const BSDF& b, V3 woWorld, double ux, double uy, int typ
   V3 wo = to_local(b, woWorld);
   if (wo.z == 0.0) return;
   RGB ff; V3 w; double p; int st = 0;
-  if (b.kind == BX_LAMBERT || b.kind == BX_OREN_NAYAR) {  // sampleF (reflection.go:305-314): sampledType 0
+  if (lambert_only || b.kind == BX_LAMBERT || b.kind == BX_OREN_NAYAR) {  // sampleF (reflection.go:305-314): sampledType 0
     w = cosine_sample_hemisphere(urx, uy);
     if (wo.z < 0) w.z *= -1;
-    p = bxdf_pdf(b, wo, w);
-    ff = bxdf_f(b, wo, w);
+    p = bxdf_pdf(b, wo, w, lambert_only);
+    ff = bxdf_f(b, wo, w, lambert_only);
   } else if (b.kind == BX_SPEC_REFL_NOOP) {  // reflection.go:557-562 + FresnelNoOp
     w = mk3(-wo.x, -wo.y, wo.z);
     p = 1.0;
@@ -387,8 +390,19 @@ GP_D void bsdf_sample_f(const BSDF& b, V3 woWorld, double ux, double uy, int typ
   *f = ff; *wi = w; *pdf = p; *sampled = st;
 }
 
+// NewOrenNayar (reflection.go:616-626), sigma in degrees; `0.45 * s2 / (s2 * 0.09)` as written
+GP_D void oren_nayar_init(BSDF* b, double sigma_deg) {
+  b->kind = BX_OREN_NAYAR;
+  double s = kPi / 180.0 * sigma_deg;
+  double s2 = s * s;
+  b->a = 1.0 - (s2 / (2.0 * (s2 + 0.33)));
+  b->b = 0.45 * s2 / (s2 * 0.09);
+}
+
 // Material.ComputeScatteringFunctions (matte.go:21-37, mirror.go:21-32, glass.go:27-75) + NewBSDF (reflection.go:128-140)
-GP_D bool compute_scattering(const DevScene& sc, int prim, const Hit& h, BSDF* b, bool allowMultipleLobes = true) {
+// lambert_only (a compile-time constant at the call site): the hit's shade class says its material is MatteMaterial with
+// sigma == 0 (scene build, gopbrt.cu), so only that branch is compiled into the caller
+GP_D bool compute_scattering(const DevScene& sc, int prim, const Hit& h, BSDF* b, bool allowMultipleLobes = true, bool lambert_only = false) {
   int mi = sc.prims[prim].z;
   if (mi < 0) return false;  // primitive.go:73-75 panics
   const MaterialDev& m = sc.materials[mi];
@@ -397,6 +411,11 @@ GP_D bool compute_scattering(const DevScene& sc, int prim, const Hit& h, BSDF* b
   b->ts = cross(b->ns, b->ss);
   b->kind = BX_NONE; b->type = 0; b->eta = 1.0; b->a = 0; b->b = 0; b->etaB = 1.0;
   b->r = rgb(0, 0, 0); b->t = rgb(0, 0, 0);
+  if (lambert_only) {
+    RGB r = clamp_rgb(tex_eval(sc, m.tex_a, h), 0, d_inf());
+    if (!is_black(r)) { b->type = BSDF_REFLECTION | BSDF_DIFFUSE; b->r = r; b->kind = BX_LAMBERT; }
+    return true;
+  }
   if (m.kind == 0) {
     RGB r = clamp_rgb(tex_eval(sc, m.tex_a, h), 0, d_inf());
     double sig = go_clamp(m.sigma, 0, 90);
@@ -404,13 +423,7 @@ GP_D bool compute_scattering(const DevScene& sc, int prim, const Hit& h, BSDF* b
       b->type = BSDF_REFLECTION | BSDF_DIFFUSE;
       b->r = r;
       if (sig == 0) b->kind = BX_LAMBERT;
-      else {  // NewOrenNayar (reflection.go:616-626)
-        b->kind = BX_OREN_NAYAR;
-        double s = kPi / 180.0 * sig;
-        double s2 = s * s;
-        b->a = 1.0 - (s2 / (2.0 * (s2 + 0.33)));
-        b->b = 0.45 * s2 / (s2 * 0.09);
-      }
+      else oren_nayar_init(b, sig);
     }
     return true;
   }
@@ -440,6 +453,21 @@ GP_D bool compute_scattering(const DevScene& sc, int prim, const Hit& h, BSDF* b
     return true;
   }
   return false;
+}
+
+// Distribution1D.SampleDiscrete (sampling.go:42-55) via FindInterval (pkg/math/math.go:64-80) over the uniform light
+// distribution (func[i] == 1, lightdistribution.go:25-34): cdf has n + 1 entries
+GP_D void sample_discrete(const double* cdf, int n, double func_int, double u, int* offset_out, double* pdf_out) {
+  int size = n + 1, first = 0, len = size;
+  while (len > 0) {
+    int half = len >> 1, middle = first + half;
+    if (cdf[middle] <= u) { first = middle + 1; len -= half + 1; }
+    else len = half;
+  }
+  *offset_out = (int)go_clamp((double)(first - 1), 0, (double)(size - 2));
+  double pdf = 0;
+  if (func_int > 0) pdf = 1.0 / (func_int / (double)n);
+  *pdf_out = pdf;
 }
 
 // ---------------------------------------------------------------- lights (pkg/lights, sphere.go:270-344, disk.go:160-170, shape.go:50-65)
@@ -512,6 +540,14 @@ __device__ __noinline__ static void disk_sample_at(const DevScene& sc, const Dis
   *pdf = p;
 }
 
+// SpawnRayToInteraction (interaction.go:91-102): the direction of the visibility segment; its origin stays the
+// UN-offset point and tMax = 1 - ShadowEpsilon
+GP_D V3 spawn_ray_to(const Intr& from, const Intr& to) {
+  V3 origin = offset_ray_origin(from.p, from.perr, from.n, to.p - from.p);
+  V3 target = offset_ray_origin(to.p, to.perr, to.n, origin - to.p);
+  return target - origin;
+}
+
 struct LightSample { RGB Li; V3 wi; double pdf; Intr p1; bool delta; };
 // Point.SampleLi (point.go:44-49), Distant.SampleLi (distant.go:40-44), DiffuseAreaLight.SampleLi (diffuse.go:47-59)
 GP_D void light_sample_li(const DevScene& sc, const LightDev& l, const Intr& ref, double ux, double uy, LightSample* ls) {
@@ -540,6 +576,13 @@ GP_D void light_sample_li(const DevScene& sc, const LightDev& l, const Intr& ref
     V3 w = ls->wi * -1.0;
     ls->Li = (l.two_sided || dot(ps.n, w) > 0) ? E : rgb(0, 0, 0);
   }
+}
+
+// RGBToXYZ (spectrum.go:35-41)
+GP_D void rgb_to_xyz(double r, double g, double b, double* X, double* Y, double* Z) {
+  *X = 0.412453 * r + 0.357580 * g + 0.180423 * b;
+  *Y = 0.212671 * r + 0.715160 * g + 0.072169 * b;
+  *Z = 0.019334 * r + 0.119193 * g + 0.950227 * b;
 }
 
 // ---------------------------------------------------------------- film geometry (film.go:106-113)
@@ -607,7 +650,45 @@ GP_D void film_add_sample(const Lanes& L, const RenderParams& P, long long lane,
     }
 }
 
+// Uniform-footprint renders (tileSize 1, Stratified sampler with at least one sampled dimension): every sample of a lane
+// goes through the integer corner of the lane's ONE pixel (StratifiedSample2D never writes its table) with
+// filter weight 1 (box filter), so all pixels of its FilmTile that a sample touches receive the very same sequence of
+// additions `contribSum += L` and `filterWeightSum += 1` (film.go:241-243).  The tile is then ONE running RGB sum, kept
+// in the PathRec's spare 24 bytes (it is in registers whenever a sample retires), and the weight is the number of samples
+// the lane has retired — known in closed form.  Saves the 256-byte tile read-modify-write per sample.
+GP_D void film_add_uniform(PathRec& pt, RGB Lc) {
+  pt.pad[0] += Lc.r * (1.0 * 1.0);  // L.MulScalar(sampleWeight * filterWeight)
+  pt.pad[1] += Lc.g * (1.0 * 1.0);
+  pt.pad[2] += Lc.b * (1.0 * 1.0);
+}
+// the pixels [p0, p1) a sample at the integer corner (px, py) touches inside its tile's pixel bounds (film.go:217-221)
+GP_D void uniform_footprint(const RenderParams& P, long long px, long long py, long long bx0, long long by0, long long bx1, long long by1,
+                            long long* p0x, long long* p0y, long long* p1x, long long* p1y) {
+  double dx = (double)px - 0.5, dy = (double)py - 0.5;
+  *p0x = (long long)go_max(ceil(dx - P.frx), (double)bx0); *p0y = (long long)go_max(ceil(dy - P.fry), (double)by0);
+  *p1x = (long long)go_min(floor(dx + P.frx) + 1, (double)bx1); *p1y = (long long)go_min(floor(dy + P.fry) + 1, (double)by1);
+}
+
 // ---------------------------------------------------------------- raygen + sampler
+// PerspectiveCamera.GenerateRayDifferential (camera.go:192-242), the ray itself (Path.Li drops the differentials)
+GP_D Ray camera_ray(const RenderParams& P, double fx, double fy, double lx, double ly) {
+  V3 pCamera = xf_point(P.raster_to_camera, mk3(fx, fy, 0), mk3(0, 0, 0), nullptr);
+  Ray ray;
+  ray.o = mk3(0, 0, 0);
+  ray.d = normalized(pCamera);
+  ray.tmax = d_inf();
+  if (P.lens_radius > 0) {
+    double plx, ply;
+    concentric_sample_disk(lx, ly, &plx, &ply);
+    plx *= P.lens_radius; ply *= P.lens_radius;
+    double ft = P.focal_distance / ray.d.z;
+    V3 pFocus = ray.d * ft + ray.o;
+    ray.o = mk3(plx, ply, 0);
+    ray.d = normalized(pFocus - ray.o);
+  }
+  return xf_ray(P.camera_to_world, ray, nullptr, nullptr);
+}
+
 // One lane's raygen step: retires the lane's finished sample into its film tile (renderWorker, integrator.go:252-265),
 // advances the sampler (StartNextSample / next pixel + StartPixel) and generates the next camera ray
 // (GenerateRayDifferential, camera.go:192-242; the differentials are dropped by Path.Li).  Returns false when the
@@ -625,7 +706,8 @@ GP_D bool generate_lane(const DevScene& sc, const Lanes& L, const RenderParams& 
   if (have_sample) {  // every lane of the regeneration queue carries a finished sample
     RGB Lc = P.integrator == 1 ? direct_unwind(L, P, lane, pt) : rgb(pt.Lr, pt.Lg, pt.Lb);
     if (is_nan(Lc.r) || is_nan(Lc.g) || is_nan(Lc.b)) { Lc = rgb(0.1, 0.1, 0.1); nans++; }  // integrator.go:256-257
-    film_add_sample(L, P, lane, tile, pt.fx, pt.fy, Lc);
+    if (P.uniform_fp) film_add_uniform(pt, Lc);
+    else film_add_sample(L, P, lane, tile, pt.fx, pt.fy, Lc);
   }
   Smp s;
   s.state = pt.rng_state; s.inc = pt.rng_inc; s.sidx = pt.sidx; s.cur1 = 0; s.cur2 = 0; s.lane = lane;
@@ -671,21 +753,7 @@ GP_D bool generate_lane(const DevScene& sc, const Lanes& L, const RenderParams& 
     double fx = (double)px + ox, fy = (double)py + oy;
     get2d(s, P, &lx, &ly);
     double time = get1d(s, L, P, fast_pixel);
-    V3 pCamera = xf_point(P.raster_to_camera, mk3(fx, fy, 0), mk3(0, 0, 0), nullptr);
-    Ray ray;
-    ray.o = mk3(0, 0, 0);
-    ray.d = normalized(pCamera);
-    ray.tmax = d_inf();
-    if (P.lens_radius > 0) {
-      double plx, ply;
-      concentric_sample_disk(lx, ly, &plx, &ply);
-      plx *= P.lens_radius; ply *= P.lens_radius;
-      double ft = P.focal_distance / ray.d.z;
-      V3 pFocus = ray.d * ft + ray.o;
-      ray.o = mk3(plx, ply, 0);
-      ray.d = normalized(pFocus - ray.o);
-    }
-    ray = xf_ray(P.camera_to_world, ray, nullptr, nullptr);
+    Ray ray = camera_ray(P, fx, fy, lx, ly);
     (void)time;  // ray.Time = Lerp(time, open, open): unused without animated transforms
     cam++;
     // BVH.Intersect's first step (bvh.go:673-675): the root node's slab test.  A camera ray that fails it hits
@@ -696,7 +764,7 @@ GP_D bool generate_lane(const DevScene& sc, const Lanes& L, const RenderParams& 
                                                ray.o, invd, invd.x < 0, invd.y < 0, invd.z < 0, ray.tmax);
     if (!enters) {
       culled++;
-      film_add_sample(L, P, lane, tile, fx, fy, rgb(0, 0, 0));
+      if (!P.uniform_fp) film_add_sample(L, P, lane, tile, fx, fy, rgb(0, 0, 0));  // (uniform footprint: L = +0 adds nothing, the weight is counted)
       continue;
     }
     RayRec rr;
@@ -721,8 +789,20 @@ GP_D bool generate_lane(const DevScene& sc, const Lanes& L, const RenderParams& 
 // Retires the lane's finished sample into its film tile (renderWorker, integrator.go:252-265), advances the sampler
 // (StartNextSample / next pixel + StartPixel) and generates the next camera ray (GenerateRayDifferential,
 // camera.go:192-242; the differentials are dropped by Path.Li).  Lanes whose tile is exhausted leave the wavefront.
-__global__ void __launch_bounds__(128, 4) k_generate(DevScene sc, Lanes L, RenderParams P, Queues Q, const int* __restrict__ in_queue,
+// MODE / INTEG: the sampler mode and integrator kind as compile-time constants (the launch picks the instantiation): the
+// FAST-mode raygen then carries none of Stratified.StartPixel's table code and the Path raygen none of the DirectLighting
+// unwind, which is what sets the register budget — and with it the number of resident warps that hide the three dependent
+// HBM round trips (queue -> PathRec -> FilmTile) of this stage.
+#ifndef GP_GEN_BLOCKS
+#define GP_GEN_BLOCKS 4
+#endif
+template <int MODE, int INTEG, int UFP>
+__global__ void __launch_bounds__(128, GP_GEN_BLOCKS) k_generate(DevScene sc, Lanes L, RenderParams P_in, Queues Q, const int* __restrict__ in_queue,
                                                   const int* __restrict__ in_count, RenderCounters* ctr) {
+  RenderParams P = P_in;
+  P.mode = MODE;
+  P.integrator = INTEG;
+  P.uniform_fp = UFP;
   long long n = in_queue ? (long long)*in_count : P.lanes_active;
   int lane_id = threadIdx.x & 31;
   unsigned long long cam = 0, nans = 0, culled = 0;
@@ -800,8 +880,11 @@ __global__ void __launch_bounds__(256) k_split_hits(Lanes L, Queues Q, const uns
 // ---------------------------------------------------------------- shade
 // One Path.Li loop body for one lane (path.go:40-155) after its closest-hit query.  Sets cont (the path continues with a
 // new ray in L.ray[lane]), finished (the sample is complete) and shadow (a visibility segment is pending in L.sray[lane]).
+// cls: the hit's shade class (bit 0 = material is not plain Lambert, bit 1 = sphere / disk hit) when the caller shades one
+// class only (a compile-time constant after inlining: the other classes' code is not compiled in), or -1 = any
 GP_D void shade_lane(const DevScene& sc, const Lanes& L, const RenderParams& P, long long lane, bool& cont, bool& finished, bool& shadow,
-                     unsigned long long& n_unsupported, unsigned long long& n_dead, int& bad) {
+                     unsigned long long& n_unsupported, unsigned long long& n_dead, int& bad, const int cls = -1) {
+  const bool lambert_only = cls >= 0 && !(cls & 1), tri_only = cls >= 0 && !(cls & 2);
   PathRec pt = L.path[lane];
   RayRec rr = L.ray[lane];
   int packed = pt.bounces;
@@ -815,9 +898,9 @@ GP_D void shade_lane(const DevScene& sc, const Lanes& L, const RenderParams& P, 
     ray.tmax = rr.tmax;
     Hit h;
     int prim;
-    hit_record(sc, rec, ray, ray.tmax, &h, &prim, bad);
+    hit_record(sc, rec, ray, ray.tmax, &h, &prim, bad, tri_only);
     BSDF bsdf;
-    if (!compute_scattering(sc, prim, h, &bsdf)) {
+    if (!compute_scattering(sc, prim, h, &bsdf, true, lambert_only)) {
       n_unsupported++;
     } else {
       Smp s;
@@ -839,16 +922,13 @@ GP_D void shade_lane(const DevScene& sc, const Lanes& L, const RenderParams& P, 
       if (bsdf.kind != BX_NONE && matches(bsdf.type, BSDF_ALL & ~BSDF_SPECULAR)) {
         if (sc.n_lights > 0) {
           double u = get1d(s, L, P, fast_pixel);
-          // Distribution1D.SampleDiscrete (sampling.go:42-55) via FindInterval (pkg/math/math.go:64-80)
-          int size = sc.n_lights + 1, first = 0, len = size;
-          while (len > 0) {
-            int half = len >> 1, middle = first + half;
-            if (sc.light_cdf[middle] <= u) { first = middle + 1; len -= half + 1; }
-            else len = half;
-          }
-          int offset = (int)go_clamp((double)(first - 1), 0, (double)(size - 2));
-          double lightPdf = 0;
-          if (sc.light_func_int > 0) lightPdf = 1.0 / (sc.light_func_int / (double)sc.n_lights);
+          int offset;
+          double lightPdf;
+          sample_discrete(sc.light_cdf, sc.n_lights, sc.light_func_int, u, &offset, &lightPdf);
+          // LightSampleStrategy Power: ComputeLightPowerDistribution (lightdistribution.go:57-68) APPENDS the powers to a
+          // slice it already made n long, and every power is Spectrum.Y() == 0 (spectrum.go:227-229): 2n zeros, FuncInt
+          // == 0, so SampleDiscrete's pdf is 0 and UniformSampleOneLight returns black right after this Get1D
+          if (P.light_power) lightPdf = 0;
           if (lightPdf != 0.0) {
             double ulx, uly, usx, usy;
             get2d(s, P, &ulx, &uly);
@@ -859,9 +939,9 @@ GP_D void shade_lane(const DevScene& sc, const Lanes& L, const RenderParams& P, 
             light_sample_li(sc, sc.lights[offset], ref, ulx, uly, &ls);
             if (!ls.delta) n_dead++;
             if (ls.pdf > 0 && !is_black(ls.Li)) {
-              RGB f = bsdf_f(bsdf, h.wo, ls.wi, flags);
+              RGB f = bsdf_f(bsdf, h.wo, ls.wi, flags, lambert_only);
               f = f * fabs(dot(ls.wi, h.ns));
-              double scatteringPdf = bsdf_pdf(bsdf, h.wo, ls.wi, flags);
+              double scatteringPdf = bsdf_pdf(bsdf, h.wo, ls.wi, flags, lambert_only);
               if (!is_black(f)) {
                 RGB Ld;
                 if (ls.delta) Ld = (f * ls.Li) / ls.pdf;
@@ -872,9 +952,7 @@ GP_D void shade_lane(const DevScene& sc, const Lanes& L, const RenderParams& P, 
                 }
                 Ld = rgb(0, 0, 0) + Ld;  // Ld.AddAssign on a zero spectrum (integrator.go:123-126)
                 // VisibilityTester.Unoccluded -> SpawnRayToInteraction (interaction.go:91-102)
-                V3 origin = offset_ray_origin(ref.p, ref.perr, ref.n, ls.p1.p - ref.p);
-                V3 target = offset_ray_origin(ls.p1.p, ls.p1.perr, ls.p1.n, origin - ls.p1.p);
-                V3 d = target - origin;
+                V3 d = spawn_ray_to(ref, ls.p1);
                 RGB c = beta * Ld;  // Ld := beta.Mul(...) (path.go:85)
                 ShadowRec sr;
                 sr.ox = ref.p.x; sr.oy = ref.p.y; sr.oz = ref.p.z; sr.dx = d.x; sr.dy = d.y; sr.dz = d.z;  // tMax = 1 - ShadowEpsilon
@@ -897,7 +975,7 @@ GP_D void shade_lane(const DevScene& sc, const Lanes& L, const RenderParams& P, 
       double ux, uy;
       get2d(s, P, &ux, &uy);
       RGB f; V3 wi; double pdf; int sflags;
-      bsdf_sample_f(bsdf, ray.d, ux, uy, BSDF_ALL, &f, &wi, &pdf, &sflags);
+      bsdf_sample_f(bsdf, ray.d, ux, uy, BSDF_ALL, &f, &wi, &pdf, &sflags, lambert_only);
       if (!(is_black(f) || pdf == 0.0)) {
         double wiAbsDotPdf = fabs(dot(wi, h.ns)) / pdf;
         beta = beta * (f * wiAbsDotPdf);
@@ -1010,15 +1088,8 @@ GP_D void shade_lane_direct(const DevScene& sc, const Lanes& L, const RenderPara
       bool sample = true;
       if (!ALL) {
         double u = get1d(s, L, P, fast_pixel);
-        int size = sc.n_lights + 1, first = 0, len = size;
-        while (len > 0) {  // Distribution1D.SampleDiscrete (sampling.go:42-55) via FindInterval (pkg/math/math.go:64-80)
-          int half = len >> 1, middle = first + half;
-          if (sc.light_cdf[middle] <= u) { first = middle + 1; len -= half + 1; }
-          else len = half;
-        }
-        offset = (int)go_clamp((double)(first - 1), 0, (double)(size - 2));
-        double lightPdf = 0;
-        if (sc.light_func_int > 0) lightPdf = 1.0 / (sc.light_func_int / (double)sc.n_lights);
+        double lightPdf;
+        sample_discrete(sc.light_cdf, sc.n_lights, sc.light_func_int, u, &offset, &lightPdf);
         sample = lightPdf != 0.0;
       }
       const int n_loop = ALL ? sc.n_lights : 1;
@@ -1044,9 +1115,7 @@ GP_D void shade_lane_direct(const DevScene& sc, const Lanes& L, const RenderPara
               Ld = ((f * ls.Li) * weight) / ls.pdf;
             }
             Ld = rgb(0, 0, 0) + Ld;
-            V3 origin = offset_ray_origin(ref.p, ref.perr, ref.n, ls.p1.p - ref.p);
-            V3 target = offset_ray_origin(ls.p1.p, ls.p1.perr, ls.p1.n, origin - ls.p1.p);
-            V3 d = target - origin;
+            V3 d = spawn_ray_to(ref, ls.p1);
             ShadowRec sr;
             sr.ox = ref.p.x; sr.oy = ref.p.y; sr.oz = ref.p.z; sr.dx = d.x; sr.dy = d.y; sr.dz = d.z;
             sr.pr = Ld.r; sr.pg = Ld.g; sr.pb = Ld.b;   // L.AddAssign(Ld) on this level's sum
@@ -1129,13 +1198,28 @@ GP_D RGB direct_unwind(const Lanes& L, const RenderParams& P, long long lane, co
 // One Path.Li loop body per lane (path.go:40-155) after the closest-hit query: scattering functions, one light
 // sample (UniformSampleOneLight / EstimateDirect) whose visibility test is deferred to the shadow queue, BSDF
 // sampling, throughput update, SpawnRay, Russian roulette.
-template <int INTEG>
-__global__ void __launch_bounds__(128, 3) k_shade(DevScene sc, Lanes L, RenderParams P, Queues Q, RenderCounters* ctr) {
-  // lanes whose ray hit something, binned by shade class: the kernel walks the four bins back to back, each starting on
-  // a warp boundary, so that (almost) every warp shades one kind of hit
+// INTEG: 0 = Path, 1 = DirectLighting / UniformSampleOne, 2 = DirectLighting / UniformSampleAll.  MODE: sampler mode.
+// CLS (Path only): the ONE shade class this launch works on — 0 triangle + Lambert, 1 triangle + other material,
+// 2 sphere / disk + Lambert, 3 sphere / disk + other — or -1: all four bins back to back.  One instantiation per class
+// keeps the sphere / disk hit reconstruction (Go trig, two matrix pairs) and the Oren-Nayar / mirror / glass lobes out
+// of the kernel that shades the common case, whose register budget then allows more resident warps for what is one
+// long dependent float64 chain per lane.
+#ifndef GP_SHADE_BLOCKS0
+#define GP_SHADE_BLOCKS0 4
+#endif
+template <int CLS> struct ShadeBlocks { static constexpr int value = 3; };
+template <> struct ShadeBlocks<0> { static constexpr int value = GP_SHADE_BLOCKS0; };
+template <int INTEG, int MODE, int CLS>
+__global__ void __launch_bounds__(128, ShadeBlocks<CLS>::value) k_shade(DevScene sc, Lanes L, RenderParams P_in, Queues Q, RenderCounters* ctr) {
+  RenderParams P = P_in;
+  P.mode = MODE;
+  P.integrator = INTEG == 0 ? 0 : 1;
+  // lanes whose ray hit something, binned by shade class; CLS < 0: the kernel walks the four bins back to back, each
+  // starting on a warp boundary, so that (almost) every warp shades one kind of hit
   long long n0 = Q.cnt[8], n1 = Q.cnt[9], n2 = Q.cnt[10], n3 = Q.cnt[11];
   long long o1 = (n0 + 31) & ~31LL, o2 = o1 + ((n1 + 31) & ~31LL), o3 = o2 + ((n2 + 31) & ~31LL);
   long long n = o3 + n3;
+  if (CLS >= 0) n = Q.cnt[8 + (CLS >= 0 ? CLS : 0)];
   int lane_id = threadIdx.x & 31;
   unsigned long long n_unsupported = 0, n_dead = 0;
   int bad = 0;
@@ -1145,7 +1229,8 @@ __global__ void __launch_bounds__(128, 3) k_shade(DevScene sc, Lanes L, RenderPa
     long long i = cbase + threadIdx.x;
     const int* bin_q;
     long long bi;
-    if (i >= o3) { bin_q = Q.shade[3]; bi = i - o3; if (bi >= n3) bi = -1; }
+    if (CLS >= 0) { bin_q = Q.shade[CLS >= 0 ? CLS : 0]; bi = i < n ? i : -1; }
+    else if (i >= o3) { bin_q = Q.shade[3]; bi = i - o3; if (bi >= n3) bi = -1; }
     else if (i >= o2) { bin_q = Q.shade[2]; bi = i - o2; if (bi >= n2) bi = -1; }
     else if (i >= o1) { bin_q = Q.shade[1]; bi = i - o1; if (bi >= n1) bi = -1; }
     else { bin_q = Q.shade[0]; bi = i; if (bi >= n0) bi = -1; }
@@ -1155,7 +1240,7 @@ __global__ void __launch_bounds__(128, 3) k_shade(DevScene sc, Lanes L, RenderPa
     long long lane = 0;
     if (valid) {
       lane = bin_q[bi];
-      if (INTEG == 0) shade_lane(sc, L, P, lane, cont, finished, shadow, n_unsupported, n_dead, bad);
+      if (INTEG == 0) shade_lane(sc, L, P, lane, cont, finished, shadow, n_unsupported, n_dead, bad, CLS);
       else if (INTEG == 1) shade_lane_direct<false>(sc, L, P, lane, cont, finished, shadow, seg_mask, n_unsupported, n_dead, bad);
       else shade_lane_direct<true>(sc, L, P, lane, cont, finished, shadow, seg_mask, n_unsupported, n_dead, bad);
     }
@@ -1216,14 +1301,34 @@ __global__ void k_film_merge(Lanes L, RenderParams P, double* __restrict__ film)
         if (x < bx0 || x >= bx1 || y < by0 || y >= by1) continue;
         if (x - bx0 >= P.tpw || y - by0 >= P.tph) continue;  // the bound's last column / row: never touched by a sample, not stored
         size_t k = (size_t)((y - by0) * P.tpw + (x - bx0)) * 4;
+        if (P.uniform_fp) {  // tileSize 1: the tile is the pixel (x0, y0); is (x, y) inside its samples' footprint?
+          long long p0x, p0y, p1x, p1y;
+          uniform_footprint(P, x0, y0, bx0, by0, bx1, by1, &p0x, &p0y, &p1x, &p1y);
+          if (x < p0x || x >= p1x || y < p0y || y >= p1y) continue;
+        }
         for (int grp = 0; grp < P.groups; grp++) {  // the tile's lane groups in ascending order (one group in STRICT mode)
           long long lane = (tile / P.world) * P.groups + grp - P.lane_base;
           if (lane < 0 || lane >= P.lanes_active) continue;
-          const double* q = L.tilepix + (size_t)lane * L.tile_stride + k;
-          double r = q[0], g = q[1], b = q[2], w = q[3];
-          X += 0.412453 * r + 0.357580 * g + 0.180423 * b;
-          Y += 0.212671 * r + 0.715160 * g + 0.072169 * b;
-          Z += 0.019334 * r + 0.119193 * g + 0.950227 * b;
+          double r, g, b, w;
+          if (P.uniform_fp) {
+            const PathRec* pt = L.path + lane;
+            r = pt->pad[0]; g = pt->pad[1]; b = pt->pad[2];
+            // filterWeightSum = the samples this lane retired: indices 1 .. spp-1 (sampler.go:29-34) with
+            // s % (s_world * groups) == s_rank * groups + grp
+            const int s_mod = P.s_world * P.groups, s_res = P.s_rank * P.groups + grp;
+            int cnt = 0;
+            if (P.spp > 1) {
+              int first = s_res == 0 ? s_mod : s_res;  // the first index >= 1 in the residue class
+              if (first <= P.spp - 1) cnt = (P.spp - 1 - first) / s_mod + 1;
+            }
+            w = (double)cnt;
+          } else {
+            const double* q = L.tilepix + (size_t)lane * L.tile_stride + k;
+            r = q[0]; g = q[1]; b = q[2]; w = q[3];
+          }
+          double tx_, ty_, tz_;
+          rgb_to_xyz(r, g, b, &tx_, &ty_, &tz_);
+          X += tx_; Y += ty_; Z += tz_;
           W += w;
         }
       }

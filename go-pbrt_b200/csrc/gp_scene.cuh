@@ -296,14 +296,15 @@ GP_D bool quadric_test(const DevScene& sc, const PrimRec* rec, uint32_t flags, c
 // (primitive, t); everything here is a deterministic function of those, so recomputing it in the shade stage gives
 // the same bits the reference computes inside Shape.Intersect (sphere.go:137-185, disk.go:95-123) followed by
 // TransformedPrimitive.Intersect (primitive.go:104-106).
-GP_D void hit_record(const DevScene& sc, int rec_index, const Ray& wray_in, double tHit, Hit* h, int* prim_out, int& bad) {
+// tri_only (a compile-time constant at the call site): the hit's shade class says it is a triangle
+GP_D void hit_record(const DevScene& sc, int rec_index, const Ray& wray_in, double tHit, Hit* h, int* prim_out, int& bad, bool tri_only = false) {
   const PrimRec* rec = sc.recs + rec_index;
   uint32_t rflags = rec->flags;
   int prim = (int)rec->prim;
   *prim_out = prim;
   int4 pr = sc.prims[prim];
   Ray ray = wray_in;
-  if (pr.x == RK_TRIANGLE) {
+  if (tri_only || pr.x == RK_TRIANGLE) {
     const double* d = rec->d;
     V3 p0 = mk3(d[0], d[1], d[2]), p1 = mk3(d[3], d[4], d[5]), p2 = mk3(d[6], d[7], d[8]);
     double t, b[3];

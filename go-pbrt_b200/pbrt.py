@@ -621,9 +621,10 @@ Uniform, Power, Spatial = 1, 2, 4  # lightdistribution.go:5-9
 
 class Path:  # path.go:10-26
     def __init__(self, maxDepth, camera, sampler, pixelBounds, rrThreshold, lightSampleStrategy):
-        if lightSampleStrategy != Uniform:
-            raise NotImplementedError("PowerLightDistribution is meaningless in the reference (SURVEY §2 row 19)")
+        # Uniform, Power (reproduced bugs included: no light is ever sampled, lightdistribution.go:44-68) or Spatial (nil
+        # distribution in the reference: the library answers GOPBRT_ERR_UNSUPPORTED where path.go:80 panics)
         self.maxDepth, self.camera, self.sampler, self.rrThreshold = maxDepth, camera, sampler, rrThreshold
+        self.lightSampleStrategy = lightSampleStrategy
 
     def GetCamera(self):
         return self.camera
@@ -632,7 +633,7 @@ class Path:  # path.go:10-26
         return self.sampler
 
     def abi(self, tileSize):
-        return abi.Integrator(0, self.maxDepth, self.rrThreshold, Uniform, 0, tileSize)
+        return abi.Integrator(0, self.maxDepth, self.rrThreshold, self.lightSampleStrategy, 0, tileSize)
 
 
 NewPath = Path

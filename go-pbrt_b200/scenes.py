@@ -236,6 +236,12 @@ def config4(W=1920, H=1080, spp=(4, 4), grid=2237):
     return scene, integ
 
 
+def config4_integrator(W, H, spp=(4, 4)):
+    """config 4's camera and Path integrator at another resolution / sample count (for a scene that is already built)"""
+    cam = _camera((0.0, 15.0, 80.0), (0.0, 0.0, 0.0), (0.0, 1.0, 0.0), 50.0, W, H)
+    return P.NewPath(10, cam, P.NewStratified(spp[0], spp[1], False, 4), None, 1, P.Uniform)
+
+
 def config5(W=3840, H=2160, spp=(32, 32), grid=2237):
     """config-4 mesh at 4K, 1023 effective spp, meant to be split across 2/4/8 GPUs."""
     return config4(W, H, spp, grid)

@@ -168,9 +168,11 @@ enum {
   GOPBRT_INTEGRATOR_PATH = 0,            /* integrator.Path (pkg/integrator/path.go:32-157)                              */
   GOPBRT_INTEGRATOR_DIRECT_LIGHTING = 1  /* integrator.DirectLighting (pkg/integrator/directlighting.go:62-104)          */
 };
-/* light_strategy: Path -> the LightSampleStrategy of lightdistribution.go:5-9 (only Uniform = 1 is reachable);
+/* light_strategy: Path -> the LightSampleStrategy of lightdistribution.go:5-9 (Uniform = 1, Power = 2, Spatial = 4).
+ *   Power is reproduced bugs included (lightdistribution.go:57-68 appends to a zero-filled slice and Spectrum.Y() is 0, so
+ *   no light is ever sampled); Spatial has no distribution in the reference (nil, path.go:80 panics) -> GOPBRT_ERR_UNSUPPORTED.
  * DirectLighting -> its LightStrategy (directlighting.go:12-15): 1 = UniformSampleAll, 2 = UniformSampleOne */
-enum { GOPBRT_LIGHTS_UNIFORM = 1 };
+enum { GOPBRT_LIGHTS_UNIFORM = 1, GOPBRT_LIGHTS_POWER = 2, GOPBRT_LIGHTS_SPATIAL = 4 };
 enum { GOPBRT_DL_SAMPLE_ALL = 1, GOPBRT_DL_SAMPLE_ONE = 2 };
 
 /* integrator.NewPath(maxDepth, camera, sampler, pixelBounds, rrThreshold, strategy) (path.go:10-18) or
@@ -278,6 +280,15 @@ int gopbrt_render_device(gopbrt_scene*, const gopbrt_camera*, const gopbrt_sampl
                          const gopbrt_film*, const gopbrt_render_options*, double* d_film, gopbrt_stats* stats_out);
 /* thread-safe; makes a running gopbrt_render return GOPBRT_ERR_CANCELLED between wavefront iterations */
 int gopbrt_cancel(gopbrt_scene*);
+
+/* Self-test hook (tests/test_shading_kats.py): evaluates ONE device function of the raygen / shade / film stages on the GPU,
+ * single thread, on flat float64 arguments, so the functions the kernels call can be pinned against known answers derived
+ * independently of the oracle (FrDielectric reflection.go:21-42, OrenNayar.F :616-652, FresnelSpecular.SampleF :482-523,
+ * BSDF.SampleF :183-253, the sampling warps sampling.go:173-198, Distribution1D.SampleDiscrete :42-55, the lights' SampleLi,
+ * FilmTile.AddSample film.go:211-248, RGBToXYZ spectrum.go:35-41, the RNG rng.go:28-57, Stratified.StartPixel
+ * stratified.go:21-48, GenerateRayDifferential camera.go:192-242, SpawnRayToInteraction interaction.go:91-102).
+ * fn: index into the KAT_* list of csrc/gp_kat.cuh.  Returns the number of doubles written, or -GOPBRT_ERR_*. */
+int gopbrt_kat_eval(gopbrt_scene*, int fn, const double* in, int n_in, double* out, int n_out);
 
 /* number of kernel launches this library has issued on the ctx since init (bench.py "gpu_launches") */
 uint64_t gopbrt_launch_count(const gopbrt_ctx*);

@@ -5,6 +5,7 @@
 //   g++ -O2 -std=c++17 -ffp-contract=off -fPIC -shared -pthread
 #include <chrono>
 #include <cstring>
+#include <string>
 
 #include "oracle_render.h"
 
@@ -162,5 +163,146 @@ void oracle_kat_sampler(const gopbrt_sampler* cfg, uint64_t seed, int n_pixels_s
   for (int k = 0; k < sample_idx; k++) s.start_next_sample();
   for (int i = 0; i < n; i++) out1d[i] = s.get1d();
   for (int i = 0; i < n; i++) { P2 p = s.get2d(); out2d[2 * i] = p.x; out2d[2 * i + 1] = p.y; }
+}
+
+// ---- generic known-answer hook: evaluates ONE oracle function on flat float64 arguments (tests/test_shading_kats.py
+// checks it against tests/golden/shading_kats.json, the independent plain-Python restatement of the cited Go lines).
+// Returns the number of doubles written, or -1 for an unknown function / bad argument count.
+int oracle_kat_eval(void* scene, const char* fn_c, const double* in, int n_in, double* out, int n_out) {
+  std::string fn(fn_c);
+  auto v3 = [&](int i) { return V3{in[i], in[i + 1], in[i + 2]}; };
+  auto put3 = [&](int i, V3 v) { out[i] = v.x; out[i + 1] = v.y; out[i + 2] = v.z; };
+  auto putc = [&](int i, RGB c) { out[i] = c.c[0]; out[i + 1] = c.c[1]; out[i + 2] = c.c[2]; };
+  if (fn == "fr_dielectric" && n_in == 3 && n_out >= 1) { out[0] = fr_dielectric(in[0], in[1], in[2]); return 1; }
+  if (fn == "oren_nayar_f" && n_in == 10 && n_out >= 3) {
+    BxDF x = make_oren_nayar(RGB(in[1], in[2], in[3]), in[0]);
+    putc(0, bxdf_f(x, v3(4), v3(7)));
+    return 3;
+  }
+  if (fn == "fresnel_specular_sample_f" && n_in == 12 && n_out >= 8) {
+    BxDF x;
+    x.kind = BX_FRESNEL_SPECULAR; x.type = BSDF_REFLECTION | BSDF_TRANSMISSION | BSDF_SPECULAR;
+    x.r = RGB(in[0], in[1], in[2]); x.t = RGB(in[3], in[4], in[5]); x.etaA = 1.0; x.etaB = in[6];
+    RGB f; V3 wi; double pdf; int st;
+    bxdf_sample_f(x, v3(7), P2{in[10], in[11]}, &f, &wi, &pdf, &st);
+    putc(0, f); put3(3, wi); out[6] = pdf; out[7] = (double)st;
+    return 8;
+  }
+  if (fn == "concentric_sample_disk" && n_in == 2 && n_out >= 2) { P2 d = concentric_sample_disk(P2{in[0], in[1]}); out[0] = d.x; out[1] = d.y; return 2; }
+  if (fn == "cosine_sample_hemisphere" && n_in == 2 && n_out >= 3) { put3(0, cosine_sample_hemisphere(P2{in[0], in[1]})); return 3; }
+  if (fn == "lambert_sample_f" && n_in == 8 && n_out >= 7) {
+    // BSDF.SampleF (reflection.go:183-253) over one Lambertian lobe in the identity shading frame: returns the LOCAL wi
+    BSDF b;
+    b.ns = V3{0, 0, 1}; b.ng = V3{0, 0, 1}; b.ss = V3{1, 0, 0}; b.ts = V3{0, 1, 0};
+    BxDF x; x.kind = BX_LAMBERT; x.type = BSDF_REFLECTION | BSDF_DIFFUSE; x.r = RGB(in[0], in[1], in[2]);
+    b.bx[b.n++] = x;
+    RGB f; V3 wi; double pdf; int st;
+    bsdf_sample_f(b, v3(3), P2{in[6], in[7]}, BSDF_ALL, &f, &wi, &pdf, &st);
+    putc(0, f); put3(3, wi); out[6] = pdf;
+    return 7;
+  }
+  if (fn == "offset_ray_origin" && n_in == 12 && n_out >= 3) { put3(0, offset_ray_origin(v3(0), v3(3), v3(6), v3(9))); return 3; }
+  if (fn == "coordinate_system" && n_in == 3 && n_out >= 6) { V3 a, b; coordinate_system(v3(0), &a, &b); put3(0, a); put3(3, b); return 6; }
+  if (fn == "sample_discrete_uniform" && n_in == 2 && n_out >= 2) {
+    int n = (int)in[0];
+    std::vector<double> cdf;
+    double func_int;
+    uniform_light_distribution(n, &cdf, &func_int);
+    int off; double pdf;
+    sample_discrete(cdf, func_int, in[1], &off, &pdf);
+    out[0] = off; out[1] = pdf;
+    return 2;
+  }
+  if (fn == "rgb_to_xyz" && n_in == 3 && n_out >= 3) {
+    // through the film: one tile holding the value, merged into a one-pixel film (film.go:115-132 + spectrum.go:35-41)
+    gopbrt_film fc{1, 1, {0, 0, 1, 1}, {0.5, 0.5}};
+    FilmCfg f = film_cfg(fc);
+    FilmTile t = film_tile(f, Bounds2i{0, 0, 1, 1});
+    t.px[0] = in[0]; t.px[1] = in[1]; t.px[2] = in[2];
+    double film[4] = {0, 0, 0, 0};
+    film_merge(f, t, film);
+    out[0] = film[0]; out[1] = film[1]; out[2] = film[2];
+    return 3;
+  }
+  if (fn == "film_add_sample" && n_in == 11) {
+    gopbrt_film fc{(int)in[0], (int)in[1], {0, 0, 1, 1}, {in[3], in[4]}};
+    FilmCfg f = film_cfg(fc);
+    int64_t ts = (int64_t)in[2], tile = (int64_t)in[5];
+    int64_t ntx = ((int64_t)in[0] + ts - 1) / ts, tx = tile % ntx, ty = tile / ntx;
+    int64_t x0 = tx * ts, y0 = ty * ts;
+    int64_t x1 = (int64_t)gm::Min((double)(x0 + ts), (double)f.cropped.x1), y1 = (int64_t)gm::Min((double)(y0 + ts), (double)f.cropped.y1);
+    FilmTile t = film_tile(f, Bounds2i{x0, y0, x1, y1});
+    film_add_sample(f, t, P2{in[6], in[7]}, RGB(in[8], in[9], in[10]), 1.0);
+    int k = 0;
+    if (n_out < 4) return -1;
+    out[k++] = (double)t.pb.x0; out[k++] = (double)t.pb.y0; out[k++] = (double)t.pb.x1; out[k++] = (double)t.pb.y1;
+    int64_t w = t.pb.x1 - t.pb.x0;
+    for (int64_t y = t.pb.y0; y < t.pb.y1; y++)
+      for (int64_t x = t.pb.x0; x < t.pb.x1; x++) {
+        const double* p = &t.px[((x - t.pb.x0) + (y - t.pb.y0) * w) * 4];
+        if (p[3] == 0) continue;  // pixels of the tile the sample did not touch
+        if (k + 6 > n_out) return -1;
+        out[k++] = (double)x; out[k++] = (double)y; out[k++] = p[0]; out[k++] = p[1]; out[k++] = p[2]; out[k++] = p[3];
+      }
+    return k;
+  }
+  if (fn == "rng_u32" && n_in == 3) {
+    Rng r;
+    if (in[0] != 0) r.set_sequence((uint64_t)in[1]);
+    int n = (int)in[2];
+    if (n > n_out) return -1;
+    for (int i = 0; i < n; i++) out[i] = (double)r.u32();
+    return n;
+  }
+  if (fn == "rng_uniform" && n_in == 2) {
+    Rng r; r.set_sequence((uint64_t)in[0]);
+    int n = (int)in[1];
+    if (n > n_out) return -1;
+    for (int i = 0; i < n; i++) out[i] = r.uniform();
+    return n;
+  }
+  if (fn == "rng_u32b" && n_in == 3) {
+    Rng r; r.set_sequence((uint64_t)in[0]);
+    int b = (int)in[1], n = (int)in[2];
+    if (n > n_out) return -1;
+    for (int i = 0; i < n; i++) out[i] = (double)r.u32b((uint32_t)(b - i));
+    return n;
+  }
+  if (fn == "stratified_start_pixel" && n_in == 5) {
+    gopbrt_sampler cfg{GOPBRT_SAMPLER_STRATIFIED, (int)in[1], (int)in[2], (int)in[3], (int)in[4], GOPBRT_MODE_STRICT};
+    Sampler s;
+    s.init(cfg);
+    s.clone_seed((uint64_t)in[0]);
+    s.start_pixel();
+    int k = 0;
+    for (auto& t : s.s1d) for (double v : t) { if (k >= n_out) return -1; out[k++] = v; }
+    for (auto& t : s.s2d) for (const P2& v : t) if (v.x != 0 || v.y != 0) return -1;  // the 2-D tables stay all zeros
+    if (k + 2 > n_out) return -1;
+    out[k++] = s.rng.uniform(); out[k++] = s.rng.uniform();
+    return k;
+  }
+  if (fn == "light_sample_li" && n_in == 12 && n_out >= 17 && scene) {
+    const Scene* sc = (const Scene*)scene;
+    int li = (int)in[0];
+    if (li < 0 || li >= (int)sc->lights.size()) return -1;
+    LightSample ls;
+    light_sample_li(*sc, sc->lights[li], Intr{v3(1), v3(4), v3(7)}, P2{in[10], in[11]}, &ls);
+    putc(0, ls.Li); put3(3, ls.wi); out[6] = ls.pdf; put3(7, ls.p1.p); put3(10, ls.p1.perr); put3(13, ls.p1.n); out[16] = ls.delta ? 1.0 : 0.0;
+    return 17;
+  }
+  if (fn == "spawn_ray_to" && n_in == 18 && n_out >= 7) {
+    Ray r = spawn_ray_to(Intr{v3(0), v3(3), v3(6)}, Intr{v3(9), v3(12), v3(15)}, 0);
+    put3(0, r.o); put3(3, r.d); out[6] = r.tmax;
+    return 7;
+  }
+  if (fn == "camera_ray" && n_in == 38 && n_out >= 6) {
+    gopbrt_camera c;
+    for (int i = 0; i < 16; i++) { c.raster_to_camera[i] = in[i]; c.camera_to_world[i] = in[16 + i]; }
+    c.lens_radius = in[32]; c.focal_distance = in[33]; c.shutter_open = 0; c.shutter_close = 0;
+    Ray r = camera_ray(c, P2{in[34], in[35]}, P2{in[36], in[37]}, 0.0);
+    put3(0, r.o); put3(3, r.d);
+    return 6;
+  }
+  return -1;
 }
 }

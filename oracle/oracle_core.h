@@ -874,6 +874,18 @@ static inline bool scene_intersect_p(const Scene& sc, const Ray& ray, TravStats*
 
 static inline bool valid_index(int64_t i, int64_t n) { return i >= 0 && i < n; }
 
+// NewUniformLightDistribution + NewDistribution1D (lightdistribution.go:25-34, sampling.go:11-40): func[i] = 1
+static inline void uniform_light_distribution(int n, std::vector<double>* cdf, double* func_int) {
+  cdf->assign(n + 1, 0.0);
+  for (int i = 1; i < n + 1; i++) (*cdf)[i] = (*cdf)[i - 1] + 1.0 / (double)n;
+  *func_int = n ? (*cdf)[n] : 0.0;
+  if (*func_int == 0.0) {
+    for (int i = 1; i < n + 1; i++) (*cdf)[i] = (double)i / (double)n;
+  } else {
+    for (int i = 1; i < n + 1; i++) (*cdf)[i] /= *func_int;
+  }
+}
+
 // accelerator.NewBVH + pbrt.NewScene (bvh.go:223-270, scene.go:16-36)
 static inline Scene* scene_from_desc(const gopbrt_scene_desc* d, int accel_mode) {
   Scene* sc = new Scene();
@@ -905,16 +917,7 @@ static inline Scene* scene_from_desc(const gopbrt_scene_desc* d, int accel_mode)
   }
   build_accel(*sc);
   if (sc->world.valid) b3_bounding_sphere(sc->world, &sc->world_center, &sc->world_radius);
-  // NewUniformLightDistribution + NewDistribution1D (lightdistribution.go:25-34, sampling.go:11-40)
-  int n = (int)sc->lights.size();
-  sc->light_cdf.assign(n + 1, 0.0);
-  for (int i = 1; i < n + 1; i++) sc->light_cdf[i] = sc->light_cdf[i - 1] + 1.0 / (double)n;
-  sc->light_func_int = n ? sc->light_cdf[n] : 0.0;
-  if (sc->light_func_int == 0.0) {
-    for (int i = 1; i < n + 1; i++) sc->light_cdf[i] = (double)i / (double)n;
-  } else {
-    for (int i = 1; i < n + 1; i++) sc->light_cdf[i] /= sc->light_func_int;
-  }
+  uniform_light_distribution((int)sc->lights.size(), &sc->light_cdf, &sc->light_func_int);
   return sc;
 }
 

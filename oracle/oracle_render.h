@@ -247,6 +247,18 @@ struct BSDF {
   BxDF bx[2];
 };
 static inline bool matches(int t, int flags) { return (t & flags) == t; }  // reflection.go:301-303
+// NewOrenNayar (reflection.go:616-626) (b = 0.45 s2 / (s2 * 0.09))
+static inline BxDF make_oren_nayar(RGB r, double sigma_deg) {
+  BxDF x;
+  x.kind = BX_OREN_NAYAR;
+  x.type = BSDF_REFLECTION | BSDF_DIFFUSE;
+  x.r = r;
+  double s = gm::Pi / 180.0 * sigma_deg;
+  double s2 = s * s;
+  x.a = 1.0 - (s2 / (2.0 * (s2 + 0.33)));
+  x.b = 0.45 * s2 / (s2 * 0.09);
+  return x;
+}
 static inline double fr_dielectric(double cosThetaI, double etaI, double etaT) {  // reflection.go:21-42
   cosThetaI = gm::Clamp(cosThetaI, -1, 1);
   bool entering = cosThetaI > 0;
@@ -474,13 +486,7 @@ static inline bool compute_scattering(const Scene& sc, const Hit& h, BSDF* b, Re
         x.type = BSDF_REFLECTION | BSDF_DIFFUSE;
         x.r = r;
         if (sig == 0) x.kind = BX_LAMBERT;
-        else {  // NewOrenNayar (reflection.go:616-626) (b = 0.45 s2 / (s2 * 0.09))
-          x.kind = BX_OREN_NAYAR;
-          double s = gm::Pi / 180.0 * sig;
-          double s2 = s * s;
-          x.a = 1.0 - (s2 / (2.0 * (s2 + 0.33)));
-          x.b = 0.45 * s2 / (s2 * 0.09);
-        }
+        else x = make_oren_nayar(r, sig);
         b->bx[b->n++] = x;
       }
       return true;
@@ -639,7 +645,7 @@ static inline void light_sample_li(const Scene& sc, const gopbrt_light& l, const
 }
 
 // ---------------------------------------------------------------- integrator
-struct Integ { int maxDepth; double rr; };
+struct Integ { int maxDepth; double rr; bool power = false; };
 
 // EstimateDirect (integrator.go:79-195) for a SurfaceInteraction, handleMedia=false, specular=false
 static inline RGB estimate_direct(const Scene& sc, const Hit& h, const BSDF& bsdf, P2 uScattering, const gopbrt_light& light,
@@ -679,20 +685,32 @@ static inline RGB estimate_direct(const Scene& sc, const Hit& h, const BSDF& bsd
   return Ld;
 }
 
-// UniformSampleOneLight (integrator.go:48-77) with SampleDiscrete (sampling.go:42-55, math.go:64-80)
-static inline RGB uniform_sample_one_light(const Scene& sc, const Hit& h, const BSDF& bsdf, Sampler& smp, RenderStats* st) {
+// Distribution1D.SampleDiscrete (sampling.go:42-55) via FindInterval (pkg/math/math.go:64-80); func[i] == 1 (uniform)
+static inline void sample_discrete(const std::vector<double>& cdf, double func_int, double u, int* offset_out, double* pdf_out) {
+  int size = (int)cdf.size(), first = 0, len = size;
+  while (len > 0) {
+    int half = len >> 1, middle = first + half;
+    if (cdf[middle] <= u) { first = middle + 1; len -= half + 1; }
+    else len = half;
+  }
+  *offset_out = (int)gm::Clamp((double)(first - 1), 0, (double)(size - 2));
+  double pdf = 0;
+  if (func_int > 0) pdf = 1.0 / (func_int / (double)(size - 1));
+  *pdf_out = pdf;
+}
+
+// UniformSampleOneLight (integrator.go:48-77).  power_strategy: Path with LightSampleStrategy Power —
+// ComputeLightPowerDistribution (lightdistribution.go:57-68) APPENDS the powers to a slice it already made n long, and
+// every power is Spectrum.Y() == 0 (spectrum.go:227-229): 2n zeros, FuncInt == 0, so SampleDiscrete's pdf is 0 and the
+// function returns black right after its Get1D.
+static inline RGB uniform_sample_one_light(const Scene& sc, const Hit& h, const BSDF& bsdf, Sampler& smp, RenderStats* st, bool power_strategy = false) {
   int nLights = (int)sc.lights.size();
   if (nLights == 0) return RGB(0);
   double u = smp.get1d();
-  int size = nLights + 1, first = 0, len = size;
-  while (len > 0) {
-    int half = len >> 1, middle = first + half;
-    if (sc.light_cdf[middle] <= u) { first = middle + 1; len -= half + 1; }
-    else len = half;
-  }
-  int offset = (int)gm::Clamp((double)(first - 1), 0, (double)(size - 2));
-  double lightPdf = 0;
-  if (sc.light_func_int > 0) lightPdf = 1.0 / (sc.light_func_int / (double)nLights);
+  if (power_strategy) return RGB(0);
+  int offset;
+  double lightPdf;
+  sample_discrete(sc.light_cdf, sc.light_func_int, u, &offset, &lightPdf);
   if (lightPdf == 0.0) return RGB(0);
   P2 uLight = smp.get2d();
   P2 uScattering = smp.get2d();
@@ -722,7 +740,7 @@ static inline RGB path_li(const Scene& sc, Ray ray, Sampler& smp, const Integ& i
     BSDF bsdf;
     if (!compute_scattering(sc, isect, &bsdf, st)) break;
     if (bsdf_num_components(bsdf, BSDF_ALL & ~BSDF_SPECULAR) > 0) {
-      RGB Ld = smul(beta, uniform_sample_one_light(sc, isect, bsdf, smp, st));
+      RGB Ld = smul(beta, uniform_sample_one_light(sc, isect, bsdf, smp, st, ig.power));
       L = sadd(L, Ld);
     }
     V3 wo = ray.d;  // sic: not negated (path.go:91)
@@ -914,7 +932,7 @@ static inline void render(const Scene& sc, const gopbrt_camera& cam, const gopbr
   std::mutex mu;
   RenderStats total;
   std::vector<std::vector<FilmTile>> done(std::max(1, opt.threads));
-  Integ ig{icfg.max_depth, icfg.rr_threshold};
+  Integ ig{icfg.max_depth, icfg.rr_threshold, icfg.kind == GOPBRT_INTEGRATOR_PATH && icfg.light_strategy == 2};
   DirectCfg dcfg{icfg.max_depth, icfg.light_strategy};
   auto worker = [&](int tid) {
     RenderStats st;

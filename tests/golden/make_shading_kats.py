@@ -306,11 +306,20 @@ def cosine_sample_hemisphere(u, cos, sin):  # sampling.go:194-198
     return [d[0], d[1], z]
 
 
-def lambert_sample_f(R, wo, u, cos, sin):  # sampleF reflection.go:305-314 + LambertianReflection.F :589-591 + pdf :343-348
-    wi = cosine_sample_hemisphere(u, cos, sin)
+def lambert_sample_f(R, wo, u, cos, sin):
+    """BSDF.SampleF (reflection.go:183-253) over ONE Lambertian lobe in the identity shading frame (wo local == world):
+    sampleF :305-314 + LambertianReflection.F :589-591 + pdf :343-348; returns the LOCAL wi (wiWorld is discarded)"""
+    z3 = [0.0, 0.0, 0.0]
+    comp = go_min(math.floor(u[0] * 1.0), 1.0 - 1)
+    ur = [go_min(u[0] * 1.0 - comp, ONE_MINUS_EPSILON), u[1]]
+    if wo[2] == 0.0:
+        return z3, z3, 0.0
+    wi = cosine_sample_hemisphere(ur, cos, sin)
     if wo[2] < 0:
         wi[2] *= -1
     pdf = abs(wi[2]) * INV_PI if wo[2] * wi[2] > 0 else 0.0
+    if pdf == 0.0:
+        return z3, z3, 0.0
     return [R[0] * INV_PI, R[1] * INV_PI, R[2] * INV_PI], wi, pdf
 
 
@@ -574,7 +583,7 @@ def main():
             for wo in ([0.1, 0.2, 0.9746794344808963], [0.1, 0.2, -0.9746794344808963]):
                 R = [0.73, 0.5, 0.1]
                 f, wi, pdf = lambert_sample_f(R, wo, u, *tr)
-                add("lambert_sample_f", trig, R + wo + u, f + wi + [pdf], "reflection.go:305-314,343-348,589-591")
+                add("lambert_sample_f", trig, R + wo + u, f + wi + [pdf], "reflection.go:183-253,305-314,343-348,589-591")
 
     for p, pe, n, w in [([0, 0, 0], [5e-324] * 3, [1, 1, 1], [1, 1, 1]), ([1.5, -2.25, 3.0], [1e-320, 0.0, 2e-322], [0.0, 0.6, -0.8], [0.3, -1.0, 0.2]),
                         ([10.0, 10.0, 10.0], [0.0, 0.0, 0.0], [0.0, 1.0, 0.0], [0.0, -1.0, 0.0]), ([-1.0, 0.99, 0.25], [5e-323, 1e-322, 5e-324], [0.0, -1.0, 0.0], [0.1, -0.5, 0.0])]:

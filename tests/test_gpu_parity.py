@@ -9,15 +9,19 @@ from oracle_lib import OracleScene, camera_rays
 pytestmark = pytest.mark.gpu
 
 
-def _cmp_closest(g, o, what):
-    """hit/miss and t bit-exact; primitive ids bit-exact except exact ties (two primitives hit at the very same t, e.g. a
-    ray through the shared edge of two triangles), which the reference resolves by BVH visit order"""
+def _cmp_closest(g, o, what, reference_order=False):
+    """hit/miss, t, primitive id, hit point and normal bit-exact.  Against the parity-spec oracle (accel 1 / 2) nothing is
+    tolerated: the closest hit is defined order-independently.  reference_order=True (the oracle running the
+    reference's own tree, visit order and running tMax, accel 0): two primitives hit at the very same t go to whichever the
+    reference's tree visits first, so up to n/20000 primitive ids may differ; the count is printed."""
     gp_, gt, gpnt, gn = g
     op, ot, opnt, on = o
     assert np.array_equal(gp_ >= 0, op >= 0), f"{what}: hit/miss differs on {np.count_nonzero((gp_ >= 0) != (op >= 0))} rays"
     assert np.array_equal(gt, ot), f"{what}: t differs on {np.count_nonzero(gt != ot)} rays"
     ties = gp_ != op
-    assert np.count_nonzero(ties) <= max(1, len(op) // 20000), f"{what}: {np.count_nonzero(ties)} primitive ids differ of {len(op)}"
+    print(f"[parity] {what}: {len(op)} rays, {np.count_nonzero(op >= 0)} hits, {np.count_nonzero(ties)} primitive-id ties")
+    allowed = max(1, len(op) // 20000) if reference_order else 0
+    assert np.count_nonzero(ties) <= allowed, f"{what}: {np.count_nonzero(ties)} primitive ids differ of {len(op)}"
     same = ~ties
     assert np.array_equal(gpnt[same], opnt[same]) and np.array_equal(gn[same], on[same]), f"{what}: hit point / normal differ"
 
@@ -64,7 +68,7 @@ def test_config1_primary_rays_bit_exact(gp, dev):
     res = g.Intersect(o, d)
     for accel in (0, 1):
         s = OracleScene(scene, accel)
-        _cmp_closest(res, s.intersect(o, d), f"config1 primary accel={accel}")
+        _cmp_closest(res, s.intersect(o, d), f"config1 primary accel={accel}", reference_order=accel == 0)
         assert np.array_equal(g.IntersectP(o, d), s.intersect_p(o, d))
         s.close()
     assert np.count_nonzero(res[0] >= 0) > 0.5 * len(o)
@@ -91,7 +95,7 @@ def test_config1_secondary_rays_bit_exact(gp, dev):
     o, d = camera_rays(integ, xs.ravel(), ys.ravel())
     p, dirs = _secondary_rays(s, o, d, 1)
     _cmp_closest(g.Intersect(p, dirs), s.intersect(p, dirs), "config1 secondary")
-    _cmp_closest(g.Intersect(p, dirs), s0.intersect(p, dirs), "config1 secondary vs reference BVH")
+    _cmp_closest(g.Intersect(p, dirs), s0.intersect(p, dirs), "config1 secondary vs reference BVH", reference_order=True)
     to_light = np.array([50.0, 20.0, 50.0]) - p  # shadow rays toward the point light, tMax = 1 - ShadowEpsilon
     assert np.array_equal(g.IntersectP(p, to_light, 0.9999), s.intersect_p(p, to_light, 0.9999))
     assert np.array_equal(g.IntersectP(p, to_light, 0.9999), s0.intersect_p(p, to_light, 0.9999))
@@ -205,6 +209,100 @@ def test_fast_mode_film_bit_exact_and_statistically_close_to_strict(gp, dev):
     integ = gp.scenes.test_integrator(96, 64, spp=(4, 4), maxDepth=5)
     film, st, ofilm, ost = _render_both(gp, dev, scene, integ, 1, mode=gp.abi.MODE_FAST, groups=1)
     _assert_film_equal(film, ofilm, st, ost, "fast mode")
+
+
+@pytest.mark.parametrize("depth", ["direct", "full"])
+@pytest.mark.parametrize("config", ["config1", "config2"])
+def test_fast_mode_is_statistically_equivalent_to_strict(gp, dev, config, depth):
+    """SURVEY §8d tier 3.  FAST (counter-based streams per (pixel, sample): the mode that splits by sample index) and STRICT
+    (the unmodified reference's per-tile streams) draw different random numbers for the same estimator, so their films
+    differ by Monte-Carlo noise only.  The per-sample films X_s (FAST, rank s of world = spp renders exactly sample s)
+    give the per-pixel sample standard deviation sigma; with n = spp - 1 samples per pixel, D = (FAST - STRICT) / n:
+      * image RMSE of D             <= 3 * rms(sigma) / sqrt(n)                    (the survey's bar)
+      * |D| > 4 * sigma * sqrt(2/n)  on at most 1 % of the pixels with sigma > 0   (two independent n-sample means)
+      * |mean(FAST) - mean(STRICT)| <= max(0.1 % of the mean, 4 standard errors)  (0.1 % is the survey's bar at 1080p;
+        at this test's 160 x 90 the standard error of the image mean is larger than that and is what binds)
+    and the weights (filterWeightSum) are identical.
+    depth = "direct": maxDepth 2, i.e. the direct light at the first hit — a bounded integrand, every pixel counts.
+    depth = "full":   the configuration's own maxDepth 10.  The reference's estimator is heavy-tailed there: BSDF.SampleF
+        hands back the LOCAL wi, so beta *= f * |wi . ns| / pdf keeps the 1 / |cos theta| of every specular
+        lobe (mirror, glass) — single samples of 1e8 .. 1e14 occur in both modes and no sample mean converges, so the
+        three bars above are not defined.  The test then uses statistics that do not need moments: the pixels whose two
+        means both stay below 10 (the reference's own sanity bound, integrator.go:73-75; the rule is symmetric in the
+        two films, so it cannot favour one) must be most of the image, their mean difference must vanish within four
+        EMPIRICAL standard errors (std of D over those pixels, 4 pixels per independent footprint), and the median of
+        |D| must match what sigma predicts for two independent n-sample means (0.6745 * sigma * sqrt(2/n)) within a
+        factor of two.
+    """
+    P = gp.pbrt
+    scene, integ = getattr(gp.scenes, config)(W=160, H=90)
+    if depth == "direct":
+        integ = P.NewPath(2, integ.GetCamera(), integ.GetSampler(), None, 1, P.Uniform)
+    spp = integ.GetSampler().GetSamplesPerPixel()
+    n = spp - 1
+    g = P.GpuScene(dev, scene)
+    P.Render(g, integ, 1)
+    strict = integ.GetCamera().GetFilm().pixels.copy()
+    P.Render(g, integ, 1, mode=gp.abi.MODE_FAST)
+    fast = integ.GetCamera().GetFilm().pixels.copy()
+    s1 = np.zeros(strict.shape[:2] + (3,))
+    s2 = np.zeros_like(s1)
+    for s in range(1, spp):  # rank s of world spp owns exactly sample index s (rank 0 owns none: indices start at 1)
+        P.Render(g, integ, 1, mode=gp.abi.MODE_FAST, rank=s, world=spp)
+        x = integ.GetCamera().GetFilm().pixels[..., :3]
+        s1 += x
+        s2 += x * x
+    g.close()
+    assert np.array_equal(fast[..., 3], strict[..., 3])
+    assert np.allclose(s1, fast[..., :3], rtol=1e-12, atol=1e-300)  # the per-sample films are the FAST film, split
+    F, S = fast[..., :3] / n, strict[..., :3] / n
+    var = np.maximum(s2 / n - (s1 / n) ** 2, 0.0) * n / (n - 1)
+    sigma = np.sqrt(var)
+    if depth == "full":
+        keep = np.broadcast_to(((F <= 10.0) & (S <= 10.0)).all(axis=2, keepdims=True), F.shape)
+        D = (F - S)[keep]
+        se = D.std() / np.sqrt(D.size / 4.0)
+        lit = sigma[keep] > 0
+        mad = np.median(np.abs(D[lit]))
+        pred = np.median(0.6745 * sigma[keep][lit] * np.sqrt(2.0 / n))
+        print(f"[tier3] {config} full: n={n} pixels kept {100 * keep.mean():.1f}% mean FAST={F[keep].mean():.6g} STRICT={S[keep].mean():.6g} "
+              f"diff={D.mean():.4g} 4SE={4 * se:.4g} median|D|={mad:.4g} predicted={pred:.4g}")
+        assert keep.mean() >= 0.6, f"only {100 * keep.mean():.1f}% of the pixels are free of heavy-tail samples"
+        assert abs(D.mean()) <= 4.0 * se
+        assert 0.5 * pred <= mad <= 2.0 * pred
+        return
+    D = F - S
+    rmse = np.sqrt(np.mean(D ** 2))
+    bar = 3.0 * np.sqrt(np.mean(var)) / np.sqrt(n)
+    lit = sigma > 0
+    out = np.count_nonzero(np.abs(D[lit]) > 4.0 * sigma[lit] * np.sqrt(2.0 / n)) / max(1, np.count_nonzero(lit))
+    mean_f, mean_s = F.mean(), S.mean()
+    se = np.sqrt(2.0 * np.mean(var) / n / (D.size / 4.0))  # standard error of the difference of the two image means
+    print(f"[tier3] {config} direct: n={n} RMSE(D)={rmse:.4g} bar={bar:.4g} outliers={100 * out:.2f}% "
+          f"mean FAST={mean_f:.6g} STRICT={mean_s:.6g} diff={abs(mean_f - mean_s) / mean_s * 100:.3f}% 4SE={4 * se / mean_s * 100:.3f}%")
+    assert rmse <= bar
+    assert out <= 0.01
+    assert abs(mean_f - mean_s) <= max(1e-3 * mean_s, 4.0 * se)
+
+
+def test_path_power_light_strategy_and_spatial(gp, dev):
+    # LightSampleStrategy Power (lightdistribution.go:44-68), bugs included: the distribution is 2n zeros, SampleDiscrete's
+    # pdf is 0, so UniformSampleOneLight returns black after its one Get1D — no shadow ray is ever traced and the film
+    # carries weights only.  Spatial has no distribution at all in the reference (nil): GOPBRT_ERR_UNSUPPORTED.
+    P = gp.pbrt
+    scene = gp.scenes.mixed_test_scene(80, seed=5)
+    base = gp.scenes.test_integrator(96, 64, spp=(3, 3), maxDepth=6)
+    integ = P.NewPath(6, base.GetCamera(), base.GetSampler(), None, 1, P.Power)
+    film, st, ofilm, ost = _render_both(gp, dev, scene, integ, 8)
+    _assert_film_equal(film, ofilm, st, ost, "Path / Power")
+    assert st["shadow_rays"] == 0 and st["closest_rays"] > st["camera_rays"] and not film[..., :3].any()
+    uni = P.NewPath(6, base.GetCamera(), base.GetSampler(), None, 1, P.Uniform)
+    film_u, st_u, _, _ = _render_both(gp, dev, scene, uni, 8)
+    assert st_u["shadow_rays"] > 0 and film_u[..., :3].any()
+    g = P.GpuScene(dev, scene)
+    with pytest.raises(RuntimeError, match="rc=5"):
+        P.Render(g, P.NewPath(6, base.GetCamera(), base.GetSampler(), None, 1, P.Spatial), 8)
+    g.close()
 
 
 def test_two_rank_partition_sums_to_single(gp, dev):
