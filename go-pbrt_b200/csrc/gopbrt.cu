@@ -234,18 +234,50 @@ static void parallel_chunks(int64_t n, F fn, int* n_chunks_out = nullptr) {
   for (auto& t : th) t.join();
 }
 
-extern "C" int gopbrt_scene_create(gopbrt_ctx* ctx, const gopbrt_scene_desc* d, gopbrt_scene** out) {
-  if (!ctx || !d || !out) return GOPBRT_ERR_INVALID;
-  *out = nullptr;
-  std::lock_guard<std::mutex> g(ctx->mu);
-  std::lock_guard<std::mutex> grun(ctx->run_mu);
-  GP_CUDA(ctx, cudaSetDevice(ctx->device));
-  auto bad = [&](const char* msg) { ctx->last_error = msg; return GOPBRT_ERR_INVALID; };
+// Everything gopbrt_scene_create derives on the host: validated tables, the primitives' reference-arithmetic world bounds, the
+// BVH, the leaf-ordered records.  Built once per scene; uploaded once per device (gopbrt_multi_scene_create replicates it).
+struct HostScene {
+  std::vector<double> xf;
+  std::vector<int> xf_flags;
+  std::vector<SphereDev> spheres;
+  std::vector<DiskDev> disks;
+  std::vector<int4> prims;
+  HB world;
+  gpbvh::Result bvh;
+  std::vector<PrimRec> recs;
+  std::vector<double> rec_bounds;
+  std::vector<gpbvh::Node32> flat;
+  unsigned long long flat_tri_mask = 0;
+  std::vector<MaterialDev> mats;
+  std::vector<TextureDev> texs;
+  std::vector<LightDev> lights;
+  std::vector<double> cdf;
+  double func_int = 0;
+  int nl = 0;
+};
+
+static int build_host_scene(const gopbrt_scene_desc* d, HostScene& H, std::string& error) {
+  auto bad = [&](const char* msg) { error = msg; return GOPBRT_ERR_INVALID; };
+  std::vector<double>& xf = H.xf;
+  std::vector<int>& xf_flags = H.xf_flags;
+  std::vector<SphereDev>& spheres = H.spheres;
+  std::vector<DiskDev>& disks = H.disks;
+  std::vector<int4>& prims = H.prims;
+  HB& world = H.world;
+  gpbvh::Result& bvh = H.bvh;
+  std::vector<PrimRec>& recs = H.recs;
+  std::vector<double>& rec_bounds = H.rec_bounds;
+  std::vector<gpbvh::Node32>& flat = H.flat;
+  unsigned long long& flat_tri_mask = H.flat_tri_mask;
+  std::vector<MaterialDev>& mats = H.mats;
+  std::vector<TextureDev>& texs = H.texs;
+  std::vector<LightDev>& lights = H.lights;
+  std::vector<double>& cdf = H.cdf;
   if (d->n_primitives < 0 || d->n_primitives > 0x7fffffff) return bad("n_primitives out of range");
 
   // ---- transforms
-  std::vector<double> xf(32 * (size_t)d->n_transforms);
-  std::vector<int> xf_flags(d->n_transforms, 0);
+  xf.assign(32 * (size_t)d->n_transforms, 0.0);
+  xf_flags.assign(d->n_transforms, 0);
   for (int i = 0; i < d->n_transforms; i++) {
     memcpy(&xf[32 * (size_t)i], d->transforms[i].m, 16 * sizeof(double));
     memcpy(&xf[32 * (size_t)i + 16], d->transforms[i].minv, 16 * sizeof(double));
@@ -255,7 +287,7 @@ extern "C" int gopbrt_scene_create(gopbrt_ctx* ctx, const gopbrt_scene_desc* d, 
   auto xf_ok = [&](int i) { return i >= 0 && i < d->n_transforms; };
 
   // ---- shapes (NewSphere sphere.go:19-32, NewDisk disk.go:22-35)
-  std::vector<SphereDev> spheres(d->n_spheres);
+  spheres.resize(d->n_spheres);
   for (int i = 0; i < d->n_spheres; i++) {
     const gopbrt_sphere& s = d->spheres[i];
     if (!xf_ok(s.object_to_world)) return bad("sphere transform index out of range");
@@ -271,7 +303,7 @@ extern "C" int gopbrt_scene_create(gopbrt_ctx* ctx, const gopbrt_scene_desc* d, 
     if (!(o.zMin > -o.radius) && !(o.zMax < o.radius) && o.phiMax >= 2 * kPi) o.flags |= RF_FULL;
     spheres[i] = o;
   }
-  std::vector<DiskDev> disks(d->n_disks);
+  disks.resize(d->n_disks);
   for (int i = 0; i < d->n_disks; i++) {
     const gopbrt_disk& s = d->disks[i];
     if (!xf_ok(s.object_to_world)) return bad("disk transform index out of range");
@@ -285,9 +317,8 @@ extern "C" int gopbrt_scene_create(gopbrt_ctx* ctx, const gopbrt_scene_desc* d, 
 
   // ---- primitives: world bounds (Primitive.WorldBound) in the reference's arithmetic
   int64_t np = d->n_primitives;
-  std::vector<int4> prims(np);
+  prims.resize(np);
   std::vector<gpbvh::Box> pb(np);
-  HB world;
   {
     std::vector<HB> part(64);
     std::vector<const char*> err(64, nullptr);
@@ -343,12 +374,13 @@ extern "C" int gopbrt_scene_create(gopbrt_ctx* ctx, const gopbrt_scene_desc* d, 
   int max_prims = d->max_prims_in_node > 0 ? std::min(255, d->max_prims_in_node) : 4;
   max_prims = std::min(max_prims, 2);
   if (const char* mp = getenv("GOPBRT_MAX_PRIMS")) max_prims = std::max(1, std::min(255, atoi(mp)));
-  gpbvh::Result bvh = gpbvh::build_bvh(pb.data(), np, max_prims);
+  bvh = gpbvh::build_bvh(pb.data(), np, max_prims);
+  if ((int64_t)bvh.order.size() != np) return bad("BVH build failed (out of host memory)");
   if (bvh.depth >= kStackDepth - 1) return bad("BVH deeper than the traversal stack");
 
   // ---- leaf-ordered primitive records + their float64 bounds
-  std::vector<PrimRec> recs(np);
-  std::vector<double> rec_bounds(6 * (size_t)np);
+  recs.resize(np);
+  rec_bounds.resize(6 * (size_t)np);
   parallel_chunks(np, [&](int64_t r0, int64_t r1, int) {
   for (int64_t r = r0; r < r1; r++) {
     uint32_t pi = bvh.order[r];
@@ -392,8 +424,8 @@ extern "C" int gopbrt_scene_create(gopbrt_ctx* ctx, const gopbrt_scene_desc* d, 
   });
 
   // ---- flat aggregate (scenes of at most kFlatMax primitives): one table entry per leaf-ordered record, triangles first
-  std::vector<gpbvh::Node32> flat;
-  unsigned long long flat_tri_mask = 0;
+  flat.clear();
+  flat_tri_mask = 0;
   if (np > 0 && np <= kFlatMax && !getenv("GOPBRT_NO_FLAT")) {
     for (int pass = 0; pass < 2; pass++)
       for (int64_t r = 0; r < np; r++) {
@@ -409,14 +441,14 @@ extern "C" int gopbrt_scene_create(gopbrt_ctx* ctx, const gopbrt_scene_desc* d, 
   }
 
   // ---- materials / textures / lights
-  std::vector<MaterialDev> mats(d->n_materials);
+  mats.resize(d->n_materials);
   for (int i = 0; i < d->n_materials; i++) {
     const gopbrt_material& m = d->materials[i];
     if (m.tex_a >= d->n_textures || m.tex_b >= d->n_textures) return bad("texture index out of range");
     if (m.kind < 0 || m.kind > 2 || m.tex_a < 0 || (m.kind == 2 && m.tex_b < 0)) return bad("bad material");
     mats[i] = MaterialDev{m.kind, m.tex_a, m.tex_b, 0, m.sigma, m.eta, m.u_rough, m.v_rough};
   }
-  std::vector<TextureDev> texs(d->n_textures);
+  texs.resize(d->n_textures);
   for (int i = 0; i < d->n_textures; i++) {
     const gopbrt_texture& t = d->textures[i];
     TextureDev o;
@@ -426,7 +458,7 @@ extern "C" int gopbrt_scene_create(gopbrt_ctx* ctx, const gopbrt_scene_desc* d, 
     o.ds = t.ds; o.dt = t.dt; o.su = t.su; o.sv = t.sv; o.du = t.du; o.dv = t.dv;
     texs[i] = o;
   }
-  std::vector<LightDev> lights(d->n_lights);
+  lights.resize(d->n_lights);
   for (int i = 0; i < d->n_lights; i++) {
     const gopbrt_light& l = d->lights[i];
     LightDev o;
@@ -439,10 +471,34 @@ extern "C" int gopbrt_scene_create(gopbrt_ctx* ctx, const gopbrt_scene_desc* d, 
     }
     lights[i] = o;
   }
-  int nl = d->n_lights;
-  std::vector<double> cdf;
-  double func_int = uniform_light_cdf(nl, cdf);
+  H.nl = d->n_lights;
+  H.func_int = uniform_light_cdf(H.nl, cdf);
+  return GOPBRT_OK;
+}
 
+
+// uploads a host scene to the context's device and binds the traversal kernels
+static int upload_scene(gopbrt_ctx* ctx, HostScene& H, gopbrt_scene** out) {
+  std::lock_guard<std::mutex> g(ctx->mu);
+  std::lock_guard<std::mutex> grun(ctx->run_mu);
+  GP_CUDA(ctx, cudaSetDevice(ctx->device));
+  std::vector<double>& xf = H.xf;
+  std::vector<int>& xf_flags = H.xf_flags;
+  std::vector<SphereDev>& spheres = H.spheres;
+  std::vector<DiskDev>& disks = H.disks;
+  std::vector<int4>& prims = H.prims;
+  HB& world = H.world;
+  gpbvh::Result& bvh = H.bvh;
+  std::vector<PrimRec>& recs = H.recs;
+  std::vector<double>& rec_bounds = H.rec_bounds;
+  std::vector<gpbvh::Node32>& flat = H.flat;
+  const unsigned long long flat_tri_mask = H.flat_tri_mask;
+  std::vector<MaterialDev>& mats = H.mats;
+  std::vector<TextureDev>& texs = H.texs;
+  std::vector<LightDev>& lights = H.lights;
+  std::vector<double>& cdf = H.cdf;
+  const double func_int = H.func_int;
+  const int nl = H.nl;
   gopbrt_scene* sc = new gopbrt_scene();
   sc->ctx = ctx;
   cudaStream_t st = ctx->stream;
@@ -506,6 +562,16 @@ extern "C" int gopbrt_scene_create(gopbrt_ctx* ctx, const gopbrt_scene_desc* d, 
   for (int k = 0; k < 7; k++) sc->trace_grid[k] = grid_for(ctx, (const void*)sc->trace_k[k], kTraceThreads, sc->trace_smem);
   *out = sc;
   return GOPBRT_OK;
+}
+
+extern "C" int gopbrt_scene_create(gopbrt_ctx* ctx, const gopbrt_scene_desc* d, gopbrt_scene** out) {
+  if (!ctx || !d || !out) return GOPBRT_ERR_INVALID;
+  *out = nullptr;
+  HostScene H;
+  std::string err;
+  int rc = build_host_scene(d, H, err);
+  if (rc != GOPBRT_OK) { std::lock_guard<std::mutex> g(ctx->mu); ctx->last_error = err; return rc; }
+  return upload_scene(ctx, H, out);
 }
 
 extern "C" void gopbrt_scene_destroy(gopbrt_scene* sc) {
