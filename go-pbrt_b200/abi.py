@@ -17,7 +17,8 @@ MAP_UV, MAP_PLANAR = 0, 1
 LIGHT_DISTANT, LIGHT_POINT, LIGHT_DIFFUSE_AREA = 0, 1, 2
 SAMPLER_STRATIFIED, SAMPLER_RANDOM = 0, 1
 MODE_STRICT, MODE_FAST = 0, 1
-FLAG_COUNT_TRAVERSAL, FLAG_FAIL_ON_PANIC, FLAG_TIME_KERNELS = 1, 2, 4
+FLAG_COUNT_TRAVERSAL, FLAG_FAIL_ON_PANIC, FLAG_TIME_KERNELS, FLAG_REDUCE_FILM = 1, 2, 4, 16
+COMM_ID_BYTES = 128
 
 # function ids of the self-test hook gopbrt_kat_eval (csrc/gp_kat.cuh: KAT_*)
 KAT_IDS = {n: i for i, n in enumerate([
@@ -114,7 +115,7 @@ class Stats(C.Structure):
                 ("tests_sphere_fast", C.c_uint64), ("tests_general", C.c_uint64), ("extend_launches", C.c_uint64),
                 ("shadow_launches", C.c_uint64), ("shadow_tests_triangle", C.c_uint64),
                 ("shadow_tests_sphere_fast", C.c_uint64), ("shadow_tests_general", C.c_uint64), ("reserved0", C.c_uint64),
-                ("reserved1", C.c_double), ("root_culled_rays", C.c_uint64)]
+                ("ms_reduce", C.c_double), ("root_culled_rays", C.c_uint64)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -124,7 +125,10 @@ class Stats(C.Structure):
 EXPORTS = ["gopbrt_abi_version", "gopbrt_init", "gopbrt_shutdown", "gopbrt_last_error", "gopbrt_scene_create",
            "gopbrt_scene_destroy", "gopbrt_scene_world_bound", "gopbrt_trace_closest", "gopbrt_trace_any",
            "gopbrt_trace_closest_device", "gopbrt_trace_any_device", "gopbrt_render", "gopbrt_render_device",
-           "gopbrt_cancel", "gopbrt_launch_count", "gopbrt_kat_eval"]
+           "gopbrt_cancel", "gopbrt_launch_count", "gopbrt_kat_eval", "gopbrt_comm_unique_id", "gopbrt_comm_init_rank",
+           "gopbrt_multi_init", "gopbrt_multi_shutdown", "gopbrt_multi_device_count", "gopbrt_multi_last_error",
+           "gopbrt_multi_launch_count", "gopbrt_multi_scene_create", "gopbrt_multi_scene_destroy", "gopbrt_multi_render",
+           "gopbrt_multi_cancel"]
 
 _lib = None
 dp = C.POINTER(C.c_double)
@@ -164,6 +168,21 @@ def load(path=None):
     lib.gopbrt_kat_eval.restype = C.c_int
     lib.gopbrt_launch_count.argtypes = [C.c_void_p]
     lib.gopbrt_launch_count.restype = C.c_uint64
+    lib.gopbrt_comm_unique_id.argtypes = [C.c_char_p]
+    lib.gopbrt_comm_init_rank.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_int]
+    lib.gopbrt_multi_init.argtypes = [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_void_p)]
+    lib.gopbrt_multi_shutdown.argtypes = [C.c_void_p]
+    lib.gopbrt_multi_shutdown.restype = None
+    lib.gopbrt_multi_device_count.argtypes = [C.c_void_p]
+    lib.gopbrt_multi_last_error.argtypes = [C.c_void_p]
+    lib.gopbrt_multi_last_error.restype = C.c_char_p
+    lib.gopbrt_multi_launch_count.argtypes = [C.c_void_p]
+    lib.gopbrt_multi_launch_count.restype = C.c_uint64
+    lib.gopbrt_multi_scene_create.argtypes = [C.c_void_p, C.POINTER(SceneDesc), C.POINTER(C.c_void_p)]
+    lib.gopbrt_multi_scene_destroy.argtypes = [C.c_void_p]
+    lib.gopbrt_multi_scene_destroy.restype = None
+    lib.gopbrt_multi_render.argtypes = rargs[:5] + [C.c_int, dp, C.POINTER(Stats)]
+    lib.gopbrt_multi_cancel.argtypes = [C.c_void_p]
     if lib.gopbrt_abi_version() != 1:
         raise RuntimeError("libgopbrt_cuda.so ABI version mismatch")
     if path is None:

@@ -14,6 +14,7 @@
 
 #include "../../include/gopbrt_cuda.h"
 #include "gp_bvh.h"
+#include "gp_comm.h"
 #include "gp_render.cuh"
 #include "gp_kat.cuh"
 
@@ -39,6 +40,9 @@ struct gopbrt_ctx {
   std::mutex run_mu;
   int grid_gen[8] = {0, 0, 0, 0, 0, 0, 0, 0}, grid_shade[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};  // persistent grids of this device (SMs x resident CTAs)
   size_t trace_smem_limit = 0;  // largest dynamic shared memory size the traversal kernels have been opted into (> 48 KB only)
+  // film reduce across GPUs (gopbrt_comm_init_rank / gopbrt_multi_init): this context's NCCL communicator and its place in it
+  gpcomm::ncclComm_t comm = nullptr;
+  int comm_rank = 0, comm_world = 1;
 };
 
 #define GP_CUDA(ctx, call)                                                                               \
@@ -162,6 +166,10 @@ int gopbrt_init(int device, gopbrt_ctx** out) {
 void gopbrt_shutdown(gopbrt_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
+  if (c->comm) {
+    std::string e;
+    if (gpcomm::Api* a = gpcomm::api(e)) a->CommDestroy(c->comm);
+  }
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -1080,33 +1088,252 @@ static int render_impl(gopbrt_scene* sc, const gopbrt_camera* cam, const gopbrt_
   return rc;
 }
 
+// ------------------------------------------------------------------------------------------------ film reduce (NCCL)
+// Sums the ranks' device films onto rank 0 with one ncclReduce on the library stream (in place on the root), and waits for
+// it.  Every rank of the communicator must arrive: callers reduce even after a cancelled or failed frame (the sum is then
+// meaningless but nobody hangs).  Returns the device time of the reduce through ms (CUDA events on the library stream).
+static int film_reduce(gopbrt_ctx* ctx, const gopbrt_render_options* opt, double* d_film, size_t n_doubles, double* ms) {
+  if (!ctx->comm) { ctx->last_error = "GOPBRT_FLAG_REDUCE_FILM without a communicator (gopbrt_comm_init_rank / gopbrt_multi_init)"; return GOPBRT_ERR_INVALID; }
+  int rank = opt ? opt->rank : 0, world = opt ? opt->world : 1;
+  if (rank != ctx->comm_rank || world != ctx->comm_world) { ctx->last_error = "render rank/world differ from the communicator's"; return GOPBRT_ERR_INVALID; }
+  std::string err;
+  gpcomm::Api* a = gpcomm::api(err);
+  if (!a) { ctx->last_error = err; return GOPBRT_ERR_CUDA; }
+  cudaEvent_t ev[2];
+  GP_CUDA(ctx, cudaEventCreate(&ev[0]));
+  GP_CUDA(ctx, cudaEventCreate(&ev[1]));
+  cudaEventRecord(ev[0], ctx->stream);
+  int r = a->Reduce(d_film, d_film, n_doubles, gpcomm::kNcclFloat64, gpcomm::kNcclSum, 0, ctx->comm, ctx->stream);
+  cudaEventRecord(ev[1], ctx->stream);
+  cudaError_t ce = cudaStreamSynchronize(ctx->stream);
+  float t = 0;
+  if (ce == cudaSuccess) cudaEventElapsedTime(&t, ev[0], ev[1]);
+  cudaEventDestroy(ev[0]);
+  cudaEventDestroy(ev[1]);
+  if (r != gpcomm::kNcclSuccess) { ctx->last_error = std::string("ncclReduce: ") + a->GetErrorString(r); return GOPBRT_ERR_CUDA; }
+  GP_CUDA(ctx, ce);
+  ctx->launches += 1;  // NCCL's reduce kernel
+  if (ms) *ms = t;
+  return GOPBRT_OK;
+}
+
+static size_t film_doubles(const gopbrt_film* film) {
+  long long cx0 = (long long)ceil((double)film->width * film->crop[0]), cy0 = (long long)ceil((double)film->height * film->crop[1]);
+  long long cx1 = (long long)ceil((double)film->width * film->crop[2]), cy1 = (long long)ceil((double)film->height * film->crop[3]);
+  if (cx1 <= cx0 || cy1 <= cy0) return 0;
+  return (size_t)(cx1 - cx0) * (cy1 - cy0) * 4;
+}
+
 extern "C" int gopbrt_render_device(gopbrt_scene* sc, const gopbrt_camera* cam, const gopbrt_sampler* smp, const gopbrt_integrator* ig,
                                     const gopbrt_film* film, const gopbrt_render_options* opt, double* d_film, gopbrt_stats* stats) {
   if (!sc || !cam || !smp || !ig || !film || !d_film) return GOPBRT_ERR_INVALID;
-  std::lock_guard<std::mutex> g(sc->mu);
-  std::lock_guard<std::mutex> grun(sc->ctx->run_mu);
-  return render_impl(sc, cam, smp, ig, film, opt, d_film, stats);
-}
-
-extern "C" int gopbrt_render(gopbrt_scene* sc, const gopbrt_camera* cam, const gopbrt_sampler* smp, const gopbrt_integrator* ig,
-                             const gopbrt_film* film, const gopbrt_render_options* opt, double* film_out, gopbrt_stats* stats) {
-  if (!sc || !cam || !smp || !ig || !film || !film_out) return GOPBRT_ERR_INVALID;
   gopbrt_ctx* ctx = sc->ctx;
   std::lock_guard<std::mutex> g(sc->mu);
   std::lock_guard<std::mutex> grun(sc->ctx->run_mu);
   GP_CUDA(ctx, cudaSetDevice(ctx->device));
-  long long cx0 = (long long)ceil((double)film->width * film->crop[0]), cy0 = (long long)ceil((double)film->height * film->crop[1]);
-  long long cx1 = (long long)ceil((double)film->width * film->crop[2]), cy1 = (long long)ceil((double)film->height * film->crop[3]);
-  if (cx1 <= cx0 || cy1 <= cy0) { ctx->last_error = "empty film"; return GOPBRT_ERR_INVALID; }
-  size_t n = (size_t)(cx1 - cx0) * (cy1 - cy0) * 4;
+  int rc = render_impl(sc, cam, smp, ig, film, opt, d_film, stats);
+  if (opt && (opt->flags & GOPBRT_FLAG_REDUCE_FILM) && rc != GOPBRT_ERR_CUDA && rc != GOPBRT_ERR_INVALID) {
+    double ms = 0;
+    int rr = film_reduce(ctx, opt, d_film, film_doubles(film), &ms);
+    if (stats) stats->ms_reduce = ms;
+    if (rc == GOPBRT_OK) rc = rr;
+  }
+  return rc;
+}
+
+extern "C" int gopbrt_render(gopbrt_scene* sc, const gopbrt_camera* cam, const gopbrt_sampler* smp, const gopbrt_integrator* ig,
+                             const gopbrt_film* film, const gopbrt_render_options* opt, double* film_out, gopbrt_stats* stats) {
+  if (!sc || !cam || !smp || !ig || !film) return GOPBRT_ERR_INVALID;
+  const bool reduce = opt && (opt->flags & GOPBRT_FLAG_REDUCE_FILM);
+  // the summed film exists on rank 0 only: the other ranks of a reduced frame pass no host buffer
+  if (!film_out && !(reduce && opt->rank != 0)) return GOPBRT_ERR_INVALID;
+  gopbrt_ctx* ctx = sc->ctx;
+  std::lock_guard<std::mutex> g(sc->mu);
+  std::lock_guard<std::mutex> grun(sc->ctx->run_mu);
+  GP_CUDA(ctx, cudaSetDevice(ctx->device));
+  size_t n = film_doubles(film);
+  if (n == 0) { ctx->last_error = "empty film"; return GOPBRT_ERR_INVALID; }
   DevBuf<double>& d_film = sc->ws.film;
   if (d_film.n != n) { d_film.release(); GP_CUDA(ctx, d_film.alloc(n)); }
   int rc = render_impl(sc, cam, smp, ig, film, opt, d_film.p, stats);
+  if (reduce && rc != GOPBRT_ERR_CUDA && rc != GOPBRT_ERR_INVALID) {
+    double ms = 0;
+    int rr = film_reduce(ctx, opt, d_film.p, n, &ms);
+    if (stats) stats->ms_reduce = ms;
+    if (rc == GOPBRT_OK) rc = rr;
+  }
   if (rc != GOPBRT_OK) return rc;
-  auto t0 = std::chrono::steady_clock::now();
-  GP_CUDA(ctx, cudaMemcpy(film_out, d_film.p, n * sizeof(double), cudaMemcpyDeviceToHost));
-  if (stats) stats->ms_download = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  if (film_out && (!reduce || opt->rank == 0)) {
+    auto t0 = std::chrono::steady_clock::now();
+    GP_CUDA(ctx, cudaMemcpy(film_out, d_film.p, n * sizeof(double), cudaMemcpyDeviceToHost));
+    if (stats) stats->ms_download = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  }
   return GOPBRT_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ communicators
+extern "C" int gopbrt_comm_unique_id(unsigned char id[GOPBRT_COMM_ID_BYTES]) {
+  if (!id) return GOPBRT_ERR_INVALID;
+  std::string err;
+  gpcomm::Api* a = gpcomm::api(err);
+  if (!a) return GOPBRT_ERR_CUDA;
+  gpcomm::ncclUniqueId u;
+  static_assert(sizeof(u) == GOPBRT_COMM_ID_BYTES, "ncclUniqueId is 128 bytes");
+  if (a->GetUniqueId(&u) != gpcomm::kNcclSuccess) return GOPBRT_ERR_CUDA;
+  memcpy(id, &u, sizeof(u));
+  return GOPBRT_OK;
+}
+
+extern "C" int gopbrt_comm_init_rank(gopbrt_ctx* ctx, const unsigned char id[GOPBRT_COMM_ID_BYTES], int rank, int world) {
+  if (!ctx || !id || world < 1 || rank < 0 || rank >= world) return GOPBRT_ERR_INVALID;
+  std::lock_guard<std::mutex> g(ctx->mu);
+  std::lock_guard<std::mutex> grun(ctx->run_mu);
+  if (ctx->comm) { ctx->last_error = "the context already has a communicator"; return GOPBRT_ERR_INVALID; }
+  std::string err;
+  gpcomm::Api* a = gpcomm::api(err);
+  if (!a) { ctx->last_error = err; return GOPBRT_ERR_CUDA; }
+  GP_CUDA(ctx, cudaSetDevice(ctx->device));
+  gpcomm::ncclUniqueId u;
+  memcpy(&u, id, sizeof(u));
+  int r = a->CommInitRank(&ctx->comm, world, u, rank);
+  if (r != gpcomm::kNcclSuccess) { ctx->comm = nullptr; ctx->last_error = std::string("ncclCommInitRank: ") + a->GetErrorString(r); return GOPBRT_ERR_CUDA; }
+  ctx->comm_rank = rank; ctx->comm_world = world;
+  return GOPBRT_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ one process, N GPUs
+// pbrt.Render is ONE call from ONE process (integrator.go:291-350, called at internal/render/server.go:164).  gopbrt_multi
+// is that call over N devices: the scene replicated per device, the frame's samples (FAST) or tiles (STRICT) split by rank,
+// one host thread per device driving its wavefront, one ncclReduce of the films onto device 0, the host film read from there.
+struct gopbrt_multi {
+  std::vector<gopbrt_ctx*> ctx;
+  std::string last_error;
+  std::mutex mu;
+};
+struct gopbrt_multi_scene {
+  gopbrt_multi* m = nullptr;
+  std::vector<gopbrt_scene*> sc;
+};
+
+extern "C" void gopbrt_multi_shutdown(gopbrt_multi* m) {
+  if (!m) return;
+  for (gopbrt_ctx* c : m->ctx) gopbrt_shutdown(c);
+  delete m;
+}
+
+extern "C" int gopbrt_multi_init(int n_gpus, const int* devices, gopbrt_multi** out) {
+  if (!out || n_gpus < 1 || n_gpus > 64) return GOPBRT_ERR_INVALID;
+  *out = nullptr;
+  gopbrt_multi* m = new gopbrt_multi();
+  std::vector<int> devs(n_gpus);
+  for (int i = 0; i < n_gpus; i++) {
+    devs[i] = devices ? devices[i] : i;
+    gopbrt_ctx* c = nullptr;
+    int rc = gopbrt_init(devs[i], &c);
+    if (rc != GOPBRT_OK) { gopbrt_multi_shutdown(m); return rc; }
+    m->ctx.push_back(c);
+  }
+  if (n_gpus > 1) {
+    std::string err;
+    gpcomm::Api* a = gpcomm::api(err);
+    if (!a) { gopbrt_multi_shutdown(m); return GOPBRT_ERR_CUDA; }
+    std::vector<gpcomm::ncclComm_t> comms(n_gpus, nullptr);
+    if (a->CommInitAll(comms.data(), n_gpus, devs.data()) != gpcomm::kNcclSuccess) { gopbrt_multi_shutdown(m); return GOPBRT_ERR_CUDA; }
+    for (int i = 0; i < n_gpus; i++) { m->ctx[i]->comm = comms[i]; m->ctx[i]->comm_rank = i; m->ctx[i]->comm_world = n_gpus; }
+  }
+  *out = m;
+  return GOPBRT_OK;
+}
+
+extern "C" int gopbrt_multi_device_count(const gopbrt_multi* m) { return m ? (int)m->ctx.size() : 0; }
+extern "C" const char* gopbrt_multi_last_error(const gopbrt_multi* m) { return m ? m->last_error.c_str() : "null multi context"; }
+extern "C" uint64_t gopbrt_multi_launch_count(const gopbrt_multi* m) {
+  uint64_t n = 0;
+  if (m) for (gopbrt_ctx* c : m->ctx) n += c->launches.load();
+  return n;
+}
+
+extern "C" void gopbrt_multi_scene_destroy(gopbrt_multi_scene* ms) {
+  if (!ms) return;
+  for (gopbrt_scene* s : ms->sc) gopbrt_scene_destroy(s);
+  delete ms;
+}
+
+extern "C" int gopbrt_multi_scene_create(gopbrt_multi* m, const gopbrt_scene_desc* d, gopbrt_multi_scene** out) {
+  if (!m || !d || !out) return GOPBRT_ERR_INVALID;
+  *out = nullptr;
+  HostScene H;  // validated, bounded and BVH-built once on the host; every device receives the same bytes
+  std::string err;
+  int rc = build_host_scene(d, H, err);
+  if (rc != GOPBRT_OK) { std::lock_guard<std::mutex> g(m->mu); m->last_error = err; return rc; }
+  const int n = (int)m->ctx.size();
+  gopbrt_multi_scene* ms = new gopbrt_multi_scene();
+  ms->m = m;
+  ms->sc.assign(n, nullptr);
+  std::vector<int> rcs(n, GOPBRT_OK);
+  std::vector<std::thread> th;
+  for (int i = 0; i < n; i++) th.emplace_back([&, i]() { rcs[i] = upload_scene(m->ctx[i], H, &ms->sc[i]); });
+  for (auto& t : th) t.join();
+  for (int i = 0; i < n; i++)
+    if (rcs[i] != GOPBRT_OK) {
+      { std::lock_guard<std::mutex> g(m->mu); m->last_error = "device " + std::to_string(m->ctx[i]->device) + ": " + m->ctx[i]->last_error; }
+      rc = rcs[i];
+      gopbrt_multi_scene_destroy(ms);
+      return rc;
+    }
+  *out = ms;
+  return GOPBRT_OK;
+}
+
+extern "C" int gopbrt_multi_cancel(gopbrt_multi_scene* ms) {
+  if (!ms) return GOPBRT_ERR_INVALID;
+  for (gopbrt_scene* s : ms->sc) gopbrt_cancel(s);
+  return GOPBRT_OK;
+}
+
+extern "C" int gopbrt_multi_render(gopbrt_multi_scene* ms, const gopbrt_camera* cam, const gopbrt_sampler* smp, const gopbrt_integrator* ig,
+                                   const gopbrt_film* film, int flags, double* film_out, gopbrt_stats* stats_out) {
+  if (!ms || !cam || !smp || !ig || !film || !film_out) return GOPBRT_ERR_INVALID;
+  const int n = (int)ms->sc.size();
+  std::vector<int> rcs(n, GOPBRT_OK);
+  std::vector<gopbrt_stats> st(n);
+  auto one = [&](int i) {
+    gopbrt_render_options o;
+    o.rank = i; o.world = n; o.max_lanes = 0;
+    o.flags = (flags & ~GOPBRT_FLAG_REDUCE_FILM) | (n > 1 ? GOPBRT_FLAG_REDUCE_FILM : 0);
+    rcs[i] = gopbrt_render(ms->sc[i], cam, smp, ig, film, &o, i == 0 ? film_out : nullptr, &st[i]);
+  };
+  std::vector<std::thread> th;
+  for (int i = 1; i < n; i++) th.emplace_back(one, i);
+  one(0);
+  for (auto& t : th) t.join();
+  int rc = GOPBRT_OK;
+  for (int i = 0; i < n; i++)
+    if (rcs[i] != GOPBRT_OK) {
+      std::lock_guard<std::mutex> g(ms->m->mu);
+      ms->m->last_error = "device " + std::to_string(ms->m->ctx[i]->device) + ": " + ms->m->ctx[i]->last_error;
+      if (rc == GOPBRT_OK) rc = rcs[i];
+    }
+  if (stats_out) {  // counters summed over the devices, times = the slowest device (the frame's critical path)
+    gopbrt_stats t = st[0];
+    for (int i = 1; i < n; i++) {
+      const gopbrt_stats& s = st[i];
+      t.camera_rays += s.camera_rays; t.closest_rays += s.closest_rays; t.shadow_rays += s.shadow_rays; t.dead_mis_rays += s.dead_mis_rays;
+      t.nodes_visited += s.nodes_visited; t.prim_tests += s.prim_tests; t.shadow_nodes_visited += s.shadow_nodes_visited;
+      t.shadow_prim_tests += s.shadow_prim_tests; t.radiance_gt10 += s.radiance_gt10; t.nan_samples += s.nan_samples;
+      t.efloat_panics += s.efloat_panics; t.stack_overflows += s.stack_overflows; t.launches += s.launches; t.lanes += s.lanes;
+      t.tests_triangle += s.tests_triangle; t.tests_sphere_fast += s.tests_sphere_fast; t.tests_general += s.tests_general;
+      t.extend_launches += s.extend_launches; t.shadow_launches += s.shadow_launches; t.root_culled_rays += s.root_culled_rays;
+      t.shadow_tests_triangle += s.shadow_tests_triangle; t.shadow_tests_sphere_fast += s.shadow_tests_sphere_fast;
+      t.shadow_tests_general += s.shadow_tests_general;
+      t.iterations = std::max(t.iterations, s.iterations);
+      t.ms_total = std::max(t.ms_total, s.ms_total); t.ms_raygen = std::max(t.ms_raygen, s.ms_raygen); t.ms_extend = std::max(t.ms_extend, s.ms_extend);
+      t.ms_shade = std::max(t.ms_shade, s.ms_shade); t.ms_shadow = std::max(t.ms_shadow, s.ms_shadow); t.ms_film = std::max(t.ms_film, s.ms_film);
+      t.ms_reduce = std::max(t.ms_reduce, s.ms_reduce);
+    }
+    *stats_out = t;
+  }
+  return rc;
 }
 
 // ------------------------------------------------------------------------------------------------ self-test hook

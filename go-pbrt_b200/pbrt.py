@@ -686,6 +686,21 @@ class Device:
             self.lib.gopbrt_shutdown(self.h)
             self.h = C.c_void_p()
 
+    @staticmethod
+    def comm_unique_id():
+        """128-byte NCCL id made on rank 0 and handed to every rank by any host channel (gopbrt_comm_unique_id)."""
+        buf = C.create_string_buffer(abi.COMM_ID_BYTES)
+        rc = abi.load().gopbrt_comm_unique_id(buf)
+        if rc != abi.OK:
+            raise RuntimeError(f"gopbrt_comm_unique_id rc={rc} (libnccl.so.2 not loadable?)")
+        return buf.raw
+
+    def comm_init(self, comm_id, rank, world):
+        """joins this context to the film-reduce communicator (gopbrt_comm_init_rank); collective over the ranks"""
+        rc = self.lib.gopbrt_comm_init_rank(self.h, bytes(comm_id), rank, world)
+        if rc != abi.OK:
+            raise RuntimeError(f"gopbrt_comm_init_rank rc={rc}: {self.error()}")
+
 
 class GpuScene:
     """gopbrt_scene: the uploaded scene (BVH built and flattened once)."""
@@ -757,13 +772,77 @@ def Render(gpu_scene, integrator, tileSize, mode=abi.MODE_STRICT, rank=0, world=
         rc = lib.gopbrt_render_device(gpu_scene.h, C.byref(c), C.byref(s), C.byref(i), C.byref(f), C.byref(o),
                                       C.c_void_p(device_film), C.byref(st))
     else:
+        host = True
         if out is not None:
             assert out.dtype == np.float64 and out.size == int(np.prod(film.shape())) and out.flags["C_CONTIGUOUS"]
             film.pixels = out.reshape(film.shape())
+        elif (flags & abi.FLAG_REDUCE_FILM) and rank != 0:
+            host = False  # the summed film exists on rank 0 only
         else:
             film.pixels = np.empty(film.shape(), dtype=np.float64)
         rc = lib.gopbrt_render(gpu_scene.h, C.byref(c), C.byref(s), C.byref(i), C.byref(f), C.byref(o),
-                               film.pixels.ctypes.data_as(abi.dp), C.byref(st))
+                               film.pixels.ctypes.data_as(abi.dp) if host else None, C.byref(st))
     if rc != abi.OK:
         raise RuntimeError(f"gopbrt_render rc={rc}: {gpu_scene.dev.error()}")
+    return st.as_dict()
+
+
+class MultiDevice:
+    """gopbrt_multi: one process, N GPUs (contexts + NCCL communicators)."""
+
+    def __init__(self, n_gpus, devices=None):
+        self.lib = abi.load()
+        self.h = C.c_void_p()
+        arr = (C.c_int * n_gpus)(*devices) if devices is not None else None
+        rc = self.lib.gopbrt_multi_init(n_gpus, arr, C.byref(self.h))
+        if rc != abi.OK:
+            raise RuntimeError(f"gopbrt_multi_init({n_gpus}) failed rc={rc} (no CPU fallback)")
+        self.n = n_gpus
+
+    def error(self):
+        e = self.lib.gopbrt_multi_last_error(self.h)
+        return e.decode() if e else ""
+
+    def launches(self):
+        return int(self.lib.gopbrt_multi_launch_count(self.h))
+
+    def close(self):
+        if self.h:
+            self.lib.gopbrt_multi_shutdown(self.h)
+            self.h = C.c_void_p()
+
+
+class MultiGpuScene:
+    """gopbrt_multi_scene: BVH built once on the host, uploaded to every device."""
+
+    def __init__(self, mdev, scene):
+        self.dev, self.scene = mdev, scene
+        self.h = C.c_void_p()
+        rc = mdev.lib.gopbrt_multi_scene_create(mdev.h, C.byref(scene.desc()), C.byref(self.h))
+        if rc != abi.OK:
+            raise RuntimeError(f"gopbrt_multi_scene_create failed rc={rc}: {mdev.error()}")
+
+    def close(self):
+        if self.h:
+            self.dev.lib.gopbrt_multi_scene_destroy(self.h)
+            self.h = C.c_void_p()
+
+
+def RenderMulti(multi_scene, integrator, tileSize, mode=abi.MODE_FAST, flags=0, out=None, groups=0):
+    """pbrt.Render over every GPU of the process (gopbrt_multi_render): samples (FAST) or tiles (STRICT) split by device, one NCCL
+    film reduce, host film from device 0.  Returns the stats dict (counters summed over devices, times = slowest device)."""
+    cam = integrator.GetCamera()
+    film = cam.GetFilm()
+    lib = multi_scene.dev.lib
+    c, s, i, f = cam.abi(), integrator.GetSampler().abi(mode), integrator.abi(tileSize), film.abi()
+    st = abi.Stats()
+    if out is not None:
+        assert out.dtype == np.float64 and out.size == int(np.prod(film.shape())) and out.flags["C_CONTIGUOUS"]
+        film.pixels = out.reshape(film.shape())
+    else:
+        film.pixels = np.empty(film.shape(), dtype=np.float64)
+    rc = lib.gopbrt_multi_render(multi_scene.h, C.byref(c), C.byref(s), C.byref(i), C.byref(f), flags | ((int(groups) & 0xff) << 8),
+                                 film.pixels.ctypes.data_as(abi.dp), C.byref(st))
+    if rc != abi.OK:
+        raise RuntimeError(f"gopbrt_multi_render rc={rc}: {multi_scene.dev.error()}")
     return st.as_dict()

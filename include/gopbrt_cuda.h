@@ -199,6 +199,11 @@ enum {
   GOPBRT_FLAG_FAIL_ON_PANIC = 2,   /* return GOPBRT_ERR_REFERENCE_PANIC instead of counting           */
   GOPBRT_FLAG_TIME_KERNELS = 4,    /* CUDA-event time every stage launch (fills ms_raygen … ms_film)   */
   /* 8: reserved (was GOPBRT_FLAG_TAIL in ABI 1 drafts; ignored) */
+  GOPBRT_FLAG_REDUCE_FILM = 16,    /* world > 1: after the last wavefront the ranks' films are summed onto rank 0 with ONE
+                                      ncclReduce (float64, sum) on the library stream — the GPU form of the reference merging
+                                      every worker's FilmTile into one Film (film.go:115-132).  Needs a communicator on the
+                                      context (gopbrt_comm_init_rank, or gopbrt_multi_init) whose rank/world equal the
+                                      render options'.  Every rank must make the call. */
   /* bits 8..15: GOPBRT_MODE_FAST only — lane groups per pixel tile (each group renders every n-th sample of the
    * rank's share, into its own FilmTile; the groups are merged in ascending order).  0 = automatic. */
   GOPBRT_FLAG_GROUPS_SHIFT = 8,
@@ -232,7 +237,7 @@ typedef struct {
   uint64_t extend_launches, shadow_launches;
   uint64_t shadow_tests_triangle, shadow_tests_sphere_fast, shadow_tests_general; /* any-hit, same split */
   uint64_t reserved0;          /* (was tail_launches; always 0) */
-  double reserved1;            /* (was ms_tail; always 0) */
+  double ms_reduce;            /* GOPBRT_FLAG_REDUCE_FILM: device time of the NCCL film reduce (CUDA events on the library stream) */
   uint64_t root_culled_rays;   /* closest_rays answered by the BVH-root slab test inside raygen (never reach the extend kernel) */
 } gopbrt_stats;
 
@@ -280,6 +285,37 @@ int gopbrt_render_device(gopbrt_scene*, const gopbrt_camera*, const gopbrt_sampl
                          const gopbrt_film*, const gopbrt_render_options*, double* d_film, gopbrt_stats* stats_out);
 /* thread-safe; makes a running gopbrt_render return GOPBRT_ERR_CANCELLED between wavefront iterations */
 int gopbrt_cancel(gopbrt_scene*);
+
+/* ---- multi-GPU: the frame's samples (FAST) or tiles (STRICT) split by rank, films summed with one NCCL reduce ----
+ * The reference renders a frame with ONE call from ONE process (pbrt.Render, integrator.go:291-350, called at
+ * internal/render/server.go:164; its workers are goroutines, integrator.go:304-312).  Two bindings of that shape:
+ *
+ * (1) one process per GPU (torchrun / MPI style): rank 0 calls gopbrt_comm_unique_id and hands the 128 bytes to every rank by
+ *     any host channel; every rank calls gopbrt_comm_init_rank on its own context; gopbrt_render / gopbrt_render_device with
+ *     {rank, world, GOPBRT_FLAG_REDUCE_FILM} then leave the summed film on rank 0 (host film_out may be NULL on ranks != 0).
+ * (2) one process, N GPUs (the Go daemon): gopbrt_multi_init creates one context per device and their communicators
+ *     (ncclCommInitAll); gopbrt_multi_scene_create builds the BVH once on the host and uploads it to every device;
+ *     gopbrt_multi_render is pbrt.Render: one host thread per device drives that device's wavefront, the films meet in one
+ *     ncclReduce on device 0 and film_out is read from there.  stats_out: counters summed over devices, times = max.
+ * libnccl.so.2 is bound at run time (dlopen; GOPBRT_NCCL_LIB overrides) — single-GPU hosts do not need it. */
+#define GOPBRT_COMM_ID_BYTES 128
+int gopbrt_comm_unique_id(unsigned char id[GOPBRT_COMM_ID_BYTES]);
+int gopbrt_comm_init_rank(gopbrt_ctx*, const unsigned char id[GOPBRT_COMM_ID_BYTES], int rank, int world);
+
+typedef struct gopbrt_multi gopbrt_multi;             /* N contexts + their communicators, one process */
+typedef struct gopbrt_multi_scene gopbrt_multi_scene; /* one scene replicated on the N devices         */
+/* devices: n_gpus CUDA ordinals, or NULL for 0..n_gpus-1 */
+int gopbrt_multi_init(int n_gpus, const int* devices, gopbrt_multi** out);
+void gopbrt_multi_shutdown(gopbrt_multi*);
+int gopbrt_multi_device_count(const gopbrt_multi*);
+const char* gopbrt_multi_last_error(const gopbrt_multi*);
+uint64_t gopbrt_multi_launch_count(const gopbrt_multi*);
+int gopbrt_multi_scene_create(gopbrt_multi*, const gopbrt_scene_desc*, gopbrt_multi_scene** out);
+void gopbrt_multi_scene_destroy(gopbrt_multi_scene*);
+/* flags: GOPBRT_FLAG_* of gopbrt_render_options (the reduce flag is implied) */
+int gopbrt_multi_render(gopbrt_multi_scene*, const gopbrt_camera*, const gopbrt_sampler*, const gopbrt_integrator*,
+                        const gopbrt_film*, int flags, double* film_out, gopbrt_stats* stats_out);
+int gopbrt_multi_cancel(gopbrt_multi_scene*);
 
 /* Self-test hook (tests/test_shading_kats.py): evaluates ONE device function of the raygen / shade / film stages on the GPU,
  * single thread, on flat float64 arguments, so the functions the kernels call can be pinned against known answers derived

@@ -267,7 +267,12 @@ def test_fast_mode_is_statistically_equivalent_to_strict(gp, dev, config, depth)
         pred = np.median(0.6745 * sigma[keep][lit] * np.sqrt(2.0 / n))
         print(f"[tier3] {config} full: n={n} pixels kept {100 * keep.mean():.1f}% mean FAST={F[keep].mean():.6g} STRICT={S[keep].mean():.6g} "
               f"diff={D.mean():.4g} 4SE={4 * se:.4g} median|D|={mad:.4g} predicted={pred:.4g}")
-        assert keep.mean() >= 0.6, f"only {100 * keep.mean():.1f}% of the pixels are free of heavy-tail samples"
+        # how many pixels stay below the bound is itself a statistic both modes must agree on (config 2, a closed room with a
+        # mirror and a glass sphere, keeps under half of them at 63 spp)
+        kf, ks = (F <= 10.0).all(axis=2).mean(), (S <= 10.0).all(axis=2).mean()
+        assert keep.mean() >= 0.25, f"only {100 * keep.mean():.1f}% of the pixels are free of heavy-tail samples"
+        npix = F.shape[0] * F.shape[1]
+        assert abs(kf - ks) <= 4.0 * np.sqrt(2.0 * max(kf * (1 - kf), 1e-4) / npix), (kf, ks)  # two independent binomial fractions
         assert abs(D.mean()) <= 4.0 * se
         assert 0.5 * pred <= mad <= 2.0 * pred
         return
