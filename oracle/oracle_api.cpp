@@ -303,6 +303,60 @@ int oracle_kat_eval(void* scene, const char* fn_c, const double* in, int n_in, d
     put3(0, r.o); put3(3, r.d);
     return 6;
   }
+  // ---- the reference's own unit-test vectors for the vector / spectrum / flag / partition helpers the path is made of
+  // (pkg/geometry/xyz_test.go, pkg/pbrt/spectrum_test.go, pkg/pbrt/reflection_test.go:9-15, pkg/accelerator/bvh_test.go:143-264;
+  // replayed by tests/test_oracle_golden.py)
+  if (fn == "xyz_op" && n_in == 8 && n_out >= 3) {  // in: op, a.xyz, b.xyz, scalar
+    int op = (int)in[0];
+    V3 a = v3(1), b = v3(4);
+    double s = in[7];
+    switch (op) {
+      case 0: put3(0, vabs(a)); return 3;                                  // Abs            xyz.go
+      case 1: out[0] = absdot(a, b); return 1;                             // AbsDot
+      case 2: put3(0, add(a, b)); return 3;                                // Add / AddAssign
+      case 3: put3(0, V3{a.x + s, a.y + s, a.z + s}); return 3;            // AddConst
+      case 4: put3(0, cross(a, b)); return 3;                              // Cross
+      case 5: out[0] = dist(a, b); return 1;                               // Distance
+      case 6: out[0] = dist2(a, b); return 1;                              // DistanceSquared
+      case 7: put3(0, V3{a.x / b.x, a.y / b.y, a.z / b.z}); return 3;      // Div / DivAssign
+      case 8: put3(0, divs(a, s)); return 3;                               // DivScalar
+      case 9: out[0] = dot(a, b); return 1;                                // Dot
+      case 10: out[0] = length(a); return 1;                               // Length
+      case 11: out[0] = len2(a); return 1;                                 // LengthSquared
+      case 12: put3(0, mul(a, b)); return 3;                               // Mul / MulAssign
+      case 13: put3(0, muls(a, s)); return 3;                              // MulScalar
+      case 14: put3(0, normalized(a)); return 3;                           // Normalize / Normalized
+      case 15: put3(0, sub(a, b)); return 3;                               // Sub / SubAssign
+      case 16: out[0] = (a.x == b.x && a.y == b.y && a.z == b.z) ? 1 : 0; return 1;  // Equals (NotEquals = !)
+      case 17: out[0] = a[(int)s]; return 1;                               // Index
+    }
+    return -1;
+  }
+  if (fn == "spectrum_op" && n_in == 8 && n_out >= 3) {  // in: op, a.rgb, b.rgb, scalar
+    int op = (int)in[0];
+    RGB a(in[1], in[2], in[3]), b(in[4], in[5], in[6]);
+    double s = in[7];
+    switch (op) {
+      case 0: putc(0, sadd(a, b)); return 3;                                           // Add / AddAssign   spectrum.go
+      case 1: putc(0, RGB(a.c[0] + s, a.c[1] + s, a.c[2] + s)); return 3;              // AddScalar
+      case 2: putc(0, sdivs(a, s)); return 3;                                          // DivScalar
+      case 3: putc(0, smul(a, b)); return 3;                                           // Mul
+      case 4: out[0] = sblack(a) ? 1 : 0; return 1;                                    // IsBlack
+    }
+    return -1;
+  }
+  if (fn == "matches_flags" && n_in == 2 && n_out >= 1) { out[0] = matches((int)in[0], (int)in[1]) ? 1 : 0; return 1; }  // reflection.go:301-303
+  if (fn == "partition_at" && n_in >= 4) {  // in: start, end, pivot, centroid.x of every element (its primitive number too); bvh.go:163-175
+    int n = n_in - 3;
+    if (n_out < n + 1) return -1;
+    std::vector<BuildInfo> info(n);
+    for (int i = 0; i < n; i++) { info[i].prim = (int)in[3 + i]; info[i].c = V3{in[3 + i], 0, 0}; }
+    int64_t r = partition_at(info, (int64_t)in[0], (int64_t)in[1], (int64_t)in[2],
+                             [](const BuildInfo& a, const BuildInfo& b) { return a.c[0] < b.c[0]; });
+    for (int i = 0; i < n; i++) out[i] = (double)info[i].prim;
+    out[n] = (double)r;
+    return n + 1;
+  }
   return -1;
 }
 }

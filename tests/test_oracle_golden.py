@@ -158,3 +158,66 @@ def test_sampler_stratified_tables(oracle, gp):
         assert all(0.0 <= v < 1.0 for v in o1)
         assert any(v != 0.0 for v in list(o2)[8:])
     assert vals <= {(i + 0.5) / 16 for i in range(16)} and len(vals) == 15
+
+
+# ---- the reference's remaining unit tests for helpers the path is made of, replayed against the oracle's own functions
+def _kat(oracle, fn, args, n_out=16):
+    oracle.oracle_kat_eval.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_double), C.c_int]
+    oracle.oracle_kat_eval.restype = C.c_int
+    vin = (C.c_double * len(args))(*args)
+    out = (C.c_double * n_out)()
+    n = oracle.oracle_kat_eval(None, fn.encode(), vin, len(args), out, n_out)
+    assert n >= 0, f"{fn}: rejected"
+    return list(out)[:n]
+
+
+def _xyz(oracle, op, a, b=(0, 0, 0), s=0.0):
+    return _kat(oracle, "xyz_op", [op, *a, *b, s])
+
+
+def test_xyz_golden(oracle):
+    # pkg/geometry/xyz_test.go:9-162, every arithmetic case (String/Set/SetIndex are Go plumbing with no counterpart)
+    assert _xyz(oracle, 0, (-1, -2, -3)) == [1, 2, 3]                       # Abs            :9-13
+    assert _xyz(oracle, 1, (-1, -2, -3), (1, 2, 3)) == [14.0]               # AbsDot         :15-18
+    assert _xyz(oracle, 2, (1, 2, 3), (1, 2, 3)) == [2, 4, 6]               # Add, AddAssign :20-29
+    assert _xyz(oracle, 3, (1, 2, 3), s=1.0) == [2, 3, 4]                   # AddConst       :31-34
+    assert _xyz(oracle, 4, (1, 2, 3), (1, 2, 4)) == [2, -1, 0]              # Cross          :36-39
+    assert _xyz(oracle, 5, (1, 2, 3), (1, 2, 4)) == [1.0]                   # Distance       :41-44
+    assert _xyz(oracle, 6, (1, 2, 3), (1, 2, 5)) == [4.0]                   # DistanceSquared:46-49
+    assert _xyz(oracle, 7, (3, 9, 27), (3, 3, 3)) == [1, 3, 9]              # Div, DivAssign :51-60
+    assert _xyz(oracle, 8, (3, 9, 27), s=3.0) == [1, 3, 9]                  # DivScalar      :62-65
+    assert _xyz(oracle, 9, (3, 9, 27), (2, 4, 6)) == [204.0]                # Dot            :67-71
+    assert _xyz(oracle, 16, (3, 9, 27), (3, 9, 27)) == [1] and _xyz(oracle, 16, (3, 9, 27), (0, 0, 0)) == [0]  # Equals / NotEquals :73-77,134-138
+    assert [_xyz(oracle, 17, (2, 3, 4), s=k)[0] for k in range(3)] == [2, 3, 4]  # Index     :79-84
+    assert _xyz(oracle, 10, (0, 3, 0)) == [3.0]                             # Length         :86-89
+    assert _xyz(oracle, 11, (0, 3, 0)) == [9.0]                             # LengthSquared  :91-94
+    assert _xyz(oracle, 12, (1, 2, 3), (1, 2, 3)) == [1, 4, 9]              # Mul, MulAssign :96-106
+    assert _xyz(oracle, 13, (1, 2, 3), s=2.0) == [2, 4, 6]                  # MulScalar      :108-111
+    assert _xyz(oracle, 14, (0, 0, 3)) == [0, 0, 1]                         # Normalize(d)   :113-132 (1/sqrt then multiply)
+    assert _xyz(oracle, 15, (2, 4, 6), (1, 3, 5)) == [1, 1, 1]              # Sub, SubAssign :152-162
+
+
+def test_spectrum_golden(oracle):
+    # pkg/pbrt/spectrum_test.go:9-67 (Clone is Go aliasing, no counterpart: RGB is a value type here)
+    sp = lambda op, a, b=(0, 0, 0), s=0.0: _kat(oracle, "spectrum_op", [op, *a, *b, s])
+    assert sp(0, (1, 1, 1), (2, 2, 2)) == [3, 3, 3]        # Add, AddAssign :9-27
+    assert sp(1, (1, 1, 1), s=2.0) == [3, 3, 3]            # AddScalar      :29-36
+    assert sp(2, (3, 3, 3), s=3.0) == [1, 1, 1]            # DivScalar      :52-55
+    assert sp(3, (3, 3, 3), (4, 4, 4)) == [12, 12, 12]     # Mul            :57-60
+    assert sp(4, (1.0, 0.0, 1.0)) == [0] and sp(4, (1, 1, 1)) == [0] and sp(4, (1e-4,) * 3) == [0] and sp(4, (0, 0, 0)) == [1]  # IsBlack :62-67
+
+
+def test_matches_flags_golden(oracle):
+    # pkg/pbrt/reflection_test.go:9-15 with the BxDFType bits of reflection.go:286-299
+    REFL, TRANS, DIFF, GLOSSY, SPEC = 1, 2, 4, 8, 16
+    ALL = REFL | TRANS | DIFF | GLOSSY | SPEC
+    m = lambda t, f: _kat(oracle, "matches_flags", [t, f]) == [1]
+    assert m(DIFF, DIFF) and m(DIFF, DIFF | REFL) and m(REFL, DIFF | REFL) and not m(REFL, DIFF) and m(REFL, ALL)
+
+
+def test_partition_primitive_info_at_golden(oracle):
+    # pkg/accelerator/bvh_test.go:143-264 — the Lomuto partition behind the reference builder's SplitSAH / SplitMiddle
+    # (elements are identified by centroid.x == primitiveNumber, as in the reference's table)
+    part = lambda xs, start, end, pivot: [int(v) for v in _kat(oracle, "partition_at", [start, end, pivot, *xs])[:-1]]
+    assert part([5, 4, 3, 2, 1], 0, 4, 2) == [1, 2, 3, 4, 5]
+    assert part([5, 1, 2, 4, 3], 0, 4, 1) == [1, 3, 2, 4, 5]
