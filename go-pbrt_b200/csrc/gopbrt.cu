@@ -69,8 +69,30 @@ struct DevBuf {
     if (e != cudaSuccess || v.empty()) return e;
     return cudaMemcpyAsync(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, s);
   }
+  // grow-only: keeps the allocation when it is already large enough (n then stays the capacity)
+  cudaError_t ensure(size_t count) { return count <= n ? cudaSuccess : alloc(count + count / 4); }
   void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
   ~DevBuf() { release(); }
+};
+
+// Scratch of the batched Intersect / IntersectP entry points, kept per scene and only ever grown: a host that traces batch
+// after batch (the parity tests of the Go side, a baking tool) pays cudaMalloc / cudaFree and page-locking once, not per call.
+struct BatchPool {
+  DevBuf<RayRec> recs;
+  DevBuf<double> rays, t, p, n;
+  DevBuf<int> rec, prim;
+  DevBuf<unsigned char> hit;
+  double* stage = nullptr;  // pinned host staging: the caller's seven SoA arrays are gathered here and go up as ONE copy
+  size_t stage_cap = 0;
+  cudaError_t ensure_stage(size_t doubles) {
+    if (doubles <= stage_cap) return cudaSuccess;
+    if (stage) cudaFreeHost(stage);
+    stage = nullptr; stage_cap = 0;
+    cudaError_t e = cudaHostAlloc((void**)&stage, (doubles + doubles / 4) * sizeof(double), cudaHostAllocDefault);
+    if (e == cudaSuccess) stage_cap = doubles + doubles / 4;
+    return e;
+  }
+  ~BatchPool() { if (stage) cudaFreeHost(stage); }
 };
 
 struct Workspace {  // per-scene render workspace, kept between gopbrt_render calls of the same shape
@@ -133,6 +155,7 @@ struct gopbrt_scene {
   uint64_t bvh_nodes = 0, bvh_depth = 0;
   std::atomic<int> cancel{0};
   Workspace ws;
+  BatchPool pool;
   std::mutex mu;
 };
 
@@ -383,7 +406,7 @@ static int build_host_scene(const gopbrt_scene_desc* d, HostScene& H, std::strin
   max_prims = std::min(max_prims, 2);
   if (const char* mp = getenv("GOPBRT_MAX_PRIMS")) max_prims = std::max(1, std::min(255, atoi(mp)));
   bvh = gpbvh::build_bvh(pb.data(), np, max_prims);
-  if ((int64_t)bvh.order.size() != np) return bad("BVH build failed (out of host memory)");
+  if ((int64_t)bvh.order.size() != np || (np > 0 && bvh.nodes.empty())) return bad("BVH build failed (out of host memory, or more primitives / nodes than a node word addresses)");
   if (bvh.depth >= kStackDepth - 1) return bad("BVH deeper than the traversal stack");
 
   // ---- leaf-ordered primitive records + their float64 bounds
@@ -459,6 +482,8 @@ static int build_host_scene(const gopbrt_scene_desc* d, HostScene& H, std::strin
   texs.resize(d->n_textures);
   for (int i = 0; i < d->n_textures; i++) {
     const gopbrt_texture& t = d->textures[i];
+    // checkerboard children must come earlier in the table: the texture graph is a DAG by construction (tex_eval recurses)
+    if (t.kind == GOPBRT_TEX_CHECKERBOARD && (t.tex1 < 0 || t.tex2 < 0 || t.tex1 >= i || t.tex2 >= i)) return bad("checkerboard child index must be smaller than the texture's own");
     TextureDev o;
     o.kind = t.kind; o.mapping = t.mapping; o.tex1 = t.tex1; o.tex2 = t.tex2;
     if (t.kind == GOPBRT_TEX_CHECKERBOARD && (t.tex1 < 0 || t.tex1 >= d->n_textures || t.tex2 < 0 || t.tex2 >= d->n_textures)) return bad("bad checkerboard children");
@@ -546,10 +571,16 @@ static int upload_scene(gopbrt_ctx* ctx, HostScene& H, gopbrt_scene** out) {
   // stacks at most three records
   sc->stack_cap = std::min(250, 3 * ((bvh.depth + 2) / 2) + 4);
   if (const char* e = getenv("GOPBRT_STACK_CAP")) sc->stack_cap = std::max(4, atoi(e));  // tuning aid (overflows are counted)
-  sc->trace_smem = (size_t)sc->stack_cap * kTraceThreads * 2 * sizeof(unsigned);  // two words (a, b) per stacked node
-  sc->trace_k[0] = k_trace<0, false>; sc->trace_k[1] = k_trace<0, true>; sc->trace_k[2] = k_trace<2, false>;
-  sc->trace_k[3] = k_trace<2, true>; sc->trace_k[4] = k_trace<1, false>;
-  sc->trace_k[5] = k_trace<3, false>; sc->trace_k[6] = k_trace<3, true>;
+  sc->trace_smem = (size_t)sc->stack_cap * kTraceThreads * sizeof(unsigned);  // one node word per stacked node
+  // scenes of triangles only get the traversal kernels that carry no sphere / disk (EFloat) code
+  bool quadrics = false;
+  for (const PrimRec& r : recs) if ((r.flags & RK_KIND_MASK) != RK_TRIANGLE) { quadrics = true; break; }
+  if (getenv("GOPBRT_GENERAL_TRACE")) quadrics = true;  // tuning aid: the general kernels on a triangle-only scene
+  static const trace_fn k_general[7] = {k_trace<0, false, true>, k_trace<0, true, true>, k_trace<2, false, true>, k_trace<2, true, true>,
+                                        k_trace<1, false, true>, k_trace<3, false, true>, k_trace<3, true, true>};
+  static const trace_fn k_triangles[7] = {k_trace<0, false, false>, k_trace<0, true, false>, k_trace<2, false, false>, k_trace<2, true, false>,
+                                          k_trace<1, false, false>, k_trace<3, false, false>, k_trace<3, true, false>};
+  for (int k = 0; k < 7; k++) sc->trace_k[k] = quadrics ? k_general[k] : k_triangles[k];
   if (D.n_flat > 0) {  // small scene: the flat aggregate answers every query (no traversal stack)
     sc->trace_k[0] = k_trace_flat<0, false>; sc->trace_k[1] = k_trace_flat<0, true>; sc->trace_k[2] = k_trace_flat<2, false>;
     sc->trace_k[3] = k_trace_flat<2, true>; sc->trace_k[4] = k_trace_flat<1, false>;
@@ -559,10 +590,8 @@ static int upload_scene(gopbrt_ctx* ctx, HostScene& H, gopbrt_scene** out) {
   // cudaFuncAttributeMaxDynamicSharedMemorySize belongs to the kernel, not to the scene: it only ever grows (a later, shallower
   // scene must not lower the limit under a deeper one that is still alive)
   if (sc->trace_smem > 48 * 1024 && sc->trace_smem > ctx->trace_smem_limit) {
-    const void* ks[7] = {(const void*)k_trace<0, false>, (const void*)k_trace<0, true>, (const void*)k_trace<2, false>, (const void*)k_trace<2, true>,
-                         (const void*)k_trace<1, false>, (const void*)k_trace<3, false>, (const void*)k_trace<3, true>};
-    for (const void* k : ks) {
-      cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sc->trace_smem);
+    for (int k = 0; k < 14; k++) {
+      cudaError_t e = cudaFuncSetAttribute((const void*)(k < 7 ? k_general[k] : k_triangles[k - 7]), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sc->trace_smem);
       if (e != cudaSuccess) { ctx->last_error = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e); delete sc; return GOPBRT_ERR_CUDA; }
     }
     ctx->trace_smem_limit = sc->trace_smem;
@@ -613,8 +642,8 @@ static RaySoA soa7(double* base, long long n) {
 // primitive ids, rec (may be null) leaf-record indices, t the hit distance (tmax where nothing was hit).
 static int trace_closest_soa_device(gopbrt_scene* sc, int64_t n, const double* rays_soa7, int32_t* prim, int32_t* rec, double* t, cudaStream_t st) {
   gopbrt_ctx* ctx = sc->ctx;
-  DevBuf<RayRec> recs;
-  GP_CUDA(ctx, recs.alloc((size_t)n));
+  DevBuf<RayRec>& recs = sc->pool.recs;
+  GP_CUDA(ctx, recs.ensure((size_t)n));
   RaySoA r = soa7(const_cast<double*>(rays_soa7), n);
   int gs = ctx->sm_count * 8;
   k_pack_rays<<<gs, 256, 0, st>>>(r, recs.p, n);
@@ -626,30 +655,35 @@ static int trace_closest_soa_device(gopbrt_scene* sc, int64_t n, const double* r
   k_unpack_hits<<<gs, 256, 0, st>>>(sc->dev, recs.p, prim, rec, t, n);
   ctx->launches += 3;
   GP_CUDA(ctx, cudaGetLastError());
-  GP_CUDA(ctx, cudaStreamSynchronize(st));  // recs is freed on return
+  GP_CUDA(ctx, cudaStreamSynchronize(st));  // the pooled records are reused by the next call
   return GOPBRT_OK;
 }
 
+// the traversal kernels index rays with 32-bit counters
+static const int64_t kMaxBatchRays = 0x7fffff00;
+
 extern "C" int gopbrt_trace_closest_device(gopbrt_scene* sc, int64_t n, const double* rays_soa7, int32_t* prim, double* t, void* stream) {
-  if (!sc || n < 0) return GOPBRT_ERR_INVALID;
+  if (!sc || n < 0 || n > kMaxBatchRays || (n > 0 && (!rays_soa7 || !t))) return GOPBRT_ERR_INVALID;
   if (n == 0) return GOPBRT_OK;
   std::lock_guard<std::mutex> grun(sc->ctx->run_mu);
+  GP_CUDA(sc->ctx, cudaSetDevice(sc->ctx->device));
   return trace_closest_soa_device(sc, n, rays_soa7, prim, nullptr, t, stream ? (cudaStream_t)stream : sc->ctx->stream);
 }
 
 static int trace_any_soa_device(gopbrt_scene* sc, int64_t n, const double* rays_soa7, uint8_t* hit, void* stream);
 extern "C" int gopbrt_trace_any_device(gopbrt_scene* sc, int64_t n, const double* rays_soa7, uint8_t* hit, void* stream) {
-  if (!sc || n < 0) return GOPBRT_ERR_INVALID;
+  if (!sc || n < 0 || n > kMaxBatchRays || (n > 0 && (!rays_soa7 || !hit))) return GOPBRT_ERR_INVALID;
   if (n == 0) return GOPBRT_OK;
   std::lock_guard<std::mutex> grun(sc->ctx->run_mu);
+  GP_CUDA(sc->ctx, cudaSetDevice(sc->ctx->device));
   return trace_any_soa_device(sc, n, rays_soa7, hit, stream);
 }
 // callers hold the context's run_mu
 static int trace_any_soa_device(gopbrt_scene* sc, int64_t n, const double* rays_soa7, uint8_t* hit, void* stream) {
   gopbrt_ctx* ctx = sc->ctx;
   cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
-  DevBuf<RayRec> recs;
-  GP_CUDA(ctx, recs.alloc((size_t)n));
+  DevBuf<RayRec>& recs = sc->pool.recs;
+  GP_CUDA(ctx, recs.ensure((size_t)n));
   RaySoA r = soa7(const_cast<double*>(rays_soa7), n);
   k_pack_rays<<<ctx->sm_count * 8, 256, 0, st>>>(r, recs.p, n);
   long long need = (n + kTraceThreads - 1) / kTraceThreads;
@@ -665,28 +699,31 @@ static int trace_any_soa_device(gopbrt_scene* sc, int64_t n, const double* rays_
 
 extern "C" int gopbrt_trace_closest(gopbrt_scene* sc, int64_t n, const double* ox, const double* oy, const double* oz, const double* dx,
                                     const double* dy, const double* dz, const double* tmax, int32_t* prim, double* t, double* p, double* nrm) {
-  if (!sc || n < 0 || (n > 0 && (!ox || !oy || !oz || !dx || !dy || !dz || !tmax || !prim || !t))) return GOPBRT_ERR_INVALID;
+  if (!sc || n < 0 || n > kMaxBatchRays || (n > 0 && (!ox || !oy || !oz || !dx || !dy || !dz || !tmax || !prim || !t))) return GOPBRT_ERR_INVALID;
   if (n == 0) return GOPBRT_OK;
   gopbrt_ctx* ctx = sc->ctx;
   std::lock_guard<std::mutex> g(sc->mu);
   std::lock_guard<std::mutex> grun(sc->ctx->run_mu);
   GP_CUDA(ctx, cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
-  DevBuf<double> rays, tt, pp, nn;
-  DevBuf<int> rec, pr;
-  GP_CUDA(ctx, rays.alloc(7 * (size_t)n));
-  GP_CUDA(ctx, tt.alloc(n));
-  GP_CUDA(ctx, rec.alloc(n));
-  GP_CUDA(ctx, pr.alloc(n));
-  GP_CUDA(ctx, pp.alloc(3 * (size_t)n));
-  GP_CUDA(ctx, nn.alloc(3 * (size_t)n));
+  BatchPool& B = sc->pool;
+  DevBuf<double>&rays = B.rays, &tt = B.t, &pp = B.p, &nn = B.n;
+  DevBuf<int>&rec = B.rec, &pr = B.prim;
+  GP_CUDA(ctx, rays.ensure(7 * (size_t)n));
+  GP_CUDA(ctx, tt.ensure(n));
+  GP_CUDA(ctx, rec.ensure(n));
+  GP_CUDA(ctx, pr.ensure(n));
+  if (p) GP_CUDA(ctx, pp.ensure(3 * (size_t)n));
+  if (nrm) GP_CUDA(ctx, nn.ensure(3 * (size_t)n));
+  GP_CUDA(ctx, B.ensure_stage(7 * (size_t)n));
   const double* src[7] = {ox, oy, oz, dx, dy, dz, tmax};
-  for (int k = 0; k < 7; k++) GP_CUDA(ctx, cudaMemcpyAsync(rays.p + (size_t)k * n, src[k], n * sizeof(double), cudaMemcpyHostToDevice, st));
+  for (int k = 0; k < 7; k++) memcpy(B.stage + (size_t)k * n, src[k], (size_t)n * sizeof(double));
+  GP_CUDA(ctx, cudaMemcpyAsync(rays.p, B.stage, 7 * (size_t)n * sizeof(double), cudaMemcpyHostToDevice, st));
   int rc = trace_closest_soa_device(sc, n, rays.p, nullptr, rec.p, tt.p, st);
   if (rc != GOPBRT_OK) return rc;
   RaySoA r = soa7(rays.p, n);
   r.tmax = tt.p;
-  k_hit_points<<<ctx->sm_count * 4, 128, 0, st>>>(sc->dev, r, rec.p, n, pr.p, pp.p, nn.p);
+  k_hit_points<<<ctx->sm_count * 4, 128, 0, st>>>(sc->dev, r, rec.p, n, pr.p, p ? pp.p : nullptr, nrm ? nn.p : nullptr);
   ctx->launches++;
   GP_CUDA(ctx, cudaGetLastError());
   GP_CUDA(ctx, cudaMemcpyAsync(prim, pr.p, n * sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -699,19 +736,22 @@ extern "C" int gopbrt_trace_closest(gopbrt_scene* sc, int64_t n, const double* o
 
 extern "C" int gopbrt_trace_any(gopbrt_scene* sc, int64_t n, const double* ox, const double* oy, const double* oz, const double* dx,
                                 const double* dy, const double* dz, const double* tmax, uint8_t* hit) {
-  if (!sc || n < 0 || (n > 0 && (!ox || !oy || !oz || !dx || !dy || !dz || !tmax || !hit))) return GOPBRT_ERR_INVALID;
+  if (!sc || n < 0 || n > kMaxBatchRays || (n > 0 && (!ox || !oy || !oz || !dx || !dy || !dz || !tmax || !hit))) return GOPBRT_ERR_INVALID;
   if (n == 0) return GOPBRT_OK;
   gopbrt_ctx* ctx = sc->ctx;
   std::lock_guard<std::mutex> g(sc->mu);
   std::lock_guard<std::mutex> grun(sc->ctx->run_mu);
   GP_CUDA(ctx, cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
-  DevBuf<double> rays;
-  DevBuf<unsigned char> h;
-  GP_CUDA(ctx, rays.alloc(7 * (size_t)n));
-  GP_CUDA(ctx, h.alloc(n));
+  BatchPool& B = sc->pool;
+  DevBuf<double>& rays = B.rays;
+  DevBuf<unsigned char>& h = B.hit;
+  GP_CUDA(ctx, rays.ensure(7 * (size_t)n));
+  GP_CUDA(ctx, h.ensure(n));
+  GP_CUDA(ctx, B.ensure_stage(7 * (size_t)n));
   const double* src[7] = {ox, oy, oz, dx, dy, dz, tmax};
-  for (int k = 0; k < 7; k++) GP_CUDA(ctx, cudaMemcpyAsync(rays.p + (size_t)k * n, src[k], n * sizeof(double), cudaMemcpyHostToDevice, st));
+  for (int k = 0; k < 7; k++) memcpy(B.stage + (size_t)k * n, src[k], (size_t)n * sizeof(double));
+  GP_CUDA(ctx, cudaMemcpyAsync(rays.p, B.stage, 7 * (size_t)n * sizeof(double), cudaMemcpyHostToDevice, st));
   int rc = trace_any_soa_device(sc, n, rays.p, h.p, st);
   if (rc != GOPBRT_OK) return rc;
   GP_CUDA(ctx, cudaMemcpyAsync(hit, h.p, n, cudaMemcpyDeviceToHost, st));
@@ -768,7 +808,9 @@ static int render_impl(gopbrt_scene* sc, const gopbrt_camera* cam, const gopbrt_
   int rank = opt ? opt->rank : 0, world = opt ? opt->world : 1;
   int flags = opt ? opt->flags : 0;
   if (world < 1 || rank < 0 || rank >= world) return bad("bad rank/world");
-  sc->cancel.store(0);
+  // A cancel request is consumed by the render call that observes it: the running one, or — when it arrived before any
+  // wavefront was launched (ctx already done, integrator.go:332-336) — this one, right here.
+  if (sc->cancel.exchange(0)) return GOPBRT_ERR_CANCELLED;
 
   RenderParams P;
   memset(&P, 0, sizeof(P));  // padding too: the struct is part of the CUDA-graph cache key
@@ -838,6 +880,9 @@ static int render_impl(gopbrt_scene* sc, const gopbrt_camera* cam, const gopbrt_
   size_t bt = table_doubles * lanes, bp = P.uniform_fp ? 0 : (size_t)tpw * tph * 4 * lanes;
   if (W.lanes != lanes || W.bytes_tables != bt || W.bytes_tilepix != bp || W.frames.n != frame_doubles * (size_t)lanes || W.sray.n != n_seg * (size_t)lanes ||
       W.occl.n != (direct_all ? n_seg * (size_t)lanes : 0) || W.codes.n != (size_t)lanes) {
+    // the shape fields are cleared first: a failed allocation below must not leave a "same shape" workspace with null buffers
+    W.lanes = 0; W.bytes_tables = 0; W.bytes_tilepix = 0;
+    if (W.graph_exec) { cudaGraphExecDestroy(W.graph_exec); W.graph_exec = nullptr; W.graph_key.clear(); }
     W.ray.release(); W.sray.release(); W.path.release(); W.i32.release(); W.tables.release(); W.tilepix.release(); W.frames.release(); W.occl.release(); W.codes.release();
     GP_CUDA(ctx, W.ray.alloc((size_t)lanes));
     GP_CUDA(ctx, W.sray.alloc(n_seg * (size_t)lanes));
@@ -901,7 +946,11 @@ static int render_impl(gopbrt_scene* sc, const gopbrt_camera* cam, const gopbrt_
   const int g_gen = ctx->grid_gen[gen_i];
   constexpr int kGraphIters = 8;
 
-  cudaEvent_t ev[2];
+  struct EventPair {  // destroyed on every return path
+    cudaEvent_t e[2] = {nullptr, nullptr};
+    ~EventPair() { for (auto x : e) if (x) cudaEventDestroy(x); }
+    cudaEvent_t& operator[](int i) { return e[i]; }
+  } ev;
   GP_CUDA(ctx, cudaEventCreate(&ev[0]));
   GP_CUDA(ctx, cudaEventCreate(&ev[1]));
   GP_CUDA(ctx, cudaEventRecord(ev[0], st));
@@ -962,9 +1011,11 @@ static int render_impl(gopbrt_scene* sc, const gopbrt_camera* cam, const gopbrt_
         cudaGraph_t graph = nullptr;
         GP_CUDA(ctx, cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
         for (int k = 0; k < kGraphIters; k++) enqueue_iteration();  // kGraphIters is even: the queue pointers end where they started
-        GP_CUDA(ctx, cudaStreamEndCapture(st, &graph));
-        cudaError_t ge = cudaGraphInstantiate(&W.graph_exec, graph, 0);
-        cudaGraphDestroy(graph);
+        // the capture is always ended — a launch error inside it must not leave the context's stream in capture mode
+        cudaError_t ce = cudaStreamEndCapture(st, &graph);
+        cudaError_t ge = ce == cudaSuccess ? cudaGraphInstantiate(&W.graph_exec, graph, 0) : ce;
+        if (graph) cudaGraphDestroy(graph);
+        if (ge != cudaSuccess) { W.graph_exec = nullptr; W.graph_key.clear(); cudaGetLastError(); }
         GP_CUDA(ctx, ge);
         W.graph_key = key;
       }
@@ -978,7 +1029,7 @@ static int render_impl(gopbrt_scene* sc, const gopbrt_camera* cam, const gopbrt_
         if (k == 0) continue;
         GP_CUDA(ctx, cudaEventSynchronize(W.graph_ev[(k - 1) & 1]));  // graph k-1 is done, graph k is running or queued
         if (*W.remaining_host == 0) break;
-        if (sc->cancel.load()) { rc = GOPBRT_ERR_CANCELLED; break; }
+        if (sc->cancel.exchange(0)) { rc = GOPBRT_ERR_CANCELLED; break; }
       }
       GP_CUDA(ctx, cudaStreamSynchronize(st));
     }
@@ -1016,7 +1067,7 @@ static int render_impl(gopbrt_scene* sc, const gopbrt_camera* cam, const gopbrt_
       if ((iterations & 3) != 0) continue;
       GP_CUDA(ctx, cudaStreamSynchronize(st));
       if (*W.remaining_host == 0) break;
-      if (sc->cancel.load()) { rc = GOPBRT_ERR_CANCELLED; break; }
+      if (sc->cancel.exchange(0)) { rc = GOPBRT_ERR_CANCELLED; break; }
     }
     tick(ST_FILM);
     k_film_merge<<<g_small, 128, 0, st>>>(L, P, d_film);
@@ -1030,8 +1081,6 @@ static int render_impl(gopbrt_scene* sc, const gopbrt_camera* cam, const gopbrt_
   GP_CUDA(ctx, cudaGetLastError());
   float ms = 0;
   cudaEventElapsedTime(&ms, ev[0], ev[1]);
-  cudaEventDestroy(ev[0]);
-  cudaEventDestroy(ev[1]);
   RenderCounters rcnt;
   TraceCounters tcnt;
   GP_CUDA(ctx, cudaMemcpy(&rcnt, W.rctr.p, sizeof(rcnt), cudaMemcpyDeviceToHost));

@@ -8,6 +8,7 @@
 // node boxes written here are float32 rounded OUTWARD of the float64 union, so they never do.
 #pragma once
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdint>
 #include <cstdlib>
@@ -80,16 +81,25 @@ struct Builder {
     int64_t n = end - start;
     int axis0 = 0;
     { float ex = cmx[0] - cmn[0], ey = cmx[1] - cmn[1], ez = cmx[2] - cmn[2]; axis0 = (ex > ey && ex > ez) ? 0 : (ey > ez ? 1 : 2); }
-    if (n <= max_prims || !(cmx[axis0] > cmn[axis0])) {
-      if (n <= 255 * 1024) {  // leaf (a degenerate cluster of coincident centroids stays one leaf; count field is 24 bits)
-        out[me].first = start;
-        out[me].n = (int)n;
-        out[me].axis = axis0;
-        return me;
-      }
+    if (n <= max_prims) {  // leaf: at most max_prims (<= kMaxLeafPrims) primitives, the count rides in two bits of the node word
+      out[me].first = start;
+      out[me].n = (int)n;
+      out[me].axis = axis0;
+      return me;
     }
     int64_t mid = -1;
     int best_axis = axis0;
+    if (!(cmx[axis0] > cmn[axis0])) {
+      // a cluster of coincident centroids: no plane separates it, so it is halved by index (logarithmic depth; the halves'
+      // boxes overlap, which costs those rays extra candidates and nothing else)
+      out[me].axis = axis0;
+      mid = (start + end) / 2;
+      int64_t l = build(out, used, start, mid, depth + 1, maxd);
+      int64_t r = build(out, used, mid, end, depth + 1, maxd);
+      out[me].left = l;
+      out[me].right = r;
+      return me;
+    }
     if (depth < 40 && n > 2) {
       const int NB = 16;
       double best = INFINITY;
@@ -158,20 +168,30 @@ struct Result {
   int depth = 0;
 };
 
-// 32-byte record of BNode i.  leaf: {a = first primitive record, b = nPrims<<8 | axis}.
-// interior: {a = index of its 4-record CHILD GROUP, b = axis0 | axis1<<2 | axis2<<4 | L_expanded<<6 | R_expanded<<7}
-// (b>>8 == 0 marks an interior record), filled in by flatten_quads.
+// 32-byte record of BNode i.  `a` is the node word the traversal carries and stacks (gp_trace.cuh):
+//   leaf:     a = first primitive record << 3 | (nPrims - 1) << 1 | 1
+//   interior: a = child-group index << 7 | axisL << 5 | axisR << 3 | axis0 << 1   (group g = records 4g .. 4g+3), filled in
+//             by flatten_quads; axisL / axisR = split axes of the left / right child when that child is interior
+//   unused slot of a group: a = kEmptyWord and the empty box.
+// `b` keeps the leaf's primitive count (host-side checks only; the kernels do not read it).
+constexpr int kMaxLeafPrims = 4;
+constexpr uint32_t kEmptyWord = 0xffffffffu;
+constexpr uint64_t kMaxLeafFirst = (1ull << 29) - 1, kMaxGroups = (1ull << 25) - 1;
+static inline uint32_t leaf_word(uint64_t first, int n) { return (uint32_t)(first << 3) | (uint32_t)((n - 1) << 1) | 1u; }
+static inline uint32_t inner_word(uint64_t group, int axis0, int axisL, int axisR) {
+  return (uint32_t)(group << 7) | (uint32_t)(axisL << 5) | (uint32_t)(axisR << 3) | (uint32_t)(axis0 << 1);
+}
 static Node32 make_record(const BNode& n) {
   Node32 o;
   for (int k = 0; k < 3; k++) { o.mn[k] = round_down(n.b.mn[k]); o.mx[k] = round_up(n.b.mx[k]); }
-  o.a = (uint32_t)n.first;
-  o.b = n.n > 0 ? (((uint32_t)n.n << 8) | (uint32_t)n.axis) : (uint32_t)n.axis;
+  o.a = n.n > 0 ? leaf_word((uint64_t)n.first, n.n) : 0u;
+  o.b = (uint32_t)n.n;
   return o;
 }
 static Node32 empty_record() {
   Node32 o;
   for (int k = 0; k < 3; k++) { o.mn[k] = INFINITY; o.mx[k] = -INFINITY; }
-  o.a = 0; o.b = 0;
+  o.a = kEmptyWord; o.b = 0;
   return o;
 }
 // Child-group layout ("quads"): the binary tree is kept as built, but an interior node's record points at a group of
@@ -191,8 +211,7 @@ static void flatten_quads(const BNode* in, int64_t i, size_t slot, std::vector<N
     const BNode& L = in[n.left];
     const BNode& R = in[n.right];
     uint32_t le = L.n == 0, re = R.n == 0;
-    rec.a = (uint32_t)g;
-    rec.b = (uint32_t)n.axis | ((uint32_t)(le ? L.axis : 0) << 2) | ((uint32_t)(re ? R.axis : 0) << 4) | (le << 6) | (re << 7);
+    rec.a = inner_word(g / 4, n.axis, le ? L.axis : 0, re ? R.axis : 0);
     out[slot] = rec;
     if (le) { flatten_quads(in, L.left, g, out); flatten_quads(in, L.right, g + 1, out); }
     else flatten_quads(in, n.left, g, out);
@@ -233,8 +252,7 @@ static void flatten_quads_at(const BNode* in, int64_t i, size_t slot, Node32* ou
   const BNode& L = in[n.left];
   const BNode& R = in[n.right];
   uint32_t le = L.n == 0, re = R.n == 0;
-  rec.a = (uint32_t)g;
-  rec.b = (uint32_t)n.axis | ((uint32_t)(le ? L.axis : 0) << 2) | ((uint32_t)(re ? R.axis : 0) << 4) | (le << 6) | (re << 7);
+  rec.a = inner_word(g / 4, n.axis, le ? L.axis : 0, re ? R.axis : 0);
   out[slot] = rec;
   int fd = fork_depth > 0 ? fork_depth - 1 : 0;
   if (le) { flatten_quads_at(in, L.left, g, out, cursor, fd, tasks); flatten_quads_at(in, L.right, g + 1, out, cursor, fd, tasks); }
@@ -274,7 +292,7 @@ static Result build_bvh(const Box* bounds, int64_t n, int max_prims) {
   GPBVH_TICK_INIT;
   Builder B;
   B.bounds = bounds;
-  B.max_prims = max_prims;
+  B.max_prims = std::max(1, std::min(max_prims, kMaxLeafPrims));
   B.cen.resize(3 * (size_t)n);
   B.idx.resize(n);
   for (int64_t i = 0; i < n; i++) {
@@ -374,8 +392,10 @@ static Result build_bvh(const Box* bounds, int64_t n, int max_prims) {
     root = cur[0];
     GPBVH_TICK("top tree");
   }
+  if ((uint64_t)n > kMaxLeafFirst) return res;  // the node word holds 29 bits of primitive index (536 M primitives)
   flatten(nodes, n_nodes, root, res.nodes);
   GPBVH_TICK("flatten");
+  if (res.nodes.size() / 4 > kMaxGroups) { res.nodes.clear(); return res; }  // ... and 25 bits of child-group index
   res.order = B.idx;
   res.depth = maxd;
   return res;

@@ -86,46 +86,56 @@ constexpr int kDescendSteps = GP_DESCEND_STEPS;
 #endif
 constexpr int kQuadricBatch = GP_QUADRIC_BATCH;   // parked sphere/disk tests that trigger their batched execution
 
+// Node words.  A record's `a` field (and every stack entry, and the traversal's current node) is ONE packed word:
+//   leaf:     first primitive record << 3 | (nPrims - 1) << 1 | 1          (nPrims <= 4, first < 2^29)
+//   interior: child-group index << 7 | axisL << 5 | axisR << 3 | axis0 << 1   (group g = records 4g .. 4g+3, 128 bytes)
+//   kEmptyWord marks the unused slot of a group whose left / right child is a leaf.
+// One word per stacked node halves the traversal stack's shared memory (44 -> 22 KB per CTA at depth 24), which is what
+// bounded the resident CTAs per SM next to the register file.
+constexpr unsigned kEmptyWord = 0xffffffffu;
+GP_D bool word_is_leaf(unsigned w) { return (w & 1u) != 0; }
+GP_D unsigned leaf_first(unsigned w) { return w >> 3; }
+GP_D unsigned leaf_count(unsigned w) { return ((w >> 1) & 3u) + 1u; }
+
 // One traversal step from an inner node whose box has passed: fetch its 4-record child group (128 contiguous bytes:
 // slots 0,1 = children of the left child, or the left child itself + an empty slot when it is a leaf; slots 2,3
 // likewise for the right child), test the (up to four) float32 boxes, continue with the first passing child in the
 // binary tree's near-first order — near side of the node's own split axis first, inside each side the near child of
 // that side's split axis first — and stack the other passing ones so that they pop in that same order.
-// (cur_a, cur_b) are the record words of the current node on entry and of the next node on exit (have_cur = false
-// when the traversal is over).  Returns the number of child records tested.
-GP_D int quad_step(const DevScene& sc, unsigned& cur_a, unsigned& cur_b, bool& have_cur, int& sp, unsigned* stack, int stride, int stack_cap,
+// `cur` is the word of the current node on entry and of the next node on exit (have_cur = false when the traversal is
+// over).  Returns the number of child records tested.
+GP_D int quad_step(const DevScene& sc, unsigned& cur, bool& have_cur, int& sp, unsigned* stack, int stride, int stack_cap,
                    const RayF32& rf, int nx, int ny, int nz, float tub, int& ovf) {
-  const float4* pp = sc.nodes + 2 * (size_t)cur_a;
+  const float4* pp = sc.nodes + 8 * (size_t)(cur >> 7);
   float4 c0a = __ldg(pp), c0b = __ldg(pp + 1), c1a = __ldg(pp + 2), c1b = __ldg(pp + 3);
   float4 c2a = __ldg(pp + 4), c2b = __ldg(pp + 5), c3a = __ldg(pp + 6), c3b = __ldg(pp + 7);
-  const bool le = (cur_b & 64u) != 0, re = (cur_b & 128u) != 0;
+  const unsigned w0 = __float_as_uint(c0a.w), w1 = __float_as_uint(c1a.w), w2 = __float_as_uint(c2a.w), w3 = __float_as_uint(c3a.w);
+  const bool le = w1 != kEmptyWord, re = w3 != kEmptyWord;
   bool p0 = slab_test_f32_maybe(c0a, c0b, rf, nx, ny, nz, tub);
   bool p1 = le && slab_test_f32_maybe(c1a, c1b, rf, nx, ny, nz, tub);
   bool p2 = slab_test_f32_maybe(c2a, c2b, rf, nx, ny, nz, tub);
   bool p3 = re && slab_test_f32_maybe(c3a, c3b, rf, nx, ny, nz, tub);
-  const int ax0 = cur_b & 3, ax1 = (cur_b >> 2) & 3, ax2 = (cur_b >> 4) & 3;
+  const int ax0 = (cur >> 1) & 3, ax1 = (cur >> 5) & 3, ax2 = (cur >> 3) & 3;
   const bool n0 = (ax0 == 0 ? nx : (ax0 == 1 ? ny : nz)) != 0;
   const bool n1 = (ax1 == 0 ? nx : (ax1 == 1 ? ny : nz)) != 0;
   const bool n2 = (ax2 == 0 ? nx : (ax2 == 1 ? ny : nz)) != 0;
-  unsigned a0 = __float_as_uint(c0a.w), b0 = __float_as_uint(c0b.w), a1 = __float_as_uint(c1a.w), b1 = __float_as_uint(c1b.w);
-  unsigned a2 = __float_as_uint(c2a.w), b2 = __float_as_uint(c2b.w), a3 = __float_as_uint(c3a.w), b3 = __float_as_uint(c3b.w);
   // left side in visit order (lf first, ls second), right side likewise
-  unsigned lfa = n1 ? a1 : a0, lfb = n1 ? b1 : b0, lsa = n1 ? a0 : a1, lsb = n1 ? b0 : b1;
+  unsigned lf = n1 ? w1 : w0, ls = n1 ? w0 : w1;
   bool plf = n1 ? p1 : p0, pls = n1 ? p0 : p1;
-  unsigned rfa = n2 ? a3 : a2, rfb = n2 ? b3 : b2, rsa = n2 ? a2 : a3, rsb = n2 ? b2 : b3;
+  unsigned rf_ = n2 ? w3 : w2, rs = n2 ? w2 : w3;
   bool prf = n2 ? p3 : p2, prs = n2 ? p2 : p3;
   // o0..o3: the four children in visit order
-  unsigned o0a = n0 ? rfa : lfa, o0b = n0 ? rfb : lfb, o1a = n0 ? rsa : lsa, o1b = n0 ? rsb : lsb;
-  unsigned o2a = n0 ? lfa : rfa, o2b = n0 ? lfb : rfb, o3a = n0 ? lsa : rsa, o3b = n0 ? lsb : rsb;
+  unsigned o0 = n0 ? rf_ : lf, o1 = n0 ? rs : ls, o2 = n0 ? lf : rf_, o3 = n0 ? ls : rs;
   bool q0 = n0 ? prf : plf, q1 = n0 ? prs : pls, q2 = n0 ? plf : prf, q3 = n0 ? pls : prs;
-  if (sp + 3 > stack_cap) { ovf = 1; have_cur = false; sp = 0; return 2 + (le ? 1 : 0) + (re ? 1 : 0); }
-  if (q3) { stack[(2 * sp) * stride] = o3a; stack[(2 * sp + 1) * stride] = o3b; ++sp; }
-  if (q2) { stack[(2 * sp) * stride] = o2a; stack[(2 * sp + 1) * stride] = o2b; ++sp; }
-  if (q1) { stack[(2 * sp) * stride] = o1a; stack[(2 * sp + 1) * stride] = o1b; ++sp; }
-  if (q0) { cur_a = o0a; cur_b = o0b; }
-  else if (sp > 0) { --sp; cur_a = stack[(2 * sp) * stride]; cur_b = stack[(2 * sp + 1) * stride]; }
+  const int tested = 2 + (le ? 1 : 0) + (re ? 1 : 0);
+  if (sp + 3 > stack_cap) { ovf = 1; have_cur = false; sp = 0; return tested; }
+  if (q3) { stack[sp * stride] = o3; ++sp; }
+  if (q2) { stack[sp * stride] = o2; ++sp; }
+  if (q1) { stack[sp * stride] = o1; ++sp; }
+  if (q0) cur = o0;
+  else if (sp > 0) { --sp; cur = stack[sp * stride]; }
   else have_cur = false;
-  return 2 + (le ? 1 : 0) + (re ? 1 : 0);
+  return tested;
 }
 
 // Persistent warps with dynamic ray replacement ("while-while" traversal):
@@ -140,17 +150,22 @@ GP_D int quad_step(const DevScene& sc, unsigned& cur_a, unsigned& cur_b, bool& h
 //            set (render loop) it also receives, per QUEUE POSITION, the hit's shade class or 4 for a miss (k_split_hits).
 // ANY=true : occluded[lane] = 1/0.
 // queue == nullptr: ray i is lane i (batched API); otherwise lane = queue[i] for i < *count.
-// dynamic shared memory: stack_cap * blockDim.x unsigned, [entry][thread] (bank-conflict free).
+// dynamic shared memory: stack_cap * blockDim.x unsigned (one word per stacked node), [entry][thread] (bank-conflict free).
 // MODE 0: closest hit over RayRec.  MODE 1: any hit over RayRec, occluded[lane] = 1/0 (batched API).
 // MODE 3: any hit over ShadowRec segments (queue entries index srays and occluded directly), occluded[e] = 1/0:
 //         DirectLighting / UniformSampleAll, whose per-light segments are summed in light order by the shade stage.
 // MODE 2: any hit over the render's ShadowRec queue, resolved in place: an unoccluded segment adds its deferred light
 //         sample to the lane's radiance (L.AddAssign(Ld), path.go:86).
+// QUADRICS = false: the scene holds triangles only (BASELINE configs 4 and 5) — the kernel carries no sphere / disk test,
+//         no parked-candidate state and no EFloat code, which is what sets the register budget of the general variant.
 #ifndef GP_TRACE_BLOCKS
 #define GP_TRACE_BLOCKS 4
 #endif
-template <int MODE, bool COUNT>
-__global__ void __launch_bounds__(kTraceThreads, GP_TRACE_BLOCKS) k_trace(DevScene sc, RayRec* __restrict__ rays, const ShadowRec* __restrict__ srays,
+#ifndef GP_TRACE_BLOCKS_TRI
+#define GP_TRACE_BLOCKS_TRI 5
+#endif
+template <int MODE, bool COUNT, bool QUADRICS>
+__global__ void __launch_bounds__(kTraceThreads, QUADRICS ? GP_TRACE_BLOCKS : GP_TRACE_BLOCKS_TRI) k_trace(DevScene sc, RayRec* __restrict__ rays, const ShadowRec* __restrict__ srays,
                                                             PathRec* __restrict__ paths, unsigned char* __restrict__ occluded,
                                                             const int* __restrict__ queue, const int* __restrict__ count, long long n_direct,
                                                             int stack_cap, int* work_counter, TraceCounters* ctr, unsigned long long* gt10_counter) {
@@ -174,9 +189,9 @@ __global__ void __launch_bounds__(kTraceThreads, GP_TRACE_BLOCKS) k_trace(DevSce
   Ray ray;
   V3 invd;
   int nx = 0, ny = 0, nz = 0, sp = 0, rec = -1, pending = -1, rec_cls = 0;
-  unsigned cur_a = 0, cur_b = 0, leaf_a = 0, leaf_n = 0, leaf_i = 0;
-  unsigned leaf2_a = 0, leaf2_n = 0;  // a second leaf, found while other lanes of the warp were still looking for their first
-  bool have_cur = false;  // (cur_a, cur_b) = record words of a node whose box has already passed
+  unsigned cur = 0, leaf_a = 0, leaf_n = 0, leaf_i = 0;
+  unsigned leaf2 = 0;  // word of a second leaf, found while other lanes of the warp were still looking for their first (0 = none)
+  bool have_cur = false;  // cur = word of a node whose box has already passed
   TriRay tray;
   tray.kx = tray.ky = tray.kz = 0; tray.Sx = tray.Sy = tray.Sz = 0;
   RayF32 rf;
@@ -227,13 +242,13 @@ __global__ void __launch_bounds__(kTraceThreads, GP_TRACE_BLOCKS) k_trace(DevSce
           t_best = ray.tmax;
           sp = 0; rec = -1; hit_any = false; pending = -1; leaf_n = 0; leaf_i = 0;
           have_cur = false;
-          leaf2_n = 0;
+          leaf2 = 0;
           // r.TMax <= 0 (or NaN): no shape test can return a hit (every one of them rejects t <= 0 and t >= tMax) and the
           // reference's root test already fails tMin < r.TMax unless the origin is inside — the ray is a miss without traversal
           if (sc.n_nodes > 0 && ray.tmax > 0) {  // the root's own box (bvh.go:673-675)
             float4 r0 = __ldg(sc.nodes), r1 = __ldg(sc.nodes + 1);
             if (COUNT) c.nodes++;
-            if (slab_test_f32_maybe(r0, r1, rf, nx, ny, nz, tmax_ub)) { cur_a = __float_as_uint(r0.w); cur_b = __float_as_uint(r1.w); have_cur = true; }
+            if (slab_test_f32_maybe(r0, r1, rf, nx, ny, nz, tmax_ub)) { cur = __float_as_uint(r0.w); have_cur = true; }
           }
           has_ray = true;
         }
@@ -255,7 +270,7 @@ __global__ void __launch_bounds__(kTraceThreads, GP_TRACE_BLOCKS) k_trace(DevSce
       const bool in_leaf = leaf_i < leaf_n || pending >= 0;
       if (!in_leaf) {
         leaf_i = 0;
-        if (leaf2_n) { leaf_a = leaf2_a; leaf_n = leaf2_n; leaf2_n = 0; }  // (left over when a parked sphere/disk test cut phase 2 short)
+        if (leaf2) { leaf_a = leaf_first(leaf2); leaf_n = leaf_count(leaf2); leaf2 = 0; }  // (left over when a parked sphere/disk test cut phase 2 short)
         else leaf_n = 0;
       }
       for (int step = 0; step < kDescendSteps; step++) {
@@ -264,16 +279,15 @@ __global__ void __launch_bounds__(kTraceThreads, GP_TRACE_BLOCKS) k_trace(DevSce
 #ifdef GP_NO_SPEC
         if (looking) {
 #else
-        if (has_ray && !in_leaf && have_cur && leaf2_n == 0) {
+        if (has_ray && !in_leaf && have_cur && leaf2 == 0) {
 #endif
-          unsigned np = cur_b >> 8;
-          if (np > 0) {  // a leaf: keep it for phase 2, continue from the stack
-            if (leaf_n == 0) { leaf_a = cur_a; leaf_n = np; }
-            else { leaf2_a = cur_a; leaf2_n = np; }
-            if (sp > 0) { --sp; cur_a = stack[(2 * sp) * stride]; cur_b = stack[(2 * sp + 1) * stride]; }
+          if (word_is_leaf(cur)) {  // a leaf: keep it for phase 2, continue from the stack
+            if (leaf_n == 0) { leaf_a = leaf_first(cur); leaf_n = leaf_count(cur); }
+            else leaf2 = cur;
+            if (sp > 0) { --sp; cur = stack[sp * stride]; }
             else have_cur = false;
           } else {
-            int tested = quad_step(sc, cur_a, cur_b, have_cur, sp, stack, stride, stack_cap, rf, nx, ny, nz, tmax_ub, ovf);
+            int tested = quad_step(sc, cur, have_cur, sp, stack, stride, stack_cap, rf, nx, ny, nz, tmax_ub, ovf);
             if (COUNT) c.nodes += tested;
           }
         }
@@ -282,16 +296,16 @@ __global__ void __launch_bounds__(kTraceThreads, GP_TRACE_BLOCKS) k_trace(DevSce
     // ---- phase 2: the leaf's candidates in order; triangles are tested here, a sphere/disk candidate is parked in
     //      `pending` (the lane stops at it, so the per-ray test order and running tMax stay the reference's)
     for (;;) {
-      if (pending >= 0) break;
+      if (QUADRICS && pending >= 0) break;
       if (leaf_i >= leaf_n) {
-        if (leaf2_n == 0) break;
-        leaf_a = leaf2_a; leaf_n = leaf2_n; leaf_i = 0; leaf2_n = 0;
+        if (leaf2 == 0) break;
+        leaf_a = leaf_first(leaf2); leaf_n = leaf_count(leaf2); leaf_i = 0; leaf2 = 0;
       }
       unsigned ri = leaf_a + leaf_i;
       leaf_i++;
       const PrimRec* prec = sc.recs + ri;
       uint32_t flags = prec->flags;
-      if ((flags & RK_KIND_MASK) == RK_TRIANGLE) {
+      if (!QUADRICS || (flags & RK_KIND_MASK) == RK_TRIANGLE) {
         // own float64 world bound = min/max of the (finite) vertices: a compare-select equals Go's Min/Max up to the
         // sign of a zero, which the slab test cannot observe
         const double2* q = (const double2*)prec;
@@ -304,7 +318,7 @@ __global__ void __launch_bounds__(kTraceThreads, GP_TRACE_BLOCKS) k_trace(DevSce
         if (COUNT) { c.prims++; c.tri++; }
         double t;
         if (tri_test_pre(p0, p1, p2, ray, tray, &t, nullptr)) {
-          if (ANY) { hit_any = true; have_cur = false; leaf_i = leaf_n; leaf2_n = 0; break; }
+          if (ANY) { hit_any = true; have_cur = false; leaf_i = leaf_n; leaf2 = 0; break; }
           if (closer_hit(sc, t, ri, t_best, rec)) {
             hit_any = true;
             t_best = t;
@@ -321,15 +335,15 @@ __global__ void __launch_bounds__(kTraceThreads, GP_TRACE_BLOCKS) k_trace(DevSce
       }
     }
     // ---- phase 3: the parked sphere/disk tests, run together once enough lanes hold one or nobody else can advance
-    {
+    if (QUADRICS) {
       unsigned pm = __ballot_sync(FULL, pending >= 0);
-      unsigned runnable = __ballot_sync(FULL, has_ray && pending < 0 && !(!have_cur && leaf_i >= leaf_n && leaf2_n == 0));
+      unsigned runnable = __ballot_sync(FULL, has_ray && pending < 0 && !(!have_cur && leaf_i >= leaf_n && leaf2 == 0));
       if (pm != 0 && (__popc(pm) >= kQuadricBatch || runnable == 0)) {
         if (pending >= 0) {
           const PrimRec* prec = sc.recs + pending;
           double t;
           if (quadric_test(sc, prec, prec->flags, ray, &t, bad)) {
-            if (ANY) { hit_any = true; have_cur = false; leaf_i = leaf_n; leaf2_n = 0; }
+            if (ANY) { hit_any = true; have_cur = false; leaf_i = leaf_n; leaf2 = 0; }
             else if (closer_hit(sc, t, (unsigned)pending, t_best, rec)) {
               hit_any = true;
               t_best = t;
@@ -343,7 +357,7 @@ __global__ void __launch_bounds__(kTraceThreads, GP_TRACE_BLOCKS) k_trace(DevSce
       }
     }
     // ---- retire finished rays
-    bool retire = has_ray && !have_cur && leaf_i >= leaf_n && leaf2_n == 0 && pending < 0;
+    bool retire = has_ray && !have_cur && leaf_i >= leaf_n && leaf2 == 0 && pending < 0;
     if (retire) {
       if (MODE == 0) {
         double2 out;

@@ -26,33 +26,26 @@ struct Walk {
     if (depth > max_depth) max_depth = depth;
     Box acc;
     box_init(acc);
-    unsigned np = n.b >> 8;
-    if (np > 0) {
-      if ((int)np > max_prims) {  // only a cluster of coincident (float32) centroids may stay one oversized leaf
-        auto cen = [&](size_t r, int k) { const Box& x = b[order[r]]; return (float)(0.5 * x.mn[k] + 0.5 * x.mx[k]); };
-        bool spread = false;
-        for (int k = 0; k < 3; k++) {
-          float lo = cen(n.a, k), hi = lo;
-          for (unsigned q = 1; q < np; q++) { float c = cen((size_t)n.a + q, k); lo = std::min(lo, c); hi = std::max(hi, c); }
-          int widest = n.b & 3;
-          if (k == widest && hi > lo) spread = true;
-        }
-        if (spread) errors++;
-      }
+    const bool leaf = (n.a & 1u) != 0 && n.a != kEmptyWord;
+    if (leaf) {
+      unsigned np = ((n.a >> 1) & 3u) + 1u, first = n.a >> 3;
+      if ((int)np > max_prims || np != n.b) errors++;  // a leaf never exceeds maxPrims (coincident centroids are halved by index)
       for (unsigned k = 0; k < np; k++) {
-        size_t r = (size_t)n.a + k;
+        size_t r = (size_t)first + k;
         if (r >= order.size()) { errors++; continue; }
         seen[order[r]]++;
         box_add(acc, b[order[r]]);
       }
     } else {
-      size_t g = n.a;
-      if (g % 4 != 0 || g + 3 >= nodes.size() || g == 0) { errors++; return acc; }
-      bool le = (n.b & 64u) != 0, re = (n.b & 128u) != 0;
-      bool valid[4] = {true, le, true, re};
-      for (int k = 0; k < 4; k++)
-        if (valid[k]) box_add(acc, visit(g + k, depth + 1));
-        else if (!(nodes[g + k].mn[0] > nodes[g + k].mx[0])) errors++;  // an unused slot must hold the empty box
+      if (n.a == kEmptyWord) { errors++; return acc; }
+      size_t g = 4 * (size_t)(n.a >> 7);
+      if (g + 3 >= nodes.size() || g == 0) { errors++; return acc; }
+      for (int k = 0; k < 4; k++) {
+        const Node32& c = nodes[g + k];
+        if (c.a != kEmptyWord) box_add(acc, visit(g + k, depth + 1));
+        else if (!(c.mn[0] > c.mx[0]) || (k != 1 && k != 3)) errors++;  // only slots 1 and 3 may be unused, and they hold the empty box
+      }
+      for (int k = 0; k < 3; k++) if (((n.a >> (1 + 2 * k)) & 3u) > 2u) errors++;  // split axes
     }
     for (int k = 0; k < 3; k++)
       if (!((double)n.mn[k] <= acc.mn[k] && (double)n.mx[k] >= acc.mx[k])) errors++;
@@ -94,7 +87,7 @@ int main() {
   int bad = 0;
   size_t sizes[] = {0, 1, 2, 3, 5, 17, 100, 1000, 30000, 250000};  // the last one takes the threaded path
   for (size_t n : sizes)
-    for (int mp : {1, 2, 4}) {
+    for (int mp : {1, 2, 4}) {  // (maxPrims above kMaxLeafPrims = 4 is clamped by the builder)
       bad += check(n, mp, 7 + (unsigned)n, false);
       if (n >= 17 && n <= 30000) bad += check(n, mp, 11 + (unsigned)n, true);
     }
