@@ -842,13 +842,16 @@ static int render_impl(gopbrt_scene* sc, const gopbrt_camera* cam, const gopbrt_
   // frame — hundreds of wavefront iterations whose tail runs nearly empty — into many short ones, paid for with lane
   // state in HBM.  Bits 8..15 of the flags choose the group count; 0 = automatic.
   P.groups = 1;
+  const long long tiles_rank = (P.ntiles - P.rank + P.world - 1) / P.world;
+  bool auto_groups = false;
   if (P.mode == GOPBRT_MODE_FAST) {
     int want = (flags >> 8) & 0xff;
     int share = (P.spp - 1 + P.s_world - 1) / P.s_world;  // samples 1..spp-1 of every pixel, split over the ranks
-    if (want == 0) want = std::max(1, std::min(8, (share + 3) / 4));  // about 4-8 samples per lane
+    // automatic: two samples per lane (measured on one B200, config 2 / 63 spp: 8 samples per lane 186 ms, 4: 167 ms, 2: 149 ms,
+    // 1: 148 ms — the last halving doubles the lane state for 1 %), bounded below by the lane-state budget
+    if (want == 0) { want = std::max(1, std::min(64, (share + 1) / 2)); auto_groups = true; }
     P.groups = std::max(1, std::min(want, std::max(1, share)));
   }
-  long long lanes_total = ((P.ntiles - P.rank + P.world - 1) / P.world) * P.groups;
 
   // GOPBRT_HOST_TIMING=1: host wall-clock of the call's phases on stderr (tuning aid)
   const bool host_timing = getenv("GOPBRT_HOST_TIMING") != nullptr;
@@ -873,8 +876,16 @@ static int render_impl(gopbrt_scene* sc, const gopbrt_camera* cam, const gopbrt_
   GP_CUDA(ctx, cudaMemGetInfo(&free_b, &total_b));
   Workspace& W = sc->ws;
   size_t held = W.lanes ? (size_t)W.lanes * per_lane : 0;
-  long long cap = (long long)(((double)(free_b + held) * 0.80) / (double)per_lane);
+  // Lane state of ONE scene handle: at most 40 % of the device's memory (GOPBRT_LANE_BUDGET_GB overrides) and 80 % of what is
+  // free right now — several scenes render on one context (one per gRPC request in the reference) and must not starve each other.
+  double budget = 0.40 * (double)total_b;
+  if (const char* e = getenv("GOPBRT_LANE_BUDGET_GB")) budget = std::max(0.25, atof(e)) * 1e9;
+  budget = std::min(budget, (double)(free_b + held) * 0.80);
+  long long cap = (long long)(budget / (double)per_lane);
   if (opt && opt->max_lanes > 0) cap = std::min<long long>(cap, opt->max_lanes);
+  // automatic lane groups shrink until one pass holds every lane (more passes would serialise what the groups parallelise)
+  if (auto_groups && tiles_rank * P.groups > cap) P.groups = (int)std::max<long long>(1, std::min<long long>(P.groups, cap / std::max<long long>(1, tiles_rank)));
+  long long lanes_total = tiles_rank * P.groups;
   long long lanes = std::max<long long>(1, std::min(lanes_total, cap));
   if (lanes * (long long)n_seg > 0x7fffff00LL) lanes = 0x7fffff00LL / (long long)n_seg;
   size_t bt = table_doubles * lanes, bp = P.uniform_fp ? 0 : (size_t)tpw * tph * 4 * lanes;

@@ -65,3 +65,22 @@ def test_scene_desc_flattening(gp):
     scene2, _ = gp.scenes.config2(W=64, H=36)
     d2 = scene2.desc()
     assert d2.n_triangles == 34 and d2.n_primitives == 36 and d2.n_vertices == 68
+
+
+def _build_abi_smoke(tmpdir):
+    """tests/cpp/abi_smoke.c: plain C99 against the header and the built library (what a cgo / FFI binding compiles to)"""
+    import subprocess
+    exe = os.path.join(str(tmpdir), "abi_smoke")
+    csrc = os.path.join(ROOT, "go-pbrt_b200", "csrc")
+    subprocess.check_call(["gcc", "-std=c99", "-pedantic", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"), "-o", exe,
+                           os.path.join(ROOT, "tests", "cpp", "abi_smoke.c"), "-L", csrc, "-lgopbrt_cuda", "-lm", f"-Wl,-rpath,{csrc}"])
+    return exe
+
+
+def test_plain_c_caller_compiles_links_and_refuses_to_run_without_a_gpu(gp, tmp_path):
+    import subprocess
+    gp.abi.load()
+    exe = _build_abi_smoke(tmp_path)
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    # on the CPU box gopbrt_init must fail (no fallback) and the program says so; on a GPU box the whole smoke passes
+    assert (out.returncode == 2 and "no CPU fallback" in out.stdout) or (out.returncode == 0 and "abi_smoke: ok" in out.stdout), out.stdout[-2000:]

@@ -85,3 +85,12 @@ def test_multi_n_devices_sum_to_the_single_gpu_film(gp, dev, mode):
         assert mst["ms_reduce"] > 0
     mg.close()
     m.close()
+
+
+def test_plain_c_caller_runs_the_whole_boundary(gp, tmp_path):
+    # tests/cpp/abi_smoke.c: scene_create -> trace_closest / trace_any -> render -> cancel semantics -> gopbrt_multi_* from C99
+    import subprocess
+    from test_abi import _build_abi_smoke
+    gp.abi.load()
+    out = subprocess.run([_build_abi_smoke(tmp_path)], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "abi_smoke: ok" in out.stdout, out.stdout[-3000:]
