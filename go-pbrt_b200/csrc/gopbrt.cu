@@ -305,6 +305,15 @@ static int build_host_scene(const gopbrt_scene_desc* d, HostScene& H, std::strin
   std::vector<LightDev>& lights = H.lights;
   std::vector<double>& cdf = H.cdf;
   if (d->n_primitives < 0 || d->n_primitives > 0x7fffffff) return bad("n_primitives out of range");
+  // GOPBRT_HOST_TIMING=1: host wall-clock of the build's phases on stderr (tuning aid)
+  const bool host_timing = getenv("GOPBRT_HOST_TIMING") != nullptr;
+  auto hw0 = std::chrono::steady_clock::now();
+  auto hw_tick = [&](const char* what) {
+    if (!host_timing) return;
+    auto now = std::chrono::steady_clock::now();
+    fprintf(stderr, "[gopbrt scene] %-22s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(now - hw0).count());
+    hw0 = now;
+  };
 
   // ---- transforms
   xf.assign(32 * (size_t)d->n_transforms, 0.0);
@@ -397,6 +406,7 @@ static int build_host_scene(const gopbrt_scene_desc* d, HostScene& H, std::strin
     }
   }
 
+  hw_tick("tables + prim bounds");
   // ---- BVH
   // maxPrimsInNode (bvh.go:223-231) is an UPPER bound on a leaf; the tree is this backend's own, and every candidate of a
   // leaf costs a record fetch plus a float64 bound test per ray, so leaves hold at most two primitives (measured on
@@ -408,6 +418,7 @@ static int build_host_scene(const gopbrt_scene_desc* d, HostScene& H, std::strin
   bvh = gpbvh::build_bvh(pb.data(), np, max_prims);
   if ((int64_t)bvh.order.size() != np || (np > 0 && bvh.nodes.empty())) return bad("BVH build failed (out of host memory, or more primitives / nodes than a node word addresses)");
   if (bvh.depth >= kStackDepth - 1) return bad("BVH deeper than the traversal stack");
+  hw_tick("bvh build + flatten");
 
   // ---- leaf-ordered primitive records + their float64 bounds
   recs.resize(np);
@@ -454,6 +465,7 @@ static int build_host_scene(const gopbrt_scene_desc* d, HostScene& H, std::strin
   }
   });
 
+  hw_tick("leaf-ordered records");
   // ---- flat aggregate (scenes of at most kFlatMax primitives): one table entry per leaf-ordered record, triangles first
   flat.clear();
   flat_tri_mask = 0;
@@ -536,6 +548,7 @@ static int upload_scene(gopbrt_ctx* ctx, HostScene& H, gopbrt_scene** out) {
   sc->ctx = ctx;
   cudaStream_t st = ctx->stream;
   std::vector<gpbvh::Node32>& nodes = bvh.nodes;
+  auto up0 = std::chrono::steady_clock::now();
   bool ok = sc->nodes.upload(nodes, st) == cudaSuccess && sc->flat.upload(flat, st) == cudaSuccess && sc->recs.upload(recs, st) == cudaSuccess &&
             sc->rec_bounds.upload(rec_bounds, st) == cudaSuccess && sc->prims.upload(prims, st) == cudaSuccess &&
             sc->xf.upload(xf, st) == cudaSuccess && sc->xf_flags.upload(xf_flags, st) == cudaSuccess &&
@@ -545,6 +558,8 @@ static int upload_scene(gopbrt_ctx* ctx, HostScene& H, gopbrt_scene** out) {
             sc->tctr.alloc(1) == cudaSuccess && cudaMemsetAsync(sc->tctr.p, 0, sizeof(TraceCounters), st) == cudaSuccess &&
             sc->work.alloc(2) == cudaSuccess && cudaMemsetAsync(sc->work.p, 0, 2 * sizeof(int), st) == cudaSuccess &&
             cudaStreamSynchronize(st) == cudaSuccess;
+  if (getenv("GOPBRT_HOST_TIMING"))
+    fprintf(stderr, "[gopbrt scene] %-22s %8.3f ms\n", "upload", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - up0).count());
   if (!ok) {
     ctx->last_error = std::string("scene upload: ") + cudaGetErrorString(cudaGetLastError());
     delete sc;

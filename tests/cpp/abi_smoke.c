@@ -117,8 +117,14 @@ int main(void) {
   CHECK(st.closest_rays >= st.camera_rays && st.shadow_rays > 0 && st.launches > 0, "ray counters");
   {
     int bad_w = 0, lit = 0;
+    /* unjittered Stratified leaves every pFilm on its pixel's integer corner (the 2-D tables are never written, sampling.go:112-127),
+       so with the box filter of radius 0.5 a sample weighs 1 in the 2 x 2 pixels around that corner (film.go:211-248): an interior
+       pixel collects 4 * (spp - 1) — its own corner's samples and its right / lower neighbours' —, a pixel of the last column or
+       row 2 *, the last pixel 1 * */
     for (i = 0; i < W * H; i++) {
-      if (px[4 * i + 3] != (double)(XS * YS - 1)) bad_w++;  /* box filter, radius 0.5: every sample weighs 1 in exactly one pixel */
+      int x = i % W, y = i / W;
+      double want = (double)(XS * YS - 1) * (x == W - 1 ? 1 : 2) * (y == H - 1 ? 1 : 2);
+      if (px[4 * i + 3] != want) bad_w++;
       if (px[4 * i + 1] > 0) lit++;
       if (!(px[4 * i] >= 0 && px[4 * i + 1] >= 0 && px[4 * i + 2] >= 0)) bad_w++;
     }
