@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -16,6 +17,7 @@
 #include "gp_bvh.h"
 #include "gp_comm.h"
 #include "gp_render.cuh"
+#include "gp_build.cuh"
 #include "gp_kat.cuh"
 
 using namespace gp;
@@ -285,6 +287,16 @@ struct HostScene {
   std::vector<double> cdf;
   double func_int = 0;
   int nl = 0;
+  // Device build (gp_build.cuh): the BVH, the child groups and the leaf-ordered records are made on the GPU from the caller's
+  // own arrays (valid for the duration of the create call).  The host only prepares what needs the reference's arithmetic:
+  // bounds and records of spheres / disks (compact lists addressed through qslot), and the per-material shade class.
+  bool device_build = false;
+  const gopbrt_scene_desc* desc = nullptr;
+  std::vector<int> qslot;
+  std::vector<PrimRec> qrecs;
+  std::vector<double> qbounds;
+  std::vector<unsigned char> mat_not_lambert;
+  int max_prims = 2;
 };
 
 static int build_host_scene(const gopbrt_scene_desc* d, HostScene& H, std::string& error) {
@@ -357,75 +369,41 @@ static int build_host_scene(const gopbrt_scene_desc* d, HostScene& H, std::strin
 
   // ---- primitives: world bounds (Primitive.WorldBound) in the reference's arithmetic
   int64_t np = d->n_primitives;
-  prims.resize(np);
-  std::vector<gpbvh::Box> pb(np);
-  {
-    std::vector<HB> part(64);
-    std::vector<const char*> err(64, nullptr);
-    int n_chunks = 1;
-    parallel_chunks(np, [&](int64_t i0, int64_t i1, int chunk) {
-      HB& wpart = part[chunk];
-      auto bad = [&](const char* msg) { err[chunk] = msg; return; };
-      for (int64_t i = i0; i < i1; i++) {
-        const gopbrt_primitive& p = d->primitives[i];
-        prims[i] = make_int4(p.shape_kind, p.shape_index, p.material, p.prim_to_world);
-        if (p.material >= d->n_materials) return bad("material index out of range");
-        if (p.prim_to_world >= d->n_transforms) return bad("prim_to_world index out of range");
-        HB b;
-        if (p.shape_kind == GOPBRT_SHAPE_SPHERE) {
-          if (p.shape_index < 0 || p.shape_index >= d->n_spheres) return bad("sphere index out of range");
-          const SphereDev& s = spheres[p.shape_index];
-          HB ob; ob.valid = true;
-          ob.mn[0] = -s.radius; ob.mn[1] = -s.radius; ob.mn[2] = s.zMin; ob.mx[0] = s.radius; ob.mx[1] = s.radius; ob.mx[2] = s.zMax;  // sphere.go:46-51
-          b = xf_bounds(m4_from(&xf[32 * (size_t)s.xf]), ob);
-        } else if (p.shape_kind == GOPBRT_SHAPE_DISK) {
-          if (p.shape_index < 0 || p.shape_index >= d->n_disks) return bad("disk index out of range");
-          const DiskDev& s = disks[p.shape_index];
-          HB ob; ob.valid = true;
-          ob.mn[0] = -s.radius; ob.mn[1] = -s.radius; ob.mn[2] = s.height; ob.mx[0] = s.radius; ob.mx[1] = s.radius; ob.mx[2] = s.height;  // disk.go:41-54
-          b = xf_bounds(m4_from(&xf[32 * (size_t)s.xf]), ob);
-        } else if (p.shape_kind == GOPBRT_SHAPE_TRIANGLE) {
-          if (p.shape_index < 0 || p.shape_index >= d->n_triangles) return bad("triangle index out of range");
-          const gopbrt_triangle& t = d->triangles[p.shape_index];
-          for (int k = 0; k < 3; k++) {
-            if (t.v[k] < 0 || t.v[k] >= d->n_vertices) return bad("vertex index out of range");
-            hb_union_point(b, mk3(d->vertices[3 * (size_t)t.v[k]], d->vertices[3 * (size_t)t.v[k] + 1], d->vertices[3 * (size_t)t.v[k] + 2]));
-          }
-          if (p.prim_to_world >= 0) return bad("TransformedPrimitive around a triangle is not supported");
-        } else {
-          return bad("unknown shape kind");
-        }
-        if (p.prim_to_world >= 0) b = xf_bounds(m4_from(&xf[32 * (size_t)p.prim_to_world]), b);  // primitive.go:127-129
-        for (int k = 0; k < 3; k++) { pb[i].mn[k] = b.mn[k]; pb[i].mx[k] = b.mx[k]; }
-        hb_union(wpart, b);
+  H.desc = d;
+  H.device_build = np > kFlatMax && !getenv("GOPBRT_HOST_BVH");
+  // validates primitive i and returns its float64 world bound; nullptr on success, else the error text
+  auto prim_bound = [&](int64_t i, HB& b) -> const char* {
+    const gopbrt_primitive& p = d->primitives[i];
+    if (p.material >= d->n_materials) return "material index out of range";
+    if (p.prim_to_world >= d->n_transforms) return "prim_to_world index out of range";
+    if (p.shape_kind == GOPBRT_SHAPE_SPHERE) {
+      if (p.shape_index < 0 || p.shape_index >= d->n_spheres) return "sphere index out of range";
+      const SphereDev& s = spheres[p.shape_index];
+      HB ob; ob.valid = true;
+      ob.mn[0] = -s.radius; ob.mn[1] = -s.radius; ob.mn[2] = s.zMin; ob.mx[0] = s.radius; ob.mx[1] = s.radius; ob.mx[2] = s.zMax;  // sphere.go:46-51
+      b = xf_bounds(m4_from(&xf[32 * (size_t)s.xf]), ob);
+    } else if (p.shape_kind == GOPBRT_SHAPE_DISK) {
+      if (p.shape_index < 0 || p.shape_index >= d->n_disks) return "disk index out of range";
+      const DiskDev& s = disks[p.shape_index];
+      HB ob; ob.valid = true;
+      ob.mn[0] = -s.radius; ob.mn[1] = -s.radius; ob.mn[2] = s.height; ob.mx[0] = s.radius; ob.mx[1] = s.radius; ob.mx[2] = s.height;  // disk.go:41-54
+      b = xf_bounds(m4_from(&xf[32 * (size_t)s.xf]), ob);
+    } else if (p.shape_kind == GOPBRT_SHAPE_TRIANGLE) {
+      if (p.shape_index < 0 || p.shape_index >= d->n_triangles) return "triangle index out of range";
+      const gopbrt_triangle& t = d->triangles[p.shape_index];
+      for (int k = 0; k < 3; k++) {
+        if (t.v[k] < 0 || t.v[k] >= d->n_vertices) return "vertex index out of range";
+        hb_union_point(b, mk3(d->vertices[3 * (size_t)t.v[k]], d->vertices[3 * (size_t)t.v[k] + 1], d->vertices[3 * (size_t)t.v[k] + 2]));
       }
-    }, &n_chunks);
-    for (int c = 0; c < n_chunks; c++) {
-      if (err[c]) return bad(err[c]);
-      if (part[c].valid) hb_union(world, part[c]);  // chunks in index order: the same union sequence, merely bracketed
+      if (p.prim_to_world >= 0) return "TransformedPrimitive around a triangle is not supported";
+    } else {
+      return "unknown shape kind";
     }
-  }
-
-  hw_tick("tables + prim bounds");
-  // ---- BVH
-  // maxPrimsInNode (bvh.go:223-231) is an UPPER bound on a leaf; the tree is this backend's own, and every candidate of a
-  // leaf costs a record fetch plus a float64 bound test per ray, so leaves hold at most two primitives (measured on
-  // B200, FAST mode: config 2 frame 246 -> 225 ms, config 4 38.4 -> 36.3 ms against leaves of four; one per leaf is no
-  // better).  Results do not depend on the tree (SURVEY §8a).  GOPBRT_MAX_PRIMS overrides (tuning aid).
-  int max_prims = d->max_prims_in_node > 0 ? std::min(255, d->max_prims_in_node) : 4;
-  max_prims = std::min(max_prims, 2);
-  if (const char* mp = getenv("GOPBRT_MAX_PRIMS")) max_prims = std::max(1, std::min(255, atoi(mp)));
-  bvh = gpbvh::build_bvh(pb.data(), np, max_prims);
-  if ((int64_t)bvh.order.size() != np || (np > 0 && bvh.nodes.empty())) return bad("BVH build failed (out of host memory, or more primitives / nodes than a node word addresses)");
-  if (bvh.depth >= kStackDepth - 1) return bad("BVH deeper than the traversal stack");
-  hw_tick("bvh build + flatten");
-
-  // ---- leaf-ordered primitive records + their float64 bounds
-  recs.resize(np);
-  rec_bounds.resize(6 * (size_t)np);
-  parallel_chunks(np, [&](int64_t r0, int64_t r1, int) {
-  for (int64_t r = r0; r < r1; r++) {
-    uint32_t pi = bvh.order[r];
+    if (p.prim_to_world >= 0) b = xf_bounds(m4_from(&xf[32 * (size_t)p.prim_to_world]), b);  // primitive.go:127-129
+    return nullptr;
+  };
+  // the traversal record of primitive pi (leaf order is applied by the caller)
+  auto make_record = [&](uint32_t pi) -> PrimRec {
     const gopbrt_primitive& p = d->primitives[pi];
     PrimRec rec;
     memset(&rec, 0, sizeof(rec));
@@ -460,10 +438,92 @@ static int build_host_scene(const gopbrt_scene_desc* d, HostScene& H, std::strin
       if (!lambert) cls |= 1u;
       rec.flags |= cls << RF_CLASS_SHIFT;
     }
-    recs[r] = rec;
-    for (int k = 0; k < 3; k++) { rec_bounds[6 * (size_t)r + k] = pb[pi].mn[k]; rec_bounds[6 * (size_t)r + 3 + k] = pb[pi].mx[k]; }
+    return rec;
+  };
+  H.max_prims = d->max_prims_in_node > 0 ? std::min(255, d->max_prims_in_node) : 4;
+  H.max_prims = std::min(H.max_prims, 2);
+  if (const char* mp = getenv("GOPBRT_MAX_PRIMS")) H.max_prims = std::max(1, std::min(255, atoi(mp)));
+  if (H.device_build) {
+    // spheres / disks only: validated, bounded and given their records here; triangles are handled on the device
+    std::vector<int64_t> cnt(65, 0);
+    int n_chunks = 1;
+    parallel_chunks(np, [&](int64_t i0, int64_t i1, int chunk) {
+      int64_t c = 0;
+      for (int64_t i = i0; i < i1; i++) c += d->primitives[i].shape_kind != GOPBRT_SHAPE_TRIANGLE;
+      cnt[chunk + 1] = c;
+    }, &n_chunks);
+    for (int c = 0; c < n_chunks; c++) cnt[c + 1] += cnt[c];
+    const int64_t nq = cnt[n_chunks];
+    if (nq > 0) {
+      H.qslot.assign(np, -1);
+      H.qrecs.resize(nq);
+      H.qbounds.resize(6 * (size_t)nq);
+      std::vector<const char*> err(64, nullptr);
+      parallel_chunks(np, [&](int64_t i0, int64_t i1, int chunk) {
+        int64_t slot = cnt[chunk];
+        for (int64_t i = i0; i < i1; i++) {
+          if (d->primitives[i].shape_kind == GOPBRT_SHAPE_TRIANGLE) continue;
+          HB b;
+          if (const char* e = prim_bound(i, b)) { err[chunk] = e; return; }
+          H.qslot[i] = (int)slot;
+          for (int k = 0; k < 3; k++) { H.qbounds[6 * (size_t)slot + k] = b.mn[k]; H.qbounds[6 * (size_t)slot + 3 + k] = b.mx[k]; }
+          H.qrecs[slot] = make_record((uint32_t)i);
+          slot++;
+        }
+      });
+      for (int c = 0; c < n_chunks; c++) if (err[c]) return bad(err[c]);
+    }
+    H.mat_not_lambert.resize(std::max(1, d->n_materials));
+    for (int m = 0; m < d->n_materials; m++)
+      H.mat_not_lambert[m] = !(d->materials[m].kind == GOPBRT_MAT_MATTE && !(go_clamp(d->materials[m].sigma, 0, 90) != 0));
+    hw_tick("sphere/disk records");
   }
-  });
+  std::vector<gpbvh::Box> pb(H.device_build ? 0 : np);
+  if (!H.device_build) {
+    prims.resize(np);
+    std::vector<HB> part(64);
+    std::vector<const char*> err(64, nullptr);
+    int n_chunks = 1;
+    parallel_chunks(np, [&](int64_t i0, int64_t i1, int chunk) {
+      HB& wpart = part[chunk];
+      for (int64_t i = i0; i < i1; i++) {
+        const gopbrt_primitive& p = d->primitives[i];
+        prims[i] = make_int4(p.shape_kind, p.shape_index, p.material, p.prim_to_world);
+        HB b;
+        if (const char* e = prim_bound(i, b)) { err[chunk] = e; return; }
+        for (int k = 0; k < 3; k++) { pb[i].mn[k] = b.mn[k]; pb[i].mx[k] = b.mx[k]; }
+        hb_union(wpart, b);
+      }
+    }, &n_chunks);
+    for (int c = 0; c < n_chunks; c++) {
+      if (err[c]) return bad(err[c]);
+      if (part[c].valid) hb_union(world, part[c]);  // chunks in index order: the same union sequence, merely bracketed
+    }
+  }
+
+  hw_tick("tables + prim bounds");
+  // ---- BVH
+  // maxPrimsInNode (bvh.go:223-231) is an UPPER bound on a leaf; the tree is this backend's own, and every candidate of a
+  // leaf costs a record fetch plus a float64 bound test per ray, so leaves hold at most two primitives (measured on
+  // B200, FAST mode: config 2 frame 246 -> 225 ms, config 4 38.4 -> 36.3 ms against leaves of four; one per leaf is no
+  // better).  Results do not depend on the tree (SURVEY §8a).  GOPBRT_MAX_PRIMS overrides (tuning aid).
+  if (!H.device_build) {
+    bvh = gpbvh::build_bvh(pb.data(), np, H.max_prims);
+    if ((int64_t)bvh.order.size() != np || (np > 0 && bvh.nodes.empty())) return bad("BVH build failed (out of host memory, or more primitives / nodes than a node word addresses)");
+    if (bvh.depth >= kStackDepth - 1) return bad("BVH deeper than the traversal stack");
+    hw_tick("bvh build + flatten");
+
+    // ---- leaf-ordered primitive records + their float64 bounds
+    recs.resize(np);
+    rec_bounds.resize(6 * (size_t)np);
+    parallel_chunks(np, [&](int64_t r0, int64_t r1, int) {
+      for (int64_t r = r0; r < r1; r++) {
+        uint32_t pi = bvh.order[r];
+        recs[r] = make_record(pi);
+        for (int k = 0; k < 3; k++) { rec_bounds[6 * (size_t)r + k] = pb[pi].mn[k]; rec_bounds[6 * (size_t)r + 3 + k] = pb[pi].mx[k]; }
+      }
+    });
+  }
 
   hw_tick("leaf-ordered records");
   // ---- flat aggregate (scenes of at most kFlatMax primitives): one table entry per leaf-ordered record, triangles first
@@ -522,6 +582,65 @@ static int build_host_scene(const gopbrt_scene_desc* d, HostScene& H, std::strin
 }
 
 
+// GOPBRT_CHECK_BVH: walks a device-built tree on the host, the way the traversal kernels read it — every primitive in exactly
+// one leaf, leaves within maxPrims, every record's float32 box around the float64 bounds of everything below it.
+static bool check_device_bvh(const gopbrt_scene_desc* d, const HostScene& H, const gpbvh::Node32* d_nodes, size_t n_records,
+                             const std::vector<unsigned>& order, int max_prims, std::string& err) {
+  std::vector<gpbvh::Node32> nodes(n_records);
+  if (cudaMemcpy(nodes.data(), d_nodes, n_records * sizeof(gpbvh::Node32), cudaMemcpyDeviceToHost) != cudaSuccess) { err = "download failed"; return false; }
+  const size_t np = order.size();
+  std::vector<unsigned char> seen(np, 0);
+  auto bound = [&](unsigned pi, double* mn, double* mx) {
+    const gopbrt_primitive& p = d->primitives[pi];
+    if (p.shape_kind == GOPBRT_SHAPE_TRIANGLE) {
+      const gopbrt_triangle& t = d->triangles[p.shape_index];
+      for (int k = 0; k < 3; k++) { mn[k] = INFINITY; mx[k] = -INFINITY; }
+      for (int v = 0; v < 3; v++) for (int k = 0; k < 3; k++) { double c = d->vertices[3 * (size_t)t.v[v] + k]; mn[k] = std::min(mn[k], c); mx[k] = std::max(mx[k], c); }
+    } else {
+      const double* q = &H.qbounds[6 * (size_t)H.qslot[pi]];
+      for (int k = 0; k < 3; k++) { mn[k] = q[k]; mx[k] = q[3 + k]; }
+    }
+  };
+  long long errors = 0;
+  struct Range { double mn[3], mx[3]; };
+  std::function<Range(size_t, int)> visit = [&](size_t rec, int depth) -> Range {
+    Range acc;
+    for (int k = 0; k < 3; k++) { acc.mn[k] = INFINITY; acc.mx[k] = -INFINITY; }
+    if (rec >= nodes.size() || depth > 70) { errors++; return acc; }
+    const gpbvh::Node32& n = nodes[rec];
+    if (n.a == gpbvh::kEmptyWord) { errors++; return acc; }
+    if (n.a & 1u) {
+      unsigned cnt = ((n.a >> 1) & 3u) + 1u, first = n.a >> 3;
+      if ((int)cnt > max_prims) errors++;
+      for (unsigned k = 0; k < cnt; k++) {
+        size_t r = (size_t)first + k;
+        if (r >= np) { errors++; continue; }
+        unsigned pi = order[r];
+        if (pi >= np || seen[pi]) { errors++; continue; }
+        seen[pi] = 1;
+        double mn[3], mx[3];
+        bound(pi, mn, mx);
+        for (int q = 0; q < 3; q++) { acc.mn[q] = std::min(acc.mn[q], mn[q]); acc.mx[q] = std::max(acc.mx[q], mx[q]); }
+      }
+    } else {
+      size_t g = 4 * (size_t)(n.a >> 7);
+      if (g == 0 || g + 3 >= nodes.size()) { errors++; return acc; }
+      for (int k = 0; k < 4; k++) {
+        if (nodes[g + k].a == gpbvh::kEmptyWord) { if (k != 1 && k != 3) errors++; continue; }
+        Range c = visit(g + k, depth + 1);
+        for (int q = 0; q < 3; q++) { acc.mn[q] = std::min(acc.mn[q], c.mn[q]); acc.mx[q] = std::max(acc.mx[q], c.mx[q]); }
+      }
+    }
+    for (int q = 0; q < 3; q++) if (!((double)n.mn[q] <= acc.mn[q] && (double)n.mx[q] >= acc.mx[q])) errors++;
+    return acc;
+  };
+  visit(0, 0);
+  long long missing = 0;
+  for (size_t i = 0; i < np; i++) missing += !seen[i];
+  if (errors || missing) { err = std::to_string(errors) + " structural / box errors, " + std::to_string(missing) + " primitives not in any leaf"; return false; }
+  return true;
+}
+
 // uploads a host scene to the context's device and binds the traversal kernels
 static int upload_scene(gopbrt_ctx* ctx, HostScene& H, gopbrt_scene** out) {
   std::lock_guard<std::mutex> g(ctx->mu);
@@ -532,7 +651,7 @@ static int upload_scene(gopbrt_ctx* ctx, HostScene& H, gopbrt_scene** out) {
   std::vector<SphereDev>& spheres = H.spheres;
   std::vector<DiskDev>& disks = H.disks;
   std::vector<int4>& prims = H.prims;
-  HB& world = H.world;
+  HB world = H.world;  // (a copy: the device build fills it per device, and devices upload concurrently)
   gpbvh::Result& bvh = H.bvh;
   std::vector<PrimRec>& recs = H.recs;
   std::vector<double>& rec_bounds = H.rec_bounds;
@@ -549,8 +668,71 @@ static int upload_scene(gopbrt_ctx* ctx, HostScene& H, gopbrt_scene** out) {
   cudaStream_t st = ctx->stream;
   std::vector<gpbvh::Node32>& nodes = bvh.nodes;
   auto up0 = std::chrono::steady_clock::now();
-  bool ok = sc->nodes.upload(nodes, st) == cudaSuccess && sc->flat.upload(flat, st) == cudaSuccess && sc->recs.upload(recs, st) == cudaSuccess &&
-            sc->rec_bounds.upload(rec_bounds, st) == cudaSuccess && sc->prims.upload(prims, st) == cudaSuccess &&
+  const bool host_timing = getenv("GOPBRT_HOST_TIMING") != nullptr;
+  int dev_depth = 0;
+  size_t dev_records = 0;
+  bool quadrics = false;
+  if (H.device_build) {
+    // ---- the caller's arrays go up as they are; tree, child groups and leaf-ordered records are made on the device
+    const gopbrt_scene_desc* d = H.desc;
+    const long long np = d->n_primitives;
+    static_assert(sizeof(gopbrt_primitive) == sizeof(int4) && sizeof(gopbrt_triangle) == sizeof(int4), "descriptor tables are uploaded verbatim");
+    DevBuf<double> d_vertices, d_qbounds;
+    DevBuf<int4> d_triangles;
+    DevBuf<int> d_qslot;
+    DevBuf<PrimRec> d_qrecs;
+    DevBuf<unsigned char> d_mnl;
+    auto up = [&](void* dst, const void* src, size_t bytes) { return bytes == 0 || cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st) == cudaSuccess; };
+    quadrics = !H.qrecs.empty();
+    bool ok = sc->prims.alloc((size_t)np) == cudaSuccess && d_vertices.alloc(3 * (size_t)d->n_vertices) == cudaSuccess &&
+              d_triangles.alloc((size_t)d->n_triangles) == cudaSuccess && sc->recs.alloc((size_t)np) == cudaSuccess &&
+              sc->rec_bounds.alloc(quadrics ? 6 * (size_t)np : 0) == cudaSuccess && d_qslot.upload(H.qslot, st) == cudaSuccess &&
+              d_qrecs.upload(H.qrecs, st) == cudaSuccess && d_qbounds.upload(H.qbounds, st) == cudaSuccess && d_mnl.upload(H.mat_not_lambert, st) == cudaSuccess &&
+              up(sc->prims.p, d->primitives, (size_t)np * sizeof(int4)) && up(d_vertices.p, d->vertices, 3 * (size_t)d->n_vertices * sizeof(double)) &&
+              up(d_triangles.p, d->triangles, (size_t)d->n_triangles * sizeof(int4));
+    if (!ok) { ctx->last_error = std::string("scene upload: ") + cudaGetErrorString(cudaGetLastError()); delete sc; return GOPBRT_ERR_CUDA; }
+    if (host_timing) {
+      cudaStreamSynchronize(st);
+      fprintf(stderr, "[gopbrt scene] %-22s %8.3f ms\n", "upload (raw arrays)", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - up0).count());
+      up0 = std::chrono::steady_clock::now();
+    }
+    gpbuild::Input in;
+    in.prims = sc->prims.p; in.n = np;
+    in.vertices = d_vertices.p; in.n_vertices = d->n_vertices;
+    in.triangles = d_triangles.p; in.n_triangles = d->n_triangles;
+    in.qslot = d_qslot.p; in.qrecs = d_qrecs.p; in.qbounds = d_qbounds.p;
+    in.mat_not_lambert = d_mnl.p; in.n_materials = d->n_materials;
+    in.max_prims = H.max_prims;
+    gpbuild::Output bo;
+    bo.recs = sc->recs.p; bo.rec_bounds = sc->rec_bounds.p;
+    bo.keep_host = getenv("GOPBRT_CHECK_BVH") != nullptr;
+    std::string berr;
+    if (!gpbuild::build(in, bo, kStackDepth - 1, st, berr)) {
+      if (bo.nodes) cudaFree(bo.nodes);
+      ctx->last_error = berr;
+      delete sc;
+      cudaGetLastError();
+      return bo.cuda_error ? GOPBRT_ERR_CUDA : GOPBRT_ERR_INVALID;
+    }
+    ctx->launches += bo.launches;
+    sc->nodes.p = (gpbvh::Node32*)bo.nodes; sc->nodes.n = bo.n_records;
+    dev_depth = bo.depth; dev_records = bo.n_records;
+    sc->class_mask = bo.class_mask;
+    world.valid = bo.world_valid;
+    for (int k = 0; k < 3; k++) { world.mn[k] = bo.world[k]; world.mx[k] = bo.world[3 + k]; }
+    if (host_timing) {
+      fprintf(stderr, "[gopbrt scene] %-22s %8.3f ms (%zu records, depth %d, %llu launches)\n", "device build", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - up0).count(),
+              bo.n_records, bo.depth, (unsigned long long)bo.launches);
+      up0 = std::chrono::steady_clock::now();
+    }
+    if (bo.keep_host) {
+      std::string cerr_;
+      if (!check_device_bvh(d, H, sc->nodes.p, bo.n_records, bo.h_order, H.max_prims, cerr_)) { ctx->last_error = "GOPBRT_CHECK_BVH: " + cerr_; delete sc; return GOPBRT_ERR_INVALID; }
+      if (host_timing) fprintf(stderr, "[gopbrt scene] device BVH checked on the host: ok\n");
+    }
+  }
+  bool ok = (H.device_build || (sc->nodes.upload(nodes, st) == cudaSuccess && sc->recs.upload(recs, st) == cudaSuccess &&
+            sc->rec_bounds.upload(rec_bounds, st) == cudaSuccess && sc->prims.upload(prims, st) == cudaSuccess)) && sc->flat.upload(flat, st) == cudaSuccess &&
             sc->xf.upload(xf, st) == cudaSuccess && sc->xf_flags.upload(xf_flags, st) == cudaSuccess &&
             sc->spheres.upload(spheres, st) == cudaSuccess && sc->disks.upload(disks, st) == cudaSuccess &&
             sc->materials.upload(mats, st) == cudaSuccess && sc->textures.upload(texs, st) == cudaSuccess &&
@@ -558,8 +740,8 @@ static int upload_scene(gopbrt_ctx* ctx, HostScene& H, gopbrt_scene** out) {
             sc->tctr.alloc(1) == cudaSuccess && cudaMemsetAsync(sc->tctr.p, 0, sizeof(TraceCounters), st) == cudaSuccess &&
             sc->work.alloc(2) == cudaSuccess && cudaMemsetAsync(sc->work.p, 0, 2 * sizeof(int), st) == cudaSuccess &&
             cudaStreamSynchronize(st) == cudaSuccess;
-  if (getenv("GOPBRT_HOST_TIMING"))
-    fprintf(stderr, "[gopbrt scene] %-22s %8.3f ms\n", "upload", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - up0).count());
+  if (host_timing)
+    fprintf(stderr, "[gopbrt scene] %-22s %8.3f ms\n", "upload (tables)", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - up0).count());
   if (!ok) {
     ctx->last_error = std::string("scene upload: ") + cudaGetErrorString(cudaGetLastError());
     delete sc;
@@ -569,7 +751,7 @@ static int upload_scene(gopbrt_ctx* ctx, HostScene& H, gopbrt_scene** out) {
   D.nodes = (const float4*)sc->nodes.p; D.recs = sc->recs.p; D.rec_bounds = sc->rec_bounds.p; D.prims = sc->prims.p;
   D.xf = sc->xf.p; D.xf_flags = sc->xf_flags.p; D.spheres = sc->spheres.p; D.disks = sc->disks.p;
   D.materials = sc->materials.p; D.textures = sc->textures.p; D.lights = sc->lights.p; D.light_cdf = sc->light_cdf.p;
-  D.n_lights = nl; D.light_func_int = func_int; D.n_nodes = (int)nodes.size();
+  D.n_lights = nl; D.light_func_int = func_int; D.n_nodes = H.device_build ? (int)dev_records : (int)nodes.size();
   D.flat = (const float4*)sc->flat.p; D.n_flat = (int)flat.size(); D.flat_tri_mask = flat_tri_mask;
   // Distant.Preprocess → Bounds3.BoundingSphere (distant.go:36-38, bounds.go:105-112)
   D.world_radius = 0;
@@ -580,15 +762,15 @@ static int upload_scene(gopbrt_ctx* ctx, HostScene& H, gopbrt_scene** out) {
     for (int k = 0; k < 3; k++) { sc->world[k] = world.mn[k]; sc->world[3 + k] = world.mx[k]; }
   }
   for (const PrimRec& r : recs) sc->class_mask |= 1u << ((r.flags & RF_CLASS_MASK) >> RF_CLASS_SHIFT);
-  sc->bvh_nodes = nodes.size();
-  sc->bvh_depth = (uint64_t)bvh.depth;
+  const int depth = H.device_build ? dev_depth : bvh.depth;
+  sc->bvh_nodes = H.device_build ? dev_records : nodes.size();
+  sc->bvh_depth = (uint64_t)depth;
   // traversal stack, [entry][thread] in dynamic shared memory: a step over a 4-record child group (two tree levels)
   // stacks at most three records
-  sc->stack_cap = std::min(250, 3 * ((bvh.depth + 2) / 2) + 4);
+  sc->stack_cap = std::min(250, 3 * ((depth + 2) / 2) + 4);
   if (const char* e = getenv("GOPBRT_STACK_CAP")) sc->stack_cap = std::max(4, atoi(e));  // tuning aid (overflows are counted)
   sc->trace_smem = (size_t)sc->stack_cap * kTraceThreads * sizeof(unsigned);  // one node word per stacked node
   // scenes of triangles only get the traversal kernels that carry no sphere / disk (EFloat) code
-  bool quadrics = false;
   for (const PrimRec& r : recs) if ((r.flags & RK_KIND_MASK) != RK_TRIANGLE) { quadrics = true; break; }
   if (getenv("GOPBRT_GENERAL_TRACE")) quadrics = true;  // tuning aid: the general kernels on a triangle-only scene
   static const trace_fn k_general[7] = {k_trace<0, false, true>, k_trace<0, true, true>, k_trace<2, false, true>, k_trace<2, true, true>,

@@ -174,11 +174,16 @@ struct Result {
 //             by flatten_quads; axisL / axisR = split axes of the left / right child when that child is interior
 //   unused slot of a group: a = kEmptyWord and the empty box.
 // `b` keeps the leaf's primitive count (host-side checks only; the kernels do not read it).
+#ifdef __CUDACC__
+#define GPBVH_HD __host__ __device__
+#else
+#define GPBVH_HD
+#endif
 constexpr int kMaxLeafPrims = 4;
 constexpr uint32_t kEmptyWord = 0xffffffffu;
 constexpr uint64_t kMaxLeafFirst = (1ull << 29) - 1, kMaxGroups = (1ull << 25) - 1;
-static inline uint32_t leaf_word(uint64_t first, int n) { return (uint32_t)(first << 3) | (uint32_t)((n - 1) << 1) | 1u; }
-static inline uint32_t inner_word(uint64_t group, int axis0, int axisL, int axisR) {
+GPBVH_HD static inline uint32_t leaf_word(uint64_t first, int n) { return (uint32_t)(first << 3) | (uint32_t)((n - 1) << 1) | 1u; }
+GPBVH_HD static inline uint32_t inner_word(uint64_t group, int axis0, int axisL, int axisR) {
   return (uint32_t)(group << 7) | (uint32_t)(axisL << 5) | (uint32_t)(axisR << 3) | (uint32_t)(axis0 << 1);
 }
 static Node32 make_record(const BNode& n) {

@@ -88,3 +88,56 @@ def test_config3_sphere_field_rays_and_film_bit_exact(gp, dev):
     _assert_film_equal(film, ofilm, st, ost, "config3 96x54")
     assert st["efloat_panics"] == 0 and st["bvh_nodes"] > 100_000
     g.close(); o.close()
+
+
+# ---- on-device BVH build (csrc/gp_build.cuh): every scene of more than 64 primitives is built on the GPU by default
+def _render_small(gp, dev, scene, integ, tile=8):
+    g = gp.pbrt.GpuScene(dev, scene)
+    st = gp.pbrt.Render(g, integ, tile)
+    film = integ.GetCamera().GetFilm().pixels.copy()
+    g.close()
+    return film, st
+
+
+@pytest.mark.parametrize("what", ["mesh", "spheres", "mixed"])
+def test_device_built_tree_is_valid_and_equals_the_host_built_one(gp, dev, monkeypatch, what):
+    """GOPBRT_CHECK_BVH walks the device-built tree on the host (every primitive in exactly one leaf, leaf sizes, every float32 box
+    around the float64 bounds below it).  Then the same frame through the HOST builder (GOPBRT_HOST_BVH): hits do not depend on
+    the tree, so the two films and ray counts must be identical bit for bit, and so must the world bound."""
+    if what == "mesh":
+        scene, _ = gp.scenes.config4(W=96, H=54, grid=320)      # 203 522 triangles
+        integ = gp.scenes.config4_integrator(96, 54, (2, 2))
+    elif what == "spheres":
+        scene, integ = gp.scenes.config3(W=96, H=54, spp=(2, 2), n_spheres=30000)
+    else:
+        scene, integ = gp.scenes.mixed_test_scene(200, seed=11), gp.scenes.test_integrator(96, 54, spp=(2, 2), maxDepth=5)
+    monkeypatch.setenv("GOPBRT_CHECK_BVH", "1")
+    g = gp.pbrt.GpuScene(dev, scene)   # raises if the check fails
+    wb_dev = g.WorldBound()
+    g.close()
+    monkeypatch.delenv("GOPBRT_CHECK_BVH")
+    film_d, st_d = _render_small(gp, dev, scene, integ)
+    monkeypatch.setenv("GOPBRT_HOST_BVH", "1")
+    g = gp.pbrt.GpuScene(dev, scene)
+    wb_host = g.WorldBound()
+    g.close()
+    film_h, st_h = _render_small(gp, dev, scene, integ)
+    assert wb_dev == wb_host
+    assert np.array_equal(film_d, film_h)
+    for k in ("camera_rays", "closest_rays", "shadow_rays"):
+        assert st_d[k] == st_h[k], k
+    assert st_d["stack_overflows"] == 0 and st_h["stack_overflows"] == 0
+
+
+def test_device_build_rejects_bad_indices(gp, dev):
+    import ctypes as C
+    scene, _ = gp.scenes.config4(W=32, H=18, grid=40)
+    d = scene.desc()
+    tri = d.triangles[5]
+    keep = tri.v[1]
+    tri.v[1] = d.n_vertices + 3
+    h = C.c_void_p()
+    assert dev.lib.gopbrt_scene_create(dev.h, C.byref(d), C.byref(h)) == gp.abi.ERR_INVALID and "vertex index" in dev.error()
+    tri.v[1] = keep
+    assert dev.lib.gopbrt_scene_create(dev.h, C.byref(d), C.byref(h)) == gp.abi.OK
+    dev.lib.gopbrt_scene_destroy(h)
