@@ -1278,8 +1278,16 @@ static int render_impl(gopbrt_scene* sc, const gopbrt_camera* cam, const gopbrt_
       if (sc->cancel.exchange(0)) { rc = GOPBRT_ERR_CANCELLED; break; }
     }
     tick(ST_FILM);
-    k_film_merge<<<g_small, 128, 0, st>>>(L, P, d_film);
-    ctx->launches++;
+    {
+      RenderParams PM = P;
+      if (P.uniform_fp && P.groups > 1 && P.lane_base % P.groups == 0 && P.lanes_active % P.groups == 0) {
+        k_group_sums<<<g_small, 128, 0, st>>>(L, P);
+        ctx->launches++;
+        PM.groups_merged = 1;
+      }
+      k_film_merge<<<g_small, 128, 0, st>>>(L, PM, d_film);
+      ctx->launches++;
+    }
   }
   tick(ST_N);
   hw_tick("wavefront loop");
