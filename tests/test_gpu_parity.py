@@ -552,6 +552,39 @@ def test_concurrent_renders_on_one_device_context(gp, dev):
         g.close()
 
 
+def test_two_full_size_scenes_share_one_context(gp, dev):
+    # two scene handles with 1080p FAST-mode workspaces (tens of GB of lane state each under the automatic lane groups) on ONE
+    # context, rendered from two host threads: the per-handle lane budget must leave room for both, and each film must equal
+    # the same handle's serial render bit for bit
+    import threading
+    P = gp.pbrt
+    jobs = []
+    for cfg, spp in (("config1", (4, 4)), ("config2", (4, 4))):
+        scene, integ = getattr(gp.scenes, cfg)(spp=spp)
+        g = P.GpuScene(dev, scene)
+        st = P.Render(g, integ, 1, mode=gp.abi.MODE_FAST)
+        assert st["lanes"] >= 1920 * 1080 * 4
+        jobs.append((g, integ, integ.GetCamera().GetFilm().pixels.copy()))
+    out, errs = [None, None], []
+
+    def work(i):
+        try:
+            g, integ, _ = jobs[i]
+            for _ in range(2):
+                P.Render(g, integ, 1, mode=gp.abi.MODE_FAST)
+            out[i] = integ.GetCamera().GetFilm().pixels.copy()
+        except Exception as e:  # noqa: BLE001
+            errs.append(e)
+
+    th = [threading.Thread(target=work, args=(i,)) for i in range(2)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert not errs, errs
+    for i, (g, integ, ref) in enumerate(jobs):
+        assert np.array_equal(out[i], ref)
+        g.close()
+
+
 def test_degenerate_renders_match_oracle(gp, dev):
     # empty aggregate, no lights, a 1x1 film, one sample per pixel (pixel.go:48-52 increments first: zero samples run),
     # maxDepth 1, a film smaller than one tile
