@@ -281,12 +281,17 @@ def main():
     barrier()
     launches0 = dev.launches()
     per_step_ms, stats = [], []
+    # clocks / throttle reasons are sampled over the device-timed loop AND the e2e loops; the sampler (an nvidia-smi process)
+    # is started before and stopped after all of them, so that neither its start-up nor its teardown lands inside a timed region
+    clocks = ClockSampler(local_rank)
+    clocks.__enter__()
+    time.sleep(0.3)
+    barrier()
     wall0 = time.time()
-    with ClockSampler(local_rank) as clocks:
-        for _ in range(args.steps):
-            st, ms = step_device(0)
-            per_step_ms.append(ms)
-            stats.append(st)
+    for _ in range(args.steps):
+        st, ms = step_device(0)
+        per_step_ms.append(ms)
+        stats.append(st)
     barrier()
     wall = time.time() - wall0
     launches = dev.launches() - launches0
@@ -303,13 +308,18 @@ def main():
     barrier()
     e0 = time.time()
     e2e_parts = {"ms_device": 0.0, "ms_reduce": 0.0, "ms_download": 0.0}
+    e2e_walls = []
     for _ in range(args.steps):
+        w0 = time.time()
         est = step_e2e(film_host_np)  # gopbrt_render: film D2H (into pinned host memory) inside the call
+        e2e_walls.append((time.time() - w0) * 1e3)
         e2e_parts["ms_device"] += est["ms_total"] / args.steps
         e2e_parts["ms_reduce"] += est["ms_reduce"] / args.steps
         e2e_parts["ms_download"] += est.get("ms_download", 0.0) / args.steps
     barrier()
     e2e_s = time.time() - e0
+    if os.environ.get("GOPBRT_BENCH_DEBUG"):
+        print("[bench] e2e per-call wall ms:", [round(x, 1) for x in e2e_walls], "loop total", round(e2e_s * 1e3, 1), file=sys.stderr)
     # the same call into a PAGEABLE host buffer (a Go []float64 is pageable): one warm call, then a few timed ones
     film_pageable = np.empty(H * W * 4, dtype=np.float64) if rank == 0 else None
     step_e2e(film_pageable)
@@ -320,6 +330,7 @@ def main():
         step_e2e(film_pageable)
     barrier()
     e2e_pageable_s = (time.time() - p0) / n_pageable
+    clocks.__exit__(None, None, None)
 
     ms_total, e2e_total, wall_max, e2e_pageable = max_over_ranks([ms_rank, e2e_s, wall, e2e_pageable_s])
     rays_total, launches_total, paths_total = sum_over_ranks([float(rays_rank), float(launches), float(stats[0]["camera_rays"])])
