@@ -355,11 +355,23 @@ def main():
         peak = float(peaks.get("hbm_gbs", 6650.0))
         achieved = bytes_frame * KS / (s_ext / 1e3) / 1e9 if s_ext > 0 else 0.0
         small = stats[0]["bvh_nodes"] <= 200  # the flat aggregate (<= 64 primitives): its table lives in shared memory
+        # DRAM bytes per launch of the extend kernel.  NOT measured in this run (a timed run carries no profiler): one
+        # `ncu --set full` capture of an extend launch of this workload (profiles/r02_traffic.json: dram__bytes_read.sum +
+        # dram__bytes_write.sum per ray of that launch), scaled to this run's average rays per launch; null for other workloads.
+        traffic, traffic_source = None, "no ncu capture of this workload under profiles/"
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
+            if tj.get("workload") == args.config:
+                traffic = tj["dram_bytes_per_ray"] * ext_rays / max(1, n_ext / KS)
+                traffic_source = ("profiles/r02_traffic.json: %.1f DRAM bytes per ray in one ncu --set full capture of an extend launch "
+                                  "(%d rays), scaled to this run's rays per launch - not measured in this run" % (tj["dram_bytes_per_ray"], tj["rays_in_launch"]))
+        except Exception:
+            pass
         roof = {"bound": "hbm", "kernel": "k_extend (closest-hit traversal, conservative f32 node boxes + fp64 own-bound / EFloat / watertight shape tests)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6.65 TB/s (of fallback)",
-                "traffic": None,
-                "traffic_note": "not measured in this run (ncu --set full captures are summarised under profiles/)",
+                "traffic": traffic,
+                "traffic_source": traffic_source,
                 "limiter": ("issue / SIMT divergence: the scene's %d-entry bound table is shared-memory resident and every ray tests every entry "
                             "(V = table size), so the algorithmic node bytes never reach DRAM; see roofline_deep_bvh for the HBM-resident tree" % cst["bvh_nodes"]
                             if small else "node-fetch latency (L2/HBM) and SIMT divergence"),

@@ -1287,7 +1287,15 @@ __global__ void k_group_sums(Lanes L, RenderParams P) {
   for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n_tiles; t += (long long)gridDim.x * blockDim.x) {
     PathRec* base = L.path + t * P.groups;
     double r = base->pad[0], g = base->pad[1], b = base->pad[2];
-    for (int k = 1; k < P.groups; k++) { const PathRec* q = base + k; r += q->pad[0]; g += q->pad[1]; b += q->pad[2]; }
+    int k = 1;
+    for (; k + 8 <= P.groups; k += 8) {  // eight records' loads in flight, added in ascending order
+      double x[8][3];
+#pragma unroll
+      for (int j = 0; j < 8; j++) { const double* q = base[k + j].pad; x[j][0] = __ldcs(q); x[j][1] = __ldcs(q + 1); x[j][2] = __ldcs(q + 2); }
+#pragma unroll
+      for (int j = 0; j < 8; j++) { r += x[j][0]; g += x[j][1]; b += x[j][2]; }
+    }
+    for (; k < P.groups; k++) { const PathRec* q = base + k; r += q->pad[0]; g += q->pad[1]; b += q->pad[2]; }
     base->pad[0] = r; base->pad[1] = g; base->pad[2] = b;
   }
 }
