@@ -281,8 +281,10 @@ def main():
     barrier()
     launches0 = dev.launches()
     per_step_ms, stats = [], []
-    # clocks / throttle reasons are sampled over the device-timed loop AND the e2e loops; the sampler (an nvidia-smi process)
-    # is started before and stopped after all of them, so that neither its start-up nor its teardown lands inside a timed region
+    # clocks / throttle reasons are sampled over the device-timed loop (CUDA events: host-side stalls do not enter `value`).  The
+    # sampler is an nvidia-smi process; NVML queries hold a driver lock for milliseconds at a time (tens on a multi-GPU box) and
+    # CUDA API calls queue behind it, so it is started before and fully stopped after that loop and never runs during the
+    # wall-clock e2e loops below.
     clocks = ClockSampler(local_rank)
     clocks.__enter__()
     time.sleep(0.3)
@@ -294,6 +296,8 @@ def main():
         stats.append(st)
     barrier()
     wall = time.time() - wall0
+    clocks.__exit__(None, None, None)
+    time.sleep(1.0)
     launches = dev.launches() - launches0
     rays_rank = sum(s["closest_rays"] + s["shadow_rays"] for s in stats)
     ms_rank = sum(per_step_ms)
@@ -330,7 +334,6 @@ def main():
         step_e2e(film_pageable)
     barrier()
     e2e_pageable_s = (time.time() - p0) / n_pageable
-    clocks.__exit__(None, None, None)
 
     ms_total, e2e_total, wall_max, e2e_pageable = max_over_ranks([ms_rank, e2e_s, wall, e2e_pageable_s])
     rays_total, launches_total, paths_total = sum_over_ranks([float(rays_rank), float(launches), float(stats[0]["camera_rays"])])

@@ -99,6 +99,8 @@ struct BatchPool {
 
 struct Workspace {  // per-scene render workspace, kept between gopbrt_render calls of the same shape
   long long lanes = 0;
+  long long cap = 0, cap_key[5] = {0, 0, 0, 0, 0};  // lane capacity granted to the last request, and what that request was
+  size_t per_lane = 0;
   size_t bytes_tables = 0, bytes_tilepix = 0;
   DevBuf<RayRec> ray;
   DevBuf<ShadowRec> sray;
@@ -117,7 +119,9 @@ struct Workspace {  // per-scene render workspace, kept between gopbrt_render ca
   cudaGraphExec_t graph_exec = nullptr;
   std::vector<unsigned char> graph_key;
   cudaEvent_t graph_ev[2] = {nullptr, nullptr};
+  cudaEvent_t frame_ev[2] = {nullptr, nullptr};
   ~Workspace() {
+    for (auto e : frame_ev) if (e) cudaEventDestroy(e);
     if (remaining_host) cudaFreeHost(remaining_host);
     for (auto e : events) cudaEventDestroy(e);
     if (graph_exec) cudaGraphExecDestroy(graph_exec);
@@ -1069,17 +1073,25 @@ static int render_impl(gopbrt_scene* sc, const gopbrt_camera* cam, const gopbrt_
   const size_t frame_doubles = P.integrator == GOPBRT_INTEGRATOR_DIRECT_LIGHTING ? (size_t)P.direct_levels * 8 : 0;
   const size_t n_seg = (size_t)P.n_seg;  // shadow segments (and shadow-queue entries) per lane
   size_t per_lane = sizeof(RayRec) + n_seg * (sizeof(ShadowRec) + 1) + sizeof(PathRec) + (8 + n_seg) * 4 + 1 + table_doubles * 8 + (P.uniform_fp ? 0 : (size_t)tpw * tph * 4 * 8) + frame_doubles * 8;
-  size_t free_b = 0, total_b = 0;
-  GP_CUDA(ctx, cudaMemGetInfo(&free_b, &total_b));
   Workspace& W = sc->ws;
-  size_t held = W.lanes ? (size_t)W.lanes * per_lane : 0;
   // Lane state of ONE scene handle: at most 40 % of the device's memory (GOPBRT_LANE_BUDGET_GB overrides) and 80 % of what is
   // free right now — several scenes render on one context (one per gRPC request in the reference) and must not starve each other.
-  double budget = 0.40 * (double)total_b;
-  if (const char* e = getenv("GOPBRT_LANE_BUDGET_GB")) budget = std::max(0.25, atof(e)) * 1e9;
-  budget = std::min(budget, (double)(free_b + held) * 0.80);
-  long long cap = (long long)(budget / (double)per_lane);
-  if (opt && opt->max_lanes > 0) cap = std::min<long long>(cap, opt->max_lanes);
+  // The device is asked for its free memory only when the request differs from the one this workspace was sized for: the
+  // query takes a driver lock that monitoring tools (NVML, nvidia-smi) hold for milliseconds at a time.
+  const long long cap_key[5] = {tiles_rank, (long long)P.groups * 2 + (auto_groups ? 1 : 0), (long long)per_lane, opt ? (long long)opt->max_lanes : 0, (long long)P.mode};
+  long long cap = W.cap;
+  if (W.lanes == 0 || memcmp(cap_key, W.cap_key, sizeof(cap_key)) != 0) {
+    size_t free_b = 0, total_b = 0;
+    GP_CUDA(ctx, cudaMemGetInfo(&free_b, &total_b));
+    size_t held = W.lanes ? (size_t)W.lanes * W.per_lane : 0;
+    double budget = 0.40 * (double)total_b;
+    if (const char* e = getenv("GOPBRT_LANE_BUDGET_GB")) budget = std::max(0.25, atof(e)) * 1e9;
+    budget = std::min(budget, (double)(free_b + held) * 0.80);
+    cap = (long long)(budget / (double)per_lane);
+    if (opt && opt->max_lanes > 0) cap = std::min<long long>(cap, opt->max_lanes);
+    W.cap = cap; W.per_lane = per_lane;
+    memcpy(W.cap_key, cap_key, sizeof(cap_key));
+  }
   // automatic lane groups shrink until one pass holds every lane (more passes would serialise what the groups parallelise)
   if (auto_groups && tiles_rank * P.groups > cap) P.groups = (int)std::max<long long>(1, std::min<long long>(P.groups, cap / std::max<long long>(1, tiles_rank)));
   long long lanes_total = tiles_rank * P.groups;
@@ -1154,13 +1166,8 @@ static int render_impl(gopbrt_scene* sc, const gopbrt_camera* cam, const gopbrt_
   const int g_gen = ctx->grid_gen[gen_i];
   constexpr int kGraphIters = 8;
 
-  struct EventPair {  // destroyed on every return path
-    cudaEvent_t e[2] = {nullptr, nullptr};
-    ~EventPair() { for (auto x : e) if (x) cudaEventDestroy(x); }
-    cudaEvent_t& operator[](int i) { return e[i]; }
-  } ev;
-  GP_CUDA(ctx, cudaEventCreate(&ev[0]));
-  GP_CUDA(ctx, cudaEventCreate(&ev[1]));
+  cudaEvent_t* ev = W.frame_ev;  // the frame's two timing events live with the workspace (no create / destroy per frame)
+  for (int k = 0; k < 2; k++) if (!ev[k]) GP_CUDA(ctx, cudaEventCreate(&ev[k]));
   GP_CUDA(ctx, cudaEventRecord(ev[0], st));
   uint64_t iterations = 0, launches0 = ctx->launches.load();
   int rc = GOPBRT_OK;
