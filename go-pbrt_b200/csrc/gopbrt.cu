@@ -101,6 +101,7 @@ struct Workspace {  // per-scene render workspace, kept between gopbrt_render ca
   long long lanes = 0;
   long long cap = 0, cap_key[5] = {0, 0, 0, 0, 0};  // lane capacity granted to the last request, and what that request was
   size_t per_lane = 0;
+  int auto_groups = 1;  // the lane-group count the automatic rule chose for that request
   size_t bytes_tables = 0, bytes_tilepix = 0;
   DevBuf<RayRec> ray;
   DevBuf<ShadowRec> sray;
@@ -1045,13 +1046,16 @@ static int render_impl(gopbrt_scene* sc, const gopbrt_camera* cam, const gopbrt_
   P.groups = 1;
   const long long tiles_rank = (P.ntiles - P.rank + P.world - 1) / P.world;
   bool auto_groups = false;
+  int share = 1;
   if (P.mode == GOPBRT_MODE_FAST) {
     int want = (flags >> 8) & 0xff;
-    int share = (P.spp - 1 + P.s_world - 1) / P.s_world;  // samples 1..spp-1 of every pixel, split over the ranks
-    // automatic: two samples per lane (measured on one B200, config 2 / 63 spp: 8 samples per lane 186 ms, 4: 167 ms, 2: 149 ms,
-    // 1: 148 ms — the last halving doubles the lane state for 1 %), bounded below by the lane-state budget
-    if (want == 0) { want = std::max(1, std::min(64, (share + 1) / 2)); auto_groups = true; }
-    P.groups = std::max(1, std::min(want, std::max(1, share)));
+    share = std::max(1, (P.spp - 1 + P.s_world - 1) / P.s_world);  // samples 1..spp-1 of every pixel, split over the ranks
+    // automatic (decided below, once the lane-state budget is known): ONE sample per lane while that state stays small, else two
+    // (measured on one B200, config 2 / 63 spp: 8 samples per lane 186 ms, 4: 167 ms, 2: 149 ms, 1: 148 ms — the last halving
+    // doubles 21 GB of lane state for 1 %; on a rank's share of the frame, where the state is small, it is worth 4-5 %: world 2
+    // 69.1 -> 66.5 ms, world 4 34.7 -> 33.3 ms, world 8 17.5 -> 16.6 ms)
+    if (want == 0) { want = std::min(64, share); auto_groups = true; }
+    P.groups = std::max(1, std::min(want, share));
   }
 
   // GOPBRT_HOST_TIMING=1: host wall-clock of the call's phases on stderr (tuning aid)
@@ -1080,7 +1084,9 @@ static int render_impl(gopbrt_scene* sc, const gopbrt_camera* cam, const gopbrt_
   // query takes a driver lock that monitoring tools (NVML, nvidia-smi) hold for milliseconds at a time.
   const long long cap_key[5] = {tiles_rank, (long long)P.groups * 2 + (auto_groups ? 1 : 0), (long long)per_lane, opt ? (long long)opt->max_lanes : 0, (long long)P.mode};
   long long cap = W.cap;
-  if (W.lanes == 0 || memcmp(cap_key, W.cap_key, sizeof(cap_key)) != 0) {
+  if (W.lanes != 0 && memcmp(cap_key, W.cap_key, sizeof(cap_key)) == 0) {
+    if (auto_groups) P.groups = W.auto_groups;
+  } else {
     size_t free_b = 0, total_b = 0;
     GP_CUDA(ctx, cudaMemGetInfo(&free_b, &total_b));
     size_t held = W.lanes ? (size_t)W.lanes * W.per_lane : 0;
@@ -1089,11 +1095,16 @@ static int render_impl(gopbrt_scene* sc, const gopbrt_camera* cam, const gopbrt_
     budget = std::min(budget, (double)(free_b + held) * 0.80);
     cap = (long long)(budget / (double)per_lane);
     if (opt && opt->max_lanes > 0) cap = std::min<long long>(cap, opt->max_lanes);
+    if (auto_groups) {
+      // one sample per lane only while the lane state stays within an eighth of the device's memory, else two per lane;
+      // then the groups shrink until one pass holds every lane (more passes would serialise what the groups parallelise)
+      if ((double)tiles_rank * P.groups * (double)per_lane > 0.125 * (double)total_b) P.groups = std::max(1, std::min(64, (share + 1) / 2));
+      if (tiles_rank * P.groups > cap) P.groups = (int)std::max<long long>(1, std::min<long long>(P.groups, cap / std::max<long long>(1, tiles_rank)));
+      W.auto_groups = P.groups;
+    }
     W.cap = cap; W.per_lane = per_lane;
     memcpy(W.cap_key, cap_key, sizeof(cap_key));
   }
-  // automatic lane groups shrink until one pass holds every lane (more passes would serialise what the groups parallelise)
-  if (auto_groups && tiles_rank * P.groups > cap) P.groups = (int)std::max<long long>(1, std::min<long long>(P.groups, cap / std::max<long long>(1, tiles_rank)));
   long long lanes_total = tiles_rank * P.groups;
   long long lanes = std::max<long long>(1, std::min(lanes_total, cap));
   if (lanes * (long long)n_seg > 0x7fffff00LL) lanes = 0x7fffff00LL / (long long)n_seg;
