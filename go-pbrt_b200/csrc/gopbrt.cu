@@ -1096,9 +1096,9 @@ static int render_impl(gopbrt_scene* sc, const gopbrt_camera* cam, const gopbrt_
     cap = (long long)(budget / (double)per_lane);
     if (opt && opt->max_lanes > 0) cap = std::min<long long>(cap, opt->max_lanes);
     if (auto_groups) {
-      // one sample per lane only while the lane state stays within an eighth of the device's memory, else two per lane;
+      // one sample per lane only while the lane state stays within a quarter of the device's memory, else two per lane;
       // then the groups shrink until one pass holds every lane (more passes would serialise what the groups parallelise)
-      if ((double)tiles_rank * P.groups * (double)per_lane > 0.125 * (double)total_b) P.groups = std::max(1, std::min(64, (share + 1) / 2));
+      if ((double)tiles_rank * P.groups * (double)per_lane > 0.25 * (double)total_b) P.groups = std::max(1, std::min(64, (share + 1) / 2));
       if (tiles_rank * P.groups > cap) P.groups = (int)std::max<long long>(1, std::min<long long>(P.groups, cap / std::max<long long>(1, tiles_rank)));
       W.auto_groups = P.groups;
     }
