@@ -132,6 +132,69 @@ GP_HD bool sphere_roots(const Ray& ray, V3 oe, V3 de, double radius, EF* t0, EF*
                 ef_muls(ef_new(radius, 0, bad), radius, bad), bad);
   return ef_quadratic(a, b, c, t0, t1, bad);
 }
+// ---- full spheres without interval arithmetic, whenever the interval bounds cannot change a decision ----
+// Sphere.Intersect reads the EFloat bounds of its two roots in four comparisons only (sphere.go:83-93: t0.hi > tMax, t1.lo <= 0,
+// t0.lo <= 0, t1.hi > tMax); the hit distance itself is the plain value t.v, and every .v is ordinary float64 arithmetic in the
+// order written here (efloat.go keeps .v = plain op).  So the ~1000-instruction interval evaluation is needed only when a root
+// lies within its own error bound of 0 or tMax — a ray leaving the sphere it starts on, a grazing hit.  Everywhere else the
+// comparisons are decided by v and a RIGOROUS UPPER BOUND W of the interval's half-width:
+//   every EFloat operation returns the hull of the exact operation on its input intervals, each end rounded to nearest and
+//   stepped one ulp outward: at most 4u|x| per end (u = 2^-53).  The inputs are (v, err) with err of the order 1e-323 |v|
+//   (the reference's MachineEpsilon is the smallest denormal), i.e. one ulp each side.  Propagating:
+//     squares and products            W <= 12u |x y|
+//     a = dx^2+dy^2+dz^2              W(a) <= 24u a
+//     b = 2 (dx ox + dy oy + dz oz)   W(b) <= 64u S,          S  = |dx ox| + |dy oy| + |dz oz|
+//     c = |o|^2 - r^2                 W(c) <= 32u (O2 + r^2), O2 = |o|^2
+//     root = EF(sqrt(disc), eps root) W <= 4u root            (the reference does NOT propagate a, b, c into the root)
+//     q = -(b +- root) / 2            W(q) <= 32u S + 12u |q|
+//     t0 = q / a                      W <= (W(q) + |t0| W(a)) / (a - W(a)) + 4u |t0|
+//     t1 = c / q                      W <= (W(c) + |t1| W(q)) / (|q| - W(q)) + 4u |t1|
+//   The code below uses FOUR TIMES these constants, and gives up (returns -1: the caller runs the interval path) whenever a
+//   comparison falls inside the bound, an operand is huge, an input error is not negligible, or q's interval could touch 0.
+//   A decided comparison is the comparison the interval path makes, so hit / miss, the root chosen and tHit are bit-identical.
+// Returns 1 = hit (*tHit, *which as sphere_select), 0 = miss, -1 = undecided.
+GP_HD int sphere_full_fast(const Ray& ray, V3 oe, V3 de, double radius, double* tHit, int* which, double* dbg = nullptr) {
+  const double ox = ray.o.x, oy = ray.o.y, oz = ray.o.z, dx = ray.d.x, dy = ray.d.y, dz = ray.d.z;
+  const double m = fmax(fmax(fmax(fabs(ox), fabs(oy)), fmax(fabs(oz), fabs(dx))), fmax(fmax(fabs(dy), fabs(dz)), fabs(radius)));
+  const double me = fmax(fmax(fmax(fabs(oe.x), fabs(oe.y)), fmax(fabs(oe.z), fabs(de.x))), fmax(fabs(de.y), fabs(de.z)));
+  if (!(m < 1e100) || !(me <= 1e-290)) return -1;
+  const double av = ((dx * dx) + (dy * dy)) + (dz * dz);
+  const double bv = (((dx * ox) + (dy * oy)) + (dz * oz)) * 2.0;
+  const double cv = (((ox * ox) + (oy * oy)) + (oz * oz)) - (radius * radius);
+  const double disc = bv * bv - 4. * av * cv;
+  if (disc < 0) return 0;  // efloat.Quadratic's own early return (efloat/math.go:36-40)
+  if (!(av > 1e-200)) return -1;
+  const double root = sqrt(disc);
+  const double q = (bv < 0) ? (bv - root) * -0.5 : (bv + root) * -0.5;
+  double r0 = q / av, r1 = cv / q;
+  const double u = 1.1102230246251565e-16, tiny = 1e-280;
+  const double S = fabs(dx * ox) + fabs(dy * oy) + fabs(dz * oz);
+  const double O2 = ox * ox + oy * oy + oz * oz;
+  const double Wq = 128 * u * S + 48 * u * fabs(q) + tiny;
+  const double Wc = 128 * u * (O2 + radius * radius) + tiny;
+  if (!(fabs(q) > 2 * Wq)) return -1;
+  double W0 = 1.01 * (Wq / av) + 128 * u * fabs(r0) + tiny;  // |t0| W(a) / a <= 96u |t0|, + 16u |t0| of rounding, + 1 / (1 - 96u)
+  double W1 = 2 * (Wc + fabs(r1) * Wq) / fabs(q) + 16 * u * fabs(r1) + tiny;
+  if (r0 > r1) { double t = r0; r0 = r1; r1 = t; t = W0; W0 = W1; W1 = t; }  // efloat/math.go:55-57 (swap on .v)
+  if (dbg) { dbg[0] = r0; dbg[1] = W0; dbg[2] = r1; dbg[3] = W1; }  // (verification build: the roots and their assumed bounds)
+  const double tmax = ray.tmax;
+  if (r0 > tmax) return 0;                  // t0.hi >= t0.v > tMax
+  if (!(r0 + W0 <= tmax)) return -1;
+  if (r1 <= 0) return 0;                    // t1.lo <= t1.v <= 0
+  if (!(r1 - W1 > 0)) return -1;
+  if (r0 <= 0) {                            // t0.lo <= t0.v <= 0: the second root is the candidate
+    if (r1 > tmax) return 0;
+    if (!(r1 + W1 <= tmax)) return -1;
+    *tHit = r1;
+    if (which) *which = 1;
+    return 1;
+  }
+  if (!(r0 - W0 > 0)) return -1;
+  *tHit = r0;
+  if (which) *which = 0;
+  return 1;
+}
+
 GP_HD V3 sphere_refine(const Ray& ray, double t, double radius) {  // sphere.go:98-104
   V3 pHit = ray.o + ray.d * t;
   pHit = pHit * (radius / sqrt(dist2(pHit, mk3(0, 0, 0))));
@@ -260,6 +323,36 @@ GP_HD void xf_hit(const M4& m, const M4& inv, Hit& h) {
   h.ns = faceforward(h.ns, h.n);
 }
 
+// GP_SPHERE_FAST_PATH: the decision of sphere_full_fast when it has one.  -DGP_CHECK_FAST_SPHERE (verification build) runs the
+// interval path as well and raises `bad` (counted as efloat_panics, which every test asserts to be 0) if the two ever disagree
+// or an interval is wider than the bound the fast path assumed; -DGP_NO_FAST_SPHERE disables the fast path.
+#if defined(GP_NO_FAST_SPHERE)
+#define GP_SPHERE_FAST_PATH(ray, oe, de, radius, tHit, bad)
+#elif defined(GP_CHECK_FAST_SPHERE)
+#define GP_SPHERE_FAST_PATH(ray, oe, de, radius, tHit, bad)                                                   \
+  {                                                                                                           \
+    double tf_ = 0, dbg_[4] = {0, -1, 0, -1};                                                                 \
+    int wf_ = -1;                                                                                             \
+    const int f_ = sphere_full_fast(ray, oe, de, radius, &tf_, &wf_, dbg_);                                   \
+    EF c0_, c1_;                                                                                              \
+    double ts_ = 0;                                                                                           \
+    int ws_ = -1;                                                                                             \
+    const bool roots_ = sphere_roots(ray, oe, de, radius, &c0_, &c1_, bad);                                   \
+    const bool h_ = roots_ && sphere_select(ray, c0_, c1_, radius, 0, 0, 0, true, &ts_, &ws_);                \
+    if (f_ >= 0 && (h_ != (f_ == 1) || (h_ && (ts_ != tf_ || ws_ != wf_)))) bad = 1;                          \
+    if (roots_ && dbg_[1] >= 0 &&                                                                             \
+        (c0_.v != dbg_[0] || c1_.v != dbg_[2] || !(c0_.hi - c0_.v <= dbg_[1]) || !(c0_.v - c0_.lo <= dbg_[1]) ||  \
+         !(c1_.hi - c1_.v <= dbg_[3]) || !(c1_.v - c1_.lo <= dbg_[3])))                                         \
+      bad = 1;                                                                                                \
+  }
+#else
+#define GP_SPHERE_FAST_PATH(ray, oe, de, radius, tHit, bad)                                                   \
+  {                                                                                                           \
+    const int f_ = sphere_full_fast(ray, oe, de, radius, tHit, nullptr);                                      \
+    if (f_ >= 0) return f_ == 1;                                                                              \
+  }
+#endif
+
 // generic primitive test used by both traversal kernels.  Returns true and the hit t (the new r.TMax,
 // primitive.go:51,102) if the primitive is hit within ray.tmax.  `bad` collects efloat.Check panics.
 // sphere / disk test (the long float64 + EFloat path); triangles are tested inline by the traversal kernel
@@ -272,6 +365,7 @@ GP_D bool quadric_test(const DevScene& sc, const PrimRec* rec, uint32_t flags, c
     if (flags & RF_HAS_P2W) ray = xf_ray(translation_m4(d[4], d[5], d[6]), ray, nullptr, nullptr);
     V3 oe, de;
     ray = xf_ray(translation_m4(d[1], d[2], d[3]), ray, &oe, &de);  // worldToObject.TransformRay (sphere.go:65)
+    GP_SPHERE_FAST_PATH(ray, oe, de, d[0], tHit, bad)
     EF t0, t1;
     if (!sphere_roots(ray, oe, de, d[0], &t0, &t1, bad)) return false;
     return sphere_select(ray, t0, t1, d[0], 0, 0, 0, true, tHit, nullptr);
@@ -283,6 +377,7 @@ GP_D bool quadric_test(const DevScene& sc, const PrimRec* rec, uint32_t flags, c
     SphereDev s = sc.spheres[pr.y];
     V3 oe, de;
     ray = xf_ray(load_m4(sc, s.xf, true), ray, &oe, &de);
+    if (flags & RF_FULL) { GP_SPHERE_FAST_PATH(ray, oe, de, s.radius, tHit, bad) }
     EF t0, t1;
     if (!sphere_roots(ray, oe, de, s.radius, &t0, &t1, bad)) return false;
     return sphere_select(ray, t0, t1, s.radius, s.zMin, s.zMax, s.phiMax, (flags & RF_FULL) != 0, tHit, nullptr);
