@@ -1034,6 +1034,8 @@ static int render_impl(gopbrt_scene* sc, const gopbrt_camera* cam, const gopbrt_
   P.light_power = (ig->kind == GOPBRT_INTEGRATOR_PATH && ig->light_strategy == GOPBRT_LIGHTS_POWER) ? 1 : 0;
   // every sample of a lane through the integer corner of the lane's one pixel, filter weight 1: see film_add_uniform
   P.uniform_fp = (ig->tile_size == 1 && smp->kind == GOPBRT_SAMPLER_STRATIFIED && smp->n_sampled_dimensions >= 1 && !getenv("GOPBRT_NO_UNIFORM_FP")) ? 1 : 0;
+  // ... and then a lane's last sample needs no trip through the regeneration queue (gp_render.cuh lane_on_last_sample)
+  P.last_in_place = (P.uniform_fp && P.mode == GOPBRT_MODE_FAST && ig->kind == GOPBRT_INTEGRATOR_PATH && !getenv("GOPBRT_NO_LAST_IN_PLACE")) ? 1 : 0;
   if (const char* ferr = film_params(film, ig->tile_size, P)) return bad(ferr);
   long long fw = P.cx1 - P.cx0, fh = P.cy1 - P.cy0;
   long long tpw = P.tpw, tph = P.tph;
@@ -1298,10 +1300,15 @@ static int render_impl(gopbrt_scene* sc, const gopbrt_camera* cam, const gopbrt_
     tick(ST_FILM);
     {
       RenderParams PM = P;
-      if (P.uniform_fp && P.groups > 1 && P.lane_base % P.groups == 0 && P.lanes_active % P.groups == 0) {
-        k_group_sums<<<g_small, 128, 0, st>>>(L, P);
+      if (P.uniform_fp && (P.groups > 1 || P.last_in_place) && P.lane_base % P.groups == 0 && P.lanes_active % P.groups == 0) {
+        if (!P.last_in_place) k_group_sums<false, false><<<g_small, 128, 0, st>>>(L, P, W.rctr.p);
+        else if (P.s_world * P.groups >= P.spp - 1) k_group_sums<true, true><<<g_small, 128, 0, st>>>(L, P, W.rctr.p);  // at most one sample per lane
+        else k_group_sums<true, false><<<g_small, 128, 0, st>>>(L, P, W.rctr.p);
         ctx->launches++;
         PM.groups_merged = 1;
+      } else if (P.last_in_place) {
+        k_fold_last<<<g_small, 128, 0, st>>>(L, P, W.rctr.p);
+        ctx->launches++;
       }
       k_film_merge<<<g_small, 128, 0, st>>>(L, PM, d_film);
       ctx->launches++;

@@ -50,8 +50,21 @@ struct RenderParams {
                                  // on those with s % (s_world * groups) == s_rank * groups + k % groups  (1 in STRICT mode)
   long long lane_base;           // first lane-slot (tile = ((lane_base + lane) / groups) * world + rank) of this pass
   long long lanes_active;        // lanes in use this pass
-  int groups_merged, pad_;       // film merge only: k_group_sums has folded every tile's lane groups into group 0's record
+  int groups_merged;             // film merge only: k_group_sums has folded every tile's lane groups into group 0's record
+  int last_in_place;             // FAST + uniform footprint + Path: a lane's LAST sample is not retired through the regeneration
+                                 // queue — its radiance stays in PathRec.L and the film fold adds it (see lane_on_last_sample)
 };
+
+// FAST mode with the uniform footprint (tileSize 1: the lane's tile is one pixel) and P.last_in_place: is the sample the lane
+// is working on (index sidx) the last one of its share?  The lane's samples are s = sidx, sidx + s_mod, ... < spp.
+// Such a sample is never sent through the regeneration queue: nothing would be generated after it, and the only thing its
+// retirement does — pad += L (film_add_uniform) — is done by the film fold (k_group_sums / k_fold_last), which adds pad + L
+// in the same order.  With one sample per lane (config 2 on one B200: 63 lane groups) raygen then runs once per frame, and
+// 130 M PathRecs are not read and rewritten once more just to move 24 bytes inside them.
+GP_D bool lane_on_last_sample(const RenderParams& P, int sidx) {
+  const int s_mod = P.s_world * P.groups;
+  return P.last_in_place && sidx + (s_mod > 1 ? s_mod : 1) >= P.spp;
+}
 
 struct RenderCounters {
   unsigned long long camera_rays, closest_rays, shadow_rays, dead_mis_rays, radiance_gt10, nan_samples, unsupported, efloat_panics;
@@ -770,7 +783,7 @@ GP_D bool generate_lane(const DevScene& sc, const Lanes& L, const RenderParams& 
     }
     RayRec rr;
     rr.ox = ray.o.x; rr.oy = ray.o.y; rr.oz = ray.o.z; rr.dx = ray.d.x; rr.dy = ray.d.y; rr.dz = ray.d.z;
-    rr.tmax = d_inf(); rr.hit_rec = -1; rr.pad = 0;
+    rr.tmax = d_inf(); rr.hit_rec = -1; rr.pad = lane_on_last_sample(P, s.sidx) ? 1 : 0;  // see k_split_hits
     L.ray[lane] = rr;
     pt.fx = fx; pt.fy = fy;
     pt.Lr = 0; pt.Lg = 0; pt.Lb = 0;
@@ -782,6 +795,7 @@ GP_D bool generate_lane(const DevScene& sc, const Lanes& L, const RenderParams& 
     break;
   }
   pt.rng_state = s.state; pt.rng_inc = s.inc; pt.sidx = s.sidx; pt.pix = pix;
+  if (P.last_in_place && !go) { pt.Lr = 0; pt.Lg = 0; pt.Lb = 0; }  // no sample in flight: the film fold adds pad + L
   L.path[lane] = pt;
   return go;
 }
@@ -849,13 +863,14 @@ __global__ void __launch_bounds__(256) k_split_hits(Lanes L, Queues Q, const uns
     int lane = 0, rec = -1, cls = 0;
     if (valid) {
       lane = Q.extend[i];
-      if (codes) { int c = codes[i]; rec = c < 4 ? 0 : -1; cls = c; }  // filed by the extend kernel under the queue position
+      if (codes) { int c = codes[i]; rec = (c & 7) < 4 ? 0 : -1; cls = c; }  // filed by the extend kernel under the queue position
       else {
         int2 rc = *(const int2*)&L.ray[lane].hit_rec;  // {hit_rec, shade class}
         rec = rc.x; cls = rc.y;
       }
     }
-    int bin = !valid ? -1 : (rec >= 0 ? cls : 4);
+    // an escaped ray ends its sample; bit 3 = it was the lane's last sample, which stays in place (lane_on_last_sample)
+    int bin = !valid ? -1 : (rec >= 0 ? (cls & 3) : ((cls & 8) ? -1 : 4));
     unsigned m[5];
 #pragma unroll
     for (int k = 0; k < 5; k++) { m[k] = __ballot_sync(0xffffffffu, bin == k); if (lane_id == 0) s_cnt[warp][k] = __popc(m[k]); }
@@ -998,7 +1013,7 @@ GP_D void shade_lane(const DevScene& sc, const Lanes& L, const RenderParams& P, 
         if (alive) {
           RayRec nr;
           nr.ox = o.x; nr.oy = o.y; nr.oz = o.z; nr.dx = wi.x; nr.dy = wi.y; nr.dz = wi.z;
-          nr.tmax = d_inf(); nr.hit_rec = -1; nr.pad = 0;
+          nr.tmax = d_inf(); nr.hit_rec = -1; nr.pad = lane_on_last_sample(P, pt.sidx) ? 1 : 0;
           L.ray[lane] = nr;
           pt.br = beta.r; pt.bg = beta.g; pt.bb = beta.b;
           cont = true;
@@ -1011,6 +1026,7 @@ GP_D void shade_lane(const DevScene& sc, const Lanes& L, const RenderParams& P, 
   }
   pt.bounces = (packed & ~255) | bounces;
   L.path[lane] = pt;
+  if (finished && lane_on_last_sample(P, pt.sidx)) finished = false;  // stays in place: no trip through the regeneration queue
 }
 
 // ---------------------------------------------------------------- DirectLighting (pkg/integrator/directlighting.go)
@@ -1282,22 +1298,63 @@ __global__ void k_advance(Queues Q, RenderCounters* ctr, int* host_visible_remai
 // They are added up in ascending group order into group 0's record before the merge — a tile is ONE FilmTile whose samples
 // were accumulated by several partial sums, and MergeFilmTile converts it to XYZ once (film.go:115-132) — so that the merge
 // reads one record per tile instead of `groups` (32 groups: 5.8 -> about 1 ms per 1080p frame).
-__global__ void k_group_sums(Lanes L, RenderParams P) {
+// LAST (RenderParams.last_in_place): a lane's last sample was never retired by raygen; its radiance is still in PathRec.L and
+// is added here: group sum = pad + L', L' = L after renderWorker's NaN replacement (integrator.go:256-257) — the addition
+// film_add_uniform would have made, in the same place of the same order.  SINGLE: no lane has more than one sample, so
+// every pad is still +0 and only the L sector of each record is read.
+GP_D void last_sample_radiance(const PathRec* q, double& r, double& g, double& b, unsigned long long& nans) {
+  r = __ldcs(&q->Lr); g = __ldcs(&q->Lg); b = __ldcs(&q->Lb);
+  if (is_nan(r) || is_nan(g) || is_nan(b)) { r = g = b = 0.1; nans++; }
+  r = r * (1.0 * 1.0); g = g * (1.0 * 1.0); b = b * (1.0 * 1.0);  // L.MulScalar(sampleWeight * filterWeight)
+}
+template <bool LAST, bool SINGLE>
+__global__ void k_group_sums(Lanes L, RenderParams P, RenderCounters* ctr) {
   const long long n_tiles = P.lanes_active / P.groups;
+  unsigned long long nans = 0;
   for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n_tiles; t += (long long)gridDim.x * blockDim.x) {
     PathRec* base = L.path + t * P.groups;
-    double r = base->pad[0], g = base->pad[1], b = base->pad[2];
+    double r = 0, g = 0, b = 0;
+    if (!SINGLE) { r = base->pad[0]; g = base->pad[1]; b = base->pad[2]; }
+    if (LAST) { double lr, lg, lb; last_sample_radiance(base, lr, lg, lb, nans); r += lr; g += lg; b += lb; }
     int k = 1;
     for (; k + 8 <= P.groups; k += 8) {  // eight records' loads in flight, added in ascending order
       double x[8][3];
 #pragma unroll
-      for (int j = 0; j < 8; j++) { const double* q = base[k + j].pad; x[j][0] = __ldcs(q); x[j][1] = __ldcs(q + 1); x[j][2] = __ldcs(q + 2); }
+      for (int j = 0; j < 8; j++) {
+        const PathRec* q = base + k + j;
+        x[j][0] = x[j][1] = x[j][2] = 0;
+        if (!SINGLE) { x[j][0] = __ldcs(q->pad); x[j][1] = __ldcs(q->pad + 1); x[j][2] = __ldcs(q->pad + 2); }
+        if (LAST) { double lr, lg, lb; last_sample_radiance(q, lr, lg, lb, nans); x[j][0] += lr; x[j][1] += lg; x[j][2] += lb; }
+      }
 #pragma unroll
       for (int j = 0; j < 8; j++) { r += x[j][0]; g += x[j][1]; b += x[j][2]; }
     }
-    for (; k < P.groups; k++) { const PathRec* q = base + k; r += q->pad[0]; g += q->pad[1]; b += q->pad[2]; }
+    for (; k < P.groups; k++) {
+      const PathRec* q = base + k;
+      double xr = 0, xg = 0, xb = 0;
+      if (!SINGLE) { xr = q->pad[0]; xg = q->pad[1]; xb = q->pad[2]; }
+      if (LAST) { double lr, lg, lb; last_sample_radiance(q, lr, lg, lb, nans); xr += lr; xg += lg; xb += lb; }
+      r += xr; g += xg; b += xb;
+    }
     base->pad[0] = r; base->pad[1] = g; base->pad[2] = b;
   }
+  if (LAST) {
+    nans = warp_sum(nans);
+    if ((threadIdx.x & 31) == 0 && nans) atomicAdd(&ctr->nan_samples, nans);
+  }
+}
+// last_in_place when the lane groups of a pass cannot be folded per tile (a pass that does not hold whole tiles): every lane
+// retires its last sample into its own pad
+__global__ void k_fold_last(Lanes L, RenderParams P, RenderCounters* ctr) {
+  unsigned long long nans = 0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < P.lanes_active; i += (long long)gridDim.x * blockDim.x) {
+    PathRec* q = L.path + i;
+    double lr, lg, lb;
+    last_sample_radiance(q, lr, lg, lb, nans);
+    q->pad[0] += lr; q->pad[1] += lg; q->pad[2] += lb;
+  }
+  nans = warp_sum(nans);
+  if ((threadIdx.x & 31) == 0 && nans) atomicAdd(&ctr->nan_samples, nans);
 }
 
 // Film.MergeFilmTile (film.go:115-132): every film pixel gathers the tiles that cover it in ascending tile order

@@ -33,11 +33,14 @@ struct __align__(32) ShadowRec {  // shade -> shadow: the visibility segment + t
   int gt10, pad;
   double pad2[2];
 };
-struct __align__(32) PathRec {    // Path.Li loop state + sampler stream of the lane.  128 B = 4 sectors
-  double br, bg, bb, Lr, Lg, Lb, eta_scale, fx, fy;
+struct __align__(32) PathRec {    // Path.Li loop state + sampler stream of the lane.  128 B = 4 sectors, grouped by who touches them:
+  double Lr, Lg, Lb, eta_scale;   // sector 0: the radiance sum — the ONE sector the shadow stage reads and writes, and the film fold reads
+  double br, bg, bb, fx;          // sector 1: throughput
+  double fy;                      // sector 2: sampler stream
   unsigned long long rng_state, rng_inc;
-  int bounces, pix, sidx, has_sample;
-  double pad[3];
+  int bounces, sidx;
+  int pix, has_sample;            // sector 3
+  double pad[3];                  //           uniform footprint: the lane's FilmTile as one RGB sum (film_add_uniform)
 };
 static_assert(sizeof(RayRec) == 64 && sizeof(ShadowRec) == 96 && sizeof(PathRec) == 128, "lane record layout");
 
@@ -233,6 +236,9 @@ __global__ void __launch_bounds__(kTraceThreads, QUADRICS ? GP_TRACE_BLOCKS : GP
             ray.o = mk3(a.x, a.y, b.x);
             ray.d = mk3(b.y, c2.x, c2.y);
             ray.tmax = d2.x;
+            // RayRec.pad bit 0 ("the lane's last sample", gp_render.cuh lane_on_last_sample) travels as bit 3 of the shade
+            // class and comes out with a MISS (a hit overwrites it: the shade stage works it out from the PathRec)
+            if (MODE == 0) rec_cls = (int)((unsigned long long)__double_as_longlong(d2.y) >> 32 & 1ULL) << 3;
           }
           invd = mk3(1 / ray.d.x, 1 / ray.d.y, 1 / ray.d.z);  // bvh.go:665-666
           nx = invd.x < 0; ny = invd.y < 0; nz = invd.z < 0;
@@ -366,7 +372,7 @@ __global__ void __launch_bounds__(kTraceThreads, QUADRICS ? GP_TRACE_BLOCKS : GP
         ((double2*)(rays + lane))[3] = out;
         // MODE 0 with `occluded` set: one byte per QUEUE POSITION — shade class 0..3 of the hit, 4 = escaped — so that
         // the split stage streams over the queue and never touches the ray records
-        if (occluded) occluded[qpos] = rec >= 0 ? (unsigned char)rec_cls : (unsigned char)4;
+        if (occluded) occluded[qpos] = rec >= 0 ? (unsigned char)rec_cls : (unsigned char)(4 | rec_cls);
       } else if (MODE == 1 || MODE == 3) {
         occluded[lane] = hit_any ? 1 : 0;
       } else {
@@ -430,6 +436,7 @@ __global__ void __launch_bounds__(kTraceThreads, 4) k_trace_flat(DevScene sc, Ra
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const long long lane = queue ? queue[i] : i;
     Ray ray;
+    int last_bit = 0;
     if (MODE >= 2) {
       const double2* q = (const double2*)(srays + lane);
       double2 a = q[0], b = q[1], c2 = q[2];
@@ -442,6 +449,7 @@ __global__ void __launch_bounds__(kTraceThreads, 4) k_trace_flat(DevScene sc, Ra
       ray.o = mk3(a.x, a.y, b.x);
       ray.d = mk3(b.y, c2.x, c2.y);
       ray.tmax = d2.x;
+      if (MODE == 0) last_bit = (int)((unsigned long long)__double_as_longlong(d2.y) >> 32 & 1ULL) << 3;  // see k_trace
     }
     const V3 invd = mk3(1 / ray.d.x, 1 / ray.d.y, 1 / ray.d.z);  // bvh.go:665-666
     const int nx = invd.x < 0, ny = invd.y < 0, nz = invd.z < 0;
@@ -454,7 +462,7 @@ __global__ void __launch_bounds__(kTraceThreads, 4) k_trace_flat(DevScene sc, Ra
         mask |= (unsigned long long)slab_test_f32_maybe(s_tab[2 * k], s_tab[2 * k + 1], rf, nx, ny, nz, tmax_ub) << k;
       if (COUNT) c.nodes += nf;
     }
-    int rec = -1, rec_cls = 0;
+    int rec = -1, rec_cls = last_bit;
     bool hit_any = false;
     double t_best = ray.tmax;  // see closer_hit: ray.tmax keeps the original tMax
     // triangles
@@ -518,7 +526,7 @@ __global__ void __launch_bounds__(kTraceThreads, 4) k_trace_flat(DevScene sc, Ra
       out.x = t_best;
       out.y = __longlong_as_double((long long)(((unsigned long long)(unsigned)rec_cls << 32) | (unsigned)rec));
       ((double2*)(rays + lane))[3] = out;
-      if (occluded) occluded[i] = rec >= 0 ? (unsigned char)rec_cls : (unsigned char)4;
+      if (occluded) occluded[i] = rec >= 0 ? (unsigned char)rec_cls : (unsigned char)(4 | rec_cls);
     } else if (MODE == 1 || MODE == 3) {
       occluded[lane] = hit_any ? 1 : 0;
     } else {
