@@ -301,6 +301,36 @@ GP_HD bool tri_test_pre(V3 p0, V3 p1, V3 p2, const Ray& ray, const TriRay& tr, d
   if (bary) { bary[0] = e0 * invDet; bary[1] = e1 * invDet; bary[2] = e2 * invDet; }
   return true;
 }
+// The same test with the vertices read through the permutation: v = the triangle's nine coordinates {p0, p1, p2} in memory
+// (the flat aggregate keeps them in shared memory), fetched as v[kx], v[ky], v[kz] — nine indexed loads instead of five
+// vector loads and 27 mask operations on 64-bit patterns; permute(p - o) == permute(p) - permute(o) component by component,
+// so every subtraction is the one tri_test_pre makes.
+GP_D bool tri_test_idx(const double* v, const Ray& ray, const TriRay& tr, double* tHit) {
+  const int kx = tr.kx, ky = tr.ky, kz = tr.kz;
+  const V3 o = permute_cyclic(ray.o, kz);
+  V3 p0t = mk3(v[kx] - o.x, v[ky] - o.y, v[kz] - o.z);
+  V3 p1t = mk3(v[3 + kx] - o.x, v[3 + ky] - o.y, v[3 + kz] - o.z);
+  V3 p2t = mk3(v[6 + kx] - o.x, v[6 + ky] - o.y, v[6 + kz] - o.z);
+  double Sx = tr.Sx, Sy = tr.Sy, Sz = tr.Sz;
+  p0t.x += Sx * p0t.z; p0t.y += Sy * p0t.z;
+  p1t.x += Sx * p1t.z; p1t.y += Sy * p1t.z;
+  p2t.x += Sx * p2t.z; p2t.y += Sy * p2t.z;
+  double e0 = p1t.x * p2t.y - p1t.y * p2t.x;
+  double e1 = p2t.x * p0t.y - p2t.y * p0t.x;
+  double e2 = p0t.x * p1t.y - p0t.y * p1t.x;
+  if (((e0 < 0) | (e1 < 0) | (e2 < 0)) & ((e0 > 0) | (e1 > 0) | (e2 > 0))) return false;
+  double det = e0 + e1 + e2;
+  if (det == 0) return false;
+  p0t.z *= Sz; p1t.z *= Sz; p2t.z *= Sz;
+  double tScaled = e0 * p0t.z + e1 * p1t.z + e2 * p2t.z;
+  if (det < 0 && (tScaled >= 0 || tScaled < ray.tmax * det)) return false;
+  if (det > 0 && (tScaled <= 0 || tScaled > ray.tmax * det)) return false;
+  double invDet = 1 / det;
+  double t = tScaled * invDet;
+  if (t <= 0 || t >= ray.tmax) return false;
+  *tHit = t;
+  return true;
+}
 GP_HD bool tri_test(V3 p0, V3 p1, V3 p2, const Ray& ray, double* tHit, double* bary) {
   return tri_test_pre(p0, p1, p2, ray, tri_ray_setup(ray.d), tHit, bary);
 }

@@ -425,8 +425,25 @@ __global__ void __launch_bounds__(kTraceThreads, 4) k_trace_flat(DevScene sc, Ra
                                                                  int stack_cap, int* work_counter, TraceCounters* ctr, unsigned long long* gt10_counter) {
   constexpr bool ANY = MODE != 0;
   __shared__ float4 s_tab[2 * kFlatMax];
+  __shared__ double s_bnd[kFlatMax][6];  // every entry's own float64 world bound (a triangle's: the min / max of its vertices)
+  __shared__ double s_vtx[kFlatMax][9];  // a triangle entry's vertices: the watertight test reads them ALREADY PERMUTED (tri_test_idx)
   const int nf = sc.n_flat;
   for (int i = threadIdx.x; i < 2 * nf; i += blockDim.x) s_tab[i] = sc.flat[i];
+  for (int k = threadIdx.x; k < nf; k += blockDim.x) {
+    const unsigned ri = __float_as_uint(sc.flat[2 * k].w);
+    if ((sc.flat_tri_mask >> k) & 1ULL) {
+      const double* d = sc.recs[ri].d;
+      for (int a = 0; a < 3; a++) {
+        const double v0 = d[a], v1 = d[3 + a], v2 = d[6 + a];
+        double lo = v0 < v1 ? v0 : v1, hi = v0 < v1 ? v1 : v0;
+        lo = v2 < lo ? v2 : lo; hi = v2 > hi ? v2 : hi;
+        s_bnd[k][a] = lo; s_bnd[k][3 + a] = hi;
+      }
+      for (int a = 0; a < 9; a++) s_vtx[k][a] = d[a];
+    } else {
+      for (int a = 0; a < 6; a++) s_bnd[k][a] = sc.rec_bounds[(size_t)ri * 6 + a];
+    }
+  }
   __syncthreads();
   const long long n = queue ? (long long)*count : n_direct;
   const unsigned long long tri_mask = sc.flat_tri_mask;
@@ -474,17 +491,12 @@ __global__ void __launch_bounds__(kTraceThreads, 4) k_trace_flat(DevScene sc, Ra
         m &= m - 1;
         const float4 t0 = s_tab[2 * k], t1 = s_tab[2 * k + 1];
         if (!ANY && hit_any && !slab_test_f32_maybe(t0, t1, rf, nx, ny, nz, tmax_ub)) continue;  // behind the hit found meanwhile
-        const unsigned ri = __float_as_uint(t0.w);
-        const double2* q = (const double2*)(sc.recs + ri);
-        double2 v0 = q[0], v1 = q[1], v2 = q[2], v3 = q[3], v4 = q[4];
-        V3 p0 = mk3(v0.y, v1.x, v1.y), p1 = mk3(v2.x, v2.y, v3.x), p2 = mk3(v3.y, v4.x, v4.y);
-        double x0 = p0.x < p1.x ? p0.x : p1.x, x1 = p0.x < p1.x ? p1.x : p0.x; x0 = p2.x < x0 ? p2.x : x0; x1 = p2.x > x1 ? p2.x : x1;
-        double y0 = p0.y < p1.y ? p0.y : p1.y, y1 = p0.y < p1.y ? p1.y : p0.y; y0 = p2.y < y0 ? p2.y : y0; y1 = p2.y > y1 ? p2.y : y1;
-        double z0 = p0.z < p1.z ? p0.z : p1.z, z1 = p0.z < p1.z ? p1.z : p0.z; z0 = p2.z < z0 ? p2.z : z0; z1 = p2.z > z1 ? p2.z : z1;
-        if (!slab_test(x0, y0, z0, x1, y1, z1, ray.o, invd, nx, ny, nz, cull_tmax(hit_any, t_best, ray.tmax))) continue;
+        const double* bb = s_bnd[k];
+        if (!slab_test(bb[0], bb[1], bb[2], bb[3], bb[4], bb[5], ray.o, invd, nx, ny, nz, cull_tmax(hit_any, t_best, ray.tmax))) continue;
         if (COUNT) { c.prims++; c.tri++; }
+        const unsigned ri = __float_as_uint(t0.w);
         double t;
-        if (tri_test_pre(p0, p1, p2, ray, tray, &t, nullptr)) {
+        if (tri_test_idx(s_vtx[k], ray, tray, &t)) {
           if (ANY) { hit_any = true; break; }
           if (closer_hit(sc, t, ri, t_best, rec)) {
             hit_any = true;
@@ -505,7 +517,7 @@ __global__ void __launch_bounds__(kTraceThreads, 4) k_trace_flat(DevScene sc, Ra
       if (!ANY && hit_any && !slab_test_f32_maybe(t0, t1, rf, nx, ny, nz, tmax_ub)) continue;
       const unsigned ri = __float_as_uint(t0.w);
       const uint32_t flags = __float_as_uint(t1.w);
-      const double* bb = sc.rec_bounds + (size_t)ri * 6;
+      const double* bb = s_bnd[k];
       if (!slab_test(bb[0], bb[1], bb[2], bb[3], bb[4], bb[5], ray.o, invd, nx, ny, nz, cull_tmax(hit_any, t_best, ray.tmax))) continue;
       if (COUNT) { c.prims++; if (flags & RF_FAST) c.sph++; else c.gen++; }
       double t;
