@@ -143,6 +143,30 @@ GP_HD_NOINLINE static double go_sin(double x) {
   y = (j == 1 || j == 2) ? poly_cos(zz) : poly_sin(z, zz);
   return sign ? -y : y;
 }
+// math.Sin(x) and math.Cos(x) of the SAME argument (the sampling warps take both of one angle): sin.go's two functions make the
+// same range reduction — |x|, the octant j, the three-term Cody-Waite remainder z — and each then evaluates one of the same
+// two polynomials.  Here the reduction and both polynomials are computed once and each result selects its own; every value is
+// produced by exactly the operations its own function performs, so both are bit-identical to go_sin / go_cos, at half the
+// arithmetic and without the octant branch (a warp's lanes fall in different octants: both polynomials ran anyway, twice).
+GP_HD_NOINLINE static void go_sincos(double x, double* sn, double* cs) {
+  const double qnan = b2f(0x7ff8000000000001ULL);
+  const double xa = fabs(x);
+  uint64_t j = (uint64_t)(long long)(xa * GP_M4PI);
+  double y = (double)(long long)j;
+  if (j & 1) { j++; y++; }
+  j &= 7;
+  bool sign_s = x < 0, sign_c = false;
+  if (j > 3) { j -= 4; sign_s = !sign_s; sign_c = !sign_c; }
+  if (j > 1) sign_c = !sign_c;
+  const double z = ((xa - y * GP_PI4A) - y * GP_PI4B) - y * GP_PI4C;
+  const double zz = z * z;
+  const double ps = poly_sin(z, zz), pc = poly_cos(zz);
+  const bool swap = (j == 1 || j == 2);
+  const double ys = swap ? pc : ps, yc = swap ? ps : pc;
+  const bool bad = is_nan(x) || is_inf(x);
+  *cs = bad ? qnan : (sign_c ? -yc : yc);
+  *sn = (x == 0 || is_nan(x)) ? x : (is_inf(x) ? qnan : (sign_s ? -ys : ys));
+}
 // ---- Go src/math/atan.go (Cephes atan.c) ----
 GP_HD double go_xatan(double x) {
   double z = x * x;

@@ -235,8 +235,10 @@ GP_D void concentric_sample_disk(double ux, double uy, double* ox, double* oy) {
   double theta, r;
   if (fabs(x) > fabs(y)) { r = x; theta = kPiOver4 * (y / x); }
   else { r = y; theta = kPiOver2 - kPiOver4 * (x / y); }
-  *ox = go_cos(theta) * r;
-  *oy = go_sin(theta) * r;
+  double sn, cs;
+  go_sincos(theta, &sn, &cs);
+  *ox = cs * r;
+  *oy = sn * r;
 }
 GP_D V3 cosine_sample_hemisphere(double ux, double uy) {
   double dx, dy;
@@ -248,7 +250,9 @@ GP_D V3 uniform_sample_sphere(double ux, double uy) {
   double z = 1.0 - 2.0 * ux;
   double r = sqrt(go_max(0, 1 - z * z));
   double phi = 2 * kPi * uy;
-  return mk3(r * go_cos(phi), r * go_sin(phi), z);
+  double sn, cs;
+  go_sincos(phi, &sn, &cs);
+  return mk3(r * cs, r * sn, z);
 }
 
 // ---------------------------------------------------------------- spectrum helpers (pkg/pbrt/spectrum.go)
@@ -528,7 +532,9 @@ __device__ __noinline__ static void sphere_sample_at(const DevScene& sc, const S
   double cosAlpha = (dc * dc + radius2 - ds * ds) / (2.0 * dc * s.radius);
   double sinAlpha = sqrt(go_max(0, 1.0 - cosAlpha * cosAlpha));
   V3 x = wcX * -1.0, y = wcY * -1.0, z = wc * -1.0;
-  V3 nWorld = x * (sinAlpha * go_cos(phi)) + y * (sinAlpha * go_sin(phi)) + z * cosAlpha;  // geometry.go:66-70
+  double snPhi, csPhi;
+  go_sincos(phi, &snPhi, &csPhi);
+  V3 nWorld = x * (sinAlpha * csPhi) + y * (sinAlpha * snPhi) + z * cosAlpha;  // geometry.go:66-70
   V3 pWorld = pCenter + nWorld * s.radius;
   it->p = pWorld;
   it->perr = vabs(pWorld) * gamma_n(5.0);
