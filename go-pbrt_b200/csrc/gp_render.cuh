@@ -116,6 +116,48 @@ GP_D void block_push(int* const (&q)[NQ], int* const (&cnt)[NQ], const bool (&pr
   __syncthreads();
 }
 
+// The same for U entries per thread at once.  A CTA-wide push costs three barriers, and a barrier costs the spread of its
+// warps' arrival times — in the raygen and shade kernels, whose warps run hundreds to thousands of instructions between two
+// pushes at their own pace, a quarter / an eighth of all stall samples (ncu).  So a raygen thread works through U queue entries
+// (the CTA through U * blockDim consecutive ones), keeps what it wants pushed — values in shared memory, the predicates as a
+// bit mask, bit u * NQ + k for entry u and queue k — and the CTA pushes once per batch: the barriers are paid once per U lanes,
+// and the CTA's run in the output queue is U times longer, in input order (entry-major, then thread order).
+constexpr int kPushBatch = 4;
+template <int NQ, int U>
+struct PushBatch {
+  int cnt[U][8][NQ];   // [entry][warp][queue] number of pushes
+  int off[U][8][NQ];   // exclusive prefix of cnt in (entry, warp) order
+  int base[NQ];
+  int val[U][256];     // [entry][thread] the value to push
+};
+template <int NQ, int U>
+GP_D void block_push_batch(int* const (&q)[NQ], int* const (&cnt)[NQ], unsigned flags, PushBatch<NQ, U>& S) {
+  const unsigned FULL = 0xffffffffu;
+  const int lane_id = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  unsigned m[U][NQ];
+#pragma unroll
+  for (int u = 0; u < U; u++)
+#pragma unroll
+    for (int k = 0; k < NQ; k++) {
+      m[u][k] = __ballot_sync(FULL, (flags >> (u * NQ + k)) & 1u);
+      if (lane_id == 0) S.cnt[u][warp][k] = __popc(m[u][k]);
+    }
+  __syncthreads();
+  if (threadIdx.x < NQ) {  // one thread per queue: the prefix over (entry, warp) and the queue's one atomic
+    int tot = 0;
+    for (int u = 0; u < U; u++)
+      for (int w2 = 0; w2 < nwarps; w2++) { S.off[u][w2][threadIdx.x] = tot; tot += S.cnt[u][w2][threadIdx.x]; }
+    S.base[threadIdx.x] = tot ? atomicAdd(cnt[threadIdx.x], tot) : 0;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int u = 0; u < U; u++)
+#pragma unroll
+    for (int k = 0; k < NQ; k++)
+      if ((flags >> (u * NQ + k)) & 1u) q[k][S.base[k] + S.off[u][warp][k] + __popc(m[u][k] & ((1u << lane_id) - 1u))] = S.val[u][threadIdx.x];
+  __syncthreads();
+}
+
 // ---------------------------------------------------------------- RNG (pkg/pbrt/rng.go — a PCG32 *variant*)
 struct Smp {
   unsigned long long state, inc;
@@ -827,21 +869,21 @@ __global__ void __launch_bounds__(128, GP_GEN_BLOCKS) k_generate(DevScene sc, La
   long long n = in_queue ? (long long)*in_count : P.lanes_active;
   int lane_id = threadIdx.x & 31;
   unsigned long long cam = 0, nans = 0, culled = 0;
-  __shared__ int s_cnt[4][1];
-  __shared__ int s_base[1];
-  for (long long cbase = (long long)blockIdx.x * blockDim.x; cbase < n; cbase += (long long)gridDim.x * blockDim.x) {
-    long long i = cbase + threadIdx.x;
-    bool valid = i < n;
-    bool go = false;
-    long long lane = 0;
-    if (valid) {
-      lane = in_queue ? in_queue[i] : i;
-      go = generate_lane(sc, L, P, lane, in_queue != nullptr, cam, nans, culled);
+  __shared__ PushBatch<1, kPushBatch> s_push;
+  for (long long cbase = (long long)blockIdx.x * blockDim.x * kPushBatch; cbase < n; cbase += (long long)gridDim.x * blockDim.x * kPushBatch) {
+    unsigned flags = 0;
+#pragma unroll 1
+    for (int u = 0; u < kPushBatch; u++) {
+      const long long i = cbase + (long long)u * blockDim.x + threadIdx.x;
+      if (i < n) {
+        const long long lane = in_queue ? in_queue[i] : i;
+        if (generate_lane(sc, L, P, lane, in_queue != nullptr, cam, nans, culled)) flags |= 1u << u;
+        s_push.val[u][threadIdx.x] = (int)lane;
+      }
     }
     int* const qs[1] = {Q.extend};
     int* const cs[1] = {Q.cnt + 0};
-    const bool ps[1] = {go};
-    block_push<1>(qs, cs, ps, (int)lane, s_cnt, s_base);
+    block_push_batch<1, kPushBatch>(qs, cs, flags, s_push);
   }
   cam = warp_sum(cam); nans = warp_sum(nans); culled = warp_sum(culled);
   if (lane_id == 0) {
@@ -1246,6 +1288,7 @@ __global__ void __launch_bounds__(128, ShadeBlocks<CLS>::value) k_shade(DevScene
   int lane_id = threadIdx.x & 31;
   unsigned long long n_unsupported = 0, n_dead = 0;
   int bad = 0;
+  // (per-lane pushes: batching them as raygen does bought nothing here on config 2 and cost 4-15 % on the sphere shade classes)
   __shared__ int s_cnt[4][3];
   __shared__ int s_base[3];
   for (long long cbase = (long long)blockIdx.x * blockDim.x; cbase < n; cbase += (long long)gridDim.x * blockDim.x) {
