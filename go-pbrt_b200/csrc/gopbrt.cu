@@ -284,8 +284,9 @@ struct HostScene {
   gpbvh::Result bvh;
   std::vector<PrimRec> recs;
   std::vector<double> rec_bounds;
-  std::vector<gpbvh::Node32> flat;
+  std::vector<gpbvh::Node32> flat;  // the flat aggregate's entries, then its box groups (n_flat_groups records)
   unsigned long long flat_tri_mask = 0;
+  int n_flat_entries = 0, n_flat_groups = 0;
   std::vector<MaterialDev> mats;
   std::vector<TextureDev> texs;
   std::vector<LightDev> lights;
@@ -546,6 +547,19 @@ static int build_host_scene(const gopbrt_scene_desc* d, HostScene& H, std::strin
         if (tri) flat_tri_mask |= 1ULL << flat.size();
         flat.push_back(e);
       }
+    // Box groups: entries whose float32 boxes are bit-identical (the two triangles of an axis-aligned or upright quad) are
+    // tested ONCE in the kernel's warp-uniform loop; a group record is {box, a | b << 32 = the mask of its entries}.
+    H.n_flat_entries = (int)flat.size();
+    std::vector<gpbvh::Node32> groups;
+    for (int k = 0; k < H.n_flat_entries; k++) {
+      size_t g = 0;
+      for (; g < groups.size(); g++)
+        if (memcmp(groups[g].mn, flat[k].mn, sizeof(float) * 3) == 0 && memcmp(groups[g].mx, flat[k].mx, sizeof(float) * 3) == 0) break;
+      if (g == groups.size()) { gpbvh::Node32 e = flat[k]; e.a = 0; e.b = 0; groups.push_back(e); }
+      if (k < 32) groups[g].a |= 1u << k; else groups[g].b |= 1u << (k - 32);
+    }
+    H.n_flat_groups = (int)groups.size();
+    flat.insert(flat.end(), groups.begin(), groups.end());
   }
 
   // ---- materials / textures / lights
@@ -757,7 +771,7 @@ static int upload_scene(gopbrt_ctx* ctx, HostScene& H, gopbrt_scene** out) {
   D.xf = sc->xf.p; D.xf_flags = sc->xf_flags.p; D.spheres = sc->spheres.p; D.disks = sc->disks.p;
   D.materials = sc->materials.p; D.textures = sc->textures.p; D.lights = sc->lights.p; D.light_cdf = sc->light_cdf.p;
   D.n_lights = nl; D.light_func_int = func_int; D.n_nodes = H.device_build ? (int)dev_records : (int)nodes.size();
-  D.flat = (const float4*)sc->flat.p; D.n_flat = (int)flat.size(); D.flat_tri_mask = flat_tri_mask;
+  D.flat = (const float4*)sc->flat.p; D.n_flat = H.n_flat_entries; D.n_flat_groups = H.n_flat_groups; D.flat_tri_mask = flat_tri_mask;
   // Distant.Preprocess → Bounds3.BoundingSphere (distant.go:36-38, bounds.go:105-112)
   D.world_radius = 0;
   if (world.valid) {

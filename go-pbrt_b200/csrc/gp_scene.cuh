@@ -59,8 +59,8 @@ struct DevScene {
   int n_nodes;
   // flat aggregate of small scenes (k_trace_flat): per primitive two float4 {min.xyz f32 rounded down, record index},
   // {max.xyz f32 rounded up, record flags}; triangles first (bit k of flat_tri_mask set), then spheres / disks
-  const float4* flat;
-  int n_flat;
+  const float4* flat;   // n_flat entries, then n_flat_groups box groups {box, mask of the entries that share it}
+  int n_flat, n_flat_groups;
   unsigned long long flat_tri_mask;
 };
 

@@ -425,10 +425,12 @@ __global__ void __launch_bounds__(kTraceThreads, 4) k_trace_flat(DevScene sc, Ra
                                                                  int stack_cap, int* work_counter, TraceCounters* ctr, unsigned long long* gt10_counter) {
   constexpr bool ANY = MODE != 0;
   __shared__ float4 s_tab[2 * kFlatMax];
+  __shared__ float4 s_grp[2 * kFlatMax];  // the distinct boxes of the table, each with the mask of the entries that have it
   __shared__ double s_bnd[kFlatMax][6];  // every entry's own float64 world bound (a triangle's: the min / max of its vertices)
   __shared__ double s_vtx[kFlatMax][9];  // a triangle entry's vertices: the watertight test reads them ALREADY PERMUTED (tri_test_idx)
-  const int nf = sc.n_flat;
+  const int nf = sc.n_flat, ng = sc.n_flat_groups;
   for (int i = threadIdx.x; i < 2 * nf; i += blockDim.x) s_tab[i] = sc.flat[i];
+  for (int i = threadIdx.x; i < 2 * ng; i += blockDim.x) s_grp[i] = sc.flat[2 * nf + i];
   for (int k = threadIdx.x; k < nf; k += blockDim.x) {
     const unsigned ri = __float_as_uint(sc.flat[2 * k].w);
     if ((sc.flat_tri_mask >> k) & 1ULL) {
@@ -475,9 +477,12 @@ __global__ void __launch_bounds__(kTraceThreads, 4) k_trace_flat(DevScene sc, Ra
     unsigned long long mask = 0;
     if (ray.tmax > 0) {  // see k_trace: a ray with tMax <= 0 (or NaN) cannot hit anything
 #pragma unroll 4
-      for (int k = 0; k < nf; k++)
-        mask |= (unsigned long long)slab_test_f32_maybe(s_tab[2 * k], s_tab[2 * k + 1], rf, nx, ny, nz, tmax_ub) << k;
-      if (COUNT) c.nodes += nf;
+      for (int g = 0; g < ng; g++) {  // one test per DISTINCT box (the two triangles of a quad mostly share theirs)
+        const float4 g0 = s_grp[2 * g], g1 = s_grp[2 * g + 1];
+        const unsigned long long gm = ((unsigned long long)__float_as_uint(g1.w) << 32) | __float_as_uint(g0.w);
+        mask |= slab_test_f32_maybe(g0, g1, rf, nx, ny, nz, tmax_ub) ? gm : 0ULL;
+      }
+      if (COUNT) c.nodes += ng;
     }
     int rec = -1, rec_cls = last_bit;
     bool hit_any = false;
