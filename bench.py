@@ -384,6 +384,48 @@ def main():
                 "per_ray": {"nodes_visited": (cst["nodes_visited"] - cst["root_culled_rays"]) / max(1, ext_rays),
                             "shape_tests": cst["prim_tests"] / max(1, ext_rays)},
                 "stage_ms_per_step": {k: sum(s[k] for s in stage_stats) / KS for k in ("ms_raygen", "ms_extend", "ms_shade", "ms_shadow", "ms_film")}}
+        # ---- the kernel that dominates THIS frame.  On the headline workload (36 primitives: the aggregate is a shared-memory table)
+        # that is the shade stage, whose bytes all come from and go to HBM: per shaded lane it reads the lane's PathRec (128 B),
+        # RayRec (64 B) and queue entry (4 B) and writes the PathRec back (128 B); a lane that continues writes a new RayRec and
+        # its queue entry (64 + 4 B), a lane with a light sample a ShadowRec and its queue entry (96 + 4 B) — DESIGN.md §4.
+        # (ms_shade = k_split_hits + the shade-class kernels of every iteration.)  The extend kernel stays on the line as
+        # roofline_extend: its SURVEY §8d "algorithmic bytes" are table bytes that never leave the SM here, so their rate is not
+        # a fraction of an HBM roof — for the HBM-resident tree see roofline_deep_bvh.
+        s_shade = sum(s["ms_shade"] for s in stage_stats)
+        st0 = stage_stats[0]
+        if s_shade > s_ext and st0.get("shaded_lanes", 0) > 0:
+            roof_ext = dict(roof)
+            if small:
+                roof_ext["bound"] = "issue / SIMT divergence (on-chip table)"
+                roof_ext["algorithmic_GBps"] = roof_ext.pop("achieved")
+                roof_ext.pop("frac", None)
+            cont_lanes = st0["closest_rays"] - st0["camera_rays"]  # every closest-hit query that is not a camera ray was spawned by a shade lane
+            n_iter = st0["iterations"]
+            n_cls = max(1, round((st0["launches"] - 3) / max(1, n_iter)) - 5)  # shade-class launches per iteration (launches per iteration = 5 + classes)
+            by_shade = st0["shaded_lanes"] * (128 + 64 + 4 + 128) + cont_lanes * (64 + 4) + st0["shadow_rays"] * (96 + 4)
+            n_sh = n_iter * n_cls * KS
+            ach = by_shade * KS / (s_shade / 1e3) / 1e9
+            traffic_sh, traffic_sh_src = None, "no ncu capture of this workload under profiles/"
+            try:
+                tj = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic_shade.json")))
+                if tj.get("workload") == args.config:
+                    traffic_sh = tj["dram_bytes_per_shaded_lane"] * st0["shaded_lanes"] / max(1, n_iter * n_cls)
+                    traffic_sh_src = ("profiles/r02_traffic_shade.json: %.1f DRAM bytes per shaded lane over the shade-class launches of one "
+                                      "wavefront iteration in one ncu --set full capture, scaled to this run's lanes per launch - not measured in this run"
+                                      % tj["dram_bytes_per_shaded_lane"])
+            except Exception:
+                pass
+            roof = {"bound": "hbm", "kernel": "k_shade (+ k_split_hits): one Path.Li loop body per lane on its HBM-resident lane records",
+                    "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                    "peak_source": roof_ext["peak_source"], "traffic": traffic_sh, "traffic_source": traffic_sh_src,
+                    "limiter": "dependent float64 chains at 16 resident warps per SM (128-168 registers): issue slots 33 % busy, long-scoreboard 5 of 12 stall cycles per issue (profiles/r02b_ncu_stage_kernels.md)",
+                    "bytes_per_launch": by_shade * KS / max(1, n_sh), "ms_per_launch": s_shade / max(1, n_sh), "launches": n_sh,
+                    "bytes_per_unit": "324 B per shaded lane + 68 B per continuing lane + 100 B per shadow ray",
+                    "units_per_step": {"shaded_lanes": st0["shaded_lanes"], "continuing_lanes": cont_lanes, "shadow_rays": st0["shadow_rays"]},
+                    "measured_over": roof_ext["measured_over"],
+                    "stage_ms_per_step": roof_ext["stage_ms_per_step"]}
+        else:
+            roof_ext = None
         lane_bytes = 64 + 96 + 128 + 36 + 1 + (0 if mode == abi.MODE_FAST else 4 * wl["spp"][0] * wl["spp"][1] * 8)
         line = {"metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": K, "warmup": max(args.min_warmup, args.warmup),
                 "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
@@ -401,6 +443,7 @@ def main():
                         "ms_per_step": e2e_total / K * 1e3, "host_buffer": "pinned", **e2e_parts,
                         "pageable_host_buffer": {"value": rays_total / K / e2e_pageable / 1e6, "ms_per_step": e2e_pageable * 1e3, "steps": n_pageable}},
                 "gpu_launches": int(launches_total), "clocks": clocks.summary(), "roofline": roof,
+                **({"roofline_extend": roof_ext} if roof_ext else {}),
                 "reference_panics": {"radiance_gt10": stats[0]["radiance_gt10"], "efloat_panics": stats[0]["efloat_panics"],
                                      "nan_samples": stats[0]["nan_samples"]}}
     if world == 1 and mode == abi.MODE_FAST:

@@ -114,7 +114,7 @@ class Stats(C.Structure):
                 ("bvh_nodes", C.c_uint64), ("bvh_depth", C.c_uint64), ("tests_triangle", C.c_uint64),
                 ("tests_sphere_fast", C.c_uint64), ("tests_general", C.c_uint64), ("extend_launches", C.c_uint64),
                 ("shadow_launches", C.c_uint64), ("shadow_tests_triangle", C.c_uint64),
-                ("shadow_tests_sphere_fast", C.c_uint64), ("shadow_tests_general", C.c_uint64), ("reserved0", C.c_uint64),
+                ("shadow_tests_sphere_fast", C.c_uint64), ("shadow_tests_general", C.c_uint64), ("shaded_lanes", C.c_uint64),
                 ("ms_reduce", C.c_double), ("root_culled_rays", C.c_uint64)]
 
     def as_dict(self):

@@ -1351,6 +1351,7 @@ static int render_impl(gopbrt_scene* sc, const gopbrt_camera* cam, const gopbrt_
     stats->tests_triangle = tcnt.t_tri; stats->tests_sphere_fast = tcnt.t_sph; stats->tests_general = tcnt.t_gen;
     stats->extend_launches = n_extend; stats->shadow_launches = n_shadow;
     stats->root_culled_rays = rcnt.root_culled;
+    stats->shaded_lanes = rcnt.shaded;
     stats->shadow_tests_triangle = tcnt.st_tri; stats->shadow_tests_sphere_fast = tcnt.st_sph; stats->shadow_tests_general = tcnt.st_gen;
     if (timing && iter_log_path) {
       FILE* fp = fopen(iter_log_path, "w");
@@ -1627,7 +1628,7 @@ extern "C" int gopbrt_multi_render(gopbrt_multi_scene* ms, const gopbrt_camera* 
       t.shadow_prim_tests += s.shadow_prim_tests; t.radiance_gt10 += s.radiance_gt10; t.nan_samples += s.nan_samples;
       t.efloat_panics += s.efloat_panics; t.stack_overflows += s.stack_overflows; t.launches += s.launches; t.lanes += s.lanes;
       t.tests_triangle += s.tests_triangle; t.tests_sphere_fast += s.tests_sphere_fast; t.tests_general += s.tests_general;
-      t.extend_launches += s.extend_launches; t.shadow_launches += s.shadow_launches; t.root_culled_rays += s.root_culled_rays;
+      t.extend_launches += s.extend_launches; t.shadow_launches += s.shadow_launches; t.root_culled_rays += s.root_culled_rays; t.shaded_lanes += s.shaded_lanes;
       t.shadow_tests_triangle += s.shadow_tests_triangle; t.shadow_tests_sphere_fast += s.shadow_tests_sphere_fast;
       t.shadow_tests_general += s.shadow_tests_general;
       t.iterations = std::max(t.iterations, s.iterations);

@@ -69,6 +69,7 @@ GP_D bool lane_on_last_sample(const RenderParams& P, int sidx) {
 struct RenderCounters {
   unsigned long long camera_rays, closest_rays, shadow_rays, dead_mis_rays, radiance_gt10, nan_samples, unsupported, efloat_panics;
   unsigned long long root_culled;  // scene.Intersect queries answered by the root-bound test inside raygen
+  unsigned long long shaded;       // lanes handed to the shade stage (hits)
 };
 
 struct Queues {
@@ -1331,6 +1332,7 @@ __global__ void k_advance(Queues Q, RenderCounters* ctr, int* host_visible_remai
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     ctr->closest_rays += (unsigned long long)Q.cnt[0];
     ctr->shadow_rays += (unsigned long long)Q.cnt[2];
+    ctr->shaded += (unsigned long long)Q.cnt[8] + (unsigned long long)Q.cnt[9] + (unsigned long long)Q.cnt[10] + (unsigned long long)Q.cnt[11];
     Q.cnt[0] = Q.cnt[1];  // extend <- extend_next (the host swaps the pointers)
     Q.cnt[1] = 0;
     Q.cnt[2] = 0;

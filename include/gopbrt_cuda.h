@@ -236,7 +236,7 @@ typedef struct {
   uint64_t tests_triangle, tests_sphere_fast, tests_general; /* closest-hit shape tests by record kind (COUNT_TRAVERSAL) */
   uint64_t extend_launches, shadow_launches;
   uint64_t shadow_tests_triangle, shadow_tests_sphere_fast, shadow_tests_general; /* any-hit, same split */
-  uint64_t reserved0;          /* (was tail_launches; always 0) */
+  uint64_t shaded_lanes;       /* lanes the shade stage worked on (closest hits that reached a Path.Li / DirectLighting.Li body) */
   double ms_reduce;            /* GOPBRT_FLAG_REDUCE_FILM: device time of the NCCL film reduce (CUDA events on the library stream) */
   uint64_t root_culled_rays;   /* closest_rays answered by the BVH-root slab test inside raygen (never reach the extend kernel) */
 } gopbrt_stats;
