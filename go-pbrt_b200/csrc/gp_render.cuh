@@ -1353,41 +1353,62 @@ __global__ void k_advance(Queues Q, RenderCounters* ctr, int* host_visible_remai
 // is added here: group sum = pad + L', L' = L after renderWorker's NaN replacement (integrator.go:256-257) — the addition
 // film_add_uniform would have made, in the same place of the same order.  SINGLE: no lane has more than one sample, so
 // every pad is still +0 and only the L sector of each record is read.
-GP_D void last_sample_radiance(const PathRec* q, double& r, double& g, double& b, unsigned long long& nans) {
-  r = __ldcs(&q->Lr); g = __ldcs(&q->Lg); b = __ldcs(&q->Lb);
+GP_D void last_sample_fix(double& r, double& g, double& b, unsigned long long& nans) {
   if (is_nan(r) || is_nan(g) || is_nan(b)) { r = g = b = 0.1; nans++; }
   r = r * (1.0 * 1.0); g = g * (1.0 * 1.0); b = b * (1.0 * 1.0);  // L.MulScalar(sampleWeight * filterWeight)
 }
+GP_D void last_sample_radiance(const PathRec* q, double& r, double& g, double& b, unsigned long long& nans) {
+  r = __ldcs(&q->Lr); g = __ldcs(&q->Lg); b = __ldcs(&q->Lb);
+  last_sample_fix(r, g, b, nans);
+}
+// One WARP per tile: the tile's `groups` records are contiguous (groups x 128 bytes), so the lanes fetch them side by side — 32
+// sectors of one or two DRAM pages per load instruction instead of 32 sectors of 32 different tiles 8 KB apart —, two rounds
+// of loads in flight, and leave each record's value (the NaN replacement applied) in shared memory; lanes 0-2 then add up one
+// colour channel each, in ascending group order: the same chain of additions one thread made before.
+// Dynamic shared memory: 3 * groups doubles per warp.
 template <bool LAST, bool SINGLE>
-__global__ void k_group_sums(Lanes L, RenderParams P, RenderCounters* ctr) {
-  const long long n_tiles = P.lanes_active / P.groups;
+__global__ void __launch_bounds__(128) k_group_sums(Lanes L, RenderParams P, RenderCounters* ctr) {
+  extern __shared__ double s_gs[];
+  const int G = P.groups;
+  const long long n_tiles = P.lanes_active / G;
+  const int lane_id = threadIdx.x & 31, w = threadIdx.x >> 5;
+  double* const v = s_gs + (size_t)w * 3 * G;  // [channel][group]
+  const long long n_warps = (long long)gridDim.x * (blockDim.x >> 5);
   unsigned long long nans = 0;
-  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n_tiles; t += (long long)gridDim.x * blockDim.x) {
-    PathRec* base = L.path + t * P.groups;
-    double r = 0, g = 0, b = 0;
-    if (!SINGLE) { r = base->pad[0]; g = base->pad[1]; b = base->pad[2]; }
-    if (LAST) { double lr, lg, lb; last_sample_radiance(base, lr, lg, lb, nans); r += lr; g += lg; b += lb; }
-    int k = 1;
-    for (; k + 8 <= P.groups; k += 8) {  // eight records' loads in flight, added in ascending order
-      double x[8][3];
-#pragma unroll
-      for (int j = 0; j < 8; j++) {
-        const PathRec* q = base + k + j;
-        x[j][0] = x[j][1] = x[j][2] = 0;
-        if (!SINGLE) { x[j][0] = __ldcs(q->pad); x[j][1] = __ldcs(q->pad + 1); x[j][2] = __ldcs(q->pad + 2); }
-        if (LAST) { double lr, lg, lb; last_sample_radiance(q, lr, lg, lb, nans); x[j][0] += lr; x[j][1] += lg; x[j][2] += lb; }
+  for (long long t = (long long)blockIdx.x * (blockDim.x >> 5) + w; t < n_tiles; t += n_warps) {
+    PathRec* base = L.path + t * G;
+    for (int k0 = 0; k0 < G; k0 += 64) {
+      const int ka = k0 + lane_id, kb = ka + 32;
+      double2 la0 = make_double2(0, 0), la1 = la0, lb0 = la0, lb1 = la0, pa0 = la0, pa1 = la0, pb0 = la0, pb1 = la0;
+      if (ka < G) {
+        if (LAST) { la0 = __ldcs((const double2*)&base[ka].Lr); la1 = __ldcs((const double2*)&base[ka].Lb); }      // {Lr, Lg} {Lb, eta}
+        if (!SINGLE) { pa0 = make_double2(__ldcs(&base[ka].pad[0]), __ldcs(&base[ka].pad[1])); pa1.x = __ldcs(&base[ka].pad[2]); }
       }
-#pragma unroll
-      for (int j = 0; j < 8; j++) { r += x[j][0]; g += x[j][1]; b += x[j][2]; }
+      if (kb < G) {
+        if (LAST) { lb0 = __ldcs((const double2*)&base[kb].Lr); lb1 = __ldcs((const double2*)&base[kb].Lb); }
+        if (!SINGLE) { pb0 = make_double2(__ldcs(&base[kb].pad[0]), __ldcs(&base[kb].pad[1])); pb1.x = __ldcs(&base[kb].pad[2]); }
+      }
+      if (ka < G) {
+        double r = pa0.x, g = pa0.y, b = pa1.x;
+        if (LAST) { double lr = la0.x, lg = la0.y, lb = la1.x; last_sample_fix(lr, lg, lb, nans); r += lr; g += lg; b += lb; }
+        v[ka] = r; v[G + ka] = g; v[2 * G + ka] = b;
+      }
+      if (kb < G) {
+        double r = pb0.x, g = pb0.y, b = pb1.x;
+        if (LAST) { double lr = lb0.x, lg = lb0.y, lb = lb1.x; last_sample_fix(lr, lg, lb, nans); r += lr; g += lg; b += lb; }
+        v[kb] = r; v[G + kb] = g; v[2 * G + kb] = b;
+      }
     }
-    for (; k < P.groups; k++) {
-      const PathRec* q = base + k;
-      double xr = 0, xg = 0, xb = 0;
-      if (!SINGLE) { xr = q->pad[0]; xg = q->pad[1]; xb = q->pad[2]; }
-      if (LAST) { double lr, lg, lb; last_sample_radiance(q, lr, lg, lb, nans); xr += lr; xg += lg; xb += lb; }
-      r += xr; g += xg; b += xb;
+    __syncwarp();
+    if (lane_id < 3) {
+      const double* c = v + lane_id * G;
+      double acc = c[0];
+      int k = 1;
+      for (; k + 4 <= G; k += 4) { const double x0 = c[k], x1 = c[k + 1], x2 = c[k + 2], x3 = c[k + 3]; acc += x0; acc += x1; acc += x2; acc += x3; }
+      for (; k < G; k++) acc += c[k];
+      base->pad[lane_id] = acc;
     }
-    base->pad[0] = r; base->pad[1] = g; base->pad[2] = b;
+    __syncwarp();
   }
   if (LAST) {
     nans = warp_sum(nans);
