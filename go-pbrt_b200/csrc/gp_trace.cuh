@@ -418,8 +418,10 @@ __global__ void __launch_bounds__(kTraceThreads, QUADRICS ? GP_TRACE_BLOCKS : GP
 // candidates does not depend on the order they are tested in (exact t ties aside).
 constexpr int kFlatMax = 64;
 
+// resident CTAs per SM: 4 for the closest-hit kernel (128 registers; at 96 it spills: config 2 extend 30.9 -> 33.1 ms), 5 for
+// the any-hit kernels, which carry no best-hit state (shadow 10.5 -> 10.0 ms)
 template <int MODE, bool COUNT>
-__global__ void __launch_bounds__(kTraceThreads, 4) k_trace_flat(DevScene sc, RayRec* __restrict__ rays, const ShadowRec* __restrict__ srays,
+__global__ void __launch_bounds__(kTraceThreads, MODE == 0 ? 4 : 5) k_trace_flat(DevScene sc, RayRec* __restrict__ rays, const ShadowRec* __restrict__ srays,
                                                                  PathRec* __restrict__ paths, unsigned char* __restrict__ occluded,
                                                                  const int* __restrict__ queue, const int* __restrict__ count, long long n_direct,
                                                                  int stack_cap, int* work_counter, TraceCounters* ctr, unsigned long long* gt10_counter) {

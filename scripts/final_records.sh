@@ -10,5 +10,6 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-fil
     python bench.py --profile --steps 1 --warmup 0 > gpurun_out/${tag}_ncu_list.log 2>&1
 ncu --set full --import-source on --clock-control none -k regex:"k_trace|k_shade|k_split" --launch-skip 6 --launch-count 6 -f \
     -o gpurun_out/${tag}_prof_cfg2 python bench.py --profile --steps 1 --warmup 0 > gpurun_out/${tag}_ncu_full.log 2>&1
+AB_MODE=1 ITER_LOG_NAME=${tag}_iter_config2_fast.csv python scripts/iter_log.py config2 > gpurun_out/${tag}_iter_log.txt 2>&1
 python scripts/fullsize_parity.py > gpurun_out/${tag}_fullsize_parity.json 2> gpurun_out/${tag}_fullsize_parity.err
 tail -c 600 gpurun_out/${tag}_fullsize_parity.json
