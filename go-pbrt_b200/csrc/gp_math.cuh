@@ -148,7 +148,9 @@ GP_HD_NOINLINE static double go_sin(double x) {
 // two polynomials.  Here the reduction and both polynomials are computed once and each result selects its own; every value is
 // produced by exactly the operations its own function performs, so both are bit-identical to go_sin / go_cos, at half the
 // arithmetic and without the octant branch (a warp's lanes fall in different octants: both polynomials ran anyway, twice).
-GP_HD_NOINLINE static void go_sincos(double x, double* sn, double* cs) {
+// (returned in registers: an out-of-line function's pointer results would travel through the thread's local-memory stack)
+struct SinCos { double sn, cs; };
+GP_HD_NOINLINE static SinCos go_sincos(double x) {
   const double qnan = b2f(0x7ff8000000000001ULL);
   const double xa = fabs(x);
   uint64_t j = (uint64_t)(long long)(xa * GP_M4PI);
@@ -164,8 +166,10 @@ GP_HD_NOINLINE static void go_sincos(double x, double* sn, double* cs) {
   const bool swap = (j == 1 || j == 2);
   const double ys = swap ? pc : ps, yc = swap ? ps : pc;
   const bool bad = is_nan(x) || is_inf(x);
-  *cs = bad ? qnan : (sign_c ? -yc : yc);
-  *sn = (x == 0 || is_nan(x)) ? x : (is_inf(x) ? qnan : (sign_s ? -ys : ys));
+  SinCos r;
+  r.cs = bad ? qnan : (sign_c ? -yc : yc);
+  r.sn = (x == 0 || is_nan(x)) ? x : (is_inf(x) ? qnan : (sign_s ? -ys : ys));
+  return r;
 }
 // ---- Go src/math/atan.go (Cephes atan.c) ----
 GP_HD double go_xatan(double x) {

@@ -278,10 +278,9 @@ GP_D void concentric_sample_disk(double ux, double uy, double* ox, double* oy) {
   double theta, r;
   if (fabs(x) > fabs(y)) { r = x; theta = kPiOver4 * (y / x); }
   else { r = y; theta = kPiOver2 - kPiOver4 * (x / y); }
-  double sn, cs;
-  go_sincos(theta, &sn, &cs);
-  *ox = cs * r;
-  *oy = sn * r;
+  const SinCos sc_ = go_sincos(theta);
+  *ox = sc_.cs * r;
+  *oy = sc_.sn * r;
 }
 GP_D V3 cosine_sample_hemisphere(double ux, double uy) {
   double dx, dy;
@@ -293,9 +292,8 @@ GP_D V3 uniform_sample_sphere(double ux, double uy) {
   double z = 1.0 - 2.0 * ux;
   double r = sqrt(go_max(0, 1 - z * z));
   double phi = 2 * kPi * uy;
-  double sn, cs;
-  go_sincos(phi, &sn, &cs);
-  return mk3(r * cs, r * sn, z);
+  const SinCos sc_ = go_sincos(phi);
+  return mk3(r * sc_.cs, r * sc_.sn, z);
 }
 
 // ---------------------------------------------------------------- spectrum helpers (pkg/pbrt/spectrum.go)
@@ -544,7 +542,10 @@ GP_D void sphere_sample(const DevScene& sc, const SphereDev& s, double ux, doubl
   it->n = n;
   *pdf = 1.0 / (s.phiMax * s.radius * (s.zMax - s.zMin));
 }
-__device__ __noinline__ static void sphere_sample_at(const DevScene& sc, const SphereDev& s, const Intr& ref, double ux, double uy, Intr* it, double* pdf) {
+// (inlined: as out-of-line functions their reference / pointer arguments — the shape record, the reference point, the sampled
+// point — went through the local-memory stack, ~60 local loads and stores per shaded lane: ncu counted more L1<->L2 traffic
+// from local memory than from the lane records)
+GP_D void sphere_sample_at(const DevScene& sc, const SphereDev& s, const Intr& ref, double ux, double uy, Intr* it, double* pdf) {
   M4 m = load_m4_plain(sc, s.xf, false);
   V3 pCenter = xf_point(m, mk3(0, 0, 0), mk3(0, 0, 0), nullptr);
   V3 pOrigin = offset_ray_origin(ref.p, ref.perr, ref.n, pCenter - ref.p);
@@ -575,9 +576,8 @@ __device__ __noinline__ static void sphere_sample_at(const DevScene& sc, const S
   double cosAlpha = (dc * dc + radius2 - ds * ds) / (2.0 * dc * s.radius);
   double sinAlpha = sqrt(go_max(0, 1.0 - cosAlpha * cosAlpha));
   V3 x = wcX * -1.0, y = wcY * -1.0, z = wc * -1.0;
-  double snPhi, csPhi;
-  go_sincos(phi, &snPhi, &csPhi);
-  V3 nWorld = x * (sinAlpha * csPhi) + y * (sinAlpha * snPhi) + z * cosAlpha;  // geometry.go:66-70
+  const SinCos scPhi = go_sincos(phi);
+  V3 nWorld = x * (sinAlpha * scPhi.cs) + y * (sinAlpha * scPhi.sn) + z * cosAlpha;  // geometry.go:66-70
   V3 pWorld = pCenter + nWorld * s.radius;
   it->p = pWorld;
   it->perr = vabs(pWorld) * gamma_n(5.0);
@@ -585,7 +585,7 @@ __device__ __noinline__ static void sphere_sample_at(const DevScene& sc, const S
   if (s.flags & RF_REVERSE) it->n = it->n * -1.0;
   *pdf = 1.0 / (2.0 * kPi * (1.0 - cosThetaMax));  // UniformConePdf (sampling.go:169-171)
 }
-__device__ __noinline__ static void disk_sample_at(const DevScene& sc, const DiskDev& d, const Intr& ref, double ux, double uy, Intr* it, double* pdf) {
+GP_D void disk_sample_at(const DevScene& sc, const DiskDev& d, const Intr& ref, double ux, double uy, Intr* it, double* pdf) {
   M4 m = load_m4_plain(sc, d.xf, false), inv = load_m4_plain(sc, d.xf, true);
   double px, py;
   concentric_sample_disk(ux, uy, &px, &py);
