@@ -1273,7 +1273,10 @@ GP_D RGB direct_unwind(const Lanes& L, const RenderParams& P, long long lane, co
 #ifndef GP_SHADE_BLOCKS0
 #define GP_SHADE_BLOCKS0 4
 #endif
-template <int CLS> struct ShadeBlocks { static constexpr int value = 3; };
+#ifndef GP_SHADE_BLOCKS_OTHER
+#define GP_SHADE_BLOCKS_OTHER 4
+#endif
+template <int CLS> struct ShadeBlocks { static constexpr int value = GP_SHADE_BLOCKS_OTHER; };
 template <> struct ShadeBlocks<0> { static constexpr int value = GP_SHADE_BLOCKS0; };
 template <int INTEG, int MODE, int CLS>
 __global__ void __launch_bounds__(128, ShadeBlocks<CLS>::value) k_shade(DevScene sc, Lanes L, RenderParams P_in, Queues Q, RenderCounters* ctr) {
