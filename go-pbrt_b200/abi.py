@@ -24,7 +24,7 @@ COMM_ID_BYTES = 128
 KAT_IDS = {n: i for i, n in enumerate([
     "fr_dielectric", "oren_nayar_f", "fresnel_specular_sample_f", "concentric_sample_disk", "cosine_sample_hemisphere", "lambert_sample_f",
     "offset_ray_origin", "coordinate_system", "sample_discrete_uniform", "rgb_to_xyz", "film_add_sample", "rng_u32", "rng_uniform",
-    "rng_u32b", "stratified_start_pixel", "light_sample_li", "spawn_ray_to", "camera_ray"])}
+    "rng_u32b", "stratified_start_pixel", "light_sample_li", "spawn_ray_to", "camera_ray", "go_math"])}
 LIGHTS_UNIFORM, LIGHTS_POWER, LIGHTS_SPATIAL = 1, 2, 4
 
 d16 = C.c_double * 16

@@ -10,7 +10,7 @@ namespace gp {
 enum {
   KAT_FR_DIELECTRIC = 0, KAT_OREN_NAYAR_F, KAT_FRESNEL_SPECULAR_SAMPLE_F, KAT_CONCENTRIC_SAMPLE_DISK, KAT_COSINE_SAMPLE_HEMISPHERE,
   KAT_LAMBERT_SAMPLE_F, KAT_OFFSET_RAY_ORIGIN, KAT_COORDINATE_SYSTEM, KAT_SAMPLE_DISCRETE_UNIFORM, KAT_RGB_TO_XYZ, KAT_FILM_ADD_SAMPLE,
-  KAT_RNG_U32, KAT_RNG_UNIFORM, KAT_RNG_U32B, KAT_STRATIFIED_START_PIXEL, KAT_LIGHT_SAMPLE_LI, KAT_SPAWN_RAY_TO, KAT_CAMERA_RAY, KAT_N
+  KAT_RNG_U32, KAT_RNG_UNIFORM, KAT_RNG_U32B, KAT_STRATIFIED_START_PIXEL, KAT_LIGHT_SAMPLE_LI, KAT_SPAWN_RAY_TO, KAT_CAMERA_RAY, KAT_GO_MATH, KAT_N
 };
 
 GP_D void kat_identity_frame(BSDF& b) {
@@ -119,6 +119,11 @@ __global__ void k_kat(DevScene sc, int fn, const double* __restrict__ in, int n_
     case KAT_SPAWN_RAY_TO: if (n_in == 18) {
       Intr a, b; a.p = v3(0); a.perr = v3(3); a.n = v3(6); b.p = v3(9); b.perr = v3(12); b.n = v3(15);
       put3(0, a.p); put3(3, spawn_ray_to(a, b)); out[6] = 1 - 0.0001; n = 7;
+    } break;
+    case KAT_GO_MATH: if (n_in == 2) {  // math.Max, math.Min, math.Sin, math.Cos, and the fused sin + cos the kernels use
+      const SinCos sc2 = go_sincos(in[0]);
+      out[0] = go_max(in[0], in[1]); out[1] = go_min(in[0], in[1]); out[2] = go_sin(in[0]); out[3] = go_cos(in[0]);
+      out[4] = sc2.sn; out[5] = sc2.cs; n = 6;
     } break;
     case KAT_CAMERA_RAY: if (n_in == 38) {
       Ray r = camera_ray(P, in[34], in[35], in[36], in[37]);

@@ -295,6 +295,10 @@ int oracle_kat_eval(void* scene, const char* fn_c, const double* in, int n_in, d
     put3(0, r.o); put3(3, r.d); out[6] = r.tmax;
     return 7;
   }
+  if (fn == "go_math" && n_in == 2 && n_out >= 6) {
+    out[0] = gomath::Max(in[0], in[1]); out[1] = gomath::Min(in[0], in[1]); out[2] = gomath::Sin(in[0]); out[3] = gomath::Cos(in[0]); out[4] = gomath::Sin(in[0]); out[5] = gomath::Cos(in[0]);
+    return 6;
+  }
   if (fn == "camera_ray" && n_in == 38 && n_out >= 6) {
     gopbrt_camera c;
     for (int i = 0; i < 16; i++) { c.raster_to_camera[i] = in[i]; c.camera_to_world[i] = in[16 + i]; }

@@ -679,6 +679,19 @@ def main():
         add("camera_ray", trig, [x for row in r2c for x in row] + [x for row in c2w for x in row] + [lr, fd] + pf + plens, o + d,
             "camera.go:192-242, transform.go:227-300")
 
+    # math.Max / math.Min with their special cases and math.Sin / math.Cos of one argument (the device also
+    # evaluates its fused sin+cos, which must equal the two separate functions): out = [Max, Min, Sin(x), Cos(x), Sin(x), Cos(x)]
+    inf, nan = float("inf"), float("nan")
+    specials = [0.0, -0.0, 1.0, -1.0, inf, -inf, nan, 5e-324, -5e-324, 2.5, 1e300]
+    for x in specials:
+        for y in specials:
+            add("go_math", "gomath", [x, y], [go_max(x, y), go_min(x, y), gomath.Sin(x), gomath.Cos(x), gomath.Sin(x), gomath.Cos(x)],
+                "go1.11 src/math/dim.go (Max, Min), sin.go (Sin, Cos)")
+    for x in (0.1, -0.1, 0.7853981633974483, 0.7853981633974484, 1.5707963267948966, 2.356194490192345, 3.141592653589793, 4.0, -5.5,
+              6.283185307179586, 6.283185307179587, 100.0, -12345.678, 1e9, 536870912.0, 0.3926990816987241, 1e-300, 2.2250738585072014e-308):
+        add("go_math", "gomath", [x, -x], [go_max(x, -x), go_min(x, -x), gomath.Sin(x), gomath.Cos(x), gomath.Sin(x), gomath.Cos(x)],
+            "go1.11 src/math/dim.go (Max, Min), sin.go (Sin, Cos)")
+
     out = dict(note="generated by tests/golden/make_shading_kats.py — independent plain-Python restatement of the cited Go lines; values are C99 hex floats",
                lights=[{k: (hx(v) if isinstance(v, list) else v) for k, v in l.items()} for l in lights], cases=cases)
     with open(os.path.join(HERE, "shading_kats.json"), "w") as f:
