@@ -942,6 +942,19 @@ __global__ void __launch_bounds__(256) k_split_hits(Lanes L, Queues Q, const uns
   }
 }
 
+// FAST mode: the index of the pixel a lane is working on (row-major in the cropped window) — what keys the sample's counter-
+// based streams.  With tileSize 1 the tile IS the pixel (ntx = the window's width), so the index is the tile number and the
+// shade stage is spared tile_bounds and two of its three integer divisions per lane.
+GP_D unsigned long long lane_fast_pixel(const RenderParams& P, long long lane, int pix) {
+  const long long tile = (P.groups == 1 ? P.lane_base + lane : div_nn(P.lane_base + lane, P.groups)) * P.world + P.rank;
+  if (P.tile_size == 1) return (unsigned long long)tile;
+  long long x0, y0, x1, y1;
+  tile_bounds(P, tile, &x0, &y0, &x1, &y1);
+  const long long prow = div_nn(pix, x1 - x0);
+  const long long px = x0 + (pix - prow * (x1 - x0)), py = y0 + prow;
+  return (unsigned long long)((py - P.cy0) * (P.cx1 - P.cx0) + (px - P.cx0));
+}
+
 // ---------------------------------------------------------------- shade
 // One Path.Li loop body for one lane (path.go:40-155) after its closest-hit query.  Sets cont (the path continues with a
 // new ray in L.ray[lane]), finished (the sample is complete) and shadow (a visibility segment is pending in L.sray[lane]).
@@ -971,16 +984,7 @@ GP_D void shade_lane(const DevScene& sc, const Lanes& L, const RenderParams& P, 
       Smp s;
       s.state = pt.rng_state; s.inc = pt.rng_inc; s.sidx = pt.sidx;
       s.cur1 = (packed >> 8) & 255; s.cur2 = (packed >> 16) & 255; s.lane = lane;
-      unsigned long long fast_pixel = 0;
-      if (P.mode == 1) {
-        long long tile = (P.groups == 1 ? P.lane_base + lane : div_nn(P.lane_base + lane, P.groups)) * P.world + P.rank;
-        long long x0, y0, x1, y1;
-        tile_bounds(P, tile, &x0, &y0, &x1, &y1);
-        int pix = pt.pix;
-        long long prow = div_nn(pix, x1 - x0);
-        long long px = x0 + (pix - prow * (x1 - x0)), py = y0 + prow;
-        fast_pixel = (unsigned long long)((py - P.cy0) * (P.cx1 - P.cx0) + (px - P.cx0));
-      }
+      const unsigned long long fast_pixel = P.mode == 1 ? lane_fast_pixel(P, lane, pt.pix) : 0ULL;
       RGB beta = rgb(pt.br, pt.bg, pt.bb);
       Intr ref; ref.p = h.p; ref.perr = h.perr; ref.n = h.n;
       // --- UniformSampleOneLight (integrator.go:48-77), skipped for perfectly specular BSDFs (path.go:84)
@@ -1136,16 +1140,7 @@ GP_D void shade_lane_direct(const DevScene& sc, const Lanes& L, const RenderPara
     Smp s;
     s.state = pt.rng_state; s.inc = pt.rng_inc; s.sidx = pt.sidx;
     s.cur1 = (packed >> 8) & 255; s.cur2 = (packed >> 16) & 255; s.lane = lane;
-    unsigned long long fast_pixel = 0;
-    if (P.mode == 1) {
-      long long tile = (P.groups == 1 ? P.lane_base + lane : div_nn(P.lane_base + lane, P.groups)) * P.world + P.rank;
-      long long x0, y0, x1, y1;
-      tile_bounds(P, tile, &x0, &y0, &x1, &y1);
-      int pix = pt.pix;
-      long long prow = div_nn(pix, x1 - x0);
-      long long px = x0 + (pix - prow * (x1 - x0)), py = y0 + prow;
-      fast_pixel = (unsigned long long)((py - P.cy0) * (P.cx1 - P.cx0) + (px - P.cx0));
-    }
+    const unsigned long long fast_pixel = P.mode == 1 ? lane_fast_pixel(P, lane, pt.pix) : 0ULL;
     Intr ref; ref.p = h.p; ref.perr = h.perr; ref.n = h.n;
     // --- direct light (directlighting.go:85-96): UniformSampleOneLight (integrator.go:48-77) or, ALL, every light once
     //     (UniformSampleAllLights' single-sample branch, integrator.go:31-36: uLight then uScattering per light)
