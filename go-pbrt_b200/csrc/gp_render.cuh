@@ -275,9 +275,12 @@ GP_D long long mod_nn(long long a, long long b) {
 GP_D void concentric_sample_disk(double ux, double uy, double* ox, double* oy) {
   double x = ux * 2.0 - 1, y = uy * 2.0 - 1;
   if (x == 0 && y == 0) { *ox = 0; *oy = 0; return; }
-  double theta, r;
-  if (fabs(x) > fabs(y)) { r = x; theta = kPiOver4 * (y / x); }
-  else { r = y; theta = kPiOver2 - kPiOver4 * (x / y); }
+  // sampling.go:183-189: r = x, theta = Pi/4 * (y / x) where |x| > |y|, else r = y, theta = Pi/2 - Pi/4 * (x / y) — ONE
+  // division behind selects (each case performs its own operations; the two branches split every warp down the middle)
+  const bool wide = fabs(x) > fabs(y);
+  const double r = wide ? x : y;
+  const double q = kPiOver4 * ((wide ? y : x) / r);
+  const double theta = wide ? q : kPiOver2 - q;
   const SinCos sc_ = go_sincos(theta);
   *ox = sc_.cs * r;
   *oy = sc_.sn * r;
