@@ -1442,6 +1442,14 @@ __global__ void k_film_merge(Lanes L, RenderParams P, double* __restrict__ film)
     double X = film[i * 4], Y = film[i * 4 + 1], Z = film[i * 4 + 2], W = film[i * 4 + 3];
     long long ty0 = (y - ext - P.cy0) / P.tile_size, ty1 = (y + ext - P.cy0) / P.tile_size;
     long long tx0 = (x - ext - P.cx0) / P.tile_size, tx1 = (x + ext - P.cx0) / P.tile_size;
+    if (P.uniform_fp) {
+      // tileSize 1, every sample at its pixel's integer corner: tile (= pixel) t reaches pixel x only if
+      // ceil(t - 0.5 - r) <= x <= floor(t - 0.5 + r) (uniform_footprint), i.e. x + 0.5 - r <= t <= x + 0.5 + r — with the box
+      // filter's r = 0.5 that is 2 x 2 tiles instead of the 5 x 5 of the general search window (the membership tests below are
+      // unchanged, and so is the order of the additions)
+      tx0 = (long long)ceil((double)x + 0.5 - P.frx) - P.cx0; tx1 = (long long)floor((double)x + 0.5 + P.frx) - P.cx0;
+      ty0 = (long long)ceil((double)y + 0.5 - P.fry) - P.cy0; ty1 = (long long)floor((double)y + 0.5 + P.fry) - P.cy0;
+    }
     if (ty0 < 0) ty0 = 0; if (tx0 < 0) tx0 = 0;
     if (ty1 >= P.nty) ty1 = P.nty - 1; if (tx1 >= P.ntx) tx1 = P.ntx - 1;
     for (long long ty = ty0; ty <= ty1; ty++)
