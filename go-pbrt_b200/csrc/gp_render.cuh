@@ -100,20 +100,15 @@ GP_D void block_push(int* const (&q)[NQ], int* const (&cnt)[NQ], const bool (&pr
 #pragma unroll
   for (int k = 0; k < NQ; k++) { m[k] = __ballot_sync(FULL, pred[k]); if (lane_id == 0) s_cnt[warp][k] = __popc(m[k]); }
   __syncthreads();
-  if (threadIdx.x < NQ) {
+  if (threadIdx.x < NQ) {  // one thread per queue: the warps' counts become their offsets in the CTA's run, then the queue's one atomic
     int tot = 0;
-    for (int w = 0; w < nwarps; w++) tot += s_cnt[w][threadIdx.x];
+    for (int w = 0; w < nwarps; w++) { const int c = s_cnt[w][threadIdx.x]; s_cnt[w][threadIdx.x] = tot; tot += c; }
     s_base[threadIdx.x] = tot ? atomicAdd(cnt[threadIdx.x], tot) : 0;
   }
   __syncthreads();
 #pragma unroll
-  for (int k = 0; k < NQ; k++) {
-    if (pred[k]) {
-      int off = s_base[k];
-      for (int w = 0; w < warp; w++) off += s_cnt[w][k];
-      q[k][off + __popc(m[k] & ((1u << lane_id) - 1u))] = v;
-    }
-  }
+  for (int k = 0; k < NQ; k++)
+    if (pred[k]) q[k][s_base[k] + s_cnt[warp][k] + __popc(m[k] & ((1u << lane_id) - 1u))] = v;
   __syncthreads();
 }
 
@@ -929,14 +924,13 @@ __global__ void __launch_bounds__(256) k_split_hits(Lanes L, Queues Q, const uns
     __syncthreads();
     if (threadIdx.x < 5) {
       int tot = 0;
-      for (int w = 0; w < 8; w++) tot += s_cnt[w][threadIdx.x];
+      for (int w = 0; w < 8; w++) { const int c = s_cnt[w][threadIdx.x]; s_cnt[w][threadIdx.x] = tot; tot += c; }  // counts -> offsets
       int* cnt = threadIdx.x < 4 ? Q.cnt + 8 + threadIdx.x : Q.cnt + 4;
       s_base[threadIdx.x] = tot ? atomicAdd(cnt, tot) : 0;
     }
     __syncthreads();
     if (bin >= 0) {
-      int off = s_base[bin];
-      for (int w = 0; w < warp; w++) off += s_cnt[w][bin];
+      const int off = s_base[bin] + s_cnt[warp][bin];
       unsigned mm = bin == 0 ? m[0] : (bin == 1 ? m[1] : (bin == 2 ? m[2] : (bin == 3 ? m[3] : m[4])));
       int* q = bin < 4 ? Q.shade[bin] : Q.regen_next;
       q[off + __popc(mm & ((1u << lane_id) - 1u))] = lane;
