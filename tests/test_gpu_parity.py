@@ -204,6 +204,30 @@ def test_flat_and_bvh_aggregates_agree_bitwise(gp, dev, monkeypatch):
     assert s0["nodes_visited"] != s1["nodes_visited"]  # two different aggregates did run
 
 
+def test_last_sample_in_place_equals_retirement_through_raygen(gp, dev, monkeypatch):
+    # FAST mode + uniform footprint + Path: a lane's last sample is not retired through the regeneration queue — the film
+    # fold adds pad + L (k_group_sums<LAST>, or k_fold_last when a pass does not hold whole tiles).  Same additions in the
+    # same order as the retirement inside raygen (GOPBRT_NO_LAST_IN_PLACE=1): bit-identical films and identical counters,
+    # with one lane per pixel, several lanes per pixel (multi-sample lanes), one sample per lane, and split passes.
+    scene, integ = gp.scenes.config2(W=96, H=54, spp=(4, 4))
+    g = gp.pbrt.GpuScene(dev, scene)
+    for kw in (dict(groups=1), dict(groups=4), dict(groups=15), dict(groups=0), dict(groups=4, max_lanes=7001), dict(groups=3, rank=1, world=2)):
+        films, stats = [], []
+        for off in (False, True):
+            if off:
+                monkeypatch.setenv("GOPBRT_NO_LAST_IN_PLACE", "1")
+            else:
+                monkeypatch.delenv("GOPBRT_NO_LAST_IN_PLACE", raising=False)
+            st = gp.pbrt.Render(g, integ, 1, mode=gp.abi.MODE_FAST, **kw)
+            films.append(integ.GetCamera().GetFilm().pixels.copy())
+            stats.append(st)
+        assert np.array_equal(films[0], films[1]), kw
+        for k in ("camera_rays", "closest_rays", "shadow_rays", "nan_samples", "shaded_lanes"):
+            assert stats[0][k] == stats[1][k], (kw, k)
+    monkeypatch.delenv("GOPBRT_NO_LAST_IN_PLACE", raising=False)
+    g.close()
+
+
 def test_fast_mode_film_bit_exact_and_statistically_close_to_strict(gp, dev):
     scene = gp.scenes.mixed_test_scene(80, seed=5)
     integ = gp.scenes.test_integrator(96, 64, spp=(4, 4), maxDepth=5)
