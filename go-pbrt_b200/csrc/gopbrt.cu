@@ -1317,8 +1317,14 @@ static int render_impl(gopbrt_scene* sc, const gopbrt_camera* cam, const gopbrt_
       if (P.uniform_fp && (P.groups > 1 || P.last_in_place) && P.lane_base % P.groups == 0 && P.lanes_active % P.groups == 0) {
         const int g_sums = ctx->sm_count * 16;
         const size_t sm_sums = (size_t)4 * 3 * P.groups * sizeof(double);  // <= 24 KB (groups <= 255)
-        if (!P.last_in_place) k_group_sums<false, false><<<g_sums, 128, sm_sums, st>>>(L, P, W.rctr.p);
-        else if (P.s_world * P.groups >= P.spp - 1) k_group_sums<true, true><<<g_sums, 128, sm_sums, st>>>(L, P, W.rctr.p);  // at most one sample per lane
+        const bool single = P.s_world * P.groups >= P.spp - 1;  // at most one sample per lane
+        if (P.groups <= 8) {  // few groups: one thread per tile (k_group_sums_small)
+          if (!P.last_in_place) k_group_sums_small<false, false, 8><<<g_small, 128, 0, st>>>(L, P, W.rctr.p);
+          else if (single) k_group_sums_small<true, true, 8><<<g_small, 128, 0, st>>>(L, P, W.rctr.p);
+          else k_group_sums_small<true, false, 8><<<g_small, 128, 0, st>>>(L, P, W.rctr.p);
+        }
+        else if (!P.last_in_place) k_group_sums<false, false><<<g_sums, 128, sm_sums, st>>>(L, P, W.rctr.p);
+        else if (single) k_group_sums<true, true><<<g_sums, 128, sm_sums, st>>>(L, P, W.rctr.p);
         else k_group_sums<true, false><<<g_sums, 128, sm_sums, st>>>(L, P, W.rctr.p);
         ctx->launches++;
         PM.groups_merged = 1;

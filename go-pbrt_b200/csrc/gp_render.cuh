@@ -1410,6 +1410,41 @@ __global__ void __launch_bounds__(128) k_group_sums(Lanes L, RenderParams P, Ren
     if ((threadIdx.x & 31) == 0 && nans) atomicAdd(&ctr->nan_samples, nans);
   }
 }
+// The same fold for FEW lane groups (a rank's share of a multi-GPU frame: 8 groups at N = 8): one THREAD per tile with all of the
+// tile's records in flight at once — a warp per tile would run at a quarter of its lanes and one dependent chain per tile.
+template <bool LAST, bool SINGLE, int GMAX>
+__global__ void __launch_bounds__(128) k_group_sums_small(Lanes L, RenderParams P, RenderCounters* ctr) {
+  const int G = P.groups;
+  const long long n_tiles = P.lanes_active / G;
+  unsigned long long nans = 0;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n_tiles; t += (long long)gridDim.x * blockDim.x) {
+    PathRec* base = L.path + t * G;
+    double2 l0[GMAX], l1[GMAX];
+    double p0[GMAX], p1[GMAX], p2[GMAX];
+#pragma unroll
+    for (int k = 0; k < GMAX; k++) {
+      if (k < G) {
+        if (LAST) { l0[k] = __ldcs((const double2*)&base[k].Lr); l1[k] = __ldcs((const double2*)&base[k].Lb); }
+        if (!SINGLE) { p0[k] = __ldcs(&base[k].pad[0]); p1[k] = __ldcs(&base[k].pad[1]); p2[k] = __ldcs(&base[k].pad[2]); }
+      }
+    }
+    double r = 0, g = 0, b = 0;
+#pragma unroll
+    for (int k = 0; k < GMAX; k++) {
+      if (k < G) {
+        double xr = 0, xg = 0, xb = 0;
+        if (!SINGLE) { xr = p0[k]; xg = p1[k]; xb = p2[k]; }
+        if (LAST) { double lr = l0[k].x, lg = l0[k].y, lb = l1[k].x; last_sample_fix(lr, lg, lb, nans); xr += lr; xg += lg; xb += lb; }
+        if (k == 0) { r = xr; g = xg; b = xb; } else { r += xr; g += xg; b += xb; }
+      }
+    }
+    base->pad[0] = r; base->pad[1] = g; base->pad[2] = b;
+  }
+  if (LAST) {
+    nans = warp_sum(nans);
+    if ((threadIdx.x & 31) == 0 && nans) atomicAdd(&ctr->nan_samples, nans);
+  }
+}
 // last_in_place when the lane groups of a pass cannot be folded per tile (a pass that does not hold whole tiles): every lane
 // retires its last sample into its own pad
 __global__ void k_fold_last(Lanes L, RenderParams P, RenderCounters* ctr) {
