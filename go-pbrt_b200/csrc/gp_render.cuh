@@ -965,6 +965,7 @@ GP_D void shade_lane(const DevScene& sc, const Lanes& L, const RenderParams& P, 
   int packed = pt.bounces;
   int bounces = (packed & 255) + 1;  // bounces++ (path.go:41)
   int rec = rr.hit_rec;
+  bool w_L = false, w_eta = false, w_beta = false, w_rng = false;
   finished = true;
   if (rec >= 0 && bounces < P.max_depth) {  // path.go:66
     Ray ray;
@@ -1035,6 +1036,7 @@ GP_D void shade_lane(const DevScene& sc, const Lanes& L, const RenderParams& P, 
           // L.AddAssign(beta.Mul(0)) (path.go:85-86): a no-op unless beta is not finite (0*Inf = NaN), kept for parity
           RGB z = beta * rgb(0, 0, 0);
           pt.Lr += z.r; pt.Lg += z.g; pt.Lb += z.b;
+          w_L = true;
         }
       }
       // --- sample the BSDF for the next direction (path.go:90-117); wo = ray.Direction, sic
@@ -1051,6 +1053,7 @@ GP_D void shade_lane(const DevScene& sc, const Lanes& L, const RenderParams& P, 
           if (dot(ray.d, h.n) > 0) etaScale *= eta * eta;
           else etaScale *= 1 / (eta * eta);
           pt.eta_scale = etaScale;
+          w_eta = true;
         }
         V3 o = offset_ray_origin(h.p, h.perr, h.n, wi);  // SpawnRay (interaction.go:68-77); wi is BSDF-local
         bool alive = true;
@@ -1066,16 +1069,26 @@ GP_D void shade_lane(const DevScene& sc, const Lanes& L, const RenderParams& P, 
           nr.tmax = d_inf(); nr.hit_rec = -1; nr.pad = lane_on_last_sample(P, pt.sidx) ? 1 : 0;
           L.ray[lane] = nr;
           pt.br = beta.r; pt.bg = beta.g; pt.bb = beta.b;
+          w_beta = true;
           cont = true;
           finished = false;
         }
       }
-      pt.rng_state = s.state; pt.rng_inc = s.inc;
+      pt.rng_state = s.state;  // (the stream's increment does not change inside a sample)
+      w_rng = true;
       packed = (s.cur1 << 8) | (s.cur2 << 16);
     }
   }
-  pt.bounces = (packed & ~255) | bounces;
-  L.path[lane] = pt;
+  // Only what this loop body changed goes back: the bounce count and sampler dimensions always, the sampler state and
+  // (if the path goes on) the throughput, rarely the radiance sum (a non-finite throughput) and the refraction scale.
+  // pFilm, the stream increment, the pixel and the film sum are the raygen stage's; not keeping them for a whole-record
+  // store frees registers for the float64 chain (and the record's fourth sector is not written at all).
+  PathRec* const pp = L.path + lane;
+  pp->bounces = (packed & ~255) | bounces;
+  if (w_rng) pp->rng_state = pt.rng_state;
+  if (w_beta) { pp->br = pt.br; pp->bg = pt.bg; pp->bb = pt.bb; }
+  if (w_L) { pp->Lr = pt.Lr; pp->Lg = pt.Lg; pp->Lb = pt.Lb; }
+  if (w_eta) pp->eta_scale = pt.eta_scale;
   if (finished && lane_on_last_sample(P, pt.sidx)) finished = false;  // stays in place: no trip through the regeneration queue
 }
 
