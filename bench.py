@@ -385,9 +385,11 @@ def main():
                             "shape_tests": cst["prim_tests"] / max(1, ext_rays)},
                 "stage_ms_per_step": {k: sum(s[k] for s in stage_stats) / KS for k in ("ms_raygen", "ms_extend", "ms_shade", "ms_shadow", "ms_film")}}
         # ---- the kernel that dominates THIS frame.  On the headline workload (36 primitives: the aggregate is a shared-memory table)
-        # that is the shade stage, whose bytes all come from and go to HBM: per shaded lane it reads the lane's PathRec (128 B),
-        # RayRec (64 B) and queue entry (4 B) and writes the PathRec back (128 B); a lane that continues writes a new RayRec and
-        # its queue entry (64 + 4 B), a lane with a light sample a ShadowRec and its queue entry (96 + 4 B) — DESIGN.md §4.
+        # that is the shade stage, whose bytes all come from and go to HBM: per shaded lane it reads three sectors of the lane's
+        # PathRec (96 B: radiance / throughput / sampler state — the fourth, the raygen stage's film sum, is not touched), the
+        # RayRec (64 B) and the queue entry (4 B) and writes the sampler-state sector back (32 B); a lane that continues also
+        # writes its throughput sector, a new RayRec and its queue entry (32 + 64 + 4 B), a lane with a light sample a
+        # ShadowRec and its queue entry (96 + 4 B) — DESIGN.md §4.
         # (ms_shade = k_split_hits + the shade-class kernels of every iteration.)  The extend kernel stays on the line as
         # roofline_extend: its SURVEY §8d "algorithmic bytes" are table bytes that never leave the SM here, so their rate is not
         # a fraction of an HBM roof — for the HBM-resident tree see roofline_deep_bvh.
@@ -402,7 +404,7 @@ def main():
             cont_lanes = st0["closest_rays"] - st0["camera_rays"]  # every closest-hit query that is not a camera ray was spawned by a shade lane
             n_iter = st0["iterations"]
             n_cls = max(1, round((st0["launches"] - 3) / max(1, n_iter)) - 5)  # shade-class launches per iteration (launches per iteration = 5 + classes)
-            by_shade = st0["shaded_lanes"] * (128 + 64 + 4 + 128) + cont_lanes * (64 + 4) + st0["shadow_rays"] * (96 + 4)
+            by_shade = st0["shaded_lanes"] * (96 + 64 + 4 + 32) + cont_lanes * (32 + 64 + 4) + st0["shadow_rays"] * (96 + 4)
             n_sh = n_iter * n_cls * KS
             ach = by_shade * KS / (s_shade / 1e3) / 1e9
             traffic_sh, traffic_sh_src = None, "no ncu capture of this workload under profiles/"
@@ -420,7 +422,7 @@ def main():
                     "peak_source": roof_ext["peak_source"], "traffic": traffic_sh, "traffic_source": traffic_sh_src,
                     "limiter": "dependent float64 chains at 16 resident warps per SM (128-168 registers): issue slots 33 % busy, long-scoreboard 5 of 12 stall cycles per issue (profiles/r02b_ncu_stage_kernels.md)",
                     "bytes_per_launch": by_shade * KS / max(1, n_sh), "ms_per_launch": s_shade / max(1, n_sh), "launches": n_sh,
-                    "bytes_per_unit": "324 B per shaded lane + 68 B per continuing lane + 100 B per shadow ray",
+                    "bytes_per_unit": "196 B per shaded lane + 100 B per continuing lane + 100 B per shadow ray",
                     "units_per_step": {"shaded_lanes": st0["shaded_lanes"], "continuing_lanes": cont_lanes, "shadow_rays": st0["shadow_rays"]},
                     "measured_over": roof_ext["measured_over"],
                     "stage_ms_per_step": roof_ext["stage_ms_per_step"]}

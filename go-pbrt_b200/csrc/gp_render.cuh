@@ -1241,11 +1241,16 @@ GP_D void shade_lane_direct(const DevScene& sc, const Lanes& L, const RenderPara
         }
       }
     }
-    pt.rng_state = s.state; pt.rng_inc = s.inc;
+    pt.rng_state = s.state;
     packed = (packed & ~((255 << 8) | (255 << 16))) | (s.cur1 << 8) | (s.cur2 << 16);
   }
-  pt.bounces = packed;
-  L.path[lane] = pt;
+  // only what a DirectLighting level changes goes back (see shade_lane): the level's radiance sum, the pending-segment mask,
+  // the sampler state, the level / dimension counters
+  PathRec* const pp = L.path + lane;
+  pp->Lr = pt.Lr; pp->Lg = pt.Lg; pp->Lb = pt.Lb;
+  pp->has_sample = pt.has_sample;
+  pp->rng_state = pt.rng_state;
+  pp->bounces = packed;
 }
 
 // the radiance of a finished DirectLighting sample: the chain of frames unwound (see shade_lane_direct)
