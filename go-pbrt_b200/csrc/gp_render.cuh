@@ -965,7 +965,7 @@ GP_D void shade_lane(const DevScene& sc, const Lanes& L, const RenderParams& P, 
   int packed = pt.bounces;
   int bounces = (packed & 255) + 1;  // bounces++ (path.go:41)
   int rec = rr.hit_rec;
-  bool w_L = false, w_eta = false, w_beta = false, w_rng = false;
+  bool w_eta = false, w_beta = false, w_rng = false;
   finished = true;
   if (rec >= 0 && bounces < P.max_depth) {  // path.go:66
     Ray ray;
@@ -1034,9 +1034,10 @@ GP_D void shade_lane(const DevScene& sc, const Lanes& L, const RenderParams& P, 
         }
         if (!shadow) {
           // L.AddAssign(beta.Mul(0)) (path.go:85-86): a no-op unless beta is not finite (0*Inf = NaN), kept for parity
+          // Adding a zero of either sign changes no radiance sum (the sum is never -0: it starts at +0), so the record's
+          // radiance is only touched — in place — when the product is NOT a zero, i.e. NaN.
           RGB z = beta * rgb(0, 0, 0);
-          pt.Lr += z.r; pt.Lg += z.g; pt.Lb += z.b;
-          w_L = true;
+          if (!(z.r == 0 && z.g == 0 && z.b == 0)) { PathRec* q = L.path + lane; q->Lr += z.r; q->Lg += z.g; q->Lb += z.b; }
         }
       }
       // --- sample the BSDF for the next direction (path.go:90-117); wo = ray.Direction, sic
@@ -1080,14 +1081,13 @@ GP_D void shade_lane(const DevScene& sc, const Lanes& L, const RenderParams& P, 
     }
   }
   // Only what this loop body changed goes back: the bounce count and sampler dimensions always, the sampler state and
-  // (if the path goes on) the throughput, rarely the radiance sum (a non-finite throughput) and the refraction scale.
+  // (if the path goes on) the throughput, rarely the refraction scale (the radiance sum is the shadow stage's to add to).
   // pFilm, the stream increment, the pixel and the film sum are the raygen stage's; not keeping them for a whole-record
   // store frees registers for the float64 chain (and the record's fourth sector is not written at all).
   PathRec* const pp = L.path + lane;
   pp->bounces = (packed & ~255) | bounces;
   if (w_rng) pp->rng_state = pt.rng_state;
   if (w_beta) { pp->br = pt.br; pp->bg = pt.bg; pp->bb = pt.bb; }
-  if (w_L) { pp->Lr = pt.Lr; pp->Lg = pt.Lg; pp->Lb = pt.Lb; }
   if (w_eta) pp->eta_scale = pt.eta_scale;
   if (finished && lane_on_last_sample(P, pt.sidx)) finished = false;  // stays in place: no trip through the regeneration queue
 }
