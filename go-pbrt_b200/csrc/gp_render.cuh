@@ -958,7 +958,7 @@ GP_D unsigned long long lane_fast_pixel(const RenderParams& P, long long lane, i
 // cls: the hit's shade class (bit 0 = material is not plain Lambert, bit 1 = sphere / disk hit) when the caller shades one
 // class only (a compile-time constant after inlining: the other classes' code is not compiled in), or -1 = any
 GP_D void shade_lane(const DevScene& sc, const Lanes& L, const RenderParams& P, long long lane, bool& cont, bool& finished, bool& shadow,
-                     unsigned long long& n_unsupported, unsigned long long& n_dead, int& bad, const int cls = -1) {
+                     unsigned& n_counts, int& bad, const int cls = -1) {
   const bool lambert_only = cls >= 0 && !(cls & 1), tri_only = cls >= 0 && !(cls & 2);
   PathRec pt = L.path[lane];
   RayRec rr = L.ray[lane];
@@ -977,7 +977,7 @@ GP_D void shade_lane(const DevScene& sc, const Lanes& L, const RenderParams& P, 
     hit_record(sc, rec, ray, ray.tmax, &h, &prim, bad, tri_only);
     BSDF bsdf;
     if (!compute_scattering(sc, prim, h, &bsdf, true, lambert_only)) {
-      n_unsupported++;
+      n_counts += 0x10000u;
     } else {
       Smp s;
       s.state = pt.rng_state; s.inc = pt.rng_inc; s.sidx = pt.sidx;
@@ -1004,7 +1004,7 @@ GP_D void shade_lane(const DevScene& sc, const Lanes& L, const RenderParams& P, 
             const int flags = BSDF_ALL & ~BSDF_SPECULAR;
             LightSample ls;
             light_sample_li(sc, sc.lights[offset], ref, ulx, uly, &ls);
-            if (!ls.delta) n_dead++;
+            if (!ls.delta) n_counts += 1u;
             if (ls.pdf > 0 && !is_black(ls.Li)) {
               RGB f = bsdf_f(bsdf, h.wo, ls.wi, flags, lambert_only);
               f = f * fabs(dot(ls.wi, h.ns));
@@ -1123,7 +1123,7 @@ GP_D void direct_collect(const Lanes& L, const RenderParams& P, long long lane, 
 // ALL = true: returns in seg_mask the segments (one per light) written to L.sray[lane * n_seg + j]
 template <bool ALL>
 GP_D void shade_lane_direct(const DevScene& sc, const Lanes& L, const RenderParams& P, long long lane, bool& cont, bool& finished, bool& shadow,
-                            unsigned& seg_mask, unsigned long long& n_unsupported, unsigned long long& n_dead, int& bad) {
+                            unsigned& seg_mask, unsigned& n_counts, int& bad) {
   PathRec pt = L.path[lane];
   RayRec rr = L.ray[lane];
   if (ALL) direct_collect(L, P, lane, pt);
@@ -1145,7 +1145,7 @@ GP_D void shade_lane_direct(const DevScene& sc, const Lanes& L, const RenderPara
   hit_record(sc, rr.hit_rec, ray, ray.tmax, &h, &prim, bad);
   BSDF bsdf;
   if (!compute_scattering(sc, prim, h, &bsdf, false)) {
-    n_unsupported++;
+    n_counts += 0x10000u;
   } else {
     Smp s;
     s.state = pt.rng_state; s.inc = pt.rng_inc; s.sidx = pt.sidx;
@@ -1172,7 +1172,7 @@ GP_D void shade_lane_direct(const DevScene& sc, const Lanes& L, const RenderPara
         const int flags = BSDF_ALL & ~BSDF_SPECULAR;  // EstimateDirect (integrator.go:79-195), specular = false
         LightSample ls;
         light_sample_li(sc, sc.lights[offset], ref, ulx, uly, &ls);
-        if (!ls.delta) n_dead++;
+        if (!ls.delta) n_counts += 1u;
         if (ls.pdf > 0 && !is_black(ls.Li)) {
           RGB f = bsdf_f(bsdf, h.wo, ls.wi, flags);
           f = f * fabs(dot(ls.wi, h.ns));
@@ -1300,7 +1300,7 @@ __global__ void __launch_bounds__(128, ShadeBlocks<CLS>::value) k_shade(DevScene
   long long n = o3 + n3;
   if (CLS >= 0) n = Q.cnt[8 + (CLS >= 0 ? CLS : 0)];
   int lane_id = threadIdx.x & 31;
-  unsigned long long n_unsupported = 0, n_dead = 0;
+  unsigned n_counts = 0;  // this thread's dead MIS rays (low 16 bits) and unsupported materials (high 16): a thread sees < 2^15 lanes per launch
   int bad = 0;
   // (per-lane pushes: batching them as raygen does bought nothing here on config 2 and cost 4-15 % on the sphere shade classes)
   __shared__ int s_cnt[4][3];
@@ -1320,9 +1320,9 @@ __global__ void __launch_bounds__(128, ShadeBlocks<CLS>::value) k_shade(DevScene
     long long lane = 0;
     if (valid) {
       lane = bin_q[bi];
-      if (INTEG == 0) shade_lane(sc, L, P, lane, cont, finished, shadow, n_unsupported, n_dead, bad, CLS);
-      else if (INTEG == 1) shade_lane_direct<false>(sc, L, P, lane, cont, finished, shadow, seg_mask, n_unsupported, n_dead, bad);
-      else shade_lane_direct<true>(sc, L, P, lane, cont, finished, shadow, seg_mask, n_unsupported, n_dead, bad);
+      if (INTEG == 0) shade_lane(sc, L, P, lane, cont, finished, shadow, n_counts, bad, CLS);
+      else if (INTEG == 1) shade_lane_direct<false>(sc, L, P, lane, cont, finished, shadow, seg_mask, n_counts, bad);
+      else shade_lane_direct<true>(sc, L, P, lane, cont, finished, shadow, seg_mask, n_counts, bad);
     }
     if (INTEG == 2) {  // UniformSampleAll: one shadow-queue entry per emitted segment (entry = lane * n_seg + light)
       for (int j = 0; j < P.n_seg; j++) queue_push(Q.shadow, Q.cnt + 2, (seg_mask >> j) & 1u, (int)(lane * P.n_seg + j));
@@ -1332,7 +1332,7 @@ __global__ void __launch_bounds__(128, ShadeBlocks<CLS>::value) k_shade(DevScene
     const bool ps[3] = {shadow, cont, finished && valid};
     block_push<3>(qs, cs, ps, (int)lane, s_cnt, s_base);
   }
-  n_unsupported = warp_sum(n_unsupported); n_dead = warp_sum(n_dead);
+  unsigned long long n_unsupported = warp_sum((unsigned long long)(n_counts >> 16)), n_dead = warp_sum((unsigned long long)(n_counts & 0xffffu));
   if (lane_id == 0) {
     if (n_unsupported) atomicAdd(&ctr->unsupported, n_unsupported);
     if (n_dead) atomicAdd(&ctr->dead_mis_rays, n_dead);
