@@ -67,3 +67,36 @@ def test_gpu_reproduces_golden_primary_rays(gp, dev, golden):
     prim, t, p, n = g.Intersect(ro, rd)
     g.close()
     assert np.array_equal(prim, golden["config1_primary_prim"]) and np.array_equal(t, golden["config1_primary_t"])
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_oracle_obeys_the_composition_invariants(gp, mode):
+    # The exact properties of the composed Path.Li loop that tests/test_gpu_parity.py checks on the CUDA path at BASELINE size
+    # (linear in the emitted radiance; maxDepth 1 and zero albedo give a black film without a shadow ray) hold for the checker too.
+    P = gp.pbrt
+
+    def render(scene, integ):
+        o = OracleScene(scene, 1)
+        film, st = o.render(integ, 1, mode=mode)
+        o.close()
+        return film, st
+
+    dims = dict(W=64, H=36, spp=(3, 3))
+    scene, integ = gp.scenes.config2(**dims)
+    f1, s1 = render(scene, integ)
+    scene2, integ2 = gp.scenes.config2(**dims)
+    for l in scene2.lights:
+        l.LEmit = [2.0 * v for v in l.LEmit]
+    f2, s2 = render(scene2, integ2)
+    assert np.array_equal(f2[..., 3], f1[..., 3]) and np.array_equal(f2[..., :3], 2.0 * f1[..., :3]) and f1[..., :3].max() > 0
+    for k in ("camera_rays", "closest_rays", "shadow_rays"):
+        assert s1[k] == s2[k], k
+    scene3, integ3 = gp.scenes.config2(**dims)
+    f3, s3 = render(scene3, P.NewPath(1, integ3.GetCamera(), integ3.GetSampler(), None, 1, P.Uniform))
+    assert not f3[..., :3].any() and s3["closest_rays"] == s3["camera_rays"] == s1["camera_rays"] and s3["shadow_rays"] == 0
+    scene4, integ4 = gp.scenes.config2(**dims)
+    for prim in scene4.aggregate.primitives:
+        if isinstance(prim.material, P.MatteMaterial):
+            prim.material.Kd.value = [0.0, 0.0, 0.0]
+    f4, s4 = render(scene4, integ4)
+    assert not f4[..., :3].any() and s4["shadow_rays"] == 0 and s4["closest_rays"] > s4["camera_rays"]

@@ -373,6 +373,55 @@ def test_full_size_properties_config1(gp, dev):
     g.close()
 
 
+def test_full_size_composition_invariants_config2(gp, dev):
+    # BASELINE size (1920x1080, 63 effective spp, FAST and — smaller — STRICT): properties of the COMPOSED Path.Li loop that follow
+    # from the reference's source and hold exactly in floating point, checked on the CUDA path alone (no oracle in the loop):
+    #  (1) linearity in the emitted radiance: every light x 2 (a power of two: exact) => the film's X, Y, Z exactly x 2, the
+    #      weights and every ray count unchanged (no path decision reads a radiance: Russian roulette reads beta, the MIS
+    #      weight reads pdfs, IsBlack tests survive the scaling — path.go:84-153, integrator.go:79-195);
+    #  (2) maxDepth 1: `bounces++` comes first and `bounces >= maxDepth` ends the path before any light is gathered
+    #      (path.go:41,66; the `bounces == 0` emission branch is dead): a black film, one closest-hit query per camera ray, no shadow ray;
+    #  (3) every matte albedo 0: f is black, so EstimateDirect makes no visibility test (integrator.go:111-126) and SampleF ends
+    #      the path (path.go:92-95): a black film and no shadow ray, while glass still bounces.
+    P = gp.pbrt
+
+    def render(scene, integ, **kw):
+        g = P.GpuScene(dev, scene)
+        st = P.Render(g, integ, 1, **kw)
+        film = integ.GetCamera().GetFilm().pixels.copy()
+        g.close()
+        return film, st
+
+    for dims, kw in ((dict(), dict(mode=gp.abi.MODE_FAST)), (dict(W=480, H=270), dict(mode=gp.abi.MODE_STRICT))):
+        scene, integ = gp.scenes.config2(**dims)
+        f1, s1 = render(scene, integ, **kw)
+        scene2, integ2 = gp.scenes.config2(**dims)
+        for l in scene2.lights:
+            l.LEmit = [2.0 * v for v in l.LEmit]
+        f2, s2 = render(scene2, integ2, **kw)
+        assert np.array_equal(f2[..., 3], f1[..., 3])
+        assert np.array_equal(f2[..., :3], 2.0 * f1[..., :3]), "the film is not linear in the emitted radiance"
+        assert f1[..., :3].max() > 0
+        for k in ("camera_rays", "closest_rays", "shadow_rays", "dead_mis_rays", "shaded_lanes"):
+            assert s1[k] == s2[k], k
+        # (2)
+        scene3, integ3 = gp.scenes.config2(**dims)
+        cam, smp = integ3.GetCamera(), integ3.GetSampler()
+        shallow = P.NewPath(1, cam, smp, None, 1, P.Uniform)
+        f3, s3 = render(scene3, shallow, **kw)
+        assert not f3[..., :3].any() and np.array_equal(f3[..., 3], f1[..., 3])
+        assert s3["closest_rays"] == s3["camera_rays"] == s1["camera_rays"] and s3["shadow_rays"] == 0
+        # (3)
+        scene4, integ4 = gp.scenes.config2(**dims)
+        for prim in scene4.aggregate.primitives:
+            m = prim.material
+            if isinstance(m, P.MatteMaterial):
+                m.Kd.value = [0.0, 0.0, 0.0]
+        f4, s4 = render(scene4, integ4, **kw)
+        assert not f4[..., :3].any() and np.array_equal(f4[..., 3], f1[..., 3])
+        assert s4["shadow_rays"] == 0 and s4["camera_rays"] == s1["camera_rays"] and s4["closest_rays"] > s4["camera_rays"]
+
+
 def test_random_sampler_and_thin_lens_film_bit_exact(gp, dev):
     # sampler.RandomSampler (random.go): every dimension from the RNG, so pFilm is jittered and the box-filter footprint
     # varies per sample; lensRadius > 0 exercises ConcentricSampleDisk in GenerateRayDifferential (camera.go:201-212)
