@@ -404,6 +404,17 @@ def test_full_size_composition_invariants_config2(gp, dev):
         assert f1[..., :3].max() > 0
         for k in ("camera_rays", "closest_rays", "shadow_rays", "dead_mis_rays", "shaded_lanes"):
             assert s1[k] == s2[k], k
+        # ... and so is DirectLighting.Li, its specular chain unwound included (directlighting.go:62-104), with both light strategies
+        if dims:
+            for strat in (P.UniformSampleOne, P.UniformSampleAll):
+                films = []
+                for scale in (1.0, 2.0):
+                    sc_, it_ = gp.scenes.config2(**dims)
+                    for l in sc_.lights:
+                        l.LEmit = [scale * v for v in l.LEmit]
+                    dl = P.NewDirectLighting(strat, 5, it_.GetCamera(), it_.GetSampler(), None)
+                    films.append(render(sc_, dl, **kw)[0])
+                assert np.array_equal(films[1][..., :3], 2.0 * films[0][..., :3]) and films[0][..., :3].max() > 0
         # (2)
         scene3, integ3 = gp.scenes.config2(**dims)
         cam, smp = integ3.GetCamera(), integ3.GetSampler()
