@@ -106,6 +106,7 @@ struct Workspace {  // per-scene render workspace, kept between gopbrt_render ca
   DevBuf<RayRec> ray;
   DevBuf<ShadowRec> sray;
   DevBuf<PathRec> path;
+  DevBuf<RadRec> rad;
   DevBuf<int> i32;        // queues
   DevBuf<double> tables, tilepix, frames;
   DevBuf<unsigned char> occl;
@@ -130,7 +131,7 @@ struct Workspace {  // per-scene render workspace, kept between gopbrt_render ca
   }
 };
 
-typedef void (*trace_fn)(DevScene, RayRec*, const ShadowRec*, PathRec*, unsigned char*, const int*, const int*, long long, int, int*,
+typedef void (*trace_fn)(DevScene, RayRec*, const ShadowRec*, RadRec*, unsigned char*, const int*, const int*, long long, int, int*,
                          TraceCounters*, unsigned long long*);
 
 struct gopbrt_scene {
@@ -1092,7 +1093,7 @@ static int render_impl(gopbrt_scene* sc, const gopbrt_camera* cam, const gopbrt_
   const size_t table_doubles = P.mode == GOPBRT_MODE_FAST ? 0 : (size_t)P.ndims * P.spp;
   const size_t frame_doubles = P.integrator == GOPBRT_INTEGRATOR_DIRECT_LIGHTING ? (size_t)P.direct_levels * 8 : 0;
   const size_t n_seg = (size_t)P.n_seg;  // shadow segments (and shadow-queue entries) per lane
-  size_t per_lane = sizeof(RayRec) + n_seg * (sizeof(ShadowRec) + 1) + sizeof(PathRec) + (8 + n_seg) * 4 + 1 + table_doubles * 8 + (P.uniform_fp ? 0 : (size_t)tpw * tph * 4 * 8) + frame_doubles * 8;
+  size_t per_lane = sizeof(RayRec) + n_seg * (sizeof(ShadowRec) + 1) + sizeof(PathRec) + sizeof(RadRec) + (8 + n_seg) * 4 + 1 + table_doubles * 8 + (P.uniform_fp ? 0 : (size_t)tpw * tph * 4 * 8) + frame_doubles * 8;
   Workspace& W = sc->ws;
   // Lane state of ONE scene handle: at most 40 % of the device's memory (GOPBRT_LANE_BUDGET_GB overrides) and 80 % of what is
   // free right now — several scenes render on one context (one per gRPC request in the reference) and must not starve each other.
@@ -1130,11 +1131,12 @@ static int render_impl(gopbrt_scene* sc, const gopbrt_camera* cam, const gopbrt_
     // the shape fields are cleared first: a failed allocation below must not leave a "same shape" workspace with null buffers
     W.lanes = 0; W.bytes_tables = 0; W.bytes_tilepix = 0;
     if (W.graph_exec) { cudaGraphExecDestroy(W.graph_exec); W.graph_exec = nullptr; W.graph_key.clear(); }
-    W.ray.release(); W.sray.release(); W.path.release(); W.i32.release(); W.tables.release(); W.tilepix.release(); W.frames.release(); W.occl.release(); W.codes.release();
+    W.ray.release(); W.sray.release(); W.path.release(); W.rad.release(); W.i32.release(); W.tables.release(); W.tilepix.release(); W.frames.release(); W.occl.release(); W.codes.release();
     GP_CUDA(ctx, W.ray.alloc((size_t)lanes));
     GP_CUDA(ctx, W.sray.alloc(n_seg * (size_t)lanes));
     GP_CUDA(ctx, W.occl.alloc(direct_all ? n_seg * (size_t)lanes : 0));
     GP_CUDA(ctx, W.path.alloc((size_t)lanes));
+    GP_CUDA(ctx, W.rad.alloc((size_t)lanes));
     GP_CUDA(ctx, W.i32.alloc((8 + n_seg) * (size_t)lanes));
     GP_CUDA(ctx, W.codes.alloc((size_t)lanes));
     GP_CUDA(ctx, W.tables.alloc(std::max<size_t>(bt, 1)));
@@ -1152,7 +1154,7 @@ static int render_impl(gopbrt_scene* sc, const gopbrt_camera* cam, const gopbrt_
   Lanes L;
   memset(&L, 0, sizeof(L));
   L.n = lanes;
-  L.ray = W.ray.p; L.sray = W.sray.p; L.path = W.path.p;
+  L.ray = W.ray.p; L.sray = W.sray.p; L.path = W.path.p; L.rad = W.rad.p;
   int* ip = W.i32.p;
   Queues Q;
   memset(&Q, 0, sizeof(Q));
@@ -1227,10 +1229,10 @@ static int render_impl(gopbrt_scene* sc, const gopbrt_camera* cam, const gopbrt_
     const bool use_graph = !timing && !iter_log_path && !count && !getenv("GOPBRT_NO_GRAPH");
     if (use_graph) {
       auto enqueue_iteration = [&]() {
-        sc->trace_k[k_ext]<<<sc->trace_grid[k_ext], kTraceThreads, smem, st>>>(sc->dev, L.ray, nullptr, L.path, W.codes.p, Q.extend, Q.cnt + 0, 0, scap, Q.cnt + 6, sc->tctr.p, nullptr);
+        sc->trace_k[k_ext]<<<sc->trace_grid[k_ext], kTraceThreads, smem, st>>>(sc->dev, L.ray, nullptr, L.rad, W.codes.p, Q.extend, Q.cnt + 0, 0, scap, Q.cnt + 6, sc->tctr.p, nullptr);
         k_split_hits<<<g_small, 256, 0, st>>>(L, Q, W.codes.p);
         for (int k = 0; k < n_shade; k++) shade_tab[shade_list[k]]<<<ctx->grid_shade[shade_list[k]], 128, 0, st>>>(sc->dev, L, P, Q, W.rctr.p);
-        sc->trace_k[k_any]<<<sc->trace_grid[k_any], kTraceThreads, smem, st>>>(sc->dev, nullptr, L.sray, L.path, L.occl, Q.shadow, Q.cnt + 2, 0, scap, Q.cnt + 7, sc->tctr.p, &W.rctr.p->radiance_gt10);
+        sc->trace_k[k_any]<<<sc->trace_grid[k_any], kTraceThreads, smem, st>>>(sc->dev, nullptr, L.sray, L.rad, L.occl, Q.shadow, Q.cnt + 2, 0, scap, Q.cnt + 7, sc->tctr.p, &W.rctr.p->radiance_gt10);
         k_advance<<<1, 32, 0, st>>>(Q, W.rctr.p, W.remaining_dev);
         std::swap(Q.extend, Q.extend_next);
         std::swap(Q.regen, Q.regen_next);
@@ -1283,7 +1285,7 @@ static int render_impl(gopbrt_scene* sc, const gopbrt_camera* cam, const gopbrt_
         iter_counts.push_back(c[0]);
       }
       tick(ST_EXTEND);
-      sc->trace_k[k_ext]<<<sc->trace_grid[k_ext], kTraceThreads, smem, st>>>(sc->dev, L.ray, nullptr, L.path, W.codes.p, Q.extend, Q.cnt + 0, 0, scap, Q.cnt + 6, sc->tctr.p, nullptr);
+      sc->trace_k[k_ext]<<<sc->trace_grid[k_ext], kTraceThreads, smem, st>>>(sc->dev, L.ray, nullptr, L.rad, W.codes.p, Q.extend, Q.cnt + 0, 0, scap, Q.cnt + 6, sc->tctr.p, nullptr);
       tick(ST_SHADE);
       k_split_hits<<<g_small, 256, 0, st>>>(L, Q, W.codes.p);
       for (int k = 0; k < n_shade; k++) shade_tab[shade_list[k]]<<<ctx->grid_shade[shade_list[k]], 128, 0, st>>>(sc->dev, L, P, Q, W.rctr.p);
@@ -1295,7 +1297,7 @@ static int render_impl(gopbrt_scene* sc, const gopbrt_camera* cam, const gopbrt_
         iter_hits.push_back(c[8] + c[9] + c[10] + c[11]);
       }
       tick(ST_SHADOW);
-      sc->trace_k[k_any]<<<sc->trace_grid[k_any], kTraceThreads, smem, st>>>(sc->dev, nullptr, L.sray, L.path, L.occl, Q.shadow, Q.cnt + 2, 0, scap, Q.cnt + 7, sc->tctr.p, &W.rctr.p->radiance_gt10);
+      sc->trace_k[k_any]<<<sc->trace_grid[k_any], kTraceThreads, smem, st>>>(sc->dev, nullptr, L.sray, L.rad, L.occl, Q.shadow, Q.cnt + 2, 0, scap, Q.cnt + 7, sc->tctr.p, &W.rctr.p->radiance_gt10);
       tick(ST_RAYGEN);
       k_advance<<<1, 32, 0, st>>>(Q, W.rctr.p, W.remaining_dev);
       std::swap(Q.extend, Q.extend_next);

@@ -19,7 +19,8 @@ struct Lanes {
   long long n;
   RayRec* ray;      // current path segment + closest-hit result
   ShadowRec* sray;  // pending visibility segment + gated light sample
-  PathRec* path;    // throughput, radiance, sampler stream
+  PathRec* path;    // throughput, sampler stream, film sum
+  RadRec* rad;      // radiance sum + refraction scale (one sector per lane, an array of its own)
   double* tables;   // [dim][k][lane] stratified 1-D tables
   double* tilepix;  // [lane][tile pixel][4] FilmTile accumulators (one contiguous record per lane)
   long long tile_stride;  // doubles per lane = tpw * tph * 4
@@ -756,7 +757,7 @@ GP_D Ray camera_ray(const RenderParams& P, double fx, double fy, double lx, doub
 // lane's tile is exhausted.
 struct PathRec;
 GP_D PathRec initial_path(const RenderParams& P, long long lane);  // defined below
-GP_D RGB direct_unwind(const Lanes& L, const RenderParams& P, long long lane, const PathRec& pt);  // DirectLighting, defined below
+GP_D RGB direct_unwind(const Lanes& L, const RenderParams& P, long long lane, const PathRec& pt, const RadRec& rd);  // DirectLighting, defined below
 GP_D bool generate_lane(const DevScene& sc, const Lanes& L, const RenderParams& P, long long lane, bool have_sample,
                         unsigned long long& cam, unsigned long long& nans, unsigned long long& culled) {
   bool go = false;
@@ -764,8 +765,11 @@ GP_D bool generate_lane(const DevScene& sc, const Lanes& L, const RenderParams& 
   long long tile = slot_tile * P.world + P.rank;
   const int s_mod = P.s_world * P.groups, s_res = P.s_rank * P.groups + (int)(slot - slot_tile * P.groups);
   PathRec pt = have_sample ? L.path[lane] : initial_path(P, lane);  // the pass's first launch starts every lane from scratch
+  RadRec rd;
+  rd.Lr = 0; rd.Lg = 0; rd.Lb = 0; rd.eta_scale = 1.0;
   if (have_sample) {  // every lane of the regeneration queue carries a finished sample
-    RGB Lc = P.integrator == 1 ? direct_unwind(L, P, lane, pt) : rgb(pt.Lr, pt.Lg, pt.Lb);
+    rd = L.rad[lane];
+    RGB Lc = P.integrator == 1 ? direct_unwind(L, P, lane, pt, rd) : rgb(rd.Lr, rd.Lg, rd.Lb);
     if (is_nan(Lc.r) || is_nan(Lc.g) || is_nan(Lc.b)) { Lc = rgb(0.1, 0.1, 0.1); nans++; }  // integrator.go:256-257
     if (P.uniform_fp) film_add_uniform(pt, Lc);
     else film_add_sample(L, P, lane, tile, pt.fx, pt.fy, Lc);
@@ -833,17 +837,18 @@ GP_D bool generate_lane(const DevScene& sc, const Lanes& L, const RenderParams& 
     rr.tmax = d_inf(); rr.hit_rec = -1; rr.pad = lane_on_last_sample(P, s.sidx) ? 1 : 0;  // see k_split_hits
     L.ray[lane] = rr;
     pt.fx = fx; pt.fy = fy;
-    pt.Lr = 0; pt.Lg = 0; pt.Lb = 0;
+    rd.Lr = 0; rd.Lg = 0; rd.Lb = 0;
     pt.br = 1.0; pt.bg = 1.0; pt.bb = 1.0;
-    pt.eta_scale = 1.0;
+    rd.eta_scale = 1.0;
     pt.bounces = (s.cur1 << 8) | (s.cur2 << 16);  // bounces in bits 0-7, sampler dimensions above
     pt.has_sample = 0;  // DirectLighting / UniformSampleAll: no shadow segments pending
     go = true;
     break;
   }
   pt.rng_state = s.state; pt.rng_inc = s.inc; pt.sidx = s.sidx; pt.pix = pix;
-  if (P.last_in_place && !go) { pt.Lr = 0; pt.Lg = 0; pt.Lb = 0; }  // no sample in flight: the film fold adds pad + L
+  if (P.last_in_place && !go) { rd.Lr = 0; rd.Lg = 0; rd.Lb = 0; }  // no sample in flight: the film fold adds pad + L
   L.path[lane] = pt;
+  L.rad[lane] = rd;
   return go;
 }
 
@@ -966,6 +971,7 @@ GP_D void shade_lane(const DevScene& sc, const Lanes& L, const RenderParams& P, 
   int bounces = (packed & 255) + 1;  // bounces++ (path.go:41)
   int rec = rr.hit_rec;
   bool w_eta = false, w_beta = false, w_rng = false;
+  double eta_new = 0;
   finished = true;
   if (rec >= 0 && bounces < P.max_depth) {  // path.go:66
     Ray ray;
@@ -1037,7 +1043,7 @@ GP_D void shade_lane(const DevScene& sc, const Lanes& L, const RenderParams& P, 
           // Adding a zero of either sign changes no radiance sum (the sum is never -0: it starts at +0), so the record's
           // radiance is only touched — in place — when the product is NOT a zero, i.e. NaN.
           RGB z = beta * rgb(0, 0, 0);
-          if (!(z.r == 0 && z.g == 0 && z.b == 0)) { PathRec* q = L.path + lane; q->Lr += z.r; q->Lg += z.g; q->Lb += z.b; }
+          if (!(z.r == 0 && z.g == 0 && z.b == 0)) { RadRec* q = L.rad + lane; q->Lr += z.r; q->Lg += z.g; q->Lb += z.b; }
         }
       }
       // --- sample the BSDF for the next direction (path.go:90-117); wo = ray.Direction, sic
@@ -1048,12 +1054,12 @@ GP_D void shade_lane(const DevScene& sc, const Lanes& L, const RenderParams& P, 
       if (!(is_black(f) || pdf == 0.0)) {
         double wiAbsDotPdf = fabs(dot(wi, h.ns)) / pdf;
         beta = beta * (f * wiAbsDotPdf);
-        double etaScale = pt.eta_scale;
+        double etaScale = L.rad[lane].eta_scale;
         if ((sflags & BSDF_SPECULAR) > 0 && (sflags & BSDF_TRANSMISSION) > 0) {
           double eta = bsdf.eta;
           if (dot(ray.d, h.n) > 0) etaScale *= eta * eta;
           else etaScale *= 1 / (eta * eta);
-          pt.eta_scale = etaScale;
+          eta_new = etaScale;
           w_eta = true;
         }
         V3 o = offset_ray_origin(h.p, h.perr, h.n, wi);  // SpawnRay (interaction.go:68-77); wi is BSDF-local
@@ -1088,7 +1094,7 @@ GP_D void shade_lane(const DevScene& sc, const Lanes& L, const RenderParams& P, 
   pp->bounces = (packed & ~255) | bounces;
   if (w_rng) pp->rng_state = pt.rng_state;
   if (w_beta) { pp->br = pt.br; pp->bg = pt.bg; pp->bb = pt.bb; }
-  if (w_eta) pp->eta_scale = pt.eta_scale;
+  if (w_eta) L.rad[lane].eta_scale = eta_new;
   if (finished && lane_on_last_sample(P, pt.sidx)) finished = false;  // stays in place: no trip through the regeneration queue
 }
 
@@ -1107,7 +1113,7 @@ constexpr int kDirectHitBit = 1 << 24;  // PathRec.bounces: the chain ended AT a
 // UniformSampleAll: the level's direct light is the sum over the lights, in light order, of the segments the shadow
 // stage found unoccluded (L.AddAssign(EstimateDirect(...)) per light, integrator.go:23-46); pt.has_sample holds the
 // mask of the segments that were emitted.  UniformSampleOne: the shadow stage has already added its single segment.
-GP_D void direct_collect(const Lanes& L, const RenderParams& P, long long lane, PathRec& pt) {
+GP_D void direct_collect(const Lanes& L, const RenderParams& P, long long lane, PathRec& pt, RadRec& rd) {
   if (!P.direct_all) return;
   unsigned mask = (unsigned)pt.has_sample;
   for (int j = 0; j < P.n_seg; j++) {
@@ -1115,7 +1121,7 @@ GP_D void direct_collect(const Lanes& L, const RenderParams& P, long long lane, 
     size_t e = (size_t)lane * P.n_seg + j;
     if (L.occl[e]) continue;
     const ShadowRec* sr = L.sray + e;
-    pt.Lr += sr->pr; pt.Lg += sr->pg; pt.Lb += sr->pb;
+    rd.Lr += sr->pr; rd.Lg += sr->pg; rd.Lb += sr->pb;
   }
   pt.has_sample = 0;
 }
@@ -1125,16 +1131,17 @@ template <bool ALL>
 GP_D void shade_lane_direct(const DevScene& sc, const Lanes& L, const RenderParams& P, long long lane, bool& cont, bool& finished, bool& shadow,
                             unsigned& seg_mask, unsigned& n_counts, int& bad) {
   PathRec pt = L.path[lane];
+  RadRec rd = L.rad[lane];
   RayRec rr = L.ray[lane];
-  if (ALL) direct_collect(L, P, lane, pt);
+  if (ALL) direct_collect(L, P, lane, pt, rd);
   int packed = pt.bounces;
   const int level = packed & 255;  // frames filed so far == specular bounces taken; Li's depth argument is 2 * level
   double* fr = L.frames + ((size_t)lane * P.direct_levels) * 8;
   finished = true;
   packed |= kDirectHitBit;
   if (level > 0) {  // the previous level's direct light is complete now: file it, start this level's sum at zero
-    fr[(level - 1) * 8 + 0] = pt.Lr; fr[(level - 1) * 8 + 1] = pt.Lg; fr[(level - 1) * 8 + 2] = pt.Lb;
-    pt.Lr = 0; pt.Lg = 0; pt.Lb = 0;
+    fr[(level - 1) * 8 + 0] = rd.Lr; fr[(level - 1) * 8 + 1] = rd.Lg; fr[(level - 1) * 8 + 2] = rd.Lb;
+    rd.Lr = 0; rd.Lg = 0; rd.Lb = 0;
   }
   Ray ray;
   ray.o = mk3(rr.ox, rr.oy, rr.oz);
@@ -1247,24 +1254,26 @@ GP_D void shade_lane_direct(const DevScene& sc, const Lanes& L, const RenderPara
   // only what a DirectLighting level changes goes back (see shade_lane): the level's radiance sum, the pending-segment mask,
   // the sampler state, the level / dimension counters
   PathRec* const pp = L.path + lane;
-  pp->Lr = pt.Lr; pp->Lg = pt.Lg; pp->Lb = pt.Lb;
+  RadRec* const rp = L.rad + lane;
+  rp->Lr = rd.Lr; rp->Lg = rd.Lg; rp->Lb = rd.Lb;
   pp->has_sample = pt.has_sample;
   pp->rng_state = pt.rng_state;
   pp->bounces = packed;
 }
 
 // the radiance of a finished DirectLighting sample: the chain of frames unwound (see shade_lane_direct)
-GP_D RGB direct_unwind(const Lanes& L, const RenderParams& P, long long lane, const PathRec& pt_in) {
+GP_D RGB direct_unwind(const Lanes& L, const RenderParams& P, long long lane, const PathRec& pt_in, const RadRec& rd_in) {
   PathRec pt = pt_in;
-  direct_collect(L, P, lane, pt);
+  RadRec rd = rd_in;
+  direct_collect(L, P, lane, pt, rd);
   const int level = pt.bounces & 255;
   const bool at_hit = (pt.bounces & kDirectHitBit) != 0;
   const double* fr = L.frames + ((size_t)lane * P.direct_levels) * 8;
   // at a hit: pt.L is that level's own direct light.  Otherwise the last ray escaped: its Li is the sum of the lights'
   // Le = 0, and pt.L is still the previous level's direct light.
-  RGB Ln = at_hit ? rgb(pt.Lr, pt.Lg, pt.Lb) : rgb(0, 0, 0);
+  RGB Ln = at_hit ? rgb(rd.Lr, rd.Lg, rd.Lb) : rgb(0, 0, 0);
   for (int j = level - 1; j >= 0; j--) {
-    RGB D = (j == level - 1 && !at_hit) ? rgb(pt.Lr, pt.Lg, pt.Lb) : rgb(fr[j * 8], fr[j * 8 + 1], fr[j * 8 + 2]);
+    RGB D = (j == level - 1 && !at_hit) ? rgb(rd.Lr, rd.Lg, rd.Lb) : rgb(fr[j * 8], fr[j * 8 + 1], fr[j * 8 + 2]);
     RGB f = rgb(fr[j * 8 + 3], fr[j * 8 + 4], fr[j * 8 + 5]);
     Ln = D + (f * Ln) * fr[j * 8 + 6];  // L.AddAssign(f.Mul(s.Li(...)).MulScalar(wi.AbsDot(ns) / pdf))
   }
@@ -1370,7 +1379,7 @@ GP_D void last_sample_fix(double& r, double& g, double& b, unsigned long long& n
   if (is_nan(r) || is_nan(g) || is_nan(b)) { r = g = b = 0.1; nans++; }
   r = r * (1.0 * 1.0); g = g * (1.0 * 1.0); b = b * (1.0 * 1.0);  // L.MulScalar(sampleWeight * filterWeight)
 }
-GP_D void last_sample_radiance(const PathRec* q, double& r, double& g, double& b, unsigned long long& nans) {
+GP_D void last_sample_radiance(const RadRec* q, double& r, double& g, double& b, unsigned long long& nans) {
   r = __ldcs(&q->Lr); g = __ldcs(&q->Lg); b = __ldcs(&q->Lb);
   last_sample_fix(r, g, b, nans);
 }
@@ -1390,15 +1399,16 @@ __global__ void __launch_bounds__(128) k_group_sums(Lanes L, RenderParams P, Ren
   unsigned long long nans = 0;
   for (long long t = (long long)blockIdx.x * (blockDim.x >> 5) + w; t < n_tiles; t += n_warps) {
     PathRec* base = L.path + t * G;
+    const RadRec* rbase = L.rad + t * G;
     for (int k0 = 0; k0 < G; k0 += 64) {
       const int ka = k0 + lane_id, kb = ka + 32;
       double2 la0 = make_double2(0, 0), la1 = la0, lb0 = la0, lb1 = la0, pa0 = la0, pa1 = la0, pb0 = la0, pb1 = la0;
       if (ka < G) {
-        if (LAST) { la0 = __ldcs((const double2*)&base[ka].Lr); la1 = __ldcs((const double2*)&base[ka].Lb); }      // {Lr, Lg} {Lb, eta}
+        if (LAST) { la0 = __ldcs((const double2*)&rbase[ka].Lr); la1 = __ldcs((const double2*)&rbase[ka].Lb); }      // {Lr, Lg} {Lb, eta}
         if (!SINGLE) { pa0 = make_double2(__ldcs(&base[ka].pad[0]), __ldcs(&base[ka].pad[1])); pa1.x = __ldcs(&base[ka].pad[2]); }
       }
       if (kb < G) {
-        if (LAST) { lb0 = __ldcs((const double2*)&base[kb].Lr); lb1 = __ldcs((const double2*)&base[kb].Lb); }
+        if (LAST) { lb0 = __ldcs((const double2*)&rbase[kb].Lr); lb1 = __ldcs((const double2*)&rbase[kb].Lb); }
         if (!SINGLE) { pb0 = make_double2(__ldcs(&base[kb].pad[0]), __ldcs(&base[kb].pad[1])); pb1.x = __ldcs(&base[kb].pad[2]); }
       }
       if (ka < G) {
@@ -1437,12 +1447,13 @@ __global__ void __launch_bounds__(128) k_group_sums_small(Lanes L, RenderParams 
   unsigned long long nans = 0;
   for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n_tiles; t += (long long)gridDim.x * blockDim.x) {
     PathRec* base = L.path + t * G;
+    const RadRec* rbase = L.rad + t * G;
     double2 l0[GMAX], l1[GMAX];
     double p0[GMAX], p1[GMAX], p2[GMAX];
 #pragma unroll
     for (int k = 0; k < GMAX; k++) {
       if (k < G) {
-        if (LAST) { l0[k] = __ldcs((const double2*)&base[k].Lr); l1[k] = __ldcs((const double2*)&base[k].Lb); }
+        if (LAST) { l0[k] = __ldcs((const double2*)&rbase[k].Lr); l1[k] = __ldcs((const double2*)&rbase[k].Lb); }
         if (!SINGLE) { p0[k] = __ldcs(&base[k].pad[0]); p1[k] = __ldcs(&base[k].pad[1]); p2[k] = __ldcs(&base[k].pad[2]); }
       }
     }
@@ -1470,7 +1481,7 @@ __global__ void k_fold_last(Lanes L, RenderParams P, RenderCounters* ctr) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < P.lanes_active; i += (long long)gridDim.x * blockDim.x) {
     PathRec* q = L.path + i;
     double lr, lg, lb;
-    last_sample_radiance(q, lr, lg, lb, nans);
+    last_sample_radiance(L.rad + i, lr, lg, lb, nans);
     q->pad[0] += lr; q->pad[1] += lg; q->pad[2] += lb;
   }
   nans = warp_sum(nans);
@@ -1554,7 +1565,7 @@ GP_D PathRec initial_path(const RenderParams& P, long long lane) {
   s.state = 0x853c49e6748fea9bULL; s.inc = 0xda3e39cb94b95bdbULL;
   rng_set_sequence(s, (unsigned long long)tile);
   PathRec pt;
-  pt.br = pt.bg = pt.bb = 1.0; pt.Lr = pt.Lg = pt.Lb = 0; pt.eta_scale = 1.0; pt.fx = pt.fy = 0;
+  pt.br = pt.bg = pt.bb = 1.0; pt.fx = pt.fy = 0;
   pt.rng_state = s.state; pt.rng_inc = s.inc;
   pt.pix = -1; pt.sidx = 0; pt.has_sample = 0; pt.bounces = 0;
   pt.pad[0] = pt.pad[1] = pt.pad[2] = 0;

@@ -33,16 +33,18 @@ struct __align__(32) ShadowRec {  // shade -> shadow: the visibility segment + t
   int gt10, pad;
   double pad2[2];
 };
-struct __align__(32) PathRec {    // Path.Li loop state + sampler stream of the lane.  128 B = 4 sectors, grouped by who touches them:
-  double Lr, Lg, Lb, eta_scale;   // sector 0: the radiance sum — the ONE sector the shadow stage reads and writes, and the film fold reads
-  double br, bg, bb, fx;          // sector 1: throughput
-  double fy;                      // sector 2: sampler stream
+struct __align__(32) RadRec {     // the lane's radiance sum (+ the refraction scale), one sector, in an array of ITS OWN: it is what the
+  double Lr, Lg, Lb, eta_scale;   // shadow stage reads and writes and what the film fold streams over — densely, 32 of every 32 bytes
+};                                // (as a PathRec sector the fold fetched one sector of every 128-byte record: 2.6 ms per 1080p frame)
+struct __align__(32) PathRec {    // Path.Li loop state + sampler stream of the lane.  96 B = 3 sectors, grouped by who touches them:
+  double br, bg, bb, fx;          // sector 0: throughput
+  double fy;                      // sector 1: sampler stream
   unsigned long long rng_state, rng_inc;
   int bounces, sidx;
-  int pix, has_sample;            // sector 3
+  int pix, has_sample;            // sector 2
   double pad[3];                  //           uniform footprint: the lane's FilmTile as one RGB sum (film_add_uniform)
 };
-static_assert(sizeof(RayRec) == 64 && sizeof(ShadowRec) == 96 && sizeof(PathRec) == 128, "lane record layout");
+static_assert(sizeof(RayRec) == 64 && sizeof(ShadowRec) == 96 && sizeof(PathRec) == 96 && sizeof(RadRec) == 32, "lane record layout");
 
 struct TraceCounters {
   unsigned long long nodes, prims, snodes, sprims, efloat_panics, stack_overflows, t_tri, t_sph, t_gen, st_tri, st_sph, st_gen;
@@ -169,7 +171,7 @@ GP_D int quad_step(const DevScene& sc, unsigned& cur, bool& have_cur, int& sp, u
 #endif
 template <int MODE, bool COUNT, bool QUADRICS>
 __global__ void __launch_bounds__(kTraceThreads, QUADRICS ? GP_TRACE_BLOCKS : GP_TRACE_BLOCKS_TRI) k_trace(DevScene sc, RayRec* __restrict__ rays, const ShadowRec* __restrict__ srays,
-                                                            PathRec* __restrict__ paths, unsigned char* __restrict__ occluded,
+                                                            RadRec* __restrict__ rads, unsigned char* __restrict__ occluded,
                                                             const int* __restrict__ queue, const int* __restrict__ count, long long n_direct,
                                                             int stack_cap, int* work_counter, TraceCounters* ctr, unsigned long long* gt10_counter) {
   constexpr bool ANY = MODE != 0;
@@ -377,7 +379,7 @@ __global__ void __launch_bounds__(kTraceThreads, QUADRICS ? GP_TRACE_BLOCKS : GP
         occluded[lane] = hit_any ? 1 : 0;
       } else {
         const ShadowRec* sr = srays + lane;
-        PathRec* pt = paths + lane;
+        RadRec* pt = rads + lane;
         double pr = sr->pr, pg = sr->pg, pb = sr->pb;
         if (!hit_any) {
           pt->Lr += pr; pt->Lg += pg; pt->Lb += pb;
@@ -422,7 +424,7 @@ constexpr int kFlatMax = 64;
 // the any-hit kernels, which carry no best-hit state (shadow 10.5 -> 10.0 ms)
 template <int MODE, bool COUNT>
 __global__ void __launch_bounds__(kTraceThreads, MODE == 0 ? 4 : 5) k_trace_flat(DevScene sc, RayRec* __restrict__ rays, const ShadowRec* __restrict__ srays,
-                                                                 PathRec* __restrict__ paths, unsigned char* __restrict__ occluded,
+                                                                 RadRec* __restrict__ rads, unsigned char* __restrict__ occluded,
                                                                  const int* __restrict__ queue, const int* __restrict__ count, long long n_direct,
                                                                  int stack_cap, int* work_counter, TraceCounters* ctr, unsigned long long* gt10_counter) {
   constexpr bool ANY = MODE != 0;
@@ -550,7 +552,7 @@ __global__ void __launch_bounds__(kTraceThreads, MODE == 0 ? 4 : 5) k_trace_flat
       occluded[lane] = hit_any ? 1 : 0;
     } else {
       const ShadowRec* sr = srays + lane;
-      PathRec* pt = paths + lane;
+      RadRec* pt = rads + lane;
       double pr = sr->pr, pg = sr->pg, pb = sr->pb;
       if (!hit_any) {
         pt->Lr += pr; pt->Lg += pg; pt->Lb += pb;
