@@ -107,6 +107,7 @@ struct Workspace {  // per-scene render workspace, kept between gopbrt_render ca
   DevBuf<ShadowRec> sray;
   DevBuf<PathRec> path;
   DevBuf<RadRec> rad;
+  DevBuf<FilmRec> fsum;
   DevBuf<int> i32;        // queues
   DevBuf<double> tables, tilepix, frames;
   DevBuf<unsigned char> occl;
@@ -1093,7 +1094,7 @@ static int render_impl(gopbrt_scene* sc, const gopbrt_camera* cam, const gopbrt_
   const size_t table_doubles = P.mode == GOPBRT_MODE_FAST ? 0 : (size_t)P.ndims * P.spp;
   const size_t frame_doubles = P.integrator == GOPBRT_INTEGRATOR_DIRECT_LIGHTING ? (size_t)P.direct_levels * 8 : 0;
   const size_t n_seg = (size_t)P.n_seg;  // shadow segments (and shadow-queue entries) per lane
-  size_t per_lane = sizeof(RayRec) + n_seg * (sizeof(ShadowRec) + 1) + sizeof(PathRec) + sizeof(RadRec) + (8 + n_seg) * 4 + 1 + table_doubles * 8 + (P.uniform_fp ? 0 : (size_t)tpw * tph * 4 * 8) + frame_doubles * 8;
+  size_t per_lane = sizeof(RayRec) + n_seg * (sizeof(ShadowRec) + 1) + sizeof(PathRec) + sizeof(RadRec) + sizeof(FilmRec) + (8 + n_seg) * 4 + 1 + table_doubles * 8 + (P.uniform_fp ? 0 : (size_t)tpw * tph * 4 * 8) + frame_doubles * 8;
   Workspace& W = sc->ws;
   // Lane state of ONE scene handle: at most 40 % of the device's memory (GOPBRT_LANE_BUDGET_GB overrides) and 80 % of what is
   // free right now — several scenes render on one context (one per gRPC request in the reference) and must not starve each other.
@@ -1131,12 +1132,13 @@ static int render_impl(gopbrt_scene* sc, const gopbrt_camera* cam, const gopbrt_
     // the shape fields are cleared first: a failed allocation below must not leave a "same shape" workspace with null buffers
     W.lanes = 0; W.bytes_tables = 0; W.bytes_tilepix = 0;
     if (W.graph_exec) { cudaGraphExecDestroy(W.graph_exec); W.graph_exec = nullptr; W.graph_key.clear(); }
-    W.ray.release(); W.sray.release(); W.path.release(); W.rad.release(); W.i32.release(); W.tables.release(); W.tilepix.release(); W.frames.release(); W.occl.release(); W.codes.release();
+    W.ray.release(); W.sray.release(); W.path.release(); W.rad.release(); W.fsum.release(); W.i32.release(); W.tables.release(); W.tilepix.release(); W.frames.release(); W.occl.release(); W.codes.release();
     GP_CUDA(ctx, W.ray.alloc((size_t)lanes));
     GP_CUDA(ctx, W.sray.alloc(n_seg * (size_t)lanes));
     GP_CUDA(ctx, W.occl.alloc(direct_all ? n_seg * (size_t)lanes : 0));
     GP_CUDA(ctx, W.path.alloc((size_t)lanes));
     GP_CUDA(ctx, W.rad.alloc((size_t)lanes));
+    GP_CUDA(ctx, W.fsum.alloc((size_t)lanes));
     GP_CUDA(ctx, W.i32.alloc((8 + n_seg) * (size_t)lanes));
     GP_CUDA(ctx, W.codes.alloc((size_t)lanes));
     GP_CUDA(ctx, W.tables.alloc(std::max<size_t>(bt, 1)));
@@ -1154,7 +1156,7 @@ static int render_impl(gopbrt_scene* sc, const gopbrt_camera* cam, const gopbrt_
   Lanes L;
   memset(&L, 0, sizeof(L));
   L.n = lanes;
-  L.ray = W.ray.p; L.sray = W.sray.p; L.path = W.path.p; L.rad = W.rad.p;
+  L.ray = W.ray.p; L.sray = W.sray.p; L.path = W.path.p; L.rad = W.rad.p; L.fsum = W.fsum.p;
   int* ip = W.i32.p;
   Queues Q;
   memset(&Q, 0, sizeof(Q));

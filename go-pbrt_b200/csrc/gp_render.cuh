@@ -21,6 +21,7 @@ struct Lanes {
   ShadowRec* sray;  // pending visibility segment + gated light sample
   PathRec* path;    // throughput, sampler stream, film sum
   RadRec* rad;      // radiance sum + refraction scale (one sector per lane, an array of its own)
+  FilmRec* fsum;    // pixel cursor, DirectLighting segment mask, uniform-footprint film sum (likewise)
   double* tables;   // [dim][k][lane] stratified 1-D tables
   double* tilepix;  // [lane][tile pixel][4] FilmTile accumulators (one contiguous record per lane)
   long long tile_stride;  // doubles per lane = tpw * tph * 4
@@ -718,7 +719,7 @@ GP_D void film_add_sample(const Lanes& L, const RenderParams& P, long long lane,
 // additions `contribSum += L` and `filterWeightSum += 1` (film.go:241-243).  The tile is then ONE running RGB sum, kept
 // in the PathRec's spare 24 bytes (it is in registers whenever a sample retires), and the weight is the number of samples
 // the lane has retired — known in closed form.  Saves the 256-byte tile read-modify-write per sample.
-GP_D void film_add_uniform(PathRec& pt, RGB Lc) {
+GP_D void film_add_uniform(FilmRec& pt, RGB Lc) {
   pt.pad[0] += Lc.r * (1.0 * 1.0);  // L.MulScalar(sampleWeight * filterWeight)
   pt.pad[1] += Lc.g * (1.0 * 1.0);
   pt.pad[2] += Lc.b * (1.0 * 1.0);
@@ -757,7 +758,7 @@ GP_D Ray camera_ray(const RenderParams& P, double fx, double fy, double lx, doub
 // lane's tile is exhausted.
 struct PathRec;
 GP_D PathRec initial_path(const RenderParams& P, long long lane);  // defined below
-GP_D RGB direct_unwind(const Lanes& L, const RenderParams& P, long long lane, const PathRec& pt, const RadRec& rd);  // DirectLighting, defined below
+GP_D RGB direct_unwind(const Lanes& L, const RenderParams& P, long long lane, const PathRec& pt, const RadRec& rd, int seg_mask);  // DirectLighting, defined below
 GP_D bool generate_lane(const DevScene& sc, const Lanes& L, const RenderParams& P, long long lane, bool have_sample,
                         unsigned long long& cam, unsigned long long& nans, unsigned long long& culled) {
   bool go = false;
@@ -767,16 +768,19 @@ GP_D bool generate_lane(const DevScene& sc, const Lanes& L, const RenderParams& 
   PathRec pt = have_sample ? L.path[lane] : initial_path(P, lane);  // the pass's first launch starts every lane from scratch
   RadRec rd;
   rd.Lr = 0; rd.Lg = 0; rd.Lb = 0; rd.eta_scale = 1.0;
+  FilmRec fm;
+  fm.pix = -1; fm.has_sample = 0; fm.pad[0] = fm.pad[1] = fm.pad[2] = 0;
   if (have_sample) {  // every lane of the regeneration queue carries a finished sample
     rd = L.rad[lane];
-    RGB Lc = P.integrator == 1 ? direct_unwind(L, P, lane, pt, rd) : rgb(rd.Lr, rd.Lg, rd.Lb);
+    fm = L.fsum[lane];
+    RGB Lc = P.integrator == 1 ? direct_unwind(L, P, lane, pt, rd, fm.has_sample) : rgb(rd.Lr, rd.Lg, rd.Lb);
     if (is_nan(Lc.r) || is_nan(Lc.g) || is_nan(Lc.b)) { Lc = rgb(0.1, 0.1, 0.1); nans++; }  // integrator.go:256-257
-    if (P.uniform_fp) film_add_uniform(pt, Lc);
+    if (P.uniform_fp) film_add_uniform(fm, Lc);
     else film_add_sample(L, P, lane, tile, pt.fx, pt.fy, Lc);
   }
   Smp s;
   s.state = pt.rng_state; s.inc = pt.rng_inc; s.sidx = pt.sidx; s.cur1 = 0; s.cur2 = 0; s.lane = lane;
-  int pix = pt.pix;
+  int pix = fm.pix;
   long long x0, y0, x1, y1;
   tile_bounds(P, tile, &x0, &y0, &x1, &y1);
   long long tw = x1 - x0, area = tw * (y1 - y0);
@@ -841,14 +845,15 @@ GP_D bool generate_lane(const DevScene& sc, const Lanes& L, const RenderParams& 
     pt.br = 1.0; pt.bg = 1.0; pt.bb = 1.0;
     rd.eta_scale = 1.0;
     pt.bounces = (s.cur1 << 8) | (s.cur2 << 16);  // bounces in bits 0-7, sampler dimensions above
-    pt.has_sample = 0;  // DirectLighting / UniformSampleAll: no shadow segments pending
+    fm.has_sample = 0;  // DirectLighting / UniformSampleAll: no shadow segments pending
     go = true;
     break;
   }
-  pt.rng_state = s.state; pt.rng_inc = s.inc; pt.sidx = s.sidx; pt.pix = pix;
+  pt.rng_state = s.state; pt.rng_inc = s.inc; pt.sidx = s.sidx; fm.pix = pix;
   if (P.last_in_place && !go) { rd.Lr = 0; rd.Lg = 0; rd.Lb = 0; }  // no sample in flight: the film fold adds pad + L
   L.path[lane] = pt;
   L.rad[lane] = rd;
+  L.fsum[lane] = fm;
   return go;
 }
 
@@ -988,7 +993,7 @@ GP_D void shade_lane(const DevScene& sc, const Lanes& L, const RenderParams& P, 
       Smp s;
       s.state = pt.rng_state; s.inc = pt.rng_inc; s.sidx = pt.sidx;
       s.cur1 = (packed >> 8) & 255; s.cur2 = (packed >> 16) & 255; s.lane = lane;
-      const unsigned long long fast_pixel = P.mode == 1 ? lane_fast_pixel(P, lane, pt.pix) : 0ULL;
+      const unsigned long long fast_pixel = P.mode == 1 ? lane_fast_pixel(P, lane, P.tile_size == 1 ? 0 : L.fsum[lane].pix) : 0ULL;
       RGB beta = rgb(pt.br, pt.bg, pt.bb);
       Intr ref; ref.p = h.p; ref.perr = h.perr; ref.n = h.n;
       // --- UniformSampleOneLight (integrator.go:48-77), skipped for perfectly specular BSDFs (path.go:84)
@@ -1113,9 +1118,9 @@ constexpr int kDirectHitBit = 1 << 24;  // PathRec.bounces: the chain ended AT a
 // UniformSampleAll: the level's direct light is the sum over the lights, in light order, of the segments the shadow
 // stage found unoccluded (L.AddAssign(EstimateDirect(...)) per light, integrator.go:23-46); pt.has_sample holds the
 // mask of the segments that were emitted.  UniformSampleOne: the shadow stage has already added its single segment.
-GP_D void direct_collect(const Lanes& L, const RenderParams& P, long long lane, PathRec& pt, RadRec& rd) {
+GP_D void direct_collect(const Lanes& L, const RenderParams& P, long long lane, int& seg_mask_io, RadRec& rd) {
   if (!P.direct_all) return;
-  unsigned mask = (unsigned)pt.has_sample;
+  unsigned mask = (unsigned)seg_mask_io;
   for (int j = 0; j < P.n_seg; j++) {
     if (!((mask >> j) & 1u)) continue;
     size_t e = (size_t)lane * P.n_seg + j;
@@ -1123,7 +1128,7 @@ GP_D void direct_collect(const Lanes& L, const RenderParams& P, long long lane, 
     const ShadowRec* sr = L.sray + e;
     rd.Lr += sr->pr; rd.Lg += sr->pg; rd.Lb += sr->pb;
   }
-  pt.has_sample = 0;
+  seg_mask_io = 0;
 }
 
 // ALL = true: returns in seg_mask the segments (one per light) written to L.sray[lane * n_seg + j]
@@ -1133,7 +1138,8 @@ GP_D void shade_lane_direct(const DevScene& sc, const Lanes& L, const RenderPara
   PathRec pt = L.path[lane];
   RadRec rd = L.rad[lane];
   RayRec rr = L.ray[lane];
-  if (ALL) direct_collect(L, P, lane, pt, rd);
+  int has_sample = 0;  // the pending-segment mask (UniformSampleAll only)
+  if (ALL) { has_sample = L.fsum[lane].has_sample; direct_collect(L, P, lane, has_sample, rd); }
   int packed = pt.bounces;
   const int level = packed & 255;  // frames filed so far == specular bounces taken; Li's depth argument is 2 * level
   double* fr = L.frames + ((size_t)lane * P.direct_levels) * 8;
@@ -1157,7 +1163,7 @@ GP_D void shade_lane_direct(const DevScene& sc, const Lanes& L, const RenderPara
     Smp s;
     s.state = pt.rng_state; s.inc = pt.rng_inc; s.sidx = pt.sidx;
     s.cur1 = (packed >> 8) & 255; s.cur2 = (packed >> 16) & 255; s.lane = lane;
-    const unsigned long long fast_pixel = P.mode == 1 ? lane_fast_pixel(P, lane, pt.pix) : 0ULL;
+    const unsigned long long fast_pixel = P.mode == 1 ? lane_fast_pixel(P, lane, P.tile_size == 1 ? 0 : L.fsum[lane].pix) : 0ULL;
     Intr ref; ref.p = h.p; ref.perr = h.perr; ref.n = h.n;
     // --- direct light (directlighting.go:85-96): UniformSampleOneLight (integrator.go:48-77) or, ALL, every light once
     //     (UniformSampleAllLights' single-sample branch, integrator.go:31-36: uLight then uScattering per light)
@@ -1205,7 +1211,7 @@ GP_D void shade_lane_direct(const DevScene& sc, const Lanes& L, const RenderPara
           }
         }
       }
-      if (ALL) pt.has_sample = (int)seg_mask;
+      if (ALL) has_sample = (int)seg_mask;
     }
     // --- specular recursion (directlighting.go:98-102): both terms draw their Get2D before anything else
     if (2 * level + 1 < P.max_depth) {
@@ -1256,16 +1262,16 @@ GP_D void shade_lane_direct(const DevScene& sc, const Lanes& L, const RenderPara
   PathRec* const pp = L.path + lane;
   RadRec* const rp = L.rad + lane;
   rp->Lr = rd.Lr; rp->Lg = rd.Lg; rp->Lb = rd.Lb;
-  pp->has_sample = pt.has_sample;
+  if (ALL) L.fsum[lane].has_sample = has_sample;
   pp->rng_state = pt.rng_state;
   pp->bounces = packed;
 }
 
 // the radiance of a finished DirectLighting sample: the chain of frames unwound (see shade_lane_direct)
-GP_D RGB direct_unwind(const Lanes& L, const RenderParams& P, long long lane, const PathRec& pt_in, const RadRec& rd_in) {
+GP_D RGB direct_unwind(const Lanes& L, const RenderParams& P, long long lane, const PathRec& pt_in, const RadRec& rd_in, int seg_mask) {
   PathRec pt = pt_in;
   RadRec rd = rd_in;
-  direct_collect(L, P, lane, pt, rd);
+  direct_collect(L, P, lane, seg_mask, rd);
   const int level = pt.bounces & 255;
   const bool at_hit = (pt.bounces & kDirectHitBit) != 0;
   const double* fr = L.frames + ((size_t)lane * P.direct_levels) * 8;
@@ -1398,7 +1404,7 @@ __global__ void __launch_bounds__(128) k_group_sums(Lanes L, RenderParams P, Ren
   const long long n_warps = (long long)gridDim.x * (blockDim.x >> 5);
   unsigned long long nans = 0;
   for (long long t = (long long)blockIdx.x * (blockDim.x >> 5) + w; t < n_tiles; t += n_warps) {
-    PathRec* base = L.path + t * G;
+    FilmRec* base = L.fsum + t * G;
     const RadRec* rbase = L.rad + t * G;
     for (int k0 = 0; k0 < G; k0 += 64) {
       const int ka = k0 + lane_id, kb = ka + 32;
@@ -1446,7 +1452,7 @@ __global__ void __launch_bounds__(128) k_group_sums_small(Lanes L, RenderParams 
   const long long n_tiles = P.lanes_active / G;
   unsigned long long nans = 0;
   for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n_tiles; t += (long long)gridDim.x * blockDim.x) {
-    PathRec* base = L.path + t * G;
+    FilmRec* base = L.fsum + t * G;
     const RadRec* rbase = L.rad + t * G;
     double2 l0[GMAX], l1[GMAX];
     double p0[GMAX], p1[GMAX], p2[GMAX];
@@ -1479,7 +1485,7 @@ __global__ void __launch_bounds__(128) k_group_sums_small(Lanes L, RenderParams 
 __global__ void k_fold_last(Lanes L, RenderParams P, RenderCounters* ctr) {
   unsigned long long nans = 0;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < P.lanes_active; i += (long long)gridDim.x * blockDim.x) {
-    PathRec* q = L.path + i;
+    FilmRec* q = L.fsum + i;
     double lr, lg, lb;
     last_sample_radiance(L.rad + i, lr, lg, lb, nans);
     q->pad[0] += lr; q->pad[1] += lg; q->pad[2] += lb;
@@ -1532,7 +1538,7 @@ __global__ void k_film_merge(Lanes L, RenderParams P, double* __restrict__ film)
           if (lane < 0 || lane >= P.lanes_active) continue;
           double r, g, b, w;
           if (P.uniform_fp) {
-            const PathRec* pt = L.path + lane;
+            const FilmRec* pt = L.fsum + lane;
             r = pt->pad[0]; g = pt->pad[1]; b = pt->pad[2];
             // filterWeightSum = the samples this lane retired: indices 1 .. spp-1 (sampler.go:29-34) with
             // s % (s_world * groups) == s_rank * groups + grp (pre-reduced groups: s % s_world == s_rank)
@@ -1567,8 +1573,7 @@ GP_D PathRec initial_path(const RenderParams& P, long long lane) {
   PathRec pt;
   pt.br = pt.bg = pt.bb = 1.0; pt.fx = pt.fy = 0;
   pt.rng_state = s.state; pt.rng_inc = s.inc;
-  pt.pix = -1; pt.sidx = 0; pt.has_sample = 0; pt.bounces = 0;
-  pt.pad[0] = pt.pad[1] = pt.pad[2] = 0;
+  pt.sidx = 0; pt.bounces = 0;
   return pt;
 }
 

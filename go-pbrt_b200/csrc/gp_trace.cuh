@@ -36,15 +36,17 @@ struct __align__(32) ShadowRec {  // shade -> shadow: the visibility segment + t
 struct __align__(32) RadRec {     // the lane's radiance sum (+ the refraction scale), one sector, in an array of ITS OWN: it is what the
   double Lr, Lg, Lb, eta_scale;   // shadow stage reads and writes and what the film fold streams over — densely, 32 of every 32 bytes
 };                                // (as a PathRec sector the fold fetched one sector of every 128-byte record: 2.6 ms per 1080p frame)
-struct __align__(32) PathRec {    // Path.Li loop state + sampler stream of the lane.  96 B = 3 sectors, grouped by who touches them:
+struct __align__(32) FilmRec {    // what only the raygen stage and the film fold / merge touch (and the DirectLighting segment mask),
+  int pix, has_sample;            // likewise an array of its own: the shade stage then reads and writes EVERY byte of the PathRecs it
+  double pad[3];                  // fetches.  pad: uniform footprint, the lane's FilmTile as one RGB sum (film_add_uniform)
+};
+struct __align__(32) PathRec {    // Path.Li loop state + sampler stream of the lane.  64 B = 2 sectors
   double br, bg, bb, fx;          // sector 0: throughput
   double fy;                      // sector 1: sampler stream
   unsigned long long rng_state, rng_inc;
   int bounces, sidx;
-  int pix, has_sample;            // sector 2
-  double pad[3];                  //           uniform footprint: the lane's FilmTile as one RGB sum (film_add_uniform)
 };
-static_assert(sizeof(RayRec) == 64 && sizeof(ShadowRec) == 96 && sizeof(PathRec) == 96 && sizeof(RadRec) == 32, "lane record layout");
+static_assert(sizeof(RayRec) == 64 && sizeof(ShadowRec) == 96 && sizeof(PathRec) == 64 && sizeof(RadRec) == 32 && sizeof(FilmRec) == 32, "lane record layout");
 
 struct TraceCounters {
   unsigned long long nodes, prims, snodes, sprims, efloat_panics, stack_overflows, t_tri, t_sph, t_gen, st_tri, st_sph, st_gen;
