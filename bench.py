@@ -385,11 +385,11 @@ def main():
                             "shape_tests": cst["prim_tests"] / max(1, ext_rays)},
                 "stage_ms_per_step": {k: sum(s[k] for s in stage_stats) / KS for k in ("ms_raygen", "ms_extend", "ms_shade", "ms_shadow", "ms_film")}}
         # ---- the kernel that dominates THIS frame.  On the headline workload (36 primitives: the aggregate is a shared-memory table)
-        # that is the shade stage, whose bytes all come from and go to HBM: per shaded lane it reads three sectors of the lane's
-        # PathRec (96 B: radiance / throughput / sampler state — the fourth, the raygen stage's film sum, is not touched), the
-        # RayRec (64 B) and the queue entry (4 B) and writes the sampler-state sector back (32 B); a lane that continues also
-        # writes its throughput sector, a new RayRec and its queue entry (32 + 64 + 4 B), a lane with a light sample a
-        # ShadowRec and its queue entry (96 + 4 B) — DESIGN.md §4.
+        # that is the shade stage, whose bytes all come from and go to HBM: per shaded lane it reads the lane's PathRec (64 B:
+        # throughput, sampler state), the refraction scale in its RadRec sector (32 B), the RayRec (64 B) and the queue entry
+        # (4 B) and writes the sampler-state sector back (32 B); a lane that continues also writes its throughput sector, a new
+        # RayRec and its queue entry (32 + 64 + 4 B), a lane with a light sample a ShadowRec and its queue entry (96 + 4 B) —
+        # DESIGN.md §4.
         # (ms_shade = k_split_hits + the shade-class kernels of every iteration.)  The extend kernel stays on the line as
         # roofline_extend: its SURVEY §8d "algorithmic bytes" are table bytes that never leave the SM here, so their rate is not
         # a fraction of an HBM roof — for the HBM-resident tree see roofline_deep_bvh.
@@ -428,7 +428,7 @@ def main():
                     "stage_ms_per_step": roof_ext["stage_ms_per_step"]}
         else:
             roof_ext = None
-        lane_bytes = 64 + 96 + 128 + 36 + 1 + (0 if mode == abi.MODE_FAST else 4 * wl["spp"][0] * wl["spp"][1] * 8)
+        lane_bytes = 64 + 96 + (64 + 32 + 32) + 36 + 1 + (0 if mode == abi.MODE_FAST else 4 * wl["spp"][0] * wl["spp"][1] * 8)
         line = {"metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": K, "warmup": max(args.min_warmup, args.warmup),
                 "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic", "config": config,
