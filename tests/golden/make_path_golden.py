@@ -1,0 +1,424 @@
+"""An INDEPENDENT restatement of the COMPOSED hot path — pbrt.Render -> renderWorker -> Path.Li -> UniformSampleOneLight ->
+EstimateDirect -> FilmTile.AddSample -> MergeFilmTile — in plain Python floats, for scenes of disks, matte surfaces and
+point lights.
+
+Why: the reference cannot run in this image (no Go toolchain) and holds no golden film.  The per-function known answers
+(make_shading_kats.py) pin the functions one by one; what they cannot pin is how Path.Li COMPOSES them (the order of the
+sampler draws, `bounces++` first, wo = ray.Direction, the local wi handed to SpawnRay, the dropped DivScalar, the shadow
+ray that starts ON the surface, the shared pointers inside TransformSurfaceInteraction, the tile loop's seeds).  The
+oracle (oracle/*.h) and the CUDA path were written by the same builder; this file is the third reading of the same Go
+source, written from the Go files cited below and from nothing under oracle/ or go-pbrt_b200/csrc/.  It renders two small
+films; tests/test_path_golden.py then requires the oracle (CPU) and the CUDA path (GPU, through the C ABI) to reproduce
+them BIT FOR BIT, ray counts included.
+
+What it takes from elsewhere, and why that does not weaken it:
+ * the per-function restatements of make_shading_kats.py (same independence rule; each is itself pinned as a KAT);
+ * the 4x4 matrices of the camera and of the shapes, as DATA, from the host mirror go-pbrt_b200/pbrt.py (LookAt,
+   Perspective, RotateX, Inverse — host-side constructors that run once per scene, outside the hot path);
+ * sin/cos from go-pbrt_b200/gomath.py (Go's math.Sin/Cos are not libm's; pinned by transform_test.go:77-81).
+ math.Atan2 (disk.go:83) is NOT needed bit-exactly here: for a full disk phi only feeds `phi > phiMax`, which cannot fire
+ (phi + 2*Pi rounds to at most 2*Pi == Radians(360), asserted below), and u, which only constant textures read.
+
+    python tests/golden/make_path_golden.py        # rewrites tests/golden/path_golden.json
+"""
+import importlib
+import importlib.util
+import json
+import math
+import os
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+_spec = importlib.util.spec_from_file_location("make_shading_kats", os.path.join(HERE, "make_shading_kats.py"))
+K = importlib.util.module_from_spec(_spec)
+_spec.loader.exec_module(K)
+gomath = K.gomath
+COS, SIN = gomath.Cos, gomath.Sin
+INF = float("inf")
+SHADOW_EPSILON = 0.0001  # pkg/math/math.go
+Z3 = [0.0, 0.0, 0.0]
+
+
+# ---------------------------------------------------------------- the scene, shared with the tests (host-mirror objects)
+def scene_and_integrator(gp, tile_note=None):
+    """Four matte disks (floor, ceiling, an annulus at object height 0.25, one tilted by RotateX) and two point lights;
+    16x12 pixels, Stratified 3x3 with jitter, 2 sampled dimensions (every later draw comes from the tile's RNG), Path
+    maxDepth 6, rrThreshold 1 (Russian roulette is live from the fourth bounce on)."""
+    P, S = gp.pbrt, gp.scenes
+    zero = P.NewConstantFloatTexture(0.0)
+
+    def matte(r, g, b):
+        return P.NewMatteMaterial(P.NewConstantSpectrumTexture(P.NewRGBSpectrum(r, g, b)), zero)
+
+    prims = [
+        P.NewGeometricPrimitive(P.NewDisk(P.Translate((0.0, 0.0, 0.0)), 0.0, 6.0, 0.0, 360), matte(0.7, 0.6, 0.5)),
+        P.NewGeometricPrimitive(P.NewDisk(P.Translate((0.5, -0.3, 5.0)), 0.0, 7.0, 0.0, 360), matte(0.8, 0.8, 0.8)),
+        P.NewGeometricPrimitive(P.NewDisk(P.Translate((1.0, 0.5, 2.0)), 0.25, 1.5, 0.5, 360), matte(0.3, 0.6, 0.9)),
+        P.NewGeometricPrimitive(P.NewDisk(P.Translate((-2.0, 1.0, 1.5)).Mul(P.RotateX(40)), 0.0, 1.2, 0.0, 360), matte(0.9, 0.4, 0.3)),
+    ]
+    lights = [P.NewPoint(P.Translate((0.3, 0.2, 4.0)), None, P.NewSpectrum(25.0)),
+              P.NewPoint(P.Translate((-3.0, -2.0, 1.0)), None, P.NewRGBSpectrum(8.0, 6.0, 4.0))]
+    scene = P.NewScene(P.NewBVH(prims, 1, P.SplitSAH), lights)
+    W, H = 16, 12
+    cam = S._camera((7.0, -6.0, 3.5), (0.0, 0.0, 1.5), (0.0, 0.0, 1.0), 50.0, W, H)
+    integ = P.NewPath(6, cam, P.NewStratified(3, 3, True, 2), None, 1.0, P.Uniform)
+    return scene, integ
+
+
+TILE_SIZES = (1, 5)   # 5 leaves ragged tiles on both axes (16 = 3*5 + 1, 12 = 2*5 + 2) and gives tiles more than one pixel
+
+
+def plain_scene(scene, integ):
+    """the same scene as plain numbers"""
+    disks = []
+    for gpr in scene.aggregate.primitives:
+        sh, mt = gpr.Shape, gpr.material
+        assert type(sh).__name__ == "Disk" and type(mt).__name__ == "MatteMaterial" and mt.sigma.value == 0.0
+        m, minv = sh.objectToWorld.Matrix.m, sh.objectToWorld.MatrixInverse.m
+        phi_max = K.radians(K.clamp(float(sh.phiMax), 0.0, 360.0))   # disk.go:34
+        assert phi_max == 2 * math.pi
+        d = dict(m=m, minv=minv, height=float(sh.height), radius=float(sh.radius), inner=float(sh.innerRadius), phi_max=phi_max,
+                 kd=[K.clamp(c, 0.0, INF) for c in mt.Kd.value])   # matte.go:29
+        d["bound"] = disk_world_bound(d)
+        disks.append(d)
+    lights = [dict(p=list(map(float, l.pLight)), I=list(l.I)) for l in scene.lights]
+    cam = integ.GetCamera()
+    film = cam.GetFilm()
+    smp = integ.GetSampler()
+    return dict(disks=disks, lights=lights, r2c=cam.RasterToCamera.Matrix.m, c2w=cam.cameraToWorld.startTransform.Matrix.m,
+                lens_radius=cam.lensRadius, focal=cam.focalDistance, res=film.FullResolution, crop=film.CroppedPixelBounds,
+                fr=film.Filter.radius, nx=smp.xSamples, ny=smp.ySamples, jitter=smp.jitter, ndims=smp.nDims,
+                max_depth=integ.maxDepth, rr=integ.rrThreshold)
+
+
+# ---------------------------------------------------------------- bounds.go:114-120,149-192,209-219; transform.go:335-344
+def disk_world_bound(d):
+    """Disk.ObjectBound (disk.go:40-53) through Transform.TransformBounds"""
+    lo, hi = [-d["radius"], -d["radius"], d["height"]], [d["radius"], d["radius"], d["height"]]
+    pick = lambda i: [(lo, hi)[i & 1][0], (lo, hi)[(i & 2) // 2][1], (lo, hi)[(i & 4) // 4][2]]
+    c, _ = K.transform_point(d["m"], lo, Z3)
+    bmin, bmax = list(c), list(c)
+    for i in range(1, 8):
+        c, _ = K.transform_point(d["m"], pick(i), Z3)
+        bmin = [K.go_min(bmin[k], c[k]) for k in range(3)]
+        bmax = [K.go_max(bmax[k], c[k]) for k in range(3)]
+    return bmin, bmax
+
+
+def go_div(a, b):  # Go float division: x/0 = +-Inf, 0/0 = NaN (Python raises)
+    if b == 0.0:
+        if a == 0.0 or a != a:
+            return float("nan")
+        return math.copysign(INF, a) * math.copysign(1.0, b)
+    return a / b
+
+
+def bounds_intersect_p(b, o, tmax, inv, neg):  # bounds.go:149-192
+    g = 1 + 2 * K.gamma(3.0)
+    t0 = (b[neg[0]][0] - o[0]) * inv[0]
+    t1 = (b[1 - neg[0]][0] - o[0]) * inv[0]
+    ty0 = (b[neg[1]][1] - o[1]) * inv[1]
+    ty1 = (b[1 - neg[1]][1] - o[1]) * inv[1]
+    t1 *= g
+    ty1 *= g
+    if t0 > ty1 or ty0 > t1:
+        return False
+    if ty0 > t0:
+        t0 = ty0
+    if ty1 < t1:
+        t1 = ty1
+    tz0 = (b[neg[2]][2] - o[2]) * inv[2]
+    tz1 = (b[1 - neg[2]][2] - o[2]) * inv[2]
+    tz1 *= g
+    if t0 > tz1 or tz0 > t1:
+        return False
+    if tz0 > t0:
+        t0 = tz0
+    if tz1 < t1:
+        t1 = tz1
+    return t0 < tmax and t1 > 0
+
+
+# ---------------------------------------------------------------- disk.go:64-158, interaction.go:171-206, transform.go:302-333
+def disk_plane_hit(d, o, w, tmax):
+    """the part Intersect and IntersectP share (disk.go:64-91 / 132-157): object-space ray, t, pHit — or None"""
+    ro, rd = K.transform_ray(d["minv"], o, w)
+    if rd[2] == 0:
+        return None
+    t = (d["height"] - ro[2]) / rd[2]
+    if t <= 0 or t >= tmax:
+        return None
+    ph = [ro[0] + rd[0] * t, ro[1] + rd[1] * t, ro[2] + rd[2] * t]   # ray.go PointAt: Origin.Add(Direction.MulScalar(t))
+    dist2 = ph[0] * ph[0] + ph[1] * ph[1]
+    if dist2 > d["radius"] * d["radius"] or dist2 < d["inner"] * d["inner"]:
+        return None
+    # phi = Atan2(y, x) (+ 2 Pi when negative) never exceeds phiMax = 2 Pi: see the module docstring
+    return t, ph, dist2, rd
+
+
+def disk_intersect(d, o, w, tmax):
+    r = disk_plane_hit(d, o, w, tmax)
+    if r is None:
+        return None
+    t, ph, dist2, rd = r
+    r_hit = math.sqrt(dist2)
+    dpdu = [-d["phi_max"] * ph[1], d["phi_max"] * ph[0], 0.0]
+    k = (d["radius"] - d["inner"]) / r_hit
+    dpdv = [ph[0] * k, ph[1] * k, 0.0 * k]
+    ph[2] = d["height"]
+    # NewSurfaceInteractionWith (interaction.go:171-206): one normal object serves Normal and Shading.Normal;
+    # reverseOrientation == transformSwapsHandedness (both false for a Disk, disk.go:27-28): no flip
+    n_obj = K.v_normalized(K.v_cross(dpdu, dpdv))
+    wo_obj = K.v_muls(rd, -1.0)
+    # TransformSurfaceInteraction (transform.go:302-333): `ret := *si` shares si.interaction and si.Shading; Normal is REPLACED
+    # by the normalised transformed normal, Shading.Normal still points at the object-space one and is transformed WITHOUT
+    # normalising, then face-forwarded; Shading.dpdu = the transformed object-space dpdu
+    p, perr = K.transform_point(d["m"], ph, Z3)
+    n = K.v_normalized(K.transform_normal(d["minv"], n_obj))
+    wo = K.v_normalized(K.transform_vector(d["m"], wo_obj))
+    ns = K.face_forward(K.transform_normal(d["minv"], n_obj), n)
+    sh_dpdu = K.transform_vector(d["m"], dpdu)
+    return t, dict(p=p, perr=perr, n=n, wo=wo, ns=ns, sh_dpdu=sh_dpdu, disk=d)
+
+
+class Scene:
+    """scene.go:38-46 over a BVH whose leaves hold one primitive (maxPrimsInNode 1): a primitive is reached iff its own
+    world bound passes Bounds3.IntersectP with the ray's CURRENT tMax (bvh.go:659-712; GeometricPrimitive.Intersect
+    shortens it, primitive.go:50-55).  The scene has no two surfaces a ray could meet at distances closer than the slab
+    arithmetic's rounding, so the visiting order (here: primitive index) cannot change an answer."""
+
+    def __init__(self, disks):
+        self.disks = disks
+        self.closest = 0
+        self.shadow = 0
+
+    @staticmethod
+    def _inv(w):
+        inv = [go_div(1.0, w[0]), go_div(1.0, w[1]), go_div(1.0, w[2])]
+        return inv, [1 if c < 0 else 0 for c in inv]   # bvh.go:665-666, xyz.go:545-556
+
+    def intersect(self, o, w, tmax):
+        self.closest += 1
+        inv, neg = self._inv(w)
+        best = None
+        for d in self.disks:
+            if bounds_intersect_p(d["bound"], o, tmax, inv, neg):
+                r = disk_intersect(d, o, w, tmax)
+                if r is not None:
+                    tmax, best = r
+        return best
+
+    def intersect_p(self, o, w, tmax):
+        self.shadow += 1
+        inv, neg = self._inv(w)
+        for d in self.disks:
+            if bounds_intersect_p(d["bound"], o, tmax, inv, neg) and disk_plane_hit(d, o, w, tmax) is not None:
+                return True
+        return False
+
+
+# ---------------------------------------------------------------- reflection.go:128-298 over one Lambertian lobe
+class BSDF:
+    def __init__(self, hit):  # NewBSDF (reflection.go:128-140) + matte.go:27-37
+        self.ns, self.ng = hit["ns"], hit["n"]
+        self.ss = K.v_normalized(hit["sh_dpdu"])
+        self.ts = K.v_cross(self.ns, self.ss)
+        self.r = hit["disk"]["kd"]
+        self.n_lobes = 0 if all(c == 0.0 for c in self.r) else 1
+
+    def to_local(self, v):  # :147-149
+        return [K.v_dot(v, self.ss), K.v_dot(v, self.ts), K.v_dot(v, self.ns)]
+
+    def f(self, wo_w, wi_w):  # BSDF.F :170-187 with flags = All &^ Specular; LambertianReflection.F :589-591
+        wi, wo = self.to_local(wi_w), self.to_local(wo_w)
+        if wo[2] == 0.0:
+            return list(Z3)
+        reflect = K.v_dot(wi_w, self.ng) * K.v_dot(wo_w, self.ng) > 0
+        f = list(Z3)
+        if self.n_lobes and reflect:
+            f = [f[i] + self.r[i] * K.INV_PI for i in range(3)]
+        return f
+
+    def pdf(self, wo_w, wi_w):  # :255-277 + :343-348
+        if self.n_lobes == 0:
+            return 0.0
+        wo, wi = self.to_local(wo_w), self.to_local(wi_w)
+        if wo[2] == 0:
+            return 0.0
+        return (abs(wi[2]) * K.INV_PI if wo[2] * wi[2] > 0 else 0.0) / 1.0
+
+    def sample_f(self, wo_w, u):  # :189-253 — returns the LOCAL wi (wiWorld is computed and dropped)
+        if self.n_lobes == 0:
+            return list(Z3), list(Z3), 0.0
+        return K.lambert_sample_f(self.r, self.to_local(wo_w), u, COS, SIN)
+
+
+# ---------------------------------------------------------------- pixel.go:55-76, sampler.go:21-35,71-77, stratified.go:21-48
+class TileSampler:
+    def __init__(self, sc, seed):
+        self.sc = sc
+        self.rng = K.Rng()
+        self.rng.set_sequence(seed)   # pixel.go:41 (clone)
+        self.t1, self.idx, self.d1, self.d2 = None, 0, 0, 0
+
+    def start_pixel(self):
+        self.t1 = K.stratified_start_pixel(self.rng, self.sc["nx"], self.sc["ny"], self.sc["jitter"], self.sc["ndims"])
+        self.idx = 0   # sampler.go:21-27
+
+    def start_next_sample(self):  # pixel.go:49-53 + sampler.go:29-35: the index moves BEFORE the first sample
+        self.d1 = self.d2 = 0
+        self.idx += 1
+        return self.idx < self.sc["nx"] * self.sc["ny"]
+
+    def get1d(self):
+        if self.d1 < self.sc["ndims"]:
+            v = self.t1[self.d1][self.idx]
+            self.d1 += 1
+            return v
+        return self.rng.uniform()
+
+    def get2d(self):
+        if self.d2 < self.sc["ndims"]:
+            self.d2 += 1
+            return [0.0, 0.0]   # the 2-D tables are never filled (sampling.go:122-124 shuffles a copy)
+        x = self.rng.uniform()
+        y = self.rng.uniform()
+        return [x, y]
+
+
+# ---------------------------------------------------------------- integrator.go:46-195 (point lights: delta, no MIS leg)
+def estimate_direct(hit, bsdf, light, scene, stats):
+    Li, wi, light_pdf, lp, lperr, ln, _ = K.light_sample_li(dict(kind="point", p=light["p"], I=light["I"]), hit["p"], hit["perr"], hit["n"],
+                                                         None, COS, SIN)
+    Ld = list(Z3)
+    if light_pdf > 0 and not all(c == 0.0 for c in Li):
+        f = bsdf.f(hit["wo"], wi)
+        k = abs(K.v_dot(wi, hit["ns"]))
+        f = [c * k for c in f]
+        bsdf.pdf(hit["wo"], wi)   # scatteringPdf: computed, unused for a delta light
+        if not all(c == 0.0 for c in f):
+            o, w = K.spawn_ray_to(hit["p"], hit["perr"], hit["n"], lp, lperr, ln)   # origin = the un-offset point
+            if scene.intersect_p(o, w, 1 - SHADOW_EPSILON):
+                Li = list(Z3)
+            if not all(c == 0.0 for c in Li):
+                Ld = [Ld[i] + (f[i] * Li[i]) / light_pdf for i in range(3)]
+    return Ld
+
+
+def uniform_sample_one_light(hit, bsdf, sc, scene, smp, stats):
+    n = len(sc["lights"])
+    if n == 0:
+        return list(Z3)
+    num, pdf = K.sample_discrete([1.0] * n, smp.get1d())   # lightdistribution.go:24-34, sampling.go:42-55
+    if pdf == 0.0:
+        return list(Z3)
+    smp.get2d()   # uLight (a point light reads neither)
+    smp.get2d()   # uScattering
+    Ld = estimate_direct(hit, bsdf, sc["lights"][num], scene, stats)
+    # integrator.go:71: spectrum.DivScalar(lightPdf) returns a NEW spectrum that is dropped; :72-74 panics above 10
+    stats["max_direct"] = max(stats["max_direct"], max(Ld))
+    return Ld
+
+
+# ---------------------------------------------------------------- path.go:32-157
+def path_li(o, w, sc, scene, smp, stats):
+    L, beta = list(Z3), [1.0, 1.0, 1.0]
+    tmax = INF
+    bounces = 0
+    eta_scale = 1.0
+    while True:
+        bounces += 1
+        hit = scene.intersect(o, w, tmax)
+        # `bounces == 0 || specularBounce` is never true here: no emitted radiance is ever added
+        if hit is None or bounces >= sc["max_depth"]:
+            break
+        bsdf = BSDF(hit)
+        if bsdf.n_lobes > 0:   # NumComponents(All &^ Specular)
+            Ld = uniform_sample_one_light(hit, bsdf, sc, scene, smp, stats)
+            L = [L[i] + beta[i] * Ld[i] for i in range(3)]
+        f, wi, pdf = bsdf.sample_f(w, smp.get2d())   # wo := ray.Direction (path.go:92)
+        if all(c == 0.0 for c in f) or pdf == 0.0:
+            break
+        k = abs(K.v_dot(wi, hit["ns"])) / pdf
+        beta = [beta[i] * (f[i] * k) for i in range(3)]
+        o = K.offset_ray_origin(hit["p"], hit["perr"], hit["n"], wi)   # isect.SpawnRay(wi), wi still LOCAL
+        w, tmax = wi, INF
+        rr = [c * eta_scale for c in beta]
+        m = K.go_max(K.go_max(rr[0], rr[1]), rr[2])
+        if m < sc["rr"] and bounces > 3:
+            q = K.go_max(0.05, 1 - m)
+            if smp.get1d() < q:
+                break
+            beta = [c / (1 - q) for c in beta]
+    return L
+
+
+# ---------------------------------------------------------------- integrator.go:228-350, film.go:106-140,211-248
+def render(sc, tile_size):
+    x0, y0, x1, y1 = sc["crop"]
+    W, H = x1 - x0, y1 - y0
+    film = [[[0.0, 0.0, 0.0, 0.0] for _ in range(W)] for _ in range(H)]
+    scene = Scene(sc["disks"])
+    stats = dict(max_direct=0.0, camera=0)
+    ntx, nty = (W + tile_size - 1) // tile_size, (H + tile_size - 1) // tile_size
+    for ty in range(nty):
+        for tx in range(ntx):
+            smp = TileSampler(sc, ty * ntx + tx)
+            bx0, by0 = x0 + tx * tile_size, y0 + ty * tile_size
+            bx1, by1 = int(K.go_min(float(bx0 + tile_size), float(x1))), int(K.go_min(float(by0 + tile_size), float(y1)))
+            tile = {}
+            pb = None
+            for py in range(by0, by1):
+                for px in range(bx0, bx1):
+                    smp.start_pixel()
+                    while smp.start_next_sample():
+                        off = smp.get2d()
+                        p_film = [float(px) + off[0], float(py) + off[1]]   # sampler.go:71-77
+                        p_lens = smp.get2d()
+                        smp.get1d()   # time: shutterClose == shutterOpen == 0 and nothing moves
+                        o, w = K.camera_ray(sc["r2c"], sc["c2w"], sc["lens_radius"], sc["focal"], p_film, p_lens, COS, SIN)
+                        stats["camera"] += 1
+                        L = path_li(o, w, sc, scene, smp, stats)
+                        if any(c != c for c in L):
+                            L = [0.1, 0.1, 0.1]   # integrator.go:251-252; Spectrum.Y() is 0 (spectrum.go:227-229): no other fix-up
+                        pb, add = K.film_tile_add_sample((bx0, by0, bx1, by1), sc["fr"][0], sc["fr"][1], sc["crop"], p_film, L)
+                        for key, (r, g, b, fw) in add.items():
+                            acc = tile.setdefault(key, [0.0, 0.0, 0.0, 0.0])
+                            acc[0] += r
+                            acc[1] += g
+                            acc[2] += b
+                            acc[3] += fw
+            for (x, y), acc in tile.items():   # MergeFilmTile (film.go:122-140)
+                assert pb[0] <= x < pb[2] and pb[1] <= y < pb[3]
+                xyz = K.rgb_to_xyz(acc[:3])
+                px = film[y - y0][x - x0]
+                for i in range(3):
+                    px[i] += xyz[i]
+                px[3] += acc[3]
+    stats["closest"], stats["shadow"] = scene.closest, scene.shadow
+    return film, stats
+
+
+def main():
+    gp = importlib.import_module("go-pbrt_b200")
+    scene, integ = scene_and_integrator(gp)
+    sc = plain_scene(scene, integ)
+    out = dict(note="made by tests/golden/make_path_golden.py (plain-Python restatement of the composed Path.Li hot path); "
+                    "film = [y][x][X, Y, Z, filterWeightSum] as float.hex()", cases={})
+    for tile in TILE_SIZES:
+        film, st = render(sc, tile)
+        assert st["max_direct"] <= 10.0, "UniformSampleOneLight would panic in the reference (integrator.go:72-74)"
+        lit = sum(1 for row in film for p in row if p[1] > 0)
+        print(f"tile {tile}: camera {st['camera']}, closest {st['closest']}, shadow {st['shadow']}, lit pixels {lit}/{len(film) * len(film[0])}, "
+              f"max direct {st['max_direct']:.3f}")
+        out["cases"][f"tile{tile}"] = dict(tile=tile, rays=[st["camera"], st["closest"], st["shadow"]],
+                                           film=[[[v.hex() for v in p] for p in row] for row in film])
+    with open(os.path.join(HERE, "path_golden.json"), "w") as f:
+        json.dump(out, f, indent=0)
+    print("wrote path_golden.json")
+
+
+if __name__ == "__main__":
+    main()
