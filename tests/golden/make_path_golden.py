@@ -43,7 +43,8 @@ Z3 = [0.0, 0.0, 0.0]
 
 # ---------------------------------------------------------------- the scene, shared with the tests (host-mirror objects)
 def scene_and_integrator(gp, tile_note=None):
-    """Four matte disks (floor, ceiling, an annulus at object height 0.25, one tilted by RotateX) and two point lights;
+    """Four matte disks (floor, ceiling, an annulus at object height 0.25, one tilted by RotateX), two point lights and a
+    two-sided disk area light (a light only: the reference never puts a light's shape into the aggregate by itself);
     16x12 pixels, Stratified 3x3 with jitter, 2 sampled dimensions (every later draw comes from the tile's RNG), Path
     maxDepth 6, rrThreshold 1 (Russian roulette is live from the fourth bounce on)."""
     P, S = gp.pbrt, gp.scenes
@@ -58,7 +59,9 @@ def scene_and_integrator(gp, tile_note=None):
         P.NewGeometricPrimitive(P.NewDisk(P.Translate((1.0, 0.5, 2.0)), 0.25, 1.5, 0.5, 360), matte(0.3, 0.6, 0.9)),
         P.NewGeometricPrimitive(P.NewDisk(P.Translate((-2.0, 1.0, 1.5)).Mul(P.RotateX(40)), 0.0, 1.2, 0.0, 360), matte(0.9, 0.4, 0.3)),
     ]
+    axf = P.Translate((-0.5, 0.8, 4.2)).Mul(P.RotateY(20))
     lights = [P.NewPoint(P.Translate((0.3, 0.2, 4.0)), None, P.NewSpectrum(25.0)),
+              P.NewDiffuseAreaLight(axf, None, P.NewRGBSpectrum(6.0, 5.0, 4.0), 1, P.NewDisk(axf, 0.0, 2.5, 0.0, 360), True),
               P.NewPoint(P.Translate((-3.0, -2.0, 1.0)), None, P.NewRGBSpectrum(8.0, 6.0, 4.0))]
     scene = P.NewScene(P.NewBVH(prims, 1, P.SplitSAH), lights)
     W, H = 16, 12
@@ -83,7 +86,16 @@ def plain_scene(scene, integ):
                  kd=[K.clamp(c, 0.0, INF) for c in mt.Kd.value])   # matte.go:29
         d["bound"] = disk_world_bound(d)
         disks.append(d)
-    lights = [dict(p=list(map(float, l.pLight)), I=list(l.I)) for l in scene.lights]
+    lights = []
+    for l in scene.lights:
+        if type(l).__name__ == "Point":
+            lights.append(dict(kind="point", p=list(map(float, l.pLight)), I=list(l.I)))
+        else:
+            sh = l.shape
+            assert type(l).__name__ == "DiffuseAreaLight" and type(sh).__name__ == "Disk" and float(sh.phiMax) == 360.0
+            lights.append(dict(kind="area", shape="disk", L=list(l.LEmit), two_sided=bool(l.twoSided), m=sh.objectToWorld.Matrix.m,
+                               minv=sh.objectToWorld.MatrixInverse.m, height=float(sh.height), radius=float(sh.radius),
+                               inner=float(sh.innerRadius), phi_max=K.radians(K.clamp(float(sh.phiMax), 0.0, 360.0))))
     cam = integ.GetCamera()
     film = cam.GetFilm()
     smp = integ.GetSampler()
@@ -288,22 +300,55 @@ class TileSampler:
         return [x, y]
 
 
-# ---------------------------------------------------------------- integrator.go:46-195 (point lights: delta, no MIS leg)
-def estimate_direct(hit, bsdf, light, scene, stats):
-    Li, wi, light_pdf, lp, lperr, ln, _ = K.light_sample_li(dict(kind="point", p=light["p"], I=light["I"]), hit["p"], hit["perr"], hit["n"],
-                                                         None, COS, SIN)
+# ---------------------------------------------------------------- shape.go:29-48, disk.go:177-185, sampling.go:208-212
+def shape_pdf_wi(light, hit, wi):
+    """PdfWi: a ray from the reference point along wi (interaction.go:65-74) against the light's shape alone"""
+    o = K.offset_ray_origin(hit["p"], hit["perr"], hit["n"], wi)
+    r = disk_intersect(light, o, wi, INF)
+    if r is None:
+        return 0.0
+    _, li = r
+    area = light["phi_max"] * 0.5 * (light["radius"] * light["radius"] - light["inner"] * light["inner"])
+    pdf = go_div(K.v_dist2(hit["p"], li["p"]), abs(K.v_dot(li["n"], K.v_muls(K.v_muls(wi, -1.0), area))))
+    return 0.0 if math.isinf(pdf) else pdf
+
+
+def power_heuristic(f_pdf, g_pdf):
+    f, g = 1.0 * f_pdf, 1.0 * g_pdf
+    return (f * f) / (f * f + g * g)
+
+
+# ---------------------------------------------------------------- integrator.go:46-195
+def estimate_direct(hit, bsdf, light, u_light, u_scattering, scene, stats):
+    Li, wi, light_pdf, lp, lperr, ln, delta = K.light_sample_li(light, hit["p"], hit["perr"], hit["n"], u_light, COS, SIN)
     Ld = list(Z3)
     if light_pdf > 0 and not all(c == 0.0 for c in Li):
         f = bsdf.f(hit["wo"], wi)
         k = abs(K.v_dot(wi, hit["ns"]))
         f = [c * k for c in f]
-        bsdf.pdf(hit["wo"], wi)   # scatteringPdf: computed, unused for a delta light
+        scattering_pdf = bsdf.pdf(hit["wo"], wi)
         if not all(c == 0.0 for c in f):
             o, w = K.spawn_ray_to(hit["p"], hit["perr"], hit["n"], lp, lperr, ln)   # origin = the un-offset point
             if scene.intersect_p(o, w, 1 - SHADOW_EPSILON):
                 Li = list(Z3)
             if not all(c == 0.0 for c in Li):
-                Ld = [Ld[i] + (f[i] * Li[i]) / light_pdf for i in range(3)]
+                if delta:
+                    Ld = [Ld[i] + (f[i] * Li[i]) / light_pdf for i in range(3)]
+                else:
+                    weight = power_heuristic(light_pdf, scattering_pdf)
+                    Ld = [Ld[i] + ((f[i] * Li[i]) * weight) / light_pdf for i in range(3)]
+    if not delta:
+        stats["nondelta"] += 1   # what the library's `dead_mis_rays` counter reports: an upper bound of the rays counted below
+        # :139-193: the BSDF-sampling leg.  f.MulScalar(|wi.ns|) is dropped (:147); wi is the LOCAL direction again; the hit
+        # primitive's area light is always nil (primitive.go:29-36 never sets it), so the ray's answer adds nothing: the leg can
+        # only end the estimate early (PdfLi == 0) — or cost one closest-hit query, counted here
+        f, wi, scattering_pdf = bsdf.sample_f(hit["wo"], u_scattering)
+        if not all(c == 0.0 for c in f) and scattering_pdf > 0.0:
+            light_pdf = shape_pdf_wi(light, hit, wi)
+            if light_pdf == 0:
+                return Ld
+            power_heuristic(scattering_pdf, light_pdf)
+            stats["dead_mis"] += 1
     return Ld
 
 
@@ -314,9 +359,9 @@ def uniform_sample_one_light(hit, bsdf, sc, scene, smp, stats):
     num, pdf = K.sample_discrete([1.0] * n, smp.get1d())   # lightdistribution.go:24-34, sampling.go:42-55
     if pdf == 0.0:
         return list(Z3)
-    smp.get2d()   # uLight (a point light reads neither)
-    smp.get2d()   # uScattering
-    Ld = estimate_direct(hit, bsdf, sc["lights"][num], scene, stats)
+    u_light = smp.get2d()
+    u_scattering = smp.get2d()
+    Ld = estimate_direct(hit, bsdf, sc["lights"][num], u_light, u_scattering, scene, stats)
     # integrator.go:71: spectrum.DivScalar(lightPdf) returns a NEW spectrum that is dropped; :72-74 panics above 10
     stats["max_direct"] = max(stats["max_direct"], max(Ld))
     return Ld
@@ -361,7 +406,7 @@ def render(sc, tile_size):
     W, H = x1 - x0, y1 - y0
     film = [[[0.0, 0.0, 0.0, 0.0] for _ in range(W)] for _ in range(H)]
     scene = Scene(sc["disks"])
-    stats = dict(max_direct=0.0, camera=0)
+    stats = dict(max_direct=0.0, camera=0, dead_mis=0, nondelta=0)
     ntx, nty = (W + tile_size - 1) // tile_size, (H + tile_size - 1) // tile_size
     for ty in range(nty):
         for tx in range(ntx):
@@ -411,9 +456,9 @@ def main():
         film, st = render(sc, tile)
         assert st["max_direct"] <= 10.0, "UniformSampleOneLight would panic in the reference (integrator.go:72-74)"
         lit = sum(1 for row in film for p in row if p[1] > 0)
-        print(f"tile {tile}: camera {st['camera']}, closest {st['closest']}, shadow {st['shadow']}, lit pixels {lit}/{len(film) * len(film[0])}, "
+        print(f"tile {tile}: camera {st['camera']}, closest {st['closest']}, shadow {st['shadow']}, dead MIS rays {st['dead_mis']} of {st['nondelta']} area-light estimates, lit pixels {lit}/{len(film) * len(film[0])}, "
               f"max direct {st['max_direct']:.3f}")
-        out["cases"][f"tile{tile}"] = dict(tile=tile, rays=[st["camera"], st["closest"], st["shadow"]],
+        out["cases"][f"tile{tile}"] = dict(tile=tile, rays=[st["camera"], st["closest"], st["shadow"]], dead_mis_rays=st["dead_mis"], nondelta_estimates=st["nondelta"],
                                            film=[[[v.hex() for v in p] for p in row] for row in film])
     with open(os.path.join(HERE, "path_golden.json"), "w") as f:
         json.dump(out, f, indent=0)

@@ -25,7 +25,7 @@ _spec.loader.exec_module(M)
 def _load():
     with open(os.path.join(HERE, "golden", "path_golden.json")) as f:
         g = json.load(f)
-    return {k: (c["tile"], np.array([[[float.fromhex(v) for v in p] for p in row] for row in c["film"]]), c["rays"])
+    return {k: (c["tile"], np.array([[[float.fromhex(v) for v in p] for p in row] for row in c["film"]]), c["rays"] + [c["nondelta_estimates"], c["dead_mis_rays"]])
             for k, c in g["cases"].items()}
 
 
@@ -40,6 +40,10 @@ def test_golden_file_covers_what_it_claims():
         assert np.count_nonzero(film[..., 1] > 0) > 100        # most of the frame is lit
         assert rays[0] == 16 * 12 * 8                          # 3x3 strata, the first one is skipped (sampler.go:29-35)
         assert rays[1] > 2 * rays[0] and rays[2] > rays[0]     # paths do bounce and do test visibility
+        # EstimateDirect's BSDF-sampling leg (integrator.go:139-193) adds nothing in the reference (the hit primitive's area light is
+        # always nil).  The library's `dead_mis_rays` counts one per area-light estimate (rays[3]); the reference would trace that ray
+        # only when SampleF succeeds and PdfLi != 0 (rays[4]) — the counter is an upper bound, and no film value depends on it
+        assert 0 < rays[4] < rays[3]
         # box filter of radius 1, samples on the pixels' upper-left corners (the 2-D tables are zeros): a pixel collects its own
         # samples and those of its right / lower neighbours — the last pixel only its own
         assert film[5, 5, 3] == 4 * 8 and film[11, 15, 3] == 8 and film[11, 3, 3] == 2 * 8
@@ -50,7 +54,7 @@ def test_generator_is_deterministic_and_matches_the_committed_file(gp, tile):
     scene, integ = M.scene_and_integrator(gp)
     film, st = M.render(M.plain_scene(scene, integ), tile)
     t, gf, rays = GOLDEN[f"tile{tile}"]
-    assert t == tile and np.array_equal(np.array(film), gf) and [st["camera"], st["closest"], st["shadow"]] == rays
+    assert t == tile and np.array_equal(np.array(film), gf) and [st["camera"], st["closest"], st["shadow"], st["nondelta"], st["dead_mis"]] == rays
 
 
 @pytest.mark.parametrize("accel", [0, 1, 2])
@@ -62,7 +66,7 @@ def test_oracle_reproduces_the_independent_path_films(gp, name, accel):
     film, st = o.render(integ, tile, mode=gp.abi.MODE_STRICT, threads=2)
     o.close()
     assert np.array_equal(film, gf), f"{np.count_nonzero(np.any(film != gf, axis=2))} pixels differ"
-    assert [st["camera_rays"], st["closest_rays"], st["shadow_rays"]] == rays
+    assert [st["camera_rays"], st["closest_rays"], st["shadow_rays"], st["dead_mis_rays"]] == rays[:4]
     assert st["radiance_gt10"] == 0 and st["nan_samples"] == 0 and st["unsupported_material"] == 0
 
 
@@ -79,5 +83,5 @@ def test_gpu_reproduces_the_independent_path_films(gp, dev, monkeypatch, name, n
     film = integ.GetCamera().GetFilm().pixels
     g.close()
     assert np.array_equal(film, gf), f"{np.count_nonzero(np.any(film != gf, axis=2))} pixels differ"
-    assert [st["camera_rays"], st["closest_rays"], st["shadow_rays"]] == rays
+    assert [st["camera_rays"], st["closest_rays"], st["shadow_rays"], st["dead_mis_rays"]] == rays[:4]
     assert st["efloat_panics"] == 0 and st["stack_overflows"] == 0 and st["radiance_gt10"] == 0
