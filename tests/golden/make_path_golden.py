@@ -43,8 +43,9 @@ Z3 = [0.0, 0.0, 0.0]
 
 # ---------------------------------------------------------------- the scene, shared with the tests (host-mirror objects)
 def scene_and_integrator(gp, tile_note=None):
-    """Four matte disks (floor, ceiling, an annulus at object height 0.25, one tilted by RotateX), two point lights and a
-    two-sided disk area light (a light only: the reference never puts a light's shape into the aggregate by itself);
+    """Four matte disks (floor, ceiling, an annulus at object height 0.25, one tilted by RotateX), a mirror disk (mirror.go: a
+    SpecularReflection lobe TYPED Reflection|Diffuse), a glass disk (glass.go: one FresnelSpecular lobe), two point lights and two
+    two-sided disk area lights (lights only: the reference never puts a light's shape into the aggregate by itself);
     16x12 pixels, Stratified 3x3 with jitter, 2 sampled dimensions (every later draw comes from the tile's RNG), Path
     maxDepth 6, rrThreshold 1 (Russian roulette is live from the fourth bounce on)."""
     P, S = gp.pbrt, gp.scenes
@@ -57,12 +58,21 @@ def scene_and_integrator(gp, tile_note=None):
         P.NewGeometricPrimitive(P.NewDisk(P.Translate((0.0, 0.0, 0.0)), 0.0, 6.0, 0.0, 360), matte(0.7, 0.6, 0.5)),
         P.NewGeometricPrimitive(P.NewDisk(P.Translate((0.5, -0.3, 5.0)), 0.0, 7.0, 0.0, 360), matte(0.8, 0.8, 0.8)),
         P.NewGeometricPrimitive(P.NewDisk(P.Translate((1.0, 0.5, 2.0)), 0.25, 1.5, 0.5, 360), matte(0.3, 0.6, 0.9)),
-        P.NewGeometricPrimitive(P.NewDisk(P.Translate((-2.0, 1.0, 1.5)).Mul(P.RotateX(40)), 0.0, 1.2, 0.0, 360), matte(0.9, 0.4, 0.3)),
+        P.NewGeometricPrimitive(P.NewDisk(P.RotateX(-40), 3.2, 1.4, 0.0, 360), matte(0.9, 0.4, 0.3)),
+        P.NewGeometricPrimitive(P.NewDisk(P.RotateY(65), 2.2, 0.9, 0.0, 360), P.NewMirror()),
+        P.NewGeometricPrimitive(P.NewDisk(P.RotateX(60), 3.0, 1.3, 0.0, 360),
+                                P.NewGlass(P.NewConstantSpectrumTexture(P.NewSpectrum(1.0)), P.NewConstantSpectrumTexture(P.NewRGBSpectrum(0.9, 1.0, 0.8)),
+                                           zero, zero, P.NewConstantFloatTexture(1.5))),
     ]
-    axf = P.Translate((-0.5, 0.8, 4.2)).Mul(P.RotateY(20))
+    # every shape transform is ONE elementary transform: Transform.Mul multiplies the inverses in the same order as the matrices
+    # (transform.go:179-184), so a product of non-commuting transforms carries a wrong inverse and the shape's bound (from m) and
+    # its intersection test (through m^-1) no longer meet — reproduced by every implementation here, but it would leave slivers
+    axf, bxf = P.Translate((-0.5, 0.8, 4.2)), P.Translate((0.5, -0.5, -1.0))
     lights = [P.NewPoint(P.Translate((0.3, 0.2, 4.0)), None, P.NewSpectrum(25.0)),
-              P.NewDiffuseAreaLight(axf, None, P.NewRGBSpectrum(6.0, 5.0, 4.0), 1, P.NewDisk(axf, 0.0, 2.5, 0.0, 360), True),
-              P.NewPoint(P.Translate((-3.0, -2.0, 1.0)), None, P.NewRGBSpectrum(8.0, 6.0, 4.0))]
+              P.NewDiffuseAreaLight(axf, None, P.NewRGBSpectrum(6.0, 5.0, 4.0), 1, P.NewDisk(axf, 0.0, 2.0, 0.0, 360), True),
+              P.NewPoint(P.Translate((-3.0, -2.0, 1.0)), None, P.NewRGBSpectrum(8.0, 6.0, 4.0)),
+              # below the floor: it lights nothing (no transmission), but the floor's BSDF-sampling leg (a LOCAL wi, pointing down) finds it
+              P.NewDiffuseAreaLight(bxf, None, P.NewRGBSpectrum(3.0, 3.0, 3.0), 1, P.NewDisk(bxf, 0.0, 3.0, 0.0, 360), True)]
     scene = P.NewScene(P.NewBVH(prims, 1, P.SplitSAH), lights)
     W, H = 16, 12
     cam = S._camera((7.0, -6.0, 3.5), (0.0, 0.0, 1.5), (0.0, 0.0, 1.0), 50.0, W, H)
@@ -78,12 +88,21 @@ def plain_scene(scene, integ):
     disks = []
     for gpr in scene.aggregate.primitives:
         sh, mt = gpr.Shape, gpr.material
-        assert type(sh).__name__ == "Disk" and type(mt).__name__ == "MatteMaterial" and mt.sigma.value == 0.0
+        assert type(sh).__name__ == "Disk"
+        kind = type(mt).__name__
+        if kind == "MatteMaterial":
+            assert mt.sigma.value == 0.0
+            mat = dict(kind="matte", kd=[K.clamp(c, 0.0, INF) for c in mt.Kd.value])   # matte.go:29
+        elif kind == "Mirror":
+            mat = dict(kind="mirror", kr=[K.clamp(c, 0.0, INF) for c in mt.Kr.value])   # mirror.go:28
+        else:
+            assert kind == "Glass" and mt.uRoughness.value == 0.0 and mt.vRoughness.value == 0.0
+            mat = dict(kind="glass", R=[K.clamp(c, 0.0, 1.0) for c in mt.Kr.value], T=[K.clamp(c, 0.0, 1.0) for c in mt.Kt.value],
+                       eta=mt.index.value)   # glass.go:32-37
         m, minv = sh.objectToWorld.Matrix.m, sh.objectToWorld.MatrixInverse.m
         phi_max = K.radians(K.clamp(float(sh.phiMax), 0.0, 360.0))   # disk.go:34
         assert phi_max == 2 * math.pi
-        d = dict(m=m, minv=minv, height=float(sh.height), radius=float(sh.radius), inner=float(sh.innerRadius), phi_max=phi_max,
-                 kd=[K.clamp(c, 0.0, INF) for c in mt.Kd.value])   # matte.go:29
+        d = dict(m=m, minv=minv, height=float(sh.height), radius=float(sh.radius), inner=float(sh.innerRadius), phi_max=phi_max, mat=mat)
         d["bound"] = disk_world_bound(d)
         disks.append(d)
     lights = []
@@ -231,40 +250,96 @@ class Scene:
         return False
 
 
-# ---------------------------------------------------------------- reflection.go:128-298 over one Lambertian lobe
+# ---------------------------------------------------------------- reflection.go:128-298; matte.go, mirror.go, glass.go
+REFL, TRANS, DIFF, GLOSSY, SPEC = K.BSDF_REFLECTION, K.BSDF_TRANSMISSION, K.BSDF_DIFFUSE, K.BSDF_GLOSSY, K.BSDF_SPECULAR
+ALL = REFL | TRANS | DIFF | GLOSSY | SPEC
+NON_SPECULAR = ALL & ~SPEC
+
+
+def black(c):
+    return all(v == 0.0 for v in c)
+
+
 class BSDF:
-    def __init__(self, hit):  # NewBSDF (reflection.go:128-140) + matte.go:27-37
+    """a BSDF of at most ONE lobe (what the three materials build for smooth surfaces with allowMultipleLobes = true)"""
+
+    def __init__(self, hit):  # NewBSDF (reflection.go:128-140)
         self.ns, self.ng = hit["ns"], hit["n"]
         self.ss = K.v_normalized(hit["sh_dpdu"])
         self.ts = K.v_cross(self.ns, self.ss)
-        self.r = hit["disk"]["kd"]
-        self.n_lobes = 0 if all(c == 0.0 for c in self.r) else 1
+        m = hit["disk"]["mat"]
+        self.eta, self.lobe, self.type = 1.0, None, 0
+        if m["kind"] == "matte":      # matte.go:27-37 -> LambertianReflection (reflection.go:576-581)
+            if not black(m["kd"]):
+                self.lobe, self.type = ("lambert", m["kd"]), REFL | DIFF
+        elif m["kind"] == "mirror":   # mirror.go:27-31 -> SpecularReflection + FresnelNoOp, typed Reflection|Diffuse (reflection.go:540)
+            if not black(m["kr"]):
+                self.lobe, self.type = ("specrefl", m["kr"]), REFL | DIFF
+        else:                         # glass.go:27-48 -> FresnelSpecular(R, T, 1, eta, Radiance)
+            self.eta = m["eta"]
+            if not (black(m["R"]) and black(m["T"])):
+                self.lobe, self.type = ("fresnel", m["R"], m["T"], m["eta"]), REFL | TRANS | SPEC
+
+    def matches(self, flags):  # MatchesFlags (reflection.go:300-302)
+        return self.lobe is not None and (self.type & flags) == self.type
+
+    def num_components(self, flags):  # :159-167
+        return 1 if self.matches(flags) else 0
 
     def to_local(self, v):  # :147-149
         return [K.v_dot(v, self.ss), K.v_dot(v, self.ts), K.v_dot(v, self.ns)]
 
-    def f(self, wo_w, wi_w):  # BSDF.F :170-187 with flags = All &^ Specular; LambertianReflection.F :589-591
+    def _lobe_f(self):   # LambertianReflection.F :589-591; the specular lobes answer zero (:553-555, :478-480)
+        if self.lobe[0] == "lambert":
+            return [c * K.INV_PI for c in self.lobe[1]]
+        return list(Z3)
+
+    def _lobe_pdf(self, wo, wi):   # :343-348 for the Lambertian lobe; the specular lobes answer zero (:572-574)
+        if self.lobe[0] == "lambert":
+            return abs(wi[2]) * K.INV_PI if wo[2] * wi[2] > 0 else 0.0
+        return 0.0
+
+    def f(self, wo_w, wi_w, flags):  # BSDF.F :170-187
         wi, wo = self.to_local(wi_w), self.to_local(wo_w)
         if wo[2] == 0.0:
             return list(Z3)
         reflect = K.v_dot(wi_w, self.ng) * K.v_dot(wo_w, self.ng) > 0
         f = list(Z3)
-        if self.n_lobes and reflect:
-            f = [f[i] + self.r[i] * K.INV_PI for i in range(3)]
+        if self.matches(flags) and ((reflect and self.type & REFL > 0) or (not reflect and self.type & TRANS > 0)):
+            lf = self._lobe_f()
+            f = [f[i] + lf[i] for i in range(3)]
         return f
 
-    def pdf(self, wo_w, wi_w):  # :255-277 + :343-348
-        if self.n_lobes == 0:
+    def pdf(self, wo_w, wi_w, flags):  # :255-277
+        if self.lobe is None:
             return 0.0
         wo, wi = self.to_local(wo_w), self.to_local(wi_w)
         if wo[2] == 0:
             return 0.0
-        return (abs(wi[2]) * K.INV_PI if wo[2] * wi[2] > 0 else 0.0) / 1.0
+        if not self.matches(flags):
+            return 0.0
+        return (0.0 + self._lobe_pdf(wo, wi)) / 1.0
 
-    def sample_f(self, wo_w, u):  # :189-253 — returns the LOCAL wi (wiWorld is computed and dropped)
-        if self.n_lobes == 0:
-            return list(Z3), list(Z3), 0.0
-        return K.lambert_sample_f(self.r, self.to_local(wo_w), u, COS, SIN)
+    def sample_f(self, wo_w, u, flags):  # :189-253 — returns the LOCAL wi (wiWorld is computed and dropped); one lobe: no pdf/f sums
+        none = (list(Z3), list(Z3), 0.0, 0)
+        if not self.matches(flags):
+            return none
+        if self.lobe[0] == "lambert":   # the KAT restatement holds the whole of BSDF.SampleF for this lobe
+            f, wi, pdf = K.lambert_sample_f(self.lobe[1], self.to_local(wo_w), u, COS, SIN)
+            return f, wi, pdf, 0
+        comp = K.go_min(math.floor(u[0] * 1.0), 1.0 - 1)
+        ur = [K.go_min(u[0] * 1.0 - comp, K.ONE_MINUS_EPSILON), u[1]]
+        wo = self.to_local(wo_w)
+        if wo[2] == 0.0:
+            return none
+        if self.lobe[0] == "specrefl":   # SpecularReflection.SampleF :557-562, FresnelNoOp :383-385; sampledType 0
+            wi = [-wo[0], -wo[1], wo[2]]
+            f, pdf, st = [(1.0 * c) / abs(wi[2]) for c in self.lobe[1]], 1.0, 0
+        else:                            # FresnelSpecular.SampleF :482-523
+            f, wi, pdf, st = K.fresnel_specular_sample_f(self.lobe[1], self.lobe[2], 1.0, self.lobe[3], wo, ur)
+        if pdf == 0.0:
+            return none
+        return f, wi, pdf, st
 
 
 # ---------------------------------------------------------------- pixel.go:55-76, sampler.go:21-35,71-77, stratified.go:21-48
@@ -323,10 +398,10 @@ def estimate_direct(hit, bsdf, light, u_light, u_scattering, scene, stats):
     Li, wi, light_pdf, lp, lperr, ln, delta = K.light_sample_li(light, hit["p"], hit["perr"], hit["n"], u_light, COS, SIN)
     Ld = list(Z3)
     if light_pdf > 0 and not all(c == 0.0 for c in Li):
-        f = bsdf.f(hit["wo"], wi)
+        f = bsdf.f(hit["wo"], wi, NON_SPECULAR)
         k = abs(K.v_dot(wi, hit["ns"]))
         f = [c * k for c in f]
-        scattering_pdf = bsdf.pdf(hit["wo"], wi)
+        scattering_pdf = bsdf.pdf(hit["wo"], wi, NON_SPECULAR)
         if not all(c == 0.0 for c in f):
             o, w = K.spawn_ray_to(hit["p"], hit["perr"], hit["n"], lp, lperr, ln)   # origin = the un-offset point
             if scene.intersect_p(o, w, 1 - SHADOW_EPSILON):
@@ -342,12 +417,13 @@ def estimate_direct(hit, bsdf, light, u_light, u_scattering, scene, stats):
         # :139-193: the BSDF-sampling leg.  f.MulScalar(|wi.ns|) is dropped (:147); wi is the LOCAL direction again; the hit
         # primitive's area light is always nil (primitive.go:29-36 never sets it), so the ray's answer adds nothing: the leg can
         # only end the estimate early (PdfLi == 0) — or cost one closest-hit query, counted here
-        f, wi, scattering_pdf = bsdf.sample_f(hit["wo"], u_scattering)
+        f, wi, scattering_pdf, sampled = bsdf.sample_f(hit["wo"], u_scattering, NON_SPECULAR)
         if not all(c == 0.0 for c in f) and scattering_pdf > 0.0:
-            light_pdf = shape_pdf_wi(light, hit, wi)
-            if light_pdf == 0:
-                return Ld
-            power_heuristic(scattering_pdf, light_pdf)
+            if sampled & SPEC == 0:
+                light_pdf = shape_pdf_wi(light, hit, wi)
+                if light_pdf == 0:
+                    return Ld
+                power_heuristic(scattering_pdf, light_pdf)
             stats["dead_mis"] += 1
     return Ld
 
@@ -372,28 +448,42 @@ def path_li(o, w, sc, scene, smp, stats):
     L, beta = list(Z3), [1.0, 1.0, 1.0]
     tmax = INF
     bounces = 0
+    specular_bounce = False
     eta_scale = 1.0
     while True:
         bounces += 1
         hit = scene.intersect(o, w, tmax)
-        # `bounces == 0 || specularBounce` is never true here: no emitted radiance is ever added
+        if bounces == 0 or specular_bounce:   # bounces is at least 1 here (path.go:41)
+            if hit is not None:
+                # isect.Le: no primitive carries an area light (primitive.go:29-36) -> a zero spectrum is added
+                L = [L[i] + beta[i] * 0.0 for i in range(3)]
+            # else: no light has LightFlagInfinite (scene.go:22-27): nothing to loop over
         if hit is None or bounces >= sc["max_depth"]:
             break
         bsdf = BSDF(hit)
-        if bsdf.n_lobes > 0:   # NumComponents(All &^ Specular)
+        if bsdf.num_components(NON_SPECULAR) > 0:
             Ld = uniform_sample_one_light(hit, bsdf, sc, scene, smp, stats)
             L = [L[i] + beta[i] * Ld[i] for i in range(3)]
-        f, wi, pdf = bsdf.sample_f(w, smp.get2d())   # wo := ray.Direction (path.go:92)
+        f, wi, pdf, flags = bsdf.sample_f(w, smp.get2d(), ALL)   # wo := ray.Direction (path.go:92)
         if all(c == 0.0 for c in f) or pdf == 0.0:
             break
         k = abs(K.v_dot(wi, hit["ns"])) / pdf
         beta = [beta[i] * (f[i] * k) for i in range(3)]
+        specular_bounce = flags & SPEC != 0
+        stats["bounce_kinds"][(bsdf.lobe[0], flags)] = stats["bounce_kinds"].get((bsdf.lobe[0], flags), 0) + 1
+        if flags & SPEC > 0 and flags & TRANS > 0:
+            eta = bsdf.eta
+            if K.v_dot(w, hit["n"]) > 0:   # `wo.Dot(isect.Normal)` with wo = the ray's direction
+                eta_scale *= eta * eta
+            else:
+                eta_scale *= 1 / (eta * eta)
         o = K.offset_ray_origin(hit["p"], hit["perr"], hit["n"], wi)   # isect.SpawnRay(wi), wi still LOCAL
         w, tmax = wi, INF
         rr = [c * eta_scale for c in beta]
         m = K.go_max(K.go_max(rr[0], rr[1]), rr[2])
         if m < sc["rr"] and bounces > 3:
             q = K.go_max(0.05, 1 - m)
+            stats["rr_tests"] += 1
             if smp.get1d() < q:
                 break
             beta = [c / (1 - q) for c in beta]
@@ -406,7 +496,7 @@ def render(sc, tile_size):
     W, H = x1 - x0, y1 - y0
     film = [[[0.0, 0.0, 0.0, 0.0] for _ in range(W)] for _ in range(H)]
     scene = Scene(sc["disks"])
-    stats = dict(max_direct=0.0, camera=0, dead_mis=0, nondelta=0)
+    stats = dict(max_direct=0.0, camera=0, dead_mis=0, nondelta=0, rr_tests=0, bounce_kinds={})
     ntx, nty = (W + tile_size - 1) // tile_size, (H + tile_size - 1) // tile_size
     for ty in range(nty):
         for tx in range(ntx):
@@ -459,6 +549,8 @@ def main():
         print(f"tile {tile}: camera {st['camera']}, closest {st['closest']}, shadow {st['shadow']}, dead MIS rays {st['dead_mis']} of {st['nondelta']} area-light estimates, lit pixels {lit}/{len(film) * len(film[0])}, "
               f"max direct {st['max_direct']:.3f}")
         out["cases"][f"tile{tile}"] = dict(tile=tile, rays=[st["camera"], st["closest"], st["shadow"]], dead_mis_rays=st["dead_mis"], nondelta_estimates=st["nondelta"],
+                                           coverage=dict(russian_roulette_tests=st["rr_tests"],
+                                                         bounces={f"{k[0]}:{k[1]}": v for k, v in sorted(st["bounce_kinds"].items())}),
                                            film=[[[v.hex() for v in p] for p in row] for row in film])
     with open(os.path.join(HERE, "path_golden.json"), "w") as f:
         json.dump(out, f, indent=0)
