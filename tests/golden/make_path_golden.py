@@ -44,7 +44,7 @@ Z3 = [0.0, 0.0, 0.0]
 # ---------------------------------------------------------------- the scene, shared with the tests (host-mirror objects)
 def scene_and_integrator(gp, tile_note=None):
     """Four matte disks (floor, ceiling, an annulus at object height 0.25, one tilted by RotateX), a mirror disk (mirror.go: a
-    SpecularReflection lobe TYPED Reflection|Diffuse), a glass disk (glass.go: one FresnelSpecular lobe), two point lights and two
+    SpecularReflection lobe TYPED Reflection|Diffuse), two glass disks (glass.go: one FresnelSpecular lobe), two point lights and two
     two-sided disk area lights (lights only: the reference never puts a light's shape into the aggregate by itself);
     16x12 pixels, Stratified 3x3 with jitter, 2 sampled dimensions (every later draw comes from the tile's RNG), Path
     maxDepth 6, rrThreshold 1 (Russian roulette is live from the fourth bounce on)."""
@@ -60,9 +60,14 @@ def scene_and_integrator(gp, tile_note=None):
         P.NewGeometricPrimitive(P.NewDisk(P.Translate((1.0, 0.5, 2.0)), 0.25, 1.5, 0.5, 360), matte(0.3, 0.6, 0.9)),
         P.NewGeometricPrimitive(P.NewDisk(P.RotateX(-40), 3.2, 1.4, 0.0, 360), matte(0.9, 0.4, 0.3)),
         P.NewGeometricPrimitive(P.NewDisk(P.RotateY(65), 2.2, 0.9, 0.0, 360), P.NewMirror()),
-        P.NewGeometricPrimitive(P.NewDisk(P.RotateX(60), 3.0, 1.3, 0.0, 360),
+        # the two glass disks turn their geometric normal (object -z) towards the camera / upwards: DirectLighting's transmission
+        # lobe reads `entering` off si.Wo, and from the back it would be past the critical angle
+        P.NewGeometricPrimitive(P.NewDisk(P.RotateX(240), -3.0, 1.3, 0.0, 360),
                                 P.NewGlass(P.NewConstantSpectrumTexture(P.NewSpectrum(1.0)), P.NewConstantSpectrumTexture(P.NewRGBSpectrum(0.9, 1.0, 0.8)),
                                            zero, zero, P.NewConstantFloatTexture(1.5))),
+        P.NewGeometricPrimitive(P.NewDisk(P.RotateX(180), -0.3, 2.5, 0.0, 360),
+                                P.NewGlass(P.NewConstantSpectrumTexture(P.NewSpectrum(1.0)), P.NewConstantSpectrumTexture(P.NewRGBSpectrum(0.8, 0.9, 1.0)),
+                                           zero, zero, P.NewConstantFloatTexture(1.33))),
     ]
     # every shape transform is ONE elementary transform: Transform.Mul multiplies the inverses in the same order as the matrices
     # (transform.go:179-184), so a product of non-commuting transforms carries a wrong inverse and the shape's bound (from m) and
