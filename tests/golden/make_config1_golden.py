@@ -330,6 +330,12 @@ def plain_scene(scene, integ):
                               theta_min=go_acos(K.clamp(K.go_min(-r, r) / r, -1, 1)), theta_max=go_acos(K.clamp(K.go_max(-r, r) / r, -1, 1)))
 
     def mat_of(mt):
+        if type(mt).__name__ == "Mirror":
+            return dict(kind="mirror", kr=[K.clamp(c, 0.0, INF) for c in mt.Kr.value])   # mirror.go:28
+        if type(mt).__name__ == "Glass":
+            assert mt.uRoughness.value == 0.0 and mt.vRoughness.value == 0.0
+            return dict(kind="glass", R=[K.clamp(c, 0.0, 1.0) for c in mt.Kr.value], T=[K.clamp(c, 0.0, 1.0) for c in mt.Kt.value],
+                        eta=mt.index.value)   # glass.go:32-37
         assert type(mt).__name__ == "MatteMaterial" and mt.sigma.value == 0.0
         kd = mt.Kd
         if type(kd).__name__ == "Checkerboard2D":
