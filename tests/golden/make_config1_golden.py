@@ -17,6 +17,7 @@ reuses): written from the Go source, nothing from oracle/ or go-pbrt_b200/csrc/.
 
     python tests/golden/make_config1_golden.py        # rewrites tests/golden/config1_golden.json
 """
+import contextlib
 import importlib
 import importlib.util
 import json
@@ -283,7 +284,7 @@ class Prim:
         s = m["ds"] + K.v_dot(p, m["vs"])
         t = m["dt"] + K.v_dot(p, m["vt"])
         even = int(math.floor(s) + math.floor(t)) % 2 == 0
-        return dict(kind="matte", kd=[K.clamp(c, 0.0, INF) for c in (m["tex1"] if even else m["tex2"])])
+        return dict(kind="matte", kd=[K.clamp(c, 0.0, INF) for c in (m["tex1"] if even else m["tex2"])], sigma=m["sigma"])
 
 
 class Scene:
@@ -336,14 +337,15 @@ def plain_scene(scene, integ):
             assert mt.uRoughness.value == 0.0 and mt.vRoughness.value == 0.0
             return dict(kind="glass", R=[K.clamp(c, 0.0, 1.0) for c in mt.Kr.value], T=[K.clamp(c, 0.0, 1.0) for c in mt.Kt.value],
                         eta=mt.index.value)   # glass.go:32-37
-        assert type(mt).__name__ == "MatteMaterial" and mt.sigma.value == 0.0
+        assert type(mt).__name__ == "MatteMaterial"
+        sigma = K.clamp(mt.sigma.value, 0, 90)   # matte.go:30
         kd = mt.Kd
         if type(kd).__name__ == "Checkerboard2D":
             mp = kd.mapping
             assert type(mp).__name__ == "PlanarMapping2D"
             return dict(kind="checker", vs=list(map(float, mp.vs)), vt=list(map(float, mp.vt)), ds=float(mp.ds), dt=float(mp.dt),
-                        tex1=list(kd.tex1.value), tex2=list(kd.tex2.value))
-        return dict(kind="matte", kd=[K.clamp(c, 0.0, INF) for c in kd.value])
+                        tex1=list(kd.tex1.value), tex2=list(kd.tex2.value), sigma=sigma)
+        return dict(kind="matte", kd=[K.clamp(c, 0.0, INF) for c in kd.value], sigma=sigma)
 
     prims = []
     for pr in scene.aggregate.primitives:
@@ -369,8 +371,8 @@ def plain_scene(scene, integ):
             lights.append(dict(kind="distant", L=list(l.L), w=list(map(float, l.wLight)), world_radius=world_radius))
         else:
             k2, shape = shape_of(l.shape)
-            assert kind == "DiffuseAreaLight" and k2 == "sphere" and not shape["reverse"]
-            lights.append(dict(shape, kind="area", shape="sphere", L=list(l.LEmit), two_sided=bool(l.twoSided)))
+            assert kind == "DiffuseAreaLight" and not shape.get("reverse", False)
+            lights.append(dict(shape, kind="area", shape=k2, L=list(l.LEmit), two_sided=bool(l.twoSided)))
     sc = {}   # the camera / film / sampler fields as make_path_golden.plain_scene fills them
     cam = integ.GetCamera()
     film = cam.GetFilm()
@@ -382,8 +384,9 @@ def plain_scene(scene, integ):
     return sc
 
 
-def render(sc, tile):
-    """make_path_golden.render with this file's Scene and a PdfWi that knows spheres"""
+@contextlib.contextmanager
+def patched(sc):
+    """make_path_golden with this file's Scene and a PdfWi that knows spheres"""
     saved = M.Scene, M.shape_pdf_wi
 
     class _Scene(Scene):
@@ -393,9 +396,14 @@ def render(sc, tile):
     M.Scene = _Scene
     M.shape_pdf_wi = lambda light, hit, wi: sphere_pdf_wi(light, hit, wi) if light["shape"] == "sphere" else saved[1](light, hit, wi)
     try:
-        return M.render(sc, tile)
+        yield
     finally:
         M.Scene, M.shape_pdf_wi = saved
+
+
+def render(sc, tile):
+    with patched(sc):
+        return M.render(sc, tile)
 
 
 def main():

@@ -53,7 +53,10 @@ class BSDF:
         self.lobes = []
         if m["kind"] == "matte":
             if not M.black(m["kd"]):
-                self.lobes.append(dict(kind="lambert", type=REFL | DIFF, r=m["kd"]))
+                if m.get("sigma", 0.0) == 0:
+                    self.lobes.append(dict(kind="lambert", type=REFL | DIFF, r=m["kd"]))
+                else:   # OrenNayar (reflection.go:616-652)
+                    self.lobes.append(dict(kind="orennayar", type=REFL | DIFF, r=m["kd"], sigma=m["sigma"]))
         elif m["kind"] == "mirror":
             if not M.black(m["kr"]):
                 self.lobes.append(dict(kind="specrefl", type=REFL | DIFF, r=m["kr"], fresnel=None))
@@ -74,22 +77,26 @@ class BSDF:
         return [lb for lb in self.lobes if (lb["type"] & flags) == lb["type"]]
 
     @staticmethod
-    def lobe_f(lb):
-        return [c * K.INV_PI for c in lb["r"]] if lb["kind"] == "lambert" else list(Z3)
+    def lobe_f(lb, wo, wi):
+        if lb["kind"] == "lambert":
+            return [c * K.INV_PI for c in lb["r"]]
+        if lb["kind"] == "orennayar":
+            return K.oren_nayar(lb["r"], lb["sigma"], wo, wi)
+        return list(Z3)
 
     @staticmethod
     def lobe_pdf(lb, wo, wi):
-        if lb["kind"] == "lambert":
+        if lb["kind"] in ("lambert", "orennayar"):
             return abs(wi[2]) * K.INV_PI if wo[2] * wi[2] > 0 else 0.0
         return 0.0
 
     @staticmethod
     def lobe_sample_f(lb, wo, u):
-        if lb["kind"] == "lambert":   # sampleF :305-314
+        if lb["kind"] in ("lambert", "orennayar"):   # sampleF :305-314
             wi = K.cosine_sample_hemisphere(u, M.COS, M.SIN)
             if wo[2] < 0:
                 wi[2] *= -1
-            return BSDF.lobe_f(lb), wi, BSDF.lobe_pdf(lb, wo, wi), 0
+            return BSDF.lobe_f(lb, wo, wi), wi, BSDF.lobe_pdf(lb, wo, wi), 0
         if lb["kind"] == "specrefl":  # :557-562; FresnelNoOp :383-385 / FresnelDielectric :400-402
             wi = [-wo[0], -wo[1], wo[2]]
             fr = 1.0 if lb["fresnel"] is None else K.fr_dielectric(wi[2], lb["fresnel"][0], lb["fresnel"][1])
@@ -114,7 +121,7 @@ class BSDF:
         f = list(Z3)
         for lb in self.matching(flags):
             if (reflect and lb["type"] & REFL > 0) or (not reflect and lb["type"] & TRANS > 0):
-                lf = self.lobe_f(lb)
+                lf = self.lobe_f(lb, wo, wi)
                 f = [f[i] + lf[i] for i in range(3)]
         return f
 
@@ -157,7 +164,7 @@ class BSDF:
             f = list(Z3)
             for other in cand:
                 if (reflect and other["type"] & REFL > 0) or (not reflect and other["type"] & TRANS > 0):
-                    lf = self.lobe_f(other)
+                    lf = self.lobe_f(other, wo, wi)
                     f = [f[i] + lf[i] for i in range(3)]
         return f, wi, pdf, st
 

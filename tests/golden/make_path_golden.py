@@ -96,8 +96,7 @@ def plain_scene(scene, integ):
         assert type(sh).__name__ == "Disk"
         kind = type(mt).__name__
         if kind == "MatteMaterial":
-            assert mt.sigma.value == 0.0
-            mat = dict(kind="matte", kd=[K.clamp(c, 0.0, INF) for c in mt.Kd.value])   # matte.go:29
+            mat = dict(kind="matte", kd=[K.clamp(c, 0.0, INF) for c in mt.Kd.value], sigma=K.clamp(mt.sigma.value, 0, 90))   # matte.go:29-30
         elif kind == "Mirror":
             mat = dict(kind="mirror", kr=[K.clamp(c, 0.0, INF) for c in mt.Kr.value])   # mirror.go:28
         else:
@@ -274,9 +273,9 @@ class BSDF:
         self.ts = K.v_cross(self.ns, self.ss)
         m = hit["disk"]["mat"]
         self.eta, self.lobe, self.type = 1.0, None, 0
-        if m["kind"] == "matte":      # matte.go:27-37 -> LambertianReflection (reflection.go:576-581)
+        if m["kind"] == "matte":      # matte.go:27-37 -> LambertianReflection (reflection.go:576-581) or OrenNayar (:616-626)
             if not black(m["kd"]):
-                self.lobe, self.type = ("lambert", m["kd"]), REFL | DIFF
+                self.lobe, self.type = ("lambert", m["kd"]) if m.get("sigma", 0.0) == 0 else ("orennayar", m["kd"], m["sigma"]), REFL | DIFF
         elif m["kind"] == "mirror":   # mirror.go:27-31 -> SpecularReflection + FresnelNoOp, typed Reflection|Diffuse (reflection.go:540)
             if not black(m["kr"]):
                 self.lobe, self.type = ("specrefl", m["kr"]), REFL | DIFF
@@ -294,13 +293,15 @@ class BSDF:
     def to_local(self, v):  # :147-149
         return [K.v_dot(v, self.ss), K.v_dot(v, self.ts), K.v_dot(v, self.ns)]
 
-    def _lobe_f(self):   # LambertianReflection.F :589-591; the specular lobes answer zero (:553-555, :478-480)
+    def _lobe_f(self, wo, wi):   # LambertianReflection.F :589-591, OrenNayar.F :628-652; the specular lobes answer zero (:553-555, :478-480)
         if self.lobe[0] == "lambert":
             return [c * K.INV_PI for c in self.lobe[1]]
+        if self.lobe[0] == "orennayar":
+            return K.oren_nayar(self.lobe[1], self.lobe[2], wo, wi)
         return list(Z3)
 
-    def _lobe_pdf(self, wo, wi):   # :343-348 for the Lambertian lobe; the specular lobes answer zero (:572-574)
-        if self.lobe[0] == "lambert":
+    def _lobe_pdf(self, wo, wi):   # :343-348 for the two diffuse lobes; the specular lobes answer zero (:572-574)
+        if self.lobe[0] in ("lambert", "orennayar"):
             return abs(wi[2]) * K.INV_PI if wo[2] * wi[2] > 0 else 0.0
         return 0.0
 
@@ -311,7 +312,7 @@ class BSDF:
         reflect = K.v_dot(wi_w, self.ng) * K.v_dot(wo_w, self.ng) > 0
         f = list(Z3)
         if self.matches(flags) and ((reflect and self.type & REFL > 0) or (not reflect and self.type & TRANS > 0)):
-            lf = self._lobe_f()
+            lf = self._lobe_f(wo, wi)
             f = [f[i] + lf[i] for i in range(3)]
         return f
 
@@ -337,7 +338,12 @@ class BSDF:
         wo = self.to_local(wo_w)
         if wo[2] == 0.0:
             return none
-        if self.lobe[0] == "specrefl":   # SpecularReflection.SampleF :557-562, FresnelNoOp :383-385; sampledType 0
+        if self.lobe[0] == "orennayar":   # sampleF :305-314 with OrenNayar's F and the cosine pdf
+            wi = K.cosine_sample_hemisphere(ur, COS, SIN)
+            if wo[2] < 0:
+                wi[2] *= -1
+            f, pdf, st = self._lobe_f(wo, wi), self._lobe_pdf(wo, wi), 0
+        elif self.lobe[0] == "specrefl":   # SpecularReflection.SampleF :557-562, FresnelNoOp :383-385; sampledType 0
             wi = [-wo[0], -wo[1], wo[2]]
             f, pdf, st = [(1.0 * c) / abs(wi[2]) for c in self.lobe[1]], 1.0, 0
         else:                            # FresnelSpecular.SampleF :482-523
