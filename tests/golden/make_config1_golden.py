@@ -12,8 +12,8 @@ reuses): written from the Go source, nothing from oracle/ or go-pbrt_b200/csrc/.
  * Sphere.PdfWi (sphere.go:350-365), the sphere area light's SampleLi (through make_shading_kats.sphere_sample_at), the distant
    light with its pOutside = wLight * 2R (distant.go:36-44) and the world radius of scene.go:17-21 / bounds.go:105-112;
  * Checkerboard2D over PlanarMapping2D (checkerboard.go:30-40, texture.go:41-46);
- * Go's math.Acos (asin.go / atan.go of Go 1.11: Cephes' atan polynomial) — restated below; math.Sin from the host mirror
-   go-pbrt_b200/gomath.py.  math.Atan2 feeds only `phi > phiMax` (cannot fire for a full sphere) and u (no texture reads it).
+ * Go's math.Acos / Atan2 (asin.go, atan.go, atan2.go of Go 1.11: Cephes' atan polynomial), restated in make_path_golden.py;
+   math.Sin from the host mirror go-pbrt_b200/gomath.py.
 
     python tests/golden/make_config1_golden.py        # rewrites tests/golden/config1_golden.json
 """
@@ -34,6 +34,7 @@ _spec.loader.exec_module(M)
 K = M.K
 Z3, INF = M.Z3, M.INF
 W, H, SPP, TILE = 24, 14, (3, 3), 4
+RETRIES = dict(tried=0, hit=0)   # coverage counter: the second-root retry of a clipped sphere (sphere.go:110-131)
 _inv_dir = M.Scene._inv   # bvh.go:665-666 (M.Scene itself is swapped out while this file renders)
 
 
@@ -41,44 +42,7 @@ def scene_and_integrator(gp):
     return gp.scenes.config1(W=W, H=H, spp=SPP)
 
 
-# ---------------------------------------------------------------- Go 1.11 math: atan.go, asin.go
-def go_xatan(x):
-    P0, P1, P2, P3, P4 = (-8.750608600031904122785e-01, -1.615753718733365076637e+01, -7.500855792314704667340e+01,
-                          -1.228866684490136173410e+02, -6.485021904942025371773e+01)
-    Q0, Q1, Q2, Q3, Q4 = (+2.485846490142306297962e+01, +1.650270098316988542046e+02, +4.328810604912902668951e+02,
-                          +4.853903996359136964868e+02, +1.945506571482613964425e+02)
-    z = x * x
-    z = z * ((((P0 * z + P1) * z + P2) * z + P3) * z + P4) / (((((z + Q0) * z + Q1) * z + Q2) * z + Q3) * z + Q4)
-    return x * z + x
-
-
-def go_satan(x):
-    morebits, tan3pio8 = 6.123233995736765886130e-17, 2.41421356237309504880
-    if x <= 0.66:
-        return go_xatan(x)
-    if x > tan3pio8:
-        return math.pi / 2 - go_xatan(1 / x) + morebits
-    return math.pi / 4 + go_xatan((x - 1) / (x + 1)) + 0.5 * morebits
-
-
-def go_asin(x):
-    if x == 0:
-        return x
-    sign = False
-    if x < 0:
-        x, sign = -x, True
-    if x > 1:
-        return float("nan")
-    temp = math.sqrt(1 - x * x)
-    if x > 0.7:
-        temp = math.pi / 2 - go_satan(temp / x)
-    else:
-        temp = go_satan(x / temp)
-    return -temp if sign else temp
-
-
-def go_acos(x):
-    return math.pi / 2 - go_asin(x)
+go_acos = M.go_acos   # Go 1.11's math.Acos, restated in make_path_golden.py
 
 
 # ---------------------------------------------------------------- pkg/efloat
@@ -181,7 +145,7 @@ def transform_bounds(m, lo, hi):
     return bmin, bmax
 
 
-# ---------------------------------------------------------------- sphere.go:64-262 (full spheres: zMin = -r, zMax = r, phiMax = 360)
+# ---------------------------------------------------------------- sphere.go:64-262
 def sphere_roots(sp, o, w, tmax):
     """what Intersect and IntersectP share: object-space ray, the chosen root, pHit"""
     ro, rd, oerr, derr = transform_ray_err(sp["minv"], o, w)
@@ -202,21 +166,43 @@ def sphere_roots(sp, o, w, tmax):
         if t.hi > tmax:
             return None
     r = sp["radius"]
-    ph = [ro[i] + rd[i] * t.v for i in range(3)]
-    ph = K.v_muls(ph, r / math.sqrt(K.v_dist2(ph, Z3)))
-    if ph[0] == 0.0 and ph[1] == 0.0:
-        ph[0] = 1e-5 * r
-    # a full sphere clips nothing: zMin > -r and zMax < r are false, phi <= 2 Pi == phiMax
-    return t.v, ph, rd
+
+    def point_at(tv):   # :96-106
+        ph = [ro[i] + rd[i] * tv for i in range(3)]
+        ph = K.v_muls(ph, r / math.sqrt(K.v_dist2(ph, Z3)))
+        if ph[0] == 0.0 and ph[1] == 0.0:
+            ph[0] = 1e-5 * r
+        phi = M.go_atan2(ph[1], ph[0])
+        if phi < 0.0:
+            phi += 2 * math.pi
+        return ph, phi
+
+    def clipped(ph, phi):   # :109
+        return (sp["z_min"] > -r and ph[2] < sp["z_min"]) or (sp["z_max"] < r and ph[2] > sp["z_max"]) or phi > sp["phi_max"]
+
+    ph, phi = point_at(t.v)
+    if clipped(ph, phi):
+        if t is t1:
+            return None
+        if t1.hi > tmax:
+            return None
+        RETRIES["tried"] += 1
+        t = t1
+        ph, phi2 = point_at(t.v)   # `phi := ...` (:125) declares a NEW variable: u below still comes from the first root's phi
+        if clipped(ph, phi2):
+            return None
+        RETRIES["hit"] += 1
+    return t.v, ph, rd, phi
 
 
 def sphere_intersect(sp, o, w, tmax):
     q = sphere_roots(sp, o, w, tmax)
     if q is None:
         return None
-    t, ph, rd = q
+    t, ph, rd, phi = q
     r, phi_max = sp["radius"], sp["phi_max"]
     theta = go_acos(K.clamp(ph[2] / r, -1, 1))
+    uv = [phi / phi_max, (theta - sp["theta_min"]) / (sp["theta_max"] - sp["theta_min"])]   # :136-138
     z_radius = math.sqrt(ph[0] * ph[0] + ph[1] * ph[1])
     inv = 1.0 / z_radius
     cos_phi, sin_phi = ph[0] * inv, ph[1] * inv
@@ -227,7 +213,7 @@ def sphere_intersect(sp, o, w, tmax):
     n = K.v_normalized(K.v_cross(dpdu, dpdv))   # NewSurfaceInteractionWith (interaction.go:171-177)
     if sp["reverse"]:                            # reverseOrientation != transformSwapsHandedness (never set: false)
         n = K.v_muls(n, -1.0)
-    rec = dict(p=ph, perr=perr, n=n, ns=n, wo=K.v_muls(rd, -1.0), sh_dpdu=dpdu)
+    rec = dict(p=ph, perr=perr, n=n, ns=n, wo=K.v_muls(rd, -1.0), sh_dpdu=dpdu, uv=uv)
     return t, tsi(sp["m"], sp["minv"], rec)
 
 
@@ -248,8 +234,8 @@ class Prim:
         if kind == "disk":
             b = transform_bounds(shape["m"], [-shape["radius"], -shape["radius"], shape["height"]], [shape["radius"], shape["radius"], shape["height"]])
         else:
-            r = shape["radius"]
-            b = transform_bounds(shape["m"], [-r, -r, -r], [r, r, r])
+            r = shape["radius"]   # Sphere.ObjectBound (sphere.go:46-51)
+            b = transform_bounds(shape["m"], [-r, -r, shape["z_min"]], [r, r, shape["z_max"]])
         if xf is not None:   # primitive.go:128-130 + transform.go:583-586
             b = transform_bounds(xf[0], b[0], b[1])
         self.bound = b
@@ -280,9 +266,13 @@ class Prim:
         m = self.mat
         if m["kind"] != "checker":
             return m
-        p = rec["p"]   # PlanarMapping2D.Map (texture.go:41-46), Checkerboard2D.Evaluate (checkerboard.go:30-40)
-        s = m["ds"] + K.v_dot(p, m["vs"])
-        t = m["dt"] + K.v_dot(p, m["vt"])
+        if "uv" in m:   # UVMapping2D.Map (texture.go:22-26)
+            su, sv, du, dv = m["uv"]
+            s, t = su * rec["uv"][0] + du, sv * rec["uv"][1] + dv
+        else:           # PlanarMapping2D.Map (texture.go:41-46); Checkerboard2D.Evaluate (checkerboard.go:30-40) below
+            p = rec["p"]
+            s = m["ds"] + K.v_dot(p, m["vs"])
+            t = m["dt"] + K.v_dot(p, m["vt"])
         even = int(math.floor(s) + math.floor(t)) % 2 == 0
         return dict(kind="matte", kd=[K.clamp(c, 0.0, INF) for c in (m["tex1"] if even else m["tex2"])], sigma=m["sigma"])
 
@@ -322,13 +312,13 @@ def plain_scene(scene, integ):
     def shape_of(sh):
         m, minv = xf_of(sh.objectToWorld)
         if type(sh).__name__ == "Disk":
-            phi_max = K.radians(K.clamp(float(sh.phiMax), 0.0, 360.0))
-            assert phi_max == 2 * math.pi
+            phi_max = K.radians(K.clamp(float(sh.phiMax), 0.0, 360.0))   # disk.go:34
             return "disk", dict(m=m, minv=minv, height=float(sh.height), radius=float(sh.radius), inner=float(sh.innerRadius), phi_max=phi_max)
-        assert type(sh).__name__ == "Sphere" and sh.zMin == -sh.radius and sh.zMax == sh.radius and float(sh.phiMax) == 360.0
-        r = float(sh.radius)
-        return "sphere", dict(m=m, minv=minv, radius=r, reverse=bool(sh.reverseOrientation), phi_max=K.radians(K.clamp(360.0, 0.0, 360.0)),
-                              theta_min=go_acos(K.clamp(K.go_min(-r, r) / r, -1, 1)), theta_max=go_acos(K.clamp(K.go_max(-r, r) / r, -1, 1)))
+        assert type(sh).__name__ == "Sphere"
+        r, z0, z1 = float(sh.radius), float(sh.zMin), float(sh.zMax)   # NewSphere (sphere.go:19-32)
+        return "sphere", dict(m=m, minv=minv, radius=r, reverse=bool(sh.reverseOrientation), phi_max=K.radians(K.clamp(float(sh.phiMax), 0.0, 360.0)),
+                              z_min=K.clamp(K.go_min(z0, z1), -r, r), z_max=K.clamp(K.go_max(z0, z1), -r, r),
+                              theta_min=go_acos(K.clamp(K.go_min(z0, z1) / r, -1, 1)), theta_max=go_acos(K.clamp(K.go_max(z0, z1) / r, -1, 1)))
 
     def mat_of(mt):
         if type(mt).__name__ == "Mirror":
@@ -342,6 +332,9 @@ def plain_scene(scene, integ):
         kd = mt.Kd
         if type(kd).__name__ == "Checkerboard2D":
             mp = kd.mapping
+            if type(mp).__name__ == "UVMapping2D":
+                return dict(kind="checker", uv=(float(mp.su), float(mp.sv), float(mp.du), float(mp.dv)),
+                            tex1=list(kd.tex1.value), tex2=list(kd.tex2.value), sigma=sigma)
             assert type(mp).__name__ == "PlanarMapping2D"
             return dict(kind="checker", vs=list(map(float, mp.vs)), vt=list(map(float, mp.vt)), ds=float(mp.ds), dt=float(mp.dt),
                         tex1=list(kd.tex1.value), tex2=list(kd.tex2.value), sigma=sigma)

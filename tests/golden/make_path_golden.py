@@ -16,8 +16,7 @@ What it takes from elsewhere, and why that does not weaken it:
  * the 4x4 matrices of the camera and of the shapes, as DATA, from the host mirror go-pbrt_b200/pbrt.py (LookAt,
    Perspective, RotateX, Inverse — host-side constructors that run once per scene, outside the hot path);
  * sin/cos from go-pbrt_b200/gomath.py (Go's math.Sin/Cos are not libm's; pinned by transform_test.go:77-81).
- math.Atan2 (disk.go:83) is NOT needed bit-exactly here: for a full disk phi only feeds `phi > phiMax`, which cannot fire
- (phi + 2*Pi rounds to at most 2*Pi == Radians(360), asserted below), and u, which only constant textures read.
+ Go 1.11's math.Atan2 / Acos (atan.go, atan2.go, asin.go: Cephes' atan polynomial) are restated below.
 
     python tests/golden/make_path_golden.py        # rewrites tests/golden/path_golden.json
 """
@@ -39,6 +38,70 @@ COS, SIN = gomath.Cos, gomath.Sin
 INF = float("inf")
 SHADOW_EPSILON = 0.0001  # pkg/math/math.go
 Z3 = [0.0, 0.0, 0.0]
+
+
+# ---------------------------------------------------------------- Go 1.11 math: atan.go, asin.go
+def go_xatan(x):
+    P0, P1, P2, P3, P4 = (-8.750608600031904122785e-01, -1.615753718733365076637e+01, -7.500855792314704667340e+01,
+                          -1.228866684490136173410e+02, -6.485021904942025371773e+01)
+    Q0, Q1, Q2, Q3, Q4 = (+2.485846490142306297962e+01, +1.650270098316988542046e+02, +4.328810604912902668951e+02,
+                          +4.853903996359136964868e+02, +1.945506571482613964425e+02)
+    z = x * x
+    z = z * ((((P0 * z + P1) * z + P2) * z + P3) * z + P4) / (((((z + Q0) * z + Q1) * z + Q2) * z + Q3) * z + Q4)
+    return x * z + x
+
+
+def go_satan(x):
+    morebits, tan3pio8 = 6.123233995736765886130e-17, 2.41421356237309504880
+    if x <= 0.66:
+        return go_xatan(x)
+    if x > tan3pio8:
+        return math.pi / 2 - go_xatan(1 / x) + morebits
+    return math.pi / 4 + go_xatan((x - 1) / (x + 1)) + 0.5 * morebits
+
+
+def go_atan(x):  # atan.go: Atan
+    if x == 0:
+        return x
+    if x > 0:
+        return go_satan(x)
+    return -go_satan(-x)
+
+
+def go_atan2(y, x):  # atan2.go (finite arguments only)
+    assert y == y and x == x and not math.isinf(x) and not math.isinf(y)
+    if y == 0:
+        if x >= 0 and math.copysign(1.0, x) > 0:
+            return math.copysign(0.0, y)
+        return math.copysign(math.pi, y)
+    if x == 0:
+        return math.copysign(math.pi / 2, y)
+    q = go_atan(y / x)
+    if x < 0:
+        if q <= 0:
+            return q + math.pi
+        return q - math.pi
+    return q
+
+
+def go_asin(x):
+    if x == 0:
+        return x
+    sign = False
+    if x < 0:
+        x, sign = -x, True
+    if x > 1:
+        return float("nan")
+    temp = math.sqrt(1 - x * x)
+    if x > 0.7:
+        temp = math.pi / 2 - go_satan(temp / x)
+    else:
+        temp = go_satan(x / temp)
+    return -temp if sign else temp
+
+
+def go_acos(x):
+    return math.pi / 2 - go_asin(x)
 
 
 # ---------------------------------------------------------------- the scene, shared with the tests (host-mirror objects)
@@ -189,16 +252,21 @@ def disk_plane_hit(d, o, w, tmax):
     dist2 = ph[0] * ph[0] + ph[1] * ph[1]
     if dist2 > d["radius"] * d["radius"] or dist2 < d["inner"] * d["inner"]:
         return None
-    # phi = Atan2(y, x) (+ 2 Pi when negative) never exceeds phiMax = 2 Pi: see the module docstring
-    return t, ph, dist2, rd
+    phi = go_atan2(ph[1], ph[0])   # disk.go:83-89
+    if phi < 0:
+        phi += 2 * math.pi
+    if phi > d["phi_max"]:
+        return None
+    return t, ph, dist2, rd, phi
 
 
 def disk_intersect(d, o, w, tmax):
     r = disk_plane_hit(d, o, w, tmax)
     if r is None:
         return None
-    t, ph, dist2, rd = r
+    t, ph, dist2, rd, phi = r
     r_hit = math.sqrt(dist2)
+    uv = [phi / d["phi_max"], 1 - (r_hit - d["inner"]) / (d["radius"] - d["inner"])]   # disk.go:92-95
     dpdu = [-d["phi_max"] * ph[1], d["phi_max"] * ph[0], 0.0]
     k = (d["radius"] - d["inner"]) / r_hit
     dpdv = [ph[0] * k, ph[1] * k, 0.0 * k]
@@ -215,7 +283,7 @@ def disk_intersect(d, o, w, tmax):
     wo = K.v_normalized(K.transform_vector(d["m"], wo_obj))
     ns = K.face_forward(K.transform_normal(d["minv"], n_obj), n)
     sh_dpdu = K.transform_vector(d["m"], dpdu)
-    return t, dict(p=p, perr=perr, n=n, wo=wo, ns=ns, sh_dpdu=sh_dpdu, disk=d)
+    return t, dict(p=p, perr=perr, n=n, wo=wo, ns=ns, sh_dpdu=sh_dpdu, disk=d, uv=uv)
 
 
 class Scene:
