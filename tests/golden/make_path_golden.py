@@ -429,7 +429,7 @@ class TileSampler:
         self.rng.set_sequence(seed)   # pixel.go:41 (clone)
         self.t1, self.idx, self.d1, self.d2 = None, 0, 0, 0
 
-    def start_pixel(self):
+    def start_pixel(self, px, py):
         self.t1 = K.stratified_start_pixel(self.rng, self.sc["nx"], self.sc["ny"], self.sc["jitter"], self.sc["ndims"])
         self.idx = 0   # sampler.go:21-27
 
@@ -452,6 +452,91 @@ class TileSampler:
         x = self.rng.uniform()
         y = self.rng.uniform()
         return [x, y]
+
+
+# ---------------------------------------------------------------- go-pbrt_b200/go/gopbrt/fast_sampler.go (GOPBRT_MODE_FAST)
+M32, M64 = (1 << 32) - 1, (1 << 64) - 1
+
+
+def kensler_permute(i, l, p):  # fast_sampler.go:103-134, uint32 arithmetic
+    w = l - 1
+    for sh in (1, 2, 4, 8, 16):
+        w |= w >> sh
+    while True:
+        i ^= p
+        i = (i * 0xe170893d) & M32
+        i ^= p >> 16
+        i ^= (i & w) >> 4
+        i ^= p >> 8
+        i = (i * 0x0929eb3f) & M32
+        i ^= p >> 23
+        i ^= (i & w) >> 1
+        i = (i * (1 | p >> 27)) & M32
+        i = (i * 0x6935fa69) & M32
+        i ^= (i & w) >> 11
+        i = (i * 0x74dcb303) & M32
+        i ^= (i & w) >> 2
+        i = (i * 0x9e501cc3) & M32
+        i ^= (i & w) >> 2
+        i = (i * 0xc860a3df) & M32
+        i &= w
+        i ^= i >> 5
+        if i < l:
+            break
+    return ((i + p) & M32) % l
+
+
+def hash_u32(a, b):  # fast_sampler.go:136-145, uint64 arithmetic
+    x = (a * 0x9E3779B97F4A7C15 + b * 0xD1B54A32D192ED03 + 0x632BE59BD9B4E019) & M64
+    x ^= x >> 32
+    x = (x * 0xD6E8FEB86659FD93) & M64
+    x ^= x >> 32
+    x = (x * 0xD6E8FEB86659FD93) & M64
+    x ^= x >> 32
+    return x & M32
+
+
+class FastSampler:
+    """FastStratified: the sampler that DEFINES the library's FAST mode — the reference's renderer, unchanged, with every
+    (pixel, sample) an independent stream.  Restated from the Go source of the sampler (the specification a Go host compiles),
+    not from the CUDA or oracle code."""
+
+    def __init__(self, sc, seed):   # Clone ignores the tile seed (fast_sampler.go:53-58)
+        self.sc = sc
+        self.rng = K.Rng()
+        self.spp = sc["nx"] * sc["ny"]
+        self.pixel, self.idx, self.d1, self.d2 = 0, 0, 0, 0
+
+    def start_pixel(self, px, py):
+        x0, y0, x1, _ = self.sc["crop"]
+        self.pixel = (py - y0) * (x1 - x0) + (px - x0)
+        self.idx = 0
+
+    def start_next_sample(self):
+        self.d1 = self.d2 = 0
+        self.idx += 1
+        if self.idx < self.spp:
+            self.rng.set_sequence((self.pixel * self.spp + self.idx) & M64)
+        return self.idx < self.spp
+
+    def get1d(self):
+        if self.d1 < self.sc["ndims"]:
+            j = kensler_permute(self.idx, self.spp, hash_u32(self.pixel, self.d1))
+            self.d1 += 1
+            delta = self.rng.uniform() if self.sc["jitter"] else 0.5
+            return K.go_min((float(j) + delta) * (1.0 / float(self.spp)), K.ONE_MINUS_EPSILON)
+        return self.rng.uniform()
+
+    def get2d(self):
+        if self.d2 < self.sc["ndims"]:
+            self.d2 += 1
+            return [0.0, 0.0]
+        x = self.rng.uniform()
+        y = self.rng.uniform()
+        return [x, y]
+
+
+SAMPLERS = {"stratified": TileSampler, "fast": FastSampler}
 
 
 # ---------------------------------------------------------------- shape.go:29-48, disk.go:177-185, sampling.go:208-212
@@ -579,14 +664,14 @@ def render(sc, tile_size):
     ntx, nty = (W + tile_size - 1) // tile_size, (H + tile_size - 1) // tile_size
     for ty in range(nty):
         for tx in range(ntx):
-            smp = TileSampler(sc, ty * ntx + tx)
+            smp = SAMPLERS[sc.get("sampler", "stratified")](sc, ty * ntx + tx)
             bx0, by0 = x0 + tx * tile_size, y0 + ty * tile_size
             bx1, by1 = int(K.go_min(float(bx0 + tile_size), float(x1))), int(K.go_min(float(by0 + tile_size), float(y1)))
             tile = {}
             pb = None
             for py in range(by0, by1):
                 for px in range(bx0, bx1):
-                    smp.start_pixel()
+                    smp.start_pixel(px, py)
                     while smp.start_next_sample():
                         off = smp.get2d()
                         p_film = [float(px) + off[0], float(py) + off[1]]   # sampler.go:71-77
