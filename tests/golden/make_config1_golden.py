@@ -227,11 +227,69 @@ def sphere_pdf_wi(light, hit, wi):  # sphere.go:350-365
     return 1.0 / (2.0 * math.pi * (1.0 - cos_max))   # UniformConePdf (sampling.go:169-171)
 
 
+# ---------------------------------------------------------------- triangles (used by make_config2_golden.py only)
+def tri_intersect(tr, o, w, tmax, want_hit=True):
+    """NOT a reference function: the reference has no triangle.  This restates the library's own DEFINITION of the shape
+    (include/gopbrt_cuda.h:66-71): world-space float64 vertices, pbrt-v3's watertight test (translate, permute,
+    shear, edge functions) in float64, `t <= 0 || t >= tMax` rejected as disk.go:75 does, hit point = barycentric combination,
+    pError = Gamma(7) * sum |b_i p_i|, uv (0,0),(1,0),(1,1), n = normalize(cross(p0 - p2, p1 - p2)) flipped by reverseOrientation,
+    shading normal = n, wo = -d un-normalised (no TransformSurfaceInteraction: the vertices are in world space)."""
+    p0, p1, p2 = tr["p"]
+    p0t, p1t, p2t = K.v_sub(p0, o), K.v_sub(p1, o), K.v_sub(p2, o)
+    a = K.v_abs(w)
+    kz = (0 if a[0] > a[2] else 2) if a[0] > a[1] else (1 if a[1] > a[2] else 2)
+    kx = (kz + 1) % 3
+    ky = (kx + 1) % 3
+    d = [w[kx], w[ky], w[kz]]
+    p0t, p1t, p2t = ([q[kx], q[ky], q[kz]] for q in (p0t, p1t, p2t))
+    sx, sy, sz = M.go_div(-d[0], d[2]), M.go_div(-d[1], d[2]), M.go_div(1.0, d[2])
+    for q in (p0t, p1t, p2t):
+        q[0] += sx * q[2]
+        q[1] += sy * q[2]
+    e0 = p1t[0] * p2t[1] - p1t[1] * p2t[0]
+    e1 = p2t[0] * p0t[1] - p2t[1] * p0t[0]
+    e2 = p0t[0] * p1t[1] - p0t[1] * p1t[0]
+    if (e0 < 0 or e1 < 0 or e2 < 0) and (e0 > 0 or e1 > 0 or e2 > 0):
+        return None
+    det = e0 + e1 + e2
+    if det == 0:
+        return None
+    for q in (p0t, p1t, p2t):
+        q[2] *= sz
+    t_scaled = e0 * p0t[2] + e1 * p1t[2] + e2 * p2t[2]
+    if det < 0 and (t_scaled >= 0 or t_scaled < tmax * det):
+        return None
+    if det > 0 and (t_scaled <= 0 or t_scaled > tmax * det):
+        return None
+    inv_det = 1 / det
+    b0, b1, b2 = e0 * inv_det, e1 * inv_det, e2 * inv_det
+    t = t_scaled * inv_det
+    if t <= 0 or t >= tmax:
+        return None
+    if not want_hit:
+        return t, None
+    dp02, dp12 = K.v_sub(p0, p2), K.v_sub(p1, p2)
+    du02, dv02, du12, dv12 = -1.0, -1.0, 0.0, -1.0
+    inv = 1 / (du02 * dv12 - dv02 * du12)
+    dpdu = K.v_muls(K.v_sub(K.v_muls(dp02, dv12), K.v_muls(dp12, dv02)), inv)
+    dpdv = K.v_muls(K.v_add(K.v_muls(dp02, -du12), K.v_muls(dp12, du02)), inv)
+    n = K.v_normalized(K.v_cross(dp02, dp12))
+    assert K.v_len2(K.v_cross(dpdu, dpdv)) != 0, "degenerate triangle: the CoordinateSystem fallback is not restated here"
+    p_abs = K.v_add(K.v_add(K.v_abs(K.v_muls(p0, b0)), K.v_abs(K.v_muls(p1, b1))), K.v_abs(K.v_muls(p2, b2)))
+    ph = K.v_add(K.v_add(K.v_muls(p0, b0), K.v_muls(p1, b1)), K.v_muls(p2, b2))
+    if tr["reverse"]:
+        n = K.v_muls(n, -1.0)
+    return t, dict(p=ph, perr=K.v_muls(p_abs, K.gamma(7.0)), n=n, ns=n, wo=K.v_muls(w, -1.0), sh_dpdu=dpdu,
+                   uv=[b0 * 0 + b1 * 1 + b2 * 1, b0 * 0 + b1 * 0 + b2 * 1])
+
+
 # ---------------------------------------------------------------- primitives: GeometricPrimitive / TransformedPrimitive
 class Prim:
     def __init__(self, kind, shape, mat, xf=None):
         self.kind, self.shape, self.mat, self.xf = kind, shape, mat, xf
-        if kind == "disk":
+        if kind == "tri":
+            b = ([min(q[k] for q in shape["p"]) for k in range(3)], [max(q[k] for q in shape["p"]) for k in range(3)])
+        elif kind == "disk":
             b = transform_bounds(shape["m"], [-shape["radius"], -shape["radius"], shape["height"]], [shape["radius"], shape["radius"], shape["height"]])
         else:
             r = shape["radius"]   # Sphere.ObjectBound (sphere.go:46-51)
@@ -247,7 +305,10 @@ class Prim:
 
     def intersect(self, o, w, tmax):
         lo, lw = self._local_ray(o, w)
-        r = M.disk_intersect(self.shape, lo, lw, tmax) if self.kind == "disk" else sphere_intersect(self.shape, lo, lw, tmax)
+        if self.kind == "tri":
+            r = tri_intersect(self.shape, lo, lw, tmax)
+        else:
+            r = M.disk_intersect(self.shape, lo, lw, tmax) if self.kind == "disk" else sphere_intersect(self.shape, lo, lw, tmax)
         if r is None:
             return None
         t, rec = r
@@ -258,6 +319,8 @@ class Prim:
 
     def intersect_p(self, o, w, tmax):
         lo, lw = self._local_ray(o, w)
+        if self.kind == "tri":
+            return tri_intersect(self.shape, lo, lw, tmax, want_hit=False) is not None
         if self.kind == "disk":
             return M.disk_plane_hit(self.shape, lo, lw, tmax) is not None
         return sphere_roots(self.shape, lo, lw, tmax) is not None
@@ -281,6 +344,8 @@ class Scene:
     """as make_path_golden.Scene, over Prims: a primitive is tested iff its own world bound passes Bounds3.IntersectP with the
     ray's current tMax"""
 
+    ORDER_INDEPENDENT = False   # make_config2_golden.py: the library's closest-hit definition (DESIGN §2) instead of the running tMax
+
     def __init__(self, prims):
         self.prims = prims
         self.closest = self.shadow = 0
@@ -289,6 +354,16 @@ class Scene:
         self.closest += 1
         inv, neg = _inv_dir(w)
         best = None
+        if Scene.ORDER_INDEPENDENT:
+            # every primitive whose own bound and shape test pass with the ray's ORIGINAL tMax; the least t wins, equal t goes to the
+            # lower primitive index
+            best_t = None
+            for pr in self.prims:
+                if M.bounds_intersect_p(pr.bound, o, tmax, inv, neg):
+                    r = pr.intersect(o, w, tmax)
+                    if r is not None and (best_t is None or r[0] < best_t):
+                        best_t, best = r
+            return best
         for pr in self.prims:
             if M.bounds_intersect_p(pr.bound, o, tmax, inv, neg):
                 r = pr.intersect(o, w, tmax)
@@ -343,6 +418,11 @@ def plain_scene(scene, integ):
     prims = []
     for pr in scene.aggregate.primitives:
         xf = None
+        if type(pr).__name__ == "TriangleMesh":   # M GeometricPrimitives in place, in index order
+            for tri in pr.indices:
+                prims.append(Prim("tri", dict(p=[[float(c) for c in pr.vertices[int(i)]] for i in tri], reverse=bool(pr.reverseOrientation)),
+                                  mat_of(pr.material)))
+            continue
         if type(pr).__name__ == "TransformedPrimitive":
             t = pr.primitiveToWorld.startTransform
             xf = xf_of(t) + (t.IsIdentity(),)

@@ -604,6 +604,8 @@ def uniform_sample_one_light(hit, bsdf, sc, scene, smp, stats):
     Ld = estimate_direct(hit, bsdf, sc["lights"][num], u_light, u_scattering, scene, stats)
     # integrator.go:71: spectrum.DivScalar(lightPdf) returns a NEW spectrum that is dropped; :72-74 panics above 10
     stats["max_direct"] = max(stats["max_direct"], max(Ld))
+    if K.go_max(K.go_max(Ld[0], Ld[1]), Ld[2]) > 10:
+        stats["gt10"] += 1   # the reference panics here; the library counts the event (`radiance_gt10`) and goes on
     return Ld
 
 
@@ -660,7 +662,7 @@ def render(sc, tile_size):
     W, H = x1 - x0, y1 - y0
     film = [[[0.0, 0.0, 0.0, 0.0] for _ in range(W)] for _ in range(H)]
     scene = Scene(sc["disks"])
-    stats = dict(max_direct=0.0, camera=0, dead_mis=0, nondelta=0, rr_tests=0, bounce_kinds={})
+    stats = dict(max_direct=0.0, camera=0, dead_mis=0, nondelta=0, rr_tests=0, gt10=0, bounce_kinds={})
     ntx, nty = (W + tile_size - 1) // tile_size, (H + tile_size - 1) // tile_size
     for ty in range(nty):
         for tx in range(ntx):
