@@ -9,8 +9,12 @@
 // pinned against every golden value the reference's own tests hold for this path (tests/test_oracle_golden.py):
 //   pkg/efloat/efloat_test.go:9-13, pkg/pbrt/ray_test.go:10-19, pkg/pbrt/transform_test.go:17-36,66-81,
 //   pkg/pbrt/light_test.go:10-44, pkg/accelerator/simple_test.go:40-108, pkg/accelerator/bvh_test.go:43-141.
-// Path.Li, samplers, RNG, BSDFs, lights, camera, film have NO reference golden ⇒ "parity unpinned" for those
-// (oracle_render.h).  Triangles do not exist in the reference ⇒ "parity unpinned", defined here.
+// (round 2 added pkg/geometry/xyz_test.go, spectrum_test.go, reflection_test.go:9-15, bvh_test.go:143-264.)
+// Path.Li, DirectLighting.Li, samplers, RNG, BSDFs, lights, camera, film have NO reference-held golden; they are pinned by
+// INDEPENDENT plain-Python restatements of the Go source instead: per function (tests/golden/make_shading_kats.py) and
+// composed — whole films of configs 1 and 2, sphere / mixed / partial-shape scenes, both integrators, both samplers and
+// FAST mode (tests/golden/make_*_golden.py) — which this oracle reproduces bit for bit, ray counts included
+// (tests/test_*_golden.py).  Triangles do not exist in the reference ⇒ "parity unpinned", defined here.
 #pragma once
 #include <algorithm>
 #include <atomic>

@@ -1,8 +1,11 @@
 // ORACLE — test infrastructure only.  Nothing under go-pbrt_b200/ may include, link or call this.
 //
 // oracle_render.h: CPU restatement of the reference's sampler / camera / BSDF / light / Path.Li / DirectLighting.Li /
-// film code.  PARITY UNPINNED: the reference holds no golden value for any of this
-//  and cannot be run here; this file follows the cited lines character by character, quirks included.
+// film code.  The reference holds no golden value for any of this and
+// cannot be run here; this file follows the cited lines character by character, quirks included.  PARITY PIN: independent
+// plain-Python restatements of the same Go source — per function (tests/golden/make_shading_kats.py) and as whole films
+// (tests/golden/make_*_golden.py: configs 1 and 2, all shapes / materials / lights / samplers, both integrators, FAST mode) — which
+// this file reproduces bit for bit with identical ray counts (tests/test_shading_kats.py, tests/test_*_golden.py).
 #pragma once
 #include <mutex>
 #include <thread>
