@@ -5,6 +5,8 @@ reverseOrientation spheres next to plain ones, a thin-lens camera (camera.go:199
 in one light list — rendered three ways:
   path_stratified   Path maxDepth 8, Stratified 3x3 jittered, 3 sampled dimensions
   path_random       Path maxDepth 8, RandomSampler(7) (random.go: every draw from the tile's RNG, nothing consumed per pixel)
+  path_power        Path with lightSampleStrategy Power: the reference's power distribution is all zeros (lightdistribution.go:58-68,
+                    spectrum.go:227-229), no light is ever sampled — a black film whose RAY COUNTS pin the sampler draws that remain
   direct_all        DirectLighting(UniformSampleAll) maxDepth 5, Stratified 3x3
 
     python tests/golden/make_mixed_golden.py        # rewrites tests/golden/mixed_golden.json
@@ -33,7 +35,7 @@ C = _load("make_config1_golden")
 C.M = M                                   # ... and in the one C patches
 C.K, C.Z3, C.INF = M.K, M.Z3, M.INF
 W, H, TILE = 18, 12, 5
-CASES = ("path_stratified", "path_random", "direct_all")
+CASES = ("path_stratified", "path_random", "path_power", "direct_all")
 
 
 def scene(gp):
@@ -87,6 +89,8 @@ def scene_and_integrator(gp, case):
         return scene(gp), P.NewPath(8, camera(gp), P.NewStratified(3, 3, True, 3), None, 1.0, P.Uniform)
     if case == "path_random":
         return scene(gp), P.NewPath(8, camera(gp), P.NewRandomSampler(7), None, 1.0, P.Uniform)
+    if case == "path_power":
+        return scene(gp), P.NewPath(8, camera(gp), P.NewStratified(3, 3, True, 3), None, 1.0, P.Power)
     return scene(gp), P.NewDirectLighting(P.UniformSampleAll, 5, camera(gp), P.NewStratified(3, 3, False, 3), None)
 
 
@@ -100,7 +104,10 @@ def plain(gp, case):
         twin = P.NewPath(8, integ.GetCamera(), P.NewStratified(integ.GetSampler().ns, 1, False, 0), None, 1.0, P.Uniform)
     if case == "direct_all":   # plain_scene reads the Path fields; DirectLighting has no roulette threshold
         twin = P.NewPath(integ.maxDepth, integ.GetCamera(), integ.GetSampler(), None, 0.0, P.Uniform)
-    return C.plain_scene(sc_scene, twin)
+    sc = C.plain_scene(sc_scene, twin)
+    if case == "path_power":
+        sc["light_strategy"] = "power"
+    return sc
 
 
 def render(sc, case):
@@ -118,7 +125,7 @@ def main():
     for case in CASES:
         sc = plain(gp, case)
         film, st = render(sc, case)
-        lit = sum(1 for row in film for p in row if p[1] > 0)
+        lit = sum(1 for row in film for p in row if p[1] != 0)
         print(f"{case}: camera {st['camera']}, closest {st['closest']}, shadow {st['shadow']}, area-light estimates {st['nondelta']}, lit pixels "
               f"{lit}/{W * H}, max direct {st['max_direct']:.3f}, bounces {st.get('bounce_kinds')}, transmitted {st.get('spec_transmit_rays')}")
         assert st["max_direct"] <= 10.0

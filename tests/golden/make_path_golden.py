@@ -596,7 +596,13 @@ def uniform_sample_one_light(hit, bsdf, sc, scene, smp, stats):
     n = len(sc["lights"])
     if n == 0:
         return list(Z3)
-    num, pdf = K.sample_discrete([1.0] * n, smp.get1d())   # lightdistribution.go:24-34, sampling.go:42-55
+    if sc.get("light_strategy", "uniform") == "power":
+        # ComputeLightPowerDistribution (lightdistribution.go:58-68) APPENDS the powers to a slice that already holds n zeros, and
+        # every power is Spectrum.Y() == 0 (spectrum.go:227-229): 2n zeros -> funcInt == 0 -> SampleDiscrete's pdf is 0 (sampling.go:50-53)
+        weights = [0.0] * n + [0.0] * n
+    else:
+        weights = [1.0] * n   # lightdistribution.go:24-34
+    num, pdf = K.sample_discrete(weights, smp.get1d())   # sampling.go:42-55
     if pdf == 0.0:
         return list(Z3)
     u_light = smp.get2d()
