@@ -7,7 +7,9 @@ in one light list — rendered three ways:
   path_random       Path maxDepth 8, RandomSampler(7) (random.go: every draw from the tile's RNG, nothing consumed per pixel)
   path_power        Path with lightSampleStrategy Power: the reference's power distribution is all zeros (lightdistribution.go:58-68,
                     spectrum.go:227-229), no light is ever sampled — a black film whose RAY COUNTS pin the sampler draws that remain
+  path_crop         Path, Stratified 2x3 unjittered, a crop window (film.go:42-46), a box filter of radius (1.5, 0.75), tileSize 3
   direct_all        DirectLighting(UniformSampleAll) maxDepth 5, Stratified 3x3
+  direct_one        DirectLighting(UniformSampleOne) maxDepth 5, Stratified 3x3
 
     python tests/golden/make_mixed_golden.py        # rewrites tests/golden/mixed_golden.json
 """
@@ -35,7 +37,8 @@ C = _load("make_config1_golden")
 C.M = M                                   # ... and in the one C patches
 C.K, C.Z3, C.INF = M.K, M.Z3, M.INF
 W, H, TILE = 18, 12, 5
-CASES = ("path_stratified", "path_random", "path_power", "direct_all")
+CASES = ("path_stratified", "path_random", "path_power", "path_crop", "direct_all", "direct_one")
+TILES = {"path_crop": 3}   # every other case: TILE
 
 
 def scene(gp):
@@ -75,9 +78,9 @@ def scene(gp):
     return P.NewScene(P.NewBVH(prims, 3, P.SplitSAH), lights)
 
 
-def camera(gp):
+def camera(gp, crop=(0.0, 0.0, 1.0, 1.0), radius=(1.0, 1.0)):
     P, S = gp.pbrt, gp.scenes
-    film = P.NewFilm("mixed.png", (W, H), (0.0, 0.0, 1.0, 1.0), P.NewBoxFilter((1.0, 1.0)), 100.0, 1.0, 1.0)
+    film = P.NewFilm("mixed.png", (W, H), crop, P.NewBoxFilter(radius), 100.0, 1.0, 1.0)
     c2w = P.LookAt((13.0, 7.0, 13.0), (0.0, 0.0, 0.0), (0.0, 1.0, 0.0))
     return P.NewPerspectiveCamera(P.NewAnimatedTransform(c2w, c2w, 0, 1), S.centred_screen_window(W, H), 0.0, 1.0, 0.35, 18.0, 45.0, film, None)
 
@@ -91,7 +94,10 @@ def scene_and_integrator(gp, case):
         return scene(gp), P.NewPath(8, camera(gp), P.NewRandomSampler(7), None, 1.0, P.Uniform)
     if case == "path_power":
         return scene(gp), P.NewPath(8, camera(gp), P.NewStratified(3, 3, True, 3), None, 1.0, P.Power)
-    return scene(gp), P.NewDirectLighting(P.UniformSampleAll, 5, camera(gp), P.NewStratified(3, 3, False, 3), None)
+    if case == "path_crop":
+        return scene(gp), P.NewPath(8, camera(gp, (0.2, 0.1, 0.9, 0.8), (1.5, 0.75)), P.NewStratified(2, 3, False, 4), None, 1.0, P.Uniform)
+    strategy = P.UniformSampleAll if case == "direct_all" else P.UniformSampleOne
+    return scene(gp), P.NewDirectLighting(strategy, 5, camera(gp), P.NewStratified(3, 3, False, 3), None)
 
 
 def plain(gp, case):
@@ -102,7 +108,7 @@ def plain(gp, case):
     twin = integ
     if case == "path_random":
         twin = P.NewPath(8, integ.GetCamera(), P.NewStratified(integ.GetSampler().ns, 1, False, 0), None, 1.0, P.Uniform)
-    if case == "direct_all":   # plain_scene reads the Path fields; DirectLighting has no roulette threshold
+    if case.startswith("direct_"):   # plain_scene reads the Path fields; DirectLighting has no roulette threshold
         twin = P.NewPath(integ.maxDepth, integ.GetCamera(), integ.GetSampler(), None, 0.0, P.Uniform)
     sc = C.plain_scene(sc_scene, twin)
     if case == "path_power":
@@ -112,10 +118,10 @@ def plain(gp, case):
 
 def render(sc, case):
     with C.patched(sc):
-        if case == "direct_all":
+        if case.startswith("direct_"):
             assert sc["max_depth"] == D.MAX_DEPTH
-            return D.render(sc, TILE, D.UNIFORM_SAMPLE_ALL)
-        return M.render(sc, TILE)
+            return D.render(sc, TILE, D.UNIFORM_SAMPLE_ALL if case == "direct_all" else D.UNIFORM_SAMPLE_ONE)
+        return M.render(sc, TILES.get(case, TILE))
 
 
 def main():

@@ -30,7 +30,13 @@ CASES = sorted(GOLDEN)
 def test_golden_file_covers_what_it_claims():
     assert CASES == sorted(X.CASES) and (RAW["width"], RAW["height"], RAW["tile"]) == (X.W, X.H, X.TILE)
     for name, (film, rays) in GOLDEN.items():
-        assert film.shape == (X.H, X.W, 4) and np.isfinite(film).all()
+        assert np.isfinite(film).all()
+        if name == "path_crop":    # ceil(18 * 0.2) .. ceil(18 * 0.9) by ceil(12 * 0.1) .. ceil(12 * 0.8); 2x3 strata minus the skipped first
+            assert film.shape == (10 - 2, 17 - 4, 4) and rays[0] == 8 * 13 * 5
+            # a box filter of radius (1.5, 0.75) on pixel-corner samples reaches x-2 .. x+1 and y-1 .. y (film.go:218-222)
+            assert film[4, 6, 3] == 4 * 2 * 5
+            continue
+        assert film.shape == (X.H, X.W, 4)
         if name == "path_power":   # no light is ever sampled: black, no visibility test, but the paths still bounce
             assert not film[..., :3].any() and rays[2] == 0 and rays[3] == 0 and rays[1] > rays[0]
         else:
@@ -39,7 +45,8 @@ def test_golden_file_covers_what_it_claims():
         b = RAW["cases"][name]["bounces"]
         assert b["orennayar:0"] > 1000 and b["specrefl:0"] > 50 and b["fresnel:17"] > 50 and b["fresnel:18"] > 50 and b["lambert:0"] > 20
     assert GOLDEN["path_random"][1][0] == X.W * X.H * 6 and GOLDEN["path_stratified"][1][0] == X.W * X.H * 8   # sample 0 is skipped
-    assert RAW["cases"]["direct_all"]["transmitted_rays"] > 50
+    assert RAW["cases"]["direct_all"]["transmitted_rays"] > 50 and RAW["cases"]["direct_one"]["transmitted_rays"] > 50
+    assert GOLDEN["direct_all"][1][3] > 3 * GOLDEN["direct_one"][1][3]
 
 
 @pytest.mark.parametrize("name", CASES)
@@ -55,7 +62,7 @@ def test_oracle_reproduces_the_independent_mixed_films(gp, name, accel):
     gf, rays = GOLDEN[name]
     scene, integ = X.scene_and_integrator(gp, name)
     o = OracleScene(scene, accel)
-    film, st = o.render(integ, X.TILE, mode=gp.abi.MODE_STRICT, threads=2)
+    film, st = o.render(integ, X.TILES.get(name, X.TILE), mode=gp.abi.MODE_STRICT, threads=2)
     o.close()
     assert np.array_equal(film, gf), f"{np.count_nonzero(np.any(film != gf, axis=2))} pixels differ"
     assert [st["camera_rays"], st["closest_rays"], st["shadow_rays"], st["dead_mis_rays"]] == rays
@@ -71,7 +78,7 @@ def test_gpu_reproduces_the_independent_mixed_films(gp, dev, monkeypatch, name, 
         monkeypatch.setenv("GOPBRT_NO_FLAT", "1")   # the BVH kernels instead of the flat table
     scene, integ = X.scene_and_integrator(gp, name)
     g = gp.pbrt.GpuScene(dev, scene)
-    st = gp.pbrt.Render(g, integ, X.TILE, mode=gp.abi.MODE_STRICT)
+    st = gp.pbrt.Render(g, integ, X.TILES.get(name, X.TILE), mode=gp.abi.MODE_STRICT)
     film = integ.GetCamera().GetFilm().pixels
     g.close()
     assert np.array_equal(film, gf), f"{np.count_nonzero(np.any(film != gf, axis=2))} pixels differ"
