@@ -455,7 +455,9 @@ def main():
                                "unit": "Mrays/s", "ms_per_step": sum(x["ms_total"] for x in sm) / K,
                                "wavefront_iterations": sm[0]["iterations"], "lanes": sm[0]["lanes"],
                                "note": "bit-exact against the oracle's STRICT mode (tests/test_gpu_parity.py); FAST is bit-exact against the "
-                                       "oracle's FAST mode and statistically equivalent to STRICT (SURVEY §8d tier 3, same test file)"}
+                                       "oracle's FAST mode and statistically equivalent to STRICT (SURVEY §8d tier 3, same test file); both "
+                                       "modes reproduce, bit for bit, the films of an independent plain-Python restatement of the Go source "
+                                       "on configs 1 and 2 (tests/test_config{1,2}_golden.py, test_fast_golden.py, test_baseline_spp_golden.py)"}
     g.close()
     del film_dev, film_host, film_host_np
 

@@ -59,7 +59,6 @@ def scene_and_integrator(gp):
 def main():
     gp = importlib.import_module("go-pbrt_b200")
     sc = C.plain_scene(*scene_and_integrator(gp))
-    calls = dict(retry=0, retry_hit=0)
     film, st = C.render(sc, TILE)
     lit = sum(1 for row in film for p in row if p[1] > 0)
     print(f"partial shapes at {W}x{H}, tile {TILE}: camera {st['camera']}, closest {st['closest']}, shadow {st['shadow']}, lit pixels {lit}/{W * H}, "

@@ -105,7 +105,7 @@ def go_acos(x):
 
 
 # ---------------------------------------------------------------- the scene, shared with the tests (host-mirror objects)
-def scene_and_integrator(gp, tile_note=None):
+def scene_and_integrator(gp):
     """Four matte disks (floor, ceiling, an annulus at object height 0.25, one tilted by RotateX), a mirror disk (mirror.go: a
     SpecularReflection lobe TYPED Reflection|Diffuse), two glass disks (glass.go: one FresnelSpecular lobe), two point lights and two
     two-sided disk area lights (lights only: the reference never puts a light's shape into the aggregate by itself);
