@@ -21,6 +21,7 @@ X = importlib.util.module_from_spec(_spec)
 _spec.loader.exec_module(X)
 C, M = X.C, X.M
 CASES = ("config1", "mixed")
+PARTITIONS = {"config1_fast_rank1of3": ("config1", "fast", 1, 1, 3), "config1_strict_rank2of3": ("config1", "stratified", 4, 2, 3)}   # case, sampler, tile, rank, world
 TILE = 1   # a FAST film's additions happen in the order of the reference's tile loop at tileSize 1
 
 
@@ -35,6 +36,15 @@ def render(gp, case):
         return M.render(sc, TILE)
 
 
+def render_partition(gp, name):
+    """one rank's share of a frame split the library's way (samples s % world == rank in FAST mode, tiles t % world == rank in STRICT)"""
+    case, sampler, tile, rank, world = PARTITIONS[name]
+    sc = C.plain_scene(*scene_and_integrator(gp, case))
+    sc.update(sampler=sampler, rank=rank, world=world)
+    with C.patched(sc):
+        return M.render(sc, tile)
+
+
 def main():
     gp = importlib.import_module("go-pbrt_b200")
     out = dict(note="made by tests/golden/make_fast_golden.py (plain-Python restatement of the reference renderer + the FastStratified sampler); "
@@ -46,6 +56,11 @@ def main():
         assert st["max_direct"] <= 10.0
         out["cases"][case] = dict(rays=[st["camera"], st["closest"], st["shadow"]], nondelta_estimates=st["nondelta"],
                                   film=[[[v.hex() for v in p] for p in row] for row in film])
+    out["partitions"] = {}
+    for name in PARTITIONS:
+        film, st = render_partition(gp, name)
+        print(f"{name}: camera {st['camera']}, closest {st['closest']}, shadow {st['shadow']}")
+        out["partitions"][name] = dict(rays=[st["camera"], st["closest"], st["shadow"]], film=[[[v.hex() for v in p] for p in row] for row in film])
     with open(os.path.join(HERE, "fast_golden.json"), "w") as f:
         json.dump(out, f, indent=0)
     print("wrote fast_golden.json")

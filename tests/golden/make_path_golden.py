@@ -670,8 +670,13 @@ def render(sc, tile_size):
     scene = Scene(sc["disks"])
     stats = dict(max_direct=0.0, camera=0, dead_mis=0, nondelta=0, rr_tests=0, gt10=0, bounce_kinds={})
     ntx, nty = (W + tile_size - 1) // tile_size, (H + tile_size - 1) // tile_size
+    # multi-GPU partition of the library (not of the reference): rank r of `world` renders samples s % world == r (FAST) or tiles
+    # t % world == r (STRICT) into a full-resolution film of its own; the films are then summed
+    fast, rank, world = sc.get("sampler") == "fast", sc.get("rank", 0), sc.get("world", 1)
     for ty in range(nty):
         for tx in range(ntx):
+            if not fast and world > 1 and (ty * ntx + tx) % world != rank:
+                continue   # the library's STRICT partition: whole tiles, so that a pixel's sample sequence stays the reference's
             smp = SAMPLERS[sc.get("sampler", "stratified")](sc, ty * ntx + tx)
             bx0, by0 = x0 + tx * tile_size, y0 + ty * tile_size
             bx1, by1 = int(K.go_min(float(bx0 + tile_size), float(x1))), int(K.go_min(float(by0 + tile_size), float(y1)))
@@ -681,6 +686,8 @@ def render(sc, tile_size):
                 for px in range(bx0, bx1):
                     smp.start_pixel(px, py)
                     while smp.start_next_sample():
+                        if fast and world > 1 and smp.idx % world != rank:
+                            continue   # the library's FAST partition: a stream per (pixel, sample), nothing to skip over
                         off = smp.get2d()
                         p_film = [float(px) + off[0], float(py) + off[1]]   # sampler.go:71-77
                         p_lens = smp.get2d()

@@ -60,6 +60,25 @@ def test_oracle_fast_mode_reproduces_the_specified_films(gp, name, accel):
     assert [st["camera_rays"], st["closest_rays"], st["shadow_rays"], st["dead_mis_rays"]] == rays
 
 
+@pytest.mark.parametrize("name", sorted(F.PARTITIONS))
+def test_oracle_reproduces_one_rank_of_a_split_frame(gp, name):
+    # the multi-GPU partition is the library's, not the reference's: samples s % world == rank in FAST mode, tiles
+    # t % world == rank in STRICT mode, each rank into a full-resolution film of its own
+    case, sampler, tile, rank, world = F.PARTITIONS[name]
+    c = RAW["partitions"][name]
+    gf = np.array([[[float.fromhex(v) for v in p] for p in row] for row in c["film"]])
+    pf, pst = F.render_partition(gp, name)
+    assert np.array_equal(np.array(pf), gf) and [pst["camera"], pst["closest"], pst["shadow"]] == c["rays"]
+    scene, integ = F.scene_and_integrator(gp, case)
+    o = OracleScene(scene, 1)
+    mode = gp.abi.MODE_FAST if sampler == "fast" else gp.abi.MODE_STRICT
+    film, st = o.render(integ, tile, mode=mode, rank=rank, world=world, threads=2)
+    o.close()
+    assert np.array_equal(film, gf), f"{np.count_nonzero(np.any(film != gf, axis=2))} pixels differ"
+    assert [st["camera_rays"], st["closest_rays"], st["shadow_rays"]] == c["rays"]
+    assert 0 < c["rays"][0] < GOLDEN["config1"][1][0]
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("groups", [1, 0])
 @pytest.mark.parametrize("name", CASES)
