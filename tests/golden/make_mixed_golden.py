@@ -41,7 +41,7 @@ CASES = ("path_stratified", "path_random", "path_power", "path_crop", "direct_al
 TILES = {"path_crop": 3}   # every other case: TILE
 
 
-def scene(gp):
+def scene(gp, point_light_scale=1.0):
     P, S = gp.pbrt, gp.scenes
     rng = S.RNG(0xA11CE)
     U = rng.UniformFloat
@@ -73,7 +73,7 @@ def scene(gp):
     sxf, dxf = P.Translate((9.0, 9.0, -4.0)), P.Translate((-3.0, 1.0, 9.5))
     lights = [P.NewDistant(P.Translate((0.0, 0.0, 0.0)), P.NewSpectrum(0.3), (-1.0, 1.0, 1.0)),
               P.NewDiffuseAreaLight(sxf, None, P.NewSpectrum(7.0), 1, P.NewSphereShape("l", sxf, False, 1.5), False),
-              P.NewPoint(P.Translate((4.0, 8.0, 6.0)), None, P.NewRGBSpectrum(40.0, 35.0, 30.0)),
+              P.NewPoint(P.Translate((4.0, 8.0, 6.0)), None, P.NewRGBSpectrum(40.0 * point_light_scale, 35.0 * point_light_scale, 30.0 * point_light_scale)),
               P.NewDiffuseAreaLight(dxf, None, P.NewRGBSpectrum(5.0, 6.0, 7.0), 1, P.NewDisk(dxf, 0.0, 2.0, 0.0, 360), True)]
     return P.NewScene(P.NewBVH(prims, 3, P.SplitSAH), lights)
 
@@ -98,6 +98,20 @@ def scene_and_integrator(gp, case):
         return scene(gp), P.NewPath(8, camera(gp, (0.2, 0.1, 0.9, 0.8), (1.5, 0.75)), P.NewStratified(2, 3, False, 4), None, 1.0, P.Uniform)
     strategy = P.UniformSampleAll if case == "direct_all" else P.UniformSampleOne
     return scene(gp), P.NewDirectLighting(strategy, 5, camera(gp), P.NewStratified(3, 3, False, 3), None)
+
+
+def bright_scene_and_integrator(gp):
+    """path_stratified with the point light 150 times brighter: UniformSampleOneLight's result exceeds 10 at many vertices, where the
+    reference panics (integrator.go:72-74).  The library counts the event (`radiance_gt10`) and carries on with the value; this case
+    (CPU tests only) pins that the oracle does exactly that and nothing else."""
+    P = gp.pbrt
+    return scene(gp, 150.0), P.NewPath(8, camera(gp), P.NewStratified(3, 3, True, 3), None, 1.0, P.Uniform)
+
+
+def render_bright(gp):
+    sc = C.plain_scene(*bright_scene_and_integrator(gp))
+    with C.patched(sc):
+        return M.render(sc, TILE)
 
 
 def plain(gp, case):
@@ -134,11 +148,16 @@ def main():
         lit = sum(1 for row in film for p in row if p[1] != 0)
         print(f"{case}: camera {st['camera']}, closest {st['closest']}, shadow {st['shadow']}, area-light estimates {st['nondelta']}, lit pixels "
               f"{lit}/{W * H}, max direct {st['max_direct']:.3f}, bounces {st.get('bounce_kinds')}, transmitted {st.get('spec_transmit_rays')}")
-        assert st["max_direct"] <= 10.0
+        assert st["max_direct"] <= 10.0 and st["gt10"] == 0
         out["cases"][case] = dict(rays=[st["camera"], st["closest"], st["shadow"]], nondelta_estimates=st["nondelta"],
                                   bounces={f"{k[0]}:{k[1]}": v for k, v in sorted(st.get("bounce_kinds", {}).items())},
                                   transmitted_rays=st.get("spec_transmit_rays", 0),
                                   film=[[[v.hex() for v in p] for p in row] for row in film])
+    film, st = render_bright(gp)
+    print(f"bright: camera {st['camera']}, closest {st['closest']}, shadow {st['shadow']}, > 10 events {st['gt10']}, max direct {st['max_direct']:.1f}")
+    assert st["gt10"] > 20
+    out["bright"] = dict(rays=[st["camera"], st["closest"], st["shadow"]], nondelta_estimates=st["nondelta"], radiance_gt10=st["gt10"],
+                         film=[[[v.hex() for v in p] for p in row] for row in film])
     with open(os.path.join(HERE, "mixed_golden.json"), "w") as f:
         json.dump(out, f, indent=0)
     print("wrote mixed_golden.json")

@@ -69,6 +69,19 @@ def test_oracle_reproduces_the_independent_mixed_films(gp, name, accel):
     assert st["radiance_gt10"] == 0 and st["nan_samples"] == 0 and st["unsupported_material"] == 0
 
 
+def test_oracle_counts_the_reference_panic_and_carries_on(gp):
+    # UniformSampleOneLight > 10: the reference panics (integrator.go:72-74); the library counts and goes on with the value
+    c = RAW["bright"]
+    gf = np.array([[[float.fromhex(v) for v in p] for p in row] for row in c["film"]])
+    scene, integ = X.bright_scene_and_integrator(gp)
+    o = OracleScene(scene, 1)
+    film, st = o.render(integ, X.TILE, mode=gp.abi.MODE_STRICT, threads=2)
+    o.close()
+    assert np.array_equal(film, gf), f"{np.count_nonzero(np.any(film != gf, axis=2))} pixels differ"
+    assert [st["camera_rays"], st["closest_rays"], st["shadow_rays"], st["dead_mis_rays"]] == c["rays"] + [c["nondelta_estimates"]]
+    assert st["radiance_gt10"] == c["radiance_gt10"] > 20
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("no_flat", [False, True])
 @pytest.mark.parametrize("name", CASES)
