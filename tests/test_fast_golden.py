@@ -79,6 +79,23 @@ def test_oracle_reproduces_one_rank_of_a_split_frame(gp, name):
     assert 0 < c["rays"][0] < GOLDEN["config1"][1][0]
 
 
+def test_the_ranks_shares_add_up_to_the_frame(gp):
+    # FAST mode's point: a pixel's samples are independent streams, so the shares of ranks 0..world-1 are disjoint and complete — their
+    # films sum to the single-rank film (to rounding: the additions associate differently), weights and ray counts exactly
+    total, rays = None, [0, 0, 0]
+    for rank in range(3):
+        F.PARTITIONS["_tmp"] = ("config1", "fast", 1, rank, 3)
+        try:
+            film, st = F.render_partition(gp, "_tmp")
+        finally:
+            del F.PARTITIONS["_tmp"]
+        film = np.array(film)
+        total = film if total is None else total + film
+        rays = [rays[0] + st["camera"], rays[1] + st["closest"], rays[2] + st["shadow"]]
+    gf, want = GOLDEN["config1"]
+    assert np.array_equal(total[..., 3], gf[..., 3]) and np.allclose(total, gf, rtol=1e-12, atol=0.0) and rays == want[:3]
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("groups", [1, 0])
 @pytest.mark.parametrize("name", CASES)
